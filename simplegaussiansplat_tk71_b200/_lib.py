@@ -1,0 +1,71 @@
+"""ctypes binding of the C ABI declared in include/gcp_abi.h.
+
+The library is the product: if it is missing or does not load, importing the ops
+fails loudly.  There is no CPU fallback and no alternative backend.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+_lib = None
+
+GCP_OK = 0
+ERRORS = {
+    -1: "GCP_ERR_INVALID_ARG",
+    -2: "GCP_ERR_WORKSPACE",
+    -3: "GCP_ERR_WATCHDOG",
+    -4: "GCP_ERR_SEGMENTS",
+}
+
+# every symbol include/gcp_abi.h declares (tests check the .so exports all of them)
+SYMBOLS = (
+    "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status",
+    "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
+    "gcp_set_variant", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
+)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        try:
+            _build.build_lib()
+        except Exception as e:  # noqa: BLE001
+            raise ImportError(
+                f"libgcp_b200.so is not built ({e}); run `python -c 'import __graft_entry__ as g; g.build()'`"
+            ) from e
+    L = ctypes.CDLL(path)
+    vp, i64, sz, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_int
+    L.gcp_abi_version.restype = ci
+    L.gcp_workspace_bytes.argtypes = [i64]
+    L.gcp_workspace_bytes.restype = sz
+    L.gcp_workspace_init.argtypes = [vp, sz, vp]
+    L.gcp_workspace_status.argtypes = [vp, vp, ctypes.POINTER(ci)]
+    L.gcp_cumprod_fwd_f32.argtypes = [vp, vp, vp, i64, vp, sz, vp]
+    L.gcp_cumsum_fwd_f32.argtypes = [vp, vp, vp, i64, vp, sz, vp]
+    L.gcp_cumprod_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp, sz, vp]
+    L.gcp_validate_segments.argtypes = [vp, vp, i64, i64, vp, sz, vp, ctypes.POINTER(i64)]
+    L.gcp_set_variant.argtypes = [ci, ci]
+    L.gcp_num_variants.argtypes = [ci]
+    L.gcp_variant_name.argtypes = [ci, ci]
+    L.gcp_variant_name.restype = ctypes.c_char_p
+    L.gcp_last_launch_count.restype = ci
+    for name in ("gcp_workspace_init", "gcp_workspace_status", "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32",
+                 "gcp_cumprod_bwd_f32", "gcp_validate_segments", "gcp_set_variant", "gcp_num_variants"):
+        getattr(L, name).restype = ci
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc == GCP_OK:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: {ERRORS.get(rc, rc)}")
+    raise RuntimeError(f"{what}: CUDA error {rc}")

@@ -1,0 +1,290 @@
+// gcp_abi.cu — C-ABI entry points of libgcp_b200.so (see include/gcp_abi.h) and the
+// host-side launch logic: variant table, grid sizing (persistent = resident CTAs x
+// 148 SMs), alignment dispatch, workspace checks.  No allocation, no host sync on the
+// compute entry points.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "gcp_abi.h"
+#include "gcp_bwd.cuh"
+#include "gcp_fwd.cuh"
+
+namespace {
+
+using namespace gcp;
+
+thread_local int t_launches = 0;
+int g_variant[2] = {-1, -1};
+
+struct DeviceInfo {
+    bool init = false;
+    int sms = 0;
+};
+DeviceInfo g_dev[64];
+
+int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+int sm_count() {
+    const int d = current_device();
+    DeviceInfo &di = g_dev[d & 63];
+    if (!di.init) {
+        cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, d);
+        di.init = true;
+    }
+    return di.sms;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct Ws {
+    uint32_t *hdr;
+    uint64_t *desc;
+};
+int check_ws(void *ws, size_t ws_bytes, int64_t n, Ws *out) {
+    if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15u) != 0) return GCP_ERR_WORKSPACE;
+    if (ws_bytes < gcp_workspace_bytes(n)) return GCP_ERR_WORKSPACE;
+    out->hdr = reinterpret_cast<uint32_t *>(ws);
+    out->desc = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(ws) + WS_HEADER_BYTES);
+    return GCP_OK;
+}
+
+// resident CTAs per SM for a persistent kernel, cached per (kernel, device)
+template <typename K>
+int persistent_ctas_per_sm(K kernel, int threads, size_t smem) {
+    static int cache[64];
+    static bool have[64];
+    const int d = current_device() & 63;
+    if (!have[d]) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+        cache[d] = nb > 0 ? nb : 1;
+        have[d] = true;
+    }
+    return cache[d];
+}
+
+inline uint32_t tiles_for(int64_t n, int tile) { return static_cast<uint32_t>((n + tile - 1) / tile); }
+
+// ------------------------------ forward ------------------------------------
+template <int OP, int WARPS, int ROWS>
+int launch_fwd_ldg(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
+    constexpr int TILE = WARPS * ROWS * 128;
+    const uint32_t nt = tiles_for(n, TILE);
+    const int in_vec = aligned16(x) && aligned16(key);
+    const int y_vec = aligned16(y);
+    k_fwd_ldg<OP, WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, in_vec, y_vec);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <int OP, int WARPS, int ROWS, int STAGES>
+int launch_fwd_tma(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
+    using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
+    const uint32_t nt = tiles_for(n, L::TILE);
+    auto kern = k_fwd_tma<OP, WARPS, ROWS, STAGES>;
+    const int threads = (WARPS + 1) * 32;
+    const int per_sm = persistent_ctas_per_sm(kern, threads, L::BYTES);
+    uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
+    if (grid > nt) grid = nt;
+    kern<<<grid, threads, L::BYTES, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, aligned16(y) ? 1 : 0);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
+constexpr int FWD_NUM_VARIANTS = 8;
+const char *const kFwdNames[FWD_NUM_VARIANTS] = {
+    "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
+    "tma_w8_r4_s3 (tile 4096, 96 KB ring)", "tma_w8_r4_s2 (tile 4096, 64 KB ring)",
+    "tma_w8_r2_s4 (tile 2048, 64 KB ring)", "tma_w4_r4_s4 (tile 2048, 160 thr)",
+    "tma_w16_r4_s3 (tile 8192, 192 KB ring)"};
+constexpr int FWD_DEFAULT = 0;
+
+template <int OP>
+int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *wsp, size_t ws_bytes,
+                 gcp_stream_t stream) {
+    t_launches = 0;
+    if (n < 0 || (n > 0 && (x == nullptr || key == nullptr || y == nullptr))) return GCP_ERR_INVALID_ARG;
+    if (n == 0) return GCP_OK;
+    Ws ws;
+    int rc = check_ws(wsp, ws_bytes, n, &ws);
+    if (rc != GCP_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int v = g_variant[0] < 0 ? FWD_DEFAULT : g_variant[0];
+    const bool in_al = aligned16(x) && aligned16(key);
+    if (v >= 3 && !in_al) v = 0;  // bulk copies need 16-byte aligned sources
+    switch (v) {
+        case 0: return launch_fwd_ldg<OP, 8, 4>(x, key, y, n, ws, s);
+        case 1: return launch_fwd_ldg<OP, 8, 2>(x, key, y, n, ws, s);
+        case 2: return launch_fwd_ldg<OP, 4, 4>(x, key, y, n, ws, s);
+        case 3: return launch_fwd_tma<OP, 8, 4, 3>(x, key, y, n, ws, s);
+        case 4: return launch_fwd_tma<OP, 8, 4, 2>(x, key, y, n, ws, s);
+        case 5: return launch_fwd_tma<OP, 8, 2, 4>(x, key, y, n, ws, s);
+        case 6: return launch_fwd_tma<OP, 4, 4, 4>(x, key, y, n, ws, s);
+        case 7: return launch_fwd_tma<OP, 16, 4, 3>(x, key, y, n, ws, s);
+        default: return GCP_ERR_INVALID_ARG;
+    }
+}
+
+// ------------------------------ backward -----------------------------------
+template <int WARPS, int ROWS>
+int launch_bwd_ldg(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
+                   Ws ws, cudaStream_t s) {
+    constexpr int TILE = WARPS * ROWS * 128;
+    const uint32_t nt = tiles_for(n, TILE);
+    const int in_vec = aligned16(x) && aligned16(g) && aligned16(inv);
+    k_bwd_ldg<WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, in_vec,
+                                                      aligned16(gin) ? 1 : 0);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <int WARPS, int ROWS, int STAGES>
+int launch_bwd_tma(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
+                   Ws ws, cudaStream_t s) {
+    using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
+    const uint32_t nt = tiles_for(n, L::TILE);
+    auto kern = k_bwd_tma<WARPS, ROWS, STAGES>;
+    const int threads = (WARPS + 1) * 32;
+    const int per_sm = persistent_ctas_per_sm(kern, threads, L::BYTES);
+    uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
+    if (grid > nt) grid = nt;
+    kern<<<grid, threads, L::BYTES, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, aligned16(gin) ? 1 : 0);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
+constexpr int BWD_NUM_VARIANTS = 8;
+const char *const kBwdNames[BWD_NUM_VARIANTS] = {
+    "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
+    "tma_w8_r4_s2 (tile 4096, 96 KB ring)", "tma_w8_r2_s4 (tile 2048, 96 KB ring)",
+    "tma_w8_r2_s3 (tile 2048, 72 KB ring)", "tma_w8_r4_s4 (tile 4096, 192 KB ring)",
+    "tma_w4_r4_s4 (tile 2048, 160 thr)"};
+constexpr int BWD_DEFAULT = 0;
+
+}  // namespace
+
+extern "C" {
+
+int gcp_abi_version(void) { return GCP_ABI_VERSION; }
+
+size_t gcp_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    const int64_t slots = (n + gcp::MIN_TILE - 1) / gcp::MIN_TILE + 1;
+    return static_cast<size_t>(gcp::WS_HEADER_BYTES) + static_cast<size_t>(slots) * gcp::WS_SLOT_BYTES;
+}
+
+int gcp_workspace_init(void *ws, size_t ws_bytes, gcp_stream_t stream) {
+    if (ws == nullptr || ws_bytes < static_cast<size_t>(gcp::WS_HEADER_BYTES)) return GCP_ERR_WORKSPACE;
+    return static_cast<int>(cudaMemsetAsync(ws, 0, ws_bytes, reinterpret_cast<cudaStream_t>(stream)));
+}
+
+int gcp_workspace_status(const void *ws, gcp_stream_t stream, int *status) {
+    if (ws == nullptr || status == nullptr) return GCP_ERR_INVALID_ARG;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    uint32_t flag = 0;
+    e = cudaMemcpy(&flag, reinterpret_cast<const uint32_t *>(ws) + gcp::HDR_ABORT, sizeof(flag),
+                   cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    *status = flag ? GCP_ERR_WATCHDOG : GCP_OK;
+    return GCP_OK;
+}
+
+int gcp_cumprod_fwd_f32(const float *x, const int32_t *key, float *y, int64_t n, void *ws, size_t ws_bytes,
+                        gcp_stream_t stream) {
+    return dispatch_fwd<gcp::OP_MUL>(x, key, y, n, ws, ws_bytes, stream);
+}
+
+int gcp_cumsum_fwd_f32(const float *x, const int32_t *key, float *y, int64_t n, void *ws, size_t ws_bytes,
+                       gcp_stream_t stream) {
+    return dispatch_fwd<gcp::OP_ADD>(x, key, y, n, ws, ws_bytes, stream);
+}
+
+int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const int32_t *inv,
+                        const int32_t *seg_end, float *gin, int64_t n, int64_t k, void *wsp, size_t ws_bytes,
+                        gcp_stream_t stream) {
+    t_launches = 0;
+    (void)seg_end;  // implied by inv (tail <=> inv[i+1] != inv[i]); see gcp_validate_segments
+    if (n < 0 || k < 0) return GCP_ERR_INVALID_ARG;
+    if (n > 0 && (x == nullptr || y == nullptr || gout == nullptr || inv == nullptr || gin == nullptr))
+        return GCP_ERR_INVALID_ARG;
+    if (n == 0) return GCP_OK;
+    Ws ws;
+    int rc = check_ws(wsp, ws_bytes, n, &ws);
+    if (rc != GCP_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int v = g_variant[1] < 0 ? BWD_DEFAULT : g_variant[1];
+    const bool in_al = aligned16(x) && aligned16(gout) && aligned16(inv);
+    if (v >= 3 && !in_al) v = 0;
+    switch (v) {
+        case 0: return launch_bwd_ldg<8, 4>(x, y, gout, inv, gin, n, ws, s);
+        case 1: return launch_bwd_ldg<8, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 2: return launch_bwd_ldg<4, 4>(x, y, gout, inv, gin, n, ws, s);
+        case 3: return launch_bwd_tma<8, 4, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 4: return launch_bwd_tma<8, 2, 4>(x, y, gout, inv, gin, n, ws, s);
+        case 5: return launch_bwd_tma<8, 2, 3>(x, y, gout, inv, gin, n, ws, s);
+        case 6: return launch_bwd_tma<8, 4, 4>(x, y, gout, inv, gin, n, ws, s);
+        case 7: return launch_bwd_tma<4, 4, 4>(x, y, gout, inv, gin, n, ws, s);
+        default: return GCP_ERR_INVALID_ARG;
+    }
+}
+
+int gcp_validate_segments(const int32_t *inv, const int32_t *seg_end, int64_t n, int64_t k, void *wsp,
+                          size_t ws_bytes, gcp_stream_t stream, int64_t *violations) {
+    t_launches = 0;
+    if (violations == nullptr || n < 0 || k < 0) return GCP_ERR_INVALID_ARG;
+    if (n > 0 && (inv == nullptr || (k > 0 && seg_end == nullptr))) return GCP_ERR_INVALID_ARG;
+    Ws ws;
+    int rc = check_ws(wsp, ws_bytes, 0, &ws);
+    if (rc != GCP_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned long long *ctr = reinterpret_cast<unsigned long long *>(ws.hdr) + gcp::HDR_VIOL64;
+    cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (n == 0 && k == 0) {
+        *violations = 0;
+        return GCP_OK;
+    }
+    const int threads = 256;
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    gcp::k_validate_segments<<<static_cast<unsigned>(blocks), threads, 0, s>>>(inv, seg_end, n, k, ctr);
+    ++t_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    unsigned long long host = 0;
+    e = cudaMemcpyAsync(&host, ctr, sizeof(host), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    *violations = static_cast<int64_t>(host);
+    return GCP_OK;
+}
+
+int gcp_set_variant(int op, int variant) {
+    if (op < 0 || op > 1) return GCP_ERR_INVALID_ARG;
+    const int nv = op == 0 ? FWD_NUM_VARIANTS : BWD_NUM_VARIANTS;
+    if (variant < -1 || variant >= nv) return GCP_ERR_INVALID_ARG;
+    g_variant[op] = variant;
+    return GCP_OK;
+}
+
+int gcp_num_variants(int op) { return op == 0 ? FWD_NUM_VARIANTS : (op == 1 ? BWD_NUM_VARIANTS : 0); }
+
+const char *gcp_variant_name(int op, int variant) {
+    if (op == 0 && variant >= 0 && variant < FWD_NUM_VARIANTS) return kFwdNames[variant];
+    if (op == 1 && variant >= 0 && variant < BWD_NUM_VARIANTS) return kBwdNames[variant];
+    return "";
+}
+
+int gcp_last_launch_count(void) { return t_launches; }
+
+}  // extern "C"

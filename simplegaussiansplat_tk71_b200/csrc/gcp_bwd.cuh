@@ -1,0 +1,508 @@
+// gcp_bwd.cuh — backward of the segmented cumprod, one pass, division-free.
+//
+// Replaces grouped_cumprod_backward_kernel
+//   (/root/reference/cuda_kernel/grouped_cumprod_backward.cu:9-41, launcher :43-65),
+// whose per-thread serial loop costs O(sum L^2) and divides by x.
+//
+//   grad_in[i] = E_i * S_i
+//   E_i = prod_{j<i, same segment} x_j          forward exclusive product (1 at a head)
+//   S_i = g_i + x_{i+1} * S_{i+1}               reverse recurrence (S = g at a tail)
+//
+// S is a reverse segmented scan of affine maps (a_i, b_i) = (tail ? 0 : x_{i+1}, g_i);
+// a tail's a = 0 is the segment reset.  Tiles are processed from the END of the
+// array (tile = num_tiles-1-ticket) so the cross-tile dependency of S always points
+// at an earlier ticket: the same decoupled look-back as the forward, mirrored.
+// E needs the opposite direction; inside a tile it is recomputed from x (no extra
+// traffic), and across the tile's left edge it is the forward output itself:
+// E(first element) = y[base-1] — ONE value of `param_cumprod` per tile, which the
+// reference op already receives as an argument.  So the pass reads x, grad_out, inv
+// (12 B/elem) and writes grad_in (4 B/elem): 16 B/elem, the algorithmic minimum.
+//
+// Same striped-float4 layout and the same two kernel shapes as gcp_fwd.cuh.
+#pragma once
+#include "gcp_device.cuh"
+#include "gcp_fwd.cuh"
+
+namespace gcp {
+
+template <int WARPS>
+struct BwdShared {
+    float wv[WARPS];  // forward product aggregates
+    uint32_t wf[WARPS];
+    float wa[WARPS];  // reverse affine aggregates
+    float wb[WARPS];
+    float r_next;     // S at the first element of the next tile (if the segment continues)
+    uint32_t tile;
+};
+
+// Reverse inclusive scan of affine maps across the warp and up its rows.
+//   agg[r]: composite of this lane's 4 elements of row r (element 0 outermost)
+//   sx[r] : out, composite of everything AFTER this lane inside the warp
+//   wagg  : out, composite of the whole warp span
+template <int ROWS>
+__device__ __forceinline__ void warp_affine_rscan_rows(const Affine (&agg)[ROWS], int lane, Affine (&sx)[ROWS],
+                                                       Affine &wagg) {
+    Affine rs = affine_id();
+#pragma unroll
+    for (int r = ROWS - 1; r >= 0; --r) {
+        Affine inc = agg[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Affine t;
+            t.a = __shfl_down_sync(0xffffffffu, inc.a, d);
+            t.b = __shfl_down_sync(0xffffffffu, inc.b, d);
+            if (lane + d < 32) inc = compose(inc, t);
+        }
+        Affine exc;
+        exc.a = __shfl_down_sync(0xffffffffu, inc.a, 1);
+        exc.b = __shfl_down_sync(0xffffffffu, inc.b, 1);
+        if (lane == 31) exc = affine_id();
+        Affine row;
+        row.a = __shfl_sync(0xffffffffu, inc.a, 0);
+        row.b = __shfl_sync(0xffffffffu, inc.b, 0);
+        sx[r] = compose(exc, rs);
+        rs = compose(row, rs);
+    }
+    wagg = rs;
+}
+
+// Look-ahead over successor tiles (higher tile index = earlier ticket).
+// Slot words: [0] INCLUSIVE R (S at the tile's first element), [1] aggregate a, [2] aggregate b.
+__device__ __forceinline__ float bwd_lookahead(const uint64_t *desc, uint32_t tile, uint32_t num_tiles,
+                                               uint32_t epoch, uint32_t *hdr, int lane) {
+    Affine carry = affine_id();
+    int64_t nb = static_cast<int64_t>(tile) + 1;
+    while (true) {
+        const int64_t idx = nb + lane;
+        Affine m = Affine{0.0f, 0.0f};  // beyond the last tile: nothing follows
+        bool term = true;
+        if (idx < static_cast<int64_t>(num_tiles)) {
+            const uint64_t *slot = desc + idx * 4;
+            uint32_t spins = 0;
+            while (true) {
+                const uint64_t d0 = ld_relaxed_u64(slot);
+                if (desc_valid(d0, epoch)) {
+                    m = Affine{0.0f, desc_value(d0)};
+                    term = true;
+                    break;
+                }
+                const uint64_t d1 = ld_relaxed_u64(slot + 1);
+                const uint64_t d2 = ld_relaxed_u64(slot + 2);
+                if (desc_valid(d1, epoch) && desc_valid(d2, epoch)) {
+                    m = Affine{desc_value(d1), desc_value(d2)};
+                    term = (m.a == 0.0f);
+                    break;
+                }
+                ++spins;
+                if ((spins & 255u) == 0u) {
+                    if (spins >= POLL_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+                    if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
+                }
+                if (spins > 8) __nanosleep(40);
+            }
+        }
+        const uint32_t tm = __ballot_sync(0xffffffffu, term);
+        const int last = tm ? (__ffs(tm) - 1) : 31;
+        Affine w = (lane <= last) ? m : affine_id();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Affine t;
+            t.a = __shfl_down_sync(0xffffffffu, w.a, d);
+            t.b = __shfl_down_sync(0xffffffffu, w.b, d);
+            if (lane + d < 32) w = compose(w, t);
+        }
+        w.a = __shfl_sync(0xffffffffu, w.a, 0);
+        w.b = __shfl_sync(0xffffffffu, w.b, 0);
+        carry = compose(carry, w);
+        if (tm) break;
+        nb += 32;
+    }
+    return carry.b;
+}
+
+// Everything after x / g / inv of the tile are in registers.
+//   iprev : inv of the element before this warp's span (lane 0), -1 if none
+//   inext : inv of the element after this warp's span (lane 31), -1 if none
+//   xnext : x of the element after this warp's span (lane 31)
+//   y_prev: y[base-1] (forward inclusive product just before the tile), any value if base == 0
+template <int WARPS, int ROWS>
+__device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const float (&g)[ROWS][4],
+                                              const int32_t (&iv)[ROWS][4], int32_t iprev, int32_t inext,
+                                              float xnext, float y_prev, uint32_t tile, uint32_t num_tiles,
+                                              int64_t base, int64_t n, float *__restrict__ gin, bool out_vec,
+                                              uint32_t epoch, uint32_t *hdr, uint64_t *desc, BwdShared<WARPS> *sh,
+                                              int warp, int lane) {
+    constexpr int TILE = WARPS * ROWS * 128;
+    // ---- head / tail bits and the x of the next element ----
+    uint32_t hm = 0u, tm = 0u;
+    float xn[ROWS];
+    int32_t carry_prev = iprev;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        int32_t p = __shfl_up_sync(0xffffffffu, iv[r][3], 1);
+        if (lane == 0) p = carry_prev;
+        carry_prev = __shfl_sync(0xffffffffu, iv[r][3], 31);
+        int32_t q = __shfl_down_sync(0xffffffffu, iv[r][0], 1);
+        float xq = __shfl_down_sync(0xffffffffu, x[r][0], 1);
+        // lane 31 takes row r+1 lane 0 (or the warp halo on the last row)
+        const int32_t q_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, iv[(r + 1 < ROWS) ? r + 1 : r][0], 0) : inext;
+        const float x_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, x[(r + 1 < ROWS) ? r + 1 : r][0], 0) : xnext;
+        if (lane == 31) {
+            q = q_next_row;
+            xq = x_next_row;
+        }
+        xn[r] = xq;
+        const uint32_t h = (iv[r][0] != p ? 1u : 0u) | (iv[r][1] != iv[r][0] ? 2u : 0u) |
+                           (iv[r][2] != iv[r][1] ? 4u : 0u) | (iv[r][3] != iv[r][2] ? 8u : 0u);
+        const uint32_t t = (iv[r][1] != iv[r][0] ? 1u : 0u) | (iv[r][2] != iv[r][1] ? 2u : 0u) |
+                           (iv[r][3] != iv[r][2] ? 4u : 0u) | (q != iv[r][3] ? 8u : 0u);
+        hm |= h << (4 * r);
+        tm |= t << (4 * r);
+    }
+    // ---- pass 1: per-lane aggregates ----
+    float fagg[ROWS];
+    Affine ragg[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t h = (hm >> (4 * r)) & 15u;
+        const uint32_t t = (tm >> (4 * r)) & 15u;
+        float p = x[r][0];
+        p = (h & 2u) ? x[r][1] : p * x[r][1];
+        p = (h & 4u) ? x[r][2] : p * x[r][2];
+        p = (h & 8u) ? x[r][3] : p * x[r][3];
+        fagg[r] = p;
+        Affine m;
+        m.a = (t & 8u) ? 0.0f : xn[r];
+        m.b = g[r][3];
+        m = compose(Affine{(t & 4u) ? 0.0f : x[r][3], g[r][2]}, m);
+        m = compose(Affine{(t & 2u) ? 0.0f : x[r][2], g[r][1]}, m);
+        m = compose(Affine{(t & 1u) ? 0.0f : x[r][1], g[r][0]}, m);
+        ragg[r] = m;
+    }
+    float cv[ROWS];
+    uint32_t cf, wf;
+    float wv;
+    warp_seg_scan_rows<OP_MUL, ROWS>(fagg, hm, lane, cv, cf, wv, wf);
+    Affine sx[ROWS];
+    Affine wagg;
+    warp_affine_rscan_rows<ROWS>(ragg, lane, sx, wagg);
+    if (lane == 0) {
+        sh->wv[warp] = wv;
+        sh->wf[warp] = wf;
+        sh->wa[warp] = wagg.a;
+        sh->wb[warp] = wagg.b;
+    }
+    named_bar_sync<WARPS * 32>(1);
+    // ---- forward prefix over earlier warps; reverse suffix over later warps; tile aggregate ----
+    float wp_v = 1.0f;
+    uint32_t wp_f = 0u;
+#pragma unroll
+    for (int j = 0; j < WARPS; ++j) {
+        if (j < warp) {
+            const float jv = sh->wv[j];
+            const uint32_t jf = sh->wf[j];
+            wp_v = jf ? jv : wp_v * jv;
+            wp_f |= jf;
+        }
+    }
+    Affine ws = affine_id();  // composite of warps after mine
+    Affine ta = affine_id();  // whole tile
+#pragma unroll
+    for (int j = WARPS - 1; j >= 0; --j) {
+        const Affine mj = Affine{sh->wa[j], sh->wb[j]};
+        if (j > warp) ws = compose(mj, ws);
+        ta = compose(mj, ta);
+    }
+    // ---- decoupled look-ahead (warp 0) ----
+    if (warp == 0) {
+        uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
+        const bool last_tile = (tile + 1u == num_tiles);
+        const bool self_complete = (ta.a == 0.0f) || last_tile;
+        if (lane == 0) {
+            if (self_complete) {
+                st_relaxed_u64(slot, pack_desc(epoch, ST_INCL, 0u, ta.b));
+            } else {
+                st_relaxed_u64(slot + 1, pack_desc(epoch, ST_AGG, 0u, ta.a));
+                st_relaxed_u64(slot + 2, pack_desc(epoch, ST_AGG, 0u, ta.b));
+            }
+        }
+        float rn = 0.0f;
+        if (!last_tile) {
+            rn = bwd_lookahead(desc, tile, num_tiles, epoch, hdr, lane);
+            if (!self_complete && lane == 0) st_relaxed_u64(slot, pack_desc(epoch, ST_INCL, 0u, apply(ta, rn)));
+        }
+        if (lane == 0) sh->r_next = rn;
+    }
+    named_bar_sync<WARPS * 32>(1);
+    const float r_next = sh->r_next;
+    // ---- pass 2: per-element S and E, store E*S ----
+    const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
+    const bool full = (base + TILE <= n);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t h = (hm >> (4 * r)) & 15u;
+        const uint32_t t = (tm >> (4 * r)) & 15u;
+        // S of the element right after this lane's e=3 (only used when e=3 is not a tail)
+        const float sn = apply(compose(sx[r], ws), r_next);
+        const float s3 = (t & 8u) ? g[r][3] : fmaf(xn[r], sn, g[r][3]);
+        const float s2 = (t & 4u) ? g[r][2] : fmaf(x[r][3], s3, g[r][2]);
+        const float s1 = (t & 2u) ? g[r][1] : fmaf(x[r][2], s2, g[r][1]);
+        const float s0 = (t & 1u) ? g[r][0] : fmaf(x[r][1], s1, g[r][0]);
+        // forward carry into e=0: product of x from the segment head up to the previous element
+        float c = cv[r];
+        bool f = (cf >> r) & 1u;
+        if (!f) {
+            c = wp_v * c;
+            f = wp_f != 0u;
+        }
+        if (!f) c = y_prev * c;
+        const float e0 = (h & 1u) ? 1.0f : c;
+        const float e1 = (h & 2u) ? 1.0f : e0 * x[r][0];
+        const float e2 = (h & 4u) ? 1.0f : e1 * x[r][1];
+        const float e3 = (h & 8u) ? 1.0f : e2 * x[r][2];
+        const float o0 = e0 * s0, o1 = e1 * s1, o2 = e2 * s2, o3 = e3 * s3;
+        const int64_t gi = wbase + r * 128 + lane * 4;
+        if (full && out_vec) {
+            stcs_f4(gin + gi, o0, o1, o2, o3);
+        } else {
+            if (gi + 0 < n) __stcs(gin + gi + 0, o0);
+            if (gi + 1 < n) __stcs(gin + gi + 1, o1);
+            if (gi + 2 < n) __stcs(gin + gi + 2, o2);
+            if (gi + 3 < n) __stcs(gin + gi + 3, o3);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_row_global_bwd(const float *__restrict__ x, const float *__restrict__ g,
+                                                    const int32_t *__restrict__ inv, int64_t gi, int64_t n,
+                                                    bool vec, float (&xv)[4], float (&gv)[4], int32_t (&iv)[4]) {
+    if (vec && gi + 3 < n) {
+        const float4 a = ldcs_f4(x + gi);
+        const float4 b = ldcs_f4(g + gi);
+        const int4 c = ldcs_i4(inv + gi);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+        iv[0] = c.x; iv[1] = c.y; iv[2] = c.z; iv[3] = c.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool in = gi + e < n;
+            xv[e] = in ? __ldcs(x + gi + e) : 1.0f;
+            gv[e] = in ? __ldcs(g + gi + e) : 0.0f;
+            iv[e] = in ? __ldcs(inv + gi + e) : -1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LDG variant: one tile per CTA, any alignment.
+// ---------------------------------------------------------------------------
+template <int WARPS, int ROWS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
+          const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
+          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int out_vec) {
+    constexpr int TILE = WARPS * ROWS * 128;
+    __shared__ BwdShared<WARPS> sh;
+    __shared__ uint32_t s_epoch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        sh.tile = atomicAdd(hdr + HDR_TICKET, 1u);
+        s_epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
+    }
+    __syncthreads();
+    const uint32_t ticket = sh.tile;
+    const uint32_t epoch = s_epoch;
+    if (ticket < num_tiles) {
+        const uint32_t tile = num_tiles - 1u - ticket;
+        const int64_t base = static_cast<int64_t>(tile) * TILE;
+        const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
+        const int64_t wend = wbase + ROWS * 128;
+        float xv[ROWS][4], gv[ROWS][4];
+        int32_t iv[ROWS][4];
+        int32_t iprev = -1, inext = -1;
+        float xnext = 0.0f;
+        if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
+        if (lane == 31 && wend < n) {
+            inext = __ldg(inv + wend);
+            xnext = __ldg(x + wend);
+        }
+        const float y_prev = (base > 0) ? __ldg(y + base - 1) : 1.0f;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            load_row_global_bwd(x, g, inv, wbase + r * 128 + lane * 4, n, in_vec != 0, xv[r], gv[r], iv[r]);
+        bwd_tile_body<WARPS, ROWS>(xv, gv, iv, iprev, inext, xnext, y_prev, tile, num_tiles, base, n, gin,
+                                   out_vec != 0, epoch, hdr, desc, &sh, warp, lane);
+    }
+    if (threadIdx.x == 0) finish_launch(hdr, epoch);
+}
+
+// ---------------------------------------------------------------------------
+// TMA variant: persistent, producer warp + STAGES-deep ring of (x, g, inv) tiles.
+// ---------------------------------------------------------------------------
+template <int WARPS, int ROWS, int STAGES>
+struct BwdTmaSmem {
+    static constexpr int TILE = WARPS * ROWS * 128;
+    static constexpr int STAGE_BYTES = TILE * 12;
+    struct Ctl {
+        uint64_t full[STAGES];
+        uint64_t empty[STAGES];
+        uint32_t tile[STAGES];
+        uint32_t mode[STAGES];
+        int32_t iprev[STAGES];
+        int32_t inext[STAGES];
+        float xnext[STAGES];
+        float yprev[STAGES];
+        uint32_t epoch;
+        BwdShared<WARPS> sh;
+    };
+    static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl));
+};
+
+template <int WARPS, int ROWS, int STAGES>
+__global__ void __launch_bounds__((WARPS + 1) * 32)
+k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
+          const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
+          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int out_vec) {
+    using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
+    constexpr int TILE = L::TILE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&ctl->full[s], 2);
+            mbar_init(&ctl->empty[s], WARPS);
+        }
+        mbar_fence_init();
+        ctl->epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
+    }
+    __syncthreads();
+    const uint32_t epoch = ctl->epoch;
+
+    if (warp == WARPS) {
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            for (uint32_t it = 0;; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
+                const uint32_t t = atomicAdd(hdr + HDR_TICKET, 1u);
+                ctl->tile[s] = t;
+                if (t >= num_tiles) {
+                    mbar_arrive(&ctl->full[s]);
+                    mbar_arrive(&ctl->full[s]);
+                    break;
+                }
+                const uint32_t tile = num_tiles - 1u - t;
+                const int64_t base = static_cast<int64_t>(tile) * TILE;
+                if (base + TILE <= n) {
+                    unsigned char *st = smem + s * L::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
+                    bulk_g2s(st, x + base, TILE * 4, &ctl->full[s], pol);
+                    bulk_g2s(st + TILE * 4, g + base, TILE * 4, &ctl->full[s], pol);
+                    bulk_g2s(st + TILE * 8, inv + base, TILE * 4, &ctl->full[s], pol);
+                    ctl->mode[s] = 1u;
+                } else {
+                    ctl->mode[s] = 0u;
+                    mbar_arrive(&ctl->full[s]);
+                }
+                const int64_t end = base + TILE;
+                const int32_t ip = (base > 0) ? __ldg(inv + base - 1) : -1;
+                const float yp = (base > 0) ? __ldg(y + base - 1) : 1.0f;
+                const int32_t in = (end < n) ? __ldg(inv + end) : -1;
+                const float xq = (end < n) ? __ldg(x + end) : 0.0f;
+                ctl->iprev[s] = ip;
+                ctl->yprev[s] = yp;
+                ctl->inext[s] = in;
+                ctl->xnext[s] = xq;
+                mbar_arrive(&ctl->full[s]);
+            }
+            finish_launch(hdr, epoch);
+        }
+        return;
+    }
+
+    for (uint32_t it = 0;; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&ctl->full[s], ph, hdr);
+        const uint32_t ticket = ctl->tile[s];
+        if (ticket >= num_tiles) break;
+        const uint32_t tile = num_tiles - 1u - ticket;
+        const int64_t base = static_cast<int64_t>(tile) * TILE;
+        const int woff = warp * (ROWS * 128);
+        const int64_t wbase = base + woff;
+        const int64_t wend = wbase + ROWS * 128;
+        float xv[ROWS][4], gv[ROWS][4];
+        int32_t iv[ROWS][4];
+        int32_t iprev = -1, inext = -1;
+        float xnext = 0.0f;
+        const float y_prev = ctl->yprev[s];
+        if (ctl->mode[s]) {
+            const float *xs = reinterpret_cast<const float *>(smem + s * L::STAGE_BYTES);
+            const float *gs = xs + TILE;
+            const int32_t *is = reinterpret_cast<const int32_t *>(xs + 2 * TILE);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int o = woff + r * 128 + lane * 4;
+                const float4 a = *reinterpret_cast<const float4 *>(xs + o);
+                const float4 b = *reinterpret_cast<const float4 *>(gs + o);
+                const int4 c = *reinterpret_cast<const int4 *>(is + o);
+                xv[r][0] = a.x; xv[r][1] = a.y; xv[r][2] = a.z; xv[r][3] = a.w;
+                gv[r][0] = b.x; gv[r][1] = b.y; gv[r][2] = b.z; gv[r][3] = b.w;
+                iv[r][0] = c.x; iv[r][1] = c.y; iv[r][2] = c.z; iv[r][3] = c.w;
+            }
+            if (lane == 0) iprev = (warp == 0) ? ctl->iprev[s] : is[woff - 1];
+            if (lane == 31) {
+                if (warp == WARPS - 1) {
+                    inext = ctl->inext[s];
+                    xnext = ctl->xnext[s];
+                } else {
+                    inext = is[woff + ROWS * 128];
+                    xnext = xs[woff + ROWS * 128];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                load_row_global_bwd(x, g, inv, wbase + r * 128 + lane * 4, n, true, xv[r], gv[r], iv[r]);
+            if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
+            if (lane == 31 && wend < n) {
+                inext = __ldg(inv + wend);
+                xnext = __ldg(x + wend);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[s]);
+        bwd_tile_body<WARPS, ROWS>(xv, gv, iv, iprev, inext, xnext, y_prev, tile, num_tiles, base, n, gin,
+                                   out_vec != 0, epoch, hdr, desc, &ctl->sh, warp, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Integer-side validation of (inv, seg_end): see gcp_validate_segments.
+// ---------------------------------------------------------------------------
+__global__ void k_validate_segments(const int32_t *__restrict__ inv, const int32_t *__restrict__ seg_end, int64_t n,
+                                    int64_t k, unsigned long long *__restrict__ violations) {
+    unsigned long long bad = 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t s = inv[i];
+        if (s < 0 || s >= k) { ++bad; continue; }
+        if (i == 0 && s != 0) ++bad;
+        if (i > 0) {
+            const int32_t p = inv[i - 1];
+            if (s != p && s != p + 1) ++bad;
+        }
+        const bool tail = (i == n - 1) || (inv[i + 1] != s);
+        if (tail != (seg_end[s] == i + 1)) ++bad;
+        if (i == n - 1 && s != k - 1) ++bad;
+    }
+    if (n == 0 && k != 0 && blockIdx.x == 0 && threadIdx.x == 0) ++bad;
+    if (bad) atomicAdd(violations, bad);
+}
+
+}  // namespace gcp

@@ -1,0 +1,178 @@
+// gcp_device.cuh — device-side building blocks shared by the scan kernels (sm_100a).
+//
+//  * PTX wrappers: mbarrier, 1-D bulk async copy (TMA engine, SASS UBLKCP), relaxed
+//    gpu-scope descriptor loads/stores, streaming vector loads/stores.
+//  * workspace layout + tile descriptors for the decoupled look-back.
+//  * warp-level segmented scan pieces.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gcp {
+
+// ----------------------------------------------------------------------------
+// Workspace layout (device memory, caller owned; see include/gcp_abi.h)
+//   [0,256)    header: u32 words  ticket@0, done@16, epoch@32, abort@33, violations(u64)@40
+//   [256, ...) 32 B descriptor slot per tile of MIN_TILE elements
+// ----------------------------------------------------------------------------
+constexpr int WS_HEADER_BYTES = 256;
+constexpr int WS_SLOT_BYTES = 32;
+constexpr int MIN_TILE = 1024;
+constexpr int HDR_TICKET = 0;
+constexpr int HDR_DONE = 16;
+constexpr int HDR_EPOCH = 32;
+constexpr int HDR_ABORT = 33;
+constexpr int HDR_VIOL64 = 20;  // index in u64 units (byte 160)
+
+constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_INCL = 2;
+constexpr uint32_t EPOCH_MASK = 0x1FFFFFFFu;
+constexpr uint32_t POLL_LIMIT = 1u << 22;  // bounded spins: fail open + sticky abort flag, never hang
+
+__device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, uint32_t status, uint32_t flag, float v) {
+    uint32_t hi = ((epoch & EPOCH_MASK) << 3) | (status << 1) | (flag & 1u);
+    return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>(__float_as_uint(v));
+}
+__device__ __forceinline__ bool desc_valid(uint64_t d, uint32_t epoch) {
+    uint32_t hi = static_cast<uint32_t>(d >> 32);
+    return ((hi >> 3) == (epoch & EPOCH_MASK)) && (((hi >> 1) & 3u) != ST_INVALID);
+}
+__device__ __forceinline__ uint32_t desc_status(uint64_t d) { return (static_cast<uint32_t>(d >> 32) >> 1) & 3u; }
+__device__ __forceinline__ uint32_t desc_flag(uint64_t d) { return static_cast<uint32_t>(d >> 32) & 1u; }
+__device__ __forceinline__ float desc_value(uint64_t d) { return __uint_as_float(static_cast<uint32_t>(d)); }
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Poll one descriptor word until it carries this launch's epoch and a non-invalid
+// status.  Bounded: on expiry sets the sticky abort flag and returns whatever is
+// there (results are then wrong, but the kernel terminates; the host sees the flag).
+__device__ __forceinline__ uint64_t poll_desc(const uint64_t *p, uint32_t epoch, uint32_t *hdr) {
+    uint64_t d = ld_relaxed_u64(p);
+    uint32_t spins = 0;
+    while (!desc_valid(d, epoch)) {
+        ++spins;
+        if ((spins & 255u) == 0u) {
+            if (spins >= POLL_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+            if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
+        }
+        if (spins > 8) __nanosleep(40);
+        d = ld_relaxed_u64(p);
+    }
+    return d;
+}
+
+// ----------------------------------------------------------------------------
+// mbarrier + bulk async copy
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait (same fail-open policy as poll_desc)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *hdr) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        ++spins;
+        if ((spins & 63u) == 0u) {
+            if (spins >= (POLL_LIMIT >> 2)) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+            if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
+        }
+    }
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared, 1-D, size multiple of 16, both 16-B aligned; completes on `bar` (complete_tx).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+template <int COUNT>
+__device__ __forceinline__ void named_bar_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// streaming global access
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldcs_f4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ int4 ldcs_i4(const int32_t *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ void stcs_f4(float *p, float a, float b, float c, float d) {
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+}
+
+// ----------------------------------------------------------------------------
+// scan operators
+// ----------------------------------------------------------------------------
+constexpr int OP_MUL = 0;
+constexpr int OP_ADD = 1;
+template <int OP>
+struct ScanOp;
+template <>
+struct ScanOp<OP_MUL> {
+    static __device__ __forceinline__ float id() { return 1.0f; }
+    static __device__ __forceinline__ float f(float a, float b) { return a * b; }
+};
+template <>
+struct ScanOp<OP_ADD> {
+    static __device__ __forceinline__ float id() { return 0.0f; }
+    static __device__ __forceinline__ float f(float a, float b) { return a + b; }
+};
+
+// Affine map S -> b + a*S (reverse scan of the backward).  a == 0 is a hard reset:
+// the right operand is then ignored even if it is Inf/NaN (tail of a segment).
+struct Affine {
+    float a, b;
+};
+__device__ __forceinline__ Affine affine_id() { return Affine{1.0f, 0.0f}; }
+// (l ∘ r)(S) = l(r(S)) : l is nearer (lower index), r is further (higher index)
+__device__ __forceinline__ Affine compose(Affine l, Affine r) {
+    Affine o;
+    o.b = (l.a == 0.0f) ? l.b : fmaf(l.a, r.b, l.b);
+    o.a = (l.a == 0.0f) ? 0.0f : l.a * r.a;
+    return o;
+}
+__device__ __forceinline__ float apply(Affine m, float s) { return (m.a == 0.0f) ? m.b : fmaf(m.a, s, m.b); }
+
+}  // namespace gcp

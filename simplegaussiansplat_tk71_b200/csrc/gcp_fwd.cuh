@@ -1,0 +1,395 @@
+// gcp_fwd.cuh — forward segmented inclusive scan (cumprod / cumsum), single pass.
+//
+// Replaces thrust::inclusive_scan_by_key at
+//   /root/reference/cuda_kernel/grouped_cumprod_forward.cu:17-23  (OP_MUL)
+//   /root/reference/cuda_kernel/grouped_cumsum_forward.cu:17-23   (OP_ADD)
+//
+// Data layout inside a tile of TILE = WARPS*ROWS*128 elements: warp w owns the
+// contiguous span [w*ROWS*128, (w+1)*ROWS*128); in row r lane l holds the four
+// consecutive elements at r*128 + l*4 ("striped float4"): every global / shared
+// access is a fully coalesced, bank-conflict-free 128-bit access, and no
+// shared-memory transpose is needed.  Scan = thread-serial over the float4 ->
+// ballot-masked segmented warp scan per row (5 SHFL) -> serial chain over the
+// ROWS rows -> WARPS warp aggregates through shared memory -> decoupled
+// look-back across tiles (one 64-bit descriptor per tile).
+//
+// Two kernels share the body:
+//   k_fwd_tma : persistent CTAs; a producer warp takes tile tickets and streams
+//               x/key tiles into a STAGES-deep shared-memory ring with 1-D bulk
+//               async copies (cp.async.bulk -> UBLKCP) completing on mbarriers.
+//   k_fwd_ldg : one tile per CTA, direct 128-bit (or scalar, for unaligned
+//               pointers) streaming loads.  Handles every alignment and n.
+#pragma once
+#include "gcp_device.cuh"
+
+namespace gcp {
+
+template <int WARPS>
+struct FwdShared {
+    float wv[WARPS];
+    uint32_t wf[WARPS];
+    float tp_v;
+    uint32_t tile;
+};
+
+// Decoupled look-back (warp-wide, 32 predecessors per round).  Returns the
+// exclusive prefix of `tile`: op over everything from the last segment head
+// before the tile up to the tile start.  Terminates at the first predecessor
+// that is INCLUSIVE or whose aggregate contains a head (flag).
+template <int OP>
+__device__ __forceinline__ float fwd_lookback(const uint64_t *desc, uint32_t tile, uint32_t epoch,
+                                              uint32_t *hdr, int lane) {
+    using O = ScanOp<OP>;
+    float carry = O::id();
+    int64_t pb = static_cast<int64_t>(tile) - 1;
+    while (true) {
+        int64_t idx = pb - lane;
+        bool term = true;
+        float v = O::id();
+        if (idx >= 0) {
+            uint64_t d = poll_desc(desc + idx * 4, epoch, hdr);
+            term = (desc_status(d) == ST_INCL) || (desc_flag(d) != 0u);
+            v = desc_value(d);
+        }
+        uint32_t tm = __ballot_sync(0xffffffffu, term);
+        int last = tm ? (__ffs(tm) - 1) : 31;
+        float w = (lane <= last) ? v : O::id();
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+        carry = O::f(w, carry);
+        if (tm) break;
+        pb -= 32;
+    }
+    return carry;
+}
+
+// Segmented inclusive scan of one aggregate per (row, lane) across the warp and
+// down its ROWS rows.
+//   agg[r] : op over this lane's 4 elements of row r after its last head
+//   hm     : head bits of the lane's elements, bit r*4+e
+//   cv/cf  : out, per-row carry INTO this lane from earlier lanes/rows of the warp
+//            (value, "a head lies between the warp start and this lane" flag bit r)
+//   wv/wf  : out, warp aggregate
+template <int OP, int ROWS>
+__device__ __forceinline__ void warp_seg_scan_rows(const float (&agg)[ROWS], uint32_t hm, int lane,
+                                                   float (&cv)[ROWS], uint32_t &cf, float &wv, uint32_t &wf) {
+    using O = ScanOp<OP>;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t le = lt | (1u << lane);
+    float rp_v = O::id();
+    uint32_t rp_f = 0u;
+    cf = 0u;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t h = (hm >> (4 * r)) & 15u;
+        const uint32_t m = __ballot_sync(0xffffffffu, h != 0u);
+        const int start = max(31 - __clz(m & le), 0);  // nearest lane <= me holding a head (0 if none)
+        float inc = agg[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            float t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane - d >= start) inc = O::f(t, inc);
+        }
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = O::id();
+        const bool ef = (m & lt) != 0u;
+        const float row_v = __shfl_sync(0xffffffffu, inc, 31);
+        const bool row_f = m != 0u;
+        cv[r] = ef ? exc : O::f(rp_v, exc);
+        cf |= ((ef || rp_f) ? 1u : 0u) << r;
+        rp_v = row_f ? row_v : O::f(rp_v, row_v);
+        rp_f |= row_f ? 1u : 0u;
+    }
+    wv = rp_v;
+    wf = rp_f;
+}
+
+// v  : in  x values, out local inclusive values (thread-serial within each float4)
+template <int OP, int ROWS>
+__device__ __forceinline__ void fwd_warp_scan(float (&v)[ROWS][4], uint32_t hm, int lane, float (&cv)[ROWS],
+                                              uint32_t &cf, float &wv, uint32_t &wf) {
+    using O = ScanOp<OP>;
+    float agg[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t h = (hm >> (4 * r)) & 15u;
+        v[r][1] = (h & 2u) ? v[r][1] : O::f(v[r][0], v[r][1]);
+        v[r][2] = (h & 4u) ? v[r][2] : O::f(v[r][1], v[r][2]);
+        v[r][3] = (h & 8u) ? v[r][3] : O::f(v[r][2], v[r][3]);
+        agg[r] = v[r][3];
+    }
+    warp_seg_scan_rows<OP, ROWS>(agg, hm, lane, cv, cf, wv, wf);
+}
+
+// Everything after the tile's x/key values are in registers.
+//   kprev : key of the element just before this warp's span (only lane 0 needs it)
+//   first_head : this warp's first element is global element 0
+template <int OP, int WARPS, int ROWS>
+__device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t (&k)[ROWS][4], int32_t kprev,
+                                              bool first_head, uint32_t tile, int64_t base, int64_t n,
+                                              float *__restrict__ y, bool y_vec, uint32_t epoch, uint32_t *hdr,
+                                              uint64_t *desc, FwdShared<WARPS> *sh, int warp, int lane) {
+    using O = ScanOp<OP>;
+    constexpr int TILE = WARPS * ROWS * 128;
+    // ---- head flags ----
+    uint32_t hm = 0u;
+    int32_t carry_key = kprev;  // key just before row r's lane 0
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        int32_t p = __shfl_up_sync(0xffffffffu, k[r][3], 1);
+        if (lane == 0) p = carry_key;
+        carry_key = __shfl_sync(0xffffffffu, k[r][3], 31);
+        uint32_t h = (k[r][0] != p ? 1u : 0u) | (k[r][1] != k[r][0] ? 2u : 0u) | (k[r][2] != k[r][1] ? 4u : 0u) |
+                     (k[r][3] != k[r][2] ? 8u : 0u);
+        if (r == 0 && lane == 0 && first_head) h |= 1u;
+        hm |= h << (4 * r);
+    }
+    // ---- warp-level scan ----
+    float cv[ROWS];
+    uint32_t cf, wf;
+    float wv;
+    fwd_warp_scan<OP, ROWS>(v, hm, lane, cv, cf, wv, wf);
+    if (lane == 0) {
+        sh->wv[warp] = wv;
+        sh->wf[warp] = wf;
+    }
+    named_bar_sync<WARPS * 32>(1);
+    // ---- exclusive prefix over warps + tile aggregate ----
+    float wp_v = O::id(), ta_v = O::id();
+    uint32_t wp_f = 0u, ta_f = 0u;
+#pragma unroll
+    for (int j = 0; j < WARPS; ++j) {
+        const float jv = sh->wv[j];
+        const uint32_t jf = sh->wf[j];
+        if (j < warp) {
+            wp_v = jf ? jv : O::f(wp_v, jv);
+            wp_f |= jf;
+        }
+        ta_v = jf ? jv : O::f(ta_v, jv);
+        ta_f |= jf;
+    }
+    // ---- decoupled look-back (warp 0) ----
+    if (warp == 0) {
+        uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
+        const bool self_complete = (ta_f != 0u) || (tile == 0u);
+        if (lane == 0) st_relaxed_u64(slot, pack_desc(epoch, self_complete ? ST_INCL : ST_AGG, ta_f, ta_v));
+        float tp = O::id();
+        if (tile > 0u) {
+            tp = fwd_lookback<OP>(desc, tile, epoch, hdr, lane);
+            if (!self_complete && lane == 0) st_relaxed_u64(slot, pack_desc(epoch, ST_INCL, 0u, O::f(tp, ta_v)));
+        }
+        if (lane == 0) sh->tp_v = tp;
+    }
+    named_bar_sync<WARPS * 32>(1);
+    const float tp_v = sh->tp_v;
+    // ---- apply carries, store ----
+    const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
+    const bool full = (base + TILE <= n);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        float c = cv[r];
+        bool f = (cf >> r) & 1u;
+        if (!f) {
+            c = O::f(wp_v, c);
+            f = wp_f != 0u;
+        }
+        if (!f) c = O::f(tp_v, c);
+        const uint32_t h = (hm >> (4 * r)) & 15u;
+        const bool n0 = !(h & 1u), n1 = n0 && !(h & 2u), n2 = n1 && !(h & 4u), n3 = n2 && !(h & 8u);
+        const float o0 = n0 ? O::f(c, v[r][0]) : v[r][0];
+        const float o1 = n1 ? O::f(c, v[r][1]) : v[r][1];
+        const float o2 = n2 ? O::f(c, v[r][2]) : v[r][2];
+        const float o3 = n3 ? O::f(c, v[r][3]) : v[r][3];
+        const int64_t gi = wbase + r * 128 + lane * 4;
+        if (full && y_vec) {
+            stcs_f4(y + gi, o0, o1, o2, o3);
+        } else {
+            if (gi + 0 < n) __stcs(y + gi + 0, o0);
+            if (gi + 1 < n) __stcs(y + gi + 1, o1);
+            if (gi + 2 < n) __stcs(y + gi + 2, o2);
+            if (gi + 3 < n) __stcs(y + gi + 3, o3);
+        }
+    }
+}
+
+// Guarded / unaligned-capable global load of one thread-row (4 elements).
+template <int OP>
+__device__ __forceinline__ void load_row_global(const float *__restrict__ x, const int32_t *__restrict__ key,
+                                                int64_t gi, int64_t n, bool vec, float (&v)[4], int32_t (&k)[4]) {
+    using O = ScanOp<OP>;
+    if (vec && gi + 3 < n) {
+        float4 a = ldcs_f4(x + gi);
+        int4 b = ldcs_i4(key + gi);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        k[0] = b.x; k[1] = b.y; k[2] = b.z; k[3] = b.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool in = gi + e < n;
+            v[e] = in ? __ldcs(x + gi + e) : O::id();
+            k[e] = in ? __ldcs(key + gi + e) : 0;
+        }
+    }
+}
+
+// Last-CTA-done: reset ticket/done and advance the epoch so the next launch on
+// the stream finds a clean workspace without a memset.
+__device__ __forceinline__ void finish_launch(uint32_t *hdr, uint32_t epoch) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(hdr + HDR_DONE, 1u);
+    if (prev == gridDim.x - 1u) {
+        hdr[HDR_TICKET] = 0u;
+        hdr[HDR_DONE] = 0u;
+        hdr[HDR_EPOCH] = epoch + 1u;
+        __threadfence();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LDG variant: one tile per CTA (ticket taken at entry), any alignment.
+// ---------------------------------------------------------------------------
+template <int OP, int WARPS, int ROWS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_fwd_ldg(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int y_vec) {
+    constexpr int TILE = WARPS * ROWS * 128;
+    __shared__ FwdShared<WARPS> sh;
+    __shared__ uint32_t s_epoch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        sh.tile = atomicAdd(hdr + HDR_TICKET, 1u);
+        s_epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
+    }
+    __syncthreads();
+    const uint32_t tile = sh.tile;
+    const uint32_t epoch = s_epoch;
+    if (tile < num_tiles) {
+        const int64_t base = static_cast<int64_t>(tile) * TILE;
+        const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
+        float v[ROWS][4];
+        int32_t k[ROWS][4];
+        int32_t kprev = 0;
+        if (lane == 0 && wbase > 0 && wbase - 1 < n) kprev = __ldg(key + wbase - 1);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            load_row_global<OP>(x, key, wbase + r * 128 + lane * 4, n, in_vec != 0, v[r], k[r]);
+        fwd_tile_body<OP, WARPS, ROWS>(v, k, kprev, wbase == 0, tile, base, n, y, y_vec != 0, epoch, hdr, desc, &sh,
+                                       warp, lane);
+    }
+    if (threadIdx.x == 0) finish_launch(hdr, epoch);
+}
+
+// ---------------------------------------------------------------------------
+// TMA variant: persistent, producer warp + STAGES-deep bulk-copy ring.
+// Requires x and key 16-byte aligned (the host falls back to k_fwd_ldg otherwise).
+// ---------------------------------------------------------------------------
+template <int WARPS, int ROWS, int STAGES>
+struct FwdTmaSmem {
+    static constexpr int TILE = WARPS * ROWS * 128;
+    static constexpr int STAGE_BYTES = TILE * 8;
+    struct Ctl {
+        uint64_t full[STAGES];
+        uint64_t empty[STAGES];
+        uint32_t tile[STAGES];
+        int32_t halo[STAGES];
+        uint32_t mode[STAGES];
+        uint32_t epoch;
+        FwdShared<WARPS> sh;
+    };
+    static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl));
+};
+
+template <int OP, int WARPS, int ROWS, int STAGES>
+__global__ void __launch_bounds__((WARPS + 1) * 32)
+k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int y_vec) {
+    using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
+    constexpr int TILE = L::TILE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&ctl->full[s], 2);       // producer: expect_tx arrive + release arrive
+            mbar_init(&ctl->empty[s], WARPS);  // one elected lane per consumer warp
+        }
+        mbar_fence_init();
+        ctl->epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
+    }
+    __syncthreads();
+    const uint32_t epoch = ctl->epoch;
+
+    if (warp == WARPS) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            for (uint32_t it = 0;; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
+                const uint32_t t = atomicAdd(hdr + HDR_TICKET, 1u);
+                ctl->tile[s] = t;
+                if (t >= num_tiles) {
+                    mbar_arrive(&ctl->full[s]);
+                    mbar_arrive(&ctl->full[s]);
+                    break;
+                }
+                const int64_t base = static_cast<int64_t>(t) * TILE;
+                if (base + TILE <= n) {
+                    unsigned char *st = smem + s * L::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
+                    bulk_g2s(st, x + base, TILE * 4, &ctl->full[s], pol);
+                    bulk_g2s(st + TILE * 4, key + base, TILE * 4, &ctl->full[s], pol);
+                    ctl->mode[s] = 1u;
+                } else {
+                    ctl->mode[s] = 0u;
+                    mbar_arrive(&ctl->full[s]);
+                }
+                ctl->halo[s] = (base > 0) ? __ldg(key + base - 1) : 0;
+                mbar_arrive(&ctl->full[s]);
+            }
+            finish_launch(hdr, epoch);
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    for (uint32_t it = 0;; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&ctl->full[s], ph, hdr);
+        const uint32_t tile = ctl->tile[s];
+        if (tile >= num_tiles) break;
+        const int64_t base = static_cast<int64_t>(tile) * TILE;
+        const int woff = warp * (ROWS * 128);
+        const int64_t wbase = base + woff;
+        float v[ROWS][4];
+        int32_t k[ROWS][4];
+        int32_t kprev = 0;
+        if (ctl->mode[s]) {
+            const float *xs = reinterpret_cast<const float *>(smem + s * L::STAGE_BYTES);
+            const int32_t *ks = reinterpret_cast<const int32_t *>(smem + s * L::STAGE_BYTES + TILE * 4);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const float4 a = *reinterpret_cast<const float4 *>(xs + woff + r * 128 + lane * 4);
+                const int4 b = *reinterpret_cast<const int4 *>(ks + woff + r * 128 + lane * 4);
+                v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w;
+                k[r][0] = b.x; k[r][1] = b.y; k[r][2] = b.z; k[r][3] = b.w;
+            }
+            if (lane == 0) kprev = (warp == 0) ? ctl->halo[s] : ks[woff - 1];
+        } else {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                load_row_global<OP>(x, key, wbase + r * 128 + lane * 4, n, true, v[r], k[r]);
+            if (lane == 0 && wbase > 0 && wbase - 1 < n) kprev = __ldg(key + wbase - 1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[s]);
+        fwd_tile_body<OP, WARPS, ROWS>(v, k, kprev, wbase == 0, tile, base, n, y, y_vec != 0, epoch, hdr, desc,
+                                       &ctl->sh, warp, lane);
+    }
+}
+
+}  // namespace gcp

@@ -1,0 +1,150 @@
+"""Host-side mirror of the reference's `grouped_cumprod` extension ops.
+
+Same names, positional signatures, in-place output convention and dtype rules as
+/root/reference/cuda_kernel/cuda_kernel.cpp:5-22; the work is done by the hand-written
+sm_100a kernels behind the C ABI (include/gcp_abi.h).  PyTorch is used only for device
+memory, the current stream and error types.
+
+Differences from the reference, all on the safe side:
+  * inputs are checked (CUDA, dtype, 1-D contiguous, equal numel, same device) instead of
+    being trusted; the reference only fails on dtype (data_ptr<T>()).
+  * launches go to the *current* torch stream and never block the host (the reference's
+    thrust calls run on the legacy stream and synchronise).
+  * grouped_cumprod_backward is the exact division-free gradient: where an x is 0 the
+    reference returns 0 (0/1e-8), this returns the true value.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_workspaces: dict = {}
+
+
+def _workspace(device: torch.device, n: int):
+    """One cached, self-resetting workspace per (device, stream); grown geometrically."""
+    L = _lib.lib()
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream)
+    need = int(L.gcp_workspace_bytes(n))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        size = max(need, 1 << 20)
+        if ws is not None:
+            size = max(size, 2 * ws.numel())
+        ws = torch.empty(size, dtype=torch.uint8, device=device)
+        _lib.check(L.gcp_workspace_init(ws.data_ptr(), ws.numel(), stream.cuda_stream), "gcp_workspace_init")
+        _workspaces[key] = ws
+    return ws, stream.cuda_stream
+
+
+def _check(t: torch.Tensor, name: str, dtype: torch.dtype, n: int | None = None, device=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        # the reference raises here too: data_ptr<float>() / data_ptr<int>() (grouped_cumprod_forward.cu:8-10)
+        raise RuntimeError(f"expected scalar type {dtype} for {name} but found {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if n is not None and t.numel() != n:
+        raise RuntimeError(f"{name} has {t.numel()} elements, expected {n}")
+    if device is not None and t.device != device:
+        raise RuntimeError(f"{name} is on {t.device}, expected {device}")
+
+
+def _scan(fn_name: str, x: torch.Tensor, key: torch.Tensor, y: torch.Tensor) -> None:
+    _check(x, "x", torch.float32)
+    n = x.numel()
+    _check(key, "key", torch.int32, n, x.device)
+    _check(y, "y", torch.float32, n, x.device)
+    if n == 0:
+        return
+    with torch.cuda.device(x.device):
+        ws, stream = _workspace(x.device, n)
+        fn = getattr(_lib.lib(), fn_name)
+        _lib.check(fn(x.data_ptr(), key.data_ptr(), y.data_ptr(), n, ws.data_ptr(), ws.numel(), stream), fn_name)
+
+
+def grouped_cumprod_forward(x: torch.Tensor, key: torch.Tensor, y: torch.Tensor) -> None:
+    """y[i] = x[i] at a segment head, else y[i-1]*x[i]; written into `y`.  Returns None.
+
+    Reference: cuda_kernel/grouped_cumprod_forward.cu:6-24, called at gs_model.py:551.
+    """
+    _scan("gcp_cumprod_fwd_f32", x, key, y)
+
+
+def grouped_cumsum_forward(x: torch.Tensor, key: torch.Tensor, y: torch.Tensor) -> None:
+    """Segmented inclusive sum, same contract.  Reference: grouped_cumsum_forward.cu:6-24 (gs_model.py:553)."""
+    _scan("gcp_cumsum_fwd_f32", x, key, y)
+
+
+def grouped_cumprod_backward(param: torch.Tensor, param_cumprod: torch.Tensor, grad_out: torch.Tensor,
+                             inv: torch.Tensor, grad_in: torch.Tensor, inv_len: torch.Tensor) -> None:
+    """grad_in[i] = dL/dparam[i] for L = sum grad_out*cumprod; written into `grad_in`.
+
+    Reference: cuda_kernel/grouped_cumprod_backward.cu:43-65 (cuda_test.py:29).  `inv` are dense
+    segment ids, `inv_len` the exclusive end offset of each segment (cuda_test.py:27).
+    """
+    _check(param, "param", torch.float32)
+    n = param.numel()
+    dev = param.device
+    _check(param_cumprod, "param_cumprod", torch.float32, n, dev)
+    _check(grad_out, "grad_out", torch.float32, n, dev)
+    _check(inv, "inv", torch.int32, n, dev)
+    _check(grad_in, "grad_in", torch.float32, n, dev)
+    _check(inv_len, "inv_len", torch.int32, None, dev)
+    if n == 0:
+        return
+    with torch.cuda.device(dev):
+        ws, stream = _workspace(dev, n)
+        L = _lib.lib()
+        _lib.check(L.gcp_cumprod_bwd_f32(param.data_ptr(), param_cumprod.data_ptr(), grad_out.data_ptr(),
+                                         inv.data_ptr(), inv_len.data_ptr(), grad_in.data_ptr(), n,
+                                         inv_len.numel(), ws.data_ptr(), ws.numel(), stream),
+                   "gcp_cumprod_bwd_f32")
+
+
+def validate_segments(inv: torch.Tensor, inv_len: torch.Tensor) -> int:
+    """Number of violations of the (inv, inv_len) layout contract; 0 means consistent.  Synchronises."""
+    import ctypes
+
+    _check(inv, "inv", torch.int32)
+    _check(inv_len, "inv_len", torch.int32, None, inv.device)
+    with torch.cuda.device(inv.device):
+        ws, stream = _workspace(inv.device, 0)
+        out = ctypes.c_int64(0)
+        _lib.check(_lib.lib().gcp_validate_segments(inv.data_ptr(), inv_len.data_ptr(), inv.numel(),
+                                                    inv_len.numel(), ws.data_ptr(), ws.numel(), stream,
+                                                    ctypes.byref(out)), "gcp_validate_segments")
+    return int(out.value)
+
+
+def workspace_status(device=None) -> int:
+    """Synchronise the current stream and return the sticky watchdog status (0 = OK)."""
+    import ctypes
+
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        ws, stream = _workspace(device, 0)
+        st = ctypes.c_int(0)
+        _lib.check(_lib.lib().gcp_workspace_status(ws.data_ptr(), stream, ctypes.byref(st)), "gcp_workspace_status")
+    return int(st.value)
+
+
+def set_variant(op: str, variant: int) -> None:
+    """Tuning hook: op in {'fwd','bwd'}; variant -1 restores the default."""
+    _lib.check(_lib.lib().gcp_set_variant(0 if op == "fwd" else 1, int(variant)), "gcp_set_variant")
+
+
+def variants(op: str) -> list:
+    L = _lib.lib()
+    o = 0 if op == "fwd" else 1
+    return [L.gcp_variant_name(o, i).decode() for i in range(L.gcp_num_variants(o))]
+
+
+def last_launch_count() -> int:
+    return int(_lib.lib().gcp_last_launch_count())

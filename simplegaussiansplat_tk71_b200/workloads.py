@@ -1,0 +1,167 @@
+"""Synthetic element lists for the compositing scan (BASELINE.json configs).
+
+An *element* is one Gaussian x pixel pair after box expansion; a *segment* is the
+depth-sorted list of elements of one pixel (reference: gs_model.py:544-566).  The
+generators below produce exactly what the reference hands to its ops at
+gs_model.py:551/:553 and cuda_test.py:23/:29:
+
+  x        f32[N]  "anti opacity" 1 - o*g  (gs_model.py:533-535)
+  key      i32[N]  pixel key y*10000 + x   (gs_model.py:538-541), sorted, equal inside a segment
+  inv      i32[N]  dense segment id 0..K-1 (cuda_test.py:21)
+  seg_end  i32[K]  exclusive end offset of each segment (cuda_test.py:27)
+  grad_out f32[N]  upstream gradient
+
+Segment lengths come from numpy (K values); per-element values from a seeded torch
+generator on the target device, so the 4K config never has to cross PCIe.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+# fit of the bundled opacity.pt logits
+OPACITY_LOGIT_MEAN = 1.735
+OPACITY_LOGIT_STD = 1.432
+
+
+@dataclass
+class ElementList:
+    name: str
+    x: torch.Tensor
+    key: torch.Tensor
+    inv: torch.Tensor
+    seg_end: torch.Tensor
+    grad_out: torch.Tensor
+    width: int
+    height: int
+
+    @property
+    def n(self) -> int:
+        return int(self.x.numel())
+
+    @property
+    def k(self) -> int:
+        return int(self.seg_end.numel())
+
+    def to(self, device) -> "ElementList":
+        return ElementList(self.name, *(t.to(device) for t in
+                                        (self.x, self.key, self.inv, self.seg_end, self.grad_out)),
+                           self.width, self.height)
+
+
+def lengths_c1(n: int = 1 << 20, k: int = 1 << 16, seed: int = 0) -> np.ndarray:
+    """C1: lognormal(ln 8, 1.0) scaled to sum n, floored, min 1, remainder +1 over the first segments."""
+    rng = np.random.default_rng(seed)
+    raw = rng.lognormal(math.log(8.0), 1.0, k)
+    L = np.maximum(1, np.floor(raw * (n / raw.sum()))).astype(np.int64)
+    diff = n - int(L.sum())
+    if diff > 0:
+        q, r = divmod(diff, k)
+        L += q
+        L[:r] += 1
+    elif diff < 0:
+        # take the excess back from the longest segments, never below 1
+        order = np.argsort(-L)
+        i = 0
+        while diff < 0:
+            j = order[i % k]
+            if L[j] > 1:
+                L[j] -= 1
+                diff += 1
+            i += 1
+    assert int(L.sum()) == n and L.min() >= 1
+    return L
+
+
+def lengths_lognormal(k: int, median: float, seed: int) -> np.ndarray:
+    """C3/C4 body: L = max(1, round(lognormal(ln median, 1.0)))."""
+    rng = np.random.default_rng(seed)
+    return np.maximum(1, np.rint(rng.lognormal(math.log(median), 1.0, k))).astype(np.int64)
+
+
+def lengths_c4(k: int, seed: int = 2160, deep: int = 512,
+               deep_lo: int = 8192, deep_hi: int = 262144):
+    """C4: lognormal(ln 30) body plus `deep` segments U[deep_lo, deep_hi] at rng-chosen pixels."""
+    rng = np.random.default_rng(seed)
+    L = np.maximum(1, np.rint(rng.lognormal(math.log(30.0), 1.0, k))).astype(np.int64)
+    pos = rng.choice(k, size=min(deep, k), replace=False)
+    L[pos] = rng.integers(deep_lo, deep_hi + 1, size=pos.size)
+    is_deep = np.zeros(k, dtype=bool)
+    is_deep[pos] = True
+    return L, is_deep
+
+
+def pixel_keys(k: int, width: int) -> np.ndarray:
+    """key = y*10000 + x for the k-th pixel in row-major order (gs_model.py:541)."""
+    p = np.arange(k, dtype=np.int64)
+    return ((p // width) * 10000 + (p % width)).astype(np.int32)
+
+
+def build(name: str, lengths: np.ndarray, width: int, height: int, seed: int,
+          device="cpu", alpha_scale_per_seg: np.ndarray | None = None,
+          zero_frac: float = 0.0) -> ElementList:
+    """Expand per-segment lengths into the five op inputs on `device`."""
+    k = int(lengths.shape[0])
+    n = int(lengths.sum())
+    assert n < 2 ** 31, "reference ops index with int32 (grouped_cumprod_backward.cu:52)"
+    dev = torch.device(device)
+    L = torch.from_numpy(lengths).to(dev)
+    seg_end64 = torch.cumsum(L, 0)
+    inv = torch.repeat_interleave(torch.arange(k, dtype=torch.int32, device=dev), L,
+                                  output_size=n)
+    pk = torch.from_numpy(pixel_keys(k, width)).to(dev)
+    key = pk[inv.long()] if k > 0 else torch.empty(0, dtype=torch.int32, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    logit = torch.empty(n, dtype=torch.float32, device=dev).normal_(
+        OPACITY_LOGIT_MEAN, OPACITY_LOGIT_STD, generator=gen)
+    o = torch.sigmoid(logit)
+    del logit
+    u = torch.empty(n, dtype=torch.float32, device=dev).uniform_(0.0, 1.0, generator=gen)
+    alpha = o * torch.exp(-4.5 * u)
+    del o, u
+    if alpha_scale_per_seg is not None:
+        sc = torch.from_numpy(alpha_scale_per_seg.astype(np.float32)).to(dev)
+        alpha = alpha * sc[inv.long()]
+    x = (1.0 - alpha).contiguous()
+    del alpha
+    if zero_frac > 0.0 and n > 0:
+        m = torch.empty(n, dtype=torch.float32, device=dev).uniform_(0.0, 1.0, generator=gen) < zero_frac
+        x[m] = 0.0
+    grad_out = torch.empty(n, dtype=torch.float32, device=dev).normal_(0.0, 1.0, generator=gen)
+    return ElementList(name, x, key.contiguous(), inv.contiguous(),
+                       seg_end64.to(torch.int32).contiguous(), grad_out, width, height)
+
+
+def c1(device="cpu", zeros: bool = False) -> ElementList:
+    """BASELINE.json configs[0]: 1 Mi elements / 64 Ki heavy-tailed segments."""
+    L = lengths_c1()
+    return build("C1 1Mi/64Ki lognormal(ln8,1)", L, 256, 256, 0, device,
+                 zero_frac=1e-5 if zeros else 0.0)
+
+
+def c3(device="cpu", view: int = 0, scale: float = 1.0) -> ElementList:
+    """BASELINE.json configs[2], scan-only route: 1920x1080 pixels, lognormal(ln 20, 1) lengths.
+
+    `scale` < 1 shrinks the pixel grid (rows) for CPU-sized parity cases; `view` shifts the seed
+    (C5: seed = 1080 + view id).
+    """
+    w, h = 1920, max(1, int(round(1080 * scale)))
+    L = lengths_lognormal(w * h, 20.0, 1080 + view)
+    return build(f"C3 {w}x{h} lognormal(ln20,1) view{view}", L, w, h, 1080 + view, device)
+
+
+def c4(device="cpu", scale: float = 1.0, deep: int = 512) -> ElementList:
+    """BASELINE.json configs[3], scan-only route: 3840x2160 + `deep` long segments (look-back path)."""
+    w, h = 3840, max(1, int(round(2160 * scale)))
+    L, is_deep = lengths_c4(w * h, 2160, deep=max(1, int(round(deep * scale))) if scale < 1 else deep)
+    sc = np.where(is_deep, 1e-3, 1.0)
+    return build(f"C4 {w}x{h} lognormal(ln30,1)+deep", L, w, h, 2160, device, alpha_scale_per_seg=sc)
+
+
+def algorithmic_bytes(n: int, k: int) -> dict:
+    """fwd 12 B/elem, bwd 16 B/elem + 4 B/segment."""
+    return {"fwd": 12 * n, "bwd": 16 * n + 4 * k, "fwd_bwd": 28 * n + 4 * k}

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/gcp_abi.h declares;
+argument validation that needs no device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gcp_abi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/gcp_abi.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared
+    assert L.gcp_abi_version() == 1
+
+
+def test_workspace_bytes_is_monotone_and_small():
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    prev = 0
+    for n in (0, 1, 1023, 1024, 1025, 1 << 20, 1 << 27, (1 << 31) - 1):
+        b = L.gcp_workspace_bytes(n)
+        assert b >= prev and b >= 256
+        prev = b
+    assert L.gcp_workspace_bytes((1 << 31) - 1) < 80 << 20  # 32 B per 1024 elements
+
+
+def test_argument_validation_without_device():
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    assert L.gcp_cumprod_fwd_f32(None, None, None, -1, None, 0, None) == -1
+    assert L.gcp_cumprod_fwd_f32(None, None, None, 0, None, 0, None) == 0     # n == 0 is a no-op
+    assert L.gcp_cumsum_fwd_f32(None, None, None, 5, None, 0, None) == -1    # null pointers
+    assert L.gcp_cumprod_bwd_f32(None, None, None, None, None, None, 0, 0, None, 0, None) == 0
+    assert L.gcp_cumprod_bwd_f32(None, None, None, None, None, None, 4, 1, None, 0, None) == -1
+    assert L.gcp_set_variant(0, 999) == -1 and L.gcp_set_variant(7, 0) == -1
+    assert L.gcp_set_variant(0, -1) == 0
+    assert L.gcp_num_variants(0) >= 2 and L.gcp_num_variants(1) >= 2
+    assert L.gcp_variant_name(0, 0).decode().startswith("ldg")
+    ws = (ctypes.c_char * 16)()
+    # workspace too small for n
+    fake = ctypes.cast(ws, ctypes.c_void_p)
+    assert L.gcp_cumprod_fwd_f32(fake, fake, fake, 100, fake, 16, None) == -2
+
+
+def test_ops_refuse_cpu_tensors_and_wrong_dtypes():
+    import torch
+
+    import grouped_cumprod as gc
+
+    x = torch.ones(4)
+    k = torch.zeros(4, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gc.grouped_cumprod_forward(x, k, torch.empty(4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gc.grouped_cumsum_forward(x, k, torch.empty(4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gc.grouped_cumprod_backward(x, x, x, k, torch.empty(4), torch.tensor([4], dtype=torch.int32))
+    assert sorted(n for n in dir(gc) if n.startswith("grouped_")) == [
+        "grouped_cumprod_backward", "grouped_cumprod_forward", "grouped_cumsum_forward"]
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "simplegaussiansplat_tk71_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "workloads.py" and False, f"{f} mentions the oracle"
+    assert "oracle" not in open(os.path.join(ROOT, "grouped_cumprod.py")).read()
