@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — segmented cumprod fwd+bwd throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c4]
+
+One *step* = one pass of the hot path over one view's element list: grouped_cumprod_forward
+followed by grouped_cumprod_backward (the reference ops of cuda_kernel.cpp:17-22) on synthetic
+data resident in HBM.  Default workload = BASELINE.json configs[2] ("synthetic 1080p, 1M Gaussians,
+heavy-tailed per-pixel segment lengths", scan-only route of SURVEY.md §8d: K = 1920*1080 segments,
+lognormal(ln 20, 1) lengths, N ~ 68 M elements) — the config the north star's 70 % target is quoted on.
+
+Prints ONE JSON line (rank 0).  value = Gelem/s fwd+bwd = (elements of all ranks) / max-over-ranks
+device time.  N > 1: one process per GPU (torchrun), each rank owns its own view (seed 1080+rank);
+views are independent (gs_model.py:402), so there is no data-path collective: scaling = weak.
+
+--impl reference: the CPU arm.  The reference has no CPU implementation of these ops,
+so this times the oracle's C/OpenMP port (oracle/gcp_oracle.c) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "segmented cumprod fwd+bwd throughput"
+UNIT = "Gelem/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic():
+    """dram bytes per launch from the committed ncu --set full capture, if any (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:  # noqa: BLE001
+            return {}
+    return {}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        except Exception:  # noqa: BLE001
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_workload(name: str, device, view: int):
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    if name == "c1":
+        return wl.c1(device)
+    if name == "c4":
+        return wl.c4(device)
+    return wl.c3(device, view=view)
+
+
+def cpu_port_run(e_cpu, min_seconds: float, max_reps: int):
+    """Time the oracle's C/OpenMP port (fwd + division-free bwd) on host tensors.  Returns (Gelem/s, reps, cores)."""
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    x, g, key = e_cpu.x.numpy(), e_cpu.grad_out.numpy(), e_cpu.key.numpy()
+    starts = orc.segment_starts(key)
+    y = np.empty_like(x)
+    gin = np.empty_like(x)
+    orc.fwd_bwd_f32_omp(x, g, starts, 0, y, gin)  # warm-up (page faults of the outputs)
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_all < min_seconds):
+        t0 = time.perf_counter()
+        orc.fwd_bwd_f32_omp(x, g, starts, 0, y, gin)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return x.shape[0] / med / 1e9, len(times), orc.max_threads(), med
+
+
+def run_reference_arm(args):
+    """CPU arm: rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import oracle as orc
+
+    orc.build()
+    torch.set_num_threads(os.cpu_count() or 1)
+    e = make_workload(args.workload, "cpu", 0)
+    x, g, key = e.x.numpy(), e.grad_out.numpy(), e.key.numpy()
+    import numpy as np
+
+    starts = orc.segment_starts(key)
+    y, gin = np.empty_like(x), np.empty_like(x)
+    for _ in range(max(1, args.warmup)):
+        orc.fwd_bwd_f32_omp(x, g, starts, 0, y, gin)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.fwd_bwd_f32_omp(x, g, starts, 0, y, gin)
+    dt = time.perf_counter() - t0
+    val = e.n * args.steps / dt / 1e9
+    cores = orc.max_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": e.name, "elements": e.n, "segments": e.k},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"whole view ({e.n} elements, {e.k} segments) per step, C/OpenMP port of the "
+                                   "ops (the reference has no CPU implementation; oracle/gcp_oracle.c)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c3", "c4"])
+    ap.add_argument("--variant-fwd", type=int, default=-1)
+    ap.add_argument("--variant-bwd", type=int, default=-1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="time every kernel variant (stderr table), then exit")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import grouped_cumprod as gc
+    from simplegaussiansplat_tk71_b200 import ops
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    e = make_workload(args.workload, device, view=rank)
+    n, k = e.n, e.k
+    y = torch.empty_like(e.x)
+    gin = torch.empty_like(e.x)
+    ops.set_variant("fwd", args.variant_fwd)
+    ops.set_variant("bwd", args.variant_bwd)
+
+    def step():
+        gc.grouped_cumprod_forward(e.x, e.key, y)
+        gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.sweep:
+        sweep(args, e, y, gin, gc, ops)
+        return
+
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = 0
+    gc.grouped_cumprod_forward(e.x, e.key, y)
+    launches_per_step += ops.last_launch_count()
+    gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
+    launches_per_step += ops.last_launch_count()
+    assert ops.workspace_status(device) == 0, "watchdog fired during warm-up"
+
+    # ---- timed region: K steps, CUDA events on the launching (current) stream ----
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        gc.grouped_cumprod_forward(e.x, e.key, y)
+        ev[2 * i + 1].record()
+        gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
+        ev[2 * i + 2].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    time.sleep(0.15)
+    clocks = sampler.stop()
+    fwd_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    bwd_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    assert ops.workspace_status(device) == 0, "watchdog fired during the timed region"
+
+    t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+    nn = torch.tensor([float(n)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+    max_ms = float(t.item())
+    total_elems = float(nn.item())
+    value = total_elems * args.steps / (max_ms * 1e-3) / 1e9
+
+    # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e_steps = max(1, args.e2e_steps)
+    hx, hk, hg, hi, hs = (t_.cpu().pin_memory() for t_ in (e.x, e.key, e.grad_out, e.inv, e.seg_end))
+    hy = torch.empty(n, dtype=torch.float32).pin_memory()
+    hgin = torch.empty(n, dtype=torch.float32).pin_memory()
+    dx, dk, dg, di, ds = (torch.empty_like(t_) for t_ in (e.x, e.key, e.grad_out, e.inv, e.seg_end))
+
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True)
+        dk.copy_(hk, non_blocking=True)
+        dg.copy_(hg, non_blocking=True)
+        di.copy_(hi, non_blocking=True)
+        ds.copy_(hs, non_blocking=True)
+        gc.grouped_cumprod_forward(dx, dk, y)
+        gc.grouped_cumprod_backward(dx, y, dg, di, gin, ds)
+        hy.copy_(y, non_blocking=True)
+        hgin.copy_(gin, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = total_elems * e2e_steps / (float(t2.item()) * 1e-3) / 1e9
+    h2d = int(sum(t_.numel() * t_.element_size() for t_ in (hx, hk, hg, hi, hs)))
+    d2h = int(hy.numel() * 4 + hgin.numel() * 4)
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle's C/OpenMP port on the same inputs ----
+    cpu = None
+    cpu_torch = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as orc
+
+            orc.build()
+            e_cpu = wl.ElementList(e.name, hx, hk, hi, hs, hg, e.width, e.height)
+            v, reps, cores, med = cpu_port_run(e_cpu, min_seconds=8.0, max_reps=12)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"whole view ({n} elements) x {reps} reps, median {med * 1e3:.1f} ms; C/OpenMP port "
+                             "of fwd + division-free bwd, parallel over segments (oracle/gcp_oracle.c)"}
+            # BASELINE.json configs[0]: pure-PyTorch CPU path on C1 (1 Mi elements / 64 Ki segments)
+            from oracle.torch_cpu_path import grouped_cumprod_fwd_bwd
+
+            torch.set_num_threads(os.cpu_count() or 1)
+            c1 = wl.c1("cpu")
+            _, _, plan = grouped_cumprod_fwd_bwd(c1.x, c1.key, c1.grad_out)
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                grouped_cumprod_fwd_bwd(c1.x, c1.key, c1.grad_out, plan)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            cpu_torch = {"value": c1.n / ts[2] / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": "C1 (1 Mi elements / 64 Ki segments), pure-PyTorch CPU path "
+                                                   f"(oracle/torch_cpu_path.py), median of 5 = {ts[2] * 1e3:.1f} ms"}
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        ab = wl.algorithmic_bytes(n, k)
+        traffic = _traffic()
+        bwd_gbs = ab["bwd"] / (bwd_ms * 1e-3) / 1e9
+        fwd_gbs = ab["fwd"] / (fwd_ms * 1e-3) / 1e9
+        both_gbs = ab["fwd_bwd"] / ((fwd_ms + bwd_ms) * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": e.name, "elements_per_gpu": n, "segments_per_gpu": k,
+                       "l2": "inputs exceed L2 (3 x %.0f MB read + %.0f MB written per op)" % (n * 4 / 1e6, n * 4 / 1e6),
+                       "variant_fwd": ops.variants("fwd")[args.variant_fwd] if args.variant_fwd >= 0 else "default",
+                       "variant_bwd": ops.variants("bwd")[args.variant_bwd] if args.variant_bwd >= 0 else "default",
+                       "parallelism": f"views x{world} (no data-path collective)"},
+            "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "roofline": {"bound": "hbm", "kernel": "grouped_cumprod_backward (k_bwd_*)", "achieved": bwd_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic.get("bwd"),
+                         "peak_source": peak_src, "algorithmic_bytes": ab["bwd"]},
+            "roofline_fwd": {"bound": "hbm", "kernel": "grouped_cumprod_forward (k_fwd_*)", "achieved": fwd_gbs,
+                             "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak, "traffic": traffic.get("fwd"),
+                             "algorithmic_bytes": ab["fwd"]},
+            "roofline_fwd_bwd": {"achieved": both_gbs, "peak": peak, "unit": "GB/s", "frac": both_gbs / peak,
+                                 "frac_of_nominal_8TBs": both_gbs / 8000.0},
+            "cpu_baseline": cpu, "cpu_baseline_torch_c1": cpu_torch,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep(args, e, y, gin, gc, ops):
+    """Times every variant of both kernels on the resident workload; prints a table to stderr and JSON to stdout."""
+    import torch
+
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    ab = wl.algorithmic_bytes(e.n, e.k)
+    peak, _ = _peaks()
+    res = {"workload": e.name, "n": e.n, "fwd": [], "bwd": []}
+    gc.grouped_cumprod_forward(e.x, e.key, y)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / args.steps
+
+    for v, name in enumerate(ops.variants("fwd")):
+        ops.set_variant("fwd", v)
+        ms = timeit(lambda: gc.grouped_cumprod_forward(e.x, e.key, y))
+        st = ops.workspace_status()
+        gbs = ab["fwd"] / ms / 1e6
+        res["fwd"].append({"variant": v, "name": name, "ms": ms, "GBs": gbs, "frac": gbs / peak, "status": st})
+        print(f"fwd v{v} {name:45s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}", file=sys.stderr)
+    ops.set_variant("fwd", -1)
+    for v, name in enumerate(ops.variants("bwd")):
+        ops.set_variant("bwd", v)
+        ms = timeit(lambda: gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end))
+        st = ops.workspace_status()
+        gbs = ab["bwd"] / ms / 1e6
+        res["bwd"].append({"variant": v, "name": name, "ms": ms, "GBs": gbs, "frac": gbs / peak, "status": st})
+        print(f"bwd v{v} {name:45s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}", file=sys.stderr)
+    ops.set_variant("bwd", -1)
+    # a plain device copy of the same byte volume as one forward op (sanity ceiling)
+    src = torch.empty(e.n * 3 // 2, dtype=torch.float32, device=e.x.device)
+    dst = torch.empty_like(src)
+    ms = timeit(lambda: dst.copy_(src))
+    res["copy"] = {"ms": ms, "GBs": src.numel() * 8 / ms / 1e6}
+    print(f"torch copy_ {src.numel() * 8 / 1e6:.0f} MB r+w: {ms:.4f} ms {res['copy']['GBs']:.1f} GB/s", file=sys.stderr)
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,303 @@
+"""-m gpu: parity of the CUDA path (through the drop-in `grouped_cumprod` module -> C ABI) against the
+fp64 oracle, the golden vectors, and the reference's own CUDA ops (oracle/_ref) on identical inputs.
+
+Tolerance (BASELINE.json north_star): |got - fp64| <= 1e-6 + 1e-5*|fp64|; integers bit-exact.
+Every kernel variant is exercised, including the look-back across tiles, unaligned base pointers,
+ragged tails, empty inputs and exact zeros.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_close, dev, reference_ops, run_bwd, run_fwd, seg_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+def _variants(op):
+    from simplegaussiansplat_tk71_b200 import ops
+
+    return list(range(len(ops.variants(op))))
+
+
+FWD_VARIANTS = list(range(8))
+BWD_VARIANTS = list(range(8))
+
+
+def _values(n, rng, zeros=0):
+    a = 1.0 / (1.0 + np.exp(-rng.normal(1.735, 1.432, n)))
+    x = (1.0 - a * np.exp(-4.5 * rng.uniform(size=n))).astype(np.float32)
+    if zeros:
+        x[rng.integers(0, n, zeros)] = 0.0
+    return x
+
+
+def test_kat1_through_dropin_module(golden, oracle):
+    import grouped_cumprod as gc
+
+    k = golden["kat1"]
+    param = torch.tensor(k["x"], device="cuda", dtype=torch.float32)
+    grad = torch.clone(param)
+    index = torch.tensor(k["key"], device="cuda", dtype=torch.int32)
+    param_cumprod = torch.zeros_like(param)
+    assert gc.grouped_cumprod_forward(param, index, param_cumprod) is None   # cuda_test.py:23
+    out = torch.zeros_like(param)
+    index_len = torch.tensor(k["seg_end"], device="cuda", dtype=torch.int32)
+    assert gc.grouped_cumprod_backward(param, param_cumprod, grad, index, out, index_len) is None  # :29
+    assert_close(param_cumprod.cpu().numpy(), k["y"], "KAT1 fwd")
+    assert_close(out.cpu().numpy(), k["grad_in"], "KAT1 bwd")
+
+
+def test_kat2_through_dropin_module(golden):
+    import grouped_cumprod as gc
+
+    k = golden["kat2"]
+    A = torch.tensor(k["A"], dtype=torch.float32, device="cuda")
+    G = torch.tensor(k["G"], device="cuda")
+    key = (G[:, 0] * (int(G.max()) + 1) + G[:, 1]).to(torch.int32)
+    skey, index = torch.sort(key, stable=True)
+    out = torch.zeros_like(A)
+    gc.grouped_cumprod_forward(A[index], skey, out)
+    y = out[torch.argsort(index)]
+    assert y.cpu().tolist() == [float(v) for v in k["expected"]]
+
+
+@pytest.mark.parametrize("variant", FWD_VARIANTS)
+@pytest.mark.parametrize("op", ["mul", "add"])
+def test_forward_sizes_and_layouts(oracle, variant, op):
+    rng = np.random.default_rng(100 + variant)
+    ofn = oracle.cumprod_fwd if op == "mul" else oracle.cumsum_fwd
+    sizes = [1, 2, 3, 4, 5, 31, 127, 128, 129, 1023, 1024, 1025, 2047, 2049, 4095, 4096, 4097, 8191, 8193,
+             12289, 40000, 100003]
+    for n in sizes:
+        x = _values(n, rng) if op == "mul" else rng.uniform(0.0, 2.0, n).astype(np.float32)
+        for layout in ("random", "one", "singletons", "runs"):
+            if layout == "random":
+                L = np.maximum(1, np.rint(rng.lognormal(np.log(9), 1.0, n))).astype(np.int64)
+                key = np.repeat(np.arange(len(L)), L)[:n]
+                key = (key * 7 + 3).astype(np.int32)
+            elif layout == "one":
+                key = np.full(n, 42, np.int32)
+            elif layout == "singletons":
+                key = np.arange(n, dtype=np.int32)
+            else:  # unsorted keys with repeated runs: adjacent-run semantics
+                key = np.repeat(rng.integers(0, 3, n), rng.integers(1, 6, n))[:n].astype(np.int32)
+            got = run_fwd(op, x, key, variant)
+            assert_close(got, ofn(x, key), f"fwd {op} v{variant} n={n} {layout}")
+
+
+@pytest.mark.parametrize("variant", FWD_VARIANTS)
+def test_forward_boundaries_on_tile_edges_and_long_segments(oracle, variant):
+    rng = np.random.default_rng(7)
+    # segments that start/end exactly on 128 / 1024 / 2048 / 4096 / 8192 element edges, and around them
+    for seglen in (128, 512, 1024, 2048, 4096, 8192, 4095, 4097, 2049):
+        n = seglen * 9 + 5
+        key = (np.arange(n) // seglen).astype(np.int32)
+        x = (1.0 - 1e-3 * rng.uniform(size=n)).astype(np.float32)
+        assert_close(run_fwd("mul", x, key, variant), oracle.cumprod_fwd(x, key), f"edge {seglen} v{variant}")
+        xs = rng.uniform(0, 1, n).astype(np.float32)
+        assert_close(run_fwd("add", xs, key, variant), oracle.cumsum_fwd(xs, key), f"edge add {seglen}")
+    # one giant segment spanning > 64 tiles (multi-round look-back) with a short prologue and epilogue
+    n = 700_001
+    key = np.zeros(n, np.int32)
+    key[:300] = -5
+    key[-7777:] = 9
+    x = (1.0 - 2e-5 * rng.uniform(size=n)).astype(np.float32)
+    assert_close(run_fwd("mul", x, key, variant), oracle.cumprod_fwd(x, key), f"giant v{variant}")
+    xs = rng.uniform(0, 1, n).astype(np.float32)
+    assert_close(run_fwd("add", xs, key, variant), oracle.cumsum_fwd(xs, key), f"giant add v{variant}")
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+def test_forward_unaligned_slices_and_zeros(oracle, variant):
+    rng = np.random.default_rng(11)
+    n = 50_001
+    L = np.maximum(1, np.rint(rng.lognormal(np.log(16), 1.0, n))).astype(np.int64)
+    key = np.repeat(np.arange(len(L)), L)[:n].astype(np.int32)
+    x = _values(n, rng, zeros=25)
+    ref = oracle.cumprod_fwd(x, key)
+    for off in [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 2, 3), (3, 3, 3), (4, 4, 4)]:
+        assert_close(run_fwd("mul", x, key, variant, off), ref, f"unaligned {off} v{variant}")
+    # exact zeros propagate exactly
+    got = run_fwd("mul", x, key, variant)
+    assert np.array_equal(got == 0.0, ref == 0.0)
+
+
+def test_empty_inputs_are_noops():
+    import grouped_cumprod as gc
+
+    e = torch.empty(0, device="cuda")
+    ei = torch.empty(0, device="cuda", dtype=torch.int32)
+    gc.grouped_cumprod_forward(e, ei, torch.empty(0, device="cuda"))
+    gc.grouped_cumsum_forward(e, ei, torch.empty(0, device="cuda"))
+    gc.grouped_cumprod_backward(e, e, e, ei, torch.empty(0, device="cuda"), ei)
+    torch.cuda.synchronize()
+
+
+def test_dtype_and_shape_errors_match_reference_behaviour():
+    import grouped_cumprod as gc
+
+    x = torch.ones(8, device="cuda")
+    k = torch.zeros(8, device="cuda", dtype=torch.int32)
+    with pytest.raises(RuntimeError):  # reference: data_ptr<int>() on an int64 tensor raises
+        gc.grouped_cumprod_forward(x, k.long(), torch.empty_like(x))
+    with pytest.raises(RuntimeError):
+        gc.grouped_cumprod_forward(x.double(), k, torch.empty_like(x))
+    with pytest.raises(RuntimeError):
+        gc.grouped_cumprod_forward(x, k[:4], torch.empty_like(x))
+
+
+@pytest.mark.parametrize("variant", BWD_VARIANTS)
+def test_backward_sizes_and_layouts(oracle, variant):
+    rng = np.random.default_rng(200 + variant)
+    sizes = [1, 2, 3, 5, 127, 128, 129, 1023, 1024, 1025, 2047, 2049, 4095, 4096, 4097, 8193, 12289, 40000,
+             100003]
+    for n in sizes:
+        for layout in ("random", "one", "singletons"):
+            if layout == "random":
+                L = np.maximum(1, np.rint(rng.lognormal(np.log(9), 1.0, n))).astype(np.int64)
+                L = L[: np.searchsorted(np.cumsum(L), n) + 1]
+                L[-1] -= L.sum() - n
+            elif layout == "one":
+                L = np.array([n])
+            else:
+                L = np.ones(n, np.int64)
+            inv, seg_end = seg_arrays(L)
+            x = _values(n, rng)
+            g = rng.uniform(0.0, 1.0, n).astype(np.float32)
+            y = oracle.cumprod_fwd(x, inv, np.float32)
+            got = run_bwd(x, y, g, inv, seg_end, variant)
+            assert_close(got, oracle.cumprod_bwd_exact(x, g, inv), f"bwd v{variant} n={n} {layout}")
+
+
+@pytest.mark.parametrize("variant", BWD_VARIANTS)
+def test_backward_tile_edges_long_segments_signed_grads(oracle, variant):
+    rng = np.random.default_rng(13)
+    for seglen in (128, 1024, 2048, 4096, 8192, 4095, 4097):
+        n = seglen * 7 + 3
+        L = [seglen] * 7 + [3]
+        inv, seg_end = seg_arrays(L)
+        x = (1.0 - 1e-3 * rng.uniform(size=n)).astype(np.float32)
+        g = rng.normal(size=n).astype(np.float32)
+        y = oracle.cumprod_fwd(x, inv, np.float32)
+        got = run_bwd(x, y, g, inv, seg_end, variant)
+        # signed g: the honest bound scales with the condition of the sum, i.e. the gradient for |g|
+        scale = oracle.cumprod_bwd_exact(x, np.abs(g), inv)
+        assert_close(got, oracle.cumprod_bwd_exact(x, g, inv), f"bwd edge {seglen} v{variant}", scale=scale)
+    # giant segment (look-ahead over > 64 tiles) between a short prologue and epilogue
+    L = [300, 700_001 - 300 - 7777, 7777]
+    n = sum(L)
+    inv, seg_end = seg_arrays(L)
+    x = (1.0 - 2e-5 * rng.uniform(size=n)).astype(np.float32)
+    g = rng.uniform(0, 1, n).astype(np.float32)
+    y = oracle.cumprod_fwd(x, inv, np.float32)
+    assert_close(run_bwd(x, y, g, inv, seg_end, variant), oracle.cumprod_bwd_exact(x, g, inv),
+                 f"bwd giant v{variant}", rtol=3e-5)
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+def test_backward_exact_at_zeros_and_unaligned(oracle, variant):
+    rng = np.random.default_rng(17)
+    n = 60_001
+    L = np.maximum(1, np.rint(rng.lognormal(np.log(16), 1.0, n))).astype(np.int64)
+    L = L[: np.searchsorted(np.cumsum(L), n) + 1]
+    L[-1] -= L.sum() - n
+    inv, seg_end = seg_arrays(L)
+    x = _values(n, rng, zeros=40)
+    g = rng.uniform(0.1, 1.0, n).astype(np.float32)
+    y = oracle.cumprod_fwd(x, inv, np.float32)
+    exact = oracle.cumprod_bwd_exact(x, g, inv)
+    for off in (0, 1, 2, 3):
+        assert_close(run_bwd(x, y, g, inv, seg_end, variant, off), exact, f"bwd zeros off={off} v{variant}")
+    # SURVEY.md §3.6-4 example: reference formula gives [1,0,0], the true gradient is [1,.75,0]
+    got = run_bwd(np.float32([.5, 0, .5]), np.float32([.5, 0, 0]), np.float32([1, 1, 1]), np.int32([0, 0, 0]),
+                  np.int32([3]), variant)
+    assert np.allclose(got, [1.0, 0.75, 0.0])
+
+
+def test_inf_nan_do_not_leak_across_segments(oracle):
+    n = 9000
+    inv, seg_end = seg_arrays([3000, 3000, 3000])
+    x = np.full(n, 0.999, np.float32)
+    g = np.ones(n, np.float32)
+    g[4000] = np.inf   # only segment 1 may be affected
+    y = oracle.cumprod_fwd(x, inv, np.float32)
+    got = run_bwd(x, y, g, inv, seg_end)
+    assert np.all(np.isfinite(got[:3000])) and np.all(np.isfinite(got[6000:]))
+    xf = x.copy()
+    xf[4000] = np.nan
+    gotf = run_fwd("mul", xf, inv)
+    assert np.all(np.isfinite(gotf[:3000])) and np.all(np.isfinite(gotf[6000:]))
+
+
+def test_against_reference_cuda_ops_on_identical_inputs(oracle):
+    ref = reference_ops()
+    if ref is None:
+        pytest.skip("oracle/_ref/grouped_cumprod_ref.so not built")
+    import grouped_cumprod as gc
+
+    rng = np.random.default_rng(23)
+    n = 300_000
+    L = np.maximum(1, np.rint(rng.lognormal(np.log(8), 1.0, n))).astype(np.int64)
+    L = L[: np.searchsorted(np.cumsum(L), n) + 1]
+    L[-1] -= L.sum() - n
+    inv_np, seg_end_np = seg_arrays(L)
+    x = dev(_values(n, rng))                 # zero-free: the two backward formulas agree there
+    g = dev(rng.uniform(0, 1, n).astype(np.float32))
+    inv, seg_end = dev(inv_np), dev(seg_end_np)
+    y_ref, y_our = torch.zeros_like(x), torch.zeros_like(x)
+    ref.grouped_cumprod_forward(x, inv, y_ref)
+    gc.grouped_cumprod_forward(x, inv, y_our)
+    s_ref, s_our = torch.zeros_like(x), torch.zeros_like(x)
+    ref.grouped_cumsum_forward(g, inv, s_ref)
+    gc.grouped_cumsum_forward(g, inv, s_our)
+    b_ref, b_our = torch.zeros_like(x), torch.zeros_like(x)
+    ref.grouped_cumprod_backward(x, y_ref, g, inv, b_ref, seg_end)
+    gc.grouped_cumprod_backward(x, y_our, g, inv, b_our, seg_end)
+    torch.cuda.synchronize()
+    assert_close(y_our.cpu().numpy(), y_ref.cpu().numpy(), "fwd ours vs reference op")
+    assert_close(s_our.cpu().numpy(), s_ref.cpu().numpy(), "cumsum ours vs reference op")
+    assert_close(b_our.cpu().numpy(), b_ref.cpu().numpy(), "bwd ours vs reference op", rtol=1e-4, atol=1e-5)
+    # and the reference ops themselves against the oracle (pins the oracle to the real reference)
+    xn, gn = x.cpu().numpy(), g.cpu().numpy()
+    assert_close(y_ref.cpu().numpy(), oracle.cumprod_fwd(xn, inv_np), "reference fwd vs oracle")
+    assert_close(s_ref.cpu().numpy(), oracle.cumsum_fwd(gn, inv_np), "reference cumsum vs oracle")
+    assert_close(b_ref.cpu().numpy(), oracle.cumprod_bwd_ref(xn, y_ref.cpu().numpy(), gn, inv_np, seg_end_np),
+                 "reference bwd vs oracle(ref formula)", rtol=1e-4, atol=1e-5)
+
+
+def test_validate_segments_bit_exact_contract():
+    from simplegaussiansplat_tk71_b200 import ops
+
+    inv_np, seg_end_np = seg_arrays([3, 1, 5000, 2, 9000])
+    inv, seg_end = dev(inv_np), dev(seg_end_np)
+    assert ops.validate_segments(inv, seg_end) == 0
+    bad = seg_end.clone()
+    bad[2] += 1
+    assert ops.validate_segments(inv, bad) > 0
+    inv2 = inv.clone()
+    inv2[10] = 4
+    assert ops.validate_segments(inv2, seg_end) > 0
+
+
+def test_autograd_function_matches_torch_autograd():
+    from simplegaussiansplat_tk71_b200 import grouped_cumprod as gcp_fn
+
+    rng = np.random.default_rng(29)
+    L = rng.integers(1, 50, size=400)
+    inv_np, seg_end_np = seg_arrays(L)
+    n = len(inv_np)
+    x = dev(_values(n, rng)).requires_grad_(True)
+    w = dev(rng.uniform(0, 1, n).astype(np.float32))
+    y = gcp_fn(x, dev(inv_np), dev(seg_end_np))
+    (y * w).sum().backward()
+    # plain torch fp64 reference: per-segment cumprod with autograd
+    xr = x.detach().double().cpu().requires_grad_(True)
+    parts, s = [], 0
+    for l in L:
+        parts.append(torch.cumprod(xr[s:s + l], 0))
+        s += l
+    yr = torch.cat(parts)
+    (yr * w.double().cpu()).sum().backward()
+    assert_close(y.detach().cpu().numpy(), yr.detach().numpy(), "autograd fwd")
+    assert_close(x.grad.cpu().numpy(), xr.grad.numpy(), "autograd bwd")
