@@ -402,22 +402,33 @@ def sweep(args, e, y, gin, gc, ops):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / args.steps
 
-    for v, name in enumerate(ops.variants("fwd")):
-        ops.set_variant("fwd", v)
-        ms = timeit(lambda: gc.grouped_cumprod_forward(e.x, e.key, y))
-        st = ops.workspace_status()
-        gbs = ab["fwd"] / ms / 1e6
-        res["fwd"].append({"variant": v, "name": name, "ms": ms, "GBs": gbs, "frac": gbs / peak, "status": st})
-        print(f"fwd v{v} {name:45s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}", file=sys.stderr)
-    ops.set_variant("fwd", -1)
-    for v, name in enumerate(ops.variants("bwd")):
-        ops.set_variant("bwd", v)
-        ms = timeit(lambda: gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end))
-        st = ops.workspace_status()
-        gbs = ab["bwd"] / ms / 1e6
-        res["bwd"].append({"variant": v, "name": name, "ms": ms, "GBs": gbs, "frac": gbs / peak, "status": st})
-        print(f"bwd v{v} {name:45s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}", file=sys.stderr)
-    ops.set_variant("bwd", -1)
+    for halo in (1, 0):
+        ops.set_option(0, halo)
+        for v, name in enumerate(ops.variants("fwd")):
+            if halo == 0 and name.startswith("ldg"):
+                continue
+            ops.set_variant("fwd", v)
+            ms = timeit(lambda: gc.grouped_cumprod_forward(e.x, e.key, y))
+            st = ops.workspace_status()
+            gbs = ab["fwd"] / ms / 1e6
+            res["fwd"].append({"variant": v, "name": name, "halo": halo, "ms": ms, "GBs": gbs, "frac": gbs / peak,
+                               "status": st})
+            print(f"fwd v{v} halo={halo} {name:42s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}",
+                  file=sys.stderr)
+        ops.set_variant("fwd", -1)
+        for v, name in enumerate(ops.variants("bwd")):
+            if halo == 0 and name.startswith("ldg"):
+                continue
+            ops.set_variant("bwd", v)
+            ms = timeit(lambda: gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end))
+            st = ops.workspace_status()
+            gbs = ab["bwd"] / ms / 1e6
+            res["bwd"].append({"variant": v, "name": name, "halo": halo, "ms": ms, "GBs": gbs, "frac": gbs / peak,
+                               "status": st})
+            print(f"bwd v{v} halo={halo} {name:42s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}",
+                  file=sys.stderr)
+        ops.set_variant("bwd", -1)
+    ops.set_option(0, 1)
     # a plain device copy of the same byte volume as one forward op (sanity ceiling)
     src = torch.empty(e.n * 3 // 2, dtype=torch.float32, device=e.x.device)
     dst = torch.empty_like(src)

@@ -110,6 +110,11 @@ int gcp_validate_segments(const int32_t *inv, const int32_t *seg_end, int64_t n,
  * Returns GCP_ERR_INVALID_ARG for unknown values.
  */
 int gcp_set_variant(int op, int variant);
+/* Tuning options.  option 0 (GCP_OPT_HALO): 1 (default) = the persistent kernels resolve each tile's
+ * cross-tile carry from the 128 elements beside the tile and touch the look-back descriptors only
+ * for segments longer than that; 0 = always use the decoupled look-back. */
+#define GCP_OPT_HALO 0
+int gcp_set_option(int option, int value);
 int gcp_num_variants(int op);
 const char *gcp_variant_name(int op, int variant);
 

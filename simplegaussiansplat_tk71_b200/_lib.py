@@ -24,7 +24,7 @@ ERRORS = {
 SYMBOLS = (
     "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status",
     "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
-    "gcp_set_variant", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
+    "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
 )
 
 
@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
     L.gcp_cumprod_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp, sz, vp]
     L.gcp_validate_segments.argtypes = [vp, vp, i64, i64, vp, sz, vp, ctypes.POINTER(i64)]
     L.gcp_set_variant.argtypes = [ci, ci]
+    L.gcp_set_option.argtypes = [ci, ci]
+    L.gcp_set_option.restype = ci
     L.gcp_num_variants.argtypes = [ci]
     L.gcp_variant_name.argtypes = [ci, ci]
     L.gcp_variant_name.restype = ctypes.c_char_p

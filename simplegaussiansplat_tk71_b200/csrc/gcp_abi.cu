@@ -16,6 +16,7 @@ using namespace gcp;
 
 thread_local int t_launches = 0;
 int g_variant[2] = {-1, -1};
+int g_option[4] = {1, 0, 0, 0};  // [0] = resolve tile carries from a 128-element halo (1) or always look back (0)
 
 struct DeviceInfo {
     bool init = false;
@@ -52,9 +53,11 @@ int check_ws(void *ws, size_t ws_bytes, int64_t n, Ws *out) {
     return GCP_OK;
 }
 
-// resident CTAs per SM for a persistent kernel, cached per (kernel, device)
-template <typename K>
-int persistent_ctas_per_sm(K kernel, int threads, size_t smem) {
+// resident CTAs per SM for a persistent kernel, cached per (kernel, device).  The kernel is a
+// non-type template parameter: distinct instantiations share one function-pointer TYPE, so a cache
+// keyed on the type alone would skip the shared-memory opt-in of all but the first of them.
+template <auto kernel>
+int persistent_ctas_per_sm(int threads, size_t smem) {
     static int cache[64];
     static bool have[64];
     const int d = current_device() & 63;
@@ -70,30 +73,49 @@ int persistent_ctas_per_sm(K kernel, int threads, size_t smem) {
 
 inline uint32_t tiles_for(int64_t n, int tile) { return static_cast<uint32_t>((n + tile - 1) / tile); }
 
+// K2 grid: one warp per tile, at most 4 CTAs of 8 warps per SM (grid-stride beyond that)
+inline unsigned fix_grid(uint32_t nt) {
+    unsigned blocks = (nt + 7u) / 8u;
+    const unsigned cap = static_cast<unsigned>(sm_count()) * 4u;
+    if (blocks > cap) blocks = cap;
+    return blocks < 1u ? 1u : blocks;
+}
+
 // ------------------------------ forward ------------------------------------
+template <int OP>
+int launch_fwd_fix(float *y, int64_t n, uint32_t nt, int tile, Ws ws, cudaStream_t s) {
+    if (nt < 2u) return GCP_OK;  // tile 0 always resolves (its first element is a head)
+    k_fwd_fix<OP><<<fix_grid(nt), 256, 0, s>>>(y, n, nt, tile, ws.hdr, ws.desc);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
 template <int OP, int WARPS, int ROWS>
 int launch_fwd_ldg(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
     constexpr int TILE = WARPS * ROWS * 128;
     const uint32_t nt = tiles_for(n, TILE);
     const int in_vec = aligned16(x) && aligned16(key);
     const int y_vec = aligned16(y);
-    k_fwd_ldg<OP, WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, in_vec, y_vec);
+    k_fwd_ldg<OP, WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, in_vec, y_vec,
+                                                          g_option[0]);
     ++t_launches;
-    return static_cast<int>(cudaGetLastError());
+    const int rc = static_cast<int>(cudaGetLastError());
+    return rc != 0 ? rc : launch_fwd_fix<OP>(y, n, nt, TILE, ws, s);
 }
 
 template <int OP, int WARPS, int ROWS, int STAGES>
 int launch_fwd_tma(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
     using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
     const uint32_t nt = tiles_for(n, L::TILE);
-    auto kern = k_fwd_tma<OP, WARPS, ROWS, STAGES>;
+    constexpr auto kern = k_fwd_tma<OP, WARPS, ROWS, STAGES>;
     const int threads = (WARPS + 1) * 32;
-    const int per_sm = persistent_ctas_per_sm(kern, threads, L::BYTES);
+    const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, aligned16(y) ? 1 : 0);
+    kern<<<grid, threads, L::BYTES, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, aligned16(y) ? 1 : 0, g_option[0]);
     ++t_launches;
-    return static_cast<int>(cudaGetLastError());
+    const int rc = static_cast<int>(cudaGetLastError());
+    return rc != 0 ? rc : launch_fwd_fix<OP>(y, n, nt, L::TILE, ws, s);
 }
 
 constexpr int FWD_NUM_VARIANTS = 8;
@@ -131,6 +153,14 @@ int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *
 }
 
 // ------------------------------ backward -----------------------------------
+inline int launch_bwd_fix(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
+                          uint32_t nt, int tile, Ws ws, cudaStream_t s) {
+    if (nt < 2u) return GCP_OK;  // the last tile always resolves (nothing follows it)
+    k_bwd_fix<<<fix_grid(nt), 256, 0, s>>>(x, y, g, inv, gin, n, nt, tile, ws.hdr, ws.desc);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
 template <int WARPS, int ROWS>
 int launch_bwd_ldg(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
                    Ws ws, cudaStream_t s) {
@@ -138,32 +168,35 @@ int launch_bwd_ldg(const float *x, const float *y, const float *g, const int32_t
     const uint32_t nt = tiles_for(n, TILE);
     const int in_vec = aligned16(x) && aligned16(g) && aligned16(inv);
     k_bwd_ldg<WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, in_vec,
-                                                      aligned16(gin) ? 1 : 0);
+                                                      aligned16(gin) ? 1 : 0, g_option[0]);
     ++t_launches;
-    return static_cast<int>(cudaGetLastError());
+    const int rc = static_cast<int>(cudaGetLastError());
+    return rc != 0 ? rc : launch_bwd_fix(x, y, g, inv, gin, n, nt, TILE, ws, s);
 }
 
-template <int WARPS, int ROWS, int STAGES>
+template <int WARPS, int ROWS, int STAGES, int MINB>
 int launch_bwd_tma(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
                    Ws ws, cudaStream_t s) {
     using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
     const uint32_t nt = tiles_for(n, L::TILE);
-    auto kern = k_bwd_tma<WARPS, ROWS, STAGES>;
+    constexpr auto kern = k_bwd_tma<WARPS, ROWS, STAGES, MINB>;
     const int threads = (WARPS + 1) * 32;
-    const int per_sm = persistent_ctas_per_sm(kern, threads, L::BYTES);
+    const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, aligned16(gin) ? 1 : 0);
+    kern<<<grid, threads, L::BYTES, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, aligned16(gin) ? 1 : 0,
+                                         g_option[0]);
     ++t_launches;
-    return static_cast<int>(cudaGetLastError());
+    const int rc = static_cast<int>(cudaGetLastError());
+    return rc != 0 ? rc : launch_bwd_fix(x, y, g, inv, gin, n, nt, L::TILE, ws, s);
 }
 
 constexpr int BWD_NUM_VARIANTS = 8;
 const char *const kBwdNames[BWD_NUM_VARIANTS] = {
     "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
-    "tma_w8_r4_s2 (tile 4096, 96 KB ring)", "tma_w8_r2_s4 (tile 2048, 96 KB ring)",
-    "tma_w8_r2_s3 (tile 2048, 72 KB ring)", "tma_w8_r4_s4 (tile 4096, 192 KB ring)",
-    "tma_w4_r4_s4 (tile 2048, 160 thr)"};
+    "tma_w8_r4_s2 (tile 4096, 96 KB ring, 2 CTA/SM)", "tma_w8_r2_s4 (tile 2048, 96 KB ring, 2 CTA/SM)",
+    "tma_w8_r2_s3 (tile 2048, 72 KB ring, 3 CTA/SM)", "tma_w8_r4_s4 (tile 4096, 192 KB ring, 1 CTA/SM)",
+    "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)"};
 constexpr int BWD_DEFAULT = 0;
 
 }  // namespace
@@ -226,11 +259,11 @@ int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const
         case 0: return launch_bwd_ldg<8, 4>(x, y, gout, inv, gin, n, ws, s);
         case 1: return launch_bwd_ldg<8, 2>(x, y, gout, inv, gin, n, ws, s);
         case 2: return launch_bwd_ldg<4, 4>(x, y, gout, inv, gin, n, ws, s);
-        case 3: return launch_bwd_tma<8, 4, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 4: return launch_bwd_tma<8, 2, 4>(x, y, gout, inv, gin, n, ws, s);
-        case 5: return launch_bwd_tma<8, 2, 3>(x, y, gout, inv, gin, n, ws, s);
-        case 6: return launch_bwd_tma<8, 4, 4>(x, y, gout, inv, gin, n, ws, s);
-        case 7: return launch_bwd_tma<4, 4, 4>(x, y, gout, inv, gin, n, ws, s);
+        case 3: return launch_bwd_tma<8, 4, 2, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 4: return launch_bwd_tma<8, 2, 4, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 5: return launch_bwd_tma<8, 2, 3, 3>(x, y, gout, inv, gin, n, ws, s);
+        case 6: return launch_bwd_tma<8, 4, 4, 1>(x, y, gout, inv, gin, n, ws, s);
+        case 7: return launch_bwd_tma<16, 2, 2, 2>(x, y, gout, inv, gin, n, ws, s);
         default: return GCP_ERR_INVALID_ARG;
     }
 }
@@ -274,6 +307,12 @@ int gcp_set_variant(int op, int variant) {
     const int nv = op == 0 ? FWD_NUM_VARIANTS : BWD_NUM_VARIANTS;
     if (variant < -1 || variant >= nv) return GCP_ERR_INVALID_ARG;
     g_variant[op] = variant;
+    return GCP_OK;
+}
+
+int gcp_set_option(int option, int value) {
+    if (option < 0 || option >= 4) return GCP_ERR_INVALID_ARG;
+    g_option[option] = value;
     return GCP_OK;
 }
 

@@ -1,4 +1,4 @@
-// gcp_bwd.cuh — backward of the segmented cumprod, one pass, division-free.
+// gcp_bwd.cuh — backward of the segmented cumprod: one streaming pass, division-free, wait-free.
 //
 // Replaces grouped_cumprod_backward_kernel
 //   (/root/reference/cuda_kernel/grouped_cumprod_backward.cu:9-41, launcher :43-65),
@@ -9,16 +9,20 @@
 //   S_i = g_i + x_{i+1} * S_{i+1}               reverse recurrence (S = g at a tail)
 //
 // S is a reverse segmented scan of affine maps (a_i, b_i) = (tail ? 0 : x_{i+1}, g_i);
-// a tail's a = 0 is the segment reset.  Tiles are processed from the END of the
-// array (tile = num_tiles-1-ticket) so the cross-tile dependency of S always points
-// at an earlier ticket: the same decoupled look-back as the forward, mirrored.
-// E needs the opposite direction; inside a tile it is recomputed from x (no extra
-// traffic), and across the tile's left edge it is the forward output itself:
-// E(first element) = y[base-1] — ONE value of `param_cumprod` per tile, which the
-// reference op already receives as an argument.  So the pass reads x, grad_out, inv
-// (12 B/elem) and writes grad_in (4 B/elem): 16 B/elem, the algorithmic minimum.
+// a tail's a = 0 is the segment reset.  E needs the other direction: inside a tile it is
+// recomputed from x by the forward's segmented warp scan (no extra traffic), and across the
+// tile's left edge it is the forward output itself, E(first element) = y[base-1] — ONE value
+// of `param_cumprod` per tile, an argument the reference op already receives.  So the pass
+// reads x, grad_out, inv (12 B/elem) and writes grad_in (4 B/elem): 16 B/elem.
 //
-// Same striped-float4 layout and the same two kernel shapes as gcp_fwd.cuh.
+// Cross-tile carry of S, mirrored from gcp_fwd.cuh and equally wait-free:
+//   K1 (k_bwd_tma / k_bwd_ldg) resolves R = S(first element after the tile) from the HALO,
+//      the 128 elements after the tile.  Unresolved tiles store provisional values for
+//      their trailing run (the elements after the tile's last tail), publish a carry
+//      descriptor (TERM R | AGG (a,b)) and a fix-up request {needs, trail start}.
+//   K2 (k_bwd_fix) one warp per unresolved tile: walks forward over the complete
+//      descriptors to the nearest TERM / already-fixed tile and recomputes the trailing run
+//      (reads x, g and y there: E_i = y[i-1]).
 #pragma once
 #include "gcp_device.cuh"
 #include "gcp_fwd.cuh"
@@ -27,11 +31,13 @@ namespace gcp {
 
 template <int WARPS>
 struct BwdShared {
-    float wv[WARPS];  // forward product aggregates
+    float wv[WARPS];     // forward product aggregates
     uint32_t wf[WARPS];
-    float wa[WARPS];  // reverse affine aggregates
+    float wa[WARPS];     // reverse affine aggregates
     float wb[WARPS];
-    float r_next;     // S at the first element of the next tile (if the segment continues)
+    int32_t lt[WARPS];   // offset of the last tail inside the warp span (-1 if none)
+    uint32_t res;        // LDG kernel: halo result of warp 0
+    float rn;
     uint32_t tile;
 };
 
@@ -66,58 +72,57 @@ __device__ __forceinline__ void warp_affine_rscan_rows(const Affine (&agg)[ROWS]
     wagg = rs;
 }
 
-// Look-ahead over successor tiles (higher tile index = earlier ticket).
-// Slot words: [0] INCLUSIVE R (S at the tile's first element), [1] aggregate a, [2] aggregate b.
-__device__ __forceinline__ float bwd_lookahead(const uint64_t *desc, uint32_t tile, uint32_t num_tiles,
-                                               uint32_t epoch, uint32_t *hdr, int lane) {
-    Affine carry = affine_id();
-    int64_t nb = static_cast<int64_t>(tile) + 1;
-    while (true) {
-        const int64_t idx = nb + lane;
-        Affine m = Affine{0.0f, 0.0f};  // beyond the last tile: nothing follows
-        bool term = true;
-        if (idx < static_cast<int64_t>(num_tiles)) {
-            const uint64_t *slot = desc + idx * 4;
-            uint32_t spins = 0;
-            while (true) {
-                const uint64_t d0 = ld_relaxed_u64(slot);
-                if (desc_valid(d0, epoch)) {
-                    m = Affine{0.0f, desc_value(d0)};
-                    term = true;
-                    break;
-                }
-                const uint64_t d1 = ld_relaxed_u64(slot + 1);
-                const uint64_t d2 = ld_relaxed_u64(slot + 2);
-                if (desc_valid(d1, epoch) && desc_valid(d2, epoch)) {
-                    m = Affine{desc_value(d1), desc_value(d2)};
-                    term = (m.a == 0.0f);
-                    break;
-                }
-                ++spins;
-                if ((spins & 255u) == 0u) {
-                    if (spins >= POLL_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
-                    if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
-                }
-                if (spins > 8) __nanosleep(40);
-            }
-        }
-        const uint32_t tm = __ballot_sync(0xffffffffu, term);
-        const int last = tm ? (__ffs(tm) - 1) : 31;
-        Affine w = (lane <= last) ? m : affine_id();
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            Affine t;
-            t.a = __shfl_down_sync(0xffffffffu, w.a, d);
-            t.b = __shfl_down_sync(0xffffffffu, w.b, d);
-            if (lane + d < 32) w = compose(w, t);
-        }
-        w.a = __shfl_sync(0xffffffffu, w.a, 0);
-        w.b = __shfl_sync(0xffffffffu, w.b, 0);
-        carry = compose(carry, w);
-        if (tm) break;
-        nb += 32;
+// All 32 lanes of one warp: resolve S at the first element after the tile (position `end`)
+// from the 128 elements that follow.  True when the tile's last element is a tail (R
+// irrelevant) or the composite of the window annihilates (a tail, or an exact zero, inside
+// it); then R = S(end).  Also returns the two halo values the consumers need:
+// inext = inv[end], xnext = x[end] (-1 / 0 beyond the array).
+__device__ __forceinline__ bool halo_suffix(const float *__restrict__ x, const float *__restrict__ g,
+                                            const int32_t *__restrict__ inv, int64_t end, int64_t n, int lane,
+                                            bool vec, float &R, int32_t &inext, float &xnext) {
+    if (end >= n) {
+        R = 0.0f;
+        inext = -1;
+        xnext = 0.0f;
+        return true;
     }
-    return carry.b;
+    const int64_t h0 = end + lane * 4;
+    float xv[4], gv[4];
+    int32_t iv[4];
+    if (vec && h0 + 3 < n) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(x + h0));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(g + h0));
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(inv + h0));
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+        iv[0] = c.x; iv[1] = c.y; iv[2] = c.z; iv[3] = c.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool in = h0 + e < n;
+            xv[e] = in ? __ldg(x + h0 + e) : 1.0f;
+            gv[e] = in ? __ldg(g + h0 + e) : 0.0f;
+            iv[e] = in ? __ldg(inv + h0 + e) : -1;  // padding differs from every id: the last element is a tail
+        }
+    }
+    const int32_t ilast = __ldg(inv + end - 1);
+    int32_t qn = __shfl_down_sync(0xffffffffu, iv[0], 1);
+    float xq = __shfl_down_sync(0xffffffffu, xv[0], 1);
+    const bool known = lane < 31;  // what follows the window is unknown
+    if (!known) xq = 1.0f;
+    inext = __shfl_sync(0xffffffffu, iv[0], 0);
+    xnext = __shfl_sync(0xffffffffu, xv[0], 0);
+    Affine m = Affine{(known && qn != iv[3]) ? 0.0f : xq, gv[3]};
+    m = compose(Affine{(iv[3] != iv[2]) ? 0.0f : xv[3], gv[2]}, m);
+    m = compose(Affine{(iv[2] != iv[1]) ? 0.0f : xv[2], gv[1]}, m);
+    m = compose(Affine{(iv[1] != iv[0]) ? 0.0f : xv[1], gv[0]}, m);
+    m = warp_compose_all(m, lane);  // everything after the first tail is annihilated
+    if (ilast != inext) {
+        R = 0.0f;
+        return true;
+    }
+    R = m.b;
+    return m.a == 0.0f;
 }
 
 // Everything after x / g / inv of the tile are in registers.
@@ -125,18 +130,20 @@ __device__ __forceinline__ float bwd_lookahead(const uint64_t *desc, uint32_t ti
 //   inext : inv of the element after this warp's span (lane 31), -1 if none
 //   xnext : x of the element after this warp's span (lane 31)
 //   y_prev: y[base-1] (forward inclusive product just before the tile), any value if base == 0
-template <int WARPS, int ROWS>
+//   resolved/rn : CTA-uniform halo result (TMA: from the producer; LDG: read from sh)
+template <int WARPS, int ROWS, bool HALO_IN_SH>
 __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const float (&g)[ROWS][4],
                                               const int32_t (&iv)[ROWS][4], int32_t iprev, int32_t inext,
-                                              float xnext, float y_prev, uint32_t tile, uint32_t num_tiles,
+                                              float xnext, float y_prev, bool resolved, float rn, uint32_t tile,
                                               int64_t base, int64_t n, float *__restrict__ gin, bool out_vec,
-                                              uint32_t epoch, uint32_t *hdr, uint64_t *desc, BwdShared<WARPS> *sh,
+                                              uint32_t epoch, uint64_t *__restrict__ desc, BwdShared<WARPS> *sh,
                                               int warp, int lane) {
     constexpr int TILE = WARPS * ROWS * 128;
-    // ---- head / tail bits and the x of the next element ----
+    // ---- head / tail bits, the x of the next element, last tail of the warp span ----
     uint32_t hm = 0u, tm = 0u;
     float xn[ROWS];
     int32_t carry_prev = iprev;
+    int32_t lt = -1;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         int32_t p = __shfl_up_sync(0xffffffffu, iv[r][3], 1);
@@ -145,8 +152,10 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         int32_t q = __shfl_down_sync(0xffffffffu, iv[r][0], 1);
         float xq = __shfl_down_sync(0xffffffffu, x[r][0], 1);
         // lane 31 takes row r+1 lane 0 (or the warp halo on the last row)
-        const int32_t q_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, iv[(r + 1 < ROWS) ? r + 1 : r][0], 0) : inext;
-        const float x_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, x[(r + 1 < ROWS) ? r + 1 : r][0], 0) : xnext;
+        constexpr int RN_MAX = ROWS - 1;
+        const int rn_idx = (r + 1 < ROWS) ? r + 1 : RN_MAX;
+        const int32_t q_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, iv[rn_idx][0], 0) : inext;
+        const float x_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, x[rn_idx][0], 0) : xnext;
         if (lane == 31) {
             q = q_next_row;
             xq = x_next_row;
@@ -158,6 +167,12 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
                            (iv[r][3] != iv[r][2] ? 4u : 0u) | (q != iv[r][3] ? 8u : 0u);
         hm |= h << (4 * r);
         tm |= t << (4 * r);
+        const uint32_t mt = __ballot_sync(0xffffffffu, t != 0u);
+        if (mt) {  // warp-uniform
+            const int l1 = 31 - __clz(mt);
+            const uint32_t t1 = __shfl_sync(0xffffffffu, t, l1);
+            lt = r * 128 + l1 * 4 + (31 - __clz(t1));
+        }
     }
     // ---- pass 1: per-lane aggregates ----
     float fagg[ROWS];
@@ -180,9 +195,9 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         ragg[r] = m;
     }
     float cv[ROWS];
-    uint32_t cf, wf;
+    uint32_t cf, wf, fh;
     float wv;
-    warp_seg_scan_rows<OP_MUL, ROWS>(fagg, hm, lane, cv, cf, wv, wf);
+    warp_seg_scan_rows<OP_MUL, ROWS>(fagg, hm, lane, cv, cf, wv, wf, fh);
     Affine sx[ROWS];
     Affine wagg;
     warp_affine_rscan_rows<ROWS>(ragg, lane, sx, wagg);
@@ -191,8 +206,13 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         sh->wf[warp] = wf;
         sh->wa[warp] = wagg.a;
         sh->wb[warp] = wagg.b;
+        sh->lt[warp] = lt;
     }
     named_bar_sync<WARPS * 32>(1);
+    if (HALO_IN_SH) {
+        resolved = sh->res != 0u;
+        rn = sh->rn;
+    }
     // ---- forward prefix over earlier warps; reverse suffix over later warps; tile aggregate ----
     float wp_v = 1.0f;
     uint32_t wp_f = 0u;
@@ -207,34 +227,25 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
     }
     Affine ws = affine_id();  // composite of warps after mine
     Affine ta = affine_id();  // whole tile
+    uint32_t trail = 0u;      // offset just after the tile's last tail
 #pragma unroll
     for (int j = WARPS - 1; j >= 0; --j) {
         const Affine mj = Affine{sh->wa[j], sh->wb[j]};
         if (j > warp) ws = compose(mj, ws);
         ta = compose(mj, ta);
+        const int32_t lj = sh->lt[j];
+        if (lj >= 0 && trail == 0u) trail = static_cast<uint32_t>(j * ROWS * 128 + lj + 1);
     }
-    // ---- decoupled look-ahead (warp 0) ----
-    if (warp == 0) {
+    // ---- publish the carry descriptor (+ fix-up request when the halo did not resolve R) ----
+    if (warp == 0 && lane == 0) {
         uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
-        const bool last_tile = (tile + 1u == num_tiles);
-        const bool self_complete = (ta.a == 0.0f) || last_tile;
-        if (lane == 0) {
-            if (self_complete) {
-                st_relaxed_u64(slot, pack_desc(epoch, ST_INCL, 0u, ta.b));
-            } else {
-                st_relaxed_u64(slot + 1, pack_desc(epoch, ST_AGG, 0u, ta.a));
-                st_relaxed_u64(slot + 2, pack_desc(epoch, ST_AGG, 0u, ta.b));
-            }
-        }
-        float rn = 0.0f;
-        if (!last_tile) {
-            rn = bwd_lookahead(desc, tile, num_tiles, epoch, hdr, lane);
-            if (!self_complete && lane == 0) st_relaxed_u64(slot, pack_desc(epoch, ST_INCL, 0u, apply(ta, rn)));
-        }
-        if (lane == 0) sh->r_next = rn;
+        const bool term = resolved || (ta.a == 0.0f);
+        slot[0] = term ? pack_desc(epoch, ST_TERM, 0u, resolved ? apply(ta, rn) : ta.b)
+                       : pack_desc(epoch, ST_AGG, 0u, ta.a);
+        slot[1] = resolved ? 0ull : static_cast<uint64_t>(FIX_FLAG | trail);
+        slot[3] = static_cast<uint64_t>(__float_as_uint(ta.b));
     }
-    named_bar_sync<WARPS * 32>(1);
-    const float r_next = sh->r_next;
+    const float r_next = resolved ? rn : 0.0f;
     // ---- pass 2: per-element S and E, store E*S ----
     const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
     const bool full = (base + TILE <= n);
@@ -295,13 +306,13 @@ __device__ __forceinline__ void load_row_global_bwd(const float *__restrict__ x,
 }
 
 // ---------------------------------------------------------------------------
-// LDG variant: one tile per CTA, any alignment.
+// K1, LDG variant: one tile per CTA, any alignment.
 // ---------------------------------------------------------------------------
 template <int WARPS, int ROWS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
           const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
-          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int out_vec) {
+          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int out_vec, int use_halo) {
     constexpr int TILE = WARPS * ROWS * 128;
     __shared__ BwdShared<WARPS> sh;
     __shared__ uint32_t s_epoch;
@@ -323,22 +334,40 @@ k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float 
         int32_t iprev = -1, inext = -1;
         float xnext = 0.0f;
         if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
-        if (lane == 31 && wend < n) {
-            inext = __ldg(inv + wend);
-            xnext = __ldg(x + wend);
-        }
         const float y_prev = (base > 0) ? __ldg(y + base - 1) : 1.0f;
 #pragma unroll
         for (int r = 0; r < ROWS; ++r)
             load_row_global_bwd(x, g, inv, wbase + r * 128 + lane * 4, n, in_vec != 0, xv[r], gv[r], iv[r]);
-        bwd_tile_body<WARPS, ROWS>(xv, gv, iv, iprev, inext, xnext, y_prev, tile, num_tiles, base, n, gin,
-                                   out_vec != 0, epoch, hdr, desc, &sh, warp, lane);
+        if (warp == WARPS - 1) {
+            // the last warp's right neighbour is the next tile: resolve R from the halo there
+            float R = 0.0f;
+            bool res;
+            const int64_t end = base + TILE;
+            if (use_halo) {
+                res = halo_suffix(x, g, inv, end, n, lane, in_vec != 0, R, inext, xnext);
+            } else {
+                res = (end >= n);
+                if (end < n) {
+                    inext = __ldg(inv + end);
+                    xnext = __ldg(x + end);
+                }
+            }
+            if (lane == 0) {
+                sh.res = res ? 1u : 0u;
+                sh.rn = R;
+            }
+        } else if (lane == 31 && wend < n) {
+            inext = __ldg(inv + wend);
+            xnext = __ldg(x + wend);
+        }
+        bwd_tile_body<WARPS, ROWS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, false, 0.0f, tile, base, n, gin,
+                                         out_vec != 0, epoch, desc, &sh, warp, lane);
     }
     if (threadIdx.x == 0) finish_launch(hdr, epoch);
 }
 
 // ---------------------------------------------------------------------------
-// TMA variant: persistent, producer warp + STAGES-deep ring of (x, g, inv) tiles.
+// K1, TMA variant: persistent, producer warp + STAGES-deep ring of (x, g, inv) tiles.
 // ---------------------------------------------------------------------------
 template <int WARPS, int ROWS, int STAGES>
 struct BwdTmaSmem {
@@ -353,17 +382,19 @@ struct BwdTmaSmem {
         int32_t inext[STAGES];
         float xnext[STAGES];
         float yprev[STAGES];
+        uint32_t resolved[STAGES];
+        float rn[STAGES];
         uint32_t epoch;
-        BwdShared<WARPS> sh;
+        BwdShared<WARPS> sh[2];
     };
     static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl));
 };
 
-template <int WARPS, int ROWS, int STAGES>
-__global__ void __launch_bounds__((WARPS + 1) * 32)
+template <int WARPS, int ROWS, int STAGES, int MINB>
+__global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
           const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
-          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int out_vec) {
+          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int out_vec, int use_halo) {
     using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
     constexpr int TILE = L::TILE;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -383,22 +414,34 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
     const uint32_t epoch = ctl->epoch;
 
     if (warp == WARPS) {
-        if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
-            for (uint32_t it = 0;; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
-                mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-                const uint32_t t = atomicAdd(hdr + HDR_TICKET, 1u);
-                ctl->tile[s] = t;
-                if (t >= num_tiles) {
+        // ===================== producer warp =====================
+        const uint64_t pol = policy_evict_first();
+        uint32_t t_next = 0;
+        if (lane == 0) t_next = atomicAdd(hdr + HDR_TICKET, 1u);
+        t_next = __shfl_sync(0xffffffffu, t_next, 0);
+        for (uint32_t it = 0;; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
+            __syncwarp();
+            const uint32_t t = t_next;
+            if (t >= num_tiles) {
+                if (lane == 0) {
+                    ctl->tile[s] = t;
                     mbar_arrive(&ctl->full[s]);
                     mbar_arrive(&ctl->full[s]);
-                    break;
                 }
-                const uint32_t tile = num_tiles - 1u - t;
-                const int64_t base = static_cast<int64_t>(tile) * TILE;
-                if (base + TILE <= n) {
+                break;
+            }
+            const uint32_t tile = num_tiles - 1u - t;  // from the end: descending addresses
+            const int64_t base = static_cast<int64_t>(tile) * TILE;
+            const int64_t end = base + TILE;
+            uint32_t t_pref = 0;
+            int32_t ip = -1;
+            float yp = 1.0f;
+            if (lane == 0) {
+                ctl->tile[s] = t;
+                if (end <= n) {
                     unsigned char *st = smem + s * L::STAGE_BYTES;
                     mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
                     bulk_g2s(st, x + base, TILE * 4, &ctl->full[s], pol);
@@ -409,19 +452,36 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
                     ctl->mode[s] = 0u;
                     mbar_arrive(&ctl->full[s]);
                 }
-                const int64_t end = base + TILE;
-                const int32_t ip = (base > 0) ? __ldg(inv + base - 1) : -1;
-                const float yp = (base > 0) ? __ldg(y + base - 1) : 1.0f;
-                const int32_t in = (end < n) ? __ldg(inv + end) : -1;
-                const float xq = (end < n) ? __ldg(x + end) : 0.0f;
+                t_pref = atomicAdd(hdr + HDR_TICKET, 1u);
+                if (base > 0) {
+                    ip = __ldg(inv + base - 1);
+                    yp = __ldg(y + base - 1);
+                }
+            }
+            float R = 0.0f, xq = 0.0f;
+            int32_t in = -1;
+            bool res;
+            if (use_halo) {
+                res = halo_suffix(x, g, inv, end, n, lane, true, R, in, xq);
+            } else {
+                res = (end >= n);
+                if (end < n) {
+                    in = __ldg(inv + end);
+                    xq = __ldg(x + end);
+                }
+            }
+            t_next = __shfl_sync(0xffffffffu, t_pref, 0);
+            if (lane == 0) {
                 ctl->iprev[s] = ip;
                 ctl->yprev[s] = yp;
                 ctl->inext[s] = in;
                 ctl->xnext[s] = xq;
+                ctl->resolved[s] = res ? 1u : 0u;
+                ctl->rn[s] = R;
                 mbar_arrive(&ctl->full[s]);
             }
-            finish_launch(hdr, epoch);
         }
+        if (lane == 0) finish_launch(hdr, epoch);
         return;
     }
 
@@ -441,6 +501,8 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
         int32_t iprev = -1, inext = -1;
         float xnext = 0.0f;
         const float y_prev = ctl->yprev[s];
+        const bool resolved = ctl->resolved[s] != 0u;
+        const float rn_res = ctl->rn[s];
         if (ctl->mode[s]) {
             const float *xs = reinterpret_cast<const float *>(smem + s * L::STAGE_BYTES);
             const float *gs = xs + TILE;
@@ -477,8 +539,117 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[s]);
-        bwd_tile_body<WARPS, ROWS>(xv, gv, iv, iprev, inext, xnext, y_prev, tile, num_tiles, base, n, gin,
-                                   out_vec != 0, epoch, hdr, desc, &ctl->sh, warp, lane);
+        bwd_tile_body<WARPS, ROWS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, base, n,
+                                          gin, out_vec != 0, epoch, desc, &ctl->sh[it & 1u], warp, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: sparse fix-up of the tiles whose R the halo could not resolve.  One warp per
+// unresolved tile; never waits (all K1 descriptors are complete).  The trailing run
+// [tile start + trail, tile end) contains no tail, so S there is a plain reverse affine
+// scan seeded with R; E_i = y[i-1] (1 at the run start when it is a segment head).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bwd_fix(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
+          const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles, int tile_elems,
+          const uint32_t *__restrict__ hdr, uint64_t *desc) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t epoch = hdr[HDR_EPOCH];
+    if (num_tiles < 2u) return;
+    // descending tile order mirrors K1's ticket order (later tiles are fixed first)
+    for (int64_t t = static_cast<int64_t>(num_tiles) - 2 - gw; t >= 0; t -= nw) {
+        const uint64_t w1 = desc[t * 4 + 1];
+        if (!(static_cast<uint32_t>(w1) & FIX_FLAG)) continue;
+        const uint32_t trail = static_cast<uint32_t>(w1) & ~FIX_FLAG;
+        // ---- walk forward to the nearest tile whose S(first element) is known ----
+        Affine carry = affine_id();
+        int64_t nb = t + 1;
+        while (true) {
+            const int64_t idx = nb + lane;
+            Affine m = Affine{0.0f, 0.0f};  // beyond the last tile: nothing follows
+            bool term = true;
+            if (idx < static_cast<int64_t>(num_tiles)) {
+                const uint64_t d0 = desc[idx * 4];
+                if (desc_status(d0) == ST_TERM) {
+                    m = Affine{0.0f, desc_value(d0)};
+                } else {
+                    const uint64_t d2 = ld_relaxed_u64(desc + idx * 4 + 2);
+                    if (desc_valid(d2, epoch)) {
+                        m = Affine{0.0f, desc_value(d2)};
+                    } else {
+                        m = Affine{desc_value(d0), __uint_as_float(static_cast<uint32_t>(desc[idx * 4 + 3]))};
+                        term = (m.a == 0.0f);
+                    }
+                }
+            }
+            const uint32_t tmk = __ballot_sync(0xffffffffu, term);
+            const int last = tmk ? (__ffs(tmk) - 1) : 31;
+            Affine w = (lane <= last) ? m : affine_id();
+            w = warp_compose_all(w, lane);
+            carry = compose(carry, w);
+            if (tmk) break;
+            nb += 32;
+        }
+        float S = carry.b;  // S at the first element of tile t+1
+        const uint64_t d0 = desc[t * 4];
+        if (desc_status(d0) == ST_AGG && lane == 0) {
+            const Affine ta = Affine{desc_value(d0), __uint_as_float(static_cast<uint32_t>(desc[t * 4 + 3]))};
+            st_relaxed_u64(desc + t * 4 + 2, pack_desc(epoch, ST_INCL, 0u, apply(ta, S)));
+        }
+        // ---- recompute the trailing run, 128 elements per step, from the tile end ----
+        const int64_t rs = t * tile_elems + trail;
+        const int64_t re = (t + 1) * tile_elems;  // < n because t <= num_tiles-2
+        bool rs_head = trail > 0u;
+        if (!rs_head) rs_head = (rs == 0) || (__ldg(inv + rs) != __ldg(inv + rs - 1));
+        for (int64_t ce = re; ce > rs; ce -= 128) {
+            const int64_t i0 = ce - 128 + lane * 4;
+            float xn[4], gv[4];
+            bool ok[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e;
+                ok[e] = (i >= rs);
+                xn[e] = ok[e] ? __ldg(x + i + 1) : 1.0f;  // i+1 <= re < n
+                gv[e] = ok[e] ? __ldg(g + i) : 0.0f;
+            }
+            Affine m = Affine{xn[3], gv[3]};
+            m = compose(Affine{xn[2], gv[2]}, m);
+            m = compose(Affine{xn[1], gv[1]}, m);
+            m = compose(Affine{xn[0], gv[0]}, m);
+            Affine inc = m;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                Affine q;
+                q.a = __shfl_down_sync(0xffffffffu, inc.a, d);
+                q.b = __shfl_down_sync(0xffffffffu, inc.b, d);
+                if (lane + d < 32) inc = compose(inc, q);
+            }
+            Affine exc;
+            exc.a = __shfl_down_sync(0xffffffffu, inc.a, 1);
+            exc.b = __shfl_down_sync(0xffffffffu, inc.b, 1);
+            if (lane == 31) exc = affine_id();
+            Affine tot;
+            tot.a = __shfl_sync(0xffffffffu, inc.a, 0);
+            tot.b = __shfl_sync(0xffffffffu, inc.b, 0);
+            const float sn = apply(exc, S);
+            const float s3 = fmaf(xn[3], sn, gv[3]);
+            const float s2 = fmaf(xn[2], s3, gv[2]);
+            const float s1 = fmaf(xn[1], s2, gv[1]);
+            const float s0 = fmaf(xn[0], s1, gv[0]);
+            const float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e;
+                if (ok[e]) {
+                    const float ev = (i == rs && rs_head) ? 1.0f : __ldg(y + i - 1);
+                    gin[i] = ev * sv[e];
+                }
+            }
+            S = apply(tot, S);
+        }
     }
 }
 

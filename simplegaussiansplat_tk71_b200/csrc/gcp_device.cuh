@@ -2,8 +2,8 @@
 //
 //  * PTX wrappers: mbarrier, 1-D bulk async copy (TMA engine, SASS UBLKCP), relaxed
 //    gpu-scope descriptor loads/stores, streaming vector loads/stores.
-//  * workspace layout + tile descriptors for the decoupled look-back.
-//  * warp-level segmented scan pieces.
+//  * workspace layout + per-tile descriptors.
+//  * scan operators (segmented product/sum, affine maps of the backward).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,8 +12,12 @@ namespace gcp {
 
 // ----------------------------------------------------------------------------
 // Workspace layout (device memory, caller owned; see include/gcp_abi.h)
-//   [0,256)    header: u32 words  ticket@0, done@16, epoch@32, abort@33, violations(u64)@40
-//   [256, ...) 32 B descriptor slot per tile of MIN_TILE elements
+//   [0,256)    header: u32 words  ticket@0, done@16, epoch@32, abort@33, violations(u64)@byte 160
+//   [256, ...) one 32-byte slot (4 x u64) per tile of >= MIN_TILE elements:
+//     word0  K1: carry descriptor of the tile   {epoch, status TERM|AGG, flag, f32 value}
+//     word1  K1: fix-up request                 {bit31 = needs fix-up, low 31 bits = run boundary}
+//     word2  K2: inclusive carry of an AGG tile {epoch, ST_INCL, f32 value}  (epoch-tagged: never cleared)
+//     word3  K1 (backward only): the `b` of an AGG tile's affine aggregate
 // ----------------------------------------------------------------------------
 constexpr int WS_HEADER_BYTES = 256;
 constexpr int WS_SLOT_BYTES = 32;
@@ -24,9 +28,10 @@ constexpr int HDR_EPOCH = 32;
 constexpr int HDR_ABORT = 33;
 constexpr int HDR_VIOL64 = 20;  // index in u64 units (byte 160)
 
-constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_INCL = 2;
+constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_TERM = 2, ST_INCL = 3;
 constexpr uint32_t EPOCH_MASK = 0x1FFFFFFFu;
-constexpr uint32_t POLL_LIMIT = 1u << 22;  // bounded spins: fail open + sticky abort flag, never hang
+constexpr uint32_t WAIT_LIMIT = 1u << 20;  // bounded mbarrier spins: fail open + sticky abort flag, never hang
+constexpr uint32_t FIX_FLAG = 0x80000000u;
 
 __device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, uint32_t status, uint32_t flag, float v) {
     uint32_t hi = ((epoch & EPOCH_MASK) << 3) | (status << 1) | (flag & 1u);
@@ -52,24 +57,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-
-// Poll one descriptor word until it carries this launch's epoch and a non-invalid
-// status.  Bounded: on expiry sets the sticky abort flag and returns whatever is
-// there (results are then wrong, but the kernel terminates; the host sees the flag).
-__device__ __forceinline__ uint64_t poll_desc(const uint64_t *p, uint32_t epoch, uint32_t *hdr) {
-    uint64_t d = ld_relaxed_u64(p);
-    uint32_t spins = 0;
-    while (!desc_valid(d, epoch)) {
-        ++spins;
-        if ((spins & 255u) == 0u) {
-            if (spins >= POLL_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
-            if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
-        }
-        if (spins > 8) __nanosleep(40);
-        d = ld_relaxed_u64(p);
-    }
-    return d;
 }
 
 // ----------------------------------------------------------------------------
@@ -103,13 +90,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait (same fail-open policy as poll_desc)
+// Bounded wait: on expiry set the sticky abort flag and carry on (results are then wrong, but the
+// kernel terminates and gcp_workspace_status reports it).  Only a bug can trip it: the only waits
+// in the kernels are on mbarriers fed by the CTA's own producer warp.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *hdr) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
         if ((spins & 63u) == 0u) {
-            if (spins >= (POLL_LIMIT >> 2)) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+            if (spins >= WAIT_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
             if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
         }
     }
@@ -174,5 +163,32 @@ __device__ __forceinline__ Affine compose(Affine l, Affine r) {
     return o;
 }
 __device__ __forceinline__ float apply(Affine m, float s) { return (m.a == 0.0f) ? m.b : fmaf(m.a, s, m.b); }
+
+// Ordered warp reduction of affine maps: lane 0 ends with m_0 ∘ m_1 ∘ ... ∘ m_31, broadcast to all.
+__device__ __forceinline__ Affine warp_compose_all(Affine m, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Affine t;
+        t.a = __shfl_down_sync(0xffffffffu, m.a, d);
+        t.b = __shfl_down_sync(0xffffffffu, m.b, d);
+        if (lane + d < 32) m = compose(m, t);
+    }
+    m.a = __shfl_sync(0xffffffffu, m.a, 0);
+    m.b = __shfl_sync(0xffffffffu, m.b, 0);
+    return m;
+}
+
+// Last-CTA-done: reset the ticket/done counters and advance the epoch so that the next launch on
+// the stream finds a clean workspace without any memset.
+__device__ __forceinline__ void finish_launch(uint32_t *hdr, uint32_t epoch) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(hdr + HDR_DONE, 1u);
+    if (prev == gridDim.x - 1u) {
+        hdr[HDR_TICKET] = 0u;
+        hdr[HDR_DONE] = 0u;
+        hdr[HDR_EPOCH] = epoch + 1u;
+        __threadfence();
+    }
+}
 
 }  // namespace gcp

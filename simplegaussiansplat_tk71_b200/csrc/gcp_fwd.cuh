@@ -1,84 +1,67 @@
-// gcp_fwd.cuh — forward segmented inclusive scan (cumprod / cumsum), single pass.
+// gcp_fwd.cuh — forward segmented inclusive scan (cumprod / cumsum), wait-free.
 //
 // Replaces thrust::inclusive_scan_by_key at
 //   /root/reference/cuda_kernel/grouped_cumprod_forward.cu:17-23  (OP_MUL)
 //   /root/reference/cuda_kernel/grouped_cumsum_forward.cu:17-23   (OP_ADD)
 //
-// Data layout inside a tile of TILE = WARPS*ROWS*128 elements: warp w owns the
-// contiguous span [w*ROWS*128, (w+1)*ROWS*128); in row r lane l holds the four
-// consecutive elements at r*128 + l*4 ("striped float4"): every global / shared
-// access is a fully coalesced, bank-conflict-free 128-bit access, and no
-// shared-memory transpose is needed.  Scan = thread-serial over the float4 ->
-// ballot-masked segmented warp scan per row (5 SHFL) -> serial chain over the
-// ROWS rows -> WARPS warp aggregates through shared memory -> decoupled
-// look-back across tiles (one 64-bit descriptor per tile).
+// Layout inside a tile of TILE = WARPS*ROWS*128 elements: warp w owns the contiguous
+// span [w*ROWS*128, (w+1)*ROWS*128); in row r lane l holds the four consecutive
+// elements at r*128 + l*4 ("striped float4"): every global / shared access is a
+// coalesced, bank-conflict-free 128-bit access and no shared-memory transpose is
+// needed.  Scan = thread-serial over the float4 -> ballot-masked segmented warp scan
+// per row (5 SHFL) -> serial chain over the ROWS rows -> WARPS warp aggregates
+// through shared memory (ONE named barrier per tile).
 //
-// Two kernels share the body:
-//   k_fwd_tma : persistent CTAs; a producer warp takes tile tickets and streams
-//               x/key tiles into a STAGES-deep shared-memory ring with 1-D bulk
-//               async copies (cp.async.bulk -> UBLKCP) completing on mbarriers.
-//   k_fwd_ldg : one tile per CTA, direct 128-bit (or scalar, for unaligned
-//               pointers) streaming loads.  Handles every alignment and n.
+// Cross-tile carry, without any inter-CTA waiting:
+//   K1 (k_fwd_tma / k_fwd_ldg)  resolves the tile's exclusive prefix from the HALO, the
+//      128 elements before the tile (a per-pixel list is ~20-50 elements, so a segment
+//      head is almost always inside it).  If no head is found the tile is "unresolved":
+//      it stores its results as if the prefix were the identity and publishes a carry
+//      descriptor {TERM|AGG, value} plus a fix-up request {needs, lead = #elements before
+//      the tile's first head}.  Nothing ever polls: K1 never blocks on another CTA.
+//   K2 (k_fwd_fix)  runs after K1 on the same stream, one warp per unresolved tile: it
+//      walks back over the (now complete) descriptors 32 tiles per round to the nearest
+//      TERM / already-fixed tile, and applies prefix (x) y over the `lead` elements.
+//      Costs ~2-3 us when nothing is unresolved.
+//
+//   k_fwd_tma : persistent CTAs; a producer warp takes tile tickets, streams x/key tiles
+//               into a STAGES-deep shared-memory ring with 1-D bulk async copies
+//               (cp.async.bulk -> UBLKCP) completing on mbarriers, and computes the halo.
+//   k_fwd_ldg : one tile per CTA, direct streaming loads; any alignment, any n.
 #pragma once
 #include "gcp_device.cuh"
 
 namespace gcp {
 
+constexpr uint32_t NO_POS = 0xFFFFFFFFu;
+
 template <int WARPS>
 struct FwdShared {
-    float wv[WARPS];
-    uint32_t wf[WARPS];
-    float tp_v;
+    float wv[WARPS];     // warp aggregates
+    uint32_t wf[WARPS];  // "warp span contains a head"
+    uint32_t fh[WARPS];  // offset of the first head inside the warp span (NO_POS if none)
+    uint32_t res;        // LDG kernel: halo result of warp 0
+    float tp;
     uint32_t tile;
 };
 
-// Decoupled look-back (warp-wide, 32 predecessors per round).  Returns the
-// exclusive prefix of `tile`: op over everything from the last segment head
-// before the tile up to the tile start.  Terminates at the first predecessor
-// that is INCLUSIVE or whose aggregate contains a head (flag).
-template <int OP>
-__device__ __forceinline__ float fwd_lookback(const uint64_t *desc, uint32_t tile, uint32_t epoch,
-                                              uint32_t *hdr, int lane) {
-    using O = ScanOp<OP>;
-    float carry = O::id();
-    int64_t pb = static_cast<int64_t>(tile) - 1;
-    while (true) {
-        int64_t idx = pb - lane;
-        bool term = true;
-        float v = O::id();
-        if (idx >= 0) {
-            uint64_t d = poll_desc(desc + idx * 4, epoch, hdr);
-            term = (desc_status(d) == ST_INCL) || (desc_flag(d) != 0u);
-            v = desc_value(d);
-        }
-        uint32_t tm = __ballot_sync(0xffffffffu, term);
-        int last = tm ? (__ffs(tm) - 1) : 31;
-        float w = (lane <= last) ? v : O::id();
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
-        carry = O::f(w, carry);
-        if (tm) break;
-        pb -= 32;
-    }
-    return carry;
-}
-
-// Segmented inclusive scan of one aggregate per (row, lane) across the warp and
-// down its ROWS rows.
+// Segmented inclusive scan of one aggregate per (row, lane) across the warp and down its rows.
 //   agg[r] : op over this lane's 4 elements of row r after its last head
 //   hm     : head bits of the lane's elements, bit r*4+e
 //   cv/cf  : out, per-row carry INTO this lane from earlier lanes/rows of the warp
-//            (value, "a head lies between the warp start and this lane" flag bit r)
-//   wv/wf  : out, warp aggregate
+//            (value; bit r of cf = "a head lies between the warp start and this lane")
+//   wv/wf  : out, warp aggregate;  fh : out, offset of the first head in the warp span
 template <int OP, int ROWS>
 __device__ __forceinline__ void warp_seg_scan_rows(const float (&agg)[ROWS], uint32_t hm, int lane,
-                                                   float (&cv)[ROWS], uint32_t &cf, float &wv, uint32_t &wf) {
+                                                   float (&cv)[ROWS], uint32_t &cf, float &wv, uint32_t &wf,
+                                                   uint32_t &fh) {
     using O = ScanOp<OP>;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t le = lt | (1u << lane);
     float rp_v = O::id();
     uint32_t rp_f = 0u;
     cf = 0u;
+    fh = NO_POS;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const uint32_t h = (hm >> (4 * r)) & 15u;
@@ -95,6 +78,11 @@ __device__ __forceinline__ void warp_seg_scan_rows(const float (&agg)[ROWS], uin
         const bool ef = (m & lt) != 0u;
         const float row_v = __shfl_sync(0xffffffffu, inc, 31);
         const bool row_f = m != 0u;
+        if (row_f && rp_f == 0u) {  // first row of the warp that holds a head (warp-uniform branch)
+            const int l0 = __ffs(m) - 1;
+            const uint32_t h0 = __shfl_sync(0xffffffffu, h, l0);
+            fh = static_cast<uint32_t>(r * 128 + l0 * 4 + (__ffs(h0) - 1));
+        }
         cv[r] = ef ? exc : O::f(rp_v, exc);
         cf |= ((ef || rp_f) ? 1u : 0u) << r;
         rp_v = row_f ? row_v : O::f(rp_v, row_v);
@@ -104,31 +92,56 @@ __device__ __forceinline__ void warp_seg_scan_rows(const float (&agg)[ROWS], uin
     wf = rp_f;
 }
 
-// v  : in  x values, out local inclusive values (thread-serial within each float4)
-template <int OP, int ROWS>
-__device__ __forceinline__ void fwd_warp_scan(float (&v)[ROWS][4], uint32_t hm, int lane, float (&cv)[ROWS],
-                                              uint32_t &cf, float &wv, uint32_t &wf) {
+// All 32 lanes of one warp: resolve the exclusive prefix of the tile that starts at `base`
+// from the 128 elements before it.  True when the tile's first element is a head (prefix
+// irrelevant) or a segment head lies inside the window; then P = op over [last head, base).
+// kprev = key[base-1].  Needs 128 <= base < n.
+template <int OP>
+__device__ __forceinline__ bool halo_prefix(const float *__restrict__ x, const int32_t *__restrict__ key,
+                                            int64_t base, int lane, bool vec, float &P, int32_t &kprev) {
     using O = ScanOp<OP>;
-    float agg[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const uint32_t h = (hm >> (4 * r)) & 15u;
-        v[r][1] = (h & 2u) ? v[r][1] : O::f(v[r][0], v[r][1]);
-        v[r][2] = (h & 4u) ? v[r][2] : O::f(v[r][1], v[r][2]);
-        v[r][3] = (h & 8u) ? v[r][3] : O::f(v[r][2], v[r][3]);
-        agg[r] = v[r][3];
+    const int64_t h0 = base - 128 + lane * 4;
+    float4 a;
+    int4 b;
+    if (vec) {
+        a = __ldg(reinterpret_cast<const float4 *>(x + h0));
+        b = __ldg(reinterpret_cast<const int4 *>(key + h0));
+    } else {
+        a = make_float4(__ldg(x + h0), __ldg(x + h0 + 1), __ldg(x + h0 + 2), __ldg(x + h0 + 3));
+        b = make_int4(__ldg(key + h0), __ldg(key + h0 + 1), __ldg(key + h0 + 2), __ldg(key + h0 + 3));
     }
-    warp_seg_scan_rows<OP, ROWS>(agg, hm, lane, cv, cf, wv, wf);
+    const int32_t kfirst = __ldg(key + base);
+    const int32_t pk = __shfl_up_sync(0xffffffffu, b.w, 1);
+    const uint32_t h = ((lane > 0 && b.x != pk) ? 1u : 0u) | (b.y != b.x ? 2u : 0u) | (b.z != b.y ? 4u : 0u) |
+                       (b.w != b.z ? 8u : 0u);
+    kprev = __shfl_sync(0xffffffffu, b.w, 31);
+    const uint32_t m = __ballot_sync(0xffffffffu, h != 0u);
+    float v = a.x;
+    v = (h & 2u) ? a.y : O::f(v, a.y);
+    v = (h & 4u) ? a.z : O::f(v, a.z);
+    v = (h & 8u) ? a.w : O::f(v, a.w);
+    const int last = 31 - __clz(m);  // highest lane holding a head, -1 if none
+    float w = (lane >= last) ? v : O::id();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+    if (kfirst != kprev) {
+        P = O::id();
+        return true;
+    }
+    P = w;
+    return m != 0u;
 }
 
 // Everything after the tile's x/key values are in registers.
-//   kprev : key of the element just before this warp's span (only lane 0 needs it)
+//   kprev      : key of the element just before this warp's span (only lane 0 needs it)
 //   first_head : this warp's first element is global element 0
-template <int OP, int WARPS, int ROWS>
+//   resolved/tp: CTA-uniform halo result (TMA kernel: from the producer; LDG kernel: read from sh)
+template <int OP, int WARPS, int ROWS, bool HALO_IN_SH>
 __device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t (&k)[ROWS][4], int32_t kprev,
-                                              bool first_head, uint32_t tile, int64_t base, int64_t n,
-                                              float *__restrict__ y, bool y_vec, uint32_t epoch, uint32_t *hdr,
-                                              uint64_t *desc, FwdShared<WARPS> *sh, int warp, int lane) {
+                                              bool first_head, bool resolved, float tp, uint32_t tile, int64_t base,
+                                              int64_t n, float *__restrict__ y, bool y_vec, uint32_t epoch,
+                                              uint64_t *__restrict__ desc, FwdShared<WARPS> *sh, int warp,
+                                              int lane) {
     using O = ScanOp<OP>;
     constexpr int TILE = WARPS * ROWS * 128;
     // ---- head flags ----
@@ -144,19 +157,33 @@ __device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t
         if (r == 0 && lane == 0 && first_head) h |= 1u;
         hm |= h << (4 * r);
     }
-    // ---- warp-level scan ----
+    // ---- thread-serial + warp-level scan ----
+    float agg[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t h = (hm >> (4 * r)) & 15u;
+        v[r][1] = (h & 2u) ? v[r][1] : O::f(v[r][0], v[r][1]);
+        v[r][2] = (h & 4u) ? v[r][2] : O::f(v[r][1], v[r][2]);
+        v[r][3] = (h & 8u) ? v[r][3] : O::f(v[r][2], v[r][3]);
+        agg[r] = v[r][3];
+    }
     float cv[ROWS];
-    uint32_t cf, wf;
+    uint32_t cf, wf, fh;
     float wv;
-    fwd_warp_scan<OP, ROWS>(v, hm, lane, cv, cf, wv, wf);
+    warp_seg_scan_rows<OP, ROWS>(agg, hm, lane, cv, cf, wv, wf, fh);
     if (lane == 0) {
         sh->wv[warp] = wv;
         sh->wf[warp] = wf;
+        sh->fh[warp] = fh;
     }
     named_bar_sync<WARPS * 32>(1);
-    // ---- exclusive prefix over warps + tile aggregate ----
+    if (HALO_IN_SH) {
+        resolved = sh->res != 0u;
+        tp = sh->tp;
+    }
+    // ---- exclusive prefix over warps, tile aggregate, first head of the tile ----
     float wp_v = O::id(), ta_v = O::id();
-    uint32_t wp_f = 0u, ta_f = 0u;
+    uint32_t wp_f = 0u, ta_f = 0u, lead = TILE;
 #pragma unroll
     for (int j = 0; j < WARPS; ++j) {
         const float jv = sh->wv[j];
@@ -165,23 +192,19 @@ __device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t
             wp_v = jf ? jv : O::f(wp_v, jv);
             wp_f |= jf;
         }
+        if (jf && ta_f == 0u) lead = static_cast<uint32_t>(j * ROWS * 128) + sh->fh[j];
         ta_v = jf ? jv : O::f(ta_v, jv);
         ta_f |= jf;
     }
-    // ---- decoupled look-back (warp 0) ----
-    if (warp == 0) {
+    // ---- publish the carry descriptor (+ fix-up request when the halo held no head) ----
+    if (warp == 0 && lane == 0) {
         uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
-        const bool self_complete = (ta_f != 0u) || (tile == 0u);
-        if (lane == 0) st_relaxed_u64(slot, pack_desc(epoch, self_complete ? ST_INCL : ST_AGG, ta_f, ta_v));
-        float tp = O::id();
-        if (tile > 0u) {
-            tp = fwd_lookback<OP>(desc, tile, epoch, hdr, lane);
-            if (!self_complete && lane == 0) st_relaxed_u64(slot, pack_desc(epoch, ST_INCL, 0u, O::f(tp, ta_v)));
-        }
-        if (lane == 0) sh->tp_v = tp;
+        const bool term = (ta_f != 0u) || resolved;
+        const float val = ta_f ? ta_v : (resolved ? O::f(tp, ta_v) : ta_v);
+        slot[0] = pack_desc(epoch, term ? ST_TERM : ST_AGG, ta_f, val);
+        slot[1] = resolved ? 0ull : static_cast<uint64_t>(FIX_FLAG | lead);
     }
-    named_bar_sync<WARPS * 32>(1);
-    const float tp_v = sh->tp_v;
+    const float tp_v = resolved ? tp : O::id();
     // ---- apply carries, store ----
     const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
     const bool full = (base + TILE <= n);
@@ -232,26 +255,15 @@ __device__ __forceinline__ void load_row_global(const float *__restrict__ x, con
     }
 }
 
-// Last-CTA-done: reset ticket/done and advance the epoch so the next launch on
-// the stream finds a clean workspace without a memset.
-__device__ __forceinline__ void finish_launch(uint32_t *hdr, uint32_t epoch) {
-    __threadfence();
-    const uint32_t prev = atomicAdd(hdr + HDR_DONE, 1u);
-    if (prev == gridDim.x - 1u) {
-        hdr[HDR_TICKET] = 0u;
-        hdr[HDR_DONE] = 0u;
-        hdr[HDR_EPOCH] = epoch + 1u;
-        __threadfence();
-    }
-}
-
 // ---------------------------------------------------------------------------
-// LDG variant: one tile per CTA (ticket taken at entry), any alignment.
+// K1, LDG variant: one tile per CTA (ticket taken at entry), any alignment.
 // ---------------------------------------------------------------------------
 template <int OP, int WARPS, int ROWS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_fwd_ldg(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
-          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int y_vec) {
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int y_vec,
+          int use_halo) {
+    using O = ScanOp<OP>;
     constexpr int TILE = WARPS * ROWS * 128;
     __shared__ FwdShared<WARPS> sh;
     __shared__ uint32_t s_epoch;
@@ -269,18 +281,31 @@ k_fwd_ldg(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
         float v[ROWS][4];
         int32_t k[ROWS][4];
         int32_t kprev = 0;
-        if (lane == 0 && wbase > 0 && wbase - 1 < n) kprev = __ldg(key + wbase - 1);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r)
             load_row_global<OP>(x, key, wbase + r * 128 + lane * 4, n, in_vec != 0, v[r], k[r]);
-        fwd_tile_body<OP, WARPS, ROWS>(v, k, kprev, wbase == 0, tile, base, n, y, y_vec != 0, epoch, hdr, desc, &sh,
-                                       warp, lane);
+        if (warp == 0) {
+            float P = O::id();
+            bool res = (tile == 0u);
+            if (tile > 0u) {
+                if (use_halo) res = halo_prefix<OP>(x, key, base, lane, in_vec != 0, P, kprev);
+                else kprev = __ldg(key + base - 1);
+            }
+            if (lane == 0) {
+                sh.res = res ? 1u : 0u;
+                sh.tp = P;
+            }
+        } else if (lane == 0 && wbase - 1 < n) {
+            kprev = __ldg(key + wbase - 1);
+        }
+        fwd_tile_body<OP, WARPS, ROWS, true>(v, k, kprev, wbase == 0, false, 0.0f, tile, base, n, y, y_vec != 0,
+                                             epoch, desc, &sh, warp, lane);
     }
     if (threadIdx.x == 0) finish_launch(hdr, epoch);
 }
 
 // ---------------------------------------------------------------------------
-// TMA variant: persistent, producer warp + STAGES-deep bulk-copy ring.
+// K1, TMA variant: persistent, producer warp + STAGES-deep bulk-copy ring.
 // Requires x and key 16-byte aligned (the host falls back to k_fwd_ldg otherwise).
 // ---------------------------------------------------------------------------
 template <int WARPS, int ROWS, int STAGES>
@@ -293,8 +318,10 @@ struct FwdTmaSmem {
         uint32_t tile[STAGES];
         int32_t halo[STAGES];
         uint32_t mode[STAGES];
+        uint32_t resolved[STAGES];
+        float tp[STAGES];
         uint32_t epoch;
-        FwdShared<WARPS> sh;
+        FwdShared<WARPS> sh[2];
     };
     static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl));
 };
@@ -302,8 +329,9 @@ struct FwdTmaSmem {
 template <int OP, int WARPS, int ROWS, int STAGES>
 __global__ void __launch_bounds__((WARPS + 1) * 32)
 k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
-          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int y_vec) {
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int y_vec, int use_halo) {
     using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
+    using O = ScanOp<OP>;
     constexpr int TILE = L::TILE;
     extern __shared__ __align__(128) unsigned char smem[];
     typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
@@ -322,21 +350,30 @@ k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
     const uint32_t epoch = ctl->epoch;
 
     if (warp == WARPS) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
-            for (uint32_t it = 0;; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
-                mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-                const uint32_t t = atomicAdd(hdr + HDR_TICKET, 1u);
-                ctl->tile[s] = t;
-                if (t >= num_tiles) {
+        // ===================== producer warp =====================
+        // lane 0: tickets, bulk copies, barriers.  All lanes: halo prefix of the tile.
+        const uint64_t pol = policy_evict_first();
+        uint32_t t_next = 0;
+        if (lane == 0) t_next = atomicAdd(hdr + HDR_TICKET, 1u);
+        t_next = __shfl_sync(0xffffffffu, t_next, 0);
+        for (uint32_t it = 0;; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
+            __syncwarp();
+            const uint32_t t = t_next;
+            if (t >= num_tiles) {
+                if (lane == 0) {
+                    ctl->tile[s] = t;
                     mbar_arrive(&ctl->full[s]);
                     mbar_arrive(&ctl->full[s]);
-                    break;
                 }
-                const int64_t base = static_cast<int64_t>(t) * TILE;
+                break;
+            }
+            const int64_t base = static_cast<int64_t>(t) * TILE;
+            uint32_t t_pref = 0;
+            if (lane == 0) {
+                ctl->tile[s] = t;
                 if (base + TILE <= n) {
                     unsigned char *st = smem + s * L::STAGE_BYTES;
                     mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
@@ -347,11 +384,24 @@ k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
                     ctl->mode[s] = 0u;
                     mbar_arrive(&ctl->full[s]);
                 }
-                ctl->halo[s] = (base > 0) ? __ldg(key + base - 1) : 0;
+                t_pref = atomicAdd(hdr + HDR_TICKET, 1u);  // next ticket: its latency overlaps the halo loads
+            }
+            float P = O::id();
+            int32_t kprev = 0;
+            bool res = (t == 0u);
+            if (t > 0u) {
+                if (use_halo) res = halo_prefix<OP>(x, key, base, lane, true, P, kprev);
+                else kprev = __ldg(key + base - 1);
+            }
+            t_next = __shfl_sync(0xffffffffu, t_pref, 0);
+            if (lane == 0) {
+                ctl->halo[s] = kprev;
+                ctl->resolved[s] = res ? 1u : 0u;
+                ctl->tp[s] = P;
                 mbar_arrive(&ctl->full[s]);
             }
-            finish_launch(hdr, epoch);
         }
+        if (lane == 0) finish_launch(hdr, epoch);
         return;
     }
 
@@ -365,6 +415,8 @@ k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
         const int64_t base = static_cast<int64_t>(tile) * TILE;
         const int woff = warp * (ROWS * 128);
         const int64_t wbase = base + woff;
+        const bool resolved = ctl->resolved[s] != 0u;
+        const float tp_res = ctl->tp[s];
         float v[ROWS][4];
         int32_t k[ROWS][4];
         int32_t kprev = 0;
@@ -387,8 +439,66 @@ k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[s]);
-        fwd_tile_body<OP, WARPS, ROWS>(v, k, kprev, wbase == 0, tile, base, n, y, y_vec != 0, epoch, hdr, desc,
-                                       &ctl->sh, warp, lane);
+        fwd_tile_body<OP, WARPS, ROWS, false>(v, k, kprev, wbase == 0, resolved, tp_res, tile, base, n, y, y_vec != 0,
+                                              epoch, desc, &ctl->sh[it & 1u], warp, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: sparse fix-up of the tiles whose prefix the halo could not resolve.
+// One warp per unresolved tile.  All K1 descriptors are complete (previous kernel on
+// the stream), so the walk never waits.  An AGG tile that has been fixed publishes its
+// inclusive carry in word2 (epoch-tagged) so that later walkers stop there; reading a
+// word2 that is not there yet only makes a walk longer, never wrong.
+// ---------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_fwd_fix(float *__restrict__ y, int64_t n, uint32_t num_tiles, int tile_elems, const uint32_t *__restrict__ hdr,
+          uint64_t *desc) {
+    using O = ScanOp<OP>;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t epoch = hdr[HDR_EPOCH];
+    for (uint32_t t = 1u + gw; t < num_tiles; t += nw) {
+        const uint64_t w1 = desc[static_cast<int64_t>(t) * 4 + 1];
+        if (!(static_cast<uint32_t>(w1) & FIX_FLAG)) continue;
+        const uint32_t lead = static_cast<uint32_t>(w1) & ~FIX_FLAG;
+        float carry = O::id();
+        int64_t pb = static_cast<int64_t>(t) - 1;
+        while (true) {
+            const int64_t idx = pb - lane;
+            bool term = true;
+            float v = O::id();
+            if (idx >= 0) {
+                const uint64_t d0 = desc[idx * 4];
+                term = desc_status(d0) == ST_TERM;
+                v = desc_value(d0);
+                if (!term) {
+                    const uint64_t d2 = ld_relaxed_u64(desc + idx * 4 + 2);
+                    if (desc_valid(d2, epoch)) {
+                        term = true;
+                        v = desc_value(d2);
+                    }
+                }
+            }
+            const uint32_t tm = __ballot_sync(0xffffffffu, term);
+            const int last = tm ? (__ffs(tm) - 1) : 31;
+            float w = (lane <= last) ? v : O::id();
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+            carry = O::f(w, carry);
+            if (tm) break;
+            pb -= 32;
+        }
+        const uint64_t d0 = desc[static_cast<int64_t>(t) * 4];
+        if (desc_status(d0) == ST_AGG && lane == 0)
+            st_relaxed_u64(desc + static_cast<int64_t>(t) * 4 + 2,
+                           pack_desc(epoch, ST_INCL, 0u, O::f(carry, desc_value(d0))));
+        const int64_t base = static_cast<int64_t>(t) * tile_elems;
+        int64_t end = base + lead;
+        if (end > n) end = n;
+        for (int64_t i = base + lane; i < end; i += 32) y[i] = O::f(carry, y[i]);
     }
 }
 

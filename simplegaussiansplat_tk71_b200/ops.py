@@ -140,6 +140,11 @@ def set_variant(op: str, variant: int) -> None:
     _lib.check(_lib.lib().gcp_set_variant(0 if op == "fwd" else 1, int(variant)), "gcp_set_variant")
 
 
+def set_option(option: int, value: int) -> None:
+    """Tuning hook: option 0 = halo resolution of tile carries (1 on / 0 always look back)."""
+    _lib.check(_lib.lib().gcp_set_option(int(option), int(value)), "gcp_set_option")
+
+
 def variants(op: str) -> list:
     L = _lib.lib()
     o = 0 if op == "fwd" else 1

@@ -104,3 +104,20 @@ def test_omp_port_matches_sequential(oracle):
     y, gin = oracle.fwd_bwd_f32_omp(x, g, starts)
     assert oracle.allclose(y, oracle.cumprod_fwd(x, key))
     assert oracle.allclose(gin, oracle.cumprod_bwd_exact(x, g, key))
+
+
+def test_oracle_matches_reference_ops_fixture(oracle):
+    """tests/golden/ref_ops_fixture.npz = outputs of the reference's own CUDA ops (built unchanged by
+    oracle/build_ref.sh) on a B200, generated by tests/golden/make_ref_fixture.py."""
+    import os
+
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ops_fixture.npz"))
+    x, g, key, inv, se = f["x"], f["g"], f["key"], f["inv"], f["seg_end"]
+    assert oracle.allclose(f["y"], oracle.cumprod_fwd(x, key))
+    assert oracle.allclose(f["cumsum"], oracle.cumsum_fwd(g, key))
+    assert oracle.allclose(f["grad_in"], oracle.cumprod_bwd_ref(x, f["y"], g, inv, se))
+    assert oracle.allclose(f["grad_in"], oracle.cumprod_bwd_exact(x, g, inv))   # zero-free input
+    # integer side of the fixture is self-consistent, bit-exact
+    starts = oracle.segment_starts(key)
+    assert np.array_equal(starts[1:], se.astype(np.int64))
+    assert np.array_equal(np.cumsum(np.r_[0, key[1:] != key[:-1]]).astype(np.int32), inv)
