@@ -44,6 +44,8 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 struct Ws {
     uint32_t *hdr;
     uint64_t *desc;
+    // list of unresolved tiles: right behind the descriptors of THIS launch's tile count
+    uint32_t *ulist(uint32_t num_tiles) const { return reinterpret_cast<uint32_t *>(desc + 4ull * num_tiles); }
 };
 int check_ws(void *ws, size_t ws_bytes, int64_t n, Ws *out) {
     if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15u) != 0) return GCP_ERR_WORKSPACE;
@@ -84,8 +86,9 @@ inline unsigned fix_grid(uint32_t nt) {
 // ------------------------------ forward ------------------------------------
 template <int OP>
 int launch_fwd_fix(float *y, int64_t n, uint32_t nt, int tile, Ws ws, cudaStream_t s) {
-    if (nt < 2u) return GCP_OK;  // tile 0 always resolves (its first element is a head)
-    k_fwd_fix<OP><<<fix_grid(nt), 256, 0, s>>>(y, n, nt, tile, ws.hdr, ws.desc);
+    // always launched behind an LDG K1 (even when nothing is unresolved): it also closes the op
+    // (resets the workspace counters, advances the epoch)
+    k_fwd_fix<OP><<<fix_grid(nt), 256, 0, s>>>(y, n, tile, ws.hdr, ws.desc, ws.ulist(nt));
     ++t_launches;
     return static_cast<int>(cudaGetLastError());
 }
@@ -96,8 +99,8 @@ int launch_fwd_ldg(const float *x, const int32_t *key, float *y, int64_t n, Ws w
     const uint32_t nt = tiles_for(n, TILE);
     const int in_vec = aligned16(x) && aligned16(key);
     const int y_vec = aligned16(y);
-    k_fwd_ldg<OP, WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, in_vec, y_vec,
-                                                          g_option[0]);
+    k_fwd_ldg<OP, WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, ws.ulist(nt), in_vec,
+                                                          y_vec, g_option[0]);
     ++t_launches;
     const int rc = static_cast<int>(cudaGetLastError());
     return rc != 0 ? rc : launch_fwd_fix<OP>(y, n, nt, TILE, ws, s);
@@ -112,10 +115,11 @@ int launch_fwd_tma(const float *x, const int32_t *key, float *y, int64_t n, Ws w
     const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, aligned16(y) ? 1 : 0, g_option[0]);
+    // ONE launch: streaming phase, grid barrier, sparse fix-up phase (all CTAs are resident)
+    kern<<<grid, threads, L::BYTES, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, ws.ulist(nt), aligned16(y) ? 1 : 0,
+                                         g_option[0]);
     ++t_launches;
-    const int rc = static_cast<int>(cudaGetLastError());
-    return rc != 0 ? rc : launch_fwd_fix<OP>(y, n, nt, L::TILE, ws, s);
+    return static_cast<int>(cudaGetLastError());
 }
 
 constexpr int FWD_NUM_VARIANTS = 8;
@@ -124,7 +128,7 @@ const char *const kFwdNames[FWD_NUM_VARIANTS] = {
     "tma_w8_r4_s3 (tile 4096, 96 KB ring)", "tma_w8_r4_s2 (tile 4096, 64 KB ring)",
     "tma_w8_r2_s4 (tile 2048, 64 KB ring)", "tma_w4_r4_s4 (tile 2048, 160 thr)",
     "tma_w16_r4_s3 (tile 8192, 192 KB ring)"};
-constexpr int FWD_DEFAULT = 0;
+constexpr int FWD_DEFAULT = 4;   // tma_w8_r4_s2
 
 template <int OP>
 int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *wsp, size_t ws_bytes,
@@ -155,8 +159,7 @@ int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *
 // ------------------------------ backward -----------------------------------
 inline int launch_bwd_fix(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
                           uint32_t nt, int tile, Ws ws, cudaStream_t s) {
-    if (nt < 2u) return GCP_OK;  // the last tile always resolves (nothing follows it)
-    k_bwd_fix<<<fix_grid(nt), 256, 0, s>>>(x, y, g, inv, gin, n, nt, tile, ws.hdr, ws.desc);
+    k_bwd_fix<<<fix_grid(nt), 256, 0, s>>>(x, y, g, inv, gin, n, nt, tile, ws.hdr, ws.desc, ws.ulist(nt));
     ++t_launches;
     return static_cast<int>(cudaGetLastError());
 }
@@ -167,7 +170,7 @@ int launch_bwd_ldg(const float *x, const float *y, const float *g, const int32_t
     constexpr int TILE = WARPS * ROWS * 128;
     const uint32_t nt = tiles_for(n, TILE);
     const int in_vec = aligned16(x) && aligned16(g) && aligned16(inv);
-    k_bwd_ldg<WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, in_vec,
+    k_bwd_ldg<WARPS, ROWS><<<nt, WARPS * 32, 0, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt), in_vec,
                                                       aligned16(gin) ? 1 : 0, g_option[0]);
     ++t_launches;
     const int rc = static_cast<int>(cudaGetLastError());
@@ -184,11 +187,10 @@ int launch_bwd_tma(const float *x, const float *y, const float *g, const int32_t
     const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, aligned16(gin) ? 1 : 0,
-                                         g_option[0]);
+    kern<<<grid, threads, L::BYTES, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
+                                         aligned16(gin) ? 1 : 0, g_option[0]);
     ++t_launches;
-    const int rc = static_cast<int>(cudaGetLastError());
-    return rc != 0 ? rc : launch_bwd_fix(x, y, g, inv, gin, n, nt, L::TILE, ws, s);
+    return static_cast<int>(cudaGetLastError());
 }
 
 constexpr int BWD_NUM_VARIANTS = 8;
@@ -197,7 +199,7 @@ const char *const kBwdNames[BWD_NUM_VARIANTS] = {
     "tma_w8_r4_s2 (tile 4096, 96 KB ring, 2 CTA/SM)", "tma_w8_r2_s4 (tile 2048, 96 KB ring, 2 CTA/SM)",
     "tma_w8_r2_s3 (tile 2048, 72 KB ring, 3 CTA/SM)", "tma_w8_r4_s4 (tile 4096, 192 KB ring, 1 CTA/SM)",
     "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)"};
-constexpr int BWD_DEFAULT = 0;
+constexpr int BWD_DEFAULT = 5;   // tma_w8_r2_s3
 
 }  // namespace
 
@@ -208,7 +210,8 @@ int gcp_abi_version(void) { return GCP_ABI_VERSION; }
 size_t gcp_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
     const int64_t slots = (n + gcp::MIN_TILE - 1) / gcp::MIN_TILE + 1;
-    return static_cast<size_t>(gcp::WS_HEADER_BYTES) + static_cast<size_t>(slots) * gcp::WS_SLOT_BYTES;
+    return static_cast<size_t>(gcp::WS_HEADER_BYTES) +
+           static_cast<size_t>(slots) * (gcp::WS_SLOT_BYTES + gcp::WS_LIST_BYTES);
 }
 
 int gcp_workspace_init(void *ws, size_t ws_bytes, gcp_stream_t stream) {

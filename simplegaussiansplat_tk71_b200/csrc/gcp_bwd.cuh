@@ -20,9 +20,10 @@
 //      the 128 elements after the tile.  Unresolved tiles store provisional values for
 //      their trailing run (the elements after the tile's last tail), publish a carry
 //      descriptor (TERM R | AGG (a,b)) and a fix-up request {needs, trail start}.
-//   K2 (k_bwd_fix) one warp per unresolved tile: walks forward over the complete
-//      descriptors to the nearest TERM / already-fixed tile and recomputes the trailing run
-//      (reads x, g and y there: E_i = y[i-1]).
+//   Fix-up (bwd_fix_tile) one warp per unresolved tile, once all descriptors are complete:
+//      walks forward over the descriptors to the nearest TERM / already-fixed tile and
+//      recomputes the trailing run (reads x, g and y there: E_i = y[i-1]).  Second phase of the
+//      same launch in the persistent kernel (grid barrier), separate kernel K2 on the LDG path.
 #pragma once
 #include "gcp_device.cuh"
 #include "gcp_fwd.cuh"
@@ -36,41 +37,10 @@ struct BwdShared {
     float wa[WARPS];     // reverse affine aggregates
     float wb[WARPS];
     int32_t lt[WARPS];   // offset of the last tail inside the warp span (-1 if none)
-    uint32_t res;        // LDG kernel: halo result of warp 0
+    uint32_t res;        // LDG kernel: halo result
     float rn;
     uint32_t tile;
 };
-
-// Reverse inclusive scan of affine maps across the warp and up its rows.
-//   agg[r]: composite of this lane's 4 elements of row r (element 0 outermost)
-//   sx[r] : out, composite of everything AFTER this lane inside the warp
-//   wagg  : out, composite of the whole warp span
-template <int ROWS>
-__device__ __forceinline__ void warp_affine_rscan_rows(const Affine (&agg)[ROWS], int lane, Affine (&sx)[ROWS],
-                                                       Affine &wagg) {
-    Affine rs = affine_id();
-#pragma unroll
-    for (int r = ROWS - 1; r >= 0; --r) {
-        Affine inc = agg[r];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            Affine t;
-            t.a = __shfl_down_sync(0xffffffffu, inc.a, d);
-            t.b = __shfl_down_sync(0xffffffffu, inc.b, d);
-            if (lane + d < 32) inc = compose(inc, t);
-        }
-        Affine exc;
-        exc.a = __shfl_down_sync(0xffffffffu, inc.a, 1);
-        exc.b = __shfl_down_sync(0xffffffffu, inc.b, 1);
-        if (lane == 31) exc = affine_id();
-        Affine row;
-        row.a = __shfl_sync(0xffffffffu, inc.a, 0);
-        row.b = __shfl_sync(0xffffffffu, inc.b, 0);
-        sx[r] = compose(exc, rs);
-        rs = compose(row, rs);
-    }
-    wagg = rs;
-}
 
 // All 32 lanes of one warp: resolve S at the first element after the tile (position `end`)
 // from the 128 elements that follow.  True when the tile's last element is a tail (R
@@ -126,9 +96,9 @@ __device__ __forceinline__ bool halo_suffix(const float *__restrict__ x, const f
 }
 
 // Everything after x / g / inv of the tile are in registers.
-//   iprev : inv of the element before this warp's span (lane 0), -1 if none
-//   inext : inv of the element after this warp's span (lane 31), -1 if none
-//   xnext : x of the element after this warp's span (lane 31)
+//   iprev : inv of the element before this warp's span (used by lane 0), -1 if none
+//   inext : inv of the element after this warp's span (used by lane 0!), -1 if none
+//   xnext : x of the element after this warp's span (used by lane 0)
 //   y_prev: y[base-1] (forward inclusive product just before the tile), any value if base == 0
 //   resolved/rn : CTA-uniform halo result (TMA: from the producer; LDG: read from sh)
 template <int WARPS, int ROWS, bool HALO_IN_SH>
@@ -136,45 +106,49 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
                                               const int32_t (&iv)[ROWS][4], int32_t iprev, int32_t inext,
                                               float xnext, float y_prev, bool resolved, float rn, uint32_t tile,
                                               int64_t base, int64_t n, float *__restrict__ gin, bool out_vec,
-                                              uint32_t epoch, uint64_t *__restrict__ desc, BwdShared<WARPS> *sh,
-                                              int warp, int lane) {
+                                              uint32_t epoch, uint32_t *__restrict__ hdr,
+                                              uint64_t *__restrict__ desc, uint32_t *__restrict__ ulist,
+                                              BwdShared<WARPS> *sh, int warp, int lane) {
+    static_assert(WARPS < 32, "cross-warp step uses one lane per warp (and lane WARPS as the identity)");
     constexpr int TILE = WARPS * ROWS * 128;
-    // ---- head / tail bits, the x of the next element, last tail of the warp span ----
+    const uint32_t lanes_lt = (1u << lane) - 1u;
+    const uint32_t lanes_le = lanes_lt | (1u << lane);
+    // ---- tail bits (one rotate-shuffle of inv per row), head bits derived from them,
+    //      x of the next element, last tail of the warp span ----
     uint32_t hm = 0u, tm = 0u;
     float xn[ROWS];
-    int32_t carry_prev = iprev;
+    uint32_t stop_room = 0u;  // 5 bits per row: (first lane >= me holding a tail) - lane
+    uint32_t carry_h = (iv[0][0] != iprev) ? 1u : 0u;  // only lane 0's value is used
     int32_t lt = -1;
+    const int src_lane = (lane + 1) & 31;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        int32_t p = __shfl_up_sync(0xffffffffu, iv[r][3], 1);
-        if (lane == 0) p = carry_prev;
-        carry_prev = __shfl_sync(0xffffffffu, iv[r][3], 31);
-        int32_t q = __shfl_down_sync(0xffffffffu, iv[r][0], 1);
-        float xq = __shfl_down_sync(0xffffffffu, x[r][0], 1);
-        // lane 31 takes row r+1 lane 0 (or the warp halo on the last row)
-        constexpr int RN_MAX = ROWS - 1;
-        const int rn_idx = (r + 1 < ROWS) ? r + 1 : RN_MAX;
-        const int32_t q_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, iv[rn_idx][0], 0) : inext;
-        const float x_next_row = (r + 1 < ROWS) ? __shfl_sync(0xffffffffu, x[rn_idx][0], 0) : xnext;
-        if (lane == 31) {
-            q = q_next_row;
-            xq = x_next_row;
-        }
-        xn[r] = xq;
-        const uint32_t h = (iv[r][0] != p ? 1u : 0u) | (iv[r][1] != iv[r][0] ? 2u : 0u) |
-                           (iv[r][2] != iv[r][1] ? 4u : 0u) | (iv[r][3] != iv[r][2] ? 8u : 0u);
+        // lane 0 lends the first element of the NEXT row (or the warp halo) to lane 31
+        constexpr int RL = ROWS - 1;
+        const int rnx = (r + 1 < ROWS) ? r + 1 : RL;
+        const int32_t lend_i = (r + 1 < ROWS) ? iv[rnx][0] : inext;
+        const float lend_x = (r + 1 < ROWS) ? x[rnx][0] : xnext;
+        const int32_t q = __shfl_sync(0xffffffffu, lane == 0 ? lend_i : iv[r][0], src_lane);
+        xn[r] = __shfl_sync(0xffffffffu, lane == 0 ? lend_x : x[r][0], src_lane);
         const uint32_t t = (iv[r][1] != iv[r][0] ? 1u : 0u) | (iv[r][2] != iv[r][1] ? 2u : 0u) |
                            (iv[r][3] != iv[r][2] ? 4u : 0u) | (q != iv[r][3] ? 8u : 0u);
-        hm |= h << (4 * r);
+        const uint32_t m3 = __ballot_sync(0xffffffffu, (t & 8u) != 0u);  // lanes whose LAST element is a tail
+        const uint32_t mt = __ballot_sync(0xffffffffu, t != 0u);         // lanes holding any tail
+        const uint32_t h0 = lane ? ((m3 >> (lane - 1)) & 1u) : carry_h;
+        carry_h = m3 >> 31;
+        hm |= (h0 | ((t & 7u) << 1)) << (4 * r);
         tm |= t << (4 * r);
-        const uint32_t mt = __ballot_sync(0xffffffffu, t != 0u);
+        const uint32_t ahead = mt & ~lanes_lt;  // tails at or after my lane
+        const uint32_t stop = ahead ? static_cast<uint32_t>(__ffs(ahead) - 1) : 31u;
+        stop_room |= (stop - lane) << (5 * r);
         if (mt) {  // warp-uniform
             const int l1 = 31 - __clz(mt);
             const uint32_t t1 = __shfl_sync(0xffffffffu, t, l1);
             lt = r * 128 + l1 * 4 + (31 - __clz(t1));
         }
     }
-    // ---- pass 1: per-lane aggregates ----
+    // ---- pass 1: per-lane aggregates (forward product after the last head; reverse affine
+    //      composite up to the first tail) ----
     float fagg[ROWS];
     Affine ragg[ROWS];
 #pragma unroll
@@ -186,26 +160,53 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         p = (h & 4u) ? x[r][2] : p * x[r][2];
         p = (h & 8u) ? x[r][3] : p * x[r][3];
         fagg[r] = p;
-        Affine m;
-        m.a = (t & 8u) ? 0.0f : xn[r];
-        m.b = g[r][3];
-        m = compose(Affine{(t & 4u) ? 0.0f : x[r][3], g[r][2]}, m);
-        m = compose(Affine{(t & 2u) ? 0.0f : x[r][2], g[r][1]}, m);
-        m = compose(Affine{(t & 1u) ? 0.0f : x[r][1], g[r][0]}, m);
-        ragg[r] = m;
+        float A = (t & 8u) ? 0.0f : xn[r];
+        float B = g[r][3];
+        B = (t & 4u) ? g[r][2] : fmaf(x[r][3], B, g[r][2]);
+        A = (t & 4u) ? 0.0f : x[r][3] * A;
+        B = (t & 2u) ? g[r][1] : fmaf(x[r][2], B, g[r][1]);
+        A = (t & 2u) ? 0.0f : x[r][2] * A;
+        B = (t & 1u) ? g[r][0] : fmaf(x[r][1], B, g[r][0]);
+        A = (t & 1u) ? 0.0f : x[r][1] * A;
+        ragg[r] = Affine{A, B};
     }
+    // ---- forward segmented warp scan of the products ----
     float cv[ROWS];
     uint32_t cf, wf, fh;
     float wv;
     warp_seg_scan_rows<OP_MUL, ROWS>(fagg, hm, lane, cv, cf, wv, wf, fh);
+    // ---- reverse warp scan of the affine maps, masked by the tail ballot: a lane only ever
+    //      combines with lanes of its own segment (plus the lane that holds the tail) ----
     Affine sx[ROWS];
-    Affine wagg;
-    warp_affine_rscan_rows<ROWS>(ragg, lane, sx, wagg);
+    Affine rs = affine_id();
+#pragma unroll
+    for (int r = ROWS - 1; r >= 0; --r) {
+        const int room = static_cast<int>((stop_room >> (5 * r)) & 31u);
+        float A = ragg[r].a, B = ragg[r].b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float ta = __shfl_down_sync(0xffffffffu, A, d);
+            const float tb = __shfl_down_sync(0xffffffffu, B, d);
+            if (d <= room) {
+                B = fmaf(A, tb, B);
+                A = A * ta;
+            }
+        }
+        Affine exc;
+        exc.a = __shfl_down_sync(0xffffffffu, A, 1);
+        exc.b = __shfl_down_sync(0xffffffffu, B, 1);
+        if (lane == 31) exc = affine_id();
+        Affine row;
+        row.a = __shfl_sync(0xffffffffu, A, 0);
+        row.b = __shfl_sync(0xffffffffu, B, 0);
+        sx[r] = compose(exc, rs);
+        rs = compose(row, rs);
+    }
     if (lane == 0) {
         sh->wv[warp] = wv;
         sh->wf[warp] = wf;
-        sh->wa[warp] = wagg.a;
-        sh->wb[warp] = wagg.b;
+        sh->wa[warp] = rs.a;
+        sh->wb[warp] = rs.b;
         sh->lt[warp] = lt;
     }
     named_bar_sync<WARPS * 32>(1);
@@ -213,28 +214,41 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         resolved = sh->res != 0u;
         rn = sh->rn;
     }
-    // ---- forward prefix over earlier warps; reverse suffix over later warps; tile aggregate ----
-    float wp_v = 1.0f;
-    uint32_t wp_f = 0u;
+    // ---- across warps, one lane per warp: forward prefix of the earlier warps, reverse suffix
+    //      of the later warps, tile aggregate, position after the tile's last tail ----
+    const bool wl = lane < WARPS;
+    float jv = wl ? sh->wv[lane] : 1.0f;
+    const uint32_t jf = wl ? sh->wf[lane] : 0u;
+    Affine jm = wl ? Affine{sh->wa[lane], sh->wb[lane]} : affine_id();
+    const int32_t jl = wl ? sh->lt[lane] : -1;
+    const uint32_t fm = __ballot_sync(0xffffffffu, jf != 0u);
+    {
+        const int start = max(31 - __clz(fm & lanes_le), 0);
 #pragma unroll
-    for (int j = 0; j < WARPS; ++j) {
-        if (j < warp) {
-            const float jv = sh->wv[j];
-            const uint32_t jf = sh->wf[j];
-            wp_v = jf ? jv : wp_v * jv;
-            wp_f |= jf;
+        for (int d = 1; d < WARPS; d <<= 1) {
+            const float tv = __shfl_up_sync(0xffffffffu, jv, d);
+            if (lane - d >= start) jv = tv * jv;
+        }
+#pragma unroll
+        for (int d = 1; d < WARPS; d <<= 1) {
+            Affine q;
+            q.a = __shfl_down_sync(0xffffffffu, jm.a, d);
+            q.b = __shfl_down_sync(0xffffffffu, jm.b, d);
+            if (lane + d < 32) jm = compose(jm, q);
         }
     }
-    Affine ws = affine_id();  // composite of warps after mine
-    Affine ta = affine_id();  // whole tile
-    uint32_t trail = 0u;      // offset just after the tile's last tail
-#pragma unroll
-    for (int j = WARPS - 1; j >= 0; --j) {
-        const Affine mj = Affine{sh->wa[j], sh->wb[j]};
-        if (j > warp) ws = compose(mj, ws);
-        ta = compose(mj, ta);
-        const int32_t lj = sh->lt[j];
-        if (lj >= 0 && trail == 0u) trail = static_cast<uint32_t>(j * ROWS * 128 + lj + 1);
+    const float wp_v = __shfl_sync(0xffffffffu, jv, warp > 0 ? warp - 1 : 0);  // used only if warp > 0
+    const bool wp_f = (fm & ((1u << warp) - 1u)) != 0u;
+    Affine ws, ta;
+    ws.a = __shfl_sync(0xffffffffu, jm.a, warp + 1 < 32 ? warp + 1 : 31);  // lanes >= WARPS hold the identity
+    ws.b = __shfl_sync(0xffffffffu, jm.b, warp + 1 < 32 ? warp + 1 : 31);
+    ta.a = __shfl_sync(0xffffffffu, jm.a, 0);
+    ta.b = __shfl_sync(0xffffffffu, jm.b, 0);
+    const uint32_t lm = __ballot_sync(0xffffffffu, jl >= 0);
+    uint32_t trail = 0u;
+    if (lm) {
+        const int jw = 31 - __clz(lm);
+        trail = static_cast<uint32_t>(jw * ROWS * 128 + __shfl_sync(0xffffffffu, jl, jw) + 1);
     }
     // ---- publish the carry descriptor (+ fix-up request when the halo did not resolve R) ----
     if (warp == 0 && lane == 0) {
@@ -242,10 +256,12 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         const bool term = resolved || (ta.a == 0.0f);
         slot[0] = term ? pack_desc(epoch, ST_TERM, 0u, resolved ? apply(ta, rn) : ta.b)
                        : pack_desc(epoch, ST_AGG, 0u, ta.a);
-        slot[1] = resolved ? 0ull : static_cast<uint64_t>(FIX_FLAG | trail);
+        slot[1] = static_cast<uint64_t>(trail);
         slot[3] = static_cast<uint64_t>(__float_as_uint(ta.b));
+        if (!resolved) ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
     }
-    const float r_next = resolved ? rn : 0.0f;
+    // S at the first element after my warp's span
+    const float s_after_warp = apply(ws, resolved ? rn : 0.0f);
     // ---- pass 2: per-element S and E, store E*S ----
     const int64_t wbase = base + static_cast<int64_t>(warp) * (ROWS * 128);
     const bool full = (base + TILE <= n);
@@ -254,7 +270,7 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         const uint32_t h = (hm >> (4 * r)) & 15u;
         const uint32_t t = (tm >> (4 * r)) & 15u;
         // S of the element right after this lane's e=3 (only used when e=3 is not a tail)
-        const float sn = apply(compose(sx[r], ws), r_next);
+        const float sn = apply(sx[r], s_after_warp);
         const float s3 = (t & 8u) ? g[r][3] : fmaf(xn[r], sn, g[r][3]);
         const float s2 = (t & 4u) ? g[r][2] : fmaf(x[r][3], s3, g[r][2]);
         const float s1 = (t & 2u) ? g[r][1] : fmaf(x[r][2], s2, g[r][1]);
@@ -263,8 +279,8 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
         float c = cv[r];
         bool f = (cf >> r) & 1u;
         if (!f) {
-            c = wp_v * c;
-            f = wp_f != 0u;
+            c = (warp > 0) ? wp_v * c : c;
+            f = wp_f;
         }
         if (!f) c = y_prev * c;
         const float e0 = (h & 1u) ? 1.0f : c;
@@ -281,6 +297,107 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
             if (gi + 2 < n) __stcs(gin + gi + 2, o2);
             if (gi + 3 < n) __stcs(gin + gi + 3, o3);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fix-up of ONE tile whose R the halo could not resolve (one warp); runs when every descriptor
+// of the launch is complete, so it never waits.  The trailing run [tile start + trail, tile end)
+// contains no tail, so S there is a plain reverse affine scan seeded with R;
+// E_i = y[i-1] (1 at the run start when it is a segment head).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bwd_fix_tile(int64_t t, const float *__restrict__ x, const float *__restrict__ y,
+                                             const float *__restrict__ g, const int32_t *__restrict__ inv,
+                                             float *gin, int64_t n, uint32_t num_tiles, int tile_elems,
+                                             uint32_t epoch, uint64_t *desc, int lane) {
+    const uint32_t trail = static_cast<uint32_t>(ld_relaxed_u64(desc + t * 4 + 1));
+    // ---- walk forward to the nearest tile whose S(first element) is known ----
+    Affine carry = affine_id();
+    int64_t nb = t + 1;
+    while (true) {
+        const int64_t idx = nb + lane;
+        Affine m = Affine{0.0f, 0.0f};  // beyond the last tile: nothing follows
+        bool term = true;
+        if (idx < static_cast<int64_t>(num_tiles)) {
+            const uint64_t d0 = ld_relaxed_u64(desc + idx * 4);
+            if (desc_status(d0) == ST_TERM) {
+                m = Affine{0.0f, desc_value(d0)};
+            } else {
+                const uint64_t d2 = ld_relaxed_u64(desc + idx * 4 + 2);
+                if (desc_valid(d2, epoch) && desc_status(d2) == ST_INCL) {
+                    m = Affine{0.0f, desc_value(d2)};
+                } else {
+                    m = Affine{desc_value(d0),
+                               __uint_as_float(static_cast<uint32_t>(ld_relaxed_u64(desc + idx * 4 + 3)))};
+                    term = (m.a == 0.0f);
+                }
+            }
+        }
+        const uint32_t tmk = __ballot_sync(0xffffffffu, term);
+        const int last = tmk ? (__ffs(tmk) - 1) : 31;
+        Affine w = (lane <= last) ? m : affine_id();
+        w = warp_compose_all(w, lane);
+        carry = compose(carry, w);
+        if (tmk) break;
+        nb += 32;
+    }
+    float S = carry.b;  // S at the first element of tile t+1
+    const uint64_t d0 = ld_relaxed_u64(desc + t * 4);
+    if (desc_status(d0) == ST_AGG && lane == 0) {
+        const Affine ta = Affine{desc_value(d0), __uint_as_float(static_cast<uint32_t>(ld_relaxed_u64(desc + t * 4 + 3)))};
+        st_relaxed_u64(desc + t * 4 + 2, pack_desc(epoch, ST_INCL, 0u, apply(ta, S)));
+    }
+    // ---- recompute the trailing run, 128 elements per step, from the tile end ----
+    const int64_t rs = t * tile_elems + trail;
+    const int64_t re = (t + 1) * tile_elems;  // < n: the last tile always resolves
+    if (rs >= re) return;
+    bool rs_head = trail > 0u;
+    if (!rs_head) rs_head = (rs == 0) || (__ldg(inv + rs) != __ldg(inv + rs - 1));
+    for (int64_t ce = re; ce > rs; ce -= 128) {
+        const int64_t i0 = ce - 128 + lane * 4;
+        float xn[4], gv[4];
+        bool ok[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i0 + e;
+            ok[e] = (i >= rs);
+            xn[e] = ok[e] ? __ldg(x + i + 1) : 1.0f;  // i+1 <= re < n
+            gv[e] = ok[e] ? __ldg(g + i) : 0.0f;
+        }
+        Affine m = Affine{xn[3], gv[3]};
+        m = compose(Affine{xn[2], gv[2]}, m);
+        m = compose(Affine{xn[1], gv[1]}, m);
+        m = compose(Affine{xn[0], gv[0]}, m);
+        Affine inc = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Affine q;
+            q.a = __shfl_down_sync(0xffffffffu, inc.a, d);
+            q.b = __shfl_down_sync(0xffffffffu, inc.b, d);
+            if (lane + d < 32) inc = compose(inc, q);
+        }
+        Affine exc;
+        exc.a = __shfl_down_sync(0xffffffffu, inc.a, 1);
+        exc.b = __shfl_down_sync(0xffffffffu, inc.b, 1);
+        if (lane == 31) exc = affine_id();
+        Affine tot;
+        tot.a = __shfl_sync(0xffffffffu, inc.a, 0);
+        tot.b = __shfl_sync(0xffffffffu, inc.b, 0);
+        const float sn = apply(exc, S);
+        const float s3 = fmaf(xn[3], sn, gv[3]);
+        const float s2 = fmaf(xn[2], s3, gv[2]);
+        const float s1 = fmaf(xn[1], s2, gv[1]);
+        const float s0 = fmaf(xn[0], s1, gv[0]);
+        const float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i0 + e;
+            if (ok[e]) {
+                const float ev = (i == rs && rs_head) ? 1.0f : __ldg(y + i - 1);
+                gin[i] = ev * sv[e];
+            }
+        }
+        S = apply(tot, S);
     }
 }
 
@@ -312,7 +429,8 @@ template <int WARPS, int ROWS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
           const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
-          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int out_vec, int use_halo) {
+          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, uint32_t *__restrict__ ulist, int in_vec,
+          int out_vec, int use_halo) {
     constexpr int TILE = WARPS * ROWS * 128;
     __shared__ BwdShared<WARPS> sh;
     __shared__ uint32_t s_epoch;
@@ -356,14 +474,14 @@ k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float 
                 sh.res = res ? 1u : 0u;
                 sh.rn = R;
             }
-        } else if (lane == 31 && wend < n) {
+        } else if (lane == 0 && wend < n) {
             inext = __ldg(inv + wend);
             xnext = __ldg(x + wend);
         }
         bwd_tile_body<WARPS, ROWS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, false, 0.0f, tile, base, n, gin,
-                                         out_vec != 0, epoch, desc, &sh, warp, lane);
+                                         out_vec != 0, epoch, hdr, desc, ulist, &sh, warp, lane);
     }
-    if (threadIdx.x == 0) finish_launch(hdr, epoch);
+    if (threadIdx.x == 0) finish_stream_kernel(hdr);
 }
 
 // ---------------------------------------------------------------------------
@@ -394,7 +512,7 @@ template <int WARPS, int ROWS, int STAGES, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
           const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
-          uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int out_vec, int use_halo) {
+          uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int out_vec, int use_halo) {
     using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
     constexpr int TILE = L::TILE;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -481,7 +599,6 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
                 mbar_arrive(&ctl->full[s]);
             }
         }
-        if (lane == 0) finish_launch(hdr, epoch);
         return;
     }
 
@@ -517,8 +634,8 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
                 gv[r][0] = b.x; gv[r][1] = b.y; gv[r][2] = b.z; gv[r][3] = b.w;
                 iv[r][0] = c.x; iv[r][1] = c.y; iv[r][2] = c.z; iv[r][3] = c.w;
             }
-            if (lane == 0) iprev = (warp == 0) ? ctl->iprev[s] : is[woff - 1];
-            if (lane == 31) {
+            if (lane == 0) {
+                iprev = (warp == 0) ? ctl->iprev[s] : is[woff - 1];
                 if (warp == WARPS - 1) {
                     inext = ctl->inext[s];
                     xnext = ctl->xnext[s];
@@ -532,7 +649,7 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
             for (int r = 0; r < ROWS; ++r)
                 load_row_global_bwd(x, g, inv, wbase + r * 128 + lane * 4, n, true, xv[r], gv[r], iv[r]);
             if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
-            if (lane == 31 && wend < n) {
+            if (lane == 0 && wend < n) {
                 inext = __ldg(inv + wend);
                 xnext = __ldg(x + wend);
             }
@@ -540,117 +657,33 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[s]);
         bwd_tile_body<WARPS, ROWS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, base, n,
-                                          gin, out_vec != 0, epoch, desc, &ctl->sh[it & 1u], warp, lane);
+                                          gin, out_vec != 0, epoch, hdr, desc, ulist, &ctl->sh[it & 1u], warp, lane);
     }
+
+    // ===================== fix-up phase (same launch) =====================
+    grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);
+    const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
+    for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
+        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch, desc, lane);
+    named_bar_sync<WARPS * 32>(1);
+    if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
 
-// ---------------------------------------------------------------------------
-// K2: sparse fix-up of the tiles whose R the halo could not resolve.  One warp per
-// unresolved tile; never waits (all K1 descriptors are complete).  The trailing run
-// [tile start + trail, tile end) contains no tail, so S there is a plain reverse affine
-// scan seeded with R; E_i = y[i-1] (1 at the run start when it is a segment head).
-// ---------------------------------------------------------------------------
+// K2 of the LDG path: the same fix-up as a separate launch (one warp per list entry).
 __global__ void __launch_bounds__(256)
 k_bwd_fix(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
-          const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles, int tile_elems,
-          const uint32_t *__restrict__ hdr, uint64_t *desc) {
+          const int32_t *__restrict__ inv, float *gin, int64_t n, uint32_t num_tiles, int tile_elems, uint32_t *hdr,
+          uint64_t *desc, const uint32_t *ulist) {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t epoch = hdr[HDR_EPOCH];
-    if (num_tiles < 2u) return;
-    // descending tile order mirrors K1's ticket order (later tiles are fixed first)
-    for (int64_t t = static_cast<int64_t>(num_tiles) - 2 - gw; t >= 0; t -= nw) {
-        const uint64_t w1 = desc[t * 4 + 1];
-        if (!(static_cast<uint32_t>(w1) & FIX_FLAG)) continue;
-        const uint32_t trail = static_cast<uint32_t>(w1) & ~FIX_FLAG;
-        // ---- walk forward to the nearest tile whose S(first element) is known ----
-        Affine carry = affine_id();
-        int64_t nb = t + 1;
-        while (true) {
-            const int64_t idx = nb + lane;
-            Affine m = Affine{0.0f, 0.0f};  // beyond the last tile: nothing follows
-            bool term = true;
-            if (idx < static_cast<int64_t>(num_tiles)) {
-                const uint64_t d0 = desc[idx * 4];
-                if (desc_status(d0) == ST_TERM) {
-                    m = Affine{0.0f, desc_value(d0)};
-                } else {
-                    const uint64_t d2 = ld_relaxed_u64(desc + idx * 4 + 2);
-                    if (desc_valid(d2, epoch)) {
-                        m = Affine{0.0f, desc_value(d2)};
-                    } else {
-                        m = Affine{desc_value(d0), __uint_as_float(static_cast<uint32_t>(desc[idx * 4 + 3]))};
-                        term = (m.a == 0.0f);
-                    }
-                }
-            }
-            const uint32_t tmk = __ballot_sync(0xffffffffu, term);
-            const int last = tmk ? (__ffs(tmk) - 1) : 31;
-            Affine w = (lane <= last) ? m : affine_id();
-            w = warp_compose_all(w, lane);
-            carry = compose(carry, w);
-            if (tmk) break;
-            nb += 32;
-        }
-        float S = carry.b;  // S at the first element of tile t+1
-        const uint64_t d0 = desc[t * 4];
-        if (desc_status(d0) == ST_AGG && lane == 0) {
-            const Affine ta = Affine{desc_value(d0), __uint_as_float(static_cast<uint32_t>(desc[t * 4 + 3]))};
-            st_relaxed_u64(desc + t * 4 + 2, pack_desc(epoch, ST_INCL, 0u, apply(ta, S)));
-        }
-        // ---- recompute the trailing run, 128 elements per step, from the tile end ----
-        const int64_t rs = t * tile_elems + trail;
-        const int64_t re = (t + 1) * tile_elems;  // < n because t <= num_tiles-2
-        bool rs_head = trail > 0u;
-        if (!rs_head) rs_head = (rs == 0) || (__ldg(inv + rs) != __ldg(inv + rs - 1));
-        for (int64_t ce = re; ce > rs; ce -= 128) {
-            const int64_t i0 = ce - 128 + lane * 4;
-            float xn[4], gv[4];
-            bool ok[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t i = i0 + e;
-                ok[e] = (i >= rs);
-                xn[e] = ok[e] ? __ldg(x + i + 1) : 1.0f;  // i+1 <= re < n
-                gv[e] = ok[e] ? __ldg(g + i) : 0.0f;
-            }
-            Affine m = Affine{xn[3], gv[3]};
-            m = compose(Affine{xn[2], gv[2]}, m);
-            m = compose(Affine{xn[1], gv[1]}, m);
-            m = compose(Affine{xn[0], gv[0]}, m);
-            Affine inc = m;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                Affine q;
-                q.a = __shfl_down_sync(0xffffffffu, inc.a, d);
-                q.b = __shfl_down_sync(0xffffffffu, inc.b, d);
-                if (lane + d < 32) inc = compose(inc, q);
-            }
-            Affine exc;
-            exc.a = __shfl_down_sync(0xffffffffu, inc.a, 1);
-            exc.b = __shfl_down_sync(0xffffffffu, inc.b, 1);
-            if (lane == 31) exc = affine_id();
-            Affine tot;
-            tot.a = __shfl_sync(0xffffffffu, inc.a, 0);
-            tot.b = __shfl_sync(0xffffffffu, inc.b, 0);
-            const float sn = apply(exc, S);
-            const float s3 = fmaf(xn[3], sn, gv[3]);
-            const float s2 = fmaf(xn[2], s3, gv[2]);
-            const float s1 = fmaf(xn[1], s2, gv[1]);
-            const float s0 = fmaf(xn[0], s1, gv[0]);
-            const float sv[4] = {s0, s1, s2, s3};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t i = i0 + e;
-                if (ok[e]) {
-                    const float ev = (i == rs && rs_head) ? 1.0f : __ldg(y + i - 1);
-                    gin[i] = ev * sv[e];
-                }
-            }
-            S = apply(tot, S);
-        }
-    }
+    const uint32_t epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
+    const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
+    for (uint32_t u = gw; u < ucount; u += nw)
+        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, tile_elems, epoch, desc,
+                     lane);
+    __syncthreads();
+    if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
 
 // ---------------------------------------------------------------------------

@@ -12,8 +12,10 @@ namespace gcp {
 
 // ----------------------------------------------------------------------------
 // Workspace layout (device memory, caller owned; see include/gcp_abi.h)
-//   [0,256)    header: u32 words  ticket@0, done@16, epoch@32, abort@33, violations(u64)@byte 160
-//   [256, ...) one 32-byte slot (4 x u64) per tile of >= MIN_TILE elements:
+//   [0,256)    header: u32 words  ticket@0, done@16, epoch@32, abort@33, violations(u64)@byte 160,
+//              ucount@48 (number of unresolved tiles), exit@56
+//   [256, ...) one 32-byte slot (4 x u64) per tile of >= MIN_TILE elements, then the list of
+//              unresolved tile indices (u32 per tile):
 //     word0  K1: carry descriptor of the tile   {epoch, status TERM|AGG, flag, f32 value}
 //     word1  K1: fix-up request                 {bit31 = needs fix-up, low 31 bits = run boundary}
 //     word2  K2: inclusive carry of an AGG tile {epoch, ST_INCL, f32 value}  (epoch-tagged: never cleared)
@@ -27,6 +29,9 @@ constexpr int HDR_DONE = 16;
 constexpr int HDR_EPOCH = 32;
 constexpr int HDR_ABORT = 33;
 constexpr int HDR_VIOL64 = 20;  // index in u64 units (byte 160)
+constexpr int HDR_UCOUNT = 48;
+constexpr int HDR_EXIT = 56;
+constexpr int WS_LIST_BYTES = 4;  // per tile
 
 constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_TERM = 2, ST_INCL = 3;
 constexpr uint32_t EPOCH_MASK = 0x1FFFFFFFu;
@@ -178,17 +183,54 @@ __device__ __forceinline__ Affine warp_compose_all(Affine m, int lane) {
     return m;
 }
 
-// Last-CTA-done: reset the ticket/done counters and advance the epoch so that the next launch on
-// the stream finds a clean workspace without any memset.
-__device__ __forceinline__ void finish_launch(uint32_t *hdr, uint32_t epoch) {
+// Last-CTA-out protocols.  The workspace resets itself: no memset between launches.
+//  * finish_stream_kernel: end of a K1 that is followed by a separate K2 (LDG path): the last CTA
+//    clears the ticket/done counters; the unresolved list and the epoch are left for K2.
+//  * finish_op: end of an op (K2, or the persistent kernel that contains its own fix-up phase): the
+//    last CTA clears every counter and advances the epoch (which invalidates all word2 entries).
+__device__ __forceinline__ void finish_stream_kernel(uint32_t *hdr) {
     __threadfence();
     const uint32_t prev = atomicAdd(hdr + HDR_DONE, 1u);
     if (prev == gridDim.x - 1u) {
         hdr[HDR_TICKET] = 0u;
         hdr[HDR_DONE] = 0u;
+        __threadfence();
+    }
+}
+__device__ __forceinline__ void finish_op(uint32_t *hdr, uint32_t epoch) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(hdr + HDR_EXIT, 1u);
+    if (prev == gridDim.x - 1u) {
+        hdr[HDR_TICKET] = 0u;
+        hdr[HDR_DONE] = 0u;
+        hdr[HDR_UCOUNT] = 0u;
+        hdr[HDR_EXIT] = 0u;
         hdr[HDR_EPOCH] = epoch + 1u;
         __threadfence();
     }
+}
+
+// Grid-wide barrier between the streaming phase and the fix-up phase of a persistent kernel.
+// Called by all consumer threads of the CTA (COUNT of them, named barrier 1).  Safe because every
+// CTA of the persistent grid is resident (grid = occupancy x SMs) and nothing in the streaming
+// phase ever waits on another CTA.  Bounded like every other spin.
+template <int COUNT>
+__device__ __forceinline__ void grid_phase_barrier(uint32_t *hdr, int tid) {
+    __threadfence();
+    named_bar_sync<COUNT>(1);
+    if (tid == 0) {
+        atomicAdd(hdr + HDR_DONE, 1u);
+        uint32_t spins = 0;
+        while (ld_relaxed_u32(hdr + HDR_DONE) < gridDim.x) {
+            __nanosleep(64);
+            if (((++spins) & 63u) == 0u) {
+                if (spins >= WAIT_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+                if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
+            }
+        }
+        __threadfence();
+    }
+    named_bar_sync<COUNT>(1);
 }
 
 }  // namespace gcp

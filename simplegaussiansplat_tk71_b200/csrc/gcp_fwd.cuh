@@ -19,10 +19,11 @@
 //      it stores its results as if the prefix were the identity and publishes a carry
 //      descriptor {TERM|AGG, value} plus a fix-up request {needs, lead = #elements before
 //      the tile's first head}.  Nothing ever polls: K1 never blocks on another CTA.
-//   K2 (k_fwd_fix)  runs after K1 on the same stream, one warp per unresolved tile: it
-//      walks back over the (now complete) descriptors 32 tiles per round to the nearest
-//      TERM / already-fixed tile, and applies prefix (x) y over the `lead` elements.
-//      Costs ~2-3 us when nothing is unresolved.
+//   Fix-up (fwd_fix_tile), one warp per unresolved tile, once all descriptors of the launch
+//      are complete: walk back over the descriptors 32 tiles per round to the nearest TERM /
+//      already-fixed tile and apply prefix (x) y over the `lead` elements.  In the persistent
+//      kernel it is a second phase of the SAME launch behind a grid barrier (all CTAs are
+//      resident); the LDG path launches it as a separate kernel K2 (k_fwd_fix).
 //
 //   k_fwd_tma : persistent CTAs; a producer warp takes tile tickets, streams x/key tiles
 //               into a STAGES-deep shared-memory ring with 1-D bulk async copies
@@ -140,7 +141,8 @@ template <int OP, int WARPS, int ROWS, bool HALO_IN_SH>
 __device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t (&k)[ROWS][4], int32_t kprev,
                                               bool first_head, bool resolved, float tp, uint32_t tile, int64_t base,
                                               int64_t n, float *__restrict__ y, bool y_vec, uint32_t epoch,
-                                              uint64_t *__restrict__ desc, FwdShared<WARPS> *sh, int warp,
+                                              uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc,
+                                              uint32_t *__restrict__ ulist, FwdShared<WARPS> *sh, int warp,
                                               int lane) {
     using O = ScanOp<OP>;
     constexpr int TILE = WARPS * ROWS * 128;
@@ -202,7 +204,8 @@ __device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t
         const bool term = (ta_f != 0u) || resolved;
         const float val = ta_f ? ta_v : (resolved ? O::f(tp, ta_v) : ta_v);
         slot[0] = pack_desc(epoch, term ? ST_TERM : ST_AGG, ta_f, val);
-        slot[1] = resolved ? 0ull : static_cast<uint64_t>(FIX_FLAG | lead);
+        slot[1] = static_cast<uint64_t>(lead);
+        if (!resolved) ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
     }
     const float tp_v = resolved ? tp : O::id();
     // ---- apply carries, store ----
@@ -235,6 +238,55 @@ __device__ __forceinline__ void fwd_tile_body(float (&v)[ROWS][4], const int32_t
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fix-up of ONE tile whose prefix the halo could not resolve (one warp).  Runs when every
+// descriptor of the launch is complete (after the grid barrier of the persistent kernel, or in
+// K2 after the LDG K1), so the walk never waits.  An AGG tile that has been fixed publishes its
+// inclusive carry in word2 (epoch-tagged) so that later walkers stop there; reading a word2 that
+// is not there yet only makes a walk longer, never wrong.
+// ---------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ void fwd_fix_tile(uint32_t t, float *y, int64_t n, int tile_elems, uint32_t epoch,
+                                             uint64_t *desc, int lane) {
+    using O = ScanOp<OP>;
+    const uint32_t lead = static_cast<uint32_t>(ld_relaxed_u64(desc + static_cast<int64_t>(t) * 4 + 1));
+    float carry = O::id();
+    int64_t pb = static_cast<int64_t>(t) - 1;
+    while (true) {
+        const int64_t idx = pb - lane;
+        bool term = true;
+        float v = O::id();
+        if (idx >= 0) {
+            const uint64_t d0 = ld_relaxed_u64(desc + idx * 4);
+            term = desc_status(d0) == ST_TERM;
+            v = desc_value(d0);
+            if (!term) {
+                const uint64_t d2 = ld_relaxed_u64(desc + idx * 4 + 2);
+                if (desc_valid(d2, epoch) && desc_status(d2) == ST_INCL) {
+                    term = true;
+                    v = desc_value(d2);
+                }
+            }
+        }
+        const uint32_t tm = __ballot_sync(0xffffffffu, term);
+        const int last = tm ? (__ffs(tm) - 1) : 31;
+        float w = (lane <= last) ? v : O::id();
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+        carry = O::f(w, carry);
+        if (tm) break;
+        pb -= 32;
+    }
+    const uint64_t d0 = ld_relaxed_u64(desc + static_cast<int64_t>(t) * 4);
+    if (desc_status(d0) == ST_AGG && lane == 0)
+        st_relaxed_u64(desc + static_cast<int64_t>(t) * 4 + 2,
+                       pack_desc(epoch, ST_INCL, 0u, O::f(carry, desc_value(d0))));
+    const int64_t base = static_cast<int64_t>(t) * tile_elems;
+    int64_t end = base + lead;
+    if (end > n) end = n;
+    for (int64_t i = base + lane; i < end; i += 32) y[i] = O::f(carry, __ldcg(y + i));
+}
+
 // Guarded / unaligned-capable global load of one thread-row (4 elements).
 template <int OP>
 __device__ __forceinline__ void load_row_global(const float *__restrict__ x, const int32_t *__restrict__ key,
@@ -261,8 +313,8 @@ __device__ __forceinline__ void load_row_global(const float *__restrict__ x, con
 template <int OP, int WARPS, int ROWS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_fwd_ldg(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
-          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int in_vec, int y_vec,
-          int use_halo) {
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc,
+          uint32_t *__restrict__ ulist, int in_vec, int y_vec, int use_halo) {
     using O = ScanOp<OP>;
     constexpr int TILE = WARPS * ROWS * 128;
     __shared__ FwdShared<WARPS> sh;
@@ -299,9 +351,9 @@ k_fwd_ldg(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
             kprev = __ldg(key + wbase - 1);
         }
         fwd_tile_body<OP, WARPS, ROWS, true>(v, k, kprev, wbase == 0, false, 0.0f, tile, base, n, y, y_vec != 0,
-                                             epoch, desc, &sh, warp, lane);
+                                             epoch, hdr, desc, ulist, &sh, warp, lane);
     }
-    if (threadIdx.x == 0) finish_launch(hdr, epoch);
+    if (threadIdx.x == 0) finish_stream_kernel(hdr);
 }
 
 // ---------------------------------------------------------------------------
@@ -329,7 +381,8 @@ struct FwdTmaSmem {
 template <int OP, int WARPS, int ROWS, int STAGES>
 __global__ void __launch_bounds__((WARPS + 1) * 32)
 k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
-          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc, int y_vec, int use_halo) {
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int y_vec,
+          int use_halo) {
     using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
     using O = ScanOp<OP>;
     constexpr int TILE = L::TILE;
@@ -401,7 +454,6 @@ k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
                 mbar_arrive(&ctl->full[s]);
             }
         }
-        if (lane == 0) finish_launch(hdr, epoch);
         return;
     }
 
@@ -440,66 +492,32 @@ k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[s]);
         fwd_tile_body<OP, WARPS, ROWS, false>(v, k, kprev, wbase == 0, resolved, tp_res, tile, base, n, y, y_vec != 0,
-                                              epoch, desc, &ctl->sh[it & 1u], warp, lane);
+                                              epoch, hdr, desc, ulist, &ctl->sh[it & 1u], warp, lane);
     }
+
+    // ===================== fix-up phase (same launch) =====================
+    // Every tile of every CTA has been stored and its descriptor published once the grid barrier
+    // opens; the few tiles the halo could not resolve are then patched, one warp per tile.
+    grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);
+    const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
+    for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
+        fwd_fix_tile<OP>(__ldcg(ulist + u), y, n, TILE, epoch, desc, lane);
+    named_bar_sync<WARPS * 32>(1);
+    if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
 
-// ---------------------------------------------------------------------------
-// K2: sparse fix-up of the tiles whose prefix the halo could not resolve.
-// One warp per unresolved tile.  All K1 descriptors are complete (previous kernel on
-// the stream), so the walk never waits.  An AGG tile that has been fixed publishes its
-// inclusive carry in word2 (epoch-tagged) so that later walkers stop there; reading a
-// word2 that is not there yet only makes a walk longer, never wrong.
-// ---------------------------------------------------------------------------
+// K2 of the LDG path: the same fix-up as a separate launch (one warp per list entry).
 template <int OP>
 __global__ void __launch_bounds__(256)
-k_fwd_fix(float *__restrict__ y, int64_t n, uint32_t num_tiles, int tile_elems, const uint32_t *__restrict__ hdr,
-          uint64_t *desc) {
-    using O = ScanOp<OP>;
+k_fwd_fix(float *y, int64_t n, int tile_elems, uint32_t *hdr, uint64_t *desc, const uint32_t *ulist) {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t epoch = hdr[HDR_EPOCH];
-    for (uint32_t t = 1u + gw; t < num_tiles; t += nw) {
-        const uint64_t w1 = desc[static_cast<int64_t>(t) * 4 + 1];
-        if (!(static_cast<uint32_t>(w1) & FIX_FLAG)) continue;
-        const uint32_t lead = static_cast<uint32_t>(w1) & ~FIX_FLAG;
-        float carry = O::id();
-        int64_t pb = static_cast<int64_t>(t) - 1;
-        while (true) {
-            const int64_t idx = pb - lane;
-            bool term = true;
-            float v = O::id();
-            if (idx >= 0) {
-                const uint64_t d0 = desc[idx * 4];
-                term = desc_status(d0) == ST_TERM;
-                v = desc_value(d0);
-                if (!term) {
-                    const uint64_t d2 = ld_relaxed_u64(desc + idx * 4 + 2);
-                    if (desc_valid(d2, epoch)) {
-                        term = true;
-                        v = desc_value(d2);
-                    }
-                }
-            }
-            const uint32_t tm = __ballot_sync(0xffffffffu, term);
-            const int last = tm ? (__ffs(tm) - 1) : 31;
-            float w = (lane <= last) ? v : O::id();
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
-            carry = O::f(w, carry);
-            if (tm) break;
-            pb -= 32;
-        }
-        const uint64_t d0 = desc[static_cast<int64_t>(t) * 4];
-        if (desc_status(d0) == ST_AGG && lane == 0)
-            st_relaxed_u64(desc + static_cast<int64_t>(t) * 4 + 2,
-                           pack_desc(epoch, ST_INCL, 0u, O::f(carry, desc_value(d0))));
-        const int64_t base = static_cast<int64_t>(t) * tile_elems;
-        int64_t end = base + lead;
-        if (end > n) end = n;
-        for (int64_t i = base + lane; i < end; i += 32) y[i] = O::f(carry, y[i]);
-    }
+    const uint32_t epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
+    const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
+    for (uint32_t u = gw; u < ucount; u += nw) fwd_fix_tile<OP>(__ldcg(ulist + u), y, n, tile_elems, epoch, desc, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
 
 }  // namespace gcp
