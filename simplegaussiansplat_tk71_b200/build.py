@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libgcp_b200.so")
 SOURCES = ["gcp_abi.cu"]
-HEADERS = ["gcp_device.cuh", "gcp_fwd.cuh", "gcp_bwd.cuh"]
+HEADERS = ["gcp_device.cuh", "gcp_fwd.cuh", "gcp_bwd.cuh", "gcp_blk.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",

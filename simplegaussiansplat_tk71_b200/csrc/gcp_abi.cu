@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include "gcp_abi.h"
+#include "gcp_blk.cuh"
 #include "gcp_bwd.cuh"
 #include "gcp_fwd.cuh"
 
@@ -75,6 +76,36 @@ int persistent_ctas_per_sm(int threads, size_t smem) {
 
 inline uint32_t tiles_for(int64_t n, int tile) { return static_cast<uint32_t>((n + tile - 1) / tile); }
 
+// ---- 2-D tensor maps ([n/32][32] elements, 128-byte rows, 128B swizzle) for the blocked kernels ----
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+bool make_tile_map(CUtensorMap *tm, const void *ptr, int64_t n, int tile, bool is_int) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr || n < tile) return false;
+    const cuuint64_t dims[2] = {32, static_cast<cuuint64_t>(n / 32)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(tile / 32)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, is_int ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+              const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // K2 grid: one warp per tile, at most 4 CTAs of 8 warps per SM (grid-stride beyond that)
 inline unsigned fix_grid(uint32_t nt) {
     unsigned blocks = (nt + 7u) / 8u;
@@ -122,13 +153,32 @@ int launch_fwd_tma(const float *x, const int32_t *key, float *y, int64_t n, Ws w
     return static_cast<int>(cudaGetLastError());
 }
 
-constexpr int FWD_NUM_VARIANTS = 8;
+template <int OP, int WARPS, int STAGES>
+int launch_fwd_blk(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
+    using L = FwdBlkSmem<WARPS, STAGES>;
+    CUtensorMap tmx, tmk;
+    if (!make_tile_map(&tmx, x, n, L::TILE, false) || !make_tile_map(&tmk, key, n, L::TILE, true))
+        return launch_fwd_ldg<OP, 8, 4>(x, key, y, n, ws, s);  // tiny n, or no driver entry point
+    const uint32_t nt = tiles_for(n, L::TILE);
+    constexpr auto kern = k_fwd_blk<OP, WARPS, STAGES>;
+    const int threads = (WARPS + 1) * 32;
+    const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
+    uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
+    if (grid > nt) grid = nt;
+    kern<<<grid, threads, L::BYTES, s>>>(tmx, tmk, x, key, y, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
+                                         aligned16(y) ? 1 : 0, g_option[0]);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
+constexpr int FWD_NUM_VARIANTS = 11;
 const char *const kFwdNames[FWD_NUM_VARIANTS] = {
     "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
     "tma_w8_r4_s3 (tile 4096, 96 KB ring)", "tma_w8_r4_s2 (tile 4096, 64 KB ring)",
     "tma_w8_r2_s4 (tile 2048, 64 KB ring)", "tma_w4_r4_s4 (tile 2048, 160 thr)",
-    "tma_w16_r4_s3 (tile 8192, 192 KB ring)"};
-constexpr int FWD_DEFAULT = 4;   // tma_w8_r4_s2
+    "tma_w16_r4_s3 (tile 8192, 192 KB ring)", "blk_w8_s2 (16 contiguous elems/lane, swizzled tensor TMA)",
+    "blk_w8_s3 (tile 4096, 96 KB ring)", "blk_w4_s4 (tile 2048, 64 KB ring)"};
+constexpr int FWD_DEFAULT = 8;   // blk_w8_s2
 
 template <int OP>
 int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *wsp, size_t ws_bytes,
@@ -142,7 +192,7 @@ int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int v = g_variant[0] < 0 ? FWD_DEFAULT : g_variant[0];
     const bool in_al = aligned16(x) && aligned16(key);
-    if (v >= 3 && !in_al) v = 0;  // bulk copies need 16-byte aligned sources
+    if (v >= 3 && !in_al) v = 2;  // bulk copies need 16-byte aligned sources: best LDG variant
     switch (v) {
         case 0: return launch_fwd_ldg<OP, 8, 4>(x, key, y, n, ws, s);
         case 1: return launch_fwd_ldg<OP, 8, 2>(x, key, y, n, ws, s);
@@ -152,6 +202,9 @@ int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *
         case 5: return launch_fwd_tma<OP, 8, 2, 4>(x, key, y, n, ws, s);
         case 6: return launch_fwd_tma<OP, 4, 4, 4>(x, key, y, n, ws, s);
         case 7: return launch_fwd_tma<OP, 16, 4, 3>(x, key, y, n, ws, s);
+        case 8: return launch_fwd_blk<OP, 8, 2>(x, key, y, n, ws, s);
+        case 9: return launch_fwd_blk<OP, 8, 3>(x, key, y, n, ws, s);
+        case 10: return launch_fwd_blk<OP, 4, 4>(x, key, y, n, ws, s);
         default: return GCP_ERR_INVALID_ARG;
     }
 }
@@ -193,13 +246,35 @@ int launch_bwd_tma(const float *x, const float *y, const float *g, const int32_t
     return static_cast<int>(cudaGetLastError());
 }
 
-constexpr int BWD_NUM_VARIANTS = 8;
+template <int WARPS, int STAGES, int MINB>
+int launch_bwd_blk(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
+                   Ws ws, cudaStream_t s) {
+    using L = BwdBlkSmem<WARPS, STAGES>;
+    CUtensorMap tmx, tmg, tmi;
+    if (!make_tile_map(&tmx, x, n, L::TILE, false) || !make_tile_map(&tmg, g, n, L::TILE, false) ||
+        !make_tile_map(&tmi, inv, n, L::TILE, true))
+        return launch_bwd_ldg<8, 4>(x, y, g, inv, gin, n, ws, s);
+    const uint32_t nt = tiles_for(n, L::TILE);
+    constexpr auto kern = k_bwd_blk<WARPS, STAGES, MINB>;
+    const int threads = (WARPS + 1) * 32;
+    const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
+    uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
+    if (grid > nt) grid = nt;
+    kern<<<grid, threads, L::BYTES, s>>>(tmx, tmg, tmi, x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
+                                         aligned16(gin) ? 1 : 0, g_option[0]);
+    ++t_launches;
+    return static_cast<int>(cudaGetLastError());
+}
+
+constexpr int BWD_NUM_VARIANTS = 12;
 const char *const kBwdNames[BWD_NUM_VARIANTS] = {
     "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
     "tma_w8_r4_s2 (tile 4096, 96 KB ring, 2 CTA/SM)", "tma_w8_r2_s4 (tile 2048, 96 KB ring, 2 CTA/SM)",
     "tma_w8_r2_s3 (tile 2048, 72 KB ring, 3 CTA/SM)", "tma_w8_r4_s4 (tile 4096, 192 KB ring, 1 CTA/SM)",
-    "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)"};
-constexpr int BWD_DEFAULT = 5;   // tma_w8_r2_s3
+    "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)", "blk_w8_s2 (16 contiguous elems/lane, 2 CTA/SM)",
+    "blk_w8_s4 (tile 4096, 192 KB ring, 1 CTA/SM)", "blk_w4_s3 (tile 2048, 72 KB ring, 3 CTA/SM)",
+    "blk_w4_s4 (tile 2048, 96 KB ring, 2 CTA/SM)"};
+constexpr int BWD_DEFAULT = 10;  // blk_w4_s3
 
 }  // namespace
 
@@ -257,7 +332,7 @@ int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int v = g_variant[1] < 0 ? BWD_DEFAULT : g_variant[1];
     const bool in_al = aligned16(x) && aligned16(gout) && aligned16(inv);
-    if (v >= 3 && !in_al) v = 0;
+    if (v >= 3 && !in_al) v = 2;
     switch (v) {
         case 0: return launch_bwd_ldg<8, 4>(x, y, gout, inv, gin, n, ws, s);
         case 1: return launch_bwd_ldg<8, 2>(x, y, gout, inv, gin, n, ws, s);
@@ -267,6 +342,10 @@ int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const
         case 5: return launch_bwd_tma<8, 2, 3, 3>(x, y, gout, inv, gin, n, ws, s);
         case 6: return launch_bwd_tma<8, 4, 4, 1>(x, y, gout, inv, gin, n, ws, s);
         case 7: return launch_bwd_tma<16, 2, 2, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 8: return launch_bwd_blk<8, 2, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 9: return launch_bwd_blk<8, 4, 1>(x, y, gout, inv, gin, n, ws, s);
+        case 10: return launch_bwd_blk<4, 3, 3>(x, y, gout, inv, gin, n, ws, s);
+        case 11: return launch_bwd_blk<4, 4, 2>(x, y, gout, inv, gin, n, ws, s);
         default: return GCP_ERR_INVALID_ARG;
     }
 }

@@ -31,8 +31,8 @@ def carry_mode(request):
     ops.set_option(0, 1)
 
 
-FWD_VARIANTS = list(range(8))
-BWD_VARIANTS = list(range(8))
+FWD_VARIANTS = list(range(11))
+BWD_VARIANTS = list(range(12))
 
 
 def _pow2_values(n, rng, span=12):
@@ -142,7 +142,7 @@ def test_forward_boundaries_on_tile_edges_and_long_segments(oracle, variant):
     assert np.all(np.abs(got - ref) <= 1e-6 + 1e-5 * np.abs(ref) + 8 * seq), np.abs(got - ref).max()
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 8])
 def test_forward_unaligned_slices_and_zeros(oracle, variant):
     rng = np.random.default_rng(11)
     n = 50_001
@@ -236,7 +236,7 @@ def test_backward_tile_edges_long_segments_signed_grads(oracle, variant):
                  f"bwd giant v{variant}", rtol=2e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 8])
 def test_backward_exact_at_zeros_and_unaligned(oracle, variant):
     rng = np.random.default_rng(17)
     n = 60_001
