@@ -274,7 +274,7 @@ const char *const kBwdNames[BWD_NUM_VARIANTS] = {
     "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)", "blk_w8_s2 (16 contiguous elems/lane, 2 CTA/SM)",
     "blk_w8_s4 (tile 4096, 192 KB ring, 1 CTA/SM)", "blk_w4_s3 (tile 2048, 72 KB ring, 3 CTA/SM)",
     "blk_w4_s4 (tile 2048, 96 KB ring, 2 CTA/SM)"};
-constexpr int BWD_DEFAULT = 10;  // blk_w4_s3
+constexpr int BWD_DEFAULT = 8;   // blk_w8_s2
 
 }  // namespace
 

@@ -210,7 +210,8 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     using O = ScanOp<OP>;
     constexpr int TILE = L::TILE;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for the 128B swizzle atom; plain pointer arithmetic keeps the shared address space
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -228,20 +229,46 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
 
     if (warp == WARPS) {
         // ===================== producer warp =====================
+        // Software pipelined: the halo loads of tile i are issued right after its TMA copies and
+        // consumed at the top of iteration i+1, so their latency overlaps the next tile's issue;
+        // tickets are fetched two iterations ahead (lane 0 keeps q0 = ready, q1 = in flight).
         const uint64_t pol = policy_evict_first();
-        uint32_t t_next = 0;
+        uint32_t q0 = 0, q1 = 0;
         if (lane == 0) {
             tma_prefetch_desc(&tm_x);
             tma_prefetch_desc(&tm_k);
-            t_next = atomicAdd(hdr + HDR_TICKET, 1u);
+            q0 = atomicAdd(hdr + HDR_TICKET, 1u);
+            q1 = atomicAdd(hdr + HDR_TICKET, 1u);
         }
-        t_next = __shfl_sync(0xffffffffu, t_next, 0);
+        bool pending = false;
+        int ps = 0;
+        int64_t pbase = 0;
+        float4 ha = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 hb = make_int4(0, 0, 0, 0);
+        int32_t hkf = 0;
         for (uint32_t it = 0;; ++it) {
+            if (pending) {
+                float P = O::id();
+                int32_t kprev = 0;
+                bool res;
+                if (use_halo) {
+                    res = halo_prefix_finish<OP>(ha, hb, hkf, lane, P, kprev);
+                } else {
+                    res = false;
+                    kprev = hkf;
+                }
+                if (lane == 0) {
+                    ctl->halo[ps] = kprev;
+                    ctl->resolved[ps] = res ? 1u : 0u;
+                    ctl->tp[ps] = P;
+                    mbar_arrive(&ctl->full[ps]);
+                }
+                pending = false;
+            }
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-            __syncwarp();
-            const uint32_t t = t_next;
+            const uint32_t t = __shfl_sync(0xffffffffu, q0, 0);
             if (t >= num_tiles) {
                 if (lane == 0) {
                     ctl->tile[s] = t;
@@ -251,7 +278,6 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                 break;
             }
             const int64_t base = static_cast<int64_t>(t) * TILE;
-            uint32_t t_pref = 0;
             if (lane == 0) {
                 ctl->tile[s] = t;
                 if (base + TILE <= n) {
@@ -264,23 +290,29 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     ctl->mode[s] = 0u;
                     mbar_arrive(&ctl->full[s]);
                 }
-                t_pref = atomicAdd(hdr + HDR_TICKET, 1u);
+                q0 = q1;
+                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
             }
-            float P = O::id();
-            int32_t kprev = 0;
-            bool res = (t == 0u);
-            if (t > 0u) {
-                if (use_halo) res = halo_prefix<OP>(x, key, base, lane, true, P, kprev);
-                else kprev = __ldg(key + base - 1);
-            }
-            t_next = __shfl_sync(0xffffffffu, t_pref, 0);
-            if (lane == 0) {
-                ctl->halo[s] = kprev;
-                ctl->resolved[s] = res ? 1u : 0u;
-                ctl->tp[s] = P;
-                mbar_arrive(&ctl->full[s]);
+            if (t == 0u) {
+                if (lane == 0) {
+                    ctl->halo[s] = 0;
+                    ctl->resolved[s] = 1u;
+                    ctl->tp[s] = O::id();
+                    mbar_arrive(&ctl->full[s]);
+                }
+            } else {
+                // issue the halo loads now, use them next iteration
+                if (use_halo) {
+                    halo_prefix_issue(x, key, base, lane, ha, hb, hkf);
+                } else {
+                    hkf = __ldg(key + base - 1);
+                }
+                pending = true;
+                ps = s;
+                pbase = base;
             }
         }
+        (void)pbase;
         return;
     }
 
@@ -520,7 +552,8 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     using L = BwdBlkSmem<WARPS, STAGES>;
     constexpr int TILE = L::TILE;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for the 128B swizzle atom; plain pointer arithmetic keeps the shared address space
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -538,21 +571,42 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
 
     if (warp == WARPS) {
         // ===================== producer warp =====================
+        // Software pipelined like the forward's: halo loads issued in iteration i are consumed at
+        // the top of iteration i+1; tickets are fetched two iterations ahead.
         const uint64_t pol = policy_evict_first();
-        uint32_t t_next = 0;
+        uint32_t q0 = 0, q1 = 0;
         if (lane == 0) {
             tma_prefetch_desc(&tm_x);
             tma_prefetch_desc(&tm_g);
             tma_prefetch_desc(&tm_i);
-            t_next = atomicAdd(hdr + HDR_TICKET, 1u);
+            q0 = atomicAdd(hdr + HDR_TICKET, 1u);
+            q1 = atomicAdd(hdr + HDR_TICKET, 1u);
         }
-        t_next = __shfl_sync(0xffffffffu, t_next, 0);
+        bool pending = false;
+        int ps = 0;
+        HaloSuffixRegs hr;
+        int32_t ip = -1;
+        float yp = 1.0f;
         for (uint32_t it = 0;; ++it) {
+            if (pending) {
+                float R = 0.0f, xq = 0.0f;
+                int32_t in = -1;
+                const bool res = halo_suffix_finish(hr, lane, use_halo != 0, R, in, xq);
+                if (lane == 0) {
+                    ctl->iprev[ps] = ip;
+                    ctl->yprev[ps] = yp;
+                    ctl->inext[ps] = in;
+                    ctl->xnext[ps] = xq;
+                    ctl->resolved[ps] = res ? 1u : 0u;
+                    ctl->rn[ps] = R;
+                    mbar_arrive(&ctl->full[ps]);
+                }
+                pending = false;
+            }
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-            __syncwarp();
-            const uint32_t t = t_next;
+            const uint32_t t = __shfl_sync(0xffffffffu, q0, 0);
             if (t >= num_tiles) {
                 if (lane == 0) {
                     ctl->tile[s] = t;
@@ -564,9 +618,6 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             const uint32_t tile = num_tiles - 1u - t;
             const int64_t base = static_cast<int64_t>(tile) * TILE;
             const int64_t end = base + TILE;
-            uint32_t t_pref = 0;
-            int32_t ip = -1;
-            float yp = 1.0f;
             if (lane == 0) {
                 ctl->tile[s] = t;
                 if (end <= n) {
@@ -581,34 +632,18 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     ctl->mode[s] = 0u;
                     mbar_arrive(&ctl->full[s]);
                 }
-                t_pref = atomicAdd(hdr + HDR_TICKET, 1u);
+                q0 = q1;
+                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+                ip = -1;
+                yp = 1.0f;
                 if (base > 0) {
                     ip = __ldg(inv + base - 1);
                     yp = __ldg(y + base - 1);
                 }
             }
-            float R = 0.0f, xq = 0.0f;
-            int32_t in = -1;
-            bool res;
-            if (use_halo) {
-                res = halo_suffix(x, g, inv, end, n, lane, true, R, in, xq);
-            } else {
-                res = (end >= n);
-                if (end < n) {
-                    in = __ldg(inv + end);
-                    xq = __ldg(x + end);
-                }
-            }
-            t_next = __shfl_sync(0xffffffffu, t_pref, 0);
-            if (lane == 0) {
-                ctl->iprev[s] = ip;
-                ctl->yprev[s] = yp;
-                ctl->inext[s] = in;
-                ctl->xnext[s] = xq;
-                ctl->resolved[s] = res ? 1u : 0u;
-                ctl->rn[s] = R;
-                mbar_arrive(&ctl->full[s]);
-            }
+            halo_suffix_issue(x, g, inv, end, n, lane, use_halo != 0, hr);
+            pending = true;
+            ps = s;
         }
         return;
     }

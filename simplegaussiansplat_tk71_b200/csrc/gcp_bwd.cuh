@@ -95,6 +95,75 @@ __device__ __forceinline__ bool halo_suffix(const float *__restrict__ x, const f
     return m.a == 0.0f;
 }
 
+// halo_suffix split in two for a software-pipelined producer (issue in iteration i, finish in i+1).
+struct HaloSuffixRegs {
+    float xv[4], gv[4];
+    int32_t iv[4];
+    int32_t ilast;
+    bool beyond;  // end >= n: nothing follows the tile
+};
+__device__ __forceinline__ void halo_suffix_issue(const float *__restrict__ x, const float *__restrict__ g,
+                                                  const int32_t *__restrict__ inv, int64_t end, int64_t n, int lane,
+                                                  bool full_window, HaloSuffixRegs &r) {
+    r.beyond = end >= n;
+    if (r.beyond) return;
+    r.ilast = __ldg(inv + end - 1);
+    if (!full_window) {  // halo resolution off: only the two values the consumers need
+        r.xv[0] = __ldg(x + end);
+        r.iv[0] = __ldg(inv + end);
+        return;
+    }
+    const int64_t h0 = end + lane * 4;
+    if (h0 + 3 < n) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(x + h0));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(g + h0));
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(inv + h0));
+        r.xv[0] = a.x; r.xv[1] = a.y; r.xv[2] = a.z; r.xv[3] = a.w;
+        r.gv[0] = b.x; r.gv[1] = b.y; r.gv[2] = b.z; r.gv[3] = b.w;
+        r.iv[0] = c.x; r.iv[1] = c.y; r.iv[2] = c.z; r.iv[3] = c.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool in = h0 + e < n;
+            r.xv[e] = in ? __ldg(x + h0 + e) : 1.0f;
+            r.gv[e] = in ? __ldg(g + h0 + e) : 0.0f;
+            r.iv[e] = in ? __ldg(inv + h0 + e) : -1;
+        }
+    }
+}
+__device__ __forceinline__ bool halo_suffix_finish(const HaloSuffixRegs &r, int lane, bool full_window, float &R,
+                                                   int32_t &inext, float &xnext) {
+    if (r.beyond) {
+        R = 0.0f;
+        inext = -1;
+        xnext = 0.0f;
+        return true;
+    }
+    if (!full_window) {
+        R = 0.0f;
+        inext = r.iv[0];
+        xnext = r.xv[0];
+        return false;
+    }
+    int32_t qn = __shfl_down_sync(0xffffffffu, r.iv[0], 1);
+    float xq = __shfl_down_sync(0xffffffffu, r.xv[0], 1);
+    const bool known = lane < 31;
+    if (!known) xq = 1.0f;
+    inext = __shfl_sync(0xffffffffu, r.iv[0], 0);
+    xnext = __shfl_sync(0xffffffffu, r.xv[0], 0);
+    Affine m = Affine{(known && qn != r.iv[3]) ? 0.0f : xq, r.gv[3]};
+    m = compose(Affine{(r.iv[3] != r.iv[2]) ? 0.0f : r.xv[3], r.gv[2]}, m);
+    m = compose(Affine{(r.iv[2] != r.iv[1]) ? 0.0f : r.xv[2], r.gv[1]}, m);
+    m = compose(Affine{(r.iv[1] != r.iv[0]) ? 0.0f : r.xv[1], r.gv[0]}, m);
+    m = warp_compose_all(m, lane);
+    if (r.ilast != inext) {
+        R = 0.0f;
+        return true;
+    }
+    R = m.b;
+    return m.a == 0.0f;
+}
+
 // Everything after x / g / inv of the tile are in registers.
 //   iprev : inv of the element before this warp's span (used by lane 0), -1 if none
 //   inext : inv of the element after this warp's span (used by lane 0!), -1 if none

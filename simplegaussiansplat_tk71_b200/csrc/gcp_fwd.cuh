@@ -133,6 +133,40 @@ __device__ __forceinline__ bool halo_prefix(const float *__restrict__ x, const i
     return m != 0u;
 }
 
+// The same halo resolution split in two so that a producer can issue the loads of tile i and
+// consume them one iteration later (software pipelining).  16-byte aligned inputs only.
+__device__ __forceinline__ void halo_prefix_issue(const float *__restrict__ x, const int32_t *__restrict__ key,
+                                                  int64_t base, int lane, float4 &a, int4 &b, int32_t &kfirst) {
+    const int64_t h0 = base - 128 + lane * 4;
+    a = __ldg(reinterpret_cast<const float4 *>(x + h0));
+    b = __ldg(reinterpret_cast<const int4 *>(key + h0));
+    kfirst = __ldg(key + base);
+}
+template <int OP>
+__device__ __forceinline__ bool halo_prefix_finish(const float4 a, const int4 b, int32_t kfirst, int lane, float &P,
+                                                   int32_t &kprev) {
+    using O = ScanOp<OP>;
+    const int32_t pk = __shfl_up_sync(0xffffffffu, b.w, 1);
+    const uint32_t h = ((lane > 0 && b.x != pk) ? 1u : 0u) | (b.y != b.x ? 2u : 0u) | (b.z != b.y ? 4u : 0u) |
+                       (b.w != b.z ? 8u : 0u);
+    kprev = __shfl_sync(0xffffffffu, b.w, 31);
+    const uint32_t m = __ballot_sync(0xffffffffu, h != 0u);
+    float v = a.x;
+    v = (h & 2u) ? a.y : O::f(v, a.y);
+    v = (h & 4u) ? a.z : O::f(v, a.z);
+    v = (h & 8u) ? a.w : O::f(v, a.w);
+    const int last = 31 - __clz(m);
+    float w = (lane >= last) ? v : O::id();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+    if (kfirst != kprev) {
+        P = O::id();
+        return true;
+    }
+    P = w;
+    return m != 0u;
+}
+
 // Everything after the tile's x/key values are in registers.
 //   kprev      : key of the element just before this warp's span (only lane 0 needs it)
 //   first_head : this warp's first element is global element 0
