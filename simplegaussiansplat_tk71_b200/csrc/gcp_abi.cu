@@ -45,7 +45,7 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 struct Ws {
     uint32_t *hdr;
     uint64_t *desc;
-    // list of unresolved tiles: right behind the descriptors of THIS launch's tile count
+    // lists of unresolved tiles (two, num_tiles entries each): right behind the descriptors of THIS launch's tile count
     uint32_t *ulist(uint32_t num_tiles) const { return reinterpret_cast<uint32_t *>(desc + 4ull * num_tiles); }
 };
 int check_ws(void *ws, size_t ws_bytes, int64_t n, Ws *out) {

@@ -82,6 +82,18 @@ __device__ __forceinline__ void ldg_blocked(const T *__restrict__ p, int64_t gi,
 #pragma unroll
     for (int e = 0; e < 16; ++e) out[e] = (gi + e < n) ? __ldg(p + gi + e) : pad;
 }
+// full-tile variant: four 128-bit loads per lane (each lane reads 64 contiguous bytes)
+template <typename T>
+__device__ __forceinline__ void ldg_blocked_vec(const T *__restrict__ p, int64_t gi, T (&out)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p + gi) + j);
+        out[4 * j + 0] = *reinterpret_cast<const T *>(&q.x);
+        out[4 * j + 1] = *reinterpret_cast<const T *>(&q.y);
+        out[4 * j + 2] = *reinterpret_cast<const T *>(&q.z);
+        out[4 * j + 3] = *reinterpret_cast<const T *>(&q.w);
+    }
+}
 __device__ __forceinline__ void stg_blocked_guarded(float *__restrict__ p, int64_t gi, int64_t n, const float (&o)[16]) {
 #pragma unroll
     for (int e = 0; e < 16; ++e)
@@ -375,14 +387,14 @@ struct BwdBlkShared {
     int32_t lt[WARPS];
 };
 
-// out: grad_in of the lane's 16 elements
-template <int WARPS>
+// out: grad_in of the lane's 16 elements.  PUBLISH = false: fix-up re-run of a tile (descriptors untouched).
+template <int WARPS, bool PUBLISH>
 __device__ __forceinline__ void bwd_blk_compute(const float (&x)[16], const float (&g)[16], const int32_t (&iv)[16],
                                                 int32_t iprev, int32_t inext, float xnext, float y_prev,
                                                 bool resolved, float rn, uint32_t tile, uint32_t epoch,
                                                 uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc,
-                                                uint32_t *__restrict__ ulist, BwdBlkShared<WARPS> *sh, int warp,
-                                                int lane, float (&out)[16]) {
+                                                uint32_t *__restrict__ ulist, uint32_t *__restrict__ ulist2,
+                                                BwdBlkShared<WARPS> *sh, int warp, int lane, float (&out)[16]) {
     static_assert(WARPS < 32, "one lane per warp in the cross-warp step");
     const uint32_t lanes_lt = (1u << lane) - 1u;
     const uint32_t lanes_le = lanes_lt | (1u << lane);
@@ -490,14 +502,17 @@ __device__ __forceinline__ void bwd_blk_compute(const float (&x)[16], const floa
         const int jw = 31 - __clz(lm);
         trail = static_cast<uint32_t>(jw * BLK_WSPAN + __shfl_sync(0xffffffffu, jl, jw) + 1);
     }
-    if (warp == 0 && lane == 0) {
+    if (PUBLISH && warp == 0 && lane == 0) {
         uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
         const bool term = resolved || (ta.a == 0.0f);
         slot[0] = term ? pack_desc(epoch, ST_TERM, 0u, resolved ? apply(ta, rn) : ta.b)
                        : pack_desc(epoch, ST_AGG, 0u, ta.a);
         slot[1] = static_cast<uint64_t>(trail);
         slot[3] = static_cast<uint64_t>(__float_as_uint(ta.b));
-        if (!resolved) ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
+        if (!resolved) {
+            if (WARPS * BLK_WSPAN - trail > LONG_RUN) ulist2[atomicAdd(hdr + HDR_UCOUNT2, 1u)] = tile;
+            else ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
+        }
     }
     // ---- pass 2 ----
     float s = apply(sx, apply(ws, resolved ? rn : 0.0f));  // S of the element right after the lane
@@ -695,8 +710,8 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             }
         }
         float out[16];
-        bwd_blk_compute<WARPS>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc, ulist,
-                               &ctl->sh[it & 1u], warp, lane, out);
+        bwd_blk_compute<WARPS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc,
+                                     ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out);
         if (staged && out_vec) {
             // the g array of the stage is only ever read by the warp that owns the span: reuse it
             // (x is read across warp boundaries for x_next, inv for the head/tail halos)
@@ -710,9 +725,46 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
 
     // ===================== fix-up phase (same launch) =====================
     grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);
+    // (a) short trailing runs: one warp per tile recomputes just the run
     const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
     for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
         bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch, desc, lane);
+    // (b) long trailing runs (tiles inside segments of thousands of elements): warp 0 finds R by
+    //     walking the descriptors, then the whole CTA re-runs the tile with R known.
+    const uint32_t ucount2 = ld_relaxed_u32(hdr + HDR_UCOUNT2);
+    unsigned char *gs0 = smem + L::ARR_BYTES;  // every stage is idle now: staging area for the stores
+    for (uint32_t u = blockIdx.x, k2 = 0; u < ucount2; u += gridDim.x, ++k2) {
+        const int64_t t = static_cast<int64_t>(__ldcg(ulist + num_tiles + u));
+        float *rbox = reinterpret_cast<float *>(&ctl->rn[0]);
+        if (warp == 0) {
+            const float R = bwd_fix_walk(t, num_tiles, epoch, desc, lane);
+            if (lane == 0) *rbox = R;
+        }
+        named_bar_sync<WARPS * 32>(1);
+        const float R = *rbox;
+        const int64_t base = t * TILE;  // t <= num_tiles-2: a full tile with a successor
+        const int64_t wbase = base + warp * BLK_WSPAN;
+        float xv[16], gv[16], out[16];
+        int32_t iv[16];
+        ldg_blocked_vec<float>(x, wbase + lane * BLK_EPL, xv);
+        ldg_blocked_vec<float>(g, wbase + lane * BLK_EPL, gv);
+        ldg_blocked_vec<int32_t>(inv, wbase + lane * BLK_EPL, iv);
+        int32_t iprev = -1, inext = -1;
+        float xnext = 0.0f;
+        if (lane == 0) {
+            if (wbase > 0) iprev = __ldg(inv + wbase - 1);
+            inext = __ldg(inv + wbase + BLK_WSPAN);
+            xnext = __ldg(x + wbase + BLK_WSPAN);
+        }
+        const float y_prev = (base > 0) ? __ldg(y + base - 1) : 1.0f;
+        bwd_blk_compute<WARPS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, true, R, static_cast<uint32_t>(t), epoch,
+                                      hdr, desc, ulist, ulist, &ctl->sh[k2 & 1u], warp, lane, out);
+        if (out_vec) {
+            store_blocked_via_smem(gs0, warp, lane, out, gin + wbase);
+        } else {
+            stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+        }
+    }
     named_bar_sync<WARPS * 32>(1);
     if (threadIdx.x == 0) finish_op(hdr, epoch);
 }

@@ -177,7 +177,8 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
                                               int64_t base, int64_t n, float *__restrict__ gin, bool out_vec,
                                               uint32_t epoch, uint32_t *__restrict__ hdr,
                                               uint64_t *__restrict__ desc, uint32_t *__restrict__ ulist,
-                                              BwdShared<WARPS> *sh, int warp, int lane) {
+                                              uint32_t *__restrict__ ulist2, BwdShared<WARPS> *sh, int warp,
+                                              int lane) {
     static_assert(WARPS < 32, "cross-warp step uses one lane per warp (and lane WARPS as the identity)");
     constexpr int TILE = WARPS * ROWS * 128;
     const uint32_t lanes_lt = (1u << lane) - 1u;
@@ -327,7 +328,10 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
                        : pack_desc(epoch, ST_AGG, 0u, ta.a);
         slot[1] = static_cast<uint64_t>(trail);
         slot[3] = static_cast<uint64_t>(__float_as_uint(ta.b));
-        if (!resolved) ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
+        if (!resolved) {
+            if (TILE - trail > LONG_RUN) ulist2[atomicAdd(hdr + HDR_UCOUNT2, 1u)] = tile;
+            else ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
+        }
     }
     // S at the first element after my warp's span
     const float s_after_warp = apply(ws, resolved ? rn : 0.0f);
@@ -375,11 +379,9 @@ __device__ __forceinline__ void bwd_tile_body(const float (&x)[ROWS][4], const f
 // contains no tail, so S there is a plain reverse affine scan seeded with R;
 // E_i = y[i-1] (1 at the run start when it is a segment head).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void bwd_fix_tile(int64_t t, const float *__restrict__ x, const float *__restrict__ y,
-                                             const float *__restrict__ g, const int32_t *__restrict__ inv,
-                                             float *gin, int64_t n, uint32_t num_tiles, int tile_elems,
-                                             uint32_t epoch, uint64_t *desc, int lane) {
-    const uint32_t trail = static_cast<uint32_t>(ld_relaxed_u64(desc + t * 4 + 1));
+// Walk forward over the (complete) descriptors to the nearest tile whose S(first element) is known;
+// returns S at the first element of tile t+1 and publishes tile t's own inclusive carry (word2).
+__device__ __forceinline__ float bwd_fix_walk(int64_t t, uint32_t num_tiles, uint32_t epoch, uint64_t *desc, int lane) {
     // ---- walk forward to the nearest tile whose S(first element) is known ----
     Affine carry = affine_id();
     int64_t nb = t + 1;
@@ -410,12 +412,21 @@ __device__ __forceinline__ void bwd_fix_tile(int64_t t, const float *__restrict_
         if (tmk) break;
         nb += 32;
     }
-    float S = carry.b;  // S at the first element of tile t+1
+    const float S = carry.b;  // S at the first element of tile t+1
     const uint64_t d0 = ld_relaxed_u64(desc + t * 4);
     if (desc_status(d0) == ST_AGG && lane == 0) {
         const Affine ta = Affine{desc_value(d0), __uint_as_float(static_cast<uint32_t>(ld_relaxed_u64(desc + t * 4 + 3)))};
         st_relaxed_u64(desc + t * 4 + 2, pack_desc(epoch, ST_INCL, 0u, apply(ta, S)));
     }
+    return S;
+}
+
+__device__ __forceinline__ void bwd_fix_tile(int64_t t, const float *__restrict__ x, const float *__restrict__ y,
+                                             const float *__restrict__ g, const int32_t *__restrict__ inv,
+                                             float *gin, int64_t n, uint32_t num_tiles, int tile_elems,
+                                             uint32_t epoch, uint64_t *desc, int lane) {
+    const uint32_t trail = static_cast<uint32_t>(ld_relaxed_u64(desc + t * 4 + 1));
+    float S = bwd_fix_walk(t, num_tiles, epoch, desc, lane);
     // ---- recompute the trailing run, 128 elements per step, from the tile end ----
     const int64_t rs = t * tile_elems + trail;
     const int64_t re = (t + 1) * tile_elems;  // < n: the last tile always resolves
@@ -548,7 +559,7 @@ k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float 
             xnext = __ldg(x + wend);
         }
         bwd_tile_body<WARPS, ROWS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, false, 0.0f, tile, base, n, gin,
-                                         out_vec != 0, epoch, hdr, desc, ulist, &sh, warp, lane);
+                                         out_vec != 0, epoch, hdr, desc, ulist, ulist + num_tiles, &sh, warp, lane);
     }
     if (threadIdx.x == 0) finish_stream_kernel(hdr);
 }
@@ -726,7 +737,8 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[s]);
         bwd_tile_body<WARPS, ROWS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, base, n,
-                                          gin, out_vec != 0, epoch, hdr, desc, ulist, &ctl->sh[it & 1u], warp, lane);
+                                          gin, out_vec != 0, epoch, hdr, desc, ulist, ulist + num_tiles,
+                                          &ctl->sh[it & 1u], warp, lane);
     }
 
     // ===================== fix-up phase (same launch) =====================
@@ -734,6 +746,10 @@ k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float 
     const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
     for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
         bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch, desc, lane);
+    const uint32_t ucount2 = ld_relaxed_u32(hdr + HDR_UCOUNT2);  // long runs: warp-level here too (legacy variant)
+    for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount2; u += gridDim.x * WARPS)
+        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + num_tiles + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch,
+                     desc, lane);
     named_bar_sync<WARPS * 32>(1);
     if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
@@ -751,6 +767,10 @@ k_bwd_fix(const float *__restrict__ x, const float *__restrict__ y, const float 
     for (uint32_t u = gw; u < ucount; u += nw)
         bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, tile_elems, epoch, desc,
                      lane);
+    const uint32_t ucount2 = ld_relaxed_u32(hdr + HDR_UCOUNT2);
+    for (uint32_t u = gw; u < ucount2; u += nw)
+        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + num_tiles + u)), x, y, g, inv, gin, n, num_tiles, tile_elems,
+                     epoch, desc, lane);
     __syncthreads();
     if (threadIdx.x == 0) finish_op(hdr, epoch);
 }

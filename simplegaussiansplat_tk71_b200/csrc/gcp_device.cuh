@@ -30,8 +30,10 @@ constexpr int HDR_EPOCH = 32;
 constexpr int HDR_ABORT = 33;
 constexpr int HDR_VIOL64 = 20;  // index in u64 units (byte 160)
 constexpr int HDR_UCOUNT = 48;
+constexpr int HDR_UCOUNT2 = 52;  // backward: unresolved tiles with a long trailing run (fixed by a whole CTA)
 constexpr int HDR_EXIT = 56;
-constexpr int WS_LIST_BYTES = 4;  // per tile
+constexpr int WS_LIST_BYTES = 8;  // per tile: two u32 lists
+constexpr uint32_t LONG_RUN = 1024;  // trailing runs longer than this are recomputed by a whole CTA
 
 constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_TERM = 2, ST_INCL = 3;
 constexpr uint32_t EPOCH_MASK = 0x1FFFFFFFu;
@@ -204,6 +206,7 @@ __device__ __forceinline__ void finish_op(uint32_t *hdr, uint32_t epoch) {
         hdr[HDR_TICKET] = 0u;
         hdr[HDR_DONE] = 0u;
         hdr[HDR_UCOUNT] = 0u;
+        hdr[HDR_UCOUNT2] = 0u;
         hdr[HDR_EXIT] = 0u;
         hdr[HDR_EPOCH] = epoch + 1u;
         __threadfence();
