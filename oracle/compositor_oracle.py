@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE — not product code.
+
+numpy (fp64) restatement of the reference compositor `custom_autograd_grouped_cumprod`
+(/root/reference/gs_model.py:477-820) for a view that fits ONE chunk (sum(boxsize) <= 2^29, gs_model.py:428),
+i.e. without the chunk carry of :611-615.  Each step names the reference lines it follows.
+
+Pinned by tests/golden/compositor_fixture.npz, which the reference Function itself produced on CPU
+(tests/golden/make_compositor_fixture.py).  Only tests/ and bench.py's cpu_baseline leg import this.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as orc
+
+
+def expand(boxsize, sp, ep):
+    """make_rect_points_parallel (uitility.py:336-366): element order = Gaussian-major, row-major inside a box."""
+    boxsize = np.asarray(boxsize, dtype=np.int64)
+    n = boxsize.shape[0]
+    N = int(boxsize.sum())
+    gid = np.repeat(np.arange(n, dtype=np.int64), boxsize)
+    goff = np.cumsum(boxsize) - boxsize
+    local = np.arange(N, dtype=np.int64) - goff[gid]
+    w = (ep[:, 0].astype(np.int64) - sp[:, 0] + 1)
+    px = sp[gid, 0].astype(np.int64) + local % w[gid]
+    py = sp[gid, 1].astype(np.int64) + local // w[gid]
+    return gid, px, py
+
+
+def forward(boxsize, sp, ep, mean, lam, opac, l_d, W, H):
+    """gs_model.py:598-624 (_forward_batch) + :666-692 (forward).  Returns (image[H+1,W+1,3] f64, cache)."""
+    gid, px, py = expand(boxsize, sp, ep)
+    mean = np.asarray(mean, dtype=np.float64)
+    lam = np.asarray(lam, dtype=np.float64)
+    o = np.asarray(opac, dtype=np.float64).reshape(-1)[gid]
+    l = np.asarray(l_d, dtype=np.float64)[gid]
+    d0 = px - mean[gid, 0]
+    d1 = py - mean[gid, 1]
+    L = lam[gid]
+    # :495  exp(-0.5 * (r-m) Lambda (r-m)^T), row vector times matrix times column vector
+    q0 = d0 * L[:, 0, 0] + d1 * L[:, 1, 0]
+    q1 = d0 * L[:, 0, 1] + d1 * L[:, 1, 1]
+    g = np.exp(-0.5 * (q0 * d0 + q1 * d1))
+    x = 1.0 - o * g                                   # :535 anti_opacity
+    key = (py * 10000 + px).astype(np.int32)          # :541
+    order = np.argsort(key, kind="stable")            # :547 (torch.sort on CUDA is stable)
+    ks = key[order]
+    # :551 inclusive cumprod in fp32 — it decides which elements survive `T != 0` (:575-578)
+    x32 = (np.float32(1.0) - np.asarray(opac, np.float32).reshape(-1)[gid] * g.astype(np.float32)).astype(np.float32)
+    incl32 = orc.cumprod_fwd(x32[order], ks, np.float32)
+    alive_s = incl32 != 0.0
+    incl64 = orc.cumprod_fwd(x[order].astype(np.float32), ks)  # fp64 accumulate of the fp32 inputs
+    xs = x[order]
+    T_s = np.where(alive_s, incl64 / np.where(xs == 0, 1.0, xs), 0.0)   # :562 inclusive -> exclusive
+    inv_order = np.empty_like(order)
+    inv_order[order] = np.arange(order.size)
+    T = T_s[inv_order]
+    alive = alive_s[inv_order]
+    p = np.where(alive[:, None], T[:, None] * l * (o * g)[:, None], 0.0)   # :500
+    image = np.zeros((H + 1, W + 1, 3))
+    np.add.at(image, (py, px), p)                      # :510-514
+    cache = dict(gid=gid, px=px, py=py, o=o, l=l, g=g, x=x, d0=d0, d1=d1, L=L, key=key, order=order,
+                 inv_order=inv_order, alive=alive, p=p, n=len(boxsize))
+    return image, cache
+
+
+def backward(cache, grad_image):
+    """gs_model.py:627-663 (_backward_batch), :733-766 (grad_*), :776-783 (scatter to Gaussians)."""
+    c = cache
+    alive = c["alive"]
+    pg = np.asarray(grad_image, dtype=np.float64)[c["py"], c["px"], :]      # :703-706
+    d = np.where(alive, (pg * c["p"]).sum(1), 0.0)                           # :710-712
+    order, inv_order = c["order"], c["inv_order"]
+    ks = c["key"][order]
+    ds = d[order]
+    # :716-722 strict suffix sum inside each pixel: (total of the segment) - (inclusive prefix)
+    incl = orc.cumsum_fwd(ds.astype(np.float32), ks)  # fp64 accumulate
+    # use fp64 directly for the oracle: segment totals
+    head = np.r_[True, ks[1:] != ks[:-1]]
+    seg = np.cumsum(head) - 1
+    tot = np.zeros(seg[-1] + 1 if seg.size else 0)
+    np.add.at(tot, seg, ds)
+    pref = np.zeros_like(ds)
+    # inclusive prefix in fp64
+    csum = np.cumsum(ds)
+    start_val = np.r_[0.0, csum[:-1]][head][seg]
+    pref = csum - start_val
+    s_sorted = tot[seg] - pref
+    s = s_sorted[inv_order]
+    o, l, g, x = c["o"], c["l"], c["g"], c["x"]
+    xsafe = np.where(alive, x, 1.0)
+    go = np.where(alive, -(g / xsafe) * s + d / o, 0.0)                      # :733-740
+    gl = np.where(alive[:, None], d[:, None] / l, 0.0)                       # :763-766 (d / l, as the reference)
+    coef = np.where(alive, -((o * g) / xsafe) * s + d, 0.0)
+    X0 = c["d0"] * c["L"][:, 0, 0] + c["d1"] * c["L"][:, 1, 0]               # (r-m) Lambda  :745
+    X1 = c["d0"] * c["L"][:, 0, 1] + c["d1"] * c["L"][:, 1, 1]
+    gm = np.stack((coef * X0, coef * X1), 1)                                 # :743-750
+    coefL = np.where(alive, 0.5 * ((o * g) / xsafe) * s - 0.5 * d, 0.0)      # :753-760
+    dd = np.stack((c["d0"] * c["d0"], c["d0"] * c["d1"], c["d1"] * c["d0"], c["d1"] * c["d1"]), 1)
+    gL = coefL[:, None] * dd
+    n = c["n"]
+    gid = c["gid"]
+    out_m = np.zeros((n, 2)); np.add.at(out_m, gid, gm)
+    out_L = np.zeros((n, 4)); np.add.at(out_L, gid, gL)
+    out_o = np.zeros((n, 1)); np.add.at(out_o, gid, go[:, None])
+    out_l = np.zeros((n, 3)); np.add.at(out_l, gid, gl)
+    del incl
+    return out_m, out_L.reshape(n, 2, 2), out_o, out_l

@@ -165,3 +165,69 @@ def c4(device="cpu", scale: float = 1.0, deep: int = 512) -> ElementList:
 def algorithmic_bytes(n: int, k: int) -> dict:
     """fwd 12 B/elem, bwd 16 B/elem + 4 B/segment."""
     return {"fwd": 12 * n, "bwd": 16 * n + 4 * k, "fwd_bwd": 28 * n + 4 * k}
+
+
+# --------------------------------------------------------------------------------------------
+# Splat route (SURVEY.md §8d, C3/C4 "splat route"): per-Gaussian inputs of the compositor
+# `custom_autograd_grouped_cumprod.apply(boxsize, batch, startpoint, endpoint, mean, Lambda, opacity, l_d, W, H)`
+# exactly as gs_model.py:405-449 prepares them (depth order = index order, integer pixel means,
+# inclusive box corners clamped to [0,W]x[0,H]).
+# --------------------------------------------------------------------------------------------
+@dataclass
+class SplatView:
+    name: str
+    boxsize: torch.Tensor      # i64[n]
+    startpoint: torch.Tensor   # i32[n,2]
+    endpoint: torch.Tensor     # i32[n,2]
+    mean: torch.Tensor         # i32[n,2] (mean_pixel is cast to int32 at gs_model.py:361)
+    lam: torch.Tensor          # f32[n,2,2]
+    opacity: torch.Tensor      # f32[n,1]
+    l_d: torch.Tensor          # f32[n,3]
+    width: int
+    height: int
+
+    @property
+    def n(self) -> int:
+        return int(self.boxsize.numel())
+
+    @property
+    def elements(self) -> int:
+        return int(self.boxsize.sum().item())
+
+
+def splat_view(width: int = 1920, height: int = 1080, n: int = 1_000_000, seed: int = 1080, device="cpu",
+               clusters: int = 256) -> SplatView:
+    rng = np.random.default_rng(seed)
+    n_cl = int(0.7 * n)
+    cc = np.stack((rng.uniform(0, width, clusters), rng.uniform(0, height, clusters)), 1)
+    sig = 0.05 * min(width, height)
+    which = rng.integers(0, clusters, n_cl)
+    c1 = cc[which] + rng.normal(0.0, sig, (n_cl, 2))
+    c2 = np.stack((rng.uniform(-0.05 * width, 1.05 * width, n - n_cl),
+                   rng.uniform(-0.05 * height, 1.05 * height, n - n_cl)), 1)
+    ctr = np.concatenate((c1, c2), 0)
+    rng.shuffle(ctr, axis=0)                                   # depth order is independent of position
+    hw_max = 10 * 0.04 * math.sqrt(width * height)             # gs_model.py:364-365
+    hw = np.clip(np.floor(rng.lognormal(math.log(2.0), 0.9, (n, 2))), 1, hw_max)
+    mean = np.floor(ctr).astype(np.int64)
+    vis = (mean[:, 0] - hw[:, 0] < width) & (mean[:, 0] + hw[:, 0] > 0) & \
+          (mean[:, 1] - hw[:, 1] < height) & (mean[:, 1] + hw[:, 1] > 0)       # gs_model.py:406
+    mean, hw = mean[vis], hw[vis].astype(np.int64)
+    sp = np.stack((np.clip(mean[:, 0] - hw[:, 0], 0, width), np.clip(mean[:, 1] - hw[:, 1], 0, height)), 1)
+    ep = np.stack((np.clip(mean[:, 0] + hw[:, 0], 0, width), np.clip(mean[:, 1] + hw[:, 1], 0, height)), 1)
+    boxsize = np.prod(ep - sp + 1, axis=1)
+    m = mean.shape[0]
+    sx = np.maximum(hw[:, 0] / 3.0, 0.5)                       # the box is the 3-sigma extent (gs_model.py:327-332)
+    sy = np.maximum(hw[:, 1] / 3.0, 0.5)
+    rho = rng.uniform(-0.6, 0.6, m)
+    det = (1 - rho * rho)
+    lam = np.zeros((m, 2, 2), np.float32)
+    lam[:, 0, 0] = 1.0 / (sx * sx * det)
+    lam[:, 1, 1] = 1.0 / (sy * sy * det)
+    lam[:, 0, 1] = lam[:, 1, 0] = -rho / (sx * sy * det)
+    opac = 1.0 / (1.0 + np.exp(-rng.normal(OPACITY_LOGIT_MEAN, OPACITY_LOGIT_STD, (m, 1))))
+    l_d = rng.uniform(0.05, 0.95, (m, 3))
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)  # noqa: E731
+    return SplatView(f"splat {width}x{height} n={m} seed{seed}", t(boxsize, torch.int64), t(sp, torch.int32),
+                     t(ep, torch.int32), t(mean, torch.int32), t(lam, torch.float32), t(opac, torch.float32),
+                     t(l_d, torch.float32), width, height)

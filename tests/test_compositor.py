@@ -1,0 +1,105 @@
+"""Compositor (rows a5-a9 of SURVEY.md §8): the native `custom_autograd_grouped_cumprod` against fixtures the
+reference's own Function produced (tests/golden/compositor_fixture.npz) and against the fp64 oracle.
+
+CPU variant: the host logic only, with the two scan ops swapped for the oracle (test-only monkeypatch).
+GPU variant (-m gpu): the real thing, through the C ABI."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from test_compositor_oracle import CASES, FIX, load_case
+
+
+def _run(case, device):
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(device if dt is None else device, dtype=dt)  # noqa: E731
+    boxsize = t(case["boxsize"])
+    sp, ep = t(case["sp"]), t(case["ep"])
+    mean = t(case["mean"]).float().requires_grad_(True)
+    lam = t(case["lam"]).requires_grad_(True)
+    opac = t(case["opac"]).requires_grad_(True)
+    l_d = t(case["l_d"]).requires_grad_(True)
+    n = boxsize.numel()
+    img = F.apply(boxsize, torch.tensor([n]), sp, ep, mean, lam, opac, l_d, torch.tensor(case["W"]), torch.tensor(case["H"]))
+    (img * t(case["grad_image"])).sum().backward()
+    return [v.detach().cpu().numpy() for v in (img, mean.grad, lam.grad, opac.grad, l_d.grad)]
+
+
+def _check(got, case, rtol=1e-3, atol=1e-4):
+    img, gm, gL, go, gl = got
+    assert img.shape == (case["H"] + 1, case["W"] + 1, 3)
+    np.testing.assert_allclose(img, case["image"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(gm, case["grad_mean"], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(gL, case["grad_lambda"], rtol=rtol, atol=10 * atol)
+    np.testing.assert_allclose(go, case["grad_opacity"], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(gl, case["grad_l"], rtol=rtol, atol=atol)
+
+
+@pytest.fixture
+def oracle_backed_ops(monkeypatch):
+    """TEST ONLY: lets the host logic of compositor.py run without a GPU."""
+    from oracle import oracle as orc
+    from simplegaussiansplat_tk71_b200 import compositor
+
+    def fwd(x, key, y):
+        y.copy_(torch.from_numpy(orc.cumprod_fwd(x.numpy(), key.numpy(), np.float32)))
+
+    def bwd(param, cp, gout, inv, gin, inv_len):
+        gin.copy_(torch.from_numpy(orc.cumprod_bwd_exact(param.numpy(), gout.numpy(), inv.numpy()).astype(np.float32)))
+
+    monkeypatch.setattr(compositor, "ops", types.SimpleNamespace(grouped_cumprod_forward=fwd,
+                                                                 grouped_cumprod_backward=bwd))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_logic_matches_reference_fixture_cpu(name, oracle_backed_ops):
+    case = load_case(np.load(FIX), name)
+    _check(_run(case, "cpu"), case)
+
+
+def test_element_plan_integer_side_is_bit_exact():
+    """Sort permutation, segment ids and offsets against torch.sort(stable=True) / unique_consecutive."""
+    from simplegaussiansplat_tk71_b200.compositor import ElementPlan
+    from oracle import compositor_oracle as co
+
+    case = load_case(np.load(FIX), "wide")
+    plan = ElementPlan(torch.from_numpy(case["boxsize"]), torch.from_numpy(case["sp"]), torch.from_numpy(case["ep"]))
+    gid, px, py = co.expand(case["boxsize"], case["sp"], case["ep"])
+    key = (py * 10000 + px).astype(np.int32)
+    order = np.argsort(key, kind="stable")
+    assert np.array_equal(plan.key_s.numpy(), key[order])
+    assert np.array_equal(plan.gid_s.numpy(), gid[order])
+    _, counts = torch.unique_consecutive(plan.key_s, return_counts=True)
+    assert np.array_equal(plan.seg_end.numpy(), np.cumsum(counts.numpy()).astype(np.int32))
+    assert np.array_equal(plan.inv.numpy(), np.repeat(np.arange(len(counts)), counts.numpy()).astype(np.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_native_compositor_matches_reference_fixture_gpu(name):
+    case = load_case(np.load(FIX), name)
+    _check(_run(case, "cuda"), case)
+
+
+@pytest.mark.gpu
+def test_native_compositor_matches_oracle_on_a_larger_scene_gpu():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from oracle import compositor_oracle as co
+    import make_compositor_fixture as mk
+
+    W, H, n = 160, 120, 4000
+    boxsize, sp, ep, mean, lam, opac, l_d = mk.make_scene(11, W, H, n, 9, opaque=20)
+    rng = np.random.default_rng(5)
+    gI = (rng.uniform(0.1, 1.0, (H + 1, W + 1, 3))).astype(np.float32)
+    case = dict(boxsize=boxsize.numpy(), sp=sp.numpy(), ep=ep.numpy(), mean=mean.numpy(), lam=lam.numpy(),
+                opac=opac.numpy(), l_d=l_d.numpy(), W=W, H=H, grad_image=gI)
+    img, cache = co.forward(case["boxsize"], case["sp"], case["ep"], case["mean"], case["lam"], case["opac"],
+                            case["l_d"], W, H)
+    gm, gL, go, gl = co.backward(cache, gI)
+    case.update(image=img, grad_mean=gm, grad_lambda=gL, grad_opacity=go, grad_l=gl)
+    _check(_run(case, "cuda"), case, rtol=2e-3, atol=2e-3)

@@ -1,0 +1,49 @@
+"""CPU: the compositor oracle (oracle/compositor_oracle.py) against fixtures produced by the reference's own
+`custom_autograd_grouped_cumprod` (gs_model.py:477-820) run on CPU — tests/golden/make_compositor_fixture.py."""
+import os
+
+import numpy as np
+import pytest
+
+FIX = os.path.join(os.path.dirname(__file__), "golden", "compositor_fixture.npz")
+CASES = ["small", "dense", "wide", "opaque"]
+
+
+def load_case(f, name):
+    g = lambda k: f[f"{name}/{k}"]  # noqa: E731
+    W, H = (int(v) for v in g("WH"))
+    return dict(boxsize=g("boxsize"), sp=g("startpoint"), ep=g("endpoint"), mean=g("mean"), lam=g("lam"),
+                opac=g("opacity"), l_d=g("l_d"), W=W, H=H, image=g("image"), grad_image=g("grad_image"),
+                grad_mean=g("grad_mean"), grad_lambda=g("grad_lambda"), grad_opacity=g("grad_opacity"),
+                grad_l=g("grad_l"))
+
+
+def close(a, b, rtol=2e-4, atol=2e-5):
+    # the reference computed in fp32 (torch CPU) with its own association order; the oracle is fp64
+    return np.allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_reference_function(name):
+    from oracle import compositor_oracle as co
+
+    c = load_case(np.load(FIX), name)
+    img, cache = co.forward(c["boxsize"], c["sp"], c["ep"], c["mean"], c["lam"], c["opac"], c["l_d"], c["W"], c["H"])
+    assert img.shape == c["image"].shape == (c["H"] + 1, c["W"] + 1, 3)
+    assert close(img, c["image"]), np.abs(img - c["image"]).max()
+    gm, gL, go, gl = co.backward(cache, c["grad_image"])
+    assert close(gm, c["grad_mean"], rtol=1e-3, atol=1e-4), np.abs(gm - c["grad_mean"]).max()
+    assert close(gL, c["grad_lambda"], rtol=1e-3, atol=1e-3), np.abs(gL - c["grad_lambda"]).max()
+    assert close(go, c["grad_opacity"], rtol=1e-3, atol=1e-4), np.abs(go - c["grad_opacity"]).max()
+    assert close(gl, c["grad_l"], rtol=1e-3, atol=1e-4), np.abs(gl - c["grad_l"]).max()
+
+
+def test_chunked_reference_render_differs_only_by_its_boundary_carry():
+    """with several chunks the reference drops one (1-alpha) factor at each chunk boundary.
+    The single-chunk image is the intended result; the fixture keeps the 3-chunk image to document the size
+    of that effect (it is NOT what the native compositor reproduces)."""
+    f = np.load(FIX)
+    one, three = f["dense/image"], f["dense/image_3chunks"]
+    assert one.shape == three.shape
+    assert np.all(three >= one - 1e-4)          # a missing (1-alpha) <= 1 factor can only brighten
+    assert np.abs(three - one).max() > 1e-3      # and it is visible
