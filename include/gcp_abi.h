@@ -121,6 +121,48 @@ const char *gcp_variant_name(int op, int variant);
 /* Number of kernels launched by the last call on this thread (for bench.py's gpu_launches). */
 int gcp_last_launch_count(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * Compositor rows: streaming kernels around the two scans.  They replace the
+ * torch op chains of /root/reference/gs_model.py:480-514 (box expansion, Gaussian kernel, pixel
+ * accumulation), :538-548 (pixel key, sort, gather) and :627-663,:733-783 (per-element gradients,
+ * scatter to Gaussians).  Per-Gaussian tables: mean f32[n,2], lam f32[n,2,2], opac f32[n], l_d f32[n,3];
+ * sp/ep i32[n,2] inclusive box corners; goff i64[n+1] exclusive element offsets (cumsum of boxsize).
+ * Sorted element list: key_s i32[N] (y*10000+x, non-decreasing), gid_s i32[N] (Gaussian of the element;
+ * inside a pixel in depth = index order).  image f32[(H+1)*(W+1)*3], as gs_model.py:505.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* key[e], gid[e] of every element in Gaussian-major order (make_rect_points_parallel, uitility.py:336-366,
+ * + unique(), gs_model.py:538-541). */
+int gcp_splat_expand(const int32_t *sp, const int32_t *ep, const int64_t *goff, int64_t n, int64_t N,
+                     int32_t *key, int32_t *gid, gcp_stream_t stream);
+
+/* Stable sort of the (key, gid) pairs by key (replaces torch.sort + gathers, gs_model.py:547-548). */
+size_t gcp_splat_sort_bytes(int64_t N);
+int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_out, int32_t *gid_out, int64_t N,
+                   int max_key, void *temp, size_t temp_bytes, gcp_stream_t stream);
+
+/* x_s[e] = 1 - opacity * exp(-1/2 (r-m) Lambda (r-m)^T)  (gs_model.py:493-495, :533-535), sorted order. */
+int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *mean, const float *lam,
+                    const float *opac, int64_t N, float *x_s, gcp_stream_t stream);
+
+/* image[pixel] += sum_i T_i alpha_i l_i with T_i the EXCLUSIVE product taken from the inclusive scan
+ * `incl` (no division; replaces gs_model.py:562, :498-514).  image must be zeroed by the caller. */
+int gcp_splat_color(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
+                    const float *l_d, int64_t N, int W, float *image, gcp_stream_t stream);
+
+/* gshift[k] = w_{k+1} inside a pixel list (0 at its tail), w_k = <dL/dI(pixel), alpha_k l_k>: the grad_out
+ * for which gcp_cumprod_bwd_f32 returns T_k*U_k (division-free replacement of gs_model.py:716-722). */
+int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
+                    const float *l_d, const float *grad_image, int64_t N, int W, float *gshift,
+                    gcp_stream_t stream);
+
+/* Per-element gradients (gs_model.py:733-766) accumulated per Gaussian (:776-783); tu = T*U from
+ * gcp_cumprod_bwd_f32.  Outputs must be zeroed by the caller: g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3]. */
+int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
+                        const int32_t *gid_s, const float *mean, const float *lam, const float *opac,
+                        const float *l_d, const float *grad_image, int64_t N, int W, float *g_mean, float *g_lam,
+                        float *g_opac, float *g_l, gcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

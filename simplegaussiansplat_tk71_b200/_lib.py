@@ -25,6 +25,8 @@ SYMBOLS = (
     "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status",
     "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
     "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
+    "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color",
+    "gcp_splat_bwd_w", "gcp_splat_bwd_grads",
 )
 
 
@@ -58,6 +60,17 @@ def lib() -> ctypes.CDLL:
     L.gcp_variant_name.argtypes = [ci, ci]
     L.gcp_variant_name.restype = ctypes.c_char_p
     L.gcp_last_launch_count.restype = ci
+    L.gcp_splat_expand.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+    L.gcp_splat_sort_bytes.argtypes = [i64]
+    L.gcp_splat_sort_bytes.restype = sz
+    L.gcp_splat_sort.argtypes = [vp, vp, vp, vp, i64, ci, vp, sz, vp]
+    L.gcp_splat_alpha.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
+    L.gcp_splat_color.argtypes = [vp, vp, vp, vp, vp, i64, ci, vp, vp]
+    L.gcp_splat_bwd_w.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
+    L.gcp_splat_bwd_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp, vp, vp, vp]
+    for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",
+                 "gcp_splat_bwd_grads"):
+        getattr(L, name).restype = ci
     for name in ("gcp_workspace_init", "gcp_workspace_status", "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32",
                  "gcp_cumprod_bwd_f32", "gcp_validate_segments", "gcp_set_variant", "gcp_num_variants"):
         getattr(L, name).restype = ci

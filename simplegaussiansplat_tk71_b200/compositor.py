@@ -12,88 +12,116 @@ fits one chunk (sum(boxsize) <= 2**29, gs_model.py:428):
     T_i = prod_{j<i, same pixel} (1 - alpha_j),   alpha = opacity * exp(-1/2 (r-m) Lambda (r-m)^T)
     image[y, x] = sum_i T_i alpha_i l_i           (elements whose inclusive product is 0 contribute nothing, :575)
 
-but not how: there is no inclusive->exclusive division (:562), no un-sort (:555), no second sorted pass with
-flips for the backward (:716-722), no chunk loop (:675, :792) and no recompute of the forward in the backward
-(:799).  The backward is division-free: with w_k = <dL/dI_pixel, alpha_k l_k>,
+but not how.  One view = nine kernel launches, all through the C ABI (include/gcp_abi.h):
 
-    dL/dalpha_i = T_i <dL/dI, l_i> - T_i U_i,     U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1}
+    forward   gcp_splat_expand   boxes -> (pixel key, Gaussian id) per element          (:480-482, :538-541)
+              gcp_splat_sort     stable radix sort by key, significant bits only        (:547-548)
+              gcp_splat_alpha    x = 1 - opacity*g in sorted order                      (:493-495, :533-535)
+              gcp_cumprod_fwd    the segmented scan (op a1)                             (:551)
+              gcp_splat_color    exclusive T from the inclusive scan (no division) and
+                                 the per-pixel colour sum                               (:562, :498-514)
+    backward  gcp_splat_bwd_w    w_k = <dL/dI, alpha_k l_k>, shifted by one in its list
+              gcp_cumprod_bwd    division-free T_k*U_k (op a3)                          (replaces :716-722)
+              gcp_splat_bwd_grads  per-element gradients accumulated per Gaussian       (:733-783)
 
-and T_i U_i is exactly what `grouped_cumprod_backward` returns for grad_out = w shifted by one inside each
-pixel list, so alpha -> 1 stays exact (the reference divides by 1-alpha at :736,:747,:757).
+There is no un-sort (:555), no flip + second sorted pass (:716-722), no chunk loop (:675, :792), no forward
+recompute in the backward (:799) and no division by 1-alpha (:736,:747,:757): with
+U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1},  dL/dalpha_i = T_i <dL/dI, l_i> - T_i U_i  stays exact as alpha -> 1.
 
-`batch` (chunk ends) is accepted and ignored: the scan kernels carry across any length, so a view is one
-pass.  The reference's chunked result differs from its own single-chunk result by one (1-alpha) factor per
-chunk boundary (tests/test_compositor_oracle.py keeps a fixture of it); the single-chunk
-result is the one reproduced here.
-
-Expansion, the stable key sort and the per-Gaussian reduction are plain torch device ops in this round
-(plumbing around the two scan launches); SURVEY.md §8f ranks 2-3 replace them next.
+`batch` (chunk ends) is accepted and ignored: the scan carries across any length, so a view is one pass.  The
+reference's chunked result differs from its own single-chunk result by one (1-alpha) factor per chunk
+boundary (tests/golden keeps a fixture of it); the single-chunk result
+is the one reproduced here.  No CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 KEY_STRIDE = 10000  # pixel key = y*10000 + x  (gs_model.py:541)
 
 
-class ElementPlan:
-    """Integer side of one view: the element list in pixel-sorted order (bit-exact contract).
-
-    gid_s   i64[N]  Gaussian of each element, sorted by (pixel key, depth)  — depth order = Gaussian index
-    px_s/py_s       pixel of each element
-    key_s   i32[N]  y*10000+x, non-decreasing
-    inv     i32[N]  dense segment (pixel list) id;  seg_end i32[K] exclusive ends  (cuda_test.py:21,27 layout)
-    head/tail bool[N]
-    """
-
-    def __init__(self, boxsize, startpoint, endpoint):
-        dev = startpoint.device
-        boxsize = boxsize.to(torch.int64)
-        n = boxsize.numel()
-        N = int(boxsize.sum().item())
-        self.n, self.N = n, N
-        gid = torch.repeat_interleave(torch.arange(n, device=dev), boxsize, output_size=N)
-        goff = torch.cumsum(boxsize, 0) - boxsize
-        local = torch.arange(N, device=dev) - goff[gid]
-        sx = startpoint[:, 0].to(torch.int64)
-        sy = startpoint[:, 1].to(torch.int64)
-        w = endpoint[:, 0].to(torch.int64) - sx + 1
-        wg = w[gid]
-        px = sx[gid] + local % wg                       # make_rect_points_parallel, uitility.py:336-366
-        py = sy[gid] + torch.div(local, wg, rounding_mode="floor")
-        key = (py * KEY_STRIDE + px).to(torch.int32)
-        key_s, perm = torch.sort(key, stable=True)      # explicitly stable (the reference relies on it, :547)
-        self.key_s = key_s
-        self.gid_s = gid[perm]
-        self.px_s = px[perm]
-        self.py_s = py[perm]
-        head = torch.ones(N, dtype=torch.bool, device=dev)
-        if N > 1:
-            head[1:] = key_s[1:] != key_s[:-1]
-        self.head = head
-        tail = torch.ones(N, dtype=torch.bool, device=dev)
-        if N > 1:
-            tail[:-1] = head[1:]
-        self.tail = tail
-        self.inv = (torch.cumsum(head.to(torch.int32), 0) - 1).to(torch.int32)
-        self.seg_end = (torch.nonzero(tail).flatten() + 1).to(torch.int32)
+def _p(t):
+    return t.data_ptr()
 
 
-def _element_values(plan: ElementPlan, mean, lam, opacity, l_d):
-    gid = plan.gid_s
-    m = mean.to(torch.float32)
-    d0 = plan.px_s.to(torch.float32) - m[gid, 0]
-    d1 = plan.py_s.to(torch.float32) - m[gid, 1]
-    L = lam[gid]
-    X0 = d0 * L[:, 0, 0] + d1 * L[:, 1, 0]              # (r-m) Lambda, gs_model.py:495,:745
-    X1 = d0 * L[:, 0, 1] + d1 * L[:, 1, 1]
-    g = torch.exp(-0.5 * (X0 * d0 + X1 * d1))
-    o = opacity.reshape(-1)[gid]
-    alpha = o * g
-    x = (1.0 - alpha).contiguous()                      # anti_opacity, gs_model.py:535
-    return d0, d1, X0, X1, g, o, alpha, x
+class _View:
+    """Device state of one rendered view kept for the backward (16 B per element + the per-Gaussian tables)."""
+    __slots__ = ("n", "N", "W", "H", "key_s", "gid_s", "x_s", "incl", "mean", "lam", "opac", "l_d")
+
+
+def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
+    dev = startpoint.device
+    if dev.type != "cuda":
+        raise RuntimeError("custom_autograd_grouped_cumprod needs CUDA tensors (there is no CPU path)")
+    L = _lib.lib()
+    v = _View()
+    v.W, v.H = W, H
+    n = boxsize.numel()
+    v.n = n
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        goff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(boxsize.to(torch.int64), 0, out=goff[1:])
+        N = int(goff[-1].item())           # one host sync per view, like the reference's .item() at uitility.py:348
+        v.N = N
+        v.mean = mean.detach().to(torch.float32).contiguous()
+        v.lam = lam.detach().to(torch.float32).reshape(n, 4).contiguous()
+        v.opac = opacity.detach().to(torch.float32).reshape(n).contiguous()
+        v.l_d = l_d.detach().to(torch.float32).contiguous()
+        image = torch.zeros((H + 1, W + 1, 3), dtype=torch.float32, device=dev)
+        if N == 0:
+            v.key_s = v.gid_s = v.x_s = v.incl = None
+            return image, v
+        if N >= 2 ** 31:
+            raise RuntimeError("a view is limited to 2**31-1 elements (the reference ops index with int32)")
+        sp = startpoint.to(torch.int32).contiguous()
+        ep = endpoint.to(torch.int32).contiguous()
+        key = torch.empty(N, dtype=torch.int32, device=dev)
+        gid = torch.empty(N, dtype=torch.int32, device=dev)
+        _lib.check(L.gcp_splat_expand(_p(sp), _p(ep), _p(goff), n, N, _p(key), _p(gid), stream), "gcp_splat_expand")
+        v.key_s = torch.empty_like(key)
+        v.gid_s = torch.empty_like(gid)
+        temp = torch.empty(int(L.gcp_splat_sort_bytes(N)), dtype=torch.uint8, device=dev)
+        _lib.check(L.gcp_splat_sort(_p(key), _p(gid), _p(v.key_s), _p(v.gid_s), N, H * KEY_STRIDE + W, _p(temp),
+                                    temp.numel(), stream), "gcp_splat_sort")
+        del key, gid, temp
+        v.x_s = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.check(L.gcp_splat_alpha(_p(v.key_s), _p(v.gid_s), _p(v.mean), _p(v.lam), _p(v.opac), N, _p(v.x_s),
+                                     stream), "gcp_splat_alpha")
+        v.incl = torch.empty_like(v.x_s)
+        ops.grouped_cumprod_forward(v.x_s, v.key_s, v.incl)
+        _lib.check(L.gcp_splat_color(_p(v.incl), _p(v.x_s), _p(v.key_s), _p(v.gid_s), _p(v.l_d), N, W, _p(image),
+                                     stream), "gcp_splat_color")
+    return image, v
+
+
+def _render_backward(v: _View, grad_image):
+    dev = grad_image.device
+    n = v.n
+    g_mean = torch.zeros((n, 2), dtype=torch.float32, device=dev)
+    g_lam = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+    g_opac = torch.zeros((n,), dtype=torch.float32, device=dev)
+    g_l = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+    if v.N == 0:
+        return g_mean, g_lam, g_opac, g_l
+    L = _lib.lib()
+    gI = grad_image.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        gshift = torch.empty_like(v.x_s)
+        _lib.check(L.gcp_splat_bwd_w(_p(v.incl), _p(v.x_s), _p(v.key_s), _p(v.gid_s), _p(v.l_d), _p(gI), v.N, v.W,
+                                     _p(gshift), stream), "gcp_splat_bwd_w")
+        tu = torch.empty_like(v.x_s)
+        # the sorted pixel keys serve as segment ids: the backward op only compares neighbours
+        # (inv_len is implied by them, include/gcp_abi.h)
+        ops.grouped_cumprod_backward(v.x_s, v.incl, gshift, v.key_s, tu,
+                                     torch.empty(0, dtype=torch.int32, device=dev))
+        _lib.check(L.gcp_splat_bwd_grads(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.mean),
+                                         _p(v.lam), _p(v.opac), _p(v.l_d), _p(gI), v.N, v.W, _p(g_mean), _p(g_lam),
+                                         _p(g_opac), _p(g_l), stream), "gcp_splat_bwd_grads")
+    return g_mean, g_lam, g_opac, g_l
 
 
 class custom_autograd_grouped_cumprod(torch.autograd.Function):
@@ -101,57 +129,16 @@ class custom_autograd_grouped_cumprod(torch.autograd.Function):
     def forward(ctx, boxsize, batch, startpoint, endpoint, mean, variance_inverse, opacity, l_d, image_width,
                 image_height):
         with torch.no_grad():
-            W, H = int(image_width), int(image_height)
-            plan = ElementPlan(boxsize, startpoint, endpoint)
-            image = torch.zeros((H + 1, W + 1, 3), dtype=torch.float32, device=startpoint.device)
-            ctx.plan = plan
-            ctx.WH = (W, H)
-            ctx.save_for_backward(mean, variance_inverse, opacity, l_d)
-            if plan.N == 0:
-                return image
-            _, _, _, _, _, _, alpha, x = _element_values(plan, mean, variance_inverse, opacity, l_d)
-            incl = torch.empty_like(x)
-            ops.grouped_cumprod_forward(x, plan.key_s, incl)            # a1
-            T = torch.where(plan.head, torch.ones_like(incl), torch.roll(incl, 1))   # exclusive, no division
-            alive = incl != 0                                           # gs_model.py:575-578
-            ta = torch.where(alive, T * alpha, torch.zeros_like(T))
-            contrib = ta[:, None] * l_d[plan.gid_s]
-            image.view(-1, 3).index_add_(0, plan.py_s * (W + 1) + plan.px_s, contrib)   # C = sum T alpha l
-            return image
+            image, view = _render_forward(boxsize, startpoint, endpoint, mean, variance_inverse, opacity, l_d,
+                                          int(image_width), int(image_height))
+        ctx.view = view
+        ctx.shapes = (mean.dtype, variance_inverse.shape, opacity.shape)
+        return image
 
     @staticmethod
     def backward(ctx, grad_image):
         with torch.no_grad():
-            mean, lam, opacity, l_d = ctx.saved_tensors
-            plan = ctx.plan
-            W, H = ctx.WH
-            n = plan.n
-            gm = torch.zeros((n, 2), dtype=torch.float32, device=grad_image.device)
-            gL = torch.zeros((n, 4), dtype=torch.float32, device=grad_image.device)
-            go = torch.zeros((n, 1), dtype=torch.float32, device=grad_image.device)
-            gl = torch.zeros((n, 3), dtype=torch.float32, device=grad_image.device)
-            if plan.N > 0:
-                gid = plan.gid_s
-                d0, d1, X0, X1, g, o, alpha, x = _element_values(plan, mean, lam, opacity, l_d)
-                incl = torch.empty_like(x)
-                ops.grouped_cumprod_forward(x, plan.key_s, incl)
-                T = torch.where(plan.head, torch.ones_like(incl), torch.roll(incl, 1))
-                alive = incl != 0
-                l = l_d[gid]
-                pg = grad_image.reshape(-1, 3)[plan.py_s * (W + 1) + plan.px_s]
-                pgl = (pg * l).sum(1)                                    # <dL/dI, l_i>
-                zero = torch.zeros_like(T)
-                w = torch.where(alive, alpha * pgl, zero)                # w_k = <dL/dI, alpha_k l_k>
-                gshift = torch.where(plan.tail, zero, torch.roll(w, -1)).contiguous()
-                TU = torch.empty_like(x)
-                ops.grouped_cumprod_backward(x, incl, gshift, plan.inv, TU, plan.seg_end)   # a3: T_i * U_i
-                dalpha = torch.where(alive, T * pgl - TU, zero)
-                d = T * w                                                # <dL/dI, p_i>
-                coef = alpha * dalpha
-                go.index_add_(0, gid, (g * dalpha)[:, None])
-                gl.index_add_(0, gid, d[:, None] / l)                    # the reference's d / l (gs_model.py:763-766)
-                gm.index_add_(0, gid, torch.stack((coef * X0, coef * X1), 1))
-                hc = -0.5 * coef
-                gL.index_add_(0, gid, torch.stack((hc * d0 * d0, hc * d0 * d1, hc * d1 * d0, hc * d1 * d1), 1))
-            return (None, None, None, None, gm.to(mean.dtype), gL.reshape(n, 2, 2), go.reshape(opacity.shape), gl,
-                    None, None)
+            g_mean, g_lam, g_opac, g_l = _render_backward(ctx.view, grad_image)
+        mdt, lshape, oshape = ctx.shapes
+        return (None, None, None, None, g_mean.to(mdt), g_lam.reshape(lshape), g_opac.reshape(oshape), g_l, None,
+                None)

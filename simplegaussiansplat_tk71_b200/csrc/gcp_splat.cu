@@ -1,0 +1,319 @@
+// gcp_splat.cu — kernels around the scan ops for the compositor rows:
+// box -> element expansion straight into (key, gaussian-id) pairs, the stable pixel-key sort,
+// per-element alpha in sorted order, per-pixel colour reduction, and the per-element /
+// per-Gaussian backward.  Everything here is a plain streaming kernel (no cross-CTA carries): the
+// two scans of a step are the ops of gcp_abi.cu (gcp_cumprod_fwd_f32 / gcp_cumprod_bwd_f32).
+//
+// Reference being replaced: the torch op chains of gs_model.py:480-514 (expansion, Gaussian kernel,
+// pixel accumulation with index_put_ atomics), :538-548 (key build + sort + gather), :627-663 and
+// :733-783 (per-element gradients and scatter_reduce to Gaussians).
+//
+// Element = (Gaussian j, pixel (x,y)) with (x,y) inside the inclusive box [sp_j, ep_j]; element order
+// before sorting = Gaussian-major, row-major inside the box (uitility.py:336-366); pixel key =
+// y*10000 + x (gs_model.py:541).  The sort is a stable LSD radix sort on the key bits only, so inside a
+// pixel the depth order (= Gaussian index order) is preserved bit-exactly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "gcp_abi.h"
+
+namespace {
+
+constexpr int KEY_STRIDE = 10000;
+constexpr int CH = 8;  // consecutive elements per thread
+
+// first index g with goff[g+1] > e  (goff: exclusive offsets, n+1 entries)
+__device__ __forceinline__ int64_t find_gaussian(const int64_t *__restrict__ goff, int64_t n, int64_t e) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(goff + mid + 1) > e) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_splat_expand(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ goff,
+               int64_t n, int64_t N, int32_t *__restrict__ key, int32_t *__restrict__ gid) {
+    const int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CH;
+    if (e0 >= N) return;
+    int64_t g = find_gaussian(goff, n, e0);
+    int64_t gbeg = __ldg(goff + g), gend = __ldg(goff + g + 1);
+    int sx = __ldg(sp + 2 * g), sy = __ldg(sp + 2 * g + 1);
+    int w = __ldg(ep + 2 * g) - sx + 1;
+    int32_t ko[CH], go[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int64_t e = e0 + i;
+        if (e < N) {
+            while (e >= gend) {  // skips empty boxes too
+                ++g;
+                gbeg = gend;
+                gend = __ldg(goff + g + 1);
+                sx = __ldg(sp + 2 * g);
+                sy = __ldg(sp + 2 * g + 1);
+                w = __ldg(ep + 2 * g) - sx + 1;
+            }
+            const int local = static_cast<int>(e - gbeg);
+            const int iy = local / w;
+            const int ix = local - iy * w;
+            ko[i] = (sy + iy) * KEY_STRIDE + sx + ix;
+            go[i] = static_cast<int32_t>(g);
+        } else {
+            ko[i] = 0;
+            go[i] = 0;
+        }
+    }
+    if (e0 + CH <= N) {
+        reinterpret_cast<int4 *>(key + e0)[0] = make_int4(ko[0], ko[1], ko[2], ko[3]);
+        reinterpret_cast<int4 *>(key + e0)[1] = make_int4(ko[4], ko[5], ko[6], ko[7]);
+        reinterpret_cast<int4 *>(gid + e0)[0] = make_int4(go[0], go[1], go[2], go[3]);
+        reinterpret_cast<int4 *>(gid + e0)[1] = make_int4(go[4], go[5], go[6], go[7]);
+    } else {
+        for (int i = 0; i < CH && e0 + i < N; ++i) {
+            key[e0 + i] = ko[i];
+            gid[e0 + i] = go[i];
+        }
+    }
+}
+
+struct Gauss {
+    float mx, my, l00, l01, l10, l11, o;
+};
+__device__ __forceinline__ Gauss load_gauss(const float *__restrict__ mean, const float *__restrict__ lam,
+                                            const float *__restrict__ opac, int g) {
+    const float2 m = __ldg(reinterpret_cast<const float2 *>(mean) + g);
+    const float4 L = __ldg(reinterpret_cast<const float4 *>(lam) + g);
+    return Gauss{m.x, m.y, L.x, L.y, L.z, L.w, __ldg(opac + g)};
+}
+// g = exp(-1/2 (r-m) Lambda (r-m)^T)  with X = (r-m) Lambda  (gs_model.py:495, :745)
+__device__ __forceinline__ float gauss_kernel(const Gauss &G, int key, float &d0, float &d1, float &X0, float &X1) {
+    const int py = key / KEY_STRIDE;
+    const int px = key - py * KEY_STRIDE;
+    d0 = static_cast<float>(px) - G.mx;
+    d1 = static_cast<float>(py) - G.my;
+    X0 = d0 * G.l00 + d1 * G.l10;
+    X1 = d0 * G.l01 + d1 * G.l11;
+    return expf(-0.5f * (X0 * d0 + X1 * d1));
+}
+
+// x_s[e] = 1 - o*g in sorted order (the scan's input)
+__global__ void __launch_bounds__(256)
+k_splat_alpha(const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s, const float *__restrict__ mean,
+              const float *__restrict__ lam, const float *__restrict__ opac, int64_t N, float *__restrict__ x_s) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
+        const Gauss G = load_gauss(mean, lam, opac, __ldg(gid_s + e));
+        float d0, d1, X0, X1;
+        const float g = gauss_kernel(G, __ldg(key_s + e), d0, d1, X0, X1);
+        x_s[e] = 1.0f - G.o * g;
+    }
+}
+
+__device__ __forceinline__ int pixel_index(int key, int W) {
+    const int py = key / KEY_STRIDE;
+    return py * (W + 1) + (key - py * KEY_STRIDE);
+}
+
+// image[pixel] += sum_i T_i alpha_i l_i  (T exclusive = previous inclusive product, 1 at a head;
+// elements whose inclusive product is 0 contribute nothing, gs_model.py:575-578)
+__global__ void __launch_bounds__(256)
+k_splat_color(const float *__restrict__ incl, const float *__restrict__ x_s, const int32_t *__restrict__ key_s,
+              const int32_t *__restrict__ gid_s, const float *__restrict__ l_d, int64_t N, int W,
+              float *__restrict__ image) {
+    const int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CH;
+    if (e0 >= N) return;
+    int kprev = (e0 > 0) ? __ldg(key_s + e0 - 1) : -1;
+    float yprev = (e0 > 0) ? __ldg(incl + e0 - 1) : 1.0f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    int kcur = -1;
+    for (int i = 0; i < CH && e0 + i < N; ++i) {
+        const int64_t e = e0 + i;
+        const int k = __ldg(key_s + e);
+        const float y = __ldg(incl + e);
+        const float T = (k != kprev) ? 1.0f : yprev;
+        if (k != kcur) {
+            if (kcur >= 0 && (a0 != 0.f || a1 != 0.f || a2 != 0.f)) {
+                float *p = image + 3 * static_cast<int64_t>(pixel_index(kcur, W));
+                atomicAdd(p, a0); atomicAdd(p + 1, a1); atomicAdd(p + 2, a2);
+            }
+            kcur = k;
+            a0 = a1 = a2 = 0.f;
+        }
+        if (y != 0.0f) {
+            const float ta = T * (1.0f - __ldg(x_s + e));
+            const int g = __ldg(gid_s + e);
+            a0 = fmaf(ta, __ldg(l_d + 3 * g), a0);
+            a1 = fmaf(ta, __ldg(l_d + 3 * g + 1), a1);
+            a2 = fmaf(ta, __ldg(l_d + 3 * g + 2), a2);
+        }
+        kprev = k;
+        yprev = y;
+    }
+    if (kcur >= 0 && (a0 != 0.f || a1 != 0.f || a2 != 0.f)) {
+        float *p = image + 3 * static_cast<int64_t>(pixel_index(kcur, W));
+        atomicAdd(p, a0); atomicAdd(p + 1, a1); atomicAdd(p + 2, a2);
+    }
+}
+
+// w_k = <dL/dI(pixel), alpha_k l_k> (0 for dead elements); gshift[k] = w_{k+1} inside a pixel list, 0 at its tail:
+// the grad_out that makes grouped_cumprod_backward return T_k * U_k.
+__device__ __forceinline__ float elem_w(const float *__restrict__ incl, const float *__restrict__ x_s,
+                                        const int32_t *__restrict__ gid_s, const float *__restrict__ l_d,
+                                        const float *__restrict__ gimg, int64_t e, int key, int W, float &pgl) {
+    const int g = __ldg(gid_s + e);
+    const float *pg = gimg + 3 * static_cast<int64_t>(pixel_index(key, W));
+    pgl = __ldg(pg) * __ldg(l_d + 3 * g) + __ldg(pg + 1) * __ldg(l_d + 3 * g + 1) +
+          __ldg(pg + 2) * __ldg(l_d + 3 * g + 2);
+    return (__ldg(incl + e) != 0.0f) ? (1.0f - __ldg(x_s + e)) * pgl : 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+k_splat_bwd_w(const float *__restrict__ incl, const float *__restrict__ x_s, const int32_t *__restrict__ key_s,
+              const int32_t *__restrict__ gid_s, const float *__restrict__ l_d, const float *__restrict__ gimg,
+              int64_t N, int W, float *__restrict__ gshift) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
+        float out = 0.0f;
+        if (e + 1 < N) {
+            const int kn = __ldg(key_s + e + 1);
+            if (kn == __ldg(key_s + e)) {
+                float pgl;
+                out = elem_w(incl, x_s, gid_s, l_d, gimg, e + 1, kn, W, pgl);
+            }
+        }
+        gshift[e] = out;
+    }
+}
+
+// per element: dalpha = T <dL/dI, l> - T U  (tu = T*U from grouped_cumprod_backward), then the reference's
+// per-element gradients (gs_model.py:733-766) accumulated per Gaussian (:776-783):
+//   d_opacity += g * dalpha          d_l[c] += d / l[c]   (the reference's d/l, d = T w)
+//   d_mean    += alpha dalpha (r-m)Lambda        d_Lambda += -1/2 alpha dalpha (r-m)^T (r-m)
+__global__ void __launch_bounds__(256)
+k_splat_bwd_grads(const float *__restrict__ incl, const float *__restrict__ x_s, const float *__restrict__ tu,
+                  const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s,
+                  const float *__restrict__ mean, const float *__restrict__ lam, const float *__restrict__ opac,
+                  const float *__restrict__ l_d, const float *__restrict__ gimg, int64_t N, int W,
+                  float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
+                  float *__restrict__ g_l) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
+        const float y = __ldg(incl + e);
+        if (y == 0.0f) continue;  // dead element: no contribution, no gradient
+        const int k = __ldg(key_s + e);
+        const bool head = (e == 0) || (__ldg(key_s + e - 1) != k);
+        const float T = head ? 1.0f : __ldg(incl + e - 1);
+        const int g = __ldg(gid_s + e);
+        const Gauss G = load_gauss(mean, lam, opac, g);
+        float d0, d1, X0, X1;
+        const float gk = gauss_kernel(G, k, d0, d1, X0, X1);
+        const float alpha = G.o * gk;
+        const float *pg = gimg + 3 * static_cast<int64_t>(pixel_index(k, W));
+        const float l0 = __ldg(l_d + 3 * g), l1 = __ldg(l_d + 3 * g + 1), l2 = __ldg(l_d + 3 * g + 2);
+        const float pgl = __ldg(pg) * l0 + __ldg(pg + 1) * l1 + __ldg(pg + 2) * l2;
+        const float dalpha = T * pgl - __ldg(tu + e);
+        const float d = T * alpha * pgl;
+        const float coef = alpha * dalpha;
+        atomicAdd(g_opac + g, gk * dalpha);
+        atomicAdd(g_l + 3 * g, d / l0);
+        atomicAdd(g_l + 3 * g + 1, d / l1);
+        atomicAdd(g_l + 3 * g + 2, d / l2);
+        atomicAdd(g_mean + 2 * g, coef * X0);
+        atomicAdd(g_mean + 2 * g + 1, coef * X1);
+        const float hc = -0.5f * coef;
+        atomicAdd(g_lam + 4 * g, hc * d0 * d0);
+        atomicAdd(g_lam + 4 * g + 1, hc * d0 * d1);
+        atomicAdd(g_lam + 4 * g + 2, hc * d1 * d0);
+        atomicAdd(g_lam + 4 * g + 3, hc * d1 * d1);
+    }
+}
+
+inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
+    int64_t b = (work + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return static_cast<unsigned>(b);
+}
+inline int key_bits(int max_key) {
+    int b = 1;
+    while (b < 31 && (1 << b) <= max_key) ++b;
+    return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcp_splat_expand(const int32_t *sp, const int32_t *ep, const int64_t *goff, int64_t n, int64_t N,
+                     int32_t *key, int32_t *gid, gcp_stream_t stream) {
+    if (n < 0 || N < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    if (!sp || !ep || !goff || !key || !gid) return GCP_ERR_INVALID_ARG;
+    k_splat_expand<<<blocks_for(N, 256 * CH), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sp, ep, goff, n, N,
+                                                                                                  key, gid);
+    return static_cast<int>(cudaGetLastError());
+}
+
+size_t gcp_splat_sort_bytes(int64_t N) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const int32_t *>(nullptr),
+                                    static_cast<int32_t *>(nullptr), static_cast<const int32_t *>(nullptr),
+                                    static_cast<int32_t *>(nullptr), N > 0 ? N : 1, 0, 32);
+    return bytes;
+}
+
+int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_out, int32_t *gid_out, int64_t N,
+                   int max_key, void *temp, size_t temp_bytes, gcp_stream_t stream) {
+    if (N < 0 || max_key < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    if (!key_in || !gid_in || !key_out || !gid_out || !temp) return GCP_ERR_INVALID_ARG;
+    // LSD radix sort over the significant key bits only: stable, so depth order inside a pixel survives
+    return static_cast<int>(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_in, key_out, gid_in, gid_out, N, 0,
+                                                            key_bits(max_key),
+                                                            reinterpret_cast<cudaStream_t>(stream)));
+}
+
+int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *mean, const float *lam,
+                    const float *opac, int64_t N, float *x_s, gcp_stream_t stream) {
+    if (N < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    k_splat_alpha<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        key_s, gid_s, mean, lam, opac, N, x_s);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_splat_color(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
+                    const float *l_d, int64_t N, int W, float *image, gcp_stream_t stream) {
+    if (N < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    k_splat_color<<<blocks_for(N, 256 * CH), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(incl, x_s, key_s, gid_s,
+                                                                                                 l_d, N, W, image);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
+                    const float *l_d, const float *grad_image, int64_t N, int W, float *gshift,
+                    gcp_stream_t stream) {
+    if (N < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    k_splat_bwd_w<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        incl, x_s, key_s, gid_s, l_d, grad_image, N, W, gshift);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
+                        const int32_t *gid_s, const float *mean, const float *lam, const float *opac,
+                        const float *l_d, const float *grad_image, int64_t N, int W, float *g_mean, float *g_lam,
+                        float *g_opac, float *g_l, gcp_stream_t stream) {
+    if (N < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    k_splat_bwd_grads<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        incl, x_s, tu, key_s, gid_s, mean, lam, opac, l_d, grad_image, N, W, g_mean, g_lam, g_opac, g_l);
+    return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -13,8 +13,9 @@ import torch
 from test_compositor_oracle import CASES, FIX, load_case
 
 
-def _run(case, device):
-    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+def _run(case, device, F=None):
+    if F is None:
+        from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
 
     t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(device if dt is None else device, dtype=dt)  # noqa: E731
     boxsize = t(case["boxsize"])
@@ -41,9 +42,9 @@ def _check(got, case, rtol=1e-3, atol=1e-4):
 
 @pytest.fixture
 def oracle_backed_ops(monkeypatch):
-    """TEST ONLY: lets the host logic of compositor.py run without a GPU."""
+    """The torch fp32 formulation (oracle/compositor_torch.py) with the scan ops backed by the C oracle."""
     from oracle import oracle as orc
-    from simplegaussiansplat_tk71_b200 import compositor
+    from oracle import compositor_torch as compositor
 
     def fwd(x, key, y):
         y.copy_(torch.from_numpy(orc.cumprod_fwd(x.numpy(), key.numpy(), np.float32)))
@@ -56,14 +57,25 @@ def oracle_backed_ops(monkeypatch):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_host_logic_matches_reference_fixture_cpu(name, oracle_backed_ops):
+def test_torch_formulation_matches_reference_fixture_cpu(name, oracle_backed_ops):
+    """Pins the division-free algorithm itself (T_i U_i through the backward op) to the reference's Function."""
+    from oracle.compositor_torch import custom_autograd_grouped_cumprod as F
+
     case = load_case(np.load(FIX), name)
-    _check(_run(case, "cpu"), case)
+    _check(_run(case, "cpu", F), case)
+
+
+def test_native_compositor_refuses_cpu_tensors():
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    case = load_case(np.load(FIX), "small")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _run(case, "cpu", F)
 
 
 def test_element_plan_integer_side_is_bit_exact():
     """Sort permutation, segment ids and offsets against torch.sort(stable=True) / unique_consecutive."""
-    from simplegaussiansplat_tk71_b200.compositor import ElementPlan
+    from oracle.compositor_torch import ElementPlan
     from oracle import compositor_oracle as co
 
     case = load_case(np.load(FIX), "wide")
@@ -83,6 +95,23 @@ def test_element_plan_integer_side_is_bit_exact():
 def test_native_compositor_matches_reference_fixture_gpu(name):
     case = load_case(np.load(FIX), name)
     _check(_run(case, "cuda"), case)
+
+
+@pytest.mark.gpu
+def test_native_expansion_and_sort_are_bit_exact_gpu():
+    """Integer side of the native path: keys, Gaussian ids and their stable order vs numpy argsort(stable)."""
+    from oracle import compositor_oracle as co
+    from simplegaussiansplat_tk71_b200 import compositor
+
+    case = load_case(np.load(FIX), "wide")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    _, view = compositor._render_forward(t(case["boxsize"]), t(case["sp"]), t(case["ep"]), t(case["mean"]).float(),
+                                         t(case["lam"]), t(case["opac"]), t(case["l_d"]), case["W"], case["H"])
+    gid, px, py = co.expand(case["boxsize"], case["sp"], case["ep"])
+    key = (py * 10000 + px).astype(np.int32)
+    order = np.argsort(key, kind="stable")
+    assert np.array_equal(view.key_s.cpu().numpy(), key[order])
+    assert np.array_equal(view.gid_s.cpu().numpy(), gid[order].astype(np.int32))
 
 
 @pytest.mark.gpu
