@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="time every kernel variant (stderr table), then exit")
+    ap.add_argument("--views", type=int, default=64, help="views per training step for the multi-view leg (C5)")
+    ap.add_argument("--no-splat", action="store_true", help="skip the splat-step / multi-view legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -313,6 +315,13 @@ def main():
     h2d = int(sum(t_.numel() * t_.element_size() for t_ in (hx, hk, hg, hi, hs)))
     d2h = int(hy.numel() * 4 + hgin.numel() * 4)
 
+    # ---- splat step @1080p and the multi-view step (BASELINE.json configs[4]) ----
+    splat = None
+    if not args.no_splat:
+        del hx, hk, hg, hi, hs, hy, hgin, dx, dk, dg, di, ds
+        splat = splat_legs(args, device, rank, world)
+        hx, hk, hi, hs, hg = (t_.cpu() for t_ in (e.x, e.key, e.inv, e.seg_end, e.grad_out))
+
     # ---- CPU baseline (rank 0, N == 1 only): the oracle's C/OpenMP port on the same inputs ----
     cpu = None
     cpu_torch = None
@@ -374,10 +383,99 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
+            "splat_step": splat,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def splat_legs(args, device, rank, world):
+    """(i) splat step ms @1080p: compositor forward+backward of ONE view (BASELINE metric, second half);
+    (ii) multi-view training step (configs[4]): `--views` views sharded round-robin over the ranks, per-Gaussian
+    gradients accumulated into one flat bucket of 38 floats per Gaussian (the reference's parameter set,
+    gs_model.py:151-158) and summed with ONE NCCL all-reduce per step."""
+    import torch
+    import torch.distributed as dist
+
+    from simplegaussiansplat_tk71_b200 import views as vw
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    mine = vw.views_for_rank(args.views, rank, world)
+    distinct = max(1, min(2, len(mine)))           # scene generation is host-side numpy: reuse a few views
+    scenes = [wl.splat_view(1920, 1080, 1_000_000, seed=1080 + mine[i] if mine else 1080, device=device)
+              for i in range(distinct)]
+    n_param = 1_000_000
+    bucket = torch.zeros(n_param * vw.PARAM_FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
+    leaves = []
+    for sc in scenes:
+        leaves.append([sc.mean.float().requires_grad_(True), sc.lam.clone().requires_grad_(True),
+                       sc.opacity.clone().requires_grad_(True), sc.l_d.clone().requires_grad_(True)])
+    gI = torch.rand(1081, 1921, 3, device=device) + 0.1
+    W, H = torch.tensor(1920), torch.tensor(1080)
+
+    def one_view(i):
+        sc, (m, lam, o, l) = scenes[i % distinct], leaves[i % distinct]
+        for t_ in (m, lam, o, l):
+            t_.grad = None
+        img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)
+        img.backward(gI)
+        k = sc.n
+        b = bucket.view(n_param, vw.PARAM_FLOATS_PER_GAUSSIAN)
+        b[:k, 0:2] += m.grad
+        b[:k, 2:6] += lam.grad.reshape(k, 4)
+        b[:k, 6:7] += o.grad
+        b[:k, 7:10] += l.grad
+        return sc.elements
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    for _ in range(2):
+        one_view(0)
+    torch.cuda.synchronize()
+    # (i) single view
+    reps = 5
+    a, bb, c = ev(), ev(), ev()
+    tf = tb = 0.0
+    sc, (m, lam, o, l) = scenes[0], leaves[0]
+    for _ in range(reps):
+        for t_ in (m, lam, o, l):
+            t_.grad = None
+        a.record()
+        img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)
+        bb.record()
+        img.backward(gI)
+        c.record()
+        torch.cuda.synchronize()
+        tf += a.elapsed_time(bb)
+        tb += bb.elapsed_time(c)
+    out = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n, "fwd_ms": tf / reps, "bwd_ms": tb / reps,
+           "ms": (tf + tb) / reps, "unit": "ms per view (render + backward)"}
+    # (ii) multi-view step
+    steps = 3
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1, t2 = ev(), ev(), ev()
+    step_ms = ar_ms = 0.0
+    elems = 0
+    for _ in range(steps):
+        bucket.zero_()
+        t0.record()
+        elems = sum(one_view(i) for i in range(len(mine)))
+        t1.record()
+        vw.allreduce_param_grads(bucket)
+        t2.record()
+        torch.cuda.synchronize()
+        step_ms += t0.elapsed_time(t2)
+        ar_ms += t1.elapsed_time(t2)
+    tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
+    _, max_ar = vw.aggregate_throughput(0, ar_ms / steps, device)
+    out["multi_view"] = {"views": args.views, "views_per_rank": len(mine), "distinct_scenes_per_rank": distinct,
+                         "step_ms": max_ms, "allreduce_ms": max_ar, "bucket_bytes": bucket.numel() * 4,
+                         "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
+                         "collective": "nccl all_reduce(sum) of the parameter-gradient bucket" if world > 1 else "none (1 rank)"}
+    return out
 
 
 def sweep(args, e, y, gin, gc, ops):

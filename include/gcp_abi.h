@@ -156,6 +156,19 @@ int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, c
                     const float *l_d, const float *grad_image, int64_t N, int W, float *gshift,
                     gcp_stream_t stream);
 
+/* Backward in two atomic-free steps (preferred over gcp_splat_bwd_grads):
+ *  gcp_splat_bwd_elem   (sorted order) writes (dalpha, d) of every element at its Gaussian-major position
+ *                       goff[g] + (y-sy)*w + (x-sx) of elem f32[N,2] — the un-sort, without a permutation;
+ *  gcp_splat_bwd_reduce (Gaussian-major) one warp per Gaussian sums the per-element gradients of
+ *                       gs_model.py:733-766 over its box (replaces scatter_reduce, :776-783); deterministic. */
+int gcp_splat_bwd_elem(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
+                       const int32_t *gid_s, const int32_t *sp, const int32_t *ep, const int64_t *goff,
+                       const float *l_d, const float *grad_image, int64_t N, int W, float *elem,
+                       gcp_stream_t stream);
+int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep, const int64_t *goff,
+                         const float *mean, const float *lam, const float *opac, const float *l_d, int64_t n,
+                         float *g_mean, float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream);
+
 /* Per-element gradients (gs_model.py:733-766) accumulated per Gaussian (:776-783); tu = T*U from
  * gcp_cumprod_bwd_f32.  Outputs must be zeroed by the caller: g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3]. */
 int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,

@@ -26,7 +26,7 @@ SYMBOLS = (
     "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
     "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
     "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color",
-    "gcp_splat_bwd_w", "gcp_splat_bwd_grads",
+    "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce",
 )
 
 
@@ -68,8 +68,10 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_color.argtypes = [vp, vp, vp, vp, vp, i64, ci, vp, vp]
     L.gcp_splat_bwd_w.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
     L.gcp_splat_bwd_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp, vp, vp, vp]
+    L.gcp_splat_bwd_elem.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
+    L.gcp_splat_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",
-                 "gcp_splat_bwd_grads"):
+                 "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce"):
         getattr(L, name).restype = ci
     for name in ("gcp_workspace_init", "gcp_workspace_status", "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32",
                  "gcp_cumprod_bwd_f32", "gcp_validate_segments", "gcp_set_variant", "gcp_num_variants"):

@@ -12,7 +12,7 @@ fits one chunk (sum(boxsize) <= 2**29, gs_model.py:428):
     T_i = prod_{j<i, same pixel} (1 - alpha_j),   alpha = opacity * exp(-1/2 (r-m) Lambda (r-m)^T)
     image[y, x] = sum_i T_i alpha_i l_i           (elements whose inclusive product is 0 contribute nothing, :575)
 
-but not how.  One view = nine kernel launches, all through the C ABI (include/gcp_abi.h):
+but not how.  One view = ten kernel launches, all through the C ABI (include/gcp_abi.h):
 
     forward   gcp_splat_expand   boxes -> (pixel key, Gaussian id) per element          (:480-482, :538-541)
               gcp_splat_sort     stable radix sort by key, significant bits only        (:547-548)
@@ -22,7 +22,10 @@ but not how.  One view = nine kernel launches, all through the C ABI (include/gc
                                  the per-pixel colour sum                               (:562, :498-514)
     backward  gcp_splat_bwd_w    w_k = <dL/dI, alpha_k l_k>, shifted by one in its list
               gcp_cumprod_bwd    division-free T_k*U_k (op a3)                          (replaces :716-722)
-              gcp_splat_bwd_grads  per-element gradients accumulated per Gaussian       (:733-783)
+              gcp_splat_bwd_elem (dalpha, d) per element, written at its Gaussian-major
+                                 position (the un-sort, without a permutation array)
+              gcp_splat_bwd_reduce one warp per Gaussian sums the per-element gradients
+                                 over its box: no atomics, deterministic                (:733-783)
 
 There is no un-sort (:555), no flip + second sorted pass (:716-722), no chunk loop (:675, :792), no forward
 recompute in the backward (:799) and no division by 1-alpha (:736,:747,:757): with
@@ -48,7 +51,8 @@ def _p(t):
 
 class _View:
     """Device state of one rendered view kept for the backward (16 B per element + the per-Gaussian tables)."""
-    __slots__ = ("n", "N", "W", "H", "key_s", "gid_s", "x_s", "incl", "mean", "lam", "opac", "l_d")
+    __slots__ = ("n", "N", "W", "H", "key_s", "gid_s", "x_s", "incl", "mean", "lam", "opac", "l_d", "sp", "ep",
+                 "goff")
 
 
 def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
@@ -71,13 +75,15 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
         v.opac = opacity.detach().to(torch.float32).reshape(n).contiguous()
         v.l_d = l_d.detach().to(torch.float32).contiguous()
         image = torch.zeros((H + 1, W + 1, 3), dtype=torch.float32, device=dev)
+        v.goff = goff
+        v.sp = startpoint.to(torch.int32).contiguous()
+        v.ep = endpoint.to(torch.int32).contiguous()
         if N == 0:
             v.key_s = v.gid_s = v.x_s = v.incl = None
             return image, v
         if N >= 2 ** 31:
             raise RuntimeError("a view is limited to 2**31-1 elements (the reference ops index with int32)")
-        sp = startpoint.to(torch.int32).contiguous()
-        ep = endpoint.to(torch.int32).contiguous()
+        sp, ep = v.sp, v.ep
         key = torch.empty(N, dtype=torch.int32, device=dev)
         gid = torch.empty(N, dtype=torch.int32, device=dev)
         _lib.check(L.gcp_splat_expand(_p(sp), _p(ep), _p(goff), n, N, _p(key), _p(gid), stream), "gcp_splat_expand")
@@ -100,12 +106,13 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
 def _render_backward(v: _View, grad_image):
     dev = grad_image.device
     n = v.n
-    g_mean = torch.zeros((n, 2), dtype=torch.float32, device=dev)
-    g_lam = torch.zeros((n, 4), dtype=torch.float32, device=dev)
-    g_opac = torch.zeros((n,), dtype=torch.float32, device=dev)
-    g_l = torch.zeros((n, 3), dtype=torch.float32, device=dev)
     if v.N == 0:
-        return g_mean, g_lam, g_opac, g_l
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        return z(n, 2), z(n, 4), z(n), z(n, 3)
+    g_mean = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    g_lam = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    g_opac = torch.empty((n,), dtype=torch.float32, device=dev)
+    g_l = torch.empty((n, 3), dtype=torch.float32, device=dev)
     L = _lib.lib()
     gI = grad_image.detach().to(torch.float32).contiguous()
     with torch.cuda.device(dev):
@@ -118,9 +125,14 @@ def _render_backward(v: _View, grad_image):
         # (inv_len is implied by them, include/gcp_abi.h)
         ops.grouped_cumprod_backward(v.x_s, v.incl, gshift, v.key_s, tu,
                                      torch.empty(0, dtype=torch.int32, device=dev))
-        _lib.check(L.gcp_splat_bwd_grads(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.mean),
-                                         _p(v.lam), _p(v.opac), _p(v.l_d), _p(gI), v.N, v.W, _p(g_mean), _p(g_lam),
-                                         _p(g_opac), _p(g_l), stream), "gcp_splat_bwd_grads")
+        elem = gshift.new_empty((v.N, 2))
+        del gshift
+        _lib.check(L.gcp_splat_bwd_elem(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.sp), _p(v.ep),
+                                        _p(v.goff), _p(v.l_d), _p(gI), v.N, v.W, _p(elem), stream),
+                   "gcp_splat_bwd_elem")
+        _lib.check(L.gcp_splat_bwd_reduce(_p(elem), _p(v.sp), _p(v.ep), _p(v.goff), _p(v.mean), _p(v.lam),
+                                          _p(v.opac), _p(v.l_d), n, _p(g_mean), _p(g_lam), _p(g_opac), _p(g_l),
+                                          stream), "gcp_splat_bwd_reduce")
     return g_mean, g_lam, g_opac, g_l
 
 

@@ -232,6 +232,102 @@ k_splat_bwd_grads(const float *__restrict__ incl, const float *__restrict__ x_s,
     }
 }
 
+// Backward, step 1 of 2 (sorted order): per element (dalpha, d) written at the element's GAUSSIAN-MAJOR
+// position e = goff[g] + (y - sy)*w + (x - sx), i.e. un-sorted without a permutation array.  Neighbouring
+// pixels of a box row are neighbouring pixel lists, so the scattered 8-byte stores of one tile land in
+// the same few sectors.
+//   dalpha = T <dL/dI, l> - T U   (tu = T*U from grouped_cumprod_backward);   d = T alpha <dL/dI, l>
+__global__ void __launch_bounds__(256)
+k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, const float *__restrict__ tu,
+                 const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s,
+                 const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ goff,
+                 const float *__restrict__ l_d, const float *__restrict__ gimg, int64_t N, int W,
+                 float2 *__restrict__ elem) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
+        const int k = __ldg(key_s + e);
+        const int g = __ldg(gid_s + e);
+        const int py = k / KEY_STRIDE, px = k - py * KEY_STRIDE;
+        const int2 s = __ldg(reinterpret_cast<const int2 *>(sp) + g);
+        const int w = __ldg(ep + 2 * g) - s.x + 1;
+        const int64_t dst = __ldg(goff + g) + static_cast<int64_t>(py - s.y) * w + (px - s.x);
+        float2 out = make_float2(0.0f, 0.0f);
+        const float y = __ldg(incl + e);
+        if (y != 0.0f) {  // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
+            const bool head = (e == 0) || (__ldg(key_s + e - 1) != k);
+            const float T = head ? 1.0f : __ldg(incl + e - 1);
+            const float *pg = gimg + 3 * static_cast<int64_t>(py * (W + 1) + px);
+            const float pgl = __ldg(pg) * __ldg(l_d + 3 * g) + __ldg(pg + 1) * __ldg(l_d + 3 * g + 1) +
+                              __ldg(pg + 2) * __ldg(l_d + 3 * g + 2);
+            const float alpha = 1.0f - __ldg(x_s + e);
+            out.x = T * pgl - __ldg(tu + e);
+            out.y = T * alpha * pgl;
+        }
+        elem[dst] = out;
+    }
+}
+
+// Backward, step 2 of 2 (Gaussian-major order): one warp per Gaussian sums the reference's per-element
+// gradients (gs_model.py:733-766) over its box — a segmented reduction without atomics, deterministic:
+//   d_opacity = sum g dalpha            d_l[c] = (sum d) / l[c]      (the reference's d/l, :763-766)
+//   d_mean    = sum alpha dalpha (r-m)Lambda          d_Lambda = sum -1/2 alpha dalpha (r-m)^T (r-m)
+__global__ void __launch_bounds__(256)
+k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
+                   const int64_t *__restrict__ goff, const float *__restrict__ mean, const float *__restrict__ lam,
+                   const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
+                   float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
+                   float *__restrict__ g_l) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t g = warp0; g < n; g += nwarps) {
+        const int64_t b = __ldg(goff + g), eend = __ldg(goff + g + 1);
+        const Gauss G = load_gauss(mean, lam, opac, static_cast<int>(g));
+        const int sx = __ldg(sp + 2 * g), sy = __ldg(sp + 2 * g + 1);
+        const int w = __ldg(ep + 2 * g) - sx + 1;
+        float a_o = 0.f, a_d = 0.f, a_m0 = 0.f, a_m1 = 0.f, a_00 = 0.f, a_01 = 0.f, a_11 = 0.f;
+        for (int64_t e = b + lane; e < eend; e += 32) {
+            const float2 v = __ldg(elem + e);
+            const int local = static_cast<int>(e - b);
+            const int iy = local / w, ix = local - iy * w;
+            const float d0 = static_cast<float>(sx + ix) - G.mx, d1 = static_cast<float>(sy + iy) - G.my;
+            const float X0 = d0 * G.l00 + d1 * G.l10, X1 = d0 * G.l01 + d1 * G.l11;
+            const float gk = expf(-0.5f * (X0 * d0 + X1 * d1));
+            const float coef = G.o * gk * v.x;
+            a_o = fmaf(gk, v.x, a_o);
+            a_d += v.y;
+            a_m0 = fmaf(coef, X0, a_m0);
+            a_m1 = fmaf(coef, X1, a_m1);
+            const float hc = -0.5f * coef;
+            a_00 = fmaf(hc * d0, d0, a_00);
+            a_01 = fmaf(hc * d0, d1, a_01);
+            a_11 = fmaf(hc * d1, d1, a_11);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            a_o += __shfl_xor_sync(0xffffffffu, a_o, d);
+            a_d += __shfl_xor_sync(0xffffffffu, a_d, d);
+            a_m0 += __shfl_xor_sync(0xffffffffu, a_m0, d);
+            a_m1 += __shfl_xor_sync(0xffffffffu, a_m1, d);
+            a_00 += __shfl_xor_sync(0xffffffffu, a_00, d);
+            a_01 += __shfl_xor_sync(0xffffffffu, a_01, d);
+            a_11 += __shfl_xor_sync(0xffffffffu, a_11, d);
+        }
+        if (lane == 0) {
+            g_opac[g] = a_o;
+            g_l[3 * g] = a_d / __ldg(l_d + 3 * g);
+            g_l[3 * g + 1] = a_d / __ldg(l_d + 3 * g + 1);
+            g_l[3 * g + 2] = a_d / __ldg(l_d + 3 * g + 2);
+            g_mean[2 * g] = a_m0;
+            g_mean[2 * g + 1] = a_m1;
+            g_lam[4 * g] = a_00;
+            g_lam[4 * g + 1] = a_01;
+            g_lam[4 * g + 2] = a_01;
+            g_lam[4 * g + 3] = a_11;
+        }
+    }
+}
+
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -313,6 +409,27 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
     if (N == 0) return GCP_OK;
     k_splat_bwd_grads<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         incl, x_s, tu, key_s, gid_s, mean, lam, opac, l_d, grad_image, N, W, g_mean, g_lam, g_opac, g_l);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_splat_bwd_elem(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
+                       const int32_t *gid_s, const int32_t *sp, const int32_t *ep, const int64_t *goff,
+                       const float *l_d, const float *grad_image, int64_t N, int W, float *elem,
+                       gcp_stream_t stream) {
+    if (N < 0) return GCP_ERR_INVALID_ARG;
+    if (N == 0) return GCP_OK;
+    k_splat_bwd_elem<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        incl, x_s, tu, key_s, gid_s, sp, ep, goff, l_d, grad_image, N, W, reinterpret_cast<float2 *>(elem));
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep, const int64_t *goff,
+                         const float *mean, const float *lam, const float *opac, const float *l_d, int64_t n,
+                         float *g_mean, float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
+    if (n < 0) return GCP_ERR_INVALID_ARG;
+    if (n == 0) return GCP_OK;
+    k_splat_bwd_reduce<<<blocks_for(n, 8, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2 *>(elem), sp, ep, goff, mean, lam, opac, l_d, n, g_mean, g_lam, g_opac, g_l);
     return static_cast<int>(cudaGetLastError());
 }
 
