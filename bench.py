@@ -13,8 +13,10 @@ Prints ONE JSON line (rank 0).  value = Gelem/s fwd+bwd = (elements of all ranks
 device time.  N > 1: one process per GPU (torchrun), each rank owns its own view (seed 1080+rank);
 views are independent (gs_model.py:402), so there is no data-path collective: scaling = weak.
 
---impl reference: the CPU arm.  The reference has no CPU implementation of these ops,
-so this times the oracle's C/OpenMP port (oracle/gcp_oracle.c) on the host cores, rank 0 only.
+--impl reference: the CPU arm, rank 0 only.  The reference has no CPU implementation of these ops
+(SURVEY.md §8c); the arm BASELINE.json names is "reference PyTorch grouped_cumprod fwd+bwd on CPU": the
+pure-PyTorch restatement in oracle/torch_cpu_path.py, all host threads.  The oracle's much faster C/OpenMP
+port is reported beside it (cpu_baseline_c_omp).
 """
 from __future__ import annotations
 
@@ -144,39 +146,63 @@ def cpu_port_run(e_cpu, min_seconds: float, max_reps: int):
     return x.shape[0] / med / 1e9, len(times), orc.max_threads(), med
 
 
+def torch_cpu_run(e_cpu, reps: int):
+    """The 'reference PyTorch path on CPU' (BASELINE.json configs[0] / north_star): pure-PyTorch segmented cumprod
+    forward + autograd backward (oracle/torch_cpu_path.py), all host threads.  The bucketing plan (a function of
+    the keys only) is built once outside the timed region.  Returns (Gelem/s, median s, threads)."""
+    import torch
+
+    from oracle.torch_cpu_path import grouped_cumprod_fwd_bwd
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, _, plan = grouped_cumprod_fwd_bwd(e_cpu.x, e_cpu.key, e_cpu.grad_out)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        grouped_cumprod_fwd_bwd(e_cpu.x, e_cpu.key, e_cpu.grad_out, plan)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return e_cpu.n / med / 1e9, med, torch.get_num_threads()
+
+
 def run_reference_arm(args):
-    """CPU arm: rank 0 only."""
+    """CPU arm, rank 0 only.  The reference ships no CPU implementation of its ops; the arm
+    BASELINE.json names is the pure-PyTorch CPU path, restated in oracle/torch_cpu_path.py.  The much faster
+    C/OpenMP port of the oracle is reported beside it (cpu_baseline_c_omp) as a stronger CPU bound."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
     from oracle import oracle as orc
+    from oracle.torch_cpu_path import grouped_cumprod_fwd_bwd
 
     orc.build()
     torch.set_num_threads(os.cpu_count() or 1)
     e = make_workload(args.workload, "cpu", 0)
-    x, g, key = e.x.numpy(), e.grad_out.numpy(), e.key.numpy()
-    import numpy as np
-
-    starts = orc.segment_starts(key)
-    y, gin = np.empty_like(x), np.empty_like(x)
-    for _ in range(max(1, args.warmup)):
-        orc.fwd_bwd_f32_omp(x, g, starts, 0, y, gin)
+    _, _, plan = grouped_cumprod_fwd_bwd(e.x, e.key, e.grad_out)
+    for _ in range(max(1, min(args.warmup, 2))):
+        grouped_cumprod_fwd_bwd(e.x, e.key, e.grad_out, plan)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.fwd_bwd_f32_omp(x, g, starts, 0, y, gin)
+        grouped_cumprod_fwd_bwd(e.x, e.key, e.grad_out, plan)
     dt = time.perf_counter() - t0
     val = e.n * args.steps / dt / 1e9
-    cores = orc.max_threads()
+    cores = torch.get_num_threads()
+    c_val, c_reps, c_cores, c_med = cpu_port_run(e, min_seconds=3.0, max_reps=6)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": e.name, "elements": e.n, "segments": e.k},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"whole view ({e.n} elements, {e.k} segments) per step, C/OpenMP port of the "
-                                   "ops (the reference has no CPU implementation; oracle/gcp_oracle.c)"},
+                         "sample": f"whole view ({e.n} elements, {e.k} segments) per step; pure-PyTorch CPU path "
+                                   "(length-bucketed torch.cumprod + autograd backward, oracle/torch_cpu_path.py) — "
+                                   "the reference has no CPU implementation of its ops"},
+        "cpu_baseline_c_omp": {"value": c_val, "unit": UNIT, "cores": c_cores, "kind": "port",
+                               "sample": f"same view x {c_reps} reps, median {c_med * 1e3:.1f} ms; C/OpenMP port "
+                                         "(oracle/gcp_oracle.c)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -324,6 +350,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N == 1 only): the oracle's C/OpenMP port on the same inputs ----
     cpu = None
+    cpu_c = None
     cpu_torch = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -331,25 +358,19 @@ def main():
 
             orc.build()
             e_cpu = wl.ElementList(e.name, hx, hk, hi, hs, hg, e.width, e.height)
-            v, reps, cores, med = cpu_port_run(e_cpu, min_seconds=8.0, max_reps=12)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"whole view ({n} elements) x {reps} reps, median {med * 1e3:.1f} ms; C/OpenMP port "
-                             "of fwd + division-free bwd, parallel over segments (oracle/gcp_oracle.c)"}
-            # BASELINE.json configs[0]: pure-PyTorch CPU path on C1 (1 Mi elements / 64 Ki segments)
-            from oracle.torch_cpu_path import grouped_cumprod_fwd_bwd
-
-            torch.set_num_threads(os.cpu_count() or 1)
+            tv, tmed, tthreads = torch_cpu_run(e_cpu, reps=5)
+            cpu = {"value": tv, "unit": UNIT, "cores": tthreads, "kind": "port",
+                   "sample": f"whole view ({n} elements) x 5 reps, median {tmed * 1e3:.0f} ms; pure-PyTorch CPU path "
+                             "(oracle/torch_cpu_path.py), the CPU arm BASELINE.json names"}
+            v, reps, cores, med = cpu_port_run(e_cpu, min_seconds=4.0, max_reps=8)
+            cpu_c = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                     "sample": f"whole view ({n} elements) x {reps} reps, median {med * 1e3:.1f} ms; C/OpenMP port "
+                               "of fwd + division-free bwd, parallel over segments (oracle/gcp_oracle.c)"}
+            # BASELINE.json configs[0]: the same PyTorch CPU path on C1 (1 Mi elements / 64 Ki segments)
             c1 = wl.c1("cpu")
-            _, _, plan = grouped_cumprod_fwd_bwd(c1.x, c1.key, c1.grad_out)
-            ts = []
-            for _ in range(5):
-                t0 = time.perf_counter()
-                grouped_cumprod_fwd_bwd(c1.x, c1.key, c1.grad_out, plan)
-                ts.append(time.perf_counter() - t0)
-            ts.sort()
-            cpu_torch = {"value": c1.n / ts[2] / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
-                         "kind": "port", "sample": "C1 (1 Mi elements / 64 Ki segments), pure-PyTorch CPU path "
-                                                   f"(oracle/torch_cpu_path.py), median of 5 = {ts[2] * 1e3:.1f} ms"}
+            c1v, c1med, _ = torch_cpu_run(c1, reps=5)
+            cpu_torch = {"value": c1v, "unit": UNIT, "cores": tthreads, "kind": "port",
+                         "sample": f"C1 (1 Mi elements / 64 Ki segments), median of 5 = {c1med * 1e3:.1f} ms"}
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
@@ -378,7 +399,7 @@ def main():
                              "algorithmic_bytes": ab["fwd"]},
             "roofline_fwd_bwd": {"achieved": both_gbs, "peak": peak, "unit": "GB/s", "frac": both_gbs / peak,
                                  "frac_of_nominal_8TBs": both_gbs / 8000.0},
-            "cpu_baseline": cpu, "cpu_baseline_torch_c1": cpu_torch,
+            "cpu_baseline": cpu, "cpu_baseline_c_omp": cpu_c, "cpu_baseline_torch_c1": cpu_torch,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
