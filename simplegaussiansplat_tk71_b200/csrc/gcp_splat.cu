@@ -100,16 +100,36 @@ __device__ __forceinline__ float gauss_kernel(const Gauss &G, int key, float &d0
     return expf(-0.5f * (X0 * d0 + X1 * d1));
 }
 
-// x_s[e] = 1 - o*g in sorted order (the scan's input)
+// x_s[e] = 1 - o*g in sorted order (the scan's input); 4 consecutive elements per thread
 __global__ void __launch_bounds__(256)
 k_splat_alpha(const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s, const float *__restrict__ mean,
               const float *__restrict__ lam, const float *__restrict__ opac, int64_t N, float *__restrict__ x_s) {
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
-        const Gauss G = load_gauss(mean, lam, opac, __ldg(gid_s + e));
-        float d0, d1, X0, X1;
-        const float g = gauss_kernel(G, __ldg(key_s + e), d0, d1, X0, X1);
-        x_s[e] = 1.0f - G.o * g;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+    for (int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e < N; e += stride) {
+        int k[4], g[4];
+        if (e + 4 <= N) {
+            const int4 kk = __ldg(reinterpret_cast<const int4 *>(key_s + e));
+            const int4 gg = __ldg(reinterpret_cast<const int4 *>(gid_s + e));
+            k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
+            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+        } else {
+            for (int i = 0; i < 4; ++i) {
+                k[i] = (e + i < N) ? __ldg(key_s + e + i) : 0;
+                g[i] = (e + i < N) ? __ldg(gid_s + e + i) : 0;
+            }
+        }
+        float out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const Gauss G = load_gauss(mean, lam, opac, g[i]);
+            float d0, d1, X0, X1;
+            out[i] = 1.0f - G.o * gauss_kernel(G, k[i], d0, d1, X0, X1);
+        }
+        if (e + 4 <= N) {
+            *reinterpret_cast<float4 *>(x_s + e) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+            for (int i = 0; i < 4 && e + i < N; ++i) x_s[e + i] = out[i];
+        }
     }
 }
 
@@ -175,17 +195,26 @@ __global__ void __launch_bounds__(256)
 k_splat_bwd_w(const float *__restrict__ incl, const float *__restrict__ x_s, const int32_t *__restrict__ key_s,
               const int32_t *__restrict__ gid_s, const float *__restrict__ l_d, const float *__restrict__ gimg,
               int64_t N, int W, float *__restrict__ gshift) {
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
-        float out = 0.0f;
-        if (e + 1 < N) {
-            const int kn = __ldg(key_s + e + 1);
-            if (kn == __ldg(key_s + e)) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+    for (int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e < N; e += stride) {
+        // elements e+1 .. e+4 are needed (w of the successor); load keys e .. e+4
+        int k[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) k[i] = (e + i < N) ? __ldg(key_s + e + i) : -1;
+        float out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            out[i] = 0.0f;
+            if (e + i + 1 < N && k[i + 1] == k[i]) {
                 float pgl;
-                out = elem_w(incl, x_s, gid_s, l_d, gimg, e + 1, kn, W, pgl);
+                out[i] = elem_w(incl, x_s, gid_s, l_d, gimg, e + i + 1, k[i + 1], W, pgl);
             }
         }
-        gshift[e] = out;
+        if (e + 4 <= N) {
+            *reinterpret_cast<float4 *>(gshift + e) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+            for (int i = 0; i < 4 && e + i < N; ++i) gshift[e + i] = out[i];
+        }
     }
 }
 
@@ -243,27 +272,54 @@ k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, 
                  const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ goff,
                  const float *__restrict__ l_d, const float *__restrict__ gimg, int64_t N, int W,
                  float2 *__restrict__ elem) {
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < N; e += stride) {
-        const int k = __ldg(key_s + e);
-        const int g = __ldg(gid_s + e);
-        const int py = k / KEY_STRIDE, px = k - py * KEY_STRIDE;
-        const int2 s = __ldg(reinterpret_cast<const int2 *>(sp) + g);
-        const int w = __ldg(ep + 2 * g) - s.x + 1;
-        const int64_t dst = __ldg(goff + g) + static_cast<int64_t>(py - s.y) * w + (px - s.x);
-        float2 out = make_float2(0.0f, 0.0f);
-        const float y = __ldg(incl + e);
-        if (y != 0.0f) {  // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
-            const bool head = (e == 0) || (__ldg(key_s + e - 1) != k);
-            const float T = head ? 1.0f : __ldg(incl + e - 1);
-            const float *pg = gimg + 3 * static_cast<int64_t>(py * (W + 1) + px);
-            const float pgl = __ldg(pg) * __ldg(l_d + 3 * g) + __ldg(pg + 1) * __ldg(l_d + 3 * g + 1) +
-                              __ldg(pg + 2) * __ldg(l_d + 3 * g + 2);
-            const float alpha = 1.0f - __ldg(x_s + e);
-            out.x = T * pgl - __ldg(tu + e);
-            out.y = T * alpha * pgl;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e0 < N; e0 += stride) {
+        int k[4], g[4];
+        float y[4], xx[4], t[4];
+        if (e0 + 4 <= N) {
+            const int4 kk = __ldg(reinterpret_cast<const int4 *>(key_s + e0));
+            const int4 gg = __ldg(reinterpret_cast<const int4 *>(gid_s + e0));
+            const float4 yy = __ldg(reinterpret_cast<const float4 *>(incl + e0));
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_s + e0));
+            const float4 tv = __ldg(reinterpret_cast<const float4 *>(tu + e0));
+            k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
+            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+            y[0] = yy.x; y[1] = yy.y; y[2] = yy.z; y[3] = yy.w;
+            xx[0] = xv.x; xx[1] = xv.y; xx[2] = xv.z; xx[3] = xv.w;
+            t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
+        } else {
+            for (int i = 0; i < 4; ++i) {
+                const bool in = e0 + i < N;
+                k[i] = in ? __ldg(key_s + e0 + i) : -1;
+                g[i] = in ? __ldg(gid_s + e0 + i) : 0;
+                y[i] = in ? __ldg(incl + e0 + i) : 0.0f;
+                xx[i] = in ? __ldg(x_s + e0 + i) : 1.0f;
+                t[i] = in ? __ldg(tu + e0 + i) : 0.0f;
+            }
         }
-        elem[dst] = out;
+        int kprev = (e0 > 0) ? __ldg(key_s + e0 - 1) : -1;
+        float yprev = (e0 > 0) ? __ldg(incl + e0 - 1) : 1.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (e0 + i < N) {
+                const int py = k[i] / KEY_STRIDE, px = k[i] - py * KEY_STRIDE;
+                const int2 s2 = __ldg(reinterpret_cast<const int2 *>(sp) + g[i]);
+                const int w = __ldg(ep + 2 * g[i]) - s2.x + 1;
+                const int64_t dst = __ldg(goff + g[i]) + static_cast<int64_t>(py - s2.y) * w + (px - s2.x);
+                float2 out = make_float2(0.0f, 0.0f);
+                if (y[i] != 0.0f) {  // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
+                    const float T = (k[i] != kprev) ? 1.0f : yprev;
+                    const float *pg = gimg + 3 * static_cast<int64_t>(py * (W + 1) + px);
+                    const float pgl = __ldg(pg) * __ldg(l_d + 3 * g[i]) + __ldg(pg + 1) * __ldg(l_d + 3 * g[i] + 1) +
+                                      __ldg(pg + 2) * __ldg(l_d + 3 * g[i] + 2);
+                    out.x = T * pgl - t[i];
+                    out.y = T * (1.0f - xx[i]) * pgl;
+                }
+                elem[dst] = out;
+            }
+            kprev = k[i];
+            yprev = y[i];
+        }
     }
 }
 
@@ -277,16 +333,22 @@ k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ 
                    const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
                    float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
                    float *__restrict__ g_l) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t g = warp0; g < n; g += nwarps) {
-        const int64_t b = __ldg(goff + g), eend = __ldg(goff + g + 1);
-        const Gauss G = load_gauss(mean, lam, opac, static_cast<int>(g));
-        const int sx = __ldg(sp + 2 * g), sy = __ldg(sp + 2 * g + 1);
-        const int w = __ldg(ep + 2 * g) - sx + 1;
+    // a box holds ~40 elements on average: 8 lanes per Gaussian, four Gaussians per warp at a time
+    constexpr int GL = 8;
+    const int sub = threadIdx.x & (GL - 1);
+    const int64_t grp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / GL;
+    const int64_t ngrp = (static_cast<int64_t>(gridDim.x) * blockDim.x) / GL;
+    const int64_t iters = (n + ngrp - 1) / ngrp;  // same trip count for every lane: shuffles stay converged
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t g = grp0 + it * ngrp;
+        const bool live = g < n;
+        const int64_t gg = live ? g : 0;
+        const int64_t b = __ldg(goff + gg), eend = live ? __ldg(goff + gg + 1) : b;
+        const Gauss G = load_gauss(mean, lam, opac, static_cast<int>(gg));
+        const int sx = __ldg(sp + 2 * gg), sy = __ldg(sp + 2 * gg + 1);
+        const int w = __ldg(ep + 2 * gg) - sx + 1;
         float a_o = 0.f, a_d = 0.f, a_m0 = 0.f, a_m1 = 0.f, a_00 = 0.f, a_01 = 0.f, a_11 = 0.f;
-        for (int64_t e = b + lane; e < eend; e += 32) {
+        for (int64_t e = b + sub; e < eend; e += GL) {
             const float2 v = __ldg(elem + e);
             const int local = static_cast<int>(e - b);
             const int iy = local / w, ix = local - iy * w;
@@ -304,7 +366,7 @@ k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ 
             a_11 = fmaf(hc * d1, d1, a_11);
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
+        for (int d = GL / 2; d >= 1; d >>= 1) {
             a_o += __shfl_xor_sync(0xffffffffu, a_o, d);
             a_d += __shfl_xor_sync(0xffffffffu, a_d, d);
             a_m0 += __shfl_xor_sync(0xffffffffu, a_m0, d);
@@ -313,7 +375,7 @@ k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ 
             a_01 += __shfl_xor_sync(0xffffffffu, a_01, d);
             a_11 += __shfl_xor_sync(0xffffffffu, a_11, d);
         }
-        if (lane == 0) {
+        if (live && sub == 0) {
             g_opac[g] = a_o;
             g_l[3 * g] = a_d / __ldg(l_d + 3 * g);
             g_l[3 * g + 1] = a_d / __ldg(l_d + 3 * g + 1);
@@ -377,7 +439,7 @@ int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *mea
                     const float *opac, int64_t N, float *x_s, gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
-    k_splat_alpha<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_splat_alpha<<<blocks_for(N, 256 * 4, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         key_s, gid_s, mean, lam, opac, N, x_s);
     return static_cast<int>(cudaGetLastError());
 }
@@ -396,7 +458,7 @@ int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, c
                     gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
-    k_splat_bwd_w<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_splat_bwd_w<<<blocks_for(N, 256 * 4, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         incl, x_s, key_s, gid_s, l_d, grad_image, N, W, gshift);
     return static_cast<int>(cudaGetLastError());
 }
@@ -418,7 +480,7 @@ int gcp_splat_bwd_elem(const float *incl, const float *x_s, const float *tu, con
                        gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
-    k_splat_bwd_elem<<<blocks_for(N, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_splat_bwd_elem<<<blocks_for(N, 256 * 4, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         incl, x_s, tu, key_s, gid_s, sp, ep, goff, l_d, grad_image, N, W, reinterpret_cast<float2 *>(elem));
     return static_cast<int>(cudaGetLastError());
 }
@@ -428,7 +490,7 @@ int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep
                          float *g_mean, float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
     if (n < 0) return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
-    k_splat_bwd_reduce<<<blocks_for(n, 8, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_splat_bwd_reduce<<<blocks_for(n, 32, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2 *>(elem), sp, ep, goff, mean, lam, opac, l_d, n, g_mean, g_lam, g_opac, g_l);
     return static_cast<int>(cudaGetLastError());
 }

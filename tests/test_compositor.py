@@ -132,3 +132,32 @@ def test_native_compositor_matches_oracle_on_a_larger_scene_gpu():
     gm, gL, go, gl = co.backward(cache, gI)
     case.update(image=img, grad_mean=gm, grad_lambda=gL, grad_opacity=go, grad_l=gl)
     _check(_run(case, "cuda"), case, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_native_compositor_edge_cases_gpu():
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    dev = "cuda"
+    W, H = 20, 10
+    # no Gaussians at all: a black image and empty gradients
+    z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+    mean = z(0, 2).requires_grad_(True)
+    img = F.apply(z(0, dt=torch.int64), torch.tensor([0]), z(0, 2, dt=torch.int32), z(0, 2, dt=torch.int32), mean,
+                  z(0, 2, 2), z(0, 1), z(0, 3), W, H)
+    assert img.shape == (H + 1, W + 1, 3) and float(img.abs().sum()) == 0.0
+    # one single-pixel Gaussian with opacity 0.5 sitting exactly on its pixel: image = 0.5 * l there, T = 1
+    sp = torch.tensor([[7, 3]], dtype=torch.int32, device=dev)
+    o = torch.tensor([[0.5]], device=dev, requires_grad=True)
+    l = torch.tensor([[0.2, 0.4, 0.8]], device=dev, requires_grad=True)
+    lam = torch.eye(2, device=dev)[None].clone().requires_grad_(True)
+    m = torch.tensor([[7.0, 3.0]], device=dev, requires_grad=True)
+    img = F.apply(torch.tensor([1], device=dev), torch.tensor([1]), sp, sp.clone(), m, lam, o, l, torch.tensor(W),
+                  torch.tensor(H))
+    assert torch.allclose(img[3, 7], torch.tensor([0.1, 0.2, 0.4], device=dev))
+    assert float(img.sum()) == pytest.approx(0.7)
+    img.sum().backward()
+    assert torch.allclose(o.grad, torch.tensor([[1.4]], device=dev))        # g * <1, l> = 0.2+0.4+0.8
+    # the reference's d/l for the colour gradient (gs_model.py:763-766): d = T alpha <1,l> = 0.7
+    assert torch.allclose(l.grad, torch.tensor([[3.5, 1.75, 0.875]], device=dev))
+    assert float(m.grad.abs().sum()) == 0.0 and float(lam.grad.abs().sum()) == 0.0   # r - m = 0
