@@ -1,0 +1,101 @@
+"""Host-buffer entry point: segmented cumprod forward + backward for arrays that live in HOST memory.
+
+The reference never moves the element arrays over PCIe (they are produced on the device, gs_model.py:598-605),
+but a caller that does hold them on the host gets the best the link allows from this streamer:
+
+  * only x, key and grad_out go up (12 B/element): the sorted pixel keys double as segment ids for the
+    backward op (it only compares neighbours), so `inv` / `inv_len` never cross the bus;
+  * the list is cut into chunks at segment boundaries (pixel lists are independent) and the chunks flow through
+    three CUDA streams — H2D copies, the two scan launches, D2H copies — with `depth` buffer sets, so the
+    uploads, the kernels and the downloads of neighbouring chunks overlap and PCIe runs full duplex.
+
+All host tensors must be pinned for the copies to be asynchronous.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _cut_points(key: torch.Tensor, chunk: int) -> list:
+    """Chunk boundaries near multiples of `chunk`, moved forward to the next segment boundary."""
+    n = key.numel()
+    cuts = [0]
+    k = key.numpy()
+    pos = chunk
+    while pos < n:
+        # first index >= pos where a new segment starts
+        window = 1 << 16
+        j = pos
+        while j < n:
+            w = k[j - 1:min(n, j + window)]
+            d = np.flatnonzero(w[1:] != w[:-1])
+            if d.size:
+                j = j + int(d[0])
+                break
+            j += window
+        if j >= n:
+            break
+        cuts.append(j)
+        pos = j + chunk
+    cuts.append(n)
+    return cuts
+
+
+class HostStreamer:
+    """Reusable pipeline for one device; buffers are allocated once for `max_chunk` elements."""
+
+    def __init__(self, device="cuda", chunk_elems: int = 8 << 20, depth: int = 3):
+        self.device = torch.device(device)
+        self.chunk = int(chunk_elems)
+        self.depth = depth
+        cap = self.chunk + (1 << 20)  # a chunk ends at the first segment boundary after `chunk`
+        self.cap = cap
+        mk = lambda dt: [torch.empty(cap, dtype=dt, device=self.device) for _ in range(depth)]  # noqa: E731
+        self.dx, self.dg, self.dy, self.dgin = mk(torch.float32), mk(torch.float32), mk(torch.float32), mk(torch.float32)
+        self.dk = mk(torch.int32)
+        self.s_up = torch.cuda.Stream(self.device)
+        self.s_run = torch.cuda.Stream(self.device)
+        self.s_down = torch.cuda.Stream(self.device)
+        self.empty_len = torch.empty(0, dtype=torch.int32, device=self.device)
+
+    def fwd_bwd(self, x, key, grad_out, y_out, grad_in_out, cuts=None):
+        """y_out = segmented inclusive cumprod(x by key); grad_in_out = its gradient for upstream grad_out.
+        All five are 1-D pinned host tensors (f32, i32, f32, f32, f32).  Returns (h2d_bytes, d2h_bytes)."""
+        n = x.numel()
+        if cuts is None:
+            cuts = _cut_points(key, self.chunk)
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_up, self.s_run, self.s_down):
+            s.wait_stream(cur)
+        up_done = [None] * self.depth
+        run_done = [None] * self.depth
+        down_done = [None] * self.depth
+        for c in range(len(cuts) - 1):
+            a, b = cuts[c], cuts[c + 1]
+            m = b - a
+            if m > self.cap:
+                raise RuntimeError(f"segment longer than the streaming buffers ({m} > {self.cap} elements)")
+            i = c % self.depth
+            with torch.cuda.stream(self.s_up):
+                if down_done[i] is not None:
+                    self.s_up.wait_event(down_done[i])      # buffer set i is free again
+                self.dx[i][:m].copy_(x[a:b], non_blocking=True)
+                self.dk[i][:m].copy_(key[a:b], non_blocking=True)
+                self.dg[i][:m].copy_(grad_out[a:b], non_blocking=True)
+                up_done[i] = self.s_up.record_event()
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(up_done[i])
+                xs, ks, gs, ys, gi = self.dx[i][:m], self.dk[i][:m], self.dg[i][:m], self.dy[i][:m], self.dgin[i][:m]
+                ops.grouped_cumprod_forward(xs, ks, ys)
+                ops.grouped_cumprod_backward(xs, ys, gs, ks, gi, self.empty_len)
+                run_done[i] = self.s_run.record_event()
+            with torch.cuda.stream(self.s_down):
+                self.s_down.wait_event(run_done[i])
+                y_out[a:b].copy_(self.dy[i][:m], non_blocking=True)
+                grad_in_out[a:b].copy_(self.dgin[i][:m], non_blocking=True)
+                down_done[i] = self.s_down.record_event()
+        cur.wait_stream(self.s_down)
+        return 12 * n, 8 * n

@@ -355,3 +355,31 @@ def test_autograd_function_matches_torch_autograd():
     (yr * w.double().cpu()).sum().backward()
     assert_close(y.detach().cpu().numpy(), yr.detach().numpy(), "autograd fwd")
     assert_close(x.grad.cpu().numpy(), xr.grad.numpy(), "autograd bwd")
+
+
+def test_host_streamer_matches_resident_ops(oracle):
+    """Host-buffer entry point: chunks cut at segment boundaries, three streams, keys doubling as segment ids."""
+    from simplegaussiansplat_tk71_b200.host import HostStreamer, _cut_points
+
+    rng = np.random.default_rng(31)
+    n = 900_000
+    L = np.maximum(1, np.rint(rng.lognormal(np.log(20), 1.0, n // 8))).astype(np.int64)
+    L[1000] = 70_000                                        # one list longer than a chunk
+    L = L[: np.searchsorted(np.cumsum(L), n) + 1]
+    L[-1] -= L.sum() - n
+    inv, _ = seg_arrays(L)
+    key = (inv.astype(np.int64) * 3 + 7).astype(np.int32)
+    x = _values(n, rng)
+    g = rng.uniform(0, 1, n).astype(np.float32)
+    hx, hk, hg = (torch.from_numpy(a).pin_memory() for a in (x, key, g))
+    hy = torch.empty(n).pin_memory()
+    hgin = torch.empty(n).pin_memory()
+    st = HostStreamer("cuda", chunk_elems=100_000, depth=3)
+    cuts = _cut_points(hk, 100_000)
+    assert cuts[0] == 0 and cuts[-1] == n and len(cuts) > 5
+    assert all(key[c] != key[c - 1] for c in cuts[1:-1])    # every cut is a segment boundary
+    up, down = st.fwd_bwd(hx, hk, hg, hy, hgin)
+    torch.cuda.synchronize()
+    assert (up, down) == (12 * n, 8 * n)
+    assert_close(hy.numpy(), oracle.cumprod_fwd(x, key), "streamer fwd")
+    assert_close(hgin.numpy(), oracle.cumprod_bwd_exact(x, g, inv), "streamer bwd")
