@@ -40,3 +40,59 @@ def allreduce_param_grads(bucket: torch.Tensor) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
     return bucket
+
+
+# --------------------------------------------------------------------------------------------
+# Per-view preparation of the compositor inputs (row a10 of SURVEY.md §8): the body of the reference's
+# per-view loop, gs_model.py:402-449, as functions.  Plain torch device ops (K-sized, not element-sized).
+# --------------------------------------------------------------------------------------------
+def visible_boxes(mean_pixel, box_half, z, width: int, height: int):
+    """Cull and clamp the depth-sorted Gaussians of ONE view.
+
+    mean_pixel i32[n,2], box_half i32/f32[n,2] (3-sigma half widths), z f32[n] camera depth, all already in
+    z order (gs_model.py:356-365).  Returns (mask bool[n], startpoint i32[m,2], endpoint i32[m,2], boxsize i64[m]):
+      mask       z > 0, box != 0, box intersects the image                      (gs_model.py:405-406)
+      corners    mean -/+ half, clamped to the INCLUSIVE range [0,W] x [0,H]     (:419-423)
+      boxsize    prod(end - start + 1)                                          (:424)
+    """
+    mx, my = mean_pixel[:, 0], mean_pixel[:, 1]
+    bx, by = box_half[:, 0], box_half[:, 1]
+    mask = (z > 0) & (bx != 0) & (mx - bx < width) & (mx + bx > 0) & (my - by < height) & (my + by > 0)
+    mx, my, bx, by = mx[mask], my[mask], bx[mask], by[mask]
+    sp = torch.stack(((mx - bx).clamp(min=0, max=width), (my - by).clamp(min=0, max=height)), 1)
+    ep = torch.stack(((mx + bx).clamp(min=0, max=width), (my + by).clamp(min=0, max=height)), 1)
+    boxsize = torch.prod((ep - sp + 1).to(torch.int64), dim=1)
+    return mask, sp.to(torch.int32), ep.to(torch.int32), boxsize
+
+
+def split_by_cumsum_parallel(x: torch.Tensor, limit: float) -> torch.Tensor:
+    """Number of items per chunk when a new chunk starts each time the running sum passes a multiple of `limit`
+    (uitility.py:478-488): counts of floor(cumsum(x) / limit)."""
+    group_id = torch.floor_divide(torch.cumsum(x, dim=0), limit)
+    _, counts = torch.unique(group_id, return_counts=True)
+    return counts
+
+
+def chunk_ends(boxsize: torch.Tensor) -> torch.Tensor:
+    """The `batch` argument of the compositor as the reference builds it (gs_model.py:428): chunks of at most
+    2**29 elements.  The native compositor renders a view in one pass and ignores it; it is produced only so that
+    callers written against the reference keep working."""
+    return torch.cumsum(split_by_cumsum_parallel(boxsize / 1024, (1024 ** 3 * 6 / 12) / 1024), dim=0)
+
+
+def render_views(mean_pixel, box_half, z, lam, opacity, l_d, width: int, height: int):
+    """The per-view loop of gs_model.py:402-454 over V views whose Gaussians are already z-sorted:
+    inputs [V,n,...]; returns images [V',3,H,W] (views without any visible Gaussian are skipped, :414-417) —
+    including the reference's final `[:,1:,1:,:].reshape(-1,3,H,W)` (a reshape, not a permute, :454)."""
+    from .compositor import custom_autograd_grouped_cumprod as F
+
+    out = []
+    for v in range(mean_pixel.shape[0]):
+        mask, sp, ep, boxsize = visible_boxes(mean_pixel[v], box_half[v], z[v], width, height)
+        if sp.shape[0] == 0:
+            continue
+        out.append(F.apply(boxsize, chunk_ends(boxsize), sp, ep, mean_pixel[v][mask], lam[v][mask], opacity[v][mask],
+                           l_d[v][mask], width, height))
+    if not out:
+        return torch.zeros((0, 3, height, width), device=mean_pixel.device)
+    return torch.stack(out, dim=0)[:, 1:, 1:, :].reshape(-1, 3, height, width)
