@@ -153,14 +153,14 @@ int launch_fwd_tma(const float *x, const int32_t *key, float *y, int64_t n, Ws w
     return static_cast<int>(cudaGetLastError());
 }
 
-template <int OP, int WARPS, int STAGES>
+template <int OP, int WARPS, int STAGES, bool DIRECT_ST = false>
 int launch_fwd_blk(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
     using L = FwdBlkSmem<WARPS, STAGES>;
     CUtensorMap tmx, tmk;
     if (!make_tile_map(&tmx, x, n, L::TILE, false) || !make_tile_map(&tmk, key, n, L::TILE, true))
         return launch_fwd_ldg<OP, 8, 4>(x, key, y, n, ws, s);  // tiny n, or no driver entry point
     const uint32_t nt = tiles_for(n, L::TILE);
-    constexpr auto kern = k_fwd_blk<OP, WARPS, STAGES>;
+    constexpr auto kern = k_fwd_blk<OP, WARPS, STAGES, DIRECT_ST>;
     const int threads = (WARPS + 1) * 32;
     const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
@@ -171,13 +171,14 @@ int launch_fwd_blk(const float *x, const int32_t *key, float *y, int64_t n, Ws w
     return static_cast<int>(cudaGetLastError());
 }
 
-constexpr int FWD_NUM_VARIANTS = 11;
+constexpr int FWD_NUM_VARIANTS = 13;
 const char *const kFwdNames[FWD_NUM_VARIANTS] = {
     "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
     "tma_w8_r4_s3 (tile 4096, 96 KB ring)", "tma_w8_r4_s2 (tile 4096, 64 KB ring)",
     "tma_w8_r2_s4 (tile 2048, 64 KB ring)", "tma_w4_r4_s4 (tile 2048, 160 thr)",
     "tma_w16_r4_s3 (tile 8192, 192 KB ring)", "blk_w8_s2 (16 contiguous elems/lane, swizzled tensor TMA)",
-    "blk_w8_s3 (tile 4096, 96 KB ring)", "blk_w4_s4 (tile 2048, 64 KB ring)"};
+    "blk_w8_s3 (tile 4096, 96 KB ring)", "blk_w4_s4 (tile 2048, 64 KB ring)",
+    "blk_w8_s2_direct (stores straight from registers, stage freed early)", "blk_w8_s3_direct"};
 constexpr int FWD_DEFAULT = 8;   // blk_w8_s2
 
 template <int OP>
@@ -205,6 +206,8 @@ int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *
         case 8: return launch_fwd_blk<OP, 8, 2>(x, key, y, n, ws, s);
         case 9: return launch_fwd_blk<OP, 8, 3>(x, key, y, n, ws, s);
         case 10: return launch_fwd_blk<OP, 4, 4>(x, key, y, n, ws, s);
+        case 11: return launch_fwd_blk<OP, 8, 2, true>(x, key, y, n, ws, s);
+        case 12: return launch_fwd_blk<OP, 8, 3, true>(x, key, y, n, ws, s);
         default: return GCP_ERR_INVALID_ARG;
     }
 }
@@ -246,7 +249,7 @@ int launch_bwd_tma(const float *x, const float *y, const float *g, const int32_t
     return static_cast<int>(cudaGetLastError());
 }
 
-template <int WARPS, int STAGES, int MINB>
+template <int WARPS, int STAGES, int MINB, bool DIRECT_ST = false>
 int launch_bwd_blk(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
                    Ws ws, cudaStream_t s) {
     using L = BwdBlkSmem<WARPS, STAGES>;
@@ -255,7 +258,7 @@ int launch_bwd_blk(const float *x, const float *y, const float *g, const int32_t
         !make_tile_map(&tmi, inv, n, L::TILE, true))
         return launch_bwd_ldg<8, 4>(x, y, g, inv, gin, n, ws, s);
     const uint32_t nt = tiles_for(n, L::TILE);
-    constexpr auto kern = k_bwd_blk<WARPS, STAGES, MINB>;
+    constexpr auto kern = k_bwd_blk<WARPS, STAGES, MINB, DIRECT_ST>;
     const int threads = (WARPS + 1) * 32;
     const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
@@ -266,14 +269,15 @@ int launch_bwd_blk(const float *x, const float *y, const float *g, const int32_t
     return static_cast<int>(cudaGetLastError());
 }
 
-constexpr int BWD_NUM_VARIANTS = 12;
+constexpr int BWD_NUM_VARIANTS = 14;
 const char *const kBwdNames[BWD_NUM_VARIANTS] = {
     "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
     "tma_w8_r4_s2 (tile 4096, 96 KB ring, 2 CTA/SM)", "tma_w8_r2_s4 (tile 2048, 96 KB ring, 2 CTA/SM)",
     "tma_w8_r2_s3 (tile 2048, 72 KB ring, 3 CTA/SM)", "tma_w8_r4_s4 (tile 4096, 192 KB ring, 1 CTA/SM)",
     "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)", "blk_w8_s2 (16 contiguous elems/lane, 2 CTA/SM)",
     "blk_w8_s4 (tile 4096, 192 KB ring, 1 CTA/SM)", "blk_w4_s3 (tile 2048, 72 KB ring, 3 CTA/SM)",
-    "blk_w4_s4 (tile 2048, 96 KB ring, 2 CTA/SM)"};
+    "blk_w4_s4 (tile 2048, 96 KB ring, 2 CTA/SM)", "blk_w8_s2_direct (stores straight from registers)",
+    "blk_w4_s3_direct (tile 2048, 3 CTA/SM)"};
 constexpr int BWD_DEFAULT = 8;   // blk_w8_s2
 
 }  // namespace
@@ -346,6 +350,8 @@ int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const
         case 9: return launch_bwd_blk<8, 4, 1>(x, y, gout, inv, gin, n, ws, s);
         case 10: return launch_bwd_blk<4, 3, 3>(x, y, gout, inv, gin, n, ws, s);
         case 11: return launch_bwd_blk<4, 4, 2>(x, y, gout, inv, gin, n, ws, s);
+        case 12: return launch_bwd_blk<8, 2, 2, true>(x, y, gout, inv, gin, n, ws, s);
+        case 13: return launch_bwd_blk<4, 3, 3, true>(x, y, gout, inv, gin, n, ws, s);
         default: return GCP_ERR_INVALID_ARG;
     }
 }

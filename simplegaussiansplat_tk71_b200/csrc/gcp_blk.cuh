@@ -76,6 +76,13 @@ __device__ __forceinline__ void store_blocked_via_smem(unsigned char *arr, int w
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// registers (blocked) -> global directly: four 128-bit streaming stores per lane, 64 contiguous bytes per lane
+__device__ __forceinline__ void store_blocked_direct(const float (&o)[16], float *__restrict__ dst_lane) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        __stcs(reinterpret_cast<float4 *>(dst_lane) + j, make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+}
+
 // guarded global load of a lane's 16 consecutive elements (partial last tile)
 template <typename T>
 __device__ __forceinline__ void ldg_blocked(const T *__restrict__ p, int64_t gi, int64_t n, T pad, T (&out)[16]) {
@@ -213,7 +220,7 @@ struct FwdBlkSmem {
     static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl)) + 1024;  // + alignment slack
 };
 
-template <int OP, int WARPS, int STAGES>
+template <int OP, int WARPS, int STAGES, bool DIRECT_ST = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32)
 k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_k,
           const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
@@ -354,16 +361,25 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             ldg_blocked<int32_t>(key, wbase + lane * BLK_EPL, n, 0, k);
             if (lane == 0 && wbase > 0 && wbase - 1 < n) kprev = __ldg(key + wbase - 1);
         }
+        if (DIRECT_ST) {  // the stage is free as soon as its values are in registers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
+        }
         fwd_blk_compute<OP, WARPS>(v, k, kprev, wbase == 0, resolved, tp_res, tile, epoch, hdr, desc, ulist,
                                    &ctl->sh[it & 1u], warp, lane);
-        if (staged && y_vec) {
-            // the x array of the stage is dead (every warp has read its own span only): reuse it
-            store_blocked_via_smem(xs, warp, lane, v, y + wbase);
+        if (DIRECT_ST) {
+            if (staged && y_vec) store_blocked_direct(v, y + wbase + lane * BLK_EPL);
+            else stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v);
         } else {
-            stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v);
+            if (staged && y_vec) {
+                // the x array of the stage is dead (every warp has read its own span only): reuse it
+                store_blocked_via_smem(xs, warp, lane, v, y + wbase);
+            } else {
+                stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->empty[s]);
     }
 
     // ===================== fix-up phase (same launch) =====================
@@ -557,7 +573,7 @@ struct BwdBlkSmem {
     static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl)) + 1024;
 };
 
-template <int WARPS, int STAGES, int MINB>
+template <int WARPS, int STAGES, int MINB, bool DIRECT_ST = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
           const __grid_constant__ CUtensorMap tm_i, const float *__restrict__ x, const float *__restrict__ y,
@@ -709,18 +725,27 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                 xnext = __ldg(x + wend);
             }
         }
+        if (DIRECT_ST) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
+        }
         float out[16];
         bwd_blk_compute<WARPS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc,
                                      ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out);
-        if (staged && out_vec) {
-            // the g array of the stage is only ever read by the warp that owns the span: reuse it
-            // (x is read across warp boundaries for x_next, inv for the head/tail halos)
-            store_blocked_via_smem(gs, warp, lane, out, gin + wbase);
+        if (DIRECT_ST) {
+            if (staged && out_vec) store_blocked_direct(out, gin + wbase + lane * BLK_EPL);
+            else stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
         } else {
-            stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+            if (staged && out_vec) {
+                // the g array of the stage is only ever read by the warp that owns the span: reuse it
+                // (x is read across warp boundaries for x_next, inv for the head/tail halos)
+                store_blocked_via_smem(gs, warp, lane, out, gin + wbase);
+            } else {
+                stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->empty[s]);
     }
 
     // ===================== fix-up phase (same launch) =====================

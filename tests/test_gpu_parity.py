@@ -31,8 +31,8 @@ def carry_mode(request):
     ops.set_option(0, 1)
 
 
-FWD_VARIANTS = list(range(11))
-BWD_VARIANTS = list(range(12))
+FWD_VARIANTS = list(range(13))
+BWD_VARIANTS = list(range(14))
 
 
 def _pow2_values(n, rng, span=12):

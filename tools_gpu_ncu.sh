@@ -7,6 +7,5 @@ run() { # name op variant halo
       python tools/prof_one.py --op $2 --variant $3 --halo $4 > gpurun_out/ncu_$1.log 2>&1
   echo "$1 rc=$?"; cat gpurun_out/plain_$1.log
 }
-run fwd_blk fwd 8 1
-run bwd_blk bwd 10 1
-run bwd_blk8 bwd 8 1
+run fwd_final fwd -1 1
+run bwd_final bwd -1 1
