@@ -141,6 +141,20 @@ size_t gcp_splat_sort_bytes(int64_t N);
 int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_out, int32_t *gid_out, int64_t N,
                    int max_key, void *temp, size_t temp_bytes, gcp_stream_t stream);
 
+/* Sort-free construction of the SAME sorted (key_s, gid_s) list (preferred over expand + sort): a counting
+ * placement that exploits that the Gaussians arrive in depth order — per image row, the intervals [sx,ex] of
+ * the boxes crossing the row are walked in Gaussian order and every element lands at
+ * offset[pixel] + (number of earlier Gaussians on that pixel), i.e. exactly its stable-sort position.
+ * poff i64[n+1] = exclusive offsets of (box height) x (number of strips the box touches) =
+ * (ey-sy+1) * ((ex>>S) - (sx>>S) + 1) with S = gcp_splat_seg_shift(), P = poff[n].  seg_off i32[(H+1)*(W+1)+1]
+ * receives the offset of every pixel list (pixels in key order; last entry = N).  Bit-identical output. */
+size_t gcp_splat_place_bytes(int64_t P, int W, int H);
+int gcp_splat_set_fill_blocks(int blocks); /* tuning hook: persistent grid of the fill kernel, 0 = default */
+int gcp_splat_seg_shift(void);             /* log2 of the strip width the library was built with */
+int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, int64_t n, int64_t P, int W, int H,
+                    int32_t *key_s, int32_t *gid_s, int32_t *seg_off, void *temp, size_t temp_bytes,
+                    gcp_stream_t stream);
+
 /* x_s[e] = 1 - opacity * exp(-1/2 (r-m) Lambda (r-m)^T)  (gs_model.py:493-495, :533-535), sorted order. */
 int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *mean, const float *lam,
                     const float *opac, int64_t N, float *x_s, gcp_stream_t stream);

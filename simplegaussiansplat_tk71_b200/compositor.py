@@ -14,8 +14,9 @@ fits one chunk (sum(boxsize) <= 2**29, gs_model.py:428):
 
 but not how.  One view = ten kernel launches, all through the C ABI (include/gcp_abi.h):
 
-    forward   gcp_splat_expand   boxes -> (pixel key, Gaussian id) per element          (:480-482, :538-541)
-              gcp_splat_sort     stable radix sort by key, significant bits only        (:547-548)
+    forward   gcp_splat_place    boxes -> the pixel-sorted (key, Gaussian id) element list, built directly by a
+                                 counting placement per image row — no sort of the N elements
+                                 (alternative kept: gcp_splat_expand + gcp_splat_sort)  (:480-482, :538-548)
               gcp_splat_alpha    x = 1 - opacity*g in sorted order                      (:493-495, :533-535)
               gcp_cumprod_fwd    the segmented scan (op a1)                             (:551)
               gcp_splat_color    exclusive T from the inclusive scan (no division) and
@@ -43,6 +44,9 @@ import torch
 from . import _lib, ops
 
 KEY_STRIDE = 10000  # pixel key = y*10000 + x  (gs_model.py:541)
+# True: build the sorted element list with the sort-free counting placement (gcp_splat_place);
+# False: expand to N (key, gid) pairs and radix-sort them (gcp_splat_expand + gcp_splat_sort).  Same output, bit for bit.
+USE_PLACEMENT = True
 
 
 def _p(t):
@@ -68,7 +72,15 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
         stream = torch.cuda.current_stream(dev).cuda_stream
         goff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         torch.cumsum(boxsize.to(torch.int64), 0, out=goff[1:])
-        N = int(goff[-1].item())           # one host sync per view, like the reference's .item() at uitility.py:348
+        # placement cells: one image row x 2^S pixels; a box contributes (rows) x (strips it touches) pairs
+        poff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        if n > 0:
+            S = int(L.gcp_splat_seg_shift())
+            rows = (endpoint[:, 1] - startpoint[:, 1] + 1).to(torch.int64)
+            strips = ((endpoint[:, 0] >> S) - (startpoint[:, 0] >> S) + 1).to(torch.int64)
+            torch.cumsum(rows * strips, 0, out=poff[1:])
+        # one host sync per view, like the reference's .item() at uitility.py:348
+        N, P = (int(t) for t in torch.stack((goff[-1], poff[-1])).tolist())
         v.N = N
         v.mean = mean.detach().to(torch.float32).contiguous()
         v.lam = lam.detach().to(torch.float32).reshape(n, 4).contiguous()
@@ -84,15 +96,23 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
         if N >= 2 ** 31:
             raise RuntimeError("a view is limited to 2**31-1 elements (the reference ops index with int32)")
         sp, ep = v.sp, v.ep
-        key = torch.empty(N, dtype=torch.int32, device=dev)
-        gid = torch.empty(N, dtype=torch.int32, device=dev)
-        _lib.check(L.gcp_splat_expand(_p(sp), _p(ep), _p(goff), n, N, _p(key), _p(gid), stream), "gcp_splat_expand")
-        v.key_s = torch.empty_like(key)
-        v.gid_s = torch.empty_like(gid)
-        temp = torch.empty(int(L.gcp_splat_sort_bytes(N)), dtype=torch.uint8, device=dev)
-        _lib.check(L.gcp_splat_sort(_p(key), _p(gid), _p(v.key_s), _p(v.gid_s), N, H * KEY_STRIDE + W, _p(temp),
-                                    temp.numel(), stream), "gcp_splat_sort")
-        del key, gid, temp
+        v.key_s = torch.empty(N, dtype=torch.int32, device=dev)
+        v.gid_s = torch.empty(N, dtype=torch.int32, device=dev)
+        if USE_PLACEMENT:
+            seg_off = torch.empty((H + 1) * (W + 1) + 1, dtype=torch.int32, device=dev)
+            temp = torch.empty(int(L.gcp_splat_place_bytes(P, W, H)), dtype=torch.uint8, device=dev)
+            _lib.check(L.gcp_splat_place(_p(sp), _p(ep), _p(poff), n, P, W, H, _p(v.key_s), _p(v.gid_s), _p(seg_off),
+                                         _p(temp), temp.numel(), stream), "gcp_splat_place")
+            del temp, seg_off
+        else:
+            key = torch.empty(N, dtype=torch.int32, device=dev)
+            gid = torch.empty(N, dtype=torch.int32, device=dev)
+            _lib.check(L.gcp_splat_expand(_p(sp), _p(ep), _p(goff), n, N, _p(key), _p(gid), stream),
+                       "gcp_splat_expand")
+            temp = torch.empty(int(L.gcp_splat_sort_bytes(N)), dtype=torch.uint8, device=dev)
+            _lib.check(L.gcp_splat_sort(_p(key), _p(gid), _p(v.key_s), _p(v.gid_s), N, H * KEY_STRIDE + W, _p(temp),
+                                        temp.numel(), stream), "gcp_splat_sort")
+            del key, gid, temp
         v.x_s = torch.empty(N, dtype=torch.float32, device=dev)
         _lib.check(L.gcp_splat_alpha(_p(v.key_s), _p(v.gid_s), _p(v.mean), _p(v.lam), _p(v.opac), N, _p(v.x_s),
                                      stream), "gcp_splat_alpha")

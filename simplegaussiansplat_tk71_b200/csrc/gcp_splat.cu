@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "gcp_abi.h"
 
@@ -390,6 +391,161 @@ k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ 
     }
 }
 
+// =====================================================================================================
+// Sort-free placement: the sorted element list is built directly, without sorting
+// the N elements.  A stable sort by pixel key is a counting sort whose rank of element (Gaussian j, pixel p)
+// is the number of Gaussians i < j that cover p — and the input already arrives in depth (= index) order.
+// The image is cut into cells of one row x 64 pixels (GCP_SEG_SHIFT).
+//   1. k_place_pairs : one (cell, Gaussian) pair per box row and strip the box touches, P ~ N/6 pairs; the
+//                      pairs are sorted by cell (a small stable radix sort on <= 16 bits, Gaussian order kept).
+//   2. k_place_count : one warp per cell adds +1/-1 at the ends of every (clipped) interval [sx,ex] of the
+//                      cell into a shared-memory difference array and prefix-sums it: per-pixel list lengths.
+//   3. exclusive scan of the lengths over the pixels in key order: segment offsets.
+//   4. k_place_fill  : one warp per cell walks the cell's intervals in Gaussian order; lanes cover the pixels
+//                      of the interval, each pixel keeps a running counter in shared memory, and the element
+//                      is written at offset[pixel] + counter: exactly the stable-sort position.
+// Output is bit-identical to expand + stable sort (checked in tests/test_compositor.py).
+// =====================================================================================================
+#ifndef GCP_SEG_SHIFT
+#define GCP_SEG_SHIFT 6
+#endif
+constexpr int SEG_SHIFT = GCP_SEG_SHIFT;  // image rows are cut into strips of 2^SEG_SHIFT pixels:
+constexpr int SEGW = 1 << SEG_SHIFT;      // one warp owns one (row, strip) cell at a time
+
+// pair key of cell (row y, strip s) = y * nseg + s
+__global__ void __launch_bounds__(256)
+k_place_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ poff,
+              int64_t n, int64_t P, int nseg, int32_t *__restrict__ pcell, int32_t *__restrict__ pgid) {
+    const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CH;
+    if (p0 >= P) return;
+    int64_t g = find_gaussian(poff, n, p0);
+    int64_t gbeg = __ldg(poff + g), gend = __ldg(poff + g + 1);
+    int sy = __ldg(sp + 2 * g + 1);
+    int s0 = __ldg(sp + 2 * g) >> SEG_SHIFT;
+    int ns = (__ldg(ep + 2 * g) >> SEG_SHIFT) - s0 + 1;
+    for (int i = 0; i < CH && p0 + i < P; ++i) {
+        const int64_t p = p0 + i;
+        while (p >= gend) {
+            ++g;
+            gbeg = gend;
+            gend = __ldg(poff + g + 1);
+            sy = __ldg(sp + 2 * g + 1);
+            s0 = __ldg(sp + 2 * g) >> SEG_SHIFT;
+            ns = (__ldg(ep + 2 * g) >> SEG_SHIFT) - s0 + 1;
+        }
+        const int local = static_cast<int>(p - gbeg);   // row-major over (box row, strip)
+        const int r = local / ns;
+        pcell[p] = (sy + r) * nseg + s0 + (local - r * ns);
+        pgid[p] = static_cast<int32_t>(g);
+    }
+}
+
+// [lo, hi) of one cell inside the cell-sorted pair list
+__device__ __forceinline__ void cell_range(const int32_t *__restrict__ pcell_s, int64_t P, int cell, int64_t &lo,
+                                           int64_t &hi) {
+    int64_t a = 0, b = P;
+    while (a < b) {
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(pcell_s + m) < cell) a = m + 1;
+        else b = m;
+    }
+    lo = a;
+    b = P;
+    while (a < b) {
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(pcell_s + m) <= cell) a = m + 1;
+        else b = m;
+    }
+    hi = a;
+}
+
+// one warp per (row, strip) cell: per-pixel list lengths from a shared-memory difference array
+__global__ void __launch_bounds__(256)
+k_place_count(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pgid_s,
+              const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t P, int W, int H, int nseg,
+              int32_t *__restrict__ cnt) {
+    __shared__ int32_t sm[8][SEGW + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int cell = blockIdx.x * 8 + wib;
+    if (cell >= (H + 1) * nseg) return;
+    const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
+    const int x1 = min(W, x0 + SEGW - 1);
+    int32_t *c = sm[wib];
+    for (int i = lane; i <= SEGW; i += 32) c[i] = 0;
+    __syncwarp();
+    int64_t lo, hi;
+    cell_range(pcell_s, P, cell, lo, hi);
+    for (int64_t p = lo + lane; p < hi; p += 32) {
+        const int g = __ldg(pgid_s + p);
+        atomicAdd(c + (max(__ldg(sp + 2 * g), x0) - x0), 1);
+        atomicAdd(c + (min(__ldg(ep + 2 * g), x1) - x0 + 1), -1);
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int i0 = 0; i0 < SEGW; i0 += 32) {
+        const int i = i0 + lane;
+        int v = c[i];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += t;
+        }
+        v += carry;
+        if (x0 + i <= x1) cnt[static_cast<int64_t>(y) * (W + 1) + x0 + i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+
+// one warp per (row, strip) cell at a time: walk the cell's intervals in Gaussian (depth) order.
+// The grid is persistent and small on purpose (see gcp_splat_place): cells are taken in index order, so the
+// lists being filled at any moment form one compact address window that stays in L2 until every 32-byte
+// sector is complete — the 4-byte scattered stores then cost no DRAM read-modify-write.
+__global__ void __launch_bounds__(256)
+k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pgid_s,
+             const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int32_t *__restrict__ off,
+             int64_t P, int W, int H, int nseg, int32_t *__restrict__ key_s, int32_t *__restrict__ gid_s) {
+    __shared__ int32_t sm[8][2 * SEGW];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ncell = (H + 1) * nseg;
+    int32_t *c = sm[wib];      // running counter per pixel of the strip
+    int32_t *o = c + SEGW;     // list offset per pixel
+    for (int cell = blockIdx.x * 8 + wib; cell < ncell; cell += gridDim.x * 8) {
+        const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
+        const int x1 = min(W, x0 + SEGW - 1);
+        for (int i = lane; i < SEGW; i += 32) {
+            c[i] = 0;
+            o[i] = (x0 + i <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x0 + i) : 0;
+        }
+        __syncwarp();
+        int64_t lo, hi;
+        cell_range(pcell_s, P, cell, lo, hi);
+        const int kbase = y * KEY_STRIDE + x0;
+        for (int64_t b = lo; b < hi; b += 32) {
+            int g = 0, a = 0, z = -1;
+            if (b + lane < hi) {
+                g = __ldg(pgid_s + b + lane);
+                a = max(__ldg(sp + 2 * g), x0) - x0;
+                z = min(__ldg(ep + 2 * g), x1) - x0;
+            }
+            const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
+            for (int k = 0; k < m; ++k) {
+                const int gg = __shfl_sync(0xffffffffu, g, k);
+                const int ia = __shfl_sync(0xffffffffu, a, k);
+                const int iz = __shfl_sync(0xffffffffu, z, k);
+                for (int i = ia + lane; i <= iz; i += 32) {
+                    const int r = c[i];
+                    c[i] = r + 1;
+                    const int dst = o[i] + r;
+                    gid_s[dst] = gg;
+                    key_s[dst] = kbase + i;
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+}
+
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -492,6 +648,81 @@ int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep
     if (n == 0) return GCP_OK;
     k_splat_bwd_reduce<<<blocks_for(n, 32, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2 *>(elem), sp, ep, goff, mean, lam, opac, l_d, n, g_mean, g_lam, g_opac, g_l);
+    return static_cast<int>(cudaGetLastError());
+}
+
+// ---- sort-free placement -------------------------------------------------------------------------
+namespace {
+int g_fill_blocks = 0;  // tuning: size of the persistent k_place_fill grid (0 = default)
+struct PlaceLayout {
+    size_t prow, pgid, prow_s, pgid_s, cnt, cub, total;
+    size_t cub_bytes;
+};
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+PlaceLayout place_layout(int64_t P, int W, int H) {
+    PlaceLayout L;
+    const size_t pb = align256(static_cast<size_t>(P > 0 ? P : 1) * 4);
+    const size_t npix = static_cast<size_t>(H + 1) * (W + 1) + 1;
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                    static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                    P > 0 ? P : 1, 0, 24);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                  static_cast<int64_t>(npix));
+    L.cub_bytes = align256(a > b ? a : b);
+    L.prow = 0;
+    L.pgid = L.prow + pb;
+    L.prow_s = L.pgid + pb;
+    L.pgid_s = L.prow_s + pb;
+    L.cnt = L.pgid_s + pb;
+    L.cub = L.cnt + align256(npix * 4);
+    L.total = L.cub + L.cub_bytes;
+    return L;
+}
+}  // namespace
+
+size_t gcp_splat_place_bytes(int64_t P, int W, int H) { return place_layout(P, W, H).total; }
+
+int gcp_splat_seg_shift(void) { return SEG_SHIFT; }
+
+int gcp_splat_set_fill_blocks(int blocks) {
+    g_fill_blocks = blocks;
+    return GCP_OK;
+}
+
+int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, int64_t n, int64_t P, int W, int H,
+                    int32_t *key_s, int32_t *gid_s, int32_t *seg_off, void *temp, size_t temp_bytes,
+                    gcp_stream_t stream) {
+    if (n < 0 || P < 0 || W < 0 || H < 0 || W >= KEY_STRIDE) return GCP_ERR_INVALID_ARG;
+    if (!seg_off || !temp) return GCP_ERR_INVALID_ARG;
+    const PlaceLayout L = place_layout(P, W, H);
+    if (temp_bytes < L.total) return GCP_ERR_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *t = static_cast<unsigned char *>(temp);
+    int32_t *prow = reinterpret_cast<int32_t *>(t + L.prow), *pgid = reinterpret_cast<int32_t *>(t + L.pgid);
+    int32_t *prow_s = reinterpret_cast<int32_t *>(t + L.prow_s), *pgid_s = reinterpret_cast<int32_t *>(t + L.pgid_s);
+    int32_t *cnt = reinterpret_cast<int32_t *>(t + L.cnt);
+    const int64_t npix = static_cast<int64_t>(H + 1) * (W + 1) + 1;
+    cudaError_t e;
+    const int nseg = (W + SEGW) >> SEG_SHIFT;  // ceil((W+1)/SEGW) strips per row
+    const int cells = (H + 1) * nseg;
+    if (P > 0) {
+        k_place_pairs<<<blocks_for(P, 256 * CH), 256, 0, s>>>(sp, ep, poff, n, P, nseg, prow, pgid);
+        size_t cb = L.cub_bytes;
+        e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, prow, prow_s, pgid, pgid_s, P, 0, key_bits(cells), s);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    const unsigned blocks = static_cast<unsigned>((cells + 7) / 8);
+    k_place_count<<<blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, P, W, H, nseg, cnt);
+    e = cudaMemsetAsync(cnt + (npix - 1), 0, 4, s);  // sentinel: the scan's last output is the element count
+    if (e != cudaSuccess) return static_cast<int>(e);
+    size_t cb = L.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(t + L.cub, cb, cnt, seg_off, npix, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    // persistent, ~3500 warps: the lists under construction (~10 KB per cell) stay inside the 126 MB L2
+    const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 444u;
+    unsigned fill_blocks = blocks < cap ? blocks : cap;
+    k_place_fill<<<fill_blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, seg_off, P, W, H, nseg, key_s, gid_s);
     return static_cast<int>(cudaGetLastError());
 }
 

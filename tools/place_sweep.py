@@ -1,0 +1,15 @@
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from simplegaussiansplat_tk71_b200 import workloads as wl, compositor, _lib
+v = wl.splat_view(1920, 1080, 1_000_000, device="cuda")
+L = _lib.lib()
+def t_fwd(reps=5):
+    ts=[]
+    for _ in range(reps+2):
+        a,b=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        a.record(); compositor._render_forward(v.boxsize, v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity, v.l_d, v.width, v.height); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    ts=sorted(ts[2:]); return ts[len(ts)//2]
+compositor.USE_PLACEMENT=False; print("expand+sort fwd ms", round(t_fwd(),3))
+compositor.USE_PLACEMENT=True
+for blocks in (37, 74, 148, 222, 296, 444, 592, 1184):
+    L.gcp_splat_set_fill_blocks(blocks); print("placement fill_blocks", blocks, "fwd ms", round(t_fwd(),3))
