@@ -493,7 +493,78 @@ def splat_legs(args, device, rank, world):
                          "step_ms": max_ms, "allreduce_ms": max_ar, "bucket_bytes": bucket.numel() * 4,
                          "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
                          "collective": "nccl all_reduce(sum) of the parameter-gradient bucket" if world > 1 else "none (1 rank)"}
+    # (iii) C2: the scene bundled with the reference (BASELINE.json configs[1]; poses synthesised), rank 0 only:
+    #       splat step per view, and the two scan ops on the element list of view 0 (per-pixel lists of ~350)
+    if rank == 0:
+        try:
+            out["c2_bundled"] = c2_leg(device)
+        except Exception as ex:  # noqa: BLE001
+            out["c2_bundled"] = {"error": str(ex)}
     return out
+
+
+def c2_leg(device):
+    import torch
+
+    import grouped_cumprod as gc
+    from simplegaussiansplat_tk71_b200 import compositor
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    views = wl.bundled_views(device)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    per_view = []
+    for sc in views:
+        m, lam, o, l = (sc.mean.float().requires_grad_(True), sc.lam.clone().requires_grad_(True),
+                        sc.opacity.clone().requires_grad_(True), sc.l_d.clone().requires_grad_(True))
+        gI = torch.rand(sc.height + 1, sc.width + 1, 3, device=device) + 0.1
+        ts = []
+        for i in range(5):
+            for t_ in (m, lam, o, l):
+                t_.grad = None
+            a, b = ev(), ev()
+            a.record()
+            img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, sc.width, sc.height)
+            img.backward(gI)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = sorted(ts[1:])
+        per_view.append({"view": sc.name, "elements": sc.elements, "gaussians": sc.n, "splat_ms": ts[len(ts) // 2]})
+        del m, lam, o, l, gI, img
+    # the scan ops on view 0's sorted element list
+    sc = views[0]
+    _, v = compositor._render_forward(sc.boxsize, sc.startpoint, sc.endpoint, sc.mean.float(), sc.lam, sc.opacity,
+                                      sc.l_d, sc.width, sc.height)
+    x, key = v.x_s, v.key_s
+    n = x.numel()
+    k = int(torch.unique_consecutive(key).numel())
+    y = torch.empty_like(x)
+    g = torch.rand_like(x)
+    gin = torch.empty_like(x)
+    nolen = torch.empty(0, dtype=torch.int32, device=device)
+    for _ in range(3):
+        gc.grouped_cumprod_forward(x, key, y)
+        gc.grouped_cumprod_backward(x, y, g, key, gin, nolen)
+    reps = 10
+    e0, e1, e2 = ev(), ev(), ev()
+    tf = tb = 0.0
+    for _ in range(reps):
+        e0.record()
+        gc.grouped_cumprod_forward(x, key, y)
+        e1.record()
+        gc.grouped_cumprod_backward(x, y, g, key, gin, nolen)
+        e2.record()
+        torch.cuda.synchronize()
+        tf += e0.elapsed_time(e1)
+        tb += e1.elapsed_time(e2)
+    tf, tb = tf / reps, tb / reps
+    peak, _ = _peaks()
+    ab = wl.algorithmic_bytes(n, k)
+    return {"views": per_view,
+            "scan_on_view0": {"elements": n, "pixel_lists": k, "mean_list_length": n / max(k, 1), "fwd_ms": tf,
+                              "bwd_ms": tb, "Gelem_s": n / ((tf + tb) * 1e-3) / 1e9,
+                              "frac_of_measured_hbm": ab["fwd_bwd"] / ((tf + tb) * 1e-3) / 1e9 / peak}}
 
 
 def sweep(args, e, y, gin, gc, ops):

@@ -231,3 +231,64 @@ def splat_view(width: int = 1920, height: int = 1080, n: int = 1_000_000, seed: 
     return SplatView(f"splat {width}x{height} n={m} seed{seed}", t(boxsize, torch.int64), t(sp, torch.int32),
                      t(ep, torch.int32), t(mean, torch.int32), t(lam, torch.float32), t(opac, torch.float32),
                      t(l_d, torch.float32), width, height)
+
+
+# --------------------------------------------------------------------------------------------
+# C2 — BASELINE.json configs[1]: the scene bundled with the reference (trained opacity.pt, COLMAP points and
+# intrinsics; data/bundled_scene.npz, derived by tools/make_bundled_scene.py).  mean.pt / color.pt / images.bin
+# are missing from the reference snapshot, so the rest is synthesised deterministically as SURVEY.md §8d
+# prescribes, and the projection follows gs_model.py:289-365 for isotropic Gaussians.
+# --------------------------------------------------------------------------------------------
+def bundled_views(device="cpu", n_views: int = 3):
+    """Returns a list of SplatView (one per synthesised pose), Gaussians already z-sorted, culled and clamped."""
+    import os
+
+    from . import views as vw
+
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "bundled_scene.npz"))
+    logits = f["opacity_logits"].astype(np.float32)
+    pts, nn3 = f["points"], f["nn3"]
+    fx, fy, cx, cy, W, H = f["intrinsics"]
+    W, H = int(W), int(H)
+    n = logits.shape[0]
+    rng = np.random.default_rng(0)
+    reps = -(-n // pts.shape[0])
+    mean = (np.tile(pts, (reps, 1))[:n] + rng.normal(0.0, 0.05, (n, 3))).astype(np.float32)   # tiled + jitter
+    scale = (np.tile(nn3, reps)[:n] / 4.0).astype(np.float32)        # exp(variance_scale): mean 3-NN distance / 4
+    centroid = pts.mean(0)
+    out = []
+    dev = torch.device(device)
+    for v in range(n_views):
+        th = 2 * math.pi * v / n_views
+        cam = centroid + 6.0 * np.array([math.cos(th), 0.0, math.sin(th)])
+        fwd = (centroid - cam) / np.linalg.norm(centroid - cam)
+        right = np.cross(fwd, np.array([0.0, -1.0, 0.0]))
+        right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        R = np.stack((right, down, fwd), 0).astype(np.float32)      # world -> camera, z forward
+        pc = (mean - cam.astype(np.float32)) @ R.T                   # gs_model.py:289-290
+        z = pc[:, 2]
+        zc = np.maximum(z, 1e-2)                                     # :294 clamp_min(1e-2)
+        px = fx * pc[:, 0] / zc + cx
+        py = fy * pc[:, 1] / zc + cy
+        # Sigma_px = s^2 J J^T + 1e-6 I with J = [[fx/z, 0, -fx X/z^2], [0, fy/z, -fy Y/z^2]]   (:308-321)
+        j00, j02 = fx / zc, -fx * pc[:, 0] / (zc * zc)
+        j11, j12 = fy / zc, -fy * pc[:, 1] / (zc * zc)
+        s2 = scale * scale
+        a = s2 * (j00 * j00 + j02 * j02) + 1e-6
+        b = s2 * (j02 * j12)
+        d = s2 * (j11 * j11 + j12 * j12) + 1e-6
+        det = a * d - b * b
+        lam = np.stack((d / det, -b / det, -b / det, a / det), 1).reshape(-1, 2, 2).astype(np.float32)   # :353
+        half = 3.0 * np.sqrt(np.stack((a, d), 1))                    # :332  3*sqrt(V^2 |lambda|) = 3*sqrt(diag)
+        half = np.minimum(half, 10 * 0.04 * math.sqrt(W * H)).astype(np.int32)                            # :364-365
+        order = np.argsort(z, kind="stable")                        # :356 z-sort
+        t = lambda arr, dt: torch.from_numpy(np.ascontiguousarray(arr[order])).to(device=dev, dtype=dt)  # noqa: E731
+        mean_px = t(np.stack((px, py), 1).clip(-2e6, 2e6), torch.float32).to(torch.int32)                # :361 int32 cast
+        mask, sp, ep, boxsize = vw.visible_boxes(mean_px, t(half, torch.int32), t(z, torch.float32), W, H)
+        opac = torch.sigmoid(t(logits[:, None], torch.float32))[mask]
+        m = int(mask.sum())
+        out.append(SplatView(f"C2 bundled scene (poses synthesised) view{v} {W}x{H} n={m}", boxsize, sp, ep,
+                             mean_px[mask], t(lam, torch.float32)[mask], opac,
+                             torch.full((m, 3), 0.499, dtype=torch.float32, device=dev), W, H))
+    return out

@@ -181,3 +181,29 @@ def test_native_compositor_edge_cases_gpu():
     # the reference's d/l for the colour gradient (gs_model.py:763-766): d = T alpha <1,l> = 0.7
     assert torch.allclose(l.grad, torch.tensor([[3.5, 1.75, 0.875]], device=dev))
     assert float(m.grad.abs().sum()) == 0.0 and float(lam.grad.abs().sum()) == 0.0   # r - m = 0
+
+
+@pytest.mark.gpu
+def test_bundled_scene_front_slice_against_oracle_gpu():
+    """C2 (BASELINE.json configs[1]): the nearest 4000 Gaussians of a bundled-scene view — boxes of hundreds of
+    pixels, per-pixel lists of hundreds of elements (most tiles go through the fix-up phase)."""
+    from oracle import compositor_oracle as co
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    sc = wl.bundled_views("cpu", n_views=2)[1]
+    k = 4000
+    case = dict(boxsize=sc.boxsize[:k].numpy(), sp=sc.startpoint[:k].numpy(), ep=sc.endpoint[:k].numpy(),
+                mean=sc.mean[:k].numpy(), lam=sc.lam[:k].numpy(), opac=sc.opacity[:k].numpy(), l_d=sc.l_d[:k].numpy(),
+                W=sc.width, H=sc.height)
+    rng = np.random.default_rng(9)
+    gI = rng.uniform(0.1, 1.0, (sc.height + 1, sc.width + 1, 3)).astype(np.float32)
+    img, cache = co.forward(case["boxsize"], case["sp"], case["ep"], case["mean"], case["lam"], case["opac"],
+                            case["l_d"], sc.width, sc.height)
+    gm, gL, go, gl = co.backward(cache, gI)
+    case.update(image=img, grad_image=gI, grad_mean=gm, grad_lambda=gL, grad_opacity=go, grad_l=gl)
+    got = _run(case, "cuda")
+    np.testing.assert_allclose(got[0], img, rtol=5e-4, atol=5e-5)
+    # sums over boxes of thousands of elements in fp32 against fp64: tolerance relative to each array's scale
+    for name, a, b in (("mean", got[1], gm), ("lambda", got[2], gL), ("opacity", got[3], go), ("l", got[4], gl)):
+        scale = float(np.abs(b).max())
+        np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4 * scale, err_msg=name)
