@@ -155,33 +155,45 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
                     int32_t *key_s, int32_t *gid_s, int32_t *seg_off, void *temp, size_t temp_bytes,
                     gcp_stream_t stream);
 
+/* The per-Gaussian tables packed into two 32-byte records per Gaussian (both arrays 32-byte aligned), so that
+ * every per-element gather of the kernels below is a single L2 sector:
+ *   rec_a f32[n,8] = {mx, my, l00, l01, l10, l11, opacity, 0}
+ *   rec_b i32[n,8] = {bits(l0), bits(l1), bits(l2), sx, sy, box width, goff low, goff high}
+ * (mean f32[n,2], lam f32[n,4] row-major Lambda, opac f32[n], l_d f32[n,3], sp/ep i32[n,2], goff i64[n+1]). */
+int gcp_splat_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
+                   const int32_t *ep, const int64_t *goff, int64_t n, float *rec_a, int32_t *rec_b,
+                   gcp_stream_t stream);
+
 /* x_s[e] = 1 - opacity * exp(-1/2 (r-m) Lambda (r-m)^T)  (gs_model.py:493-495, :533-535), sorted order. */
-int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *mean, const float *lam,
-                    const float *opac, int64_t N, float *x_s, gcp_stream_t stream);
+int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *rec_a, int64_t N, float *x_s,
+                    gcp_stream_t stream);
 
 /* image[pixel] += sum_i T_i alpha_i l_i with T_i the EXCLUSIVE product taken from the inclusive scan
  * `incl` (no division; replaces gs_model.py:562, :498-514).  image must be zeroed by the caller. */
 int gcp_splat_color(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
-                    const float *l_d, int64_t N, int W, float *image, gcp_stream_t stream);
+                    const int32_t *rec_b, int64_t N, int W, float *image, gcp_stream_t stream);
 
 /* gshift[k] = w_{k+1} inside a pixel list (0 at its tail), w_k = <dL/dI(pixel), alpha_k l_k>: the grad_out
  * for which gcp_cumprod_bwd_f32 returns T_k*U_k (division-free replacement of gs_model.py:716-722). */
 int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
-                    const float *l_d, const float *grad_image, int64_t N, int W, float *gshift,
+                    const int32_t *rec_b, const float *grad_image, int64_t N, int W, float *gshift,
                     gcp_stream_t stream);
 
 /* Backward in two atomic-free steps (preferred over gcp_splat_bwd_grads):
  *  gcp_splat_bwd_elem   (sorted order) writes (dalpha, d) of every element at its Gaussian-major position
  *                       goff[g] + (y-sy)*w + (x-sx) of elem f32[N,2] — the un-sort, without a permutation;
- *  gcp_splat_bwd_reduce (Gaussian-major) one warp per Gaussian sums the per-element gradients of
- *                       gs_model.py:733-766 over its box (replaces scatter_reduce, :776-783); deterministic. */
+ *  gcp_splat_bwd_reduce (Gaussian-major) sums the per-element gradients of gs_model.py:733-766 over each box
+ *                       (replaces scatter_reduce, :776-783); deterministic, balanced over box sizes (small
+ *                       boxes 8 lanes each, large boxes cut into 1024-element pieces).  temp: at least
+ *                       gcp_splat_bwd_reduce_bytes(N, n) bytes of scratch, 16-byte aligned. */
 int gcp_splat_bwd_elem(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
-                       const int32_t *gid_s, const int32_t *sp, const int32_t *ep, const int64_t *goff,
-                       const float *l_d, const float *grad_image, int64_t N, int W, float *elem,
-                       gcp_stream_t stream);
+                       const int32_t *gid_s, const int32_t *rec_b, const float *grad_image, int64_t N, int W,
+                       float *elem, gcp_stream_t stream);
+size_t gcp_splat_bwd_reduce_bytes(int64_t N, int64_t n);
 int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep, const int64_t *goff,
-                         const float *mean, const float *lam, const float *opac, const float *l_d, int64_t n,
-                         float *g_mean, float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream);
+                         const float *mean, const float *lam, const float *opac, const float *l_d, int64_t N,
+                         int64_t n, float *g_mean, float *g_lam, float *g_opac, float *g_l, void *temp,
+                         size_t temp_bytes, gcp_stream_t stream);
 
 /* Per-element gradients (gs_model.py:733-766) accumulated per Gaussian (:776-783); tu = T*U from
  * gcp_cumprod_bwd_f32.  Outputs must be zeroed by the caller: g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3]. */

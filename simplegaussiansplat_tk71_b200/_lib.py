@@ -25,8 +25,8 @@ SYMBOLS = (
     "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status",
     "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
     "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
-    "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color",
-    "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce",
+    "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_pack", "gcp_splat_alpha", "gcp_splat_color",
+    "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce", "gcp_splat_bwd_reduce_bytes",
     "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_seg_shift",
 )
 
@@ -65,7 +65,9 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_sort_bytes.argtypes = [i64]
     L.gcp_splat_sort_bytes.restype = sz
     L.gcp_splat_sort.argtypes = [vp, vp, vp, vp, i64, ci, vp, sz, vp]
-    L.gcp_splat_alpha.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
+    L.gcp_splat_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]
+    L.gcp_splat_pack.restype = ci
+    L.gcp_splat_alpha.argtypes = [vp, vp, vp, i64, vp, vp]
     L.gcp_splat_color.argtypes = [vp, vp, vp, vp, vp, i64, ci, vp, vp]
     L.gcp_splat_bwd_w.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
     L.gcp_splat_bwd_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp, vp, vp, vp]
@@ -76,8 +78,10 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_set_fill_blocks.argtypes = [ci]
     L.gcp_splat_set_fill_blocks.restype = ci
     L.gcp_splat_seg_shift.restype = ci
-    L.gcp_splat_bwd_elem.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
-    L.gcp_splat_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.gcp_splat_bwd_elem.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
+    L.gcp_splat_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]
+    L.gcp_splat_bwd_reduce_bytes.argtypes = [i64, i64]
+    L.gcp_splat_bwd_reduce_bytes.restype = sz
     for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",
                  "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce"):
         getattr(L, name).restype = ci

@@ -12,9 +12,10 @@ fits one chunk (sum(boxsize) <= 2**29, gs_model.py:428):
     T_i = prod_{j<i, same pixel} (1 - alpha_j),   alpha = opacity * exp(-1/2 (r-m) Lambda (r-m)^T)
     image[y, x] = sum_i T_i alpha_i l_i           (elements whose inclusive product is 0 contribute nothing, :575)
 
-but not how.  One view = ten kernel launches, all through the C ABI (include/gcp_abi.h):
+but not how.  One view = a dozen kernel launches, all through the C ABI (include/gcp_abi.h):
 
-    forward   gcp_splat_place    boxes -> the pixel-sorted (key, Gaussian id) element list, built directly by a
+    forward   gcp_splat_pack     per-Gaussian tables -> two 32-byte records (one L2 sector per gather)
+              gcp_splat_place    boxes -> the pixel-sorted (key, Gaussian id) element list, built directly by a
                                  counting placement per image row — no sort of the N elements
                                  (alternative kept: gcp_splat_expand + gcp_splat_sort)  (:480-482, :538-548)
               gcp_splat_alpha    x = 1 - opacity*g in sorted order                      (:493-495, :533-535)
@@ -25,8 +26,9 @@ but not how.  One view = ten kernel launches, all through the C ABI (include/gcp
               gcp_cumprod_bwd    division-free T_k*U_k (op a3)                          (replaces :716-722)
               gcp_splat_bwd_elem (dalpha, d) per element, written at its Gaussian-major
                                  position (the un-sort, without a permutation array)
-              gcp_splat_bwd_reduce one warp per Gaussian sums the per-element gradients
-                                 over its box: no atomics, deterministic                (:733-783)
+              gcp_splat_bwd_reduce per-element gradients summed over each box (small boxes 8 lanes
+                                 each, large ones in 1024-element pieces): no float atomics,
+                                 deterministic                                          (:733-783)
 
 There is no un-sort (:555), no flip + second sorted pass (:716-722), no chunk loop (:675, :792), no forward
 recompute in the backward (:799) and no division by 1-alpha (:736,:747,:757): with
@@ -53,10 +55,24 @@ def _p(t):
     return t.data_ptr()
 
 
+_scratch = {}
+
+
+def _scratch_bytes(dev, tag: str, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch per (device, stream, purpose): the kernels' temporaries are not re-allocated every view
+    (keeps the caching allocator from splitting and re-growing the large per-view blocks)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, tag)
+    t = _scratch.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, device=dev)
+        _scratch[key] = t
+    return t
+
+
 class _View:
     """Device state of one rendered view kept for the backward (16 B per element + the per-Gaussian tables)."""
     __slots__ = ("n", "N", "W", "H", "key_s", "gid_s", "x_s", "incl", "mean", "lam", "opac", "l_d", "sp", "ep",
-                 "goff")
+                 "goff", "rec_a", "rec_b")
 
 
 def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
@@ -96,11 +112,16 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
         if N >= 2 ** 31:
             raise RuntimeError("a view is limited to 2**31-1 elements (the reference ops index with int32)")
         sp, ep = v.sp, v.ep
+        # per-Gaussian tables as 32-byte records: one L2 sector per gather in the per-element kernels
+        v.rec_a = torch.empty((n, 8), dtype=torch.float32, device=dev)
+        v.rec_b = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        _lib.check(L.gcp_splat_pack(_p(v.mean), _p(v.lam), _p(v.opac), _p(v.l_d), _p(sp), _p(ep), _p(goff), n,
+                                    _p(v.rec_a), _p(v.rec_b), stream), "gcp_splat_pack")
         v.key_s = torch.empty(N, dtype=torch.int32, device=dev)
         v.gid_s = torch.empty(N, dtype=torch.int32, device=dev)
         if USE_PLACEMENT:
             seg_off = torch.empty((H + 1) * (W + 1) + 1, dtype=torch.int32, device=dev)
-            temp = torch.empty(int(L.gcp_splat_place_bytes(P, W, H)), dtype=torch.uint8, device=dev)
+            temp = _scratch_bytes(dev, "place", int(L.gcp_splat_place_bytes(P, W, H)))
             _lib.check(L.gcp_splat_place(_p(sp), _p(ep), _p(poff), n, P, W, H, _p(v.key_s), _p(v.gid_s), _p(seg_off),
                                          _p(temp), temp.numel(), stream), "gcp_splat_place")
             del temp, seg_off
@@ -114,11 +135,11 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
                                         temp.numel(), stream), "gcp_splat_sort")
             del key, gid, temp
         v.x_s = torch.empty(N, dtype=torch.float32, device=dev)
-        _lib.check(L.gcp_splat_alpha(_p(v.key_s), _p(v.gid_s), _p(v.mean), _p(v.lam), _p(v.opac), N, _p(v.x_s),
-                                     stream), "gcp_splat_alpha")
+        _lib.check(L.gcp_splat_alpha(_p(v.key_s), _p(v.gid_s), _p(v.rec_a), N, _p(v.x_s), stream),
+                   "gcp_splat_alpha")
         v.incl = torch.empty_like(v.x_s)
         ops.grouped_cumprod_forward(v.x_s, v.key_s, v.incl)
-        _lib.check(L.gcp_splat_color(_p(v.incl), _p(v.x_s), _p(v.key_s), _p(v.gid_s), _p(v.l_d), N, W, _p(image),
+        _lib.check(L.gcp_splat_color(_p(v.incl), _p(v.x_s), _p(v.key_s), _p(v.gid_s), _p(v.rec_b), N, W, _p(image),
                                      stream), "gcp_splat_color")
     return image, v
 
@@ -138,7 +159,7 @@ def _render_backward(v: _View, grad_image):
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         gshift = torch.empty_like(v.x_s)
-        _lib.check(L.gcp_splat_bwd_w(_p(v.incl), _p(v.x_s), _p(v.key_s), _p(v.gid_s), _p(v.l_d), _p(gI), v.N, v.W,
+        _lib.check(L.gcp_splat_bwd_w(_p(v.incl), _p(v.x_s), _p(v.key_s), _p(v.gid_s), _p(v.rec_b), _p(gI), v.N, v.W,
                                      _p(gshift), stream), "gcp_splat_bwd_w")
         tu = torch.empty_like(v.x_s)
         # the sorted pixel keys serve as segment ids: the backward op only compares neighbours
@@ -147,12 +168,12 @@ def _render_backward(v: _View, grad_image):
                                      torch.empty(0, dtype=torch.int32, device=dev))
         elem = gshift.new_empty((v.N, 2))
         del gshift
-        _lib.check(L.gcp_splat_bwd_elem(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.sp), _p(v.ep),
-                                        _p(v.goff), _p(v.l_d), _p(gI), v.N, v.W, _p(elem), stream),
-                   "gcp_splat_bwd_elem")
+        _lib.check(L.gcp_splat_bwd_elem(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.rec_b), _p(gI),
+                                        v.N, v.W, _p(elem), stream), "gcp_splat_bwd_elem")
+        temp = _scratch_bytes(dev, "reduce", int(L.gcp_splat_bwd_reduce_bytes(v.N, n)))
         _lib.check(L.gcp_splat_bwd_reduce(_p(elem), _p(v.sp), _p(v.ep), _p(v.goff), _p(v.mean), _p(v.lam),
-                                          _p(v.opac), _p(v.l_d), n, _p(g_mean), _p(g_lam), _p(g_opac), _p(g_l),
-                                          stream), "gcp_splat_bwd_reduce")
+                                          _p(v.opac), _p(v.l_d), v.N, n, _p(g_mean), _p(g_lam), _p(g_opac),
+                                          _p(g_l), _p(temp), temp.numel(), stream), "gcp_splat_bwd_reduce")
     return g_mean, g_lam, g_opac, g_l
 
 

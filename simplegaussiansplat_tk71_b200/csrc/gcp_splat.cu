@@ -14,6 +14,7 @@
 // pixel the depth order (= Gaussian index order) is preserved bit-exactly.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -101,10 +102,45 @@ __device__ __forceinline__ float gauss_kernel(const Gauss &G, int key, float &d0
     return expf(-0.5f * (X0 * d0 + X1 * d1));
 }
 
+// Per-Gaussian tables packed into 32-byte records, one L2 sector per gather in the per-element kernels
+// (consecutive elements of a pixel list belong to unrelated Gaussians: every gather is its own sector):
+//   rec_a[g] = {mx, my, l00, l01 | l10, l11, o, 0}                 -> k_splat_alpha
+//   rec_b[g] = {l0, l1, l2, bits(sx) | sy, w, goff_lo, goff_hi}    -> colour / backward kernels (first half only
+//                                                                     where the box is not needed)
+__global__ void __launch_bounds__(256)
+k_splat_pack(const float *__restrict__ mean, const float *__restrict__ lam, const float *__restrict__ opac,
+             const float *__restrict__ l_d, const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
+             const int64_t *__restrict__ goff, int64_t n, float4 *__restrict__ rec_a, int4 *__restrict__ rec_b) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const Gauss G = load_gauss(mean, lam, opac, static_cast<int>(g));
+    rec_a[2 * g] = make_float4(G.mx, G.my, G.l00, G.l01);
+    rec_a[2 * g + 1] = make_float4(G.l10, G.l11, G.o, 0.f);
+    const int sx = __ldg(sp + 2 * g), sy = __ldg(sp + 2 * g + 1);
+    const int64_t off = __ldg(goff + g);
+    rec_b[2 * g] = make_int4(__float_as_int(__ldg(l_d + 3 * g)), __float_as_int(__ldg(l_d + 3 * g + 1)),
+                             __float_as_int(__ldg(l_d + 3 * g + 2)), sx);
+    rec_b[2 * g + 1] = make_int4(sy, __ldg(ep + 2 * g) - sx + 1, static_cast<int>(off & 0xffffffffll),
+                                 static_cast<int>(off >> 32));
+}
+
+// one 32-byte record in one instruction (LDG.256, sm_100)
+__device__ __forceinline__ void ldg256(const void *p, int4 &u, int4 &v) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w), "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ Gauss load_rec_a(const float4 *__restrict__ rec_a, int g) {
+    int4 u, v;
+    ldg256(rec_a + 2 * static_cast<int64_t>(g), u, v);
+    return Gauss{__int_as_float(u.x), __int_as_float(u.y), __int_as_float(u.z), __int_as_float(u.w),
+                 __int_as_float(v.x), __int_as_float(v.y), __int_as_float(v.z)};
+}
+
 // x_s[e] = 1 - o*g in sorted order (the scan's input); 4 consecutive elements per thread
 __global__ void __launch_bounds__(256)
-k_splat_alpha(const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s, const float *__restrict__ mean,
-              const float *__restrict__ lam, const float *__restrict__ opac, int64_t N, float *__restrict__ x_s) {
+k_splat_alpha(const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s,
+              const float4 *__restrict__ rec_a, int64_t N, float *__restrict__ x_s) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
     for (int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e < N; e += stride) {
         int k[4], g[4];
@@ -119,12 +155,14 @@ k_splat_alpha(const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid
                 g[i] = (e + i < N) ? __ldg(gid_s + e + i) : 0;
             }
         }
+        Gauss G[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) G[i] = load_rec_a(rec_a, g[i]);
         float out[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const Gauss G = load_gauss(mean, lam, opac, g[i]);
             float d0, d1, X0, X1;
-            out[i] = 1.0f - G.o * gauss_kernel(G, k[i], d0, d1, X0, X1);
+            out[i] = 1.0f - G[i].o * gauss_kernel(G[i], k[i], d0, d1, X0, X1);
         }
         if (e + 4 <= N) {
             *reinterpret_cast<float4 *>(x_s + e) = make_float4(out[0], out[1], out[2], out[3]);
@@ -139,76 +177,125 @@ __device__ __forceinline__ int pixel_index(int key, int W) {
     return py * (W + 1) + (key - py * KEY_STRIDE);
 }
 
-// image[pixel] += sum_i T_i alpha_i l_i  (T exclusive = previous inclusive product, 1 at a head;
-// elements whose inclusive product is 0 contribute nothing, gs_model.py:575-578)
-__global__ void __launch_bounds__(256)
-k_splat_color(const float *__restrict__ incl, const float *__restrict__ x_s, const int32_t *__restrict__ key_s,
-              const int32_t *__restrict__ gid_s, const float *__restrict__ l_d, int64_t N, int W,
-              float *__restrict__ image) {
-    const int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CH;
-    if (e0 >= N) return;
-    int kprev = (e0 > 0) ? __ldg(key_s + e0 - 1) : -1;
-    float yprev = (e0 > 0) ? __ldg(incl + e0 - 1) : 1.0f;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    int kcur = -1;
-    for (int i = 0; i < CH && e0 + i < N; ++i) {
-        const int64_t e = e0 + i;
-        const int k = __ldg(key_s + e);
-        const float y = __ldg(incl + e);
-        const float T = (k != kprev) ? 1.0f : yprev;
-        if (k != kcur) {
-            if (kcur >= 0 && (a0 != 0.f || a1 != 0.f || a2 != 0.f)) {
-                float *p = image + 3 * static_cast<int64_t>(pixel_index(kcur, W));
-                atomicAdd(p, a0); atomicAdd(p + 1, a1); atomicAdd(p + 2, a2);
-            }
-            kcur = k;
-            a0 = a1 = a2 = 0.f;
-        }
-        if (y != 0.0f) {
-            const float ta = T * (1.0f - __ldg(x_s + e));
-            const int g = __ldg(gid_s + e);
-            a0 = fmaf(ta, __ldg(l_d + 3 * g), a0);
-            a1 = fmaf(ta, __ldg(l_d + 3 * g + 1), a1);
-            a2 = fmaf(ta, __ldg(l_d + 3 * g + 2), a2);
-        }
-        kprev = k;
-        yprev = y;
+// 8 consecutive elements of arrays a (int) / f (float) starting at e (e % 8 == 0 for every thread: vector loads)
+__device__ __forceinline__ void load8(const int32_t *__restrict__ a, int64_t e, int64_t N, int (&v)[8], int fill) {
+    if (e + 8 <= N) {
+        const int4 p = __ldg(reinterpret_cast<const int4 *>(a + e)), q = __ldg(reinterpret_cast<const int4 *>(a + e) + 1);
+        v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (e + i < N) ? __ldg(a + e + i) : fill;
     }
-    if (kcur >= 0 && (a0 != 0.f || a1 != 0.f || a2 != 0.f)) {
-        float *p = image + 3 * static_cast<int64_t>(pixel_index(kcur, W));
+}
+__device__ __forceinline__ void load8(const float *__restrict__ a, int64_t e, int64_t N, float (&v)[8], float fill) {
+    if (e + 8 <= N) {
+        const float4 p = __ldg(reinterpret_cast<const float4 *>(a + e)),
+                     q = __ldg(reinterpret_cast<const float4 *>(a + e) + 1);
+        v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (e + i < N) ? __ldg(a + e + i) : fill;
+    }
+}
+
+__device__ __forceinline__ void color_flush(float *__restrict__ image, int key, int W, float a0, float a1, float a2) {
+    if (key >= 0 && (a0 != 0.f || a1 != 0.f || a2 != 0.f)) {
+        float *p = image + 3 * static_cast<int64_t>(pixel_index(key, W));
         atomicAdd(p, a0); atomicAdd(p + 1, a1); atomicAdd(p + 2, a2);
     }
 }
 
-// w_k = <dL/dI(pixel), alpha_k l_k> (0 for dead elements); gshift[k] = w_{k+1} inside a pixel list, 0 at its tail:
-// the grad_out that makes grouped_cumprod_backward return T_k * U_k.
-__device__ __forceinline__ float elem_w(const float *__restrict__ incl, const float *__restrict__ x_s,
-                                        const int32_t *__restrict__ gid_s, const float *__restrict__ l_d,
-                                        const float *__restrict__ gimg, int64_t e, int key, int W, float &pgl) {
-    const int g = __ldg(gid_s + e);
-    const float *pg = gimg + 3 * static_cast<int64_t>(pixel_index(key, W));
-    pgl = __ldg(pg) * __ldg(l_d + 3 * g) + __ldg(pg + 1) * __ldg(l_d + 3 * g + 1) +
-          __ldg(pg + 2) * __ldg(l_d + 3 * g + 2);
-    return (__ldg(incl + e) != 0.0f) ? (1.0f - __ldg(x_s + e)) * pgl : 0.0f;
+// image[pixel] += sum_i T_i alpha_i l_i  (T exclusive = previous inclusive product, 1 at a head;
+// elements whose inclusive product is 0 contribute nothing, gs_model.py:575-578).
+// 8 consecutive elements per thread; a thread adds the partial sum of every pixel run it sees (one atomic
+// triple per run and thread — a run of a few hundred elements is a few dozen adds).
+__global__ void __launch_bounds__(256)
+k_splat_color(const float *__restrict__ incl, const float *__restrict__ x_s, const int32_t *__restrict__ key_s,
+              const int32_t *__restrict__ gid_s, const int4 *__restrict__ rec_b, int64_t N, int W,
+              float *__restrict__ image) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; e0 < N; e0 += stride) {
+        int k[8], g[8];
+        float y[8], x[8];
+        load8(key_s, e0, N, k, -1);
+        load8(gid_s, e0, N, g, 0);
+        load8(incl, e0, N, y, 0.0f);
+        load8(x_s, e0, N, x, 1.0f);
+        int kprev = (e0 > 0) ? __ldg(key_s + e0 - 1) : -1;
+        float yprev = (e0 > 0) ? __ldg(incl + e0 - 1) : 1.0f;
+        int4 l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = (y[i] != 0.0f) ? __ldg(rec_b + 2 * static_cast<int64_t>(g[i])) : make_int4(0, 0, 0, 0);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        int kcur = -1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float T = (k[i] != kprev) ? 1.0f : yprev;
+            if (k[i] != kcur) {
+                color_flush(image, kcur, W, a0, a1, a2);
+                kcur = k[i];
+                a0 = a1 = a2 = 0.f;
+            }
+            if (y[i] != 0.0f) {
+                const float ta = T * (1.0f - x[i]);
+                a0 = fmaf(ta, __int_as_float(l[i].x), a0);
+                a1 = fmaf(ta, __int_as_float(l[i].y), a1);
+                a2 = fmaf(ta, __int_as_float(l[i].z), a2);
+            }
+            kprev = k[i];
+            yprev = y[i];
+        }
+        color_flush(image, kcur, W, a0, a1, a2);
+    }
 }
 
+// gshift[k] = w_{k+1} inside a pixel list, 0 at its tail, with w_k = <dL/dI(pixel), alpha_k l_k> (0 for dead
+// elements): the grad_out that makes grouped_cumprod_backward return T_k * U_k.  4 elements per thread.
 __global__ void __launch_bounds__(256)
 k_splat_bwd_w(const float *__restrict__ incl, const float *__restrict__ x_s, const int32_t *__restrict__ key_s,
-              const int32_t *__restrict__ gid_s, const float *__restrict__ l_d, const float *__restrict__ gimg,
+              const int32_t *__restrict__ gid_s, const int4 *__restrict__ rec_b, const float *__restrict__ gimg,
               int64_t N, int W, float *__restrict__ gshift) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
     for (int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e < N; e += stride) {
-        // elements e+1 .. e+4 are needed (w of the successor); load keys e .. e+4
-        int k[5];
+        // elements e+1 .. e+4 are needed (w of the successor): slots 0..4 hold elements e .. e+4
+        int k[5], g[5];
+        float y[5], x[5];
+        if (e + 4 <= N) {
+            const int4 kk = __ldg(reinterpret_cast<const int4 *>(key_s + e));
+            const int4 gg = __ldg(reinterpret_cast<const int4 *>(gid_s + e));
+            const float4 yy = __ldg(reinterpret_cast<const float4 *>(incl + e));
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_s + e));
+            k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
+            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+            y[0] = yy.x; y[1] = yy.y; y[2] = yy.z; y[3] = yy.w;
+            x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) k[i] = (e + i < N) ? __ldg(key_s + e + i) : -1;
+            for (int i = 0; i < 4; ++i) {
+                const bool in = e + i < N;
+                k[i] = in ? __ldg(key_s + e + i) : -1;
+                g[i] = in ? __ldg(gid_s + e + i) : 0;
+                y[i] = in ? __ldg(incl + e + i) : 0.0f;
+                x[i] = in ? __ldg(x_s + e + i) : 1.0f;
+            }
+        }
+        {
+            const bool in = e + 4 < N;
+            k[4] = in ? __ldg(key_s + e + 4) : -1;
+            g[4] = in ? __ldg(gid_s + e + 4) : 0;
+            y[4] = in ? __ldg(incl + e + 4) : 0.0f;
+            x[4] = in ? __ldg(x_s + e + 4) : 1.0f;
+        }
         float out[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             out[i] = 0.0f;
-            if (e + i + 1 < N && k[i + 1] == k[i]) {
-                float pgl;
-                out[i] = elem_w(incl, x_s, gid_s, l_d, gimg, e + i + 1, k[i + 1], W, pgl);
+            if (k[i + 1] == k[i] && k[i] >= 0 && y[i + 1] != 0.0f) {
+                const int4 l = __ldg(rec_b + 2 * static_cast<int64_t>(g[i + 1]));
+                const float *pg = gimg + 3 * static_cast<int64_t>(pixel_index(k[i + 1], W));
+                const float pgl = __ldg(pg) * __int_as_float(l.x) + __ldg(pg + 1) * __int_as_float(l.y) +
+                                  __ldg(pg + 2) * __int_as_float(l.z);
+                out[i] = (1.0f - x[i + 1]) * pgl;
             }
         }
         if (e + 4 <= N) {
@@ -270,8 +357,7 @@ k_splat_bwd_grads(const float *__restrict__ incl, const float *__restrict__ x_s,
 __global__ void __launch_bounds__(256)
 k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, const float *__restrict__ tu,
                  const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s,
-                 const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ goff,
-                 const float *__restrict__ l_d, const float *__restrict__ gimg, int64_t N, int W,
+                 const int4 *__restrict__ rec_b, const float *__restrict__ gimg, int64_t N, int W,
                  float2 *__restrict__ elem) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
     for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e0 < N; e0 += stride) {
@@ -300,19 +386,24 @@ k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, 
         }
         int kprev = (e0 > 0) ? __ldg(key_s + e0 - 1) : -1;
         float yprev = (e0 > 0) ? __ldg(incl + e0 - 1) : 1.0f;
+        int4 ra[4], rb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ldg256(rec_b + 2 * static_cast<int64_t>(g[i]), ra[i], rb[i]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (e0 + i < N) {
                 const int py = k[i] / KEY_STRIDE, px = k[i] - py * KEY_STRIDE;
-                const int2 s2 = __ldg(reinterpret_cast<const int2 *>(sp) + g[i]);
-                const int w = __ldg(ep + 2 * g[i]) - s2.x + 1;
-                const int64_t dst = __ldg(goff + g[i]) + static_cast<int64_t>(py - s2.y) * w + (px - s2.x);
+                const int sx = ra[i].w, sy = rb[i].x, w = rb[i].y;
+                const int64_t off = (static_cast<int64_t>(rb[i].w) << 32) | static_cast<uint32_t>(rb[i].z);
+                const int64_t dst = off + static_cast<int64_t>(py - sy) * w + (px - sx);
                 float2 out = make_float2(0.0f, 0.0f);
                 if (y[i] != 0.0f) {  // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
                     const float T = (k[i] != kprev) ? 1.0f : yprev;
                     const float *pg = gimg + 3 * static_cast<int64_t>(py * (W + 1) + px);
-                    const float pgl = __ldg(pg) * __ldg(l_d + 3 * g[i]) + __ldg(pg + 1) * __ldg(l_d + 3 * g[i] + 1) +
-                                      __ldg(pg + 2) * __ldg(l_d + 3 * g[i] + 2);
+                    const float pgl = __ldg(pg) * __int_as_float(ra[i].x) + __ldg(pg + 1) * __int_as_float(ra[i].y) +
+                                      __ldg(pg + 2) * __int_as_float(ra[i].z);
                     out.x = T * pgl - t[i];
                     out.y = T * (1.0f - xx[i]) * pgl;
                 }
@@ -324,17 +415,76 @@ k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, 
     }
 }
 
-// Backward, step 2 of 2 (Gaussian-major order): one warp per Gaussian sums the reference's per-element
-// gradients (gs_model.py:733-766) over its box — a segmented reduction without atomics, deterministic:
+// Backward, step 2 of 2 (Gaussian-major order): the reference's per-element gradients (gs_model.py:733-766)
+// summed over each Gaussian's box — a segmented reduction without float atomics, deterministic:
 //   d_opacity = sum g dalpha            d_l[c] = (sum d) / l[c]      (the reference's d/l, :763-766)
 //   d_mean    = sum alpha dalpha (r-m)Lambda          d_Lambda = sum -1/2 alpha dalpha (r-m)^T (r-m)
+// Work is balanced over box sizes from a few pixels to >100 K (bundled scene, C2):
+//   k_splat_bwd_reduce        boxes of <= RED_SMALL elements: 8 lanes per Gaussian.  Larger boxes are cut into
+//                             pieces of RED_PIECE elements and appended to a piece list (an integer atomic
+//                             reserves the contiguous slots; slot order does not enter any float sum).
+//   k_splat_bwd_reduce_pieces one warp per piece -> one partial 7-vector per slot.
+//   k_splat_bwd_reduce_final  the partials of one Gaussian are added in piece order.
+constexpr int RED_SMALL = 256;
+constexpr int RED_PIECE = 1024;
+
+struct RedAcc {
+    float o = 0.f, d = 0.f, m0 = 0.f, m1 = 0.f, a00 = 0.f, a01 = 0.f, a11 = 0.f;
+};
+
+__device__ __forceinline__ void red_add(RedAcc &A, const float2 v, const int local, const int w, const int sx,
+                                        const int sy, const Gauss &G) {
+    const int iy = local / w, ix = local - iy * w;
+    const float d0 = static_cast<float>(sx + ix) - G.mx, d1 = static_cast<float>(sy + iy) - G.my;
+    const float X0 = d0 * G.l00 + d1 * G.l10, X1 = d0 * G.l01 + d1 * G.l11;
+    const float gk = expf(-0.5f * (X0 * d0 + X1 * d1));
+    const float coef = G.o * gk * v.x;
+    A.o = fmaf(gk, v.x, A.o);
+    A.d += v.y;
+    A.m0 = fmaf(coef, X0, A.m0);
+    A.m1 = fmaf(coef, X1, A.m1);
+    const float hc = -0.5f * coef;
+    A.a00 = fmaf(hc * d0, d0, A.a00);
+    A.a01 = fmaf(hc * d0, d1, A.a01);
+    A.a11 = fmaf(hc * d1, d1, A.a11);
+}
+
+template <int LANES>
+__device__ __forceinline__ void red_lanes(RedAcc &A) {
+#pragma unroll
+    for (int d = LANES / 2; d >= 1; d >>= 1) {
+        A.o += __shfl_xor_sync(0xffffffffu, A.o, d);
+        A.d += __shfl_xor_sync(0xffffffffu, A.d, d);
+        A.m0 += __shfl_xor_sync(0xffffffffu, A.m0, d);
+        A.m1 += __shfl_xor_sync(0xffffffffu, A.m1, d);
+        A.a00 += __shfl_xor_sync(0xffffffffu, A.a00, d);
+        A.a01 += __shfl_xor_sync(0xffffffffu, A.a01, d);
+        A.a11 += __shfl_xor_sync(0xffffffffu, A.a11, d);
+    }
+}
+
+__device__ __forceinline__ void red_store(const RedAcc &A, const int64_t g, const float *__restrict__ l_d,
+                                          float *__restrict__ g_mean, float *__restrict__ g_lam,
+                                          float *__restrict__ g_opac, float *__restrict__ g_l) {
+    g_opac[g] = A.o;
+    g_l[3 * g] = A.d / __ldg(l_d + 3 * g);
+    g_l[3 * g + 1] = A.d / __ldg(l_d + 3 * g + 1);
+    g_l[3 * g + 2] = A.d / __ldg(l_d + 3 * g + 2);
+    g_mean[2 * g] = A.m0;
+    g_mean[2 * g + 1] = A.m1;
+    g_lam[4 * g] = A.a00;
+    g_lam[4 * g + 1] = A.a01;
+    g_lam[4 * g + 2] = A.a01;
+    g_lam[4 * g + 3] = A.a11;
+}
+
 __global__ void __launch_bounds__(256)
 k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
                    const int64_t *__restrict__ goff, const float *__restrict__ mean, const float *__restrict__ lam,
                    const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
                    float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
-                   float *__restrict__ g_l) {
-    // a box holds ~40 elements on average: 8 lanes per Gaussian, four Gaussians per warp at a time
+                   float *__restrict__ g_l, unsigned int *__restrict__ pcount, int32_t *__restrict__ piece_g,
+                   int32_t *__restrict__ piece_i) {
     constexpr int GL = 8;
     const int sub = threadIdx.x & (GL - 1);
     const int64_t grp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / GL;
@@ -344,50 +494,90 @@ k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ 
         const int64_t g = grp0 + it * ngrp;
         const bool live = g < n;
         const int64_t gg = live ? g : 0;
-        const int64_t b = __ldg(goff + gg), eend = live ? __ldg(goff + gg + 1) : b;
+        const int64_t b = __ldg(goff + gg);
+        int64_t eend = live ? __ldg(goff + gg + 1) : b;
+        const bool big = eend - b > RED_SMALL;
+        if (big) {
+            if (sub == 0) {
+                const int np = static_cast<int>((eend - b + RED_PIECE - 1) / RED_PIECE);
+                const unsigned int base = atomicAdd(pcount, static_cast<unsigned int>(np));
+                for (int i = 0; i < np; ++i) {
+                    piece_g[base + i] = static_cast<int32_t>(g);
+                    piece_i[base + i] = i;
+                }
+            }
+            eend = b;
+        }
         const Gauss G = load_gauss(mean, lam, opac, static_cast<int>(gg));
         const int sx = __ldg(sp + 2 * gg), sy = __ldg(sp + 2 * gg + 1);
         const int w = __ldg(ep + 2 * gg) - sx + 1;
-        float a_o = 0.f, a_d = 0.f, a_m0 = 0.f, a_m1 = 0.f, a_00 = 0.f, a_01 = 0.f, a_11 = 0.f;
-        for (int64_t e = b + sub; e < eend; e += GL) {
-            const float2 v = __ldg(elem + e);
-            const int local = static_cast<int>(e - b);
-            const int iy = local / w, ix = local - iy * w;
-            const float d0 = static_cast<float>(sx + ix) - G.mx, d1 = static_cast<float>(sy + iy) - G.my;
-            const float X0 = d0 * G.l00 + d1 * G.l10, X1 = d0 * G.l01 + d1 * G.l11;
-            const float gk = expf(-0.5f * (X0 * d0 + X1 * d1));
-            const float coef = G.o * gk * v.x;
-            a_o = fmaf(gk, v.x, a_o);
-            a_d += v.y;
-            a_m0 = fmaf(coef, X0, a_m0);
-            a_m1 = fmaf(coef, X1, a_m1);
-            const float hc = -0.5f * coef;
-            a_00 = fmaf(hc * d0, d0, a_00);
-            a_01 = fmaf(hc * d0, d1, a_01);
-            a_11 = fmaf(hc * d1, d1, a_11);
-        }
+        RedAcc A;
+        for (int64_t e = b + sub; e < eend; e += 4 * GL) {  // four loads in flight per lane
+            float2 v[4];
 #pragma unroll
-        for (int d = GL / 2; d >= 1; d >>= 1) {
-            a_o += __shfl_xor_sync(0xffffffffu, a_o, d);
-            a_d += __shfl_xor_sync(0xffffffffu, a_d, d);
-            a_m0 += __shfl_xor_sync(0xffffffffu, a_m0, d);
-            a_m1 += __shfl_xor_sync(0xffffffffu, a_m1, d);
-            a_00 += __shfl_xor_sync(0xffffffffu, a_00, d);
-            a_01 += __shfl_xor_sync(0xffffffffu, a_01, d);
-            a_11 += __shfl_xor_sync(0xffffffffu, a_11, d);
+            for (int u = 0; u < 4; ++u) v[u] = (e + u * GL < eend) ? __ldg(elem + e + u * GL) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e + u * GL < eend) red_add(A, v[u], static_cast<int>(e + u * GL - b), w, sx, sy, G);
         }
-        if (live && sub == 0) {
-            g_opac[g] = a_o;
-            g_l[3 * g] = a_d / __ldg(l_d + 3 * g);
-            g_l[3 * g + 1] = a_d / __ldg(l_d + 3 * g + 1);
-            g_l[3 * g + 2] = a_d / __ldg(l_d + 3 * g + 2);
-            g_mean[2 * g] = a_m0;
-            g_mean[2 * g + 1] = a_m1;
-            g_lam[4 * g] = a_00;
-            g_lam[4 * g + 1] = a_01;
-            g_lam[4 * g + 2] = a_01;
-            g_lam[4 * g + 3] = a_11;
+        red_lanes<GL>(A);
+        if (live && !big && sub == 0) red_store(A, g, l_d, g_mean, g_lam, g_opac, g_l);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_splat_bwd_reduce_pieces(const float2 *__restrict__ elem, const int32_t *__restrict__ sp,
+                          const int32_t *__restrict__ ep, const int64_t *__restrict__ goff,
+                          const float *__restrict__ mean, const float *__restrict__ lam,
+                          const float *__restrict__ opac, const unsigned int *__restrict__ pcount,
+                          const int32_t *__restrict__ piece_g, const int32_t *__restrict__ piece_i,
+                          float4 *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int np = *pcount;
+    const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < np; p += nwarps) {
+        const int g = __ldg(piece_g + p);
+        const int64_t g0 = __ldg(goff + g);
+        const int64_t b = g0 + static_cast<int64_t>(__ldg(piece_i + p)) * RED_PIECE;
+        const int64_t eend = min(__ldg(goff + g + 1), b + RED_PIECE);
+        const Gauss G = load_gauss(mean, lam, opac, g);
+        const int sx = __ldg(sp + 2 * g), sy = __ldg(sp + 2 * g + 1);
+        const int w = __ldg(ep + 2 * g) - sx + 1;
+        RedAcc A;
+        for (int64_t e = b + lane; e < eend; e += 4 * 32) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (e + u * 32 < eend) ? __ldg(elem + e + u * 32) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e + u * 32 < eend) red_add(A, v[u], static_cast<int>(e + u * 32 - g0), w, sx, sy, G);
         }
+        red_lanes<32>(A);
+        if (lane == 0) {
+            partial[2 * static_cast<size_t>(p)] = make_float4(A.o, A.d, A.m0, A.m1);
+            partial[2 * static_cast<size_t>(p) + 1] = make_float4(A.a00, A.a01, A.a11, 0.f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_splat_bwd_reduce_final(const int64_t *__restrict__ goff, const float *__restrict__ l_d,
+                         const unsigned int *__restrict__ pcount, const int32_t *__restrict__ piece_g,
+                         const int32_t *__restrict__ piece_i, const float4 *__restrict__ partial,
+                         float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
+                         float *__restrict__ g_l) {
+    const unsigned int np = *pcount;
+    for (unsigned int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        if (__ldg(piece_i + p) != 0) continue;
+        const int g = __ldg(piece_g + p);
+        const int cnt = static_cast<int>((__ldg(goff + g + 1) - __ldg(goff + g) + RED_PIECE - 1) / RED_PIECE);
+        RedAcc A;
+        for (int i = 0; i < cnt; ++i) {
+            const float4 u = partial[2 * static_cast<size_t>(p + i)], v = partial[2 * static_cast<size_t>(p + i) + 1];
+            A.o += u.x; A.d += u.y; A.m0 += u.z; A.m1 += u.w;
+            A.a00 += v.x; A.a01 += v.y; A.a11 += v.z;
+        }
+        red_store(A, g, l_d, g_mean, g_lam, g_opac, g_l);
     }
 }
 
@@ -496,6 +686,52 @@ k_place_count(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ p
     }
 }
 
+// key_s from the pixel-list offsets: streaming, coalesced (the fill below then scatters only the Gaussian ids).
+// One block per 256 consecutive pixels (image order = key order): its elements form one contiguous range.
+__global__ void __launch_bounds__(256)
+k_place_keys(const int32_t *__restrict__ off, int npix, int W, int32_t *__restrict__ key_s) {
+    __shared__ int32_t so[257];
+    __shared__ int32_t sk[256];
+    const int p0 = blockIdx.x * 256;
+    const int np = min(256, npix - p0);
+    for (int i = threadIdx.x; i <= np; i += 256) so[i] = __ldg(off + p0 + i);
+    if (threadIdx.x < np) {
+        const int p = p0 + threadIdx.x, y = p / (W + 1);
+        sk[threadIdx.x] = y * KEY_STRIDE + (p - y * (W + 1));
+    }
+    __syncthreads();
+    const int s0 = so[0], s1 = so[np];
+    // aligned groups of 4 elements per thread: one search, then a walk; interior groups are one 16-byte store
+    for (int c = (s0 >> 2) + threadIdx.x; c < ((s1 + 3) >> 2); c += 256) {
+        const int e0 = c << 2;
+        const int lo = max(e0, s0), hi = min(e0 + 4, s1);
+        int a = 0, b = np;  // last pixel j with so[j] <= lo (empty lists share their successor's offset)
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (so[m] <= lo) a = m;
+            else b = m;
+        }
+        int v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = e0 + i;
+            if (e >= lo && e < hi) {
+                while (so[a + 1] <= e) ++a;
+                v[i] = sk[a];
+            } else {
+                v[i] = 0;
+            }
+        }
+        if (lo == e0 && hi == e0 + 4) {
+            *reinterpret_cast<int4 *>(key_s + e0) = make_int4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (e0 + i >= lo && e0 + i < hi) key_s[e0 + i] = v[i];
+        }
+    }
+}
+
 // one warp per (row, strip) cell at a time: walk the cell's intervals in Gaussian (depth) order.
 // The grid is persistent and small on purpose (see gcp_splat_place): cells are taken in index order, so the
 // lists being filled at any moment form one compact address window that stays in L2 until every 32-byte
@@ -503,7 +739,7 @@ k_place_count(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ p
 __global__ void __launch_bounds__(256)
 k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pgid_s,
              const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int32_t *__restrict__ off,
-             int64_t P, int W, int H, int nseg, int32_t *__restrict__ key_s, int32_t *__restrict__ gid_s) {
+             int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s) {
     __shared__ int32_t sm[8][2 * SEGW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int ncell = (H + 1) * nseg;
@@ -519,7 +755,6 @@ k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pg
         __syncwarp();
         int64_t lo, hi;
         cell_range(pcell_s, P, cell, lo, hi);
-        const int kbase = y * KEY_STRIDE + x0;
         for (int64_t b = lo; b < hi; b += 32) {
             int g = 0, a = 0, z = -1;
             if (b + lane < hi) {
@@ -535,9 +770,7 @@ k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pg
                 for (int i = ia + lane; i <= iz; i += 32) {
                     const int r = c[i];
                     c[i] = r + 1;
-                    const int dst = o[i] + r;
-                    gid_s[dst] = gg;
-                    key_s[dst] = kbase + i;
+                    gid_s[o[i] + r] = gg;
                 }
                 __syncwarp();
             }
@@ -591,31 +824,42 @@ int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_ou
                                                             reinterpret_cast<cudaStream_t>(stream)));
 }
 
-int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *mean, const float *lam,
-                    const float *opac, int64_t N, float *x_s, gcp_stream_t stream) {
+int gcp_splat_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
+                   const int32_t *ep, const int64_t *goff, int64_t n, float *rec_a, int32_t *rec_b,
+                   gcp_stream_t stream) {
+    if (n < 0) return GCP_ERR_INVALID_ARG;
+    if (n == 0) return GCP_OK;
+    if ((reinterpret_cast<uintptr_t>(rec_a) | reinterpret_cast<uintptr_t>(rec_b)) & 31) return GCP_ERR_INVALID_ARG;
+    k_splat_pack<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        mean, lam, opac, l_d, sp, ep, goff, n, reinterpret_cast<float4 *>(rec_a), reinterpret_cast<int4 *>(rec_b));
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_splat_alpha(const int32_t *key_s, const int32_t *gid_s, const float *rec_a, int64_t N, float *x_s,
+                    gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
     k_splat_alpha<<<blocks_for(N, 256 * 4, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        key_s, gid_s, mean, lam, opac, N, x_s);
+        key_s, gid_s, reinterpret_cast<const float4 *>(rec_a), N, x_s);
     return static_cast<int>(cudaGetLastError());
 }
 
 int gcp_splat_color(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
-                    const float *l_d, int64_t N, int W, float *image, gcp_stream_t stream) {
+                    const int32_t *rec_b, int64_t N, int W, float *image, gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
-    k_splat_color<<<blocks_for(N, 256 * CH), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(incl, x_s, key_s, gid_s,
-                                                                                                 l_d, N, W, image);
+    k_splat_color<<<blocks_for(N, 256 * 8, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        incl, x_s, key_s, gid_s, reinterpret_cast<const int4 *>(rec_b), N, W, image);
     return static_cast<int>(cudaGetLastError());
 }
 
 int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, const int32_t *gid_s,
-                    const float *l_d, const float *grad_image, int64_t N, int W, float *gshift,
+                    const int32_t *rec_b, const float *grad_image, int64_t N, int W, float *gshift,
                     gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
     k_splat_bwd_w<<<blocks_for(N, 256 * 4, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        incl, x_s, key_s, gid_s, l_d, grad_image, N, W, gshift);
+        incl, x_s, key_s, gid_s, reinterpret_cast<const int4 *>(rec_b), grad_image, N, W, gshift);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -631,23 +875,60 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
 }
 
 int gcp_splat_bwd_elem(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
-                       const int32_t *gid_s, const int32_t *sp, const int32_t *ep, const int64_t *goff,
-                       const float *l_d, const float *grad_image, int64_t N, int W, float *elem,
-                       gcp_stream_t stream) {
+                       const int32_t *gid_s, const int32_t *rec_b, const float *grad_image, int64_t N, int W,
+                       float *elem, gcp_stream_t stream) {
     if (N < 0) return GCP_ERR_INVALID_ARG;
     if (N == 0) return GCP_OK;
     k_splat_bwd_elem<<<blocks_for(N, 256 * 4, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        incl, x_s, tu, key_s, gid_s, sp, ep, goff, l_d, grad_image, N, W, reinterpret_cast<float2 *>(elem));
+        incl, x_s, tu, key_s, gid_s, reinterpret_cast<const int4 *>(rec_b), grad_image, N, W,
+        reinterpret_cast<float2 *>(elem));
     return static_cast<int>(cudaGetLastError());
 }
 
+namespace {
+struct ReduceLayout {
+    size_t piece_g, piece_i, partial, total, cap;
+};
+ReduceLayout reduce_layout(int64_t N, int64_t n) {
+    ReduceLayout l;
+    const int64_t nbig = std::min<int64_t>(n, N / RED_SMALL);
+    l.cap = static_cast<size_t>(N / RED_PIECE + nbig + 1);
+    size_t off = 256;  // header: piece counter
+    l.piece_g = off; off += (l.cap * 4 + 255) & ~size_t(255);
+    l.piece_i = off; off += (l.cap * 4 + 255) & ~size_t(255);
+    l.partial = off; off += l.cap * 32;
+    l.total = off;
+    return l;
+}
+}  // namespace
+
+size_t gcp_splat_bwd_reduce_bytes(int64_t N, int64_t n) { return (N < 0 || n < 0) ? 0 : reduce_layout(N, n).total; }
+
 int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep, const int64_t *goff,
-                         const float *mean, const float *lam, const float *opac, const float *l_d, int64_t n,
-                         float *g_mean, float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
-    if (n < 0) return GCP_ERR_INVALID_ARG;
+                         const float *mean, const float *lam, const float *opac, const float *l_d, int64_t N,
+                         int64_t n, float *g_mean, float *g_lam, float *g_opac, float *g_l, void *temp,
+                         size_t temp_bytes, gcp_stream_t stream) {
+    if (n < 0 || N < 0) return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
-    k_splat_bwd_reduce<<<blocks_for(n, 32, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float2 *>(elem), sp, ep, goff, mean, lam, opac, l_d, n, g_mean, g_lam, g_opac, g_l);
+    const ReduceLayout l = reduce_layout(N, n);
+    if (temp == nullptr || temp_bytes < l.total) return GCP_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(temp) & 15) return GCP_ERR_INVALID_ARG;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    char *t = static_cast<char *>(temp);
+    auto *pcount = reinterpret_cast<unsigned int *>(t);
+    auto *piece_g = reinterpret_cast<int32_t *>(t + l.piece_g);
+    auto *piece_i = reinterpret_cast<int32_t *>(t + l.piece_i);
+    auto *partial = reinterpret_cast<float4 *>(t + l.partial);
+    cudaError_t e = cudaMemsetAsync(pcount, 0, 256, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_splat_bwd_reduce<<<blocks_for(n, 32, 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const float2 *>(elem), sp, ep, goff, mean, lam, opac, l_d, n, g_mean, g_lam, g_opac, g_l,
+        pcount, piece_g, piece_i);
+    const int piece_blocks = static_cast<int>(std::min<size_t>(148 * 8, (l.cap + 7) / 8));
+    k_splat_bwd_reduce_pieces<<<piece_blocks, 256, 0, st>>>(reinterpret_cast<const float2 *>(elem), sp, ep, goff,
+                                                            mean, lam, opac, pcount, piece_g, piece_i, partial);
+    k_splat_bwd_reduce_final<<<std::min<int>(148 * 4, static_cast<int>((l.cap + 255) / 256)), 256, 0, st>>>(
+        goff, l_d, pcount, piece_g, piece_i, partial, g_mean, g_lam, g_opac, g_l);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -722,7 +1003,9 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
     // persistent, ~3500 warps: the lists under construction (~10 KB per cell) stay inside the 126 MB L2
     const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 444u;
     unsigned fill_blocks = blocks < cap ? blocks : cap;
-    k_place_fill<<<fill_blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, seg_off, P, W, H, nseg, key_s, gid_s);
+    k_place_keys<<<static_cast<unsigned>((npix - 1 + 255) / 256), 256, 0, s>>>(seg_off, static_cast<int>(npix - 1), W,
+                                                                              key_s);
+    k_place_fill<<<fill_blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -15,8 +15,9 @@ ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--c2", type=int, default=-1, help="use view K of the bundled-scene workload (C2) instead")
 a = ap.parse_args()
-v = wl.splat_view(a.width, a.height, a.n, device="cuda")
+v = wl.bundled_views("cuda")[a.c2] if a.c2 >= 0 else wl.splat_view(a.width, a.height, a.n, device="cuda")
 print(v.name, "elements", v.elements)
 mean = v.mean.float().requires_grad_(True)
 lam = v.lam.clone().requires_grad_(True)
@@ -40,6 +41,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 tf = tb = 0.0
+per_step = []
 for _ in range(a.steps):
     for t in (mean, lam, opac, l_d):
         t.grad = None
@@ -51,5 +53,15 @@ for _ in range(a.steps):
     torch.cuda.synchronize()
     tf += e0.elapsed_time(e1)
     tb += e1.elapsed_time(e2)
+    per_step.append((round(e0.elapsed_time(e1), 3), round(e1.elapsed_time(e2), 3)))
+print("per step (fwd, bwd) ms:", per_step)
 print(f"splat step: fwd {tf / a.steps:.3f} ms  bwd {tb / a.steps:.3f} ms  total {(tf + tb) / a.steps:.3f} ms "
       f"({v.elements / ((tf + tb) / a.steps) / 1e6:.2f} Gelem/s), peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+
+if os.environ.get("SPLAT_PROFILE"):
+    # per-kernel device times of one step under the torch (kineto) profiler — for a breakdown, not a bench value
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
