@@ -147,7 +147,8 @@ int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_ou
  * offset[pixel] + (number of earlier Gaussians on that pixel), i.e. exactly its stable-sort position.
  * poff i64[n+1] = exclusive offsets of (box height) x (number of strips the box touches) =
  * (ey-sy+1) * ((ex>>S) - (sx>>S) + 1) with S = gcp_splat_seg_shift(), P = poff[n].  seg_off i32[(H+1)*(W+1)+1]
- * receives the offset of every pixel list (pixels in key order; last entry = N).  Bit-identical output. */
+ * receives the offset of every pixel list (pixels in key order; last entry = N).  Bit-identical output.
+ * key_s must be 16-byte aligned (vector stores). */
 size_t gcp_splat_place_bytes(int64_t P, int W, int H);
 int gcp_splat_set_fill_blocks(int blocks); /* tuning hook: persistent grid of the fill kernel, 0 = default */
 int gcp_splat_seg_shift(void);             /* log2 of the strip width the library was built with */

@@ -126,9 +126,12 @@ k_splat_pack(const float *__restrict__ mean, const float *__restrict__ lam, cons
 
 // one 32-byte record in one instruction (LDG.256, sm_100)
 __device__ __forceinline__ void ldg256(const void *p, int4 &u, int4 &v) {
+    // volatile + memory clobber: keeps the compiler from sinking a gather below later stores / into branches, so
+    // that several gathers issued back to back stay in flight together
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w), "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
+                 : "l"(p)
+                 : "memory");
 }
 __device__ __forceinline__ Gauss load_rec_a(const float4 *__restrict__ rec_a, int g) {
     int4 u, v;
@@ -138,7 +141,7 @@ __device__ __forceinline__ Gauss load_rec_a(const float4 *__restrict__ rec_a, in
 }
 
 // x_s[e] = 1 - o*g in sorted order (the scan's input); 4 consecutive elements per thread
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_splat_alpha(const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s,
               const float4 *__restrict__ rec_a, int64_t N, float *__restrict__ x_s) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
@@ -354,7 +357,7 @@ k_splat_bwd_grads(const float *__restrict__ incl, const float *__restrict__ x_s,
 // pixels of a box row are neighbouring pixel lists, so the scattered 8-byte stores of one tile land in
 // the same few sectors.
 //   dalpha = T <dL/dI, l> - T U   (tu = T*U from grouped_cumprod_backward);   d = T alpha <dL/dI, l>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, const float *__restrict__ tu,
                  const int32_t *__restrict__ key_s, const int32_t *__restrict__ gid_s,
                  const int4 *__restrict__ rec_b, const float *__restrict__ gimg, int64_t N, int W,
@@ -364,11 +367,12 @@ k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, 
         int k[4], g[4];
         float y[4], xx[4], t[4];
         if (e0 + 4 <= N) {
-            const int4 kk = __ldg(reinterpret_cast<const int4 *>(key_s + e0));
-            const int4 gg = __ldg(reinterpret_cast<const int4 *>(gid_s + e0));
-            const float4 yy = __ldg(reinterpret_cast<const float4 *>(incl + e0));
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_s + e0));
-            const float4 tv = __ldg(reinterpret_cast<const float4 *>(tu + e0));
+            // read-once streams: evict-first, so that the dirty lines of `elem` stay in L2 until their box is complete
+            const int4 kk = __ldcs(reinterpret_cast<const int4 *>(key_s + e0));
+            const int4 gg = __ldcs(reinterpret_cast<const int4 *>(gid_s + e0));
+            const float4 yy = __ldcs(reinterpret_cast<const float4 *>(incl + e0));
+            const float4 xv = __ldcs(reinterpret_cast<const float4 *>(x_s + e0));
+            const float4 tv = __ldcs(reinterpret_cast<const float4 *>(tu + e0));
             k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
             g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
             y[0] = yy.x; y[1] = yy.y; y[2] = yy.z; y[3] = yy.w;
@@ -387,28 +391,28 @@ k_splat_bwd_elem(const float *__restrict__ incl, const float *__restrict__ x_s, 
         int kprev = (e0 > 0) ? __ldg(key_s + e0 - 1) : -1;
         float yprev = (e0 > 0) ? __ldg(incl + e0 - 1) : 1.0f;
         int4 ra[4], rb[4];
+        float pg[4][3];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             ldg256(rec_b + 2 * static_cast<int64_t>(g[i]), ra[i], rb[i]);
+            const float *q = gimg + 3 * static_cast<int64_t>(pixel_index(max(k[i], 0), W));
+            pg[i][0] = __ldg(q); pg[i][1] = __ldg(q + 1); pg[i][2] = __ldg(q + 2);
         }
+        // branch-free per element (only the store is predicated): the four gathers above stay in flight together
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (e0 + i < N) {
-                const int py = k[i] / KEY_STRIDE, px = k[i] - py * KEY_STRIDE;
-                const int sx = ra[i].w, sy = rb[i].x, w = rb[i].y;
-                const int64_t off = (static_cast<int64_t>(rb[i].w) << 32) | static_cast<uint32_t>(rb[i].z);
-                const int64_t dst = off + static_cast<int64_t>(py - sy) * w + (px - sx);
-                float2 out = make_float2(0.0f, 0.0f);
-                if (y[i] != 0.0f) {  // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
-                    const float T = (k[i] != kprev) ? 1.0f : yprev;
-                    const float *pg = gimg + 3 * static_cast<int64_t>(py * (W + 1) + px);
-                    const float pgl = __ldg(pg) * __int_as_float(ra[i].x) + __ldg(pg + 1) * __int_as_float(ra[i].y) +
-                                      __ldg(pg + 2) * __int_as_float(ra[i].z);
-                    out.x = T * pgl - t[i];
-                    out.y = T * (1.0f - xx[i]) * pgl;
-                }
-                elem[dst] = out;
-            }
+            const int kk = max(k[i], 0);
+            const int py = kk / KEY_STRIDE, px = kk - py * KEY_STRIDE;
+            const int sx = ra[i].w, sy = rb[i].x, w = rb[i].y;
+            const int64_t off = (static_cast<int64_t>(rb[i].w) << 32) | static_cast<uint32_t>(rb[i].z);
+            const int64_t dst = off + static_cast<int64_t>(py - sy) * w + (px - sx);
+            const float T = (k[i] != kprev) ? 1.0f : yprev;
+            const float pgl = pg[i][0] * __int_as_float(ra[i].x) + pg[i][1] * __int_as_float(ra[i].y) +
+                              pg[i][2] * __int_as_float(ra[i].z);
+            // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
+            const bool alive = y[i] != 0.0f;
+            const float2 out = make_float2(alive ? T * pgl - t[i] : 0.0f, alive ? T * (1.0f - xx[i]) * pgl : 0.0f);
+            if (e0 + i < N) elem[dst] = out;
             kprev = k[i];
             yprev = y[i];
         }
@@ -733,6 +737,10 @@ k_place_keys(const int32_t *__restrict__ off, int npix, int W, int32_t *__restri
 }
 
 // one warp per (row, strip) cell at a time: walk the cell's intervals in Gaussian (depth) order.
+// Lane l owns pixels l, l+32, ... of the strip: list offset and running count live in REGISTERS, so an interval
+// costs three shuffles and a predicated store per owned pixel — no shared-memory read-modify-write chain between
+// consecutive intervals (that chain, not the store traffic, bounded the shared-memory-counter version; a FIFO
+// that merged eight appends into one 32-byte store was slower still).
 // The grid is persistent and small on purpose (see gcp_splat_place): cells are taken in index order, so the
 // lists being filled at any moment form one compact address window that stays in L2 until every 32-byte
 // sector is complete — the 4-byte scattered stores then cost no DRAM read-modify-write.
@@ -740,42 +748,49 @@ __global__ void __launch_bounds__(256)
 k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pgid_s,
              const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int32_t *__restrict__ off,
              int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s) {
-    __shared__ int32_t sm[8][2 * SEGW];
+    constexpr int PPL = SEGW / 32;  // pixels per lane
+    static_assert(SEGW % 32 == 0, "strip width must be a multiple of the warp size");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int ncell = (H + 1) * nseg;
-    int32_t *c = sm[wib];      // running counter per pixel of the strip
-    int32_t *o = c + SEGW;     // list offset per pixel
     for (int cell = blockIdx.x * 8 + wib; cell < ncell; cell += gridDim.x * 8) {
         const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
         const int x1 = min(W, x0 + SEGW - 1);
-        for (int i = lane; i < SEGW; i += 32) {
-            c[i] = 0;
-            o[i] = (x0 + i <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x0 + i) : 0;
+        int32_t *dst[PPL];  // next free slot of the owned pixels' lists
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int x = x0 + lane + 32 * q;
+            dst[q] = gid_s + ((x <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x) : 0);
         }
-        __syncwarp();
         int64_t lo, hi;
         cell_range(pcell_s, P, cell, lo, hi);
+        // intervals in batches of 32 (one per lane); the next batch is in flight while this one is walked
+        int g = 0, a = 0, z = -1;
+        if (lo + lane < hi) {
+            g = __ldg(pgid_s + lo + lane);
+            a = max(__ldg(sp + 2 * g), x0) - x0;
+            z = min(__ldg(ep + 2 * g), x1) - x0;
+        }
         for (int64_t b = lo; b < hi; b += 32) {
-            int g = 0, a = 0, z = -1;
-            if (b + lane < hi) {
-                g = __ldg(pgid_s + b + lane);
-                a = max(__ldg(sp + 2 * g), x0) - x0;
-                z = min(__ldg(ep + 2 * g), x1) - x0;
+            int gn = 0, an = 0, zn = -1;
+            if (b + 32 + lane < hi) {
+                gn = __ldg(pgid_s + b + 32 + lane);
+                an = max(__ldg(sp + 2 * gn), x0) - x0;
+                zn = min(__ldg(ep + 2 * gn), x1) - x0;
             }
             const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
+#pragma unroll 4
             for (int k = 0; k < m; ++k) {
                 const int gg = __shfl_sync(0xffffffffu, g, k);
                 const int ia = __shfl_sync(0xffffffffu, a, k);
                 const int iz = __shfl_sync(0xffffffffu, z, k);
-                for (int i = ia + lane; i <= iz; i += 32) {
-                    const int r = c[i];
-                    c[i] = r + 1;
-                    gid_s[o[i] + r] = gg;
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const int i = lane + 32 * q;
+                    if (i >= ia && i <= iz) *dst[q]++ = gg;
                 }
-                __syncwarp();
             }
+            g = gn; a = an; z = zn;
         }
-        __syncwarp();
     }
 }
 
@@ -976,6 +991,7 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
                     gcp_stream_t stream) {
     if (n < 0 || P < 0 || W < 0 || H < 0 || W >= KEY_STRIDE) return GCP_ERR_INVALID_ARG;
     if (!seg_off || !temp) return GCP_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(key_s) & 15) return GCP_ERR_INVALID_ARG;
     const PlaceLayout L = place_layout(P, W, H);
     if (temp_bytes < L.total) return GCP_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
