@@ -436,9 +436,20 @@ struct RedAcc {
     float o = 0.f, d = 0.f, m0 = 0.f, m1 = 0.f, a00 = 0.f, a01 = 0.f, a11 = 0.f;
 };
 
-__device__ __forceinline__ void red_add(RedAcc &A, const float2 v, const int local, const int w, const int sx,
-                                        const int sy, const Gauss &G) {
-    const int iy = local / w, ix = local - iy * w;
+// inv_w = 1/w in float: (local + 0.5) * inv_w truncates to local / w for local < 2^21 (the +-1 fix-up below covers
+// the rounding of inv_w); larger boxes take the integer division
+__device__ __forceinline__ void red_add(RedAcc &A, const float2 v, const int local, const int w, const float inv_w,
+                                        const int sx, const int sy, const Gauss &G) {
+    int iy, ix;
+    if (local < (1 << 21)) {
+        iy = __float2int_rz((static_cast<float>(local) + 0.5f) * inv_w);
+        ix = local - iy * w;
+        if (ix < 0) { ix += w; --iy; }
+        if (ix >= w) { ix -= w; ++iy; }
+    } else {
+        iy = local / w;
+        ix = local - iy * w;
+    }
     const float d0 = static_cast<float>(sx + ix) - G.mx, d1 = static_cast<float>(sy + iy) - G.my;
     const float X0 = d0 * G.l00 + d1 * G.l10, X1 = d0 * G.l01 + d1 * G.l11;
     const float gk = expf(-0.5f * (X0 * d0 + X1 * d1));
@@ -515,15 +526,10 @@ k_splat_bwd_reduce(const float2 *__restrict__ elem, const int32_t *__restrict__ 
         const Gauss G = load_gauss(mean, lam, opac, static_cast<int>(gg));
         const int sx = __ldg(sp + 2 * gg), sy = __ldg(sp + 2 * gg + 1);
         const int w = __ldg(ep + 2 * gg) - sx + 1;
+        const float inv_w = 1.0f / static_cast<float>(w);
         RedAcc A;
-        for (int64_t e = b + sub; e < eend; e += 4 * GL) {  // four loads in flight per lane
-            float2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (e + u * GL < eend) ? __ldg(elem + e + u * GL) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (e + u * GL < eend) red_add(A, v[u], static_cast<int>(e + u * GL - b), w, sx, sy, G);
-        }
+        for (int64_t e = b + sub; e < eend; e += GL)
+            red_add(A, __ldg(elem + e), static_cast<int>(e - b), w, inv_w, sx, sy, G);
         red_lanes<GL>(A);
         if (live && !big && sub == 0) red_store(A, g, l_d, g_mean, g_lam, g_opac, g_l);
     }
@@ -547,15 +553,11 @@ k_splat_bwd_reduce_pieces(const float2 *__restrict__ elem, const int32_t *__rest
         const Gauss G = load_gauss(mean, lam, opac, g);
         const int sx = __ldg(sp + 2 * g), sy = __ldg(sp + 2 * g + 1);
         const int w = __ldg(ep + 2 * g) - sx + 1;
+        const float inv_w = 1.0f / static_cast<float>(w);
         RedAcc A;
-        for (int64_t e = b + lane; e < eend; e += 4 * 32) {
-            float2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (e + u * 32 < eend) ? __ldg(elem + e + u * 32) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (e + u * 32 < eend) red_add(A, v[u], static_cast<int>(e + u * 32 - g0), w, sx, sy, G);
-        }
+#pragma unroll 4
+        for (int64_t e = b + lane; e < eend; e += 32)
+            red_add(A, __ldg(elem + e), static_cast<int>(e - g0), w, inv_w, sx, sy, G);
         red_lanes<32>(A);
         if (lane == 0) {
             partial[2 * static_cast<size_t>(p)] = make_float4(A.o, A.d, A.m0, A.m1);
@@ -693,7 +695,7 @@ k_place_count(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ p
 // key_s from the pixel-list offsets: streaming, coalesced (the fill below then scatters only the Gaussian ids).
 // One block per 256 consecutive pixels (image order = key order): its elements form one contiguous range.
 __global__ void __launch_bounds__(256)
-k_place_keys(const int32_t *__restrict__ off, int npix, int W, int32_t *__restrict__ key_s) {
+k_place_keys_short(const int32_t *__restrict__ off, int npix, int W, int32_t *__restrict__ key_s) {
     __shared__ int32_t so[257];
     __shared__ int32_t sk[256];
     const int p0 = blockIdx.x * 256;
@@ -733,6 +735,25 @@ k_place_keys(const int32_t *__restrict__ off, int npix, int W, int32_t *__restri
             for (int i = 0; i < 4; ++i)
                 if (e0 + i >= lo && e0 + i < hi) key_s[e0 + i] = v[i];
         }
+    }
+}
+
+// long lists (hundreds of elements per pixel, C2): one warp per 32 consecutive pixels, each list in turn is
+// written by the whole warp
+__global__ void __launch_bounds__(256)
+k_place_keys_long(const int32_t *__restrict__ off, int npix, int W, int32_t *__restrict__ key_s) {
+    const int lane = threadIdx.x & 31;
+    const int p0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+    if (p0 >= npix) return;
+    const int p = min(p0 + lane, npix - 1);
+    const int st = __ldg(off + p), en = (p0 + lane < npix) ? __ldg(off + p + 1) : st;
+    const int y = p / (W + 1);
+    const int key = y * KEY_STRIDE + (p - y * (W + 1));
+    const int cnt = min(32, npix - p0);
+    for (int j = 0; j < cnt; ++j) {
+        const int s = __shfl_sync(0xffffffffu, st, j), e = __shfl_sync(0xffffffffu, en, j);
+        const int k = __shfl_sync(0xffffffffu, key, j);
+        for (int i = s + lane; i < e; i += 32) key_s[i] = k;
     }
 }
 
@@ -1019,8 +1040,12 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
     // persistent, ~3500 warps: the lists under construction (~10 KB per cell) stay inside the 126 MB L2
     const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 444u;
     unsigned fill_blocks = blocks < cap ? blocks : cap;
-    k_place_keys<<<static_cast<unsigned>((npix - 1 + 255) / 256), 256, 0, s>>>(seg_off, static_cast<int>(npix - 1), W,
-                                                                              key_s);
+    // short lists: per-element search inside 256-pixel blocks; long lists (>= 8 intervals per pixel): warp per list
+    const unsigned key_blocks = static_cast<unsigned>((npix - 1 + 255) / 256);
+    if (P / (npix - 1) >= 8)
+        k_place_keys_long<<<key_blocks, 256, 0, s>>>(seg_off, static_cast<int>(npix - 1), W, key_s);
+    else
+        k_place_keys_short<<<key_blocks, 256, 0, s>>>(seg_off, static_cast<int>(npix - 1), W, key_s);
     k_place_fill<<<fill_blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
     return static_cast<int>(cudaGetLastError());
 }
