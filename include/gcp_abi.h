@@ -151,6 +151,9 @@ int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_ou
  * key_s must be 16-byte aligned (vector stores). */
 size_t gcp_splat_place_bytes(int64_t P, int W, int H);
 int gcp_splat_set_fill_blocks(int blocks); /* tuning hook: persistent grid of the fill kernel, 0 = default */
+/* tuning hook: from this many (cell, Gaussian) pairs per pixel (P / pixels) on, lists count as long and the
+ * warp-per-list key kernel and the transposed, ballot-compacting fill are used (default 8) */
+int gcp_splat_set_long_list_threshold(int pairs_per_pixel);
 int gcp_splat_seg_shift(void);             /* log2 of the strip width the library was built with */
 int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, int64_t n, int64_t P, int W, int H,
                     int32_t *key_s, int32_t *gid_s, int32_t *seg_off, void *temp, size_t temp_bytes,

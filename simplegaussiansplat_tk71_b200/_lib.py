@@ -27,7 +27,7 @@ SYMBOLS = (
     "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
     "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_pack", "gcp_splat_alpha", "gcp_splat_color",
     "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce", "gcp_splat_bwd_reduce_bytes",
-    "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_seg_shift",
+    "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_set_long_list_threshold", "gcp_splat_seg_shift",
 )
 
 
@@ -77,6 +77,8 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_place.restype = ci
     L.gcp_splat_set_fill_blocks.argtypes = [ci]
     L.gcp_splat_set_fill_blocks.restype = ci
+    L.gcp_splat_set_long_list_threshold.argtypes = [ci]
+    L.gcp_splat_set_long_list_threshold.restype = ci
     L.gcp_splat_seg_shift.restype = ci
     L.gcp_splat_bwd_elem.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp]
     L.gcp_splat_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]

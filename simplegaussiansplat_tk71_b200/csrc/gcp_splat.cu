@@ -636,28 +636,20 @@ k_place_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, co
     }
 }
 
-// [lo, hi) of one cell inside the cell-sorted pair list
-__device__ __forceinline__ void cell_range(const int32_t *__restrict__ pcell_s, int64_t P, int cell, int64_t &lo,
-                                           int64_t &hi) {
-    int64_t a = 0, b = P;
-    while (a < b) {
-        const int64_t m = (a + b) >> 1;
-        if (__ldg(pcell_s + m) < cell) a = m + 1;
-        else b = m;
-    }
-    lo = a;
-    b = P;
-    while (a < b) {
-        const int64_t m = (a + b) >> 1;
-        if (__ldg(pcell_s + m) <= cell) a = m + 1;
-        else b = m;
-    }
-    hi = a;
+// cstart[c] = first pair of cell c inside the cell-sorted pair list (cstart[ncell] = P): one thread per pair
+// writes the entries of every cell that begins at its position (empty cells included)
+__global__ void __launch_bounds__(256)
+k_place_cellstart(const int32_t *__restrict__ pcell_s, int64_t P, int ncell, int32_t *__restrict__ cstart) {
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    const int prev = (p == 0) ? -1 : __ldg(pcell_s + p - 1);
+    const int cur = (p == P) ? ncell : __ldg(pcell_s + p);
+    for (int c = prev + 1; c <= cur; ++c) cstart[c] = static_cast<int32_t>(p);
 }
 
 // one warp per (row, strip) cell: per-pixel list lengths from a shared-memory difference array
 __global__ void __launch_bounds__(256)
-k_place_count(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pgid_s,
+k_place_count(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgid_s,
               const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t P, int W, int H, int nseg,
               int32_t *__restrict__ cnt) {
     __shared__ int32_t sm[8][SEGW + 1];
@@ -669,8 +661,7 @@ k_place_count(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ p
     int32_t *c = sm[wib];
     for (int i = lane; i <= SEGW; i += 32) c[i] = 0;
     __syncwarp();
-    int64_t lo, hi;
-    cell_range(pcell_s, P, cell, lo, hi);
+    const int64_t lo = __ldg(cstart + cell), hi = __ldg(cstart + cell + 1);
     for (int64_t p = lo + lane; p < hi; p += 32) {
         const int g = __ldg(pgid_s + p);
         atomicAdd(c + (max(__ldg(sp + 2 * g), x0) - x0), 1);
@@ -766,7 +757,7 @@ k_place_keys_long(const int32_t *__restrict__ off, int npix, int W, int32_t *__r
 // lists being filled at any moment form one compact address window that stays in L2 until every 32-byte
 // sector is complete — the 4-byte scattered stores then cost no DRAM read-modify-write.
 __global__ void __launch_bounds__(256)
-k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pgid_s,
+k_place_fill(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgid_s,
              const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int32_t *__restrict__ off,
              int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s) {
     constexpr int PPL = SEGW / 32;  // pixels per lane
@@ -776,28 +767,24 @@ k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pg
     for (int cell = blockIdx.x * 8 + wib; cell < ncell; cell += gridDim.x * 8) {
         const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
         const int x1 = min(W, x0 + SEGW - 1);
+        const int64_t lo = __ldg(cstart + cell), hi = __ldg(cstart + cell + 1);
         int32_t *dst[PPL];  // next free slot of the owned pixels' lists
 #pragma unroll
         for (int q = 0; q < PPL; ++q) {
             const int x = x0 + lane + 32 * q;
             dst[q] = gid_s + ((x <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x) : 0);
         }
-        int64_t lo, hi;
-        cell_range(pcell_s, P, cell, lo, hi);
-        // intervals in batches of 32 (one per lane); the next batch is in flight while this one is walked
-        int g = 0, a = 0, z = -1;
-        if (lo + lane < hi) {
-            g = __ldg(pgid_s + lo + lane);
-            a = max(__ldg(sp + 2 * g), x0) - x0;
-            z = min(__ldg(ep + 2 * g), x1) - x0;
-        }
+        // intervals in batches of 32 (one per lane), software-pipelined two deep: the ids of batch b+2 and the box
+        // columns of batch b+1 are in flight while batch b is walked (the columns depend on the ids)
+        int g = 0, g1 = 0, rs = KEY_STRIDE, re = -1;
+        if (lo + lane < hi) g = __ldg(pgid_s + lo + lane);
+        if (lo + 32 + lane < hi) g1 = __ldg(pgid_s + lo + 32 + lane);
+        if (lo + lane < hi) { rs = __ldg(sp + 2 * g); re = __ldg(ep + 2 * g); }
         for (int64_t b = lo; b < hi; b += 32) {
-            int gn = 0, an = 0, zn = -1;
-            if (b + 32 + lane < hi) {
-                gn = __ldg(pgid_s + b + 32 + lane);
-                an = max(__ldg(sp + 2 * gn), x0) - x0;
-                zn = min(__ldg(ep + 2 * gn), x1) - x0;
-            }
+            const int a = max(rs, x0) - x0, z = min(re, x1) - x0;
+            int g2 = 0, rs1 = KEY_STRIDE, re1 = -1;
+            if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
+            if (b + 32 + lane < hi) { rs1 = __ldg(sp + 2 * g1); re1 = __ldg(ep + 2 * g1); }
             const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
 #pragma unroll 4
             for (int k = 0; k < m; ++k) {
@@ -810,7 +797,62 @@ k_place_fill(const int32_t *__restrict__ pcell_s, const int32_t *__restrict__ pg
                     if (i >= ia && i <= iz) *dst[q]++ = gg;
                 }
             }
-            g = gn; a = an; z = zn;
+            g = g1; g1 = g2; rs = rs1; re = re1;
+        }
+    }
+}
+
+// Long lists (hundreds of elements per pixel, wide boxes — the bundled scene, C2): the scattered stores of the
+// kernel above, one 4-byte request per element, saturate the load/store path.  Transposed walk instead: the
+// lanes hold 32 intervals of the cell; for every pixel of the strip in turn, the intervals covering it are
+// compacted with a ballot and written as one contiguous run.  Same output, coalesced stores.
+__global__ void __launch_bounds__(256)
+k_place_fill_long(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgid_s,
+                  const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int32_t *__restrict__ off,
+                  int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s, unsigned int *__restrict__ ticket) {
+    constexpr int PPL = SEGW / 32;
+    const int lane = threadIdx.x & 31;
+    const int ncell = (H + 1) * nseg;
+    const unsigned lt = (1u << lane) - 1u;
+    for (;;) {
+        // cells are handed out dynamically (their sizes differ by an order of magnitude)
+        int cell = 0;
+        if (lane == 0) cell = static_cast<int>(atomicAdd(ticket, 1u));
+        cell = __shfl_sync(0xffffffffu, cell, 0);
+        if (cell >= ncell) break;
+        const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
+        const int x1 = min(W, x0 + SEGW - 1);
+        const int64_t lo = __ldg(cstart + cell), hi = __ldg(cstart + cell + 1);
+        int pos[PPL];  // next free slot of the owned pixels' lists (lane l owns pixels l, l+32, ...)
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int x = x0 + lane + 32 * q;
+            pos[q] = (x <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x) : 0;
+        }
+        int g = 0, g1 = 0, rs = KEY_STRIDE, re = -1;
+        if (lo + lane < hi) g = __ldg(pgid_s + lo + lane);
+        if (lo + 32 + lane < hi) g1 = __ldg(pgid_s + lo + 32 + lane);
+        if (lo + lane < hi) { rs = __ldg(sp + 2 * g); re = __ldg(ep + 2 * g); }
+        for (int64_t b = lo; b < hi; b += 32) {
+            const int a = max(rs, x0) - x0, z = min(re, x1) - x0;  // empty (a > z) for lanes past the end
+            int g2 = 0, rs1 = KEY_STRIDE, re1 = -1;
+            if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
+            if (b + 32 + lane < hi) { rs1 = __ldg(sp + 2 * g1); re1 = __ldg(ep + 2 * g1); }
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                int add = 0;  // elements appended to the pixel this lane owns
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const int i = 32 * q + j;
+                    const bool cov = (a <= i) && (i <= z);
+                    const unsigned m = __ballot_sync(0xffffffffu, cov);
+                    const int base = __shfl_sync(0xffffffffu, pos[q], j);
+                    if (cov) gid_s[base + __popc(m & lt)] = g;
+                    if (lane == j) add = __popc(m);
+                }
+                pos[q] += add;
+            }
+            g = g1; g1 = g2; rs = rs1; re = re1;
         }
     }
 }
@@ -971,8 +1013,9 @@ int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep
 // ---- sort-free placement -------------------------------------------------------------------------
 namespace {
 int g_fill_blocks = 0;  // tuning: size of the persistent k_place_fill grid (0 = default)
+int g_long_min = 8;     // tuning: pairs per pixel from which the long-list kernels are used
 struct PlaceLayout {
-    size_t prow, pgid, prow_s, pgid_s, cnt, cub, total;
+    size_t prow, pgid, prow_s, pgid_s, cnt, cstart, cub, total;
     size_t cub_bytes;
 };
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -992,7 +1035,9 @@ PlaceLayout place_layout(int64_t P, int W, int H) {
     L.prow_s = L.pgid + pb;
     L.pgid_s = L.prow_s + pb;
     L.cnt = L.pgid_s + pb;
-    L.cub = L.cnt + align256(npix * 4);
+    L.cstart = L.cnt + align256(npix * 4);  // cells + 1 offsets, then one ticket word
+    const size_t ncell = static_cast<size_t>(H + 1) * ((W + SEGW) >> SEG_SHIFT);
+    L.cub = L.cstart + align256((ncell + 2) * 4);
     L.total = L.cub + L.cub_bytes;
     return L;
 }
@@ -1004,6 +1049,12 @@ int gcp_splat_seg_shift(void) { return SEG_SHIFT; }
 
 int gcp_splat_set_fill_blocks(int blocks) {
     g_fill_blocks = blocks;
+    return GCP_OK;
+}
+
+int gcp_splat_set_long_list_threshold(int pairs_per_pixel) {
+    if (pairs_per_pixel < 0) return GCP_ERR_INVALID_ARG;
+    g_long_min = pairs_per_pixel;
     return GCP_OK;
 }
 
@@ -1030,23 +1081,34 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
         e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, prow, prow_s, pgid, pgid_s, P, 0, key_bits(cells), s);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
+    int32_t *cstart = reinterpret_cast<int32_t *>(t + L.cstart);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(cstart + cells + 1);
+    k_place_cellstart<<<blocks_for(P + 1, 256), 256, 0, s>>>(prow_s, P, cells, cstart);
     const unsigned blocks = static_cast<unsigned>((cells + 7) / 8);
-    k_place_count<<<blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, P, W, H, nseg, cnt);
+    k_place_count<<<blocks, 256, 0, s>>>(cstart, pgid_s, sp, ep, P, W, H, nseg, cnt);
     e = cudaMemsetAsync(cnt + (npix - 1), 0, 4, s);  // sentinel: the scan's last output is the element count
     if (e != cudaSuccess) return static_cast<int>(e);
     size_t cb = L.cub_bytes;
     e = cub::DeviceScan::ExclusiveSum(t + L.cub, cb, cnt, seg_off, npix, s);
     if (e != cudaSuccess) return static_cast<int>(e);
     // persistent, ~3500 warps: the lists under construction (~10 KB per cell) stay inside the 126 MB L2
-    const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 444u;
+    const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 222u;
     unsigned fill_blocks = blocks < cap ? blocks : cap;
     // short lists: per-element search inside 256-pixel blocks; long lists (>= 8 intervals per pixel): warp per list
     const unsigned key_blocks = static_cast<unsigned>((npix - 1 + 255) / 256);
-    if (P / (npix - 1) >= 8)
+    const bool long_lists = P / (npix - 1) >= g_long_min;
+    if (long_lists)
         k_place_keys_long<<<key_blocks, 256, 0, s>>>(seg_off, static_cast<int>(npix - 1), W, key_s);
     else
         k_place_keys_short<<<key_blocks, 256, 0, s>>>(seg_off, static_cast<int>(npix - 1), W, key_s);
-    k_place_fill<<<fill_blocks, 256, 0, s>>>(prow_s, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
+    if (long_lists) {
+        e = cudaMemsetAsync(ticket, 0, 4, s);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        k_place_fill_long<<<std::min(blocks, 148u * 8u), 256, 0, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg,
+                                                                      gid_s, ticket);
+    } else {
+        k_place_fill<<<fill_blocks, 256, 0, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
+    }
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -135,6 +135,25 @@ def test_placement_equals_sort_on_a_1080p_scene_gpu(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_placement_equals_sort_on_long_pixel_lists_gpu(monkeypatch):
+    """Bundled-scene view (C2): per-pixel lists of hundreds of elements take the transposed (ballot-compacting)
+    fill and the warp-per-list key kernel; the result must still be the stable sort, bit for bit."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+
+    v = wl.bundled_views("cuda", n_views=3)[2]
+    outs = []
+    for placement in (True, False):
+        monkeypatch.setattr(compositor, "USE_PLACEMENT", placement)
+        img, view = compositor._render_forward(v.boxsize, v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity,
+                                               v.l_d, v.width, v.height)
+        outs.append((view.key_s.clone(), view.gid_s.clone(), img))
+        del view
+    assert outs[0][0].numel() == v.elements
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-5)   # colour sums use float atomics
+
+
+@pytest.mark.gpu
 def test_native_compositor_matches_oracle_on_a_larger_scene_gpu():
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))

@@ -13,3 +13,10 @@ compositor.USE_PLACEMENT=False; print("expand+sort fwd ms", round(t_fwd(),3))
 compositor.USE_PLACEMENT=True
 for blocks in (37, 74, 148, 222, 296, 444, 592, 1184):
     L.gcp_splat_set_fill_blocks(blocks); print("placement fill_blocks", blocks, "fwd ms", round(t_fwd(),3))
+L.gcp_splat_set_fill_blocks(0)
+for thr in (8, 0):  # 0 = long-list kernels (warp-per-list keys, transposed fill) forced on the 1080p scene
+    L.gcp_splat_set_long_list_threshold(thr); print("long-list threshold", thr, "fwd ms", round(t_fwd(), 3))
+L.gcp_splat_set_long_list_threshold(8)
+v = wl.bundled_views("cuda")[1]
+for thr in (8, 1 << 20):  # 1<<20 = short-list kernels forced on the bundled scene
+    L.gcp_splat_set_long_list_threshold(thr); print("bundled scene: long-list threshold", thr, "fwd ms", round(t_fwd(), 3))
