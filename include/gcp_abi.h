@@ -156,8 +156,16 @@ int gcp_splat_set_fill_blocks(int blocks); /* tuning hook: persistent grid of th
 int gcp_splat_set_long_list_threshold(int pairs_per_pixel);
 int gcp_splat_seg_shift(void);             /* log2 of the strip width the library was built with */
 int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, int64_t n, int64_t P, int W, int H,
-                    int32_t *key_s, int32_t *gid_s, int32_t *seg_off, void *temp, size_t temp_bytes,
-                    gcp_stream_t stream);
+                    int32_t *key_s, int32_t *gid_s, int32_t *seg_off, int32_t *cell_start, int32_t *pair_gid,
+                    int32_t *batch_table, void *temp, size_t temp_bytes, gcp_stream_t stream);
+/* Optional outputs (NULL: not kept) that gcp_splat_bwd_elem_cells needs in the backward of a long-list view:
+ * cell_start i32[gcp_splat_num_cells(W,H)+1] and pair_gid i32[P] = the (cell, Gaussian) pair list sorted by cell;
+ * batch_table i32[gcp_splat_batch_table_ints(P,W,H)] = per batch of 32 pairs of a cell: cell, first pair, and the
+ * list position of each of the strip's pixels at the start of the batch (written only when
+ * gcp_splat_long_lists(P,W,H)). */
+int64_t gcp_splat_batch_table_ints(int64_t P, int W, int H);
+int gcp_splat_num_cells(int W, int H);
+int gcp_splat_long_lists(int64_t P, int W, int H); /* 1 if the long-list kernels are selected for this view */
 
 /* The per-Gaussian tables packed into two 32-byte records per Gaussian (both arrays 32-byte aligned), so that
  * every per-element gather of the kernels below is a single L2 sector:
@@ -193,6 +201,13 @@ int gcp_splat_bwd_w(const float *incl, const float *x_s, const int32_t *key_s, c
 int gcp_splat_bwd_elem(const float *incl, const float *x_s, const float *tu, const int32_t *key_s,
                        const int32_t *gid_s, const int32_t *rec_b, const float *grad_image, int64_t N, int W,
                        float *elem, gcp_stream_t stream);
+/* Same result as gcp_splat_bwd_elem for views with long pixel lists (gcp_splat_long_lists): the un-sort as a
+ * shared-memory transposition over the placement's batches, every global access coalesced.  seg_off,
+ * cell_start, pair_gid, batch_table: outputs of gcp_splat_place for the same view. */
+int gcp_splat_bwd_elem_cells(const float *incl, const float *x_s, const float *tu, const int32_t *rec_b,
+                             const float *grad_image, const int32_t *seg_off, const int32_t *cell_start,
+                             const int32_t *pair_gid, const int32_t *batch_table, int64_t P, int W, int H,
+                             float *elem, gcp_stream_t stream);
 size_t gcp_splat_bwd_reduce_bytes(int64_t N, int64_t n);
 int gcp_splat_bwd_reduce(const float *elem, const int32_t *sp, const int32_t *ep, const int64_t *goff,
                          const float *mean, const float *lam, const float *opac, const float *l_d, int64_t N,

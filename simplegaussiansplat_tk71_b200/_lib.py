@@ -28,6 +28,7 @@ SYMBOLS = (
     "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_pack", "gcp_splat_alpha", "gcp_splat_color",
     "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce", "gcp_splat_bwd_reduce_bytes",
     "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_set_long_list_threshold", "gcp_splat_seg_shift",
+    "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
 )
 
 
@@ -73,7 +74,15 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_bwd_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, vp, vp, vp, vp, vp]
     L.gcp_splat_place_bytes.argtypes = [i64, ci, ci]
     L.gcp_splat_place_bytes.restype = sz
-    L.gcp_splat_place.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, sz, vp]
+    L.gcp_splat_place.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.gcp_splat_batch_table_ints.argtypes = [i64, ci, ci]
+    L.gcp_splat_batch_table_ints.restype = i64
+    L.gcp_splat_num_cells.argtypes = [ci, ci]
+    L.gcp_splat_num_cells.restype = ci
+    L.gcp_splat_long_lists.argtypes = [i64, ci, ci]
+    L.gcp_splat_long_lists.restype = ci
+    L.gcp_splat_bwd_elem_cells.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
+    L.gcp_splat_bwd_elem_cells.restype = ci
     L.gcp_splat_place.restype = ci
     L.gcp_splat_set_fill_blocks.argtypes = [ci]
     L.gcp_splat_set_fill_blocks.restype = ci

@@ -72,7 +72,7 @@ def _scratch_bytes(dev, tag: str, nbytes: int) -> torch.Tensor:
 class _View:
     """Device state of one rendered view kept for the backward (16 B per element + the per-Gaussian tables)."""
     __slots__ = ("n", "N", "W", "H", "key_s", "gid_s", "x_s", "incl", "mean", "lam", "opac", "l_d", "sp", "ep",
-                 "goff", "rec_a", "rec_b")
+                 "goff", "rec_a", "rec_b", "seg_off", "cstart", "pgid", "btab", "P")
 
 
 def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
@@ -82,6 +82,8 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
     L = _lib.lib()
     v = _View()
     v.W, v.H = W, H
+    v.seg_off = v.cstart = v.pgid = v.btab = None
+    v.P = 0
     n = boxsize.numel()
     v.n = n
     with torch.cuda.device(dev):
@@ -122,8 +124,18 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
         if USE_PLACEMENT:
             seg_off = torch.empty((H + 1) * (W + 1) + 1, dtype=torch.int32, device=dev)
             temp = _scratch_bytes(dev, "place", int(L.gcp_splat_place_bytes(P, W, H)))
+            if L.gcp_splat_long_lists(P, W, H):
+                # long pixel lists: the backward walks the placement's cells again, keep the pair list with the view
+                v.seg_off = seg_off
+                v.cstart = torch.empty(int(L.gcp_splat_num_cells(W, H)) + 1, dtype=torch.int32, device=dev)
+                v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+                v.btab = torch.empty(int(L.gcp_splat_batch_table_ints(P, W, H)), dtype=torch.int32, device=dev)
+                v.P = P
+                cs, pg, bt = _p(v.cstart), _p(v.pgid), _p(v.btab)
+            else:
+                cs = pg = bt = None
             _lib.check(L.gcp_splat_place(_p(sp), _p(ep), _p(poff), n, P, W, H, _p(v.key_s), _p(v.gid_s), _p(seg_off),
-                                         _p(temp), temp.numel(), stream), "gcp_splat_place")
+                                         cs, pg, bt, _p(temp), temp.numel(), stream), "gcp_splat_place")
             del temp, seg_off
         else:
             key = torch.empty(N, dtype=torch.int32, device=dev)
@@ -168,8 +180,13 @@ def _render_backward(v: _View, grad_image):
                                      torch.empty(0, dtype=torch.int32, device=dev))
         elem = gshift.new_empty((v.N, 2))
         del gshift
-        _lib.check(L.gcp_splat_bwd_elem(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.rec_b), _p(gI),
-                                        v.N, v.W, _p(elem), stream), "gcp_splat_bwd_elem")
+        if v.pgid is not None:
+            _lib.check(L.gcp_splat_bwd_elem_cells(_p(v.incl), _p(v.x_s), _p(tu), _p(v.rec_b), _p(gI), _p(v.seg_off),
+                                                  _p(v.cstart), _p(v.pgid), _p(v.btab), v.P, v.W, v.H, _p(elem),
+                                                  stream), "gcp_splat_bwd_elem_cells")
+        else:
+            _lib.check(L.gcp_splat_bwd_elem(_p(v.incl), _p(v.x_s), _p(tu), _p(v.key_s), _p(v.gid_s), _p(v.rec_b),
+                                            _p(gI), v.N, v.W, _p(elem), stream), "gcp_splat_bwd_elem")
         temp = _scratch_bytes(dev, "reduce", int(L.gcp_splat_bwd_reduce_bytes(v.N, n)))
         _lib.check(L.gcp_splat_bwd_reduce(_p(elem), _p(v.sp), _p(v.ep), _p(v.goff), _p(v.mean), _p(v.lam),
                                           _p(v.opac), _p(v.l_d), v.N, n, _p(g_mean), _p(g_lam), _p(g_opac),

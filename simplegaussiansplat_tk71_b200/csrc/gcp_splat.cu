@@ -809,7 +809,8 @@ k_place_fill(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgi
 __global__ void __launch_bounds__(256)
 k_place_fill_long(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgid_s,
                   const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int32_t *__restrict__ off,
-                  int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s, unsigned int *__restrict__ ticket) {
+                  int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s, unsigned int *__restrict__ ticket,
+                  int32_t *__restrict__ btab, int64_t nslot) {
     constexpr int PPL = SEGW / 32;
     const int lane = threadIdx.x & 31;
     const int ncell = (H + 1) * nseg;
@@ -838,6 +839,17 @@ k_place_fill_long(const int32_t *__restrict__ cstart, const int32_t *__restrict_
             int g2 = 0, rs1 = KEY_STRIDE, re1 = -1;
             if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
             if (b + 32 + lane < hi) { rs1 = __ldg(sp + 2 * g1); re1 = __ldg(ep + 2 * g1); }
+            if (btab != nullptr) {
+                // batch table for the backward (gcp_splat_bwd_elem_cells): slot -> cell, first pair, list positions
+                // at the start of the batch.  slot = b/32 + cell is unique and increasing along the pair list.
+                const int64_t slot = (b >> 5) + cell;
+                if (lane == 0) {
+                    btab[slot] = cell;
+                    btab[nslot + slot] = static_cast<int32_t>(b);
+                }
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) btab[2 * nslot + slot * SEGW + lane + 32 * q] = pos[q];
+            }
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
                 int add = 0;  // elements appended to the pixel this lane owns
@@ -853,6 +865,111 @@ k_place_fill_long(const int32_t *__restrict__ cstart, const int32_t *__restrict_
                 pos[q] += add;
             }
             g = g1; g1 = g2; rs = rs1; re = re1;
+        }
+    }
+}
+
+// Backward step 1 for LONG pixel lists (C2): the un-sort as a transposition through shared memory, every global
+// access coalesced.  The per-element version above issues one scattered 8-byte store (and one 32-byte gather)
+// per element, and the request rate of scattered accesses bounds it.  Here a warp walks a (row, strip) cell of
+// the forward placement again: its lanes hold 32 of the cell's (Gaussian, interval) pairs — box, colour and
+// Gaussian-major row address in registers, loaded once per pair instead of once per element.
+//   read phase : for every pixel of a 32-pixel half strip, the pairs covering it are compacted with a ballot —
+//                they are exactly the next elements of that pixel's list, in order — so incl / x / T*U are read
+//                as contiguous runs; (dalpha, d) goes to a padded shared-memory tile [pair][pixel];
+//   write phase: for every pair, the lanes run along its pixels and store the row segment of the Gaussian-major
+//                array elem as one contiguous run.
+// Same values as k_splat_bwd_elem, bit for bit (same expressions).
+constexpr int BEL_WARPS = 8;
+constexpr int BEL_STRIDE = 33;  // float2 entries per tile row: odd -> conflict-free column writes and row reads
+
+__global__ void __launch_bounds__(BEL_WARPS * 32)
+k_splat_bwd_elem_cells(const float *__restrict__ incl, const float *__restrict__ x_s, const float *__restrict__ tu,
+                       const int4 *__restrict__ rec_b, const float *__restrict__ gimg,
+                       const int32_t *__restrict__ off, const int32_t *__restrict__ cstart,
+                       const int32_t *__restrict__ pgid_s, const int32_t *__restrict__ btab, int64_t nslot, int W,
+                       int nseg, float2 *__restrict__ elem) {
+    extern __shared__ float2 bel_tiles[];
+    constexpr int PPL = SEGW / 32;
+    const int lane = threadIdx.x & 31;
+    float2 *tile = bel_tiles + (threadIdx.x >> 5) * (32 * BEL_STRIDE);
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t nwarp = static_cast<int64_t>(gridDim.x) * BEL_WARPS;
+    // one warp per batch (32 pairs of one cell); the batches are independent: the forward recorded the list
+    // positions at the start of every batch
+    for (int64_t slot = static_cast<int64_t>(blockIdx.x) * BEL_WARPS + (threadIdx.x >> 5); slot < nslot; slot += nwarp) {
+        const int cell = __ldg(btab + slot);
+        if (cell < 0) continue;  // unused slot
+        const int64_t b = __ldg(btab + nslot + slot);
+        const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
+        const int x1 = min(W, x0 + SEGW - 1);
+        const int64_t hi = __ldg(cstart + cell + 1);
+        const int nv = static_cast<int>(hi - b < 32 ? hi - b : 32);
+        int4 ra = make_int4(0, 0, 0, KEY_STRIDE), rb = make_int4(0, 0, 0, 0);  // empty interval: sx > any pixel, w = 0
+        if (lane < nv) ldg256(rec_b + 2 * static_cast<int64_t>(__ldg(pgid_s + b + lane)), ra, rb);
+        int pos[PPL], st[PPL];  // next element at the start of the batch / first element of the owned pixels' lists
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int x = x0 + lane + 32 * q;
+            pos[q] = __ldg(btab + 2 * nslot + slot * SEGW + lane + 32 * q);
+            st[q] = (x <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x) : 0;
+        }
+        const float *grow = gimg + 3 * (static_cast<int64_t>(y) * (W + 1) + x0);
+        const int sx = ra.w, sy = rb.x, w = rb.y;
+        const int a = max(sx, x0) - x0, z = min(sx + w - 1, x1) - x0;  // a > z for lanes past the end
+        const float l0 = __int_as_float(ra.x), l1 = __int_as_float(ra.y), l2 = __int_as_float(ra.z);
+        // Gaussian-major address of strip pixel 0 on this row (may lie before the box: only [a, z] is used)
+        const int64_t rowbase = ((static_cast<int64_t>(rb.w) << 32) | static_cast<uint32_t>(rb.z)) +
+                                static_cast<int64_t>(y - sy) * w + (x0 - sx);
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            if (x0 + 32 * q > x1) break;
+            // read phase in groups of 8 pixels: positions first (ballots only), then all loads, then the math
+#pragma unroll 1
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                int e[8], first[8];
+                bool cov[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = 32 * q + j0 + u;
+                    cov[u] = (a <= i) && (i <= z);
+                    const unsigned m = __ballot_sync(0xffffffffu, cov[u]);
+                    e[u] = __shfl_sync(0xffffffffu, pos[q], j0 + u) + __popc(m & lt);
+                    first[u] = __shfl_sync(0xffffffffu, st[q], j0 + u);
+                }
+                float yv[8], xv[8], tv[8], yp[8], p0[8], p1[8], p2[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = 32 * q + j0 + u;
+                    yv[u] = cov[u] ? __ldg(incl + e[u]) : 0.0f;
+                    xv[u] = cov[u] ? __ldg(x_s + e[u]) : 1.0f;
+                    tv[u] = cov[u] ? __ldg(tu + e[u]) : 0.0f;
+                    yp[u] = (cov[u] && e[u] != first[u]) ? __ldg(incl + e[u] - 1) : 1.0f;
+                    p0[u] = cov[u] ? __ldg(grow + 3 * i) : 0.0f;
+                    p1[u] = cov[u] ? __ldg(grow + 3 * i + 1) : 0.0f;
+                    p2[u] = cov[u] ? __ldg(grow + 3 * i + 2) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (cov[u]) {
+                        const float T = yp[u];
+                        const float pgl = p0[u] * l0 + p1[u] * l1 + p2[u] * l2;
+                        // dead elements (inclusive product 0) carry no gradient, gs_model.py:575-578
+                        const bool alive = yv[u] != 0.0f;
+                        tile[lane * BEL_STRIDE + j0 + u] =
+                            make_float2(alive ? T * pgl - tv[u] : 0.0f, alive ? T * (1.0f - xv[u]) * pgl : 0.0f);
+                    }
+                }
+            }
+            __syncwarp();
+            for (int k = 0; k < nv; ++k) {
+                const int ka = __shfl_sync(0xffffffffu, a, k), kz = __shfl_sync(0xffffffffu, z, k);
+                if (kz < 32 * q || ka > 32 * q + 31) continue;  // the pair does not touch this half strip
+                const int64_t kb = __shfl_sync(0xffffffffu, rowbase, k);
+                const int i = 32 * q + lane;
+                if (ka <= i && i <= kz) elem[kb + i] = tile[k * BEL_STRIDE + lane];
+            }
+            __syncwarp();
         }
     }
 }
@@ -1058,9 +1175,48 @@ int gcp_splat_set_long_list_threshold(int pairs_per_pixel) {
     return GCP_OK;
 }
 
+int gcp_splat_long_lists(int64_t P, int W, int H) {
+    if (P < 0 || W < 0 || H < 0) return 0;
+    return P / (static_cast<int64_t>(H + 1) * (W + 1)) >= g_long_min ? 1 : 0;
+}
+
+int gcp_splat_num_cells(int W, int H) { return (W < 0 || H < 0) ? 0 : (H + 1) * ((W + SEGW) >> SEG_SHIFT); }
+
+int64_t gcp_splat_batch_table_ints(int64_t P, int W, int H) {
+    if (P < 0 || W < 0 || H < 0) return 0;
+    const int64_t nslot = (P >> 5) + gcp_splat_num_cells(W, H) + 1;
+    return nslot * (2 + SEGW);
+}
+
+int gcp_splat_bwd_elem_cells(const float *incl, const float *x_s, const float *tu, const int32_t *rec_b,
+                             const float *grad_image, const int32_t *seg_off, const int32_t *cell_start,
+                             const int32_t *pair_gid, const int32_t *batch_table, int64_t P, int W, int H,
+                             float *elem, gcp_stream_t stream) {
+    if (P < 0 || W < 0 || H < 0 || W >= KEY_STRIDE) return GCP_ERR_INVALID_ARG;
+    if (!incl || !x_s || !tu || !rec_b || !grad_image || !seg_off || !cell_start || !pair_gid || !batch_table || !elem)
+        return GCP_ERR_INVALID_ARG;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    constexpr int smem = BEL_WARPS * 32 * BEL_STRIDE * static_cast<int>(sizeof(float2));
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_splat_bwd_elem_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_splat_bwd_elem_cells, BEL_WARPS * 32, smem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int nseg = (W + SEGW) >> SEG_SHIFT;
+    const int64_t nslot = (P >> 5) + static_cast<int64_t>(H + 1) * nseg + 1;
+    const int grid = static_cast<int>(std::min<int64_t>((nslot + BEL_WARPS - 1) / BEL_WARPS, 148 * blocks_per_sm));
+    k_splat_bwd_elem_cells<<<grid, BEL_WARPS * 32, smem, st>>>(
+        incl, x_s, tu, reinterpret_cast<const int4 *>(rec_b), grad_image, seg_off, cell_start, pair_gid, batch_table,
+        nslot, W, nseg, reinterpret_cast<float2 *>(elem));
+    return static_cast<int>(cudaGetLastError());
+}
+
 int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, int64_t n, int64_t P, int W, int H,
-                    int32_t *key_s, int32_t *gid_s, int32_t *seg_off, void *temp, size_t temp_bytes,
-                    gcp_stream_t stream) {
+                    int32_t *key_s, int32_t *gid_s, int32_t *seg_off, int32_t *cell_start, int32_t *pair_gid,
+                    int32_t *batch_table, void *temp, size_t temp_bytes, gcp_stream_t stream) {
     if (n < 0 || P < 0 || W < 0 || H < 0 || W >= KEY_STRIDE) return GCP_ERR_INVALID_ARG;
     if (!seg_off || !temp) return GCP_ERR_INVALID_ARG;
     if (reinterpret_cast<uintptr_t>(key_s) & 15) return GCP_ERR_INVALID_ARG;
@@ -1069,7 +1225,8 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     unsigned char *t = static_cast<unsigned char *>(temp);
     int32_t *prow = reinterpret_cast<int32_t *>(t + L.prow), *pgid = reinterpret_cast<int32_t *>(t + L.pgid);
-    int32_t *prow_s = reinterpret_cast<int32_t *>(t + L.prow_s), *pgid_s = reinterpret_cast<int32_t *>(t + L.pgid_s);
+    int32_t *prow_s = reinterpret_cast<int32_t *>(t + L.prow_s);
+    int32_t *pgid_s = pair_gid ? pair_gid : reinterpret_cast<int32_t *>(t + L.pgid_s);
     int32_t *cnt = reinterpret_cast<int32_t *>(t + L.cnt);
     const int64_t npix = static_cast<int64_t>(H + 1) * (W + 1) + 1;
     cudaError_t e;
@@ -1081,8 +1238,8 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
         e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, prow, prow_s, pgid, pgid_s, P, 0, key_bits(cells), s);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
-    int32_t *cstart = reinterpret_cast<int32_t *>(t + L.cstart);
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(cstart + cells + 1);
+    int32_t *cstart = cell_start ? cell_start : reinterpret_cast<int32_t *>(t + L.cstart);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(reinterpret_cast<int32_t *>(t + L.cstart) + cells + 1);
     k_place_cellstart<<<blocks_for(P + 1, 256), 256, 0, s>>>(prow_s, P, cells, cstart);
     const unsigned blocks = static_cast<unsigned>((cells + 7) / 8);
     k_place_count<<<blocks, 256, 0, s>>>(cstart, pgid_s, sp, ep, P, W, H, nseg, cnt);
@@ -1104,8 +1261,13 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
     if (long_lists) {
         e = cudaMemsetAsync(ticket, 0, 4, s);
         if (e != cudaSuccess) return static_cast<int>(e);
+        const int64_t nslot = (P >> 5) + cells + 1;
+        if (batch_table) {
+            e = cudaMemsetAsync(batch_table, 0xff, static_cast<size_t>(nslot) * 4, s);  // slot -> cell = -1: unused
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
         k_place_fill_long<<<std::min(blocks, 148u * 8u), 256, 0, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg,
-                                                                      gid_s, ticket);
+                                                                      gid_s, ticket, batch_table, nslot);
     } else {
         k_place_fill<<<fill_blocks, 256, 0, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
     }

@@ -154,6 +154,33 @@ def test_placement_equals_sort_on_long_pixel_lists_gpu(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_long_list_backward_equals_per_element_backward_gpu():
+    """C2 view: the cell-walking, shared-memory-transposing backward un-sort (long pixel lists) must give exactly
+    the gradients of the per-element scatter version (the reduction that follows is deterministic)."""
+    from simplegaussiansplat_tk71_b200 import _lib, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    v = wl.bundled_views("cuda", n_views=3)[2]
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+    L = _lib.lib()
+    grads = []
+    try:
+        for thr in (8, 1 << 20):  # default (long-list kernels) / short-list kernels forced
+            L.gcp_splat_set_long_list_threshold(thr)
+            m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                            v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+            img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+            img.backward(gI)
+            grads.append([t.grad.clone() for t in (m, lam, o, l)])
+            del img
+    finally:
+        L.gcp_splat_set_long_list_threshold(8)
+    for a, b in zip(*grads):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
 def test_native_compositor_matches_oracle_on_a_larger_scene_gpu():
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
