@@ -167,6 +167,13 @@ int64_t gcp_splat_batch_table_ints(int64_t P, int W, int H);
 int gcp_splat_num_cells(int W, int H);
 int gcp_splat_long_lists(int64_t P, int W, int H); /* 1 if the long-list kernels are selected for this view */
 
+/* View prologue in one call: goff i64[n+1] = exclusive offsets of boxsize i64[n] (element offsets per Gaussian,
+ * the reference's cumsum, gs_model.py:427), poff i64[n+1] = exclusive offsets of the (cell, Gaussian) pair
+ * counts gcp_splat_place expects, totals i64[2] = {N, P} (device memory; one D2H copy gives the host both). */
+size_t gcp_splat_prepare_bytes(int64_t n);
+int gcp_splat_prepare(const int64_t *boxsize, const int32_t *sp, const int32_t *ep, int64_t n, int64_t *goff,
+                      int64_t *poff, int64_t *totals, void *temp, size_t temp_bytes, gcp_stream_t stream);
+
 /* The per-Gaussian tables packed into two 32-byte records per Gaussian (both arrays 32-byte aligned), so that
  * every per-element gather of the kernels below is a single L2 sector:
  *   rec_a f32[n,8] = {mx, my, l00, l01, l10, l11, opacity, 0}

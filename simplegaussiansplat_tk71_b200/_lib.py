@@ -25,7 +25,7 @@ SYMBOLS = (
     "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status",
     "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
     "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
-    "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_pack", "gcp_splat_alpha", "gcp_splat_color",
+    "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_prepare_bytes", "gcp_splat_prepare", "gcp_splat_pack", "gcp_splat_alpha", "gcp_splat_color",
     "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce", "gcp_splat_bwd_reduce_bytes",
     "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_set_long_list_threshold", "gcp_splat_seg_shift",
     "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
@@ -66,6 +66,10 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_sort_bytes.argtypes = [i64]
     L.gcp_splat_sort_bytes.restype = sz
     L.gcp_splat_sort.argtypes = [vp, vp, vp, vp, i64, ci, vp, sz, vp]
+    L.gcp_splat_prepare_bytes.argtypes = [i64]
+    L.gcp_splat_prepare_bytes.restype = sz
+    L.gcp_splat_prepare.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.gcp_splat_prepare.restype = ci
     L.gcp_splat_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     L.gcp_splat_pack.restype = ci
     L.gcp_splat_alpha.argtypes = [vp, vp, vp, i64, vp, vp]

@@ -88,37 +88,37 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
     v.n = n
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        goff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(boxsize.to(torch.int64), 0, out=goff[1:])
-        # placement cells: one image row x 2^S pixels; a box contributes (rows) x (strips it touches) pairs
-        poff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        if n > 0:
-            S = int(L.gcp_splat_seg_shift())
-            rows = (endpoint[:, 1] - startpoint[:, 1] + 1).to(torch.int64)
-            strips = ((endpoint[:, 0] >> S) - (startpoint[:, 0] >> S) + 1).to(torch.int64)
-            torch.cumsum(rows * strips, 0, out=poff[1:])
-        # one host sync per view, like the reference's .item() at uitility.py:348
-        N, P = (int(t) for t in torch.stack((goff[-1], poff[-1])).tolist())
-        v.N = N
+        v.sp = startpoint.to(torch.int32).contiguous()
+        v.ep = endpoint.to(torch.int32).contiguous()
+        # element offsets per Gaussian and (cell, Gaussian) pair offsets (placement cells: one image row x 2^S
+        # pixels; a box contributes rows x strips-it-touches pairs) in one call; then one host sync per view for
+        # the two totals, like the reference's .item() at uitility.py:348
+        offs = torch.empty((2, n + 1), dtype=torch.int64, device=dev)
+        goff, poff = offs[0], offs[1]
+        totals = torch.empty(2, dtype=torch.int64, device=dev)
+        temp = _scratch_bytes(dev, "prepare", int(L.gcp_splat_prepare_bytes(n)))
+        _lib.check(L.gcp_splat_prepare(_p(boxsize.to(torch.int64).contiguous()), _p(v.sp), _p(v.ep), n, _p(goff),
+                                       _p(poff), _p(totals), _p(temp), temp.numel(), stream), "gcp_splat_prepare")
+        v.goff = goff
         v.mean = mean.detach().to(torch.float32).contiguous()
         v.lam = lam.detach().to(torch.float32).reshape(n, 4).contiguous()
         v.opac = opacity.detach().to(torch.float32).reshape(n).contiguous()
         v.l_d = l_d.detach().to(torch.float32).contiguous()
         image = torch.zeros((H + 1, W + 1, 3), dtype=torch.float32, device=dev)
-        v.goff = goff
-        v.sp = startpoint.to(torch.int32).contiguous()
-        v.ep = endpoint.to(torch.int32).contiguous()
+        sp, ep = v.sp, v.ep
+        # per-Gaussian tables as 32-byte records: one L2 sector per gather in the per-element kernels
+        # (queued before the host waits for the totals, so the device has work meanwhile)
+        v.rec_a = torch.empty((n, 8), dtype=torch.float32, device=dev)
+        v.rec_b = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        _lib.check(L.gcp_splat_pack(_p(v.mean), _p(v.lam), _p(v.opac), _p(v.l_d), _p(sp), _p(ep), _p(goff), n,
+                                    _p(v.rec_a), _p(v.rec_b), stream), "gcp_splat_pack")
+        N, P = totals.tolist()
+        v.N = N
         if N == 0:
             v.key_s = v.gid_s = v.x_s = v.incl = None
             return image, v
         if N >= 2 ** 31:
             raise RuntimeError("a view is limited to 2**31-1 elements (the reference ops index with int32)")
-        sp, ep = v.sp, v.ep
-        # per-Gaussian tables as 32-byte records: one L2 sector per gather in the per-element kernels
-        v.rec_a = torch.empty((n, 8), dtype=torch.float32, device=dev)
-        v.rec_b = torch.empty((n, 8), dtype=torch.int32, device=dev)
-        _lib.check(L.gcp_splat_pack(_p(v.mean), _p(v.lam), _p(v.opac), _p(v.l_d), _p(sp), _p(ep), _p(goff), n,
-                                    _p(v.rec_a), _p(v.rec_b), stream), "gcp_splat_pack")
         v.key_s = torch.empty(N, dtype=torch.int32, device=dev)
         v.gid_s = torch.empty(N, dtype=torch.int32, device=dev)
         if USE_PLACEMENT:

@@ -18,6 +18,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "gcp_abi.h"
 
@@ -974,6 +976,22 @@ k_splat_bwd_elem_cells(const float *__restrict__ incl, const float *__restrict__
     }
 }
 
+// (cell, Gaussian) pairs of one box: rows x strips it touches (0 for an empty / inverted box)
+struct PairCount {
+    const int32_t *sp, *ep;
+    __host__ __device__ __forceinline__ int64_t operator()(int64_t g) const {
+        const int sx = sp[2 * g], sy = sp[2 * g + 1], ex = ep[2 * g], ey = ep[2 * g + 1];
+        if (ex < sx || ey < sy) return 0;
+        return static_cast<int64_t>(ey - sy + 1) * ((ex >> SEG_SHIFT) - (sx >> SEG_SHIFT) + 1);
+    }
+};
+
+__global__ void k_prepare_totals(const int64_t *__restrict__ goff, const int64_t *__restrict__ poff, int64_t n,
+                                 int64_t *__restrict__ totals) {
+    totals[0] = goff[n];
+    totals[1] = poff[n];
+}
+
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -1017,6 +1035,41 @@ int gcp_splat_sort(const int32_t *key_in, const int32_t *gid_in, int32_t *key_ou
     return static_cast<int>(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_in, key_out, gid_in, gid_out, N, 0,
                                                             key_bits(max_key),
                                                             reinterpret_cast<cudaStream_t>(stream)));
+}
+
+size_t gcp_splat_prepare_bytes(int64_t n) {
+    size_t a = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, a, static_cast<const int64_t *>(nullptr), static_cast<int64_t *>(nullptr),
+                                  n > 0 ? n : 1);
+    return a + 256;  // the transform-iterator scan needs no more than the plain one of the same value type
+}
+
+int gcp_splat_prepare(const int64_t *boxsize, const int32_t *sp, const int32_t *ep, int64_t n, int64_t *goff,
+                      int64_t *poff, int64_t *totals, void *temp, size_t temp_bytes, gcp_stream_t stream) {
+    if (n < 0 || !goff || !poff || !totals) return GCP_ERR_INVALID_ARG;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(goff, 0, 8, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaMemsetAsync(poff, 0, 8, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (n > 0) {
+        if (!boxsize || !sp || !ep || !temp) return GCP_ERR_INVALID_ARG;
+        size_t need = 0;
+        auto pairs = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), PairCount{sp, ep});
+        cub::DeviceScan::InclusiveSum(nullptr, need, pairs, poff + 1, n);
+        size_t need2 = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, need2, boxsize, goff + 1, n);
+        if (need2 > need) need = need2;
+        if (temp_bytes < need) return GCP_ERR_WORKSPACE;
+        size_t tb = temp_bytes;
+        e = cub::DeviceScan::InclusiveSum(temp, tb, boxsize, goff + 1, n, st);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        tb = temp_bytes;
+        e = cub::DeviceScan::InclusiveSum(temp, tb, pairs, poff + 1, n, st);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    k_prepare_totals<<<1, 1, 0, st>>>(goff, poff, n, totals);
+    return static_cast<int>(cudaGetLastError());
 }
 
 int gcp_splat_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,

@@ -65,3 +65,5 @@ if os.environ.get("SPLAT_PROFILE"):
         step()
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    if os.environ.get("SPLAT_TRACE"):
+        prof.export_chrome_trace(os.environ["SPLAT_TRACE"])
