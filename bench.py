@@ -206,7 +206,10 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
+_OUT = sys.stdout
 
 
 def main():
@@ -225,6 +228,12 @@ def main():
     ap.add_argument("--no-splat", action="store_true", help="skip the splat-step / multi-view legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly the JSON line(s) this script prints: everything libraries write to file descriptor 1
+    # (NCCL's version banner, for one) is sent to stderr instead
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -400,7 +409,7 @@ def main():
             "clocks": clocks,
             "splat_step": splat,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -623,7 +632,7 @@ def sweep(args, e, y, gin, gc, ops):
     ms = timeit(lambda: dst.copy_(src))
     res["copy"] = {"ms": ms, "GBs": src.numel() * 8 / ms / 1e6}
     print(f"torch copy_ {src.numel() * 8 / 1e6:.0f} MB r+w: {ms:.4f} ms {res['copy']['GBs']:.1f} GB/s", file=sys.stderr)
-    print(json.dumps(res), flush=True)
+    print(json.dumps(res), file=_OUT, flush=True)
 
 
 if __name__ == "__main__":
