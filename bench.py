@@ -498,8 +498,14 @@ def splat_legs(args, device, rank, world):
         ar_ms += t1.elapsed_time(t2)
     tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
     _, max_ar = vw.aggregate_throughput(0, ar_ms / steps, device)
+    # the rank that arrives last waits for nobody: its time is the collective itself
+    min_ar = torch.tensor([ar_ms / steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(min_ar, op=dist.ReduceOp.MIN)
+    min_ar = float(min_ar.item())
     out["multi_view"] = {"views": args.views, "views_per_rank": len(mine), "distinct_scenes_per_rank": distinct,
-                         "step_ms": max_ms, "allreduce_ms": max_ar, "bucket_bytes": bucket.numel() * 4,
+                         "step_ms": max_ms, "allreduce_ms": min_ar, "allreduce_plus_wait_for_slowest_rank_ms": max_ar,
+                         "bucket_bytes": bucket.numel() * 4,
                          "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
                          "collective": "nccl all_reduce(sum) of the parameter-gradient bucket" if world > 1 else "none (1 rank)"}
     # (iii) C2: the scene bundled with the reference (BASELINE.json configs[1]; poses synthesised), rank 0 only:
