@@ -750,6 +750,8 @@ k_place_keys_long(const int32_t *__restrict__ off, int npix, int W, int32_t *__r
     }
 }
 
+constexpr int FILL_STAGE = 2048;  // staged elements per warp (8 KB)
+
 // one warp per (row, strip) cell at a time: walk the cell's intervals in Gaussian (depth) order.
 // Lane l owns pixels l, l+32, ... of the strip: list offset and running count live in REGISTERS, so an interval
 // costs three shuffles and a predicated store per owned pixel — no shared-memory read-modify-write chain between
@@ -764,17 +766,25 @@ k_place_fill(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgi
              int64_t P, int W, int H, int nseg, int32_t *__restrict__ gid_s) {
     constexpr int PPL = SEGW / 32;  // pixels per lane
     static_assert(SEGW % 32 == 0, "strip width must be a multiple of the warp size");
+    extern __shared__ int32_t fill_stage[];  // FILL_STAGE entries per warp
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int32_t *stage = fill_stage + wib * FILL_STAGE;
     const int ncell = (H + 1) * nseg;
     for (int cell = blockIdx.x * 8 + wib; cell < ncell; cell += gridDim.x * 8) {
         const int y = cell / nseg, x0 = (cell - y * nseg) << SEG_SHIFT;
         const int x1 = min(W, x0 + SEGW - 1);
         const int64_t lo = __ldg(cstart + cell), hi = __ldg(cstart + cell + 1);
+        // the lists of the cell's pixels are one contiguous range [c0, c1) of gid_s: if it fits, the scattered
+        // appends go to shared memory and the range leaves as coalesced stores
+        const int64_t prow = static_cast<int64_t>(y) * (W + 1);
+        const int c0 = __ldg(off + prow + x0), c1 = __ldg(off + prow + x1 + 1);
+        const bool staged = c1 - c0 <= FILL_STAGE;
+        int32_t *const base = staged ? stage - c0 : gid_s;
         int32_t *dst[PPL];  // next free slot of the owned pixels' lists
 #pragma unroll
         for (int q = 0; q < PPL; ++q) {
             const int x = x0 + lane + 32 * q;
-            dst[q] = gid_s + ((x <= x1) ? __ldg(off + static_cast<int64_t>(y) * (W + 1) + x) : 0);
+            dst[q] = base + ((x <= x1) ? __ldg(off + prow + x) : c0);
         }
         // intervals in batches of 32 (one per lane), software-pipelined two deep: the ids of batch b+2 and the box
         // columns of batch b+1 are in flight while batch b is walked (the columns depend on the ids)
@@ -800,6 +810,11 @@ k_place_fill(const int32_t *__restrict__ cstart, const int32_t *__restrict__ pgi
                 }
             }
             g = g1; g1 = g2; rs = rs1; re = re1;
+        }
+        if (staged) {
+            __syncwarp();
+            for (int i = lane; i < c1 - c0; i += 32) gid_s[c0 + i] = stage[i];
+            __syncwarp();
         }
     }
 }
@@ -1301,8 +1316,8 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
     size_t cb = L.cub_bytes;
     e = cub::DeviceScan::ExclusiveSum(t + L.cub, cb, cnt, seg_off, npix, s);
     if (e != cudaSuccess) return static_cast<int>(e);
-    // persistent, ~3500 warps: the lists under construction (~10 KB per cell) stay inside the 126 MB L2
-    const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 222u;
+    // persistent: three 64 KB-staging blocks per SM; cells taken in index order keep the output window compact
+    const unsigned cap = g_fill_blocks > 0 ? static_cast<unsigned>(g_fill_blocks) : 444u;
     unsigned fill_blocks = blocks < cap ? blocks : cap;
     // short lists: per-element search inside 256-pixel blocks; long lists (>= 8 intervals per pixel): warp per list
     const unsigned key_blocks = static_cast<unsigned>((npix - 1 + 255) / 256);
@@ -1322,7 +1337,14 @@ int gcp_splat_place(const int32_t *sp, const int32_t *ep, const int64_t *poff, i
         k_place_fill_long<<<std::min(blocks, 148u * 8u), 256, 0, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg,
                                                                       gid_s, ticket, batch_table, nslot);
     } else {
-        k_place_fill<<<fill_blocks, 256, 0, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
+        constexpr int fill_smem = 8 * FILL_STAGE * 4;
+        static bool fill_attr = false;
+        if (!fill_attr) {
+            e = cudaFuncSetAttribute(k_place_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, fill_smem);
+            if (e != cudaSuccess) return static_cast<int>(e);
+            fill_attr = true;
+        }
+        k_place_fill<<<fill_blocks, 256, fill_smem, s>>>(cstart, pgid_s, sp, ep, seg_off, P, W, H, nseg, gid_s);
     }
     return static_cast<int>(cudaGetLastError());
 }
