@@ -83,3 +83,28 @@ def test_product_path_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "workloads.py" and False, f"{f} mentions the oracle"
     assert "oracle" not in open(os.path.join(ROOT, "grouped_cumprod.py")).read()
+
+
+def test_splat_size_helpers_are_pure_host_arithmetic():
+    """The sizing helpers of the compositor section run without a GPU (no compute): cells of one row x 2^S pixels,
+    long-list selection by pairs per pixel, batch-table and reduce-scratch sizes."""
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    S = L.gcp_splat_seg_shift()
+    assert S == 6
+    W, H = 1920, 1080
+    nseg = (W + (1 << S)) >> S
+    assert L.gcp_splat_num_cells(W, H) == (H + 1) * nseg
+    npix = (H + 1) * (W + 1)
+    assert L.gcp_splat_long_lists(8 * npix, W, H) == 1 and L.gcp_splat_long_lists(8 * npix - 1, W, H) == 0
+    P = 6_000_000
+    assert L.gcp_splat_batch_table_ints(P, W, H) == ((P >> 5) + (H + 1) * nseg + 1) * (2 + (1 << S))
+    assert L.gcp_splat_long_lists(-1, W, H) == 0 and L.gcp_splat_num_cells(-1, H) == 0
+    # reduce scratch: header + two id arrays + one 32-byte partial per piece; grows with N
+    a, b = L.gcp_splat_bwd_reduce_bytes(10_000_000, 100_000), L.gcp_splat_bwd_reduce_bytes(20_000_000, 100_000)
+    assert 0 < a < b < 20_000_000 * 8
+    try:
+        assert L.gcp_splat_set_long_list_threshold(-1) == -1      # GCP_ERR_INVALID_ARG
+    finally:
+        L.gcp_splat_set_long_list_threshold(8)
