@@ -24,6 +24,11 @@ namespace gcp {
 
 constexpr int BLK_EPL = 16;              // elements per lane
 constexpr int BLK_WSPAN = 32 * BLK_EPL;  // elements per warp = 512
+#ifndef GCP_BLK_HQ
+#define GCP_BLK_HQ 2
+#endif
+constexpr int BLK_HQ = GCP_BLK_HQ;       // halo window = 128 * BLK_HQ elements (resolves a tile's carry in place when a
+                                         // segment boundary lies that close; the data are the neighbouring tile's, in L2)
 
 // byte offset inside a swizzled stage array for logical byte offset `b` (128B swizzle)
 __device__ __forceinline__ uint32_t swz(uint32_t b) { return b ^ (((b >> 7) & 7u) << 4); }
@@ -262,19 +267,18 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         bool pending = false;
         int ps = 0;
         int64_t pbase = 0;
-        float4 ha = make_float4(0.f, 0.f, 0.f, 0.f);
-        int4 hb = make_int4(0, 0, 0, 0);
-        int32_t hkf = 0;
+        HaloPrefixRegs<BLK_HQ> hp;
+        hp.kfirst = 0;
         for (uint32_t it = 0;; ++it) {
             if (pending) {
                 float P = O::id();
                 int32_t kprev = 0;
                 bool res;
                 if (use_halo) {
-                    res = halo_prefix_finish<OP>(ha, hb, hkf, lane, P, kprev);
+                    res = halo_prefix_finish<OP, BLK_HQ>(hp, lane, P, kprev);
                 } else {
                     res = false;
-                    kprev = hkf;
+                    kprev = hp.kfirst;
                 }
                 if (lane == 0) {
                     ctl->halo[ps] = kprev;
@@ -322,9 +326,9 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             } else {
                 // issue the halo loads now, use them next iteration
                 if (use_halo) {
-                    halo_prefix_issue(x, key, base, lane, ha, hb, hkf);
+                    halo_prefix_issue<BLK_HQ>(x, key, base, lane, hp);
                 } else {
-                    hkf = __ldg(key + base - 1);
+                    hp.kfirst = __ldg(key + base - 1);
                 }
                 pending = true;
                 ps = s;
@@ -615,7 +619,7 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         }
         bool pending = false;
         int ps = 0;
-        HaloSuffixRegs hr;
+        HaloSuffixRegs<BLK_HQ> hr;
         int32_t ip = -1;
         float yp = 1.0f;
         for (uint32_t it = 0;; ++it) {

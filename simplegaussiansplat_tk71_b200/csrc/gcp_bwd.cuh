@@ -96,15 +96,18 @@ __device__ __forceinline__ bool halo_suffix(const float *__restrict__ x, const f
 }
 
 // halo_suffix split in two for a software-pipelined producer (issue in iteration i, finish in i+1).
+// HQ = float4 quads per lane: the window is the 128*HQ elements after the tile.
+template <int HQ>
 struct HaloSuffixRegs {
-    float xv[4], gv[4];
-    int32_t iv[4];
+    float xv[4 * HQ], gv[4 * HQ];
+    int32_t iv[4 * HQ];
     int32_t ilast;
     bool beyond;  // end >= n: nothing follows the tile
 };
+template <int HQ>
 __device__ __forceinline__ void halo_suffix_issue(const float *__restrict__ x, const float *__restrict__ g,
                                                   const int32_t *__restrict__ inv, int64_t end, int64_t n, int lane,
-                                                  bool full_window, HaloSuffixRegs &r) {
+                                                  bool full_window, HaloSuffixRegs<HQ> &r) {
     r.beyond = end >= n;
     if (r.beyond) return;
     r.ilast = __ldg(inv + end - 1);
@@ -113,25 +116,30 @@ __device__ __forceinline__ void halo_suffix_issue(const float *__restrict__ x, c
         r.iv[0] = __ldg(inv + end);
         return;
     }
-    const int64_t h0 = end + lane * 4;
-    if (h0 + 3 < n) {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(x + h0));
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(g + h0));
-        const int4 c = __ldg(reinterpret_cast<const int4 *>(inv + h0));
-        r.xv[0] = a.x; r.xv[1] = a.y; r.xv[2] = a.z; r.xv[3] = a.w;
-        r.gv[0] = b.x; r.gv[1] = b.y; r.gv[2] = b.z; r.gv[3] = b.w;
-        r.iv[0] = c.x; r.iv[1] = c.y; r.iv[2] = c.z; r.iv[3] = c.w;
-    } else {
+    const int64_t h0 = end + lane * (4 * HQ);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool in = h0 + e < n;
-            r.xv[e] = in ? __ldg(x + h0 + e) : 1.0f;
-            r.gv[e] = in ? __ldg(g + h0 + e) : 0.0f;
-            r.iv[e] = in ? __ldg(inv + h0 + e) : -1;
+    for (int c = 0; c < HQ; ++c) {
+        const int64_t hc = h0 + 4 * c;
+        if (hc + 3 < n) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(x + hc));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(g + hc));
+            const int4 k = __ldg(reinterpret_cast<const int4 *>(inv + hc));
+            r.xv[4 * c] = a.x; r.xv[4 * c + 1] = a.y; r.xv[4 * c + 2] = a.z; r.xv[4 * c + 3] = a.w;
+            r.gv[4 * c] = b.x; r.gv[4 * c + 1] = b.y; r.gv[4 * c + 2] = b.z; r.gv[4 * c + 3] = b.w;
+            r.iv[4 * c] = k.x; r.iv[4 * c + 1] = k.y; r.iv[4 * c + 2] = k.z; r.iv[4 * c + 3] = k.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool in = hc + e < n;
+                r.xv[4 * c + e] = in ? __ldg(x + hc + e) : 1.0f;
+                r.gv[4 * c + e] = in ? __ldg(g + hc + e) : 0.0f;
+                r.iv[4 * c + e] = in ? __ldg(inv + hc + e) : -1;  // padding differs from every id: a tail before it
+            }
         }
     }
 }
-__device__ __forceinline__ bool halo_suffix_finish(const HaloSuffixRegs &r, int lane, bool full_window, float &R,
+template <int HQ>
+__device__ __forceinline__ bool halo_suffix_finish(const HaloSuffixRegs<HQ> &r, int lane, bool full_window, float &R,
                                                    int32_t &inext, float &xnext) {
     if (r.beyond) {
         R = 0.0f;
@@ -145,17 +153,17 @@ __device__ __forceinline__ bool halo_suffix_finish(const HaloSuffixRegs &r, int 
         xnext = r.xv[0];
         return false;
     }
+    constexpr int E = 4 * HQ;
     int32_t qn = __shfl_down_sync(0xffffffffu, r.iv[0], 1);
     float xq = __shfl_down_sync(0xffffffffu, r.xv[0], 1);
-    const bool known = lane < 31;
+    const bool known = lane < 31;  // what follows the window is unknown
     if (!known) xq = 1.0f;
     inext = __shfl_sync(0xffffffffu, r.iv[0], 0);
     xnext = __shfl_sync(0xffffffffu, r.xv[0], 0);
-    Affine m = Affine{(known && qn != r.iv[3]) ? 0.0f : xq, r.gv[3]};
-    m = compose(Affine{(r.iv[3] != r.iv[2]) ? 0.0f : r.xv[3], r.gv[2]}, m);
-    m = compose(Affine{(r.iv[2] != r.iv[1]) ? 0.0f : r.xv[2], r.gv[1]}, m);
-    m = compose(Affine{(r.iv[1] != r.iv[0]) ? 0.0f : r.xv[1], r.gv[0]}, m);
-    m = warp_compose_all(m, lane);
+    Affine m = Affine{(known && qn != r.iv[E - 1]) ? 0.0f : xq, r.gv[E - 1]};
+#pragma unroll
+    for (int e = E - 1; e >= 1; --e) m = compose(Affine{(r.iv[e] != r.iv[e - 1]) ? 0.0f : r.xv[e], r.gv[e - 1]}, m);
+    m = warp_compose_all(m, lane);  // everything after the first tail is annihilated
     if (r.ilast != inext) {
         R = 0.0f;
         return true;

@@ -93,6 +93,17 @@ __device__ __forceinline__ void warp_seg_scan_rows(const float (&agg)[ROWS], uin
     wf = rp_f;
 }
 
+// op over the 32 lanes' values, every lane gets the result.  Only ADJACENT lane ranges are ever combined (a
+// shfl_down tree, then a broadcast), like the reference's thrust scan: a butterfly would also multiply
+// non-adjacent ranges, whose product can overflow although every contiguous sub-range product is finite.
+template <int OP>
+__device__ __forceinline__ float warp_reduce_ordered(float w) {
+    using O = ScanOp<OP>;
+#pragma unroll
+    for (int d = 1; d <= 16; d <<= 1) w = O::f(w, __shfl_down_sync(0xffffffffu, w, d));
+    return __shfl_sync(0xffffffffu, w, 0);
+}
+
 // All 32 lanes of one warp: resolve the exclusive prefix of the tile that starts at `base`
 // from the 128 elements before it.  True when the tile's first element is a head (prefix
 // irrelevant) or a segment head lies inside the window; then P = op over [last head, base).
@@ -123,8 +134,7 @@ __device__ __forceinline__ bool halo_prefix(const float *__restrict__ x, const i
     v = (h & 8u) ? a.w : O::f(v, a.w);
     const int last = 31 - __clz(m);  // highest lane holding a head, -1 if none
     float w = (lane >= last) ? v : O::id();
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+    w = warp_reduce_ordered<OP>(w);
     if (kfirst != kprev) {
         P = O::id();
         return true;
@@ -135,31 +145,49 @@ __device__ __forceinline__ bool halo_prefix(const float *__restrict__ x, const i
 
 // The same halo resolution split in two so that a producer can issue the loads of tile i and
 // consume them one iteration later (software pipelining).  16-byte aligned inputs only.
+// HQ = float4 quads per lane: the window is the 128*HQ elements before the tile (base >= 128*HQ).
+template <int HQ>
+struct HaloPrefixRegs {
+    float4 a[HQ];
+    int4 b[HQ];
+    int32_t kfirst;  // key[base]; with halo resolution off: key[base-1]
+};
+template <int HQ>
 __device__ __forceinline__ void halo_prefix_issue(const float *__restrict__ x, const int32_t *__restrict__ key,
-                                                  int64_t base, int lane, float4 &a, int4 &b, int32_t &kfirst) {
-    const int64_t h0 = base - 128 + lane * 4;
-    a = __ldg(reinterpret_cast<const float4 *>(x + h0));
-    b = __ldg(reinterpret_cast<const int4 *>(key + h0));
-    kfirst = __ldg(key + base);
-}
-template <int OP>
-__device__ __forceinline__ bool halo_prefix_finish(const float4 a, const int4 b, int32_t kfirst, int lane, float &P,
-                                                   int32_t &kprev) {
-    using O = ScanOp<OP>;
-    const int32_t pk = __shfl_up_sync(0xffffffffu, b.w, 1);
-    const uint32_t h = ((lane > 0 && b.x != pk) ? 1u : 0u) | (b.y != b.x ? 2u : 0u) | (b.z != b.y ? 4u : 0u) |
-                       (b.w != b.z ? 8u : 0u);
-    kprev = __shfl_sync(0xffffffffu, b.w, 31);
-    const uint32_t m = __ballot_sync(0xffffffffu, h != 0u);
-    float v = a.x;
-    v = (h & 2u) ? a.y : O::f(v, a.y);
-    v = (h & 4u) ? a.z : O::f(v, a.z);
-    v = (h & 8u) ? a.w : O::f(v, a.w);
-    const int last = 31 - __clz(m);
-    float w = (lane >= last) ? v : O::id();
+                                                  int64_t base, int lane, HaloPrefixRegs<HQ> &r) {
+    const int64_t h0 = base - 128 * HQ + lane * (4 * HQ);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
-    if (kfirst != kprev) {
+    for (int c = 0; c < HQ; ++c) {
+        r.a[c] = __ldg(reinterpret_cast<const float4 *>(x + h0) + c);
+        r.b[c] = __ldg(reinterpret_cast<const int4 *>(key + h0) + c);
+    }
+    r.kfirst = __ldg(key + base);
+}
+template <int OP, int HQ>
+__device__ __forceinline__ bool halo_prefix_finish(const HaloPrefixRegs<HQ> &r, int lane, float &P, int32_t &kprev) {
+    using O = ScanOp<OP>;
+    float xv[4 * HQ];
+    int32_t kv[4 * HQ];
+#pragma unroll
+    for (int c = 0; c < HQ; ++c) {
+        xv[4 * c] = r.a[c].x; xv[4 * c + 1] = r.a[c].y; xv[4 * c + 2] = r.a[c].z; xv[4 * c + 3] = r.a[c].w;
+        kv[4 * c] = r.b[c].x; kv[4 * c + 1] = r.b[c].y; kv[4 * c + 2] = r.b[c].z; kv[4 * c + 3] = r.b[c].w;
+    }
+    const int32_t pk = __shfl_up_sync(0xffffffffu, kv[4 * HQ - 1], 1);
+    kprev = __shfl_sync(0xffffffffu, kv[4 * HQ - 1], 31);
+    bool any = lane > 0 && kv[0] != pk;
+    float v = xv[0];  // op over the lane's elements since its last head
+#pragma unroll
+    for (int e = 1; e < 4 * HQ; ++e) {
+        const bool h = kv[e] != kv[e - 1];
+        v = h ? xv[e] : O::f(v, xv[e]);
+        any |= h;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, any);
+    const int last = 31 - __clz(m);  // highest lane holding a head, -1 if none
+    float w = (lane >= last) ? v : O::id();
+    w = warp_reduce_ordered<OP>(w);
+    if (r.kfirst != kprev) {
         P = O::id();
         return true;
     }
@@ -305,8 +333,7 @@ __device__ __forceinline__ void fwd_fix_tile(uint32_t t, float *y, int64_t n, in
         const uint32_t tm = __ballot_sync(0xffffffffu, term);
         const int last = tm ? (__ffs(tm) - 1) : 31;
         float w = (lane <= last) ? v : O::id();
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) w = O::f(w, __shfl_xor_sync(0xffffffffu, w, d));
+        w = warp_reduce_ordered<OP>(w);
         carry = O::f(w, carry);
         if (tm) break;
         pb -= 32;

@@ -36,8 +36,10 @@ BWD_VARIANTS = list(range(14))
 
 
 def _pow2_values(n, rng, span=12):
-    """x in {0.5, 1, 2} with the running exponent reflected inside +-span: every partial product is an
-    exact power of two, so ANY association order gives bit-identical fp32 results."""
+    """x in {0.5, 1, 2} with the running exponent reflected inside +-span: the product of every CONTIGUOUS range
+    is an exact power of two within 2**(+-2*span), so any association order gives bit-identical fp32 results.
+    (Products of non-adjacent ranges are not bounded: a scan that commutes operands can overflow on this data —
+    it did, in the descriptor walk, until its warp reduction was made order-preserving.)"""
     steps = rng.integers(-1, 2, n)
     e = 0
     out = np.empty(n, np.float32)
@@ -93,7 +95,7 @@ def test_kat2_through_dropin_module(golden):
 def test_forward_sizes_and_layouts(oracle, variant, op):
     rng = np.random.default_rng(100 + variant)
     ofn = oracle.cumprod_fwd if op == "mul" else oracle.cumsum_fwd
-    sizes = [1, 2, 3, 4, 5, 31, 127, 128, 129, 1023, 1024, 1025, 2047, 2049, 4095, 4096, 4097, 8191, 8193,
+    sizes = [1, 2, 3, 4, 5, 31, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025, 2047, 2049, 4095, 4096, 4097, 8191, 8193,
              12289, 40000, 100003]
     for n in sizes:
         x = _values(n, rng) if op == "mul" else rng.uniform(0.0, 2.0, n).astype(np.float32)
@@ -116,7 +118,7 @@ def test_forward_sizes_and_layouts(oracle, variant, op):
 def test_forward_boundaries_on_tile_edges_and_long_segments(oracle, variant):
     rng = np.random.default_rng(7)
     # segments that start/end exactly on 128 / 1024 / 2048 / 4096 / 8192 element edges, and around them
-    for seglen in (128, 512, 1024, 2048, 4096, 8192, 4095, 4097, 2049):
+    for seglen in (128, 256, 255, 257, 512, 1024, 2048, 4096, 8192, 4095, 4097, 2049):
         n = seglen * 9 + 5
         key = (np.arange(n) // seglen).astype(np.int32)
         x = (1.0 - 1e-3 * rng.uniform(size=n)).astype(np.float32)
@@ -184,7 +186,7 @@ def test_dtype_and_shape_errors_match_reference_behaviour():
 @pytest.mark.parametrize("variant", BWD_VARIANTS)
 def test_backward_sizes_and_layouts(oracle, variant):
     rng = np.random.default_rng(200 + variant)
-    sizes = [1, 2, 3, 5, 127, 128, 129, 1023, 1024, 1025, 2047, 2049, 4095, 4096, 4097, 8193, 12289, 40000,
+    sizes = [1, 2, 3, 5, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025, 2047, 2049, 4095, 4096, 4097, 8193, 12289, 40000,
              100003]
     for n in sizes:
         for layout in ("random", "one", "singletons"):
@@ -207,7 +209,7 @@ def test_backward_sizes_and_layouts(oracle, variant):
 @pytest.mark.parametrize("variant", BWD_VARIANTS)
 def test_backward_tile_edges_long_segments_signed_grads(oracle, variant):
     rng = np.random.default_rng(13)
-    for seglen in (128, 1024, 2048, 4096, 8192, 4095, 4097):
+    for seglen in (128, 256, 255, 257, 1024, 2048, 4096, 8192, 4095, 4097):
         n = seglen * 7 + 3
         L = [seglen] * 7 + [3]
         inv, seg_end = seg_arrays(L)
