@@ -422,6 +422,7 @@ def splat_legs(args, device, rank, world):
     import torch
     import torch.distributed as dist
 
+    from simplegaussiansplat_tk71_b200 import compositor
     from simplegaussiansplat_tk71_b200 import views as vw
     from simplegaussiansplat_tk71_b200 import workloads as wl
     from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
@@ -439,18 +440,22 @@ def splat_legs(args, device, rank, world):
     gI = torch.rand(1081, 1921, 3, device=device) + 0.1
     W, H = torch.tensor(1920), torch.tensor(1080)
 
-    def one_view(i):
+    def one_view(i, plan_next=False):
         sc, (m, lam, o, l) = scenes[i % distinct], leaves[i % distinct]
+        if plan_next:  # the next view's prologue (offsets, element count) runs on a side stream meanwhile
+            nx = scenes[(i + 1) % distinct]
+            compositor.plan_view(nx.boxsize, nx.startpoint, nx.endpoint)
         for t_ in (m, lam, o, l):
             t_.grad = None
         img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)
         img.backward(gI)
+        # flat bucket laid out like a DDP bucket: one contiguous section per parameter tensor
+        # (mean [n,2] | Lambda [n,4] | opacity [n,1] | l [n,3] | the 28 remaining floats per Gaussian)
         k = sc.n
-        b = bucket.view(n_param, vw.PARAM_FLOATS_PER_GAUSSIAN)
-        b[:k, 0:2] += m.grad
-        b[:k, 2:6] += lam.grad.reshape(k, 4)
-        b[:k, 6:7] += o.grad
-        b[:k, 7:10] += l.grad
+        bucket[0:2 * k] += m.grad.reshape(-1)
+        bucket[2 * n_param:2 * n_param + 4 * k] += lam.grad.reshape(-1)
+        bucket[6 * n_param:6 * n_param + k] += o.grad.reshape(-1)
+        bucket[7 * n_param:7 * n_param + 3 * k] += l.grad.reshape(-1)
         return sc.elements
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -489,13 +494,14 @@ def splat_legs(args, device, rank, world):
     for _ in range(steps):
         bucket.zero_()
         t0.record()
-        elems = sum(one_view(i) for i in range(len(mine)))
+        elems = sum(one_view(i, plan_next=True) for i in range(len(mine)))
         t1.record()
         vw.allreduce_param_grads(bucket)
         t2.record()
         torch.cuda.synchronize()
         step_ms += t0.elapsed_time(t2)
         ar_ms += t1.elapsed_time(t2)
+        print(f"multi-view step: {t0.elapsed_time(t2):.2f} ms", file=sys.stderr)
     tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
     _, max_ar = vw.aggregate_throughput(0, ar_ms / steps, device)
     # the rank that arrives last waits for nobody: its time is the collective itself

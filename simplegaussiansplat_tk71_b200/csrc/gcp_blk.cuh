@@ -25,7 +25,7 @@ namespace gcp {
 constexpr int BLK_EPL = 16;              // elements per lane
 constexpr int BLK_WSPAN = 32 * BLK_EPL;  // elements per warp = 512
 #ifndef GCP_BLK_HQ
-#define GCP_BLK_HQ 2
+#define GCP_BLK_HQ 4
 #endif
 constexpr int BLK_HQ = GCP_BLK_HQ;       // halo window = 128 * BLK_HQ elements (resolves a tile's carry in place when a
                                          // segment boundary lies that close; the data are the neighbouring tile's, in L2)

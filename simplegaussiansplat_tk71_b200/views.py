@@ -84,11 +84,19 @@ def render_views(mean_pixel, box_half, z, lam, opacity, l_d, width: int, height:
     """The per-view loop of gs_model.py:402-454 over V views whose Gaussians are already z-sorted:
     inputs [V,n,...]; returns images [V',3,H,W] (views without any visible Gaussian are skipped, :414-417) —
     including the reference's final `[:,1:,1:,:].reshape(-1,3,H,W)` (a reshape, not a permute, :454)."""
-    from .compositor import custom_autograd_grouped_cumprod as F
+    from .compositor import custom_autograd_grouped_cumprod as F, plan_view
 
     out = []
-    for v in range(mean_pixel.shape[0]):
-        mask, sp, ep, boxsize = visible_boxes(mean_pixel[v], box_half[v], z[v], width, height)
+    V = mean_pixel.shape[0]
+    nxt = visible_boxes(mean_pixel[0], box_half[0], z[0], width, height) if V else None
+    for v in range(V):
+        mask, sp, ep, boxsize = nxt
+        if v + 1 < V:
+            # cull the next view now and queue its prologue on a side stream: its element count is then already
+            # on the host when its turn comes (compositor.plan_view)
+            nxt = visible_boxes(mean_pixel[v + 1], box_half[v + 1], z[v + 1], width, height)
+            if nxt[1].shape[0]:
+                plan_view(nxt[3], nxt[1], nxt[2])
         if sp.shape[0] == 0:
             continue
         out.append(F.apply(boxsize, chunk_ends(boxsize), sp, ep, mean_pixel[v][mask], lam[v][mask], opacity[v][mask],

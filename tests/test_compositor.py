@@ -253,3 +253,28 @@ def test_bundled_scene_front_slice_against_oracle_gpu():
     for name, a, b in (("mean", got[1], gm), ("lambda", got[2], gL), ("opacity", got[3], go), ("l", got[4], gl)):
         scale = float(np.abs(b).max())
         np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4 * scale, err_msg=name)
+
+
+@pytest.mark.gpu
+def test_planned_view_equals_unplanned_gpu():
+    """compositor.plan_view only moves the prologue to a side stream: same element list, same image, same grads."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    v = wl.splat_view(640, 360, 60_000, seed=3, device="cuda")
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+    res = []
+    for planned in (False, True, True):
+        if planned:
+            compositor.plan_view(v.boxsize, v.startpoint, v.endpoint)
+            assert len(compositor._plans) == 1
+        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                        v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+        assert len(compositor._plans) == 0          # consumed
+        img.backward(gI)
+        res.append([img.detach().clone()] + [t.grad.clone() for t in (m, lam, o, l)])
+    for other in res[1:]:
+        assert torch.allclose(res[0][0], other[0], rtol=1e-5, atol=1e-6)   # colour sums use float atomics
+        for a, b in zip(res[0][1:], other[1:]):
+            assert torch.equal(a, b)
