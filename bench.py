@@ -494,14 +494,23 @@ def splat_legs(args, device, rank, world):
     for _ in range(steps):
         bucket.zero_()
         t0.record()
-        elems = sum(one_view(i, plan_next=True) for i in range(len(mine)))
+        marks = []
+        elems = 0
+        host_t0 = time.perf_counter()
+        for i in range(len(mine)):
+            if os.environ.get("BENCH_MV_TRACE") and i % 8 == 0:
+                marks.append(ev())
+                marks[-1].record()
+            elems += one_view(i, plan_next=True)
+        host_ms = (time.perf_counter() - host_t0) * 1e3
         t1.record()
         vw.allreduce_param_grads(bucket)
         t2.record()
         torch.cuda.synchronize()
         step_ms += t0.elapsed_time(t2)
         ar_ms += t1.elapsed_time(t2)
-        print(f"multi-view step: {t0.elapsed_time(t2):.2f} ms", file=sys.stderr)
+        print(f"multi-view step: {t0.elapsed_time(t2):.2f} ms (host enqueue loop {host_ms:.2f} ms) " +
+              " ".join(f"{marks[j].elapsed_time(marks[j + 1]) / 8:.3f}" for j in range(len(marks) - 1)), file=sys.stderr)
     tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
     _, max_ar = vw.aggregate_throughput(0, ar_ms / steps, device)
     # the rank that arrives last waits for nobody: its time is the collective itself

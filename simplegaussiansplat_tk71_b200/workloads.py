@@ -192,7 +192,12 @@ class SplatView:
 
     @property
     def elements(self) -> int:
-        return int(self.boxsize.sum().item())
+        # cached: the reduction + .item() is a full device sync, which a timed loop must not pay per view
+        c = self.__dict__.get("_elements")
+        if c is None:
+            c = int(self.boxsize.sum().item())
+            self.__dict__["_elements"] = c
+        return c
 
 
 def splat_view(width: int = 1920, height: int = 1080, n: int = 1_000_000, seed: int = 1080, device="cpu",
