@@ -444,7 +444,7 @@ def splat_legs(args, device, rank, world):
         sc, (m, lam, o, l) = scenes[i % distinct], leaves[i % distinct]
         if plan_next:  # the next view's prologue (offsets, element count) runs on a side stream meanwhile
             nx = scenes[(i + 1) % distinct]
-            compositor.plan_view(nx.boxsize, nx.startpoint, nx.endpoint)
+            compositor.plan_view(nx.boxsize, nx.startpoint, nx.endpoint, 1920, 1080)
         for t_ in (m, lam, o, l):
             t_.grad = None
         img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)
@@ -462,27 +462,38 @@ def splat_legs(args, device, rank, world):
     for _ in range(2):
         one_view(0)
     torch.cuda.synchronize()
-    # (i) single view
+    # (i) single view, through both compositor routes (compositor.ROUTE is the default one and the headline)
     reps = 9
-    a, bb, c = ev(), ev(), ev()
-    tfs, tbs = [], []
     sc, (m, lam, o, l) = scenes[0], leaves[0]
-    for _ in range(reps):
-        for t_ in (m, lam, o, l):
-            t_.grad = None
-        a.record()
-        img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)
-        bb.record()
-        img.backward(gI)
-        c.record()
-        torch.cuda.synchronize()
-        tfs.append(a.elapsed_time(bb))
-        tbs.append(bb.elapsed_time(c))
-    tfs.sort()
-    tbs.sort()
-    tf, tb = tfs[reps // 2], tbs[reps // 2]     # medians: the forward has one host sync and is sensitive to host jitter
-    out = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n, "fwd_ms": tf, "bwd_ms": tb,
-           "ms": tf + tb, "unit": "ms per view (render + backward), median of 9"}
+
+    def time_single():
+        a, bb, c = ev(), ev(), ev()
+        tfs, tbs = [], []
+        for it in range(reps + 2):
+            for t_ in (m, lam, o, l):
+                t_.grad = None
+            a.record()
+            img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)
+            bb.record()
+            img.backward(gI)
+            c.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tfs.append(a.elapsed_time(bb))
+                tbs.append(bb.elapsed_time(c))
+        tfs.sort()
+        tbs.sort()
+        # medians: the forward has one host sync and is sensitive to host jitter
+        return {"fwd_ms": tfs[reps // 2], "bwd_ms": tbs[reps // 2], "ms": tfs[reps // 2] + tbs[reps // 2]}
+
+    default_route = compositor.ROUTE
+    routes = {}
+    for r in ("lists", "tiles"):
+        compositor.ROUTE = r
+        routes[r] = time_single()
+    compositor.ROUTE = default_route
+    out = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n, "route": default_route,
+           **routes[default_route], "unit": "ms per view (render + backward), median of 9", "routes": routes}
     # (ii) multi-view step
     steps = 3
     if world > 1:
@@ -548,24 +559,34 @@ def c2_leg(device):
         m, lam, o, l = (sc.mean.float().requires_grad_(True), sc.lam.clone().requires_grad_(True),
                         sc.opacity.clone().requires_grad_(True), sc.l_d.clone().requires_grad_(True))
         gI = torch.rand(sc.height + 1, sc.width + 1, 3, device=device) + 0.1
-        ts = []
-        for i in range(5):
-            for t_ in (m, lam, o, l):
-                t_.grad = None
-            a, b = ev(), ev()
-            a.record()
-            img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, sc.width, sc.height)
-            img.backward(gI)
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        ts = sorted(ts[1:])
-        per_view.append({"view": sc.name, "elements": sc.elements, "gaussians": sc.n, "splat_ms": ts[len(ts) // 2]})
+        by_route = {}
+        default_route = compositor.ROUTE
+        for r in ("lists", "tiles"):
+            compositor.ROUTE = r
+            ts = []
+            for i in range(5):
+                for t_ in (m, lam, o, l):
+                    t_.grad = None
+                a, b = ev(), ev()
+                a.record()
+                img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, sc.width,
+                              sc.height)
+                img.backward(gI)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ts = sorted(ts[1:])
+            by_route[r] = ts[len(ts) // 2]
+        compositor.ROUTE = default_route
+        per_view.append({"view": sc.name, "elements": sc.elements, "gaussians": sc.n, "route": default_route,
+                         "splat_ms": by_route[default_route], "splat_ms_by_route": by_route})
         del m, lam, o, l, gI, img
     # the scan ops on view 0's sorted element list
     sc = views[0]
+    default_route, compositor.ROUTE = compositor.ROUTE, "lists"
     _, v = compositor._render_forward(sc.boxsize, sc.startpoint, sc.endpoint, sc.mean.float(), sc.lam, sc.opacity,
                                       sc.l_d, sc.width, sc.height)
+    compositor.ROUTE = default_route
     x, key = v.x_s, v.key_s
     n = x.numel()
     k = int(torch.unique_consecutive(key).numel())

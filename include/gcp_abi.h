@@ -228,6 +228,43 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
                         const float *l_d, const float *grad_image, int64_t N, int W, float *g_mean, float *g_lam,
                         float *g_opac, float *g_l, gcp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused compositor route (csrc/gcp_tile.cu).  The same per-pixel segmented scan —
+ * T_i = prod_{j<i}(1-alpha_j), C = sum T_i alpha_i l_i, gs_model.py:544-566 + :498-514 forward, :627-663 +
+ * :733-783 backward — evaluated one pixel per lane without materialising the element lists: the image is cut
+ * into tiles of gcp_tile_width() x gcp_tile_height() = 32 pixels, a box contributes one (tile, Gaussian) pair
+ * per tile it touches, the pairs are stably sorted by tile (Gaussian = depth order kept inside a tile, hence
+ * inside every pixel: the order of torch.sort at gs_model.py:547), and one warp walks each tile's list.
+ * No float atomics: results are bitwise reproducible.  Boxes are clipped to [0,W] x [0,H].
+ *   toff       i64[n+1]  exclusive offsets of the Gaussians' pairs (Gaussian-major, row-major over its tiles)
+ *   rec        32-byte aligned, 64 bytes per Gaussian (packed tables)
+ *   tile_start i32[gcp_tile_num_tiles(W,H)+1], pair_gid i32[P]: the tile-sorted pair list
+ *   t_keep     f32[P*32]: exclusive T of every (pair, lane), kept by the forward for the backward
+ *   partial    f32[P*8]: per-pair gradient sums, Gaussian-major
+ * ------------------------------------------------------------------------------------------------ */
+int gcp_tile_width(void);
+int gcp_tile_height(void);
+int gcp_tile_num_tiles(int W, int H);
+/* toff and totals i64[1] = {P} (device memory) from the boxes; temp >= gcp_tile_prepare_bytes(n). */
+size_t gcp_tile_prepare_bytes(int64_t n);
+int gcp_tile_prepare(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, int64_t *toff, int64_t *totals,
+                     void *temp, size_t temp_bytes, gcp_stream_t stream);
+int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
+                  const int32_t *ep, const int64_t *toff, int64_t n, int W, int H, int32_t *rec,
+                  gcp_stream_t stream);
+/* pair emission + stable sort by tile + tile offsets; temp >= gcp_tile_bin_bytes(P). */
+size_t gcp_tile_bin_bytes(int64_t P);
+int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
+                 int32_t *tile_start, int32_t *pair_gid, void *temp, size_t temp_bytes, gcp_stream_t stream);
+/* image f32[(H+1)*(W+1)*3] is written completely (no need to zero it). */
+int gcp_tile_render(const int32_t *tile_start, const int32_t *pair_gid, const int32_t *rec, int64_t P, int W, int H,
+                    float *image, float *t_keep, gcp_stream_t stream);
+int gcp_tile_backward(const int32_t *tile_start, const int32_t *pair_gid, const int32_t *rec, const float *t_keep,
+                      const float *grad_image, int64_t P, int W, int H, float *partial, gcp_stream_t stream);
+/* g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3] written completely (d_l = (sum d)/l, gs_model.py:763-766). */
+int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,
+                    float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libgcp_b200.so")
 SOURCES = {
     "gcp_abi.cu": ["gcp_device.cuh", "gcp_fwd.cuh", "gcp_bwd.cuh", "gcp_blk.cuh"],
     "gcp_splat.cu": [],
+    "gcp_tile.cu": [],
 }
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 

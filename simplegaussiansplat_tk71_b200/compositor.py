@@ -49,6 +49,11 @@ KEY_STRIDE = 10000  # pixel key = y*10000 + x  (gs_model.py:541)
 # True: build the sorted element list with the sort-free counting placement (gcp_splat_place);
 # False: expand to N (key, gid) pairs and radix-sort them (gcp_splat_expand + gcp_splat_sort).  Same output, bit for bit.
 USE_PLACEMENT = True
+# "tiles": the fused route (csrc/gcp_tile.cu) — one warp per 8x4-pixel tile walks the tile's Gaussians in depth order
+#          with the running T of its pixels in registers; no element list, no float atomics (bitwise reproducible).
+# "lists": the element-list route — placement, alpha, the scan ops a1/a3 (gcp_cumprod_fwd/bwd), colour, un-sort.
+# Same image and gradients within fp32 rounding (tests/test_compositor.py runs every case through both).
+ROUTE = "tiles"
 
 
 def _p(t):
@@ -75,7 +80,26 @@ _side_streams = {}
 
 
 class _Plan:
-    __slots__ = ("boxsize", "startpoint", "endpoint", "sp", "ep", "offs", "host", "event")
+    __slots__ = ("boxsize", "startpoint", "endpoint", "sp", "ep", "offs", "host", "event", "route")
+
+
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (the kernels read the tables with vector loads; a sliced view may not be)."""
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
+def _prologue_tiles(L, dev, startpoint, endpoint, n, W, H):
+    """(tile, Gaussian) pair offsets per Gaussian and the pair count, on the current stream."""
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    sp = _aligned(startpoint.to(torch.int32))
+    ep = _aligned(endpoint.to(torch.int32))
+    toff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    totals = torch.empty(1, dtype=torch.int64, device=dev)
+    temp = _scratch_bytes(dev, "prepare", int(L.gcp_tile_prepare_bytes(n)))
+    _lib.check(L.gcp_tile_prepare(_p(sp), _p(ep), n, W, H, _p(toff), _p(totals), _p(temp), temp.numel(), stream),
+               "gcp_tile_prepare")
+    return sp, ep, toff, totals
 
 
 def _prologue(L, dev, boxsize, startpoint, endpoint, n):
@@ -92,17 +116,21 @@ def _prologue(L, dev, boxsize, startpoint, endpoint, n):
     return sp, ep, offs, totals
 
 
-def plan_view(boxsize, startpoint, endpoint) -> None:
+def plan_view(boxsize, startpoint, endpoint, image_width=None, image_height=None) -> None:
     """Optional: queue a view's prologue (offsets and the element / pair counts) on a side stream ahead of its
     `custom_autograd_grouped_cumprod.apply(...)`.  The one host sync of a view then finds its two numbers already
     in pinned host memory instead of draining the device queue: a driver that renders many views (views.py,
     bench.py) plans view i+1 before it runs view i.  The plan is consumed by the next apply() that receives the
-    SAME three tensors; the tensors must not be modified in between."""
+    SAME three tensors (and, for the tile route, the same image size — without it that route cannot plan and
+    apply() runs the prologue itself); the tensors must not be modified in between."""
     dev = startpoint.device
     if dev.type != "cuda":
         raise RuntimeError("plan_view needs CUDA tensors")
     L = _lib.lib()
     n = boxsize.numel()
+    tiles = ROUTE == "tiles"
+    if tiles and (image_width is None or image_height is None):
+        return
     with torch.cuda.device(dev):
         side = _side_streams.get(dev.index)
         if side is None:
@@ -111,8 +139,14 @@ def plan_view(boxsize, startpoint, endpoint) -> None:
         pl = _Plan()
         pl.boxsize, pl.startpoint, pl.endpoint = boxsize, startpoint, endpoint  # keep the addresses alive
         with torch.cuda.stream(side):
-            pl.sp, pl.ep, pl.offs, totals = _prologue(L, dev, boxsize, startpoint, endpoint, n)
-            pl.host = torch.empty(2, dtype=torch.int64, pin_memory=True)
+            if tiles:
+                pl.sp, pl.ep, pl.offs, totals = _prologue_tiles(L, dev, startpoint, endpoint, n, int(image_width),
+                                                                int(image_height))
+                pl.route = ("tiles", int(image_width), int(image_height))
+            else:
+                pl.sp, pl.ep, pl.offs, totals = _prologue(L, dev, boxsize, startpoint, endpoint, n)
+                pl.route = ("lists",)
+            pl.host = torch.empty(totals.numel(), dtype=torch.int64, pin_memory=True)
             pl.host.copy_(totals, non_blocking=True)
             pl.event = torch.cuda.Event()
             pl.event.record(side)
@@ -127,10 +161,88 @@ class _View:
                  "goff", "rec_a", "rec_b", "seg_off", "cstart", "pgid", "btab", "P")
 
 
+class _TileView:
+    """Tile route: the tile-sorted pair list, the packed tables and the exclusive T of every (pair, lane)
+    (128 B per pair) kept for the backward."""
+    __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "pgid", "tkeep", "l_d")
+
+
+def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
+    dev = startpoint.device
+    L = _lib.lib()
+    v = _TileView()
+    v.W, v.H = W, H
+    n = boxsize.numel()
+    v.n = n
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        stream = cur.cuda_stream
+        plan = _plans.pop((_p(boxsize), _p(startpoint), _p(endpoint), n), None)
+        if plan is not None and plan.route != ("tiles", W, H):
+            plan = None
+        if plan is not None:
+            cur.wait_event(plan.event)
+            sp, ep, toff, totals = plan.sp, plan.ep, plan.offs, None
+            for t_ in (sp, ep, toff):
+                t_.record_stream(cur)
+        else:
+            sp, ep, toff, totals = _prologue_tiles(L, dev, startpoint, endpoint, n, W, H)
+        v.toff = toff
+        v.l_d = _aligned(l_d.detach().to(torch.float32))
+        mean_ = _aligned(mean.detach().to(torch.float32))
+        lam_ = _aligned(lam.detach().to(torch.float32).reshape(n, 4))
+        opac_ = opacity.detach().to(torch.float32).reshape(n).contiguous()
+        # queued before the host waits for the pair count, so the device has work meanwhile
+        v.rec = torch.empty((n, 16), dtype=torch.int32, device=dev)
+        _lib.check(L.gcp_tile_pack(_p(mean_), _p(lam_), _p(opac_), _p(v.l_d), _p(sp), _p(ep), _p(toff), n, W, H,
+                                   _p(v.rec), stream), "gcp_tile_pack")
+        image = torch.empty((H + 1, W + 1, 3), dtype=torch.float32, device=dev)  # every pixel is written by its lane
+        if plan is not None:
+            plan.event.synchronize()
+            (P,) = plan.host.tolist()
+        else:
+            (P,) = totals.tolist()   # the one host sync of a view, like the reference's .item() at uitility.py:348
+        if P >= 2 ** 31 - 64:
+            raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
+        v.P = P
+        v.tstart = torch.empty(int(L.gcp_tile_num_tiles(W, H)) + 1, dtype=torch.int32, device=dev)
+        v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+        v.tkeep = torch.empty(max(P, 1) * 32, dtype=torch.float32, device=dev)
+        temp = _scratch_bytes(dev, "bin", int(L.gcp_tile_bin_bytes(P)))
+        _lib.check(L.gcp_tile_bin(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.pgid), _p(temp),
+                                  temp.numel(), stream), "gcp_tile_bin")
+        _lib.check(L.gcp_tile_render(_p(v.tstart), _p(v.pgid), _p(v.rec), P, W, H, _p(image), _p(v.tkeep), stream),
+                   "gcp_tile_render")
+    return image, v
+
+
+def _render_backward_tiles(v: _TileView, grad_image):
+    dev = grad_image.device
+    n = v.n
+    L = _lib.lib()
+    g_mean = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    g_lam = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    g_opac = torch.empty((n,), dtype=torch.float32, device=dev)
+    g_l = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    gI = grad_image.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        partial = torch.empty(max(v.P, 1) * 8, dtype=torch.float32, device=dev)
+        _lib.check(L.gcp_tile_backward(_p(v.tstart), _p(v.pgid), _p(v.rec), _p(v.tkeep), _p(gI), v.P, v.W, v.H,
+                                       _p(partial), stream), "gcp_tile_backward")
+        _lib.check(L.gcp_tile_reduce(_p(partial), _p(v.toff), _p(v.l_d), n, _p(g_mean), _p(g_lam), _p(g_opac),
+                                     _p(g_l), stream), "gcp_tile_reduce")
+    return g_mean, g_lam, g_opac, g_l
+
+
 def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
     dev = startpoint.device
     if dev.type != "cuda":
         raise RuntimeError("custom_autograd_grouped_cumprod needs CUDA tensors (there is no CPU path)")
+    if ROUTE == "tiles":
+        return _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H)
+    if ROUTE != "lists":
+        raise ValueError(f"unknown compositor route {ROUTE!r}")
     L = _lib.lib()
     v = _View()
     v.W, v.H = W, H
@@ -141,6 +253,8 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         plan = _plans.pop((_p(boxsize), _p(startpoint), _p(endpoint), n), None)
+        if plan is not None and plan.route != ("lists",):
+            plan = None
         if plan is not None:
             # planned ahead (plan_view): the prologue ran on a side stream, its totals are in pinned memory
             cur = torch.cuda.current_stream(dev)
@@ -213,7 +327,9 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
     return image, v
 
 
-def _render_backward(v: _View, grad_image):
+def _render_backward(v, grad_image):
+    if isinstance(v, _TileView):
+        return _render_backward_tiles(v, grad_image)
     dev = grad_image.device
     n = v.n
     if v.N == 0:

@@ -1,0 +1,525 @@
+// gcp_tile.cu — the fused compositor route: exclusive transmittance, colour sum and the
+// division-free backward in ONE pass per direction, without materialising the per-pixel element lists.
+//
+// The per-pixel segmented scan  T_i = prod_{j<i} (1 - alpha_j),  C = sum_i T_i alpha_i l_i  (gs_model.py:544-566,
+// :498-514) is evaluated with one pixel per lane: the image is cut into tiles of 8 x 4 pixels = one warp, every
+// box contributes one (tile, Gaussian) pair per tile it touches, the pairs are sorted by tile with a stable radix
+// sort — the Gaussians arrive in depth order, so every tile list (and with it every pixel list) stays in depth
+// order, the same order torch.sort gives the reference at gs_model.py:547 — and a warp walks its tile's list
+// with the running T of its pixels in registers.
+//
+//   forward   k_tile_render   : alpha = o * exp(-1/2 d Lambda d^T) (:493-495,:533-535), T, colour; the exclusive
+//                               T of every (pair, lane) is kept for the backward (128 contiguous bytes per pair)
+//   backward  k_tile_backward : the list walked in reverse with U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1}
+//                               (w = <dL/dI, alpha l>), dL/dalpha_i = T_i <dL/dI, l_i> - T_i U_i — no division by
+//                               1-alpha (:736,:747,:757 divide) — and the reference's per-element gradients
+//                               (:733-766) summed over the lanes of the pair in a fixed order;
+//             k_tile_reduce   : the partial sums of a Gaussian's pairs added in pair order (:776-783).
+// No float atomics anywhere: a pixel belongs to one lane, a partial to one pair — bitwise reproducible.
+// Elements whose inclusive product is 0 contribute nothing and get no gradient (gs_model.py:575-578).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "gcp_abi.h"
+
+namespace {
+
+constexpr int TSX = 3, TSY = 2;                 // tile = 8 x 4 pixels, lane = (y & 3) * 8 + (x & 7)
+constexpr int TW = 1 << TSX, TH = 1 << TSY;
+static_assert(TW * TH == 32, "one tile is one warp");
+constexpr int REC_WORDS = 16;                   // per-Gaussian record: 64 bytes = two 32-byte sectors
+constexpr int CHP = 8;                          // consecutive pairs per thread in the emit kernel
+
+inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
+    int64_t b = (work + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return static_cast<unsigned>(b);
+}
+inline int key_bits(int max_key) {
+    int b = 1;
+    while (b < 31 && (1 << b) <= max_key) ++b;
+    return b;
+}
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// box of Gaussian g clipped to the image [0,W] x [0,H] (the caller clamps already, gs_model.py:419-425)
+struct Box {
+    int sx, sy, ex, ey;
+};
+__host__ __device__ __forceinline__ Box clip_box(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
+                                                 int64_t g, int W, int H) {
+    Box b;
+    b.sx = sp[2 * g] > 0 ? sp[2 * g] : 0;
+    b.sy = sp[2 * g + 1] > 0 ? sp[2 * g + 1] : 0;
+    b.ex = ep[2 * g] < W ? ep[2 * g] : W;
+    b.ey = ep[2 * g + 1] < H ? ep[2 * g + 1] : H;
+    return b;
+}
+// (tile, Gaussian) pairs of one box (0 for an empty / inverted box)
+struct TilePairCount {
+    const int32_t *sp, *ep;
+    int W, H;
+    __host__ __device__ __forceinline__ int64_t operator()(int64_t g) const {
+        const Box b = clip_box(sp, ep, g, W, H);
+        if (b.ex < b.sx || b.ey < b.sy) return 0;
+        return static_cast<int64_t>((b.ex >> TSX) - (b.sx >> TSX) + 1) * ((b.ey >> TSY) - (b.sy >> TSY) + 1);
+    }
+};
+
+__global__ void k_tile_totals(const int64_t *__restrict__ toff, int64_t n, int64_t *__restrict__ totals) {
+    totals[0] = toff[n];
+}
+
+// rec[g] = {mx, my, l00, l01 | l10, l11, o, l0 || l1, l2, sx, sy | ex, ey, toff, 0}
+__global__ void __launch_bounds__(256)
+k_tile_pack(const float *__restrict__ mean, const float *__restrict__ lam, const float *__restrict__ opac,
+            const float *__restrict__ l_d, const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
+            const int64_t *__restrict__ toff, int64_t n, int W, int H, int4 *__restrict__ rec) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const float2 m = __ldg(reinterpret_cast<const float2 *>(mean) + g);
+    const float4 L = __ldg(reinterpret_cast<const float4 *>(lam) + g);
+    const Box b = clip_box(sp, ep, g, W, H);
+    auto f = [](float v) { return __float_as_int(v); };
+    rec[4 * g] = make_int4(f(m.x), f(m.y), f(L.x), f(L.y));
+    rec[4 * g + 1] = make_int4(f(L.z), f(L.w), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
+    rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
+    rec[4 * g + 3] = make_int4(b.ex, b.ey, static_cast<int>(__ldg(toff + g)), 0);
+}
+
+// first index g with off[g+1] > e
+__device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, int64_t n, int64_t e) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid + 1) > e) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+// pair p of Gaussian g (Gaussian-major, row-major over the tiles of its box): ptile[p] = tile index, pgid[p] = g
+__global__ void __launch_bounds__(256)
+k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
+             int64_t n, int64_t P, int W, int H, int ntx, int32_t *__restrict__ ptile, int32_t *__restrict__ pgid) {
+    const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CHP;
+    if (p0 >= P) return;
+    int64_t g = find_owner(toff, n, p0);
+    int64_t gbeg = __ldg(toff + g), gend = __ldg(toff + g + 1);
+    Box b = clip_box(sp, ep, g, W, H);
+    int tx0 = b.sx >> TSX, ty0 = b.sy >> TSY, nx = (b.ex >> TSX) - tx0 + 1;
+    for (int i = 0; i < CHP && p0 + i < P; ++i) {
+        const int64_t p = p0 + i;
+        while (p >= gend) {  // skips Gaussians without pairs too
+            ++g;
+            gbeg = gend;
+            gend = __ldg(toff + g + 1);
+            b = clip_box(sp, ep, g, W, H);
+            tx0 = b.sx >> TSX; ty0 = b.sy >> TSY; nx = (b.ex >> TSX) - tx0 + 1;
+        }
+        const int local = static_cast<int>(p - gbeg);
+        const int r = local / nx;
+        ptile[p] = (ty0 + r) * ntx + tx0 + (local - r * nx);
+        pgid[p] = static_cast<int32_t>(g);
+    }
+}
+
+// tstart[t] = first pair of tile t in the tile-sorted pair list (tstart[ntiles] = P), empty tiles included
+__global__ void __launch_bounds__(256)
+k_tile_start(const int32_t *__restrict__ ptile_s, int64_t P, int ntiles, int32_t *__restrict__ tstart) {
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    const int prev = (p == 0) ? -1 : __ldg(ptile_s + p - 1);
+    const int cur = (p == P) ? ntiles : __ldg(ptile_s + p);
+    for (int c = prev + 1; c <= cur; ++c) tstart[c] = static_cast<int32_t>(p);
+}
+
+// one 32-byte sector in one instruction (LDG.256, sm_100)
+__device__ __forceinline__ void ldg256(const void *p, int4 &u, int4 &v) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w), "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+}
+
+struct RecRegs {
+    int4 a, b, c, d;
+};
+__device__ __forceinline__ RecRegs load_rec(const int4 *__restrict__ rec, int g) {
+    RecRegs r;
+    ldg256(rec + 4 * static_cast<int64_t>(g), r.a, r.b);
+    ldg256(rec + 4 * static_cast<int64_t>(g) + 2, r.c, r.d);
+    return r;
+}
+
+// What the walk needs of a pair, staged in shared memory by the lane that loaded it (three broadcast LDS.128 per
+// pair in the walk): {mx, my, l00, l01} {l10, l11, o, l0} {l1, l2, coverage mask of the tile, Gaussian-major pair id}
+struct PairSlot {
+    float4 a, b;
+    float2 c;
+    uint32_t mask;
+    int32_t q;
+};
+static_assert(sizeof(PairSlot) == 48, "three 16-byte words");
+
+__device__ __forceinline__ void stage_pair(PairSlot *slot, const RecRegs &r, bool live, int tx, int ty, int x0, int y0) {
+    const int sx = r.c.z, sy = r.c.w, ex = r.d.x, ey = r.d.y;
+    // lanes of the tile inside the box: columns [xa, xb] of rows [ya, yb]
+    const int xa = max(sx, x0) - x0, xb = min(ex, x0 + TW - 1) - x0;
+    const int ya = max(sy, y0) - y0, yb = min(ey, y0 + TH - 1) - y0;
+    uint32_t mask = 0;
+    if (live && xa <= xb && ya <= yb) {
+        const uint32_t xm = ((2u << xb) - 1u) & ~((1u << xa) - 1u);
+        const uint32_t rows = (0x01010101u >> (8 * (TH - 1 - (yb - ya)))) << (8 * ya);
+        mask = xm * rows;
+    }
+    const int tx0 = sx >> TSX, ty0 = sy >> TSY, nx = (ex >> TSX) - tx0 + 1;
+    slot->a = make_float4(__int_as_float(r.a.x), __int_as_float(r.a.y), __int_as_float(r.a.z), __int_as_float(r.a.w));
+    slot->b = make_float4(__int_as_float(r.b.x), __int_as_float(r.b.y), __int_as_float(r.b.z), __int_as_float(r.b.w));
+    slot->c = make_float2(__int_as_float(r.c.x), __int_as_float(r.c.y));
+    slot->mask = mask;
+    slot->q = r.d.z + (ty - ty0) * nx + (tx - tx0);
+}
+
+struct PairEval {
+    float d0, d1, X0, X1, gk, x;
+};
+// g = exp(-1/2 (r-m) Lambda (r-m)^T) with X = (r-m) Lambda (gs_model.py:495, :745); x = 1 - o g (:533-535)
+__device__ __forceinline__ PairEval eval_pair(const float4 &a, const float4 &b, float px, float py) {
+    PairEval e;
+    e.d0 = px - a.x;
+    e.d1 = py - a.y;
+    e.X0 = e.d0 * a.z + e.d1 * b.x;
+    e.X1 = e.d0 * a.w + e.d1 * b.y;
+    e.gk = expf(-0.5f * (e.X0 * e.d0 + e.X1 * e.d1));
+    e.x = 1.0f - b.z * e.gk;
+    return e;
+}
+
+constexpr int TILE_WARPS = 8;
+
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
+              int ntx, int ntiles, int W, int H, float *__restrict__ image, float *__restrict__ tkeep) {
+    __shared__ PairSlot slots[TILE_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int t = blockIdx.x * TILE_WARPS + wib;
+    if (t >= ntiles) return;  // warp-uniform; only __syncwarp below
+    const int ty = t / ntx, tx = t - ty * ntx;
+    const int x0 = tx << TSX, y0 = ty << TSY;
+    const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
+    const float px = static_cast<float>(ix), py = static_cast<float>(iy);
+    const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
+    PairSlot *sl = slots[wib];
+    float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    // software pipeline over batches of 32 pairs: ids two batches ahead, records one batch ahead
+    int g1 = 0;
+    RecRegs r = {};
+    if (lo + lane < hi) r = load_rec(rec, __ldg(pgid_s + lo + lane));
+    if (lo + 32 + lane < hi) g1 = __ldg(pgid_s + lo + 32 + lane);
+    for (int64_t b = lo; b < hi; b += 32) {
+        stage_pair(sl + lane, r, b + lane < hi, tx, ty, x0, y0);
+        int g2 = 0;
+        if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
+        if (b + 32 + lane < hi) r = load_rec(rec, g1);
+        g1 = g2;
+        __syncwarp();
+        const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
+        float *tk = tkeep + b * 32 + lane;
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {
+            const float4 A = sl[k].a, B = sl[k].b;
+            const float2 C = sl[k].c;
+            const bool cov = (sl[k].mask >> lane) & 1u;
+            const PairEval e = eval_pair(A, B, px, py);
+            const float tin = T * e.x;
+            __stcs(tk + k * 32, T);
+            if (cov) {
+                if (tin != 0.0f) {
+                    const float ta = T * (1.0f - e.x);
+                    c0 = fmaf(ta, B.w, c0);
+                    c1 = fmaf(ta, C.x, c1);
+                    c2 = fmaf(ta, C.y, c2);
+                }
+                T = tin;
+            }
+        }
+        __syncwarp();
+    }
+    if (ix <= W && iy <= H) {
+        float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+        p[0] = c0; p[1] = c1; p[2] = c2;
+    }
+}
+
+// sum of 8 values per lane over the 32 lanes in 9 shuffles (halving butterfly): afterwards the four lanes
+// 4c' .. 4c'+3 hold component comp(c') = 4*bit2(c') + 2*bit1(c') + bit0(c'), c' = lane >> 2 with its bits read as
+// (lane bit 4, lane bit 3, lane bit 2).  The order of the additions is fixed: bitwise reproducible.
+__device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
+    const unsigned F = 0xffffffffu;
+    float k4[4], k2[2];
+    {
+        const bool h = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = h ? v[4 + i] : v[i], send = h ? v[i] : v[4 + i];
+            k4[i] = keep + __shfl_xor_sync(F, send, 16);
+        }
+    }
+    {
+        const bool h = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = h ? k4[2 + i] : k4[i], send = h ? k4[i] : k4[2 + i];
+            k2[i] = keep + __shfl_xor_sync(F, send, 8);
+        }
+    }
+    const bool h = lane & 4;
+    float s = (h ? k2[1] : k2[0]) + __shfl_xor_sync(F, h ? k2[0] : k2[1], 4);
+    s += __shfl_xor_sync(F, s, 2);
+    s += __shfl_xor_sync(F, s, 1);
+    return s;
+}
+
+// partial[q] = {sum g dalpha, sum d, sum coef X0, sum coef X1, sum hc d0 d0, sum hc d0 d1, sum hc d1 d1, 0}
+// over the pixels of pair q (coef = alpha dalpha, hc = -coef/2), see gs_model.py:733-766
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
+                const float *__restrict__ tkeep, const float *__restrict__ gimg, int ntx, int ntiles, int W, int H,
+                float *__restrict__ partial) {
+    __shared__ PairSlot slots[TILE_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int t = blockIdx.x * TILE_WARPS + wib;
+    if (t >= ntiles) return;
+    const int ty = t / ntx, tx = t - ty * ntx;
+    const int x0 = tx << TSX, y0 = ty << TSY;
+    const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
+    const float px = static_cast<float>(ix), py = static_cast<float>(iy);
+    const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
+    if (lo >= hi) return;
+    float pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
+    if (ix <= W && iy <= H) {
+        const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+        pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
+    }
+    PairSlot *sl = slots[wib];
+    const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float U = 0.0f;
+    // batches of 32 pairs from the END of the tile's list; batch j covers [bb, bb + m), bb = hi - 32 (j+1) clipped
+    int g1 = 0;
+    RecRegs r = {};
+    {
+        const int64_t bb = (hi - 32 > lo) ? hi - 32 : lo;
+        if (bb + lane < hi) r = load_rec(rec, __ldg(pgid_s + bb + lane));
+        const int64_t e1 = bb, b1 = (e1 - 32 > lo) ? e1 - 32 : lo;
+        if (b1 + lane < e1) g1 = __ldg(pgid_s + b1 + lane);
+    }
+    for (int64_t be = hi; be > lo;) {
+        const int64_t bb = (be - 32 > lo) ? be - 32 : lo;
+        const int m = static_cast<int>(be - bb);
+        stage_pair(sl + lane, r, lane < m, tx, ty, x0, y0);
+        // next batch [b1, bb), the one after [b2, b1)
+        const int64_t b1 = (bb - 32 > lo) ? bb - 32 : lo;
+        const int64_t b2 = (b1 - 32 > lo) ? b1 - 32 : lo;
+        int g2 = 0;
+        if (b2 + lane < b1) g2 = __ldg(pgid_s + b2 + lane);
+        if (b1 + lane < bb) r = load_rec(rec, g1);
+        g1 = g2;
+        __syncwarp();
+        const float *tk = tkeep + bb * 32 + lane;
+#pragma unroll 2
+        for (int k = m - 1; k >= 0; --k) {
+            const float4 A = sl[k].a, B = sl[k].b;
+            const float2 C = sl[k].c;
+            const bool cov = (sl[k].mask >> lane) & 1u;
+            const int q = sl[k].q;
+            const float T = __ldcs(tk + k * 32);
+            const PairEval e = eval_pair(A, B, px, py);
+            const bool alive = cov && (T * e.x != 0.0f);
+            const float alpha = 1.0f - e.x;
+            const float pgl = pg0 * B.w + pg1 * C.x + pg2 * C.y;
+            const float dalpha = alive ? T * pgl - T * U : 0.0f;
+            const float d = alive ? T * alpha * pgl : 0.0f;
+            if (cov) U = fmaf(e.x, U, alive ? alpha * pgl : 0.0f);   // U_{i-1} = w_i + x_i U_i
+            const float coef = B.z * e.gk * dalpha;
+            const float hc = -0.5f * coef;
+            float v[8] = {e.gk * dalpha, d, coef * e.X0, coef * e.X1, hc * e.d0 * e.d0, hc * e.d0 * e.d1,
+                          hc * e.d1 * e.d1, 0.0f};
+            const float s = reduce8(v, lane);
+            if ((lane & 3) == 0) partial[static_cast<int64_t>(q) * 8 + comp] = s;
+        }
+        __syncwarp();
+        be = bb;
+    }
+}
+
+// 8 lanes per Gaussian, lane c adds component c of the Gaussian's partials in pair order, then the lane owning a
+// component writes its gradients: d_l[c] = (sum d) / l[c] is the reference's d / l (gs_model.py:763-766)
+__global__ void __launch_bounds__(256)
+k_tile_reduce(const float *__restrict__ partial, const int64_t *__restrict__ toff, const float *__restrict__ l_d,
+              int64_t n, float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
+              float *__restrict__ g_l) {
+    const int c = threadIdx.x & 7;
+    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+    if (g >= n) return;
+    const int64_t b = __ldg(toff + g), e = __ldg(toff + g + 1);
+    float s = 0.0f;
+    int64_t q = b;
+    for (; q + 4 <= e; q += 4) {
+        const float v0 = __ldcs(partial + q * 8 + c), v1 = __ldcs(partial + (q + 1) * 8 + c);
+        const float v2 = __ldcs(partial + (q + 2) * 8 + c), v3 = __ldcs(partial + (q + 3) * 8 + c);
+        s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; q < e; ++q) s += __ldcs(partial + q * 8 + c);
+    switch (c) {
+        case 0: g_opac[g] = s; break;
+        case 1:
+            g_l[3 * g] = s / __ldg(l_d + 3 * g);
+            g_l[3 * g + 1] = s / __ldg(l_d + 3 * g + 1);
+            g_l[3 * g + 2] = s / __ldg(l_d + 3 * g + 2);
+            break;
+        case 2: g_mean[2 * g] = s; break;
+        case 3: g_mean[2 * g + 1] = s; break;
+        case 4: g_lam[4 * g] = s; break;
+        case 5: g_lam[4 * g + 1] = s; g_lam[4 * g + 2] = s; break;
+        case 6: g_lam[4 * g + 3] = s; break;
+        default: break;
+    }
+}
+
+struct BinLayout {
+    size_t ptile, pgid, ptile_s, cub, total, cub_bytes;
+};
+BinLayout bin_layout(int64_t P) {
+    BinLayout L;
+    const size_t pb = align256(static_cast<size_t>(P > 0 ? P : 1) * 4);
+    size_t a = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                    static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                    P > 0 ? P : 1, 0, 24);
+    L.cub_bytes = align256(a);
+    L.ptile = 0;
+    L.pgid = L.ptile + pb;
+    L.ptile_s = L.pgid + pb;
+    L.cub = L.ptile_s + pb;
+    L.total = L.cub + L.cub_bytes;
+    return L;
+}
+
+inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >= 32768; }
+inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
+inline int tiles_y(int H) { return (H + TH) >> TSY; }
+
+}  // namespace
+
+extern "C" {
+
+int gcp_tile_width(void) { return TW; }
+int gcp_tile_height(void) { return TH; }
+int gcp_tile_num_tiles(int W, int H) { return bad_image(W, H) ? 0 : tiles_x(W) * tiles_y(H); }
+
+size_t gcp_tile_prepare_bytes(int64_t n) {
+    size_t a = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, a, static_cast<const int64_t *>(nullptr), static_cast<int64_t *>(nullptr),
+                                  n > 0 ? n : 1);
+    return a + 256;
+}
+
+int gcp_tile_prepare(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, int64_t *toff, int64_t *totals,
+                     void *temp, size_t temp_bytes, gcp_stream_t stream) {
+    if (n < 0 || bad_image(W, H) || !toff || !totals) return GCP_ERR_INVALID_ARG;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(toff, 0, 8, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (n > 0) {
+        if (!sp || !ep || !temp) return GCP_ERR_INVALID_ARG;
+        auto pairs = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0),
+                                                     TilePairCount{sp, ep, W, H});
+        size_t need = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, need, pairs, toff + 1, n);
+        if (temp_bytes < need) return GCP_ERR_WORKSPACE;
+        size_t tb = temp_bytes;
+        e = cub::DeviceScan::InclusiveSum(temp, tb, pairs, toff + 1, n, st);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    k_tile_totals<<<1, 1, 0, st>>>(toff, n, totals);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
+                  const int32_t *ep, const int64_t *toff, int64_t n, int W, int H, int32_t *rec,
+                  gcp_stream_t stream) {
+    if (n < 0 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
+    if (n == 0) return GCP_OK;
+    if (!mean || !lam || !opac || !l_d || !sp || !ep || !toff || !rec) return GCP_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(rec) & 31) return GCP_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(mean) & 7) || (reinterpret_cast<uintptr_t>(lam) & 15)) return GCP_ERR_INVALID_ARG;
+    k_tile_pack<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        mean, lam, opac, l_d, sp, ep, toff, n, W, H, reinterpret_cast<int4 *>(rec));
+    return static_cast<int>(cudaGetLastError());
+}
+
+size_t gcp_tile_bin_bytes(int64_t P) { return P < 0 ? 0 : bin_layout(P).total; }
+
+int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
+                 int32_t *tile_start, int32_t *pair_gid, void *temp, size_t temp_bytes, gcp_stream_t stream) {
+    if (n < 0 || P < 0 || P >= (int64_t(1) << 31) - 64 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
+    if (!tile_start || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid))) return GCP_ERR_INVALID_ARG;
+    const BinLayout L = bin_layout(P);
+    if (temp_bytes < L.total) return GCP_ERR_WORKSPACE;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *t = static_cast<unsigned char *>(temp);
+    int32_t *ptile = reinterpret_cast<int32_t *>(t + L.ptile), *pgid = reinterpret_cast<int32_t *>(t + L.pgid);
+    int32_t *ptile_s = reinterpret_cast<int32_t *>(t + L.ptile_s);
+    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    if (P > 0) {
+        k_tile_pairs<<<blocks_for(P, 256 * CHP), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
+        size_t cb = L.cub_bytes;
+        // stable LSD radix sort on the tile bits only: inside a tile the Gaussians keep their (depth) order
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, ptile, ptile_s, pgid, pair_gid, P, 0,
+                                                        key_bits(ntiles), st);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    k_tile_start<<<blocks_for(P + 1, 256), 256, 0, st>>>(ptile_s, P, ntiles, tile_start);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_tile_render(const int32_t *tile_start, const int32_t *pair_gid, const int32_t *rec, int64_t P, int W, int H,
+                    float *image, float *t_keep, gcp_stream_t stream) {
+    if (P < 0 || bad_image(W, H) || !tile_start || !image) return GCP_ERR_INVALID_ARG;
+    if (P > 0 && (!pair_gid || !rec || !t_keep)) return GCP_ERR_INVALID_ARG;
+    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    k_tile_render<<<blocks_for(ntiles, TILE_WARPS), TILE_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), ntx, ntiles, W, H, image, t_keep);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_tile_backward(const int32_t *tile_start, const int32_t *pair_gid, const int32_t *rec, const float *t_keep,
+                      const float *grad_image, int64_t P, int W, int H, float *partial, gcp_stream_t stream) {
+    if (P < 0 || bad_image(W, H) || !tile_start || !grad_image) return GCP_ERR_INVALID_ARG;
+    if (P == 0) return GCP_OK;
+    if (!pair_gid || !rec || !t_keep || !partial) return GCP_ERR_INVALID_ARG;
+    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    k_tile_backward<<<blocks_for(ntiles, TILE_WARPS), TILE_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), t_keep, grad_image, ntx, ntiles, W, H, partial);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,
+                    float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
+    if (n < 0) return GCP_ERR_INVALID_ARG;
+    if (n == 0) return GCP_OK;
+    if (!toff || !l_d || !g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
+    k_tile_reduce<<<blocks_for(n, 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, toff, l_d, n, g_mean,
+                                                                                         g_lam, g_opac, g_l);
+    return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -96,7 +96,7 @@ def render_views(mean_pixel, box_half, z, lam, opacity, l_d, width: int, height:
             # on the host when its turn comes (compositor.plan_view)
             nxt = visible_boxes(mean_pixel[v + 1], box_half[v + 1], z[v + 1], width, height)
             if nxt[1].shape[0]:
-                plan_view(nxt[3], nxt[1], nxt[2])
+                plan_view(nxt[3], nxt[1], nxt[2], width, height)
         if sp.shape[0] == 0:
             continue
         out.append(F.apply(boxsize, chunk_ends(boxsize), sp, ep, mean_pixel[v][mask], lam[v][mask], opacity[v][mask],

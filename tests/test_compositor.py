@@ -13,6 +13,24 @@ import torch
 from test_compositor_oracle import CASES, FIX, load_case
 
 
+ROUTES = ["tiles", "lists"]   # compositor.ROUTE: the fused tile walk / the element lists + scan ops
+
+
+@pytest.fixture(params=ROUTES)
+def route(request, monkeypatch):
+    from simplegaussiansplat_tk71_b200 import compositor
+
+    monkeypatch.setattr(compositor, "ROUTE", request.param)
+    return request.param
+
+
+@pytest.fixture
+def lists_route(monkeypatch):
+    from simplegaussiansplat_tk71_b200 import compositor
+
+    monkeypatch.setattr(compositor, "ROUTE", "lists")
+
+
 def _run(case, device, F=None):
     if F is None:
         from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
@@ -92,7 +110,7 @@ def test_element_plan_integer_side_is_bit_exact():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
-def test_native_compositor_matches_reference_fixture_gpu(name):
+def test_native_compositor_matches_reference_fixture_gpu(name, route):
     case = load_case(np.load(FIX), name)
     _check(_run(case, "cuda"), case)
 
@@ -100,7 +118,7 @@ def test_native_compositor_matches_reference_fixture_gpu(name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("placement", [True, False], ids=["counting-placement", "expand+radix-sort"])
 @pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
-def test_native_element_list_is_bit_exact_gpu(name, placement, monkeypatch):
+def test_native_element_list_is_bit_exact_gpu(name, placement, monkeypatch, lists_route):
     """Integer side of the native path: keys, Gaussian ids and their stable order vs numpy argsort(stable),
     for both ways of building the list."""
     from oracle import compositor_oracle as co
@@ -119,7 +137,7 @@ def test_native_element_list_is_bit_exact_gpu(name, placement, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_placement_equals_sort_on_a_1080p_scene_gpu(monkeypatch):
+def test_placement_equals_sort_on_a_1080p_scene_gpu(monkeypatch, lists_route):
     """The two list builders agree bit for bit at full scale (0.2 M Gaussians, 1920x1080, ~8 M elements)."""
     from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
 
@@ -135,7 +153,7 @@ def test_placement_equals_sort_on_a_1080p_scene_gpu(monkeypatch):
 
 
 @pytest.mark.gpu
-def test_placement_equals_sort_on_long_pixel_lists_gpu(monkeypatch):
+def test_placement_equals_sort_on_long_pixel_lists_gpu(monkeypatch, lists_route):
     """Bundled-scene view (C2): per-pixel lists of hundreds of elements take the transposed (ballot-compacting)
     fill and the warp-per-list key kernel; the result must still be the stable sort, bit for bit."""
     from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
@@ -154,7 +172,7 @@ def test_placement_equals_sort_on_long_pixel_lists_gpu(monkeypatch):
 
 
 @pytest.mark.gpu
-def test_long_list_backward_equals_per_element_backward_gpu():
+def test_long_list_backward_equals_per_element_backward_gpu(lists_route):
     """C2 view: the cell-walking, shared-memory-transposing backward un-sort (long pixel lists) must give exactly
     the gradients of the per-element scatter version (the reduction that follows is deterministic)."""
     from simplegaussiansplat_tk71_b200 import _lib, workloads as wl
@@ -181,7 +199,7 @@ def test_long_list_backward_equals_per_element_backward_gpu():
 
 
 @pytest.mark.gpu
-def test_native_compositor_matches_oracle_on_a_larger_scene_gpu():
+def test_native_compositor_matches_oracle_on_a_larger_scene_gpu(route):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     from oracle import compositor_oracle as co
@@ -201,7 +219,7 @@ def test_native_compositor_matches_oracle_on_a_larger_scene_gpu():
 
 
 @pytest.mark.gpu
-def test_native_compositor_edge_cases_gpu():
+def test_native_compositor_edge_cases_gpu(route):
     from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
 
     dev = "cuda"
@@ -230,7 +248,7 @@ def test_native_compositor_edge_cases_gpu():
 
 
 @pytest.mark.gpu
-def test_bundled_scene_front_slice_against_oracle_gpu():
+def test_bundled_scene_front_slice_against_oracle_gpu(route):
     """C2 (BASELINE.json configs[1]): the nearest 4000 Gaussians of a bundled-scene view — boxes of hundreds of
     pixels, per-pixel lists of hundreds of elements (most tiles go through the fix-up phase)."""
     from oracle import compositor_oracle as co
@@ -256,7 +274,7 @@ def test_bundled_scene_front_slice_against_oracle_gpu():
 
 
 @pytest.mark.gpu
-def test_planned_view_equals_unplanned_gpu():
+def test_planned_view_equals_unplanned_gpu(route):
     """compositor.plan_view only moves the prologue to a side stream: same element list, same image, same grads."""
     from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
     from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
@@ -266,7 +284,7 @@ def test_planned_view_equals_unplanned_gpu():
     res = []
     for planned in (False, True, True):
         if planned:
-            compositor.plan_view(v.boxsize, v.startpoint, v.endpoint)
+            compositor.plan_view(v.boxsize, v.startpoint, v.endpoint, v.width, v.height)
             assert len(compositor._plans) == 1
         m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
                         v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
@@ -278,3 +296,90 @@ def test_planned_view_equals_unplanned_gpu():
         assert torch.allclose(res[0][0], other[0], rtol=1e-5, atol=1e-6)   # colour sums use float atomics
         for a, b in zip(res[0][1:], other[1:]):
             assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
+def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
+    """Integer side of the tile route: the (tile, Gaussian) pairs, their stable order by tile and the tile offsets
+    against numpy (argsort(kind="stable") of the Gaussian-major pair list)."""
+    from simplegaussiansplat_tk71_b200 import _lib, compositor
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    case = load_case(np.load(FIX), name)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    _, view = compositor._render_forward(t(case["boxsize"]), t(case["sp"]), t(case["ep"]), t(case["mean"]).float(),
+                                         t(case["lam"]), t(case["opac"]), t(case["l_d"]), case["W"], case["H"])
+    L = _lib.lib()
+    tw, th = L.gcp_tile_width(), L.gcp_tile_height()
+    W, H = case["W"], case["H"]
+    ntx = (W + tw) // tw
+    ntiles = ntx * ((H + th) // th)
+    assert ntiles == L.gcp_tile_num_tiles(W, H)
+    tiles, gids, counts = [], [], []
+    for g, ((sx, sy), (ex, ey)) in enumerate(zip(case["sp"].tolist(), case["ep"].tolist())):
+        sx, sy, ex, ey = max(sx, 0), max(sy, 0), min(ex, W), min(ey, H)
+        c = 0
+        if ex >= sx and ey >= sy:
+            for ty in range(sy // th, ey // th + 1):
+                for tx in range(sx // tw, ex // tw + 1):
+                    tiles.append(ty * ntx + tx)
+                    gids.append(g)
+                    c += 1
+        counts.append(c)
+    tiles, gids = np.asarray(tiles, np.int64), np.asarray(gids, np.int32)
+    assert view.P == len(tiles)
+    assert np.array_equal(view.toff.cpu().numpy(), np.concatenate([[0], np.cumsum(counts)]))
+    order = np.argsort(tiles, kind="stable")
+    assert np.array_equal(view.pgid.cpu().numpy()[:view.P], gids[order])
+    start = np.searchsorted(tiles[order], np.arange(ntiles + 1), side="left")
+    assert np.array_equal(view.tstart.cpu().numpy(), start.astype(np.int32))
+
+
+def _both_routes(v, gI, monkeypatch, repeats=1):
+    from simplegaussiansplat_tk71_b200 import compositor
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    res = {}
+    for r in ["tiles"] * repeats + ["lists"]:
+        monkeypatch.setattr(compositor, "ROUTE", r)
+        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                        v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+        img.backward(gI)
+        res.setdefault(r, []).append([img.detach().clone()] + [t.grad.clone() for t in (m, lam, o, l)])
+        del img
+    return res
+
+
+def _assert_routes_agree(res, rtol, atol_scale):
+    a, b = res["tiles"][0], res["lists"][0]
+    for name, x, y in zip(("image", "mean", "lambda", "opacity", "l"), a, b):
+        assert torch.isfinite(x).all(), name
+        scale = float(y.abs().max())
+        assert torch.allclose(x, y, rtol=rtol, atol=atol_scale * scale), (name, float((x - y).abs().max()), scale)
+
+
+@pytest.mark.gpu
+def test_tile_route_equals_list_route_on_a_1080p_scene_gpu(monkeypatch):
+    """Both routes compute the same sums in different fp32 orders; the tile route has no float atomics and must
+    be bitwise reproducible."""
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    v = wl.splat_view(1920, 1080, 200_000, seed=7, device="cuda")
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+    res = _both_routes(v, gI, monkeypatch, repeats=2)
+    _assert_routes_agree(res, rtol=2e-4, atol_scale=2e-6)
+    for x, y in zip(*res["tiles"]):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.gpu
+def test_tile_route_equals_list_route_on_long_pixel_lists_gpu(monkeypatch):
+    """Bundled-scene view (C2): lists of hundreds of elements per pixel, boxes of 10^5 pixels."""
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    v = wl.bundled_views("cuda", n_views=3)[2]
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+    res = _both_routes(v, gI, monkeypatch)
+    _assert_routes_agree(res, rtol=2e-3, atol_scale=2e-5)

@@ -26,7 +26,7 @@ def one_view(i, plan_next):
     sc, (m, lam, o, l) = scenes[i % 2], leaves[i % 2]
     if plan_next:
         nx = scenes[(i + 1) % 2]
-        compositor.plan_view(nx.boxsize, nx.startpoint, nx.endpoint)
+        compositor.plan_view(nx.boxsize, nx.startpoint, nx.endpoint, 1920, 1080)
     for t_ in (m, lam, o, l):
         t_.grad = None
     img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, W, H)

@@ -16,7 +16,11 @@ ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--c2", type=int, default=-1, help="use view K of the bundled-scene workload (C2) instead")
+ap.add_argument("--route", default=None, help="compositor route: tiles | lists (default: compositor.ROUTE)")
 a = ap.parse_args()
+if a.route:
+    from simplegaussiansplat_tk71_b200 import compositor  # noqa: E402
+    compositor.ROUTE = a.route
 v = wl.bundled_views("cuda")[a.c2] if a.c2 >= 0 else wl.splat_view(a.width, a.height, a.n, device="cuda")
 print(v.name, "elements", v.elements)
 mean = v.mean.float().requires_grad_(True)
