@@ -77,7 +77,13 @@ __global__ void k_tile_totals(const int64_t *__restrict__ toff, int64_t n, int64
     totals[0] = toff[n];
 }
 
-// rec[g] = {mx, my, l00, l01 | l10, l11, o, l0 || l1, l2, sx, sy | ex, ey, toff, 0}
+// Lambda is stored pre-multiplied by -log2(e)/2, so that the walk kernels get g = exp(-1/2 d Lambda d^T) as one
+// ex2.approx of d Lambda' d^T (relative error 2^-22; expf costs eight instructions, this one two); the backward
+// multiplies its d_mean terms by EXP2_UNSCALE = -2 ln 2 to undo the factor in X = d Lambda.
+constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
+constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
+
+// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, toff, 0}
 __global__ void __launch_bounds__(256)
 k_tile_pack(const float *__restrict__ mean, const float *__restrict__ lam, const float *__restrict__ opac,
             const float *__restrict__ l_d, const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
@@ -88,8 +94,8 @@ k_tile_pack(const float *__restrict__ mean, const float *__restrict__ lam, const
     const float4 L = __ldg(reinterpret_cast<const float4 *>(lam) + g);
     const Box b = clip_box(sp, ep, g, W, H);
     auto f = [](float v) { return __float_as_int(v); };
-    rec[4 * g] = make_int4(f(m.x), f(m.y), f(L.x), f(L.y));
-    rec[4 * g + 1] = make_int4(f(L.z), f(L.w), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
+    rec[4 * g] = make_int4(f(m.x), f(m.y), f(L.x * EXP2_SCALE), f(L.y * EXP2_SCALE));
+    rec[4 * g + 1] = make_int4(f(L.z * EXP2_SCALE), f(L.w * EXP2_SCALE), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
     rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
     rec[4 * g + 3] = make_int4(b.ex, b.ey, static_cast<int>(__ldg(toff + g)), 0);
 }
@@ -139,6 +145,38 @@ k_tile_start(const int32_t *__restrict__ ptile_s, int64_t P, int ntiles, int32_t
     const int prev = (p == 0) ? -1 : __ldg(ptile_s + p - 1);
     const int cur = (p == P) ? ntiles : __ldg(ptile_s + p);
     for (int c = prev + 1; c <= cur; ++c) tstart[c] = static_cast<int32_t>(p);
+}
+
+// Longest tiles first: torder = the tiles whose list is longer than `long_len` (from the front, any order), then
+// the others (filled from the back).  The walk kernels hand tiles out in this order (a warp per tile, dynamic
+// tickets), so the long serial walks start at once and the short ones fill in behind them.  ctr[0] / ctr[1]:
+// front / back counters (zeroed by the caller); warp-aggregated, two atomics per warp.
+__global__ void __launch_bounds__(256)
+k_tile_order(const int32_t *__restrict__ tstart, int ntiles, int long_len, int32_t *__restrict__ torder,
+             unsigned int *__restrict__ ctr) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = t < ntiles;
+    const bool is_long = in && (__ldg(tstart + t + 1) - __ldg(tstart + t) > long_len);
+    const unsigned ml = __ballot_sync(0xffffffffu, is_long), ms = __ballot_sync(0xffffffffu, in && !is_long);
+    unsigned bl = 0, bs = 0;
+    if (lane == 0) {
+        if (ml) bl = atomicAdd(ctr, __popc(ml));
+        if (ms) bs = atomicAdd(ctr + 1, __popc(ms));
+    }
+    bl = __shfl_sync(0xffffffffu, bl, 0);
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (is_long) torder[bl + __popc(ml & lt)] = t;
+    else if (in) torder[ntiles - 1 - (bs + __popc(ms & lt))] = t;
+}
+
+// next tile of this warp (dynamic ticket), -1 when none is left
+__device__ __forceinline__ int next_tile(unsigned int *ticket, const int32_t *__restrict__ torder, int ntiles, int lane) {
+    unsigned i = 0;
+    if (lane == 0) i = atomicAdd(ticket, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    return i < static_cast<unsigned>(ntiles) ? __ldg(torder + i) : -1;
 }
 
 // one 32-byte sector in one instruction (LDG.256, sm_100)
@@ -191,14 +229,16 @@ __device__ __forceinline__ void stage_pair(PairSlot *slot, const RecRegs &r, boo
 struct PairEval {
     float d0, d1, X0, X1, gk, x;
 };
-// g = exp(-1/2 (r-m) Lambda (r-m)^T) with X = (r-m) Lambda (gs_model.py:495, :745); x = 1 - o g (:533-535)
+// g = exp(-1/2 (r-m) Lambda (r-m)^T) with X = (r-m) Lambda (gs_model.py:495, :745); x = 1 - o g (:533-535).
+// The record holds Lambda' = EXP2_SCALE Lambda: X0, X1 come out scaled by EXP2_SCALE and g = 2^(X' . d).
 __device__ __forceinline__ PairEval eval_pair(const float4 &a, const float4 &b, float px, float py) {
     PairEval e;
     e.d0 = px - a.x;
     e.d1 = py - a.y;
     e.X0 = e.d0 * a.z + e.d1 * b.x;
     e.X1 = e.d0 * a.w + e.d1 * b.y;
-    e.gk = expf(-0.5f * (e.X0 * e.d0 + e.X1 * e.d1));
+    const float p2 = e.X0 * e.d0 + e.X1 * e.d1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.gk) : "f"(p2));
     e.x = 1.0f - b.z * e.gk;
     return e;
 }
@@ -207,55 +247,55 @@ constexpr int TILE_WARPS = 8;
 
 __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
-              int ntx, int ntiles, int W, int H, float *__restrict__ image, float *__restrict__ tkeep) {
+              const int32_t *__restrict__ torder, unsigned int *__restrict__ ticket, int ntx, int ntiles, int W, int H,
+              float *__restrict__ image, float *__restrict__ tkeep) {
     __shared__ PairSlot slots[TILE_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int t = blockIdx.x * TILE_WARPS + wib;
-    if (t >= ntiles) return;  // warp-uniform; only __syncwarp below
-    const int ty = t / ntx, tx = t - ty * ntx;
-    const int x0 = tx << TSX, y0 = ty << TSY;
-    const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
-    const float px = static_cast<float>(ix), py = static_cast<float>(iy);
-    const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
     PairSlot *sl = slots[wib];
-    float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    // software pipeline over batches of 32 pairs: ids two batches ahead, records one batch ahead
-    int g1 = 0;
-    RecRegs r = {};
-    if (lo + lane < hi) r = load_rec(rec, __ldg(pgid_s + lo + lane));
-    if (lo + 32 + lane < hi) g1 = __ldg(pgid_s + lo + 32 + lane);
-    for (int64_t b = lo; b < hi; b += 32) {
-        stage_pair(sl + lane, r, b + lane < hi, tx, ty, x0, y0);
-        int g2 = 0;
-        if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
-        if (b + 32 + lane < hi) r = load_rec(rec, g1);
-        g1 = g2;
-        __syncwarp();
-        const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
-        float *tk = tkeep + b * 32 + lane;
+    for (;;) {  // warp-uniform loop; only __syncwarp inside
+        const int t = next_tile(ticket, torder, ntiles, lane);
+        if (t < 0) break;
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int x0 = tx << TSX, y0 = ty << TSY;
+        const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
+        const float px = static_cast<float>(ix), py = static_cast<float>(iy);
+        const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
+        float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        // software pipeline over batches of 32 pairs: ids two batches ahead, records one batch ahead
+        int g1 = 0;
+        RecRegs r = {};
+        if (lo + lane < hi) r = load_rec(rec, __ldg(pgid_s + lo + lane));
+        if (lo + 32 + lane < hi) g1 = __ldg(pgid_s + lo + 32 + lane);
+        for (int64_t b = lo; b < hi; b += 32) {
+            stage_pair(sl + lane, r, b + lane < hi, tx, ty, x0, y0);
+            int g2 = 0;
+            if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
+            if (b + 32 + lane < hi) r = load_rec(rec, g1);
+            g1 = g2;
+            __syncwarp();
+            const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
+            float *tk = tkeep + b * 32 + lane;
 #pragma unroll 4
-        for (int k = 0; k < m; ++k) {
-            const float4 A = sl[k].a, B = sl[k].b;
-            const float2 C = sl[k].c;
-            const bool cov = (sl[k].mask >> lane) & 1u;
-            const PairEval e = eval_pair(A, B, px, py);
-            const float tin = T * e.x;
-            __stcs(tk + k * 32, T);
-            if (cov) {
-                if (tin != 0.0f) {
-                    const float ta = T * (1.0f - e.x);
-                    c0 = fmaf(ta, B.w, c0);
-                    c1 = fmaf(ta, C.x, c1);
-                    c2 = fmaf(ta, C.y, c2);
-                }
-                T = tin;
+            for (int k = 0; k < m; ++k) {
+                const float4 A = sl[k].a, B = sl[k].b;
+                const float2 C = sl[k].c;
+                const bool cov = (sl[k].mask >> lane) & 1u;
+                const PairEval e = eval_pair(A, B, px, py);
+                const float tin = T * e.x;
+                __stcs(tk + k * 32, T);
+                // branch-free: an element outside the box, or dead (inclusive product 0, gs_model.py:575-578), adds 0
+                const float ta = (cov && tin != 0.0f) ? T * (1.0f - e.x) : 0.0f;
+                c0 = fmaf(ta, B.w, c0);
+                c1 = fmaf(ta, C.x, c1);
+                c2 = fmaf(ta, C.y, c2);
+                T = cov ? tin : T;
             }
+            __syncwarp();
         }
-        __syncwarp();
-    }
-    if (ix <= W && iy <= H) {
-        float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
-        p[0] = c0; p[1] = c1; p[2] = c2;
+        if (ix <= W && iy <= H) {
+            float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+            p[0] = c0; p[1] = c1; p[2] = c2;
+        }
     }
 }
 
@@ -292,92 +332,98 @@ __device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
 // over the pixels of pair q (coef = alpha dalpha, hc = -coef/2), see gs_model.py:733-766
 __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
+                const int32_t *__restrict__ torder, unsigned int *__restrict__ ticket,
                 const float *__restrict__ tkeep, const float *__restrict__ gimg, int ntx, int ntiles, int W, int H,
                 float *__restrict__ partial) {
     __shared__ PairSlot slots[TILE_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int t = blockIdx.x * TILE_WARPS + wib;
-    if (t >= ntiles) return;
-    const int ty = t / ntx, tx = t - ty * ntx;
-    const int x0 = tx << TSX, y0 = ty << TSY;
-    const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
-    const float px = static_cast<float>(ix), py = static_cast<float>(iy);
-    const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
-    if (lo >= hi) return;
-    float pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
-    if (ix <= W && iy <= H) {
-        const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
-        pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
-    }
     PairSlot *sl = slots[wib];
     const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    float U = 0.0f;
-    // batches of 32 pairs from the END of the tile's list; batch j covers [bb, bb + m), bb = hi - 32 (j+1) clipped
-    int g1 = 0;
-    RecRegs r = {};
-    {
-        const int64_t bb = (hi - 32 > lo) ? hi - 32 : lo;
-        if (bb + lane < hi) r = load_rec(rec, __ldg(pgid_s + bb + lane));
-        const int64_t e1 = bb, b1 = (e1 - 32 > lo) ? e1 - 32 : lo;
-        if (b1 + lane < e1) g1 = __ldg(pgid_s + b1 + lane);
-    }
-    for (int64_t be = hi; be > lo;) {
-        const int64_t bb = (be - 32 > lo) ? be - 32 : lo;
-        const int m = static_cast<int>(be - bb);
-        stage_pair(sl + lane, r, lane < m, tx, ty, x0, y0);
-        // next batch [b1, bb), the one after [b2, b1)
-        const int64_t b1 = (bb - 32 > lo) ? bb - 32 : lo;
-        const int64_t b2 = (b1 - 32 > lo) ? b1 - 32 : lo;
-        int g2 = 0;
-        if (b2 + lane < b1) g2 = __ldg(pgid_s + b2 + lane);
-        if (b1 + lane < bb) r = load_rec(rec, g1);
-        g1 = g2;
-        __syncwarp();
-        const float *tk = tkeep + bb * 32 + lane;
-#pragma unroll 2
-        for (int k = m - 1; k >= 0; --k) {
-            const float4 A = sl[k].a, B = sl[k].b;
-            const float2 C = sl[k].c;
-            const bool cov = (sl[k].mask >> lane) & 1u;
-            const int q = sl[k].q;
-            const float T = __ldcs(tk + k * 32);
-            const PairEval e = eval_pair(A, B, px, py);
-            const bool alive = cov && (T * e.x != 0.0f);
-            const float alpha = 1.0f - e.x;
-            const float pgl = pg0 * B.w + pg1 * C.x + pg2 * C.y;
-            const float dalpha = alive ? T * pgl - T * U : 0.0f;
-            const float d = alive ? T * alpha * pgl : 0.0f;
-            if (cov) U = fmaf(e.x, U, alive ? alpha * pgl : 0.0f);   // U_{i-1} = w_i + x_i U_i
-            const float coef = B.z * e.gk * dalpha;
-            const float hc = -0.5f * coef;
-            float v[8] = {e.gk * dalpha, d, coef * e.X0, coef * e.X1, hc * e.d0 * e.d0, hc * e.d0 * e.d1,
-                          hc * e.d1 * e.d1, 0.0f};
-            const float s = reduce8(v, lane);
-            if ((lane & 3) == 0) partial[static_cast<int64_t>(q) * 8 + comp] = s;
+    for (;;) {
+        const int t = next_tile(ticket, torder, ntiles, lane);
+        if (t < 0) break;
+        const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
+        if (lo >= hi) continue;
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int x0 = tx << TSX, y0 = ty << TSY;
+        const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
+        const float px = static_cast<float>(ix), py = static_cast<float>(iy);
+        float pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
+        if (ix <= W && iy <= H) {
+            const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+            pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
         }
-        __syncwarp();
-        be = bb;
+        float U = 0.0f;
+        // batches of 32 pairs from the END of the tile's list: [bb, be), be = hi, hi - 32, ...
+        int g1 = 0;
+        RecRegs r = {};
+        {
+            const int64_t bb = (hi - 32 > lo) ? hi - 32 : lo;
+            if (bb + lane < hi) r = load_rec(rec, __ldg(pgid_s + bb + lane));
+            const int64_t b1 = (bb - 32 > lo) ? bb - 32 : lo;
+            if (b1 + lane < bb) g1 = __ldg(pgid_s + b1 + lane);
+        }
+        // the kept T of the four pairs walked next, loaded one group (four pairs) ahead of their use, across batch
+        // boundaries: every batch but the last one walked holds 32 pairs, so the groups never straddle a batch
+        const float *tl = tkeep + lane;
+        float tc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tc[j] = (hi - 1 - j >= lo) ? __ldcs(tl + (hi - 1 - j) * 32) : 0.0f;
+        for (int64_t be = hi; be > lo;) {
+            const int64_t bb = (be - 32 > lo) ? be - 32 : lo;
+            const int m = static_cast<int>(be - bb);
+            stage_pair(sl + lane, r, lane < m, tx, ty, x0, y0);
+            // next batch [b1, bb), the one after [b2, b1)
+            const int64_t b1 = (bb - 32 > lo) ? bb - 32 : lo;
+            const int64_t b2 = (b1 - 32 > lo) ? b1 - 32 : lo;
+            int g2 = 0;
+            if (b2 + lane < b1) g2 = __ldg(pgid_s + b2 + lane);
+            if (b1 + lane < bb) r = load_rec(rec, g1);
+            g1 = g2;
+            __syncwarp();
+            for (int k0 = m - 1; k0 >= 0; k0 -= 4) {
+                float tn[4];
+                const int64_t pn = bb + k0 - 4;   // first pair of the next group
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tn[j] = (pn - j >= lo) ? __ldcs(tl + (pn - j) * 32) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 - j;
+                    if (k < 0) break;   // warp-uniform (last batch walked only)
+                    const float4 A = sl[k].a, B = sl[k].b;
+                    const float2 C = sl[k].c;
+                    const bool cov = (sl[k].mask >> lane) & 1u;
+                    const int q = sl[k].q;
+                    const float T = tc[j];
+                    const PairEval e = eval_pair(A, B, px, py);
+                    const bool alive = cov && (T * e.x != 0.0f);
+                    const float alpha = 1.0f - e.x;
+                    const float pgl = pg0 * B.w + pg1 * C.x + pg2 * C.y;
+                    const float dalpha = alive ? T * pgl - T * U : 0.0f;
+                    const float d = alive ? T * alpha * pgl : 0.0f;
+                    U = cov ? fmaf(e.x, U, alive ? alpha * pgl : 0.0f) : U;   // U_{i-1} = w_i + x_i U_i
+                    const float coef = B.z * e.gk * dalpha;
+                    const float hc = -0.5f * coef;
+                    const float cm = EXP2_UNSCALE * coef;   // e.X0, e.X1 carry the factor EXP2_SCALE
+                    float v[8] = {e.gk * dalpha, d, cm * e.X0, cm * e.X1, hc * e.d0 * e.d0, hc * e.d0 * e.d1,
+                                  hc * e.d1 * e.d1, 0.0f};
+                    const float s = reduce8(v, lane);
+                    if ((lane & 3) == 0) partial[static_cast<int64_t>(q) * 8 + comp] = s;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc[j] = tn[j];
+            }
+            __syncwarp();
+            be = bb;
+        }
     }
 }
 
-// 8 lanes per Gaussian, lane c adds component c of the Gaussian's partials in pair order, then the lane owning a
-// component writes its gradients: d_l[c] = (sum d) / l[c] is the reference's d / l (gs_model.py:763-766)
-__global__ void __launch_bounds__(256)
-k_tile_reduce(const float *__restrict__ partial, const int64_t *__restrict__ toff, const float *__restrict__ l_d,
-              int64_t n, float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
-              float *__restrict__ g_l) {
-    const int c = threadIdx.x & 7;
-    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
-    if (g >= n) return;
-    const int64_t b = __ldg(toff + g), e = __ldg(toff + g + 1);
-    float s = 0.0f;
-    int64_t q = b;
-    for (; q + 4 <= e; q += 4) {
-        const float v0 = __ldcs(partial + q * 8 + c), v1 = __ldcs(partial + (q + 1) * 8 + c);
-        const float v2 = __ldcs(partial + (q + 2) * 8 + c), v3 = __ldcs(partial + (q + 3) * 8 + c);
-        s += v0; s += v1; s += v2; s += v3;
-    }
-    for (; q < e; ++q) s += __ldcs(partial + q * 8 + c);
+// lane c of a group of 8 owns component c of a Gaussian's gradient sums and writes what derives from it:
+// d_l[k] = (sum d) / l[k] is the reference's d / l (gs_model.py:763-766)
+__device__ __forceinline__ void store_component(int c, float s, int64_t g, const float *__restrict__ l_d,
+                                                float *__restrict__ g_mean, float *__restrict__ g_lam,
+                                                float *__restrict__ g_opac, float *__restrict__ g_l) {
     switch (c) {
         case 0: g_opac[g] = s; break;
         case 1:
@@ -391,6 +437,66 @@ k_tile_reduce(const float *__restrict__ partial, const int64_t *__restrict__ tof
         case 5: g_lam[4 * g + 1] = s; g_lam[4 * g + 2] = s; break;
         case 6: g_lam[4 * g + 3] = s; break;
         default: break;
+    }
+}
+
+constexpr int RED_BIG = 64;  // Gaussians with more pairs than this go to k_tile_reduce_big (one block each)
+
+// 8 lanes per Gaussian: lane c adds component c of the Gaussian's partials in pair order.  Gaussians with more than
+// RED_BIG pairs (boxes of thousands of pixels, bundled scene) are appended to `big` instead; the order of that
+// list does not enter any float sum.
+__global__ void __launch_bounds__(256)
+k_tile_reduce(const float *__restrict__ partial, const int64_t *__restrict__ toff, const float *__restrict__ l_d,
+              int64_t n, float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
+              float *__restrict__ g_l, unsigned int *__restrict__ nbig, int32_t *__restrict__ big) {
+    const int c = threadIdx.x & 7;
+    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+    if (g >= n) return;
+    const int64_t b = __ldg(toff + g), e = __ldg(toff + g + 1);
+    if (e - b > RED_BIG) {
+        if (c == 0) big[atomicAdd(nbig, 1u)] = static_cast<int32_t>(g);
+        return;
+    }
+    float s = 0.0f;
+    int64_t q = b;
+    for (; q + 4 <= e; q += 4) {
+        const float v0 = __ldcs(partial + q * 8 + c), v1 = __ldcs(partial + (q + 1) * 8 + c);
+        const float v2 = __ldcs(partial + (q + 2) * 8 + c), v3 = __ldcs(partial + (q + 3) * 8 + c);
+        s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; q < e; ++q) s += __ldcs(partial + q * 8 + c);
+    store_component(c, s, g, l_d, g_mean, g_lam, g_opac, g_l);
+}
+
+// one block per big Gaussian: 32 groups of 8 lanes stride over its pairs (group j takes pairs j, j+32, ...), the 32
+// group sums are added in group order — a fixed order, bitwise reproducible
+__global__ void __launch_bounds__(256)
+k_tile_reduce_big(const float *__restrict__ partial, const int64_t *__restrict__ toff, const float *__restrict__ l_d,
+                  float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
+                  float *__restrict__ g_l, const unsigned int *__restrict__ nbig, const int32_t *__restrict__ big) {
+    __shared__ float sums[32][8];
+    const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
+    const unsigned int nb = *nbig;
+    for (unsigned int i = blockIdx.x; i < nb; i += gridDim.x) {
+        const int64_t g = __ldg(big + i);
+        const int64_t b = __ldg(toff + g), e = __ldg(toff + g + 1);
+        float s = 0.0f;
+        int64_t q = b + j;
+        for (; q + 96 < e; q += 128) {
+            const float v0 = __ldcs(partial + q * 8 + c), v1 = __ldcs(partial + (q + 32) * 8 + c);
+            const float v2 = __ldcs(partial + (q + 64) * 8 + c), v3 = __ldcs(partial + (q + 96) * 8 + c);
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; q < e; q += 32) s += __ldcs(partial + q * 8 + c);
+        sums[j][c] = s;
+        __syncthreads();
+        if (j == 0) {
+            float t = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) t += sums[k][c];
+            store_component(c, t, g, l_d, g_mean, g_lam, g_opac, g_l);
+        }
+        __syncthreads();
     }
 }
 
@@ -413,6 +519,23 @@ BinLayout bin_layout(int64_t P) {
     return L;
 }
 
+// persistent grid of the walk kernels: every resident warp slot of the device, never more warps than tiles
+unsigned walk_grid(const void *kernel, int ntiles) {
+    static const void *known[2] = {nullptr, nullptr};
+    static unsigned slots[2] = {0, 0};  // resident blocks of the (two) walk kernels, queried once
+    int i = (known[0] == kernel || known[0] == nullptr) ? 0 : 1;
+    if (known[i] != kernel) {
+        int dev = 0, sms = 148, per_sm = 4;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_WARPS * 32, 0) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 1;
+        slots[i] = static_cast<unsigned>(sms * per_sm);
+        known[i] = kernel;
+    }
+    return std::max(1u, std::min(blocks_for(ntiles, TILE_WARPS), slots[i]));
+}
+
 inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >= 32768; }
 inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
 inline int tiles_y(int H) { return (H + TH) >> TSY; }
@@ -424,6 +547,7 @@ extern "C" {
 int gcp_tile_width(void) { return TW; }
 int gcp_tile_height(void) { return TH; }
 int gcp_tile_num_tiles(int W, int H) { return bad_image(W, H) ? 0 : tiles_x(W) * tiles_y(H); }
+int gcp_tile_order_ints(int W, int H) { return bad_image(W, H) ? 0 : tiles_x(W) * tiles_y(H) + 4; }
 
 size_t gcp_tile_prepare_bytes(int64_t n) {
     size_t a = 0;
@@ -469,9 +593,10 @@ int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const 
 size_t gcp_tile_bin_bytes(int64_t P) { return P < 0 ? 0 : bin_layout(P).total; }
 
 int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
-                 int32_t *tile_start, int32_t *pair_gid, void *temp, size_t temp_bytes, gcp_stream_t stream) {
+                 int32_t *tile_start, int32_t *tile_order, int32_t *pair_gid, void *temp, size_t temp_bytes,
+                 gcp_stream_t stream) {
     if (n < 0 || P < 0 || P >= (int64_t(1) << 31) - 64 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
-    if (!tile_start || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid))) return GCP_ERR_INVALID_ARG;
+    if (!tile_start || !tile_order || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid))) return GCP_ERR_INVALID_ARG;
     const BinLayout L = bin_layout(P);
     if (temp_bytes < L.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
@@ -488,37 +613,64 @@ int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int6
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     k_tile_start<<<blocks_for(P + 1, 256), 256, 0, st>>>(ptile_s, P, ntiles, tile_start);
+    // walk order: tiles with more than twice the mean list length first
+    unsigned int *ctr = reinterpret_cast<unsigned int *>(tile_order + ntiles);
+    cudaError_t e = cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int long_len = static_cast<int>(std::min<int64_t>(2 * (P / ntiles) + 1, 0x7fffffff));
+    k_tile_order<<<blocks_for(ntiles, 256), 256, 0, st>>>(tile_start, ntiles, long_len, tile_order, ctr);
     return static_cast<int>(cudaGetLastError());
 }
 
-int gcp_tile_render(const int32_t *tile_start, const int32_t *pair_gid, const int32_t *rec, int64_t P, int W, int H,
-                    float *image, float *t_keep, gcp_stream_t stream) {
-    if (P < 0 || bad_image(W, H) || !tile_start || !image) return GCP_ERR_INVALID_ARG;
+int gcp_tile_render(const int32_t *tile_start, int32_t *tile_order, const int32_t *pair_gid, const int32_t *rec,
+                    int64_t P, int W, int H, float *image, float *t_keep, gcp_stream_t stream) {
+    if (P < 0 || bad_image(W, H) || !tile_start || !tile_order || !image) return GCP_ERR_INVALID_ARG;
     if (P > 0 && (!pair_gid || !rec || !t_keep)) return GCP_ERR_INVALID_ARG;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    k_tile_render<<<blocks_for(ntiles, TILE_WARPS), TILE_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), ntx, ntiles, W, H, image, t_keep);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(tile_order + ntiles) + 2;
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_tile_render<<<walk_grid(reinterpret_cast<const void *>(k_tile_render), ntiles), TILE_WARPS * 32, 0, st>>>(
+        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), tile_order, ticket, ntx, ntiles, W, H, image,
+        t_keep);
     return static_cast<int>(cudaGetLastError());
 }
 
-int gcp_tile_backward(const int32_t *tile_start, const int32_t *pair_gid, const int32_t *rec, const float *t_keep,
-                      const float *grad_image, int64_t P, int W, int H, float *partial, gcp_stream_t stream) {
-    if (P < 0 || bad_image(W, H) || !tile_start || !grad_image) return GCP_ERR_INVALID_ARG;
+int gcp_tile_backward(const int32_t *tile_start, int32_t *tile_order, const int32_t *pair_gid, const int32_t *rec,
+                      const float *t_keep, const float *grad_image, int64_t P, int W, int H, float *partial,
+                      gcp_stream_t stream) {
+    if (P < 0 || bad_image(W, H) || !tile_start || !tile_order || !grad_image) return GCP_ERR_INVALID_ARG;
     if (P == 0) return GCP_OK;
     if (!pair_gid || !rec || !t_keep || !partial) return GCP_ERR_INVALID_ARG;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    k_tile_backward<<<blocks_for(ntiles, TILE_WARPS), TILE_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), t_keep, grad_image, ntx, ntiles, W, H, partial);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(tile_order + ntiles) + 3;
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_tile_backward<<<walk_grid(reinterpret_cast<const void *>(k_tile_backward), ntiles), TILE_WARPS * 32, 0, st>>>(
+        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), tile_order, ticket, t_keep, grad_image, ntx,
+        ntiles, W, H, partial);
     return static_cast<int>(cudaGetLastError());
 }
 
+size_t gcp_tile_reduce_bytes(int64_t n) { return n < 0 ? 0 : 256 + align256(static_cast<size_t>(n) * 4); }
+
 int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,
-                    float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
+                    float *g_lam, float *g_opac, float *g_l, void *temp, size_t temp_bytes, gcp_stream_t stream) {
     if (n < 0) return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
     if (!toff || !l_d || !g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
-    k_tile_reduce<<<blocks_for(n, 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, toff, l_d, n, g_mean,
-                                                                                         g_lam, g_opac, g_l);
+    if (!temp || temp_bytes < gcp_tile_reduce_bytes(n) || (reinterpret_cast<uintptr_t>(temp) & 3))
+        return GCP_ERR_WORKSPACE;
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int *nbig = static_cast<unsigned int *>(temp);
+    int32_t *big = reinterpret_cast<int32_t *>(static_cast<unsigned char *>(temp) + 256);
+    cudaError_t e = cudaMemsetAsync(nbig, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_tile_reduce<<<blocks_for(n, 32), 256, 0, st>>>(partial, toff, l_d, n, g_mean, g_lam, g_opac, g_l, nbig, big);
+    k_tile_reduce_big<<<blocks_for(n, 1, 148 * 8), 256, 0, st>>>(partial, toff, l_d, g_mean, g_lam, g_opac, g_l, nbig,
+                                                                 big);
     return static_cast<int>(cudaGetLastError());
 }
 

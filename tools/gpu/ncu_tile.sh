@@ -1,0 +1,6 @@
+#!/bin/bash
+# ncu --set full of the tile-route kernels of one 1080p step and one bundled-scene step
+mkdir -p gpurun_out
+python tools/splat_time.py --route tiles --steps 1 && ncu --set full --clock-control none --import-source on -k regex:'k_tile_render|k_tile_backward|k_tile_reduce' --launch-skip 3 -c 3 -f -o gpurun_out/tile_c3 python tools/splat_time.py --route tiles --steps 1 > gpurun_out/ncu_tile_c3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_tile_render|k_tile_backward|k_tile_reduce' --launch-skip 3 -c 3 -f -o gpurun_out/tile_c2 python tools/splat_time.py --route tiles --c2 1 --steps 1 > gpurun_out/ncu_tile_c2.log 2>&1
+ls -la gpurun_out/*.ncu-rep
