@@ -239,15 +239,22 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
  *   toff       i64[n+1]  exclusive offsets of the Gaussians' pairs (Gaussian-major, row-major over its tiles)
  *   rec        32-byte aligned, 64 bytes per Gaussian (packed tables)
  *   tile_start i32[gcp_tile_num_tiles(W,H)+1], pair_gid i32[P]: the tile-sorted pair list
- *   tile_order i32[gcp_tile_order_ints(W,H)]: the order the walk kernels hand tiles to their warps (long lists
- *              first), followed by four counter words the library uses (order build, walk tickets)
- *   t_keep     f32[P*32]: exclusive T of every (pair, lane), kept by the forward for the backward
+ *   piece_plan i32[gcp_tile_plan_ints(P,W,H)]: the walk kernels' work units.  A PIECE is at most
+ *              gcp_tile_piece_pairs() (default 128) consecutive pairs of one tile; a longer list is cut into
+ *              several pieces walked by different warps, and the per-pixel carries between them (T forward,
+ *              U backward — the segmented scan's cross-block carries) are resolved by two small combine kernels
+ *   piece_state f32[gcp_tile_state_floats(P,W,H)]: aggregate, colour and carries of the pieces (forward -> backward)
+ *   t_keep     f32[P*32]: exclusive T (local to its piece) of every (pair, lane), kept for the backward
  *   partial    f32[P*8]: per-pair gradient sums, Gaussian-major
  * ------------------------------------------------------------------------------------------------ */
 int gcp_tile_width(void);
 int gcp_tile_height(void);
 int gcp_tile_num_tiles(int W, int H);
-int gcp_tile_order_ints(int W, int H);
+int gcp_tile_set_piece_pairs(int pairs);   /* tuning / tests: multiple of 32 */
+int gcp_tile_piece_pairs(void);
+int64_t gcp_tile_piece_cap(int64_t P, int W, int H);
+int64_t gcp_tile_plan_ints(int64_t P, int W, int H);
+int64_t gcp_tile_state_floats(int64_t P, int W, int H);
 /* toff and totals i64[1] = {P} (device memory) from the boxes; temp >= gcp_tile_prepare_bytes(n). */
 size_t gcp_tile_prepare_bytes(int64_t n);
 int gcp_tile_prepare(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, int64_t *toff, int64_t *totals,
@@ -255,17 +262,17 @@ int gcp_tile_prepare(const int32_t *sp, const int32_t *ep, int64_t n, int W, int
 int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
                   const int32_t *ep, const int64_t *toff, int64_t n, int W, int H, int32_t *rec,
                   gcp_stream_t stream);
-/* pair emission + stable sort by tile + tile offsets; temp >= gcp_tile_bin_bytes(P). */
-size_t gcp_tile_bin_bytes(int64_t P);
+/* pair emission + stable sort by tile + tile offsets; temp >= gcp_tile_bin_bytes(P, W, H). */
+size_t gcp_tile_bin_bytes(int64_t P, int W, int H);
 int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
-                 int32_t *tile_start, int32_t *tile_order, int32_t *pair_gid, void *temp, size_t temp_bytes,
+                 int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
                  gcp_stream_t stream);
 /* image f32[(H+1)*(W+1)*3] is written completely (no need to zero it). */
-int gcp_tile_render(const int32_t *tile_start, int32_t *tile_order, const int32_t *pair_gid, const int32_t *rec,
-                    int64_t P, int W, int H, float *image, float *t_keep, gcp_stream_t stream);
-int gcp_tile_backward(const int32_t *tile_start, int32_t *tile_order, const int32_t *pair_gid, const int32_t *rec,
-                      const float *t_keep, const float *grad_image, int64_t P, int W, int H, float *partial,
-                      gcp_stream_t stream);
+int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
+                    int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream);
+int gcp_tile_backward(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
+                      const float *t_keep, float *piece_state, const float *grad_image, int64_t P, int W, int H,
+                      float *partial, gcp_stream_t stream);
 /* g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3] written completely (d_l = (sum d)/l, gs_model.py:763-766). */
 size_t gcp_tile_reduce_bytes(int64_t n);   /* scratch: the list of Gaussians with many pairs */
 int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,

@@ -29,7 +29,8 @@ SYMBOLS = (
     "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce", "gcp_splat_bwd_reduce_bytes",
     "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_set_long_list_threshold", "gcp_splat_seg_shift",
     "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
-    "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_order_ints", "gcp_tile_prepare_bytes", "gcp_tile_prepare",
+    "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs", "gcp_tile_piece_cap",
+    "gcp_tile_plan_ints", "gcp_tile_state_floats", "gcp_tile_prepare_bytes", "gcp_tile_prepare",
     "gcp_tile_pack", "gcp_tile_bin_bytes", "gcp_tile_bin", "gcp_tile_render", "gcp_tile_backward", "gcp_tile_reduce", "gcp_tile_reduce_bytes",
 )
 
@@ -103,17 +104,21 @@ def lib() -> ctypes.CDLL:
     L.gcp_tile_height.restype = ci
     L.gcp_tile_num_tiles.argtypes = [ci, ci]
     L.gcp_tile_num_tiles.restype = ci
-    L.gcp_tile_order_ints.argtypes = [ci, ci]
-    L.gcp_tile_order_ints.restype = ci
+    L.gcp_tile_set_piece_pairs.argtypes = [ci]
+    L.gcp_tile_set_piece_pairs.restype = ci
+    L.gcp_tile_piece_pairs.restype = ci
+    for name in ("gcp_tile_piece_cap", "gcp_tile_plan_ints", "gcp_tile_state_floats"):
+        getattr(L, name).argtypes = [i64, ci, ci]
+        getattr(L, name).restype = i64
     L.gcp_tile_prepare_bytes.argtypes = [i64]
     L.gcp_tile_prepare_bytes.restype = sz
     L.gcp_tile_prepare.argtypes = [vp, vp, i64, ci, ci, vp, vp, vp, sz, vp]
     L.gcp_tile_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
-    L.gcp_tile_bin_bytes.argtypes = [i64]
+    L.gcp_tile_bin_bytes.argtypes = [i64, ci, ci]
     L.gcp_tile_bin_bytes.restype = sz
     L.gcp_tile_bin.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, sz, vp]
-    L.gcp_tile_render.argtypes = [vp, vp, vp, vp, i64, ci, ci, vp, vp, vp]
-    L.gcp_tile_backward.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
+    L.gcp_tile_render.argtypes = [vp, vp, vp, vp, i64, ci, ci, vp, vp, vp, vp]
+    L.gcp_tile_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
     L.gcp_tile_reduce.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
     L.gcp_tile_reduce_bytes.argtypes = [i64]
     L.gcp_tile_reduce_bytes.restype = sz

@@ -164,7 +164,7 @@ class _View:
 class _TileView:
     """Tile route: the tile-sorted pair list, the packed tables and the exclusive T of every (pair, lane)
     (128 B per pair) kept for the backward."""
-    __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "torder", "pgid", "tkeep", "l_d")
+    __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "plan", "pstate", "pgid", "tkeep", "l_d")
 
 
 def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
@@ -206,14 +206,15 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
             raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
         v.P = P
         v.tstart = torch.empty(int(L.gcp_tile_num_tiles(W, H)) + 1, dtype=torch.int32, device=dev)
-        v.torder = torch.empty(int(L.gcp_tile_order_ints(W, H)), dtype=torch.int32, device=dev)
+        v.plan = torch.empty(int(L.gcp_tile_plan_ints(P, W, H)), dtype=torch.int32, device=dev)
+        v.pstate = torch.empty(int(L.gcp_tile_state_floats(P, W, H)), dtype=torch.float32, device=dev)
         v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
         v.tkeep = torch.empty(max(P, 1) * 32, dtype=torch.float32, device=dev)
-        temp = _scratch_bytes(dev, "bin", int(L.gcp_tile_bin_bytes(P)))
-        _lib.check(L.gcp_tile_bin(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.torder), _p(v.pgid),
+        temp = _scratch_bytes(dev, "bin", int(L.gcp_tile_bin_bytes(P, W, H)))
+        _lib.check(L.gcp_tile_bin(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.plan), _p(v.pgid),
                                   _p(temp), temp.numel(), stream), "gcp_tile_bin")
-        _lib.check(L.gcp_tile_render(_p(v.tstart), _p(v.torder), _p(v.pgid), _p(v.rec), P, W, H, _p(image),
-                                     _p(v.tkeep), stream), "gcp_tile_render")
+        _lib.check(L.gcp_tile_render(_p(v.tstart), _p(v.plan), _p(v.pgid), _p(v.rec), P, W, H, _p(image),
+                                     _p(v.tkeep), _p(v.pstate), stream), "gcp_tile_render")
     return image, v
 
 
@@ -229,8 +230,8 @@ def _render_backward_tiles(v: _TileView, grad_image):
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         partial = torch.empty(max(v.P, 1) * 8, dtype=torch.float32, device=dev)
-        _lib.check(L.gcp_tile_backward(_p(v.tstart), _p(v.torder), _p(v.pgid), _p(v.rec), _p(v.tkeep), _p(gI), v.P,
-                                       v.W, v.H, _p(partial), stream), "gcp_tile_backward")
+        _lib.check(L.gcp_tile_backward(_p(v.tstart), _p(v.plan), _p(v.pgid), _p(v.rec), _p(v.tkeep), _p(v.pstate),
+                                       _p(gI), v.P, v.W, v.H, _p(partial), stream), "gcp_tile_backward")
         temp = _scratch_bytes(dev, "tile_reduce", int(L.gcp_tile_reduce_bytes(n)))
         _lib.check(L.gcp_tile_reduce(_p(partial), _p(v.toff), _p(v.l_d), n, _p(g_mean), _p(g_lam), _p(g_opac),
                                      _p(g_l), _p(temp), temp.numel(), stream), "gcp_tile_reduce")

@@ -147,36 +147,57 @@ k_tile_start(const int32_t *__restrict__ ptile_s, int64_t P, int ntiles, int32_t
     for (int c = prev + 1; c <= cur; ++c) tstart[c] = static_cast<int32_t>(p);
 }
 
-// Longest tiles first: torder = the tiles whose list is longer than `long_len` (from the front, any order), then
-// the others (filled from the back).  The walk kernels hand tiles out in this order (a warp per tile, dynamic
-// tickets), so the long serial walks start at once and the short ones fill in behind them.  ctr[0] / ctr[1]:
-// front / back counters (zeroed by the caller); warp-aggregated, two atomics per warp.
-__global__ void __launch_bounds__(256)
-k_tile_order(const int32_t *__restrict__ tstart, int ntiles, int long_len, int32_t *__restrict__ torder,
-             unsigned int *__restrict__ ctr) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool in = t < ntiles;
-    const bool is_long = in && (__ldg(tstart + t + 1) - __ldg(tstart + t) > long_len);
-    const unsigned ml = __ballot_sync(0xffffffffu, is_long), ms = __ballot_sync(0xffffffffu, in && !is_long);
-    unsigned bl = 0, bs = 0;
-    if (lane == 0) {
-        if (ml) bl = atomicAdd(ctr, __popc(ml));
-        if (ms) bs = atomicAdd(ctr + 1, __popc(ms));
+// Work units of the walk kernels are PIECES: at most `piece` consecutive pairs of one tile's list (a multiple of
+// 32).  Most tiles are one piece.  A tile with a long list (bundled scene: thousands of Gaussians over one tile,
+// ten times the mean) is cut into several, walked by different warps at the same time, each starting from the
+// identity; the per-pixel carries between the pieces of a tile are the segmented scan's cross-block carries:
+//   forward : T_i = carry_p * Tlocal_i,  carry_p = prod of the aggregates of the earlier pieces; the colour is
+//             linear in the carry, C = sum_p carry_p * C_p                                  (k_tile_combine_fwd)
+//   backward: U after the last element of piece p:  U_in(p) = Tagg_{p+1} U_in(p+1) + <dL/dI, C_{p+1}>  — the
+//             affine map of a piece is made of the SAME two per-pixel quantities the forward already produced,
+//             its aggregate and its colour, so the backward needs no pass of its own for them  (k_tile_combine_bwd)
+// piece state per piece (f32[192]): {Tagg[32], C0[32], C1[32], C2[32], carry[32], U_in[32]}, touched only for the
+// pieces of multi-piece tiles.
+constexpr int PIECE_STATE = 192;
+
+struct PieceCount {   // pieces of tile t: ceil(len / piece), 1 for an empty tile (its pixels still get written)
+    const int32_t *tstart;
+    int piece;
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t t) const {
+        const int len = tstart[t + 1] - tstart[t];
+        return len <= piece ? 1 : (len + piece - 1) / piece;
     }
-    bl = __shfl_sync(0xffffffffu, bl, 0);
-    bs = __shfl_sync(0xffffffffu, bs, 0);
-    const unsigned lt = (1u << lane) - 1u;
-    if (is_long) torder[bl + __popc(ml & lt)] = t;
-    else if (in) torder[ntiles - 1 - (bs + __popc(ms & lt))] = t;
+};
+
+// ptile[p] = tile of piece p  (pstart: exclusive offsets of the tiles' pieces, pstart[ntiles] = number of pieces)
+__global__ void __launch_bounds__(256)
+k_tile_pieces(const int32_t *__restrict__ pstart, int ntiles, int32_t *__restrict__ ptile) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int b = __ldg(pstart + t), e = __ldg(pstart + t + 1);
+    for (int p = b; p < e; ++p) ptile[p] = t;
 }
 
-// next tile of this warp (dynamic ticket), -1 when none is left
-__device__ __forceinline__ int next_tile(unsigned int *ticket, const int32_t *__restrict__ torder, int ntiles, int lane) {
+struct Piece {
+    int p, t, np;        // piece id, tile, pieces of that tile
+    int64_t lo, hi;      // pair range of the piece inside the tile-sorted pair list
+};
+// next piece of this warp (dynamic ticket); false when none is left
+__device__ __forceinline__ bool next_piece(unsigned int *ticket, const int32_t *__restrict__ tstart,
+                                           const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile,
+                                           int npieces, int piece, int lane, Piece &w) {
     unsigned i = 0;
     if (lane == 0) i = atomicAdd(ticket, 1u);
     i = __shfl_sync(0xffffffffu, i, 0);
-    return i < static_cast<unsigned>(ntiles) ? __ldg(torder + i) : -1;
+    if (i >= static_cast<unsigned>(npieces)) return false;
+    w.p = static_cast<int>(i);
+    w.t = __ldg(ptile + i);
+    const int p0 = __ldg(pstart + w.t);
+    w.np = __ldg(pstart + w.t + 1) - p0;
+    const int64_t tlo = __ldg(tstart + w.t), thi = __ldg(tstart + w.t + 1);
+    w.lo = tlo + static_cast<int64_t>(w.p - p0) * piece;
+    w.hi = (w.lo + piece < thi) ? w.lo + piece : thi;
+    return true;
 }
 
 // one 32-byte sector in one instruction (LDG.256, sm_100)
@@ -247,20 +268,22 @@ constexpr int TILE_WARPS = 8;
 
 __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
-              const int32_t *__restrict__ torder, unsigned int *__restrict__ ticket, int ntx, int ntiles, int W, int H,
-              float *__restrict__ image, float *__restrict__ tkeep) {
+              const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
+              int piece, int ntx, int ntiles, int W, int H, float *__restrict__ image, float *__restrict__ tkeep,
+              float *__restrict__ pstate) {
     __shared__ PairSlot slots[TILE_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     PairSlot *sl = slots[wib];
-    for (;;) {  // warp-uniform loop; only __syncwarp inside
-        const int t = next_tile(ticket, torder, ntiles, lane);
-        if (t < 0) break;
+    const int npieces = __ldg(pstart + ntiles);
+    Piece w;
+    while (next_piece(ticket, tstart, pstart, ptile, npieces, piece, lane, w)) {  // warp-uniform; only __syncwarp inside
+        const int t = w.t;
         const int ty = t / ntx, tx = t - ty * ntx;
         const int x0 = tx << TSX, y0 = ty << TSY;
         const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
         const float px = static_cast<float>(ix), py = static_cast<float>(iy);
-        const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
-        float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        const int64_t lo = w.lo, hi = w.hi;
+        float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;   // T: local to the piece (its carry is applied afterwards)
         // software pipeline over batches of 32 pairs: ids two batches ahead, records one batch ahead
         int g1 = 0;
         RecRegs r = {};
@@ -292,10 +315,63 @@ k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pg
             }
             __syncwarp();
         }
-        if (ix <= W && iy <= H) {
+        if (w.np > 1) {
+            float *ps = pstate + static_cast<int64_t>(w.p) * PIECE_STATE + lane;
+            ps[0] = T; ps[32] = c0; ps[64] = c1; ps[96] = c2;
+        } else if (ix <= W && iy <= H) {
             float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
             p[0] = c0; p[1] = c1; p[2] = c2;
         }
+    }
+}
+
+// tiles of several pieces: the carry of every piece (kept for the backward), and the pixel's colour
+__global__ void __launch_bounds__(256)
+k_tile_combine_fwd(const int32_t *__restrict__ pstart, int ntx, int ntiles, int W, int H, float *__restrict__ pstate,
+                   float *__restrict__ image) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int p0 = __ldg(pstart + t), np = __ldg(pstart + t + 1) - p0;
+    if (np <= 1) return;
+    float carry = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int k = 0; k < np; ++k) {
+        float *ps = pstate + static_cast<int64_t>(p0 + k) * PIECE_STATE + lane;
+        ps[128] = carry;
+        c0 = fmaf(carry, ps[32], c0);
+        c1 = fmaf(carry, ps[64], c1);
+        c2 = fmaf(carry, ps[96], c2);
+        carry *= ps[0];
+    }
+    const int ty = t / ntx, tx = t - ty * ntx;
+    const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
+    if (ix <= W && iy <= H) {
+        float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+        p[0] = c0; p[1] = c1; p[2] = c2;
+    }
+}
+
+// tiles of several pieces: U after the last element of every piece, from the pieces behind it
+__global__ void __launch_bounds__(256)
+k_tile_combine_bwd(const int32_t *__restrict__ pstart, const float *__restrict__ gimg, int ntx, int ntiles, int W,
+                   int H, float *__restrict__ pstate) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int p0 = __ldg(pstart + t), np = __ldg(pstart + t + 1) - p0;
+    if (np <= 1) return;
+    const int ty = t / ntx, tx = t - ty * ntx;
+    const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
+    float pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
+    if (ix <= W && iy <= H) {
+        const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+        pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
+    }
+    float U = 0.0f;
+    for (int k = np - 1; k >= 0; --k) {
+        float *ps = pstate + static_cast<int64_t>(p0 + k) * PIECE_STATE + lane;
+        ps[160] = U;
+        U = fmaf(ps[0], U, pg0 * ps[32] + pg1 * ps[64] + pg2 * ps[96]);
     }
 }
 
@@ -330,19 +406,20 @@ __device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
 
 // partial[q] = {sum g dalpha, sum d, sum coef X0, sum coef X1, sum hc d0 d0, sum hc d0 d1, sum hc d1 d1, 0}
 // over the pixels of pair q (coef = alpha dalpha, hc = -coef/2), see gs_model.py:733-766
-__global__ void __launch_bounds__(TILE_WARPS * 32)
+__global__ void __launch_bounds__(TILE_WARPS * 32, 4)
 k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
-                const int32_t *__restrict__ torder, unsigned int *__restrict__ ticket,
-                const float *__restrict__ tkeep, const float *__restrict__ gimg, int ntx, int ntiles, int W, int H,
-                float *__restrict__ partial) {
+                const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
+                int piece, const float *__restrict__ tkeep, const float *__restrict__ pstate,
+                const float *__restrict__ gimg, int ntx, int ntiles, int W, int H, float *__restrict__ partial) {
     __shared__ PairSlot slots[TILE_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     PairSlot *sl = slots[wib];
     const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    for (;;) {
-        const int t = next_tile(ticket, torder, ntiles, lane);
-        if (t < 0) break;
-        const int64_t lo = __ldg(tstart + t), hi = __ldg(tstart + t + 1);
+    const int npieces = __ldg(pstart + ntiles);
+    Piece w;
+    while (next_piece(ticket, tstart, pstart, ptile, npieces, piece, lane, w)) {
+        const int t = w.t;
+        const int64_t lo = w.lo, hi = w.hi;
         if (lo >= hi) continue;
         const int ty = t / ntx, tx = t - ty * ntx;
         const int x0 = tx << TSX, y0 = ty << TSY;
@@ -353,8 +430,14 @@ k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ 
             const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
             pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
         }
-        float U = 0.0f;
-        // batches of 32 pairs from the END of the tile's list: [bb, be), be = hi, hi - 32, ...
+        // a piece of a longer list starts from the carries the combine kernels left: T = carry * Tlocal, U = U_in
+        float carry = 1.0f, U = 0.0f;
+        if (w.np > 1) {
+            const float *ps = pstate + static_cast<int64_t>(w.p) * PIECE_STATE + lane;
+            carry = __ldg(ps + 128);
+            U = __ldg(ps + 160);
+        }
+        // batches of 32 pairs from the END of the piece: [bb, be), be = hi, hi - 32, ...
         int g1 = 0;
         RecRegs r = {};
         {
@@ -394,7 +477,7 @@ k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ 
                     const float2 C = sl[k].c;
                     const bool cov = (sl[k].mask >> lane) & 1u;
                     const int q = sl[k].q;
-                    const float T = tc[j];
+                    const float T = carry * tc[j];
                     const PairEval e = eval_pair(A, B, px, py);
                     const bool alive = cov && (T * e.x != 0.0f);
                     const float alpha = 1.0f - e.x;
@@ -503,14 +586,17 @@ k_tile_reduce_big(const float *__restrict__ partial, const int64_t *__restrict__
 struct BinLayout {
     size_t ptile, pgid, ptile_s, cub, total, cub_bytes;
 };
-BinLayout bin_layout(int64_t P) {
+BinLayout bin_layout(int64_t P, int ntiles) {
     BinLayout L;
     const size_t pb = align256(static_cast<size_t>(P > 0 ? P : 1) * 4);
     size_t a = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
                                     static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
                                     P > 0 ? P : 1, 0, 24);
-    L.cub_bytes = align256(a);
+    size_t b = 0;   // the scan of the tiles' piece counts shares the sort's scratch
+    cub::DeviceScan::InclusiveSum(nullptr, b, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                  ntiles > 0 ? ntiles : 1);
+    L.cub_bytes = align256(std::max(a, b) + 256);
     L.ptile = 0;
     L.pgid = L.ptile + pb;
     L.ptile_s = L.pgid + pb;
@@ -520,7 +606,7 @@ BinLayout bin_layout(int64_t P) {
 }
 
 // persistent grid of the walk kernels: every resident warp slot of the device, never more warps than tiles
-unsigned walk_grid(const void *kernel, int ntiles) {
+unsigned walk_grid(const void *kernel, int64_t nwork) {
     static const void *known[2] = {nullptr, nullptr};
     static unsigned slots[2] = {0, 0};  // resident blocks of the (two) walk kernels, queried once
     int i = (known[0] == kernel || known[0] == nullptr) ? 0 : 1;
@@ -533,8 +619,10 @@ unsigned walk_grid(const void *kernel, int ntiles) {
         slots[i] = static_cast<unsigned>(sms * per_sm);
         known[i] = kernel;
     }
-    return std::max(1u, std::min(blocks_for(ntiles, TILE_WARPS), slots[i]));
+    return std::max(1u, std::min(blocks_for(nwork, TILE_WARPS), slots[i]));
 }
+
+int g_piece = 128;  // pairs per piece (gcp_tile_set_piece_pairs)
 
 inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >= 32768; }
 inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
@@ -547,7 +635,21 @@ extern "C" {
 int gcp_tile_width(void) { return TW; }
 int gcp_tile_height(void) { return TH; }
 int gcp_tile_num_tiles(int W, int H) { return bad_image(W, H) ? 0 : tiles_x(W) * tiles_y(H); }
-int gcp_tile_order_ints(int W, int H) { return bad_image(W, H) ? 0 : tiles_x(W) * tiles_y(H) + 4; }
+/* longest run of one tile's pairs a single warp walks (multiple of 32); longer lists are cut into pieces */
+int gcp_tile_set_piece_pairs(int pairs) {
+    if (pairs < 32 || pairs > (1 << 20) || (pairs & 31)) return GCP_ERR_INVALID_ARG;
+    g_piece = pairs;
+    return GCP_OK;
+}
+int gcp_tile_piece_pairs(void) { return g_piece; }
+int64_t gcp_tile_piece_cap(int64_t P, int W, int H) {
+    return (P < 0 || bad_image(W, H)) ? 0 : tiles_x(W) * tiles_y(H) + P / g_piece + 1;
+}
+/* piece_plan i32[]: piece_start[ntiles+1] | piece_tile[cap] | 4 counter words */
+int64_t gcp_tile_plan_ints(int64_t P, int W, int H) {
+    return (P < 0 || bad_image(W, H)) ? 0 : tiles_x(W) * tiles_y(H) + 1 + gcp_tile_piece_cap(P, W, H) + 4;
+}
+int64_t gcp_tile_state_floats(int64_t P, int W, int H) { return gcp_tile_piece_cap(P, W, H) * PIECE_STATE; }
 
 size_t gcp_tile_prepare_bytes(int64_t n) {
     size_t a = 0;
@@ -590,67 +692,92 @@ int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const 
     return static_cast<int>(cudaGetLastError());
 }
 
-size_t gcp_tile_bin_bytes(int64_t P) { return P < 0 ? 0 : bin_layout(P).total; }
+size_t gcp_tile_bin_bytes(int64_t P, int W, int H) {
+    return (P < 0 || bad_image(W, H)) ? 0 : bin_layout(P, tiles_x(W) * tiles_y(H)).total;
+}
 
 int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
-                 int32_t *tile_start, int32_t *tile_order, int32_t *pair_gid, void *temp, size_t temp_bytes,
+                 int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
                  gcp_stream_t stream) {
     if (n < 0 || P < 0 || P >= (int64_t(1) << 31) - 64 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
-    if (!tile_start || !tile_order || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid))) return GCP_ERR_INVALID_ARG;
-    const BinLayout L = bin_layout(P);
+    if (!tile_start || !piece_plan || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid)))
+        return GCP_ERR_INVALID_ARG;
+    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    const BinLayout L = bin_layout(P, ntiles);
     if (temp_bytes < L.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char *t = static_cast<unsigned char *>(temp);
     int32_t *ptile = reinterpret_cast<int32_t *>(t + L.ptile), *pgid = reinterpret_cast<int32_t *>(t + L.pgid);
     int32_t *ptile_s = reinterpret_cast<int32_t *>(t + L.ptile_s);
-    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    cudaError_t e;
     if (P > 0) {
         k_tile_pairs<<<blocks_for(P, 256 * CHP), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
         size_t cb = L.cub_bytes;
         // stable LSD radix sort on the tile bits only: inside a tile the Gaussians keep their (depth) order
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, ptile, ptile_s, pgid, pair_gid, P, 0,
-                                                        key_bits(ntiles), st);
+        e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, ptile, ptile_s, pgid, pair_gid, P, 0, key_bits(ntiles), st);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     k_tile_start<<<blocks_for(P + 1, 256), 256, 0, st>>>(ptile_s, P, ntiles, tile_start);
-    // walk order: tiles with more than twice the mean list length first
-    unsigned int *ctr = reinterpret_cast<unsigned int *>(tile_order + ntiles);
-    cudaError_t e = cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st);
+    // the pieces: exclusive offsets per tile, then the tile of every piece
+    int32_t *pstart = piece_plan, *piece_tile = piece_plan + ntiles + 1;
+    e = cudaMemsetAsync(pstart, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return static_cast<int>(e);
-    const int long_len = static_cast<int>(std::min<int64_t>(2 * (P / ntiles) + 1, 0x7fffffff));
-    k_tile_order<<<blocks_for(ntiles, 256), 256, 0, st>>>(tile_start, ntiles, long_len, tile_order, ctr);
+    auto counts = thrust::make_transform_iterator(thrust::counting_iterator<int32_t>(0), PieceCount{tile_start, g_piece});
+    size_t need = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, need, counts, pstart + 1, ntiles);
+    if (need > L.cub_bytes) return GCP_ERR_WORKSPACE;
+    size_t cb = L.cub_bytes;
+    e = cub::DeviceScan::InclusiveSum(t + L.cub, cb, counts, pstart + 1, ntiles, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_tile_pieces<<<blocks_for(ntiles, 256), 256, 0, st>>>(pstart, ntiles, piece_tile);
     return static_cast<int>(cudaGetLastError());
 }
 
-int gcp_tile_render(const int32_t *tile_start, int32_t *tile_order, const int32_t *pair_gid, const int32_t *rec,
-                    int64_t P, int W, int H, float *image, float *t_keep, gcp_stream_t stream) {
-    if (P < 0 || bad_image(W, H) || !tile_start || !tile_order || !image) return GCP_ERR_INVALID_ARG;
+namespace {
+struct PlanView {
+    const int32_t *pstart, *ptile;
+    unsigned int *tickets;
+    int64_t cap;
+};
+PlanView plan_view(int32_t *piece_plan, int64_t P, int W, int H) {
+    const int ntiles = tiles_x(W) * tiles_y(H);
+    const int64_t cap = gcp_tile_piece_cap(P, W, H);
+    return PlanView{piece_plan, piece_plan + ntiles + 1,
+                    reinterpret_cast<unsigned int *>(piece_plan + ntiles + 1 + cap), cap};
+}
+}  // namespace
+
+int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
+                    int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream) {
+    if (P < 0 || bad_image(W, H) || !tile_start || !piece_plan || !image || !piece_state) return GCP_ERR_INVALID_ARG;
     if (P > 0 && (!pair_gid || !rec || !t_keep)) return GCP_ERR_INVALID_ARG;
     auto st = reinterpret_cast<cudaStream_t>(stream);
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(tile_order + ntiles) + 2;
-    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+    const PlanView pv = plan_view(piece_plan, P, W, H);
+    cudaError_t e = cudaMemsetAsync(pv.tickets, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_tile_render<<<walk_grid(reinterpret_cast<const void *>(k_tile_render), ntiles), TILE_WARPS * 32, 0, st>>>(
-        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), tile_order, ticket, ntx, ntiles, W, H, image,
-        t_keep);
+    k_tile_render<<<walk_grid(reinterpret_cast<const void *>(k_tile_render), pv.cap), TILE_WARPS * 32, 0, st>>>(
+        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), pv.pstart, pv.ptile, pv.tickets, g_piece, ntx,
+        ntiles, W, H, image, t_keep, piece_state);
+    k_tile_combine_fwd<<<blocks_for(ntiles, 8), 256, 0, st>>>(pv.pstart, ntx, ntiles, W, H, piece_state, image);
     return static_cast<int>(cudaGetLastError());
 }
 
-int gcp_tile_backward(const int32_t *tile_start, int32_t *tile_order, const int32_t *pair_gid, const int32_t *rec,
-                      const float *t_keep, const float *grad_image, int64_t P, int W, int H, float *partial,
-                      gcp_stream_t stream) {
-    if (P < 0 || bad_image(W, H) || !tile_start || !tile_order || !grad_image) return GCP_ERR_INVALID_ARG;
+int gcp_tile_backward(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
+                      const float *t_keep, float *piece_state, const float *grad_image, int64_t P, int W, int H,
+                      float *partial, gcp_stream_t stream) {
+    if (P < 0 || bad_image(W, H) || !tile_start || !piece_plan || !grad_image) return GCP_ERR_INVALID_ARG;
     if (P == 0) return GCP_OK;
-    if (!pair_gid || !rec || !t_keep || !partial) return GCP_ERR_INVALID_ARG;
+    if (!pair_gid || !rec || !t_keep || !partial || !piece_state) return GCP_ERR_INVALID_ARG;
     auto st = reinterpret_cast<cudaStream_t>(stream);
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(tile_order + ntiles) + 3;
-    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+    const PlanView pv = plan_view(piece_plan, P, W, H);
+    cudaError_t e = cudaMemsetAsync(pv.tickets + 1, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_tile_backward<<<walk_grid(reinterpret_cast<const void *>(k_tile_backward), ntiles), TILE_WARPS * 32, 0, st>>>(
-        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), tile_order, ticket, t_keep, grad_image, ntx,
-        ntiles, W, H, partial);
+    k_tile_combine_bwd<<<blocks_for(ntiles, 8), 256, 0, st>>>(pv.pstart, grad_image, ntx, ntiles, W, H, piece_state);
+    k_tile_backward<<<walk_grid(reinterpret_cast<const void *>(k_tile_backward), pv.cap), TILE_WARPS * 32, 0, st>>>(
+        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), pv.pstart, pv.ptile, pv.tickets + 1, g_piece,
+        t_keep, piece_state, grad_image, ntx, ntiles, W, H, partial);
     return static_cast<int>(cudaGetLastError());
 }
 

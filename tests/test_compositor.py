@@ -383,3 +383,41 @@ def test_tile_route_equals_list_route_on_long_pixel_lists_gpu(monkeypatch):
     gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
     res = _both_routes(v, gI, monkeypatch)
     _assert_routes_agree(res, rtol=2e-3, atol_scale=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_tile_route_with_32_pair_pieces_gpu(name, monkeypatch):
+    """Every tile list longer than 32 pairs cut into pieces walked independently: the carries between the pieces
+    (T forward, U backward) must reproduce the reference fixtures, and a larger scene must equal the result with
+    the default piece length up to fp32 rounding."""
+    from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    L = _lib.lib()
+    default = L.gcp_tile_piece_pairs()
+    assert L.gcp_tile_set_piece_pairs(33) != 0          # must be a multiple of 32
+    try:
+        assert L.gcp_tile_set_piece_pairs(32) == 0
+        case = load_case(np.load(FIX), name)
+        _check(_run(case, "cuda"), case)
+        if name == "dense":
+            v = wl.bundled_views("cpu", n_views=2)[1]
+            k = 20000
+            gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+            outs = []
+            for pairs in (32, default):
+                assert L.gcp_tile_set_piece_pairs(pairs) == 0
+                m, lam, o, l = (v.mean[:k].float().cuda().requires_grad_(True), v.lam[:k].cuda().requires_grad_(True),
+                                v.opacity[:k].cuda().requires_grad_(True), v.l_d[:k].cuda().requires_grad_(True))
+                img = compositor.custom_autograd_grouped_cumprod.apply(
+                    v.boxsize[:k].cuda(), torch.tensor([k]), v.startpoint[:k].cuda(), v.endpoint[:k].cuda(), m, lam, o,
+                    l, v.width, v.height)
+                img.backward(gI)
+                outs.append([img.detach()] + [t.grad for t in (m, lam, o, l)])
+            for a, b in zip(*outs):
+                assert torch.isfinite(a).all()
+                scale = float(b.abs().max())
+                assert torch.allclose(a, b, rtol=1e-3, atol=1e-5 * scale), float((a - b).abs().max())
+    finally:
+        L.gcp_tile_set_piece_pairs(default)
