@@ -34,7 +34,6 @@ constexpr int TSX = 3, TSY = 2;                 // tile = 8 x 4 pixels, lane = (
 constexpr int TW = 1 << TSX, TH = 1 << TSY;
 static_assert(TW * TH == 32, "one tile is one warp");
 constexpr int REC_WORDS = 16;                   // per-Gaussian record: 64 bytes = two 32-byte sectors
-constexpr int CHP = 8;                          // consecutive pairs per thread in the emit kernel
 
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
@@ -100,6 +99,47 @@ k_tile_pack(const float *__restrict__ mean, const float *__restrict__ lam, const
     rec[4 * g + 3] = make_int4(b.ex, b.ey, static_cast<int>(__ldg(toff + g)), 0);
 }
 
+// pair p of Gaussian g (Gaussian-major, row-major over the tiles of its box): ptile[p] = tile index, pgid[p] = g.
+// One thread per Gaussian writes the pairs of a small box (adjacent threads write adjacent runs); a box of more
+// than 32 tiles is written by the whole warp afterwards.
+__global__ void __launch_bounds__(256)
+k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
+             int64_t n, int W, int H, int ntx, int32_t *__restrict__ ptile, int32_t *__restrict__ pgid) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int64_t beg = 0;
+    int cnt = 0, tx0 = 0, ty0 = 0, nx = 1;
+    if (g < n) {
+        beg = __ldg(toff + g);
+        cnt = static_cast<int>(__ldg(toff + g + 1) - beg);
+        const Box b = clip_box(sp, ep, g, W, H);
+        tx0 = b.sx >> TSX; ty0 = b.sy >> TSY; nx = (b.ex >> TSX) - tx0 + 1;
+    }
+    if (cnt <= 32) {
+        int r = 0, c = 0;
+        for (int i = 0; i < cnt; ++i) {
+            ptile[beg + i] = (ty0 + r) * ntx + tx0 + c;
+            pgid[beg + i] = static_cast<int32_t>(g);
+            if (++c == nx) { c = 0; ++r; }
+        }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, cnt > 32);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int64_t bbeg = __shfl_sync(0xffffffffu, beg, src);
+        const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
+        const int btx0 = __shfl_sync(0xffffffffu, tx0, src), bty0 = __shfl_sync(0xffffffffu, ty0, src);
+        const int bnx = __shfl_sync(0xffffffffu, nx, src);
+        const int32_t bg = static_cast<int32_t>(g - lane + src);
+        for (int i = lane; i < bcnt; i += 32) {
+            const int r = i / bnx;
+            ptile[bbeg + i] = (bty0 + r) * ntx + btx0 + (i - r * bnx);
+            pgid[bbeg + i] = bg;
+        }
+    }
+}
+
 // first index g with off[g+1] > e
 __device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, int64_t n, int64_t e) {
     int64_t lo = 0, hi = n - 1;
@@ -111,10 +151,13 @@ __device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, i
     return lo;
 }
 
-// pair p of Gaussian g (Gaussian-major, row-major over the tiles of its box): ptile[p] = tile index, pgid[p] = g
+// the same list, parallel over PAIRS (8 consecutive ones per thread, one search for the first): for views whose
+// boxes span many tiles each (bundled scene: ten pairs per Gaussian on average, thousands for some)
+constexpr int CHP = 8;
 __global__ void __launch_bounds__(256)
-k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
-             int64_t n, int64_t P, int W, int H, int ntx, int32_t *__restrict__ ptile, int32_t *__restrict__ pgid) {
+k_tile_pairs_flat(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
+                  int64_t n, int64_t P, int W, int H, int ntx, int32_t *__restrict__ ptile,
+                  int32_t *__restrict__ pgid) {
     const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CHP;
     if (p0 >= P) return;
     int64_t g = find_owner(toff, n, p0);
@@ -266,7 +309,7 @@ __device__ __forceinline__ PairEval eval_pair(const float4 &a, const float4 &b, 
 
 constexpr int TILE_WARPS = 8;
 
-__global__ void __launch_bounds__(TILE_WARPS * 32)
+__global__ void __launch_bounds__(TILE_WARPS * 32, 4)
 k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
               const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
               int piece, int ntx, int ntiles, int W, int H, float *__restrict__ image, float *__restrict__ tkeep,
@@ -711,7 +754,10 @@ int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int6
     int32_t *ptile_s = reinterpret_cast<int32_t *>(t + L.ptile_s);
     cudaError_t e;
     if (P > 0) {
-        k_tile_pairs<<<blocks_for(P, 256 * CHP), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
+        if (P <= 6 * n)   // small boxes: a thread per Gaussian; boxes of many tiles: parallel over the pairs
+            k_tile_pairs<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, toff, n, W, H, ntx, ptile, pgid);
+        else
+            k_tile_pairs_flat<<<blocks_for(P, 256 * CHP), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
         size_t cb = L.cub_bytes;
         // stable LSD radix sort on the tile bits only: inside a tile the Gaussians keep their (depth) order
         e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, ptile, ptile_s, pgid, pair_gid, P, 0, key_bits(ntiles), st);
