@@ -267,7 +267,9 @@ size_t gcp_tile_bin_bytes(int64_t P, int W, int H);
 int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
                  int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
                  gcp_stream_t stream);
-/* image f32[(H+1)*(W+1)*3] is written completely (no need to zero it). */
+/* image f32[(H+1)*(W+1)*3] is written completely (no need to zero it).  t_keep may be NULL when no backward will
+ * follow (a render without gradients skips the 128 B per pair).  gcp_tile_piece_pairs() must not change between
+ * gcp_tile_bin and the last walk of the same view. */
 int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
                     int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream);
 int gcp_tile_backward(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,

@@ -164,14 +164,15 @@ class _View:
 class _TileView:
     """Tile route: the tile-sorted pair list, the packed tables and the exclusive T of every (pair, lane)
     (128 B per pair) kept for the backward."""
-    __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "plan", "pstate", "pgid", "tkeep", "l_d")
+    __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "plan", "pstate", "pgid", "tkeep", "l_d", "piece")
 
 
-def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
+def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep=True) -> tuple:
     dev = startpoint.device
     L = _lib.lib()
     v = _TileView()
     v.W, v.H = W, H
+    v.piece = int(L.gcp_tile_piece_pairs())
     n = boxsize.numel()
     v.n = n
     with torch.cuda.device(dev):
@@ -209,12 +210,12 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
         v.plan = torch.empty(int(L.gcp_tile_plan_ints(P, W, H)), dtype=torch.int32, device=dev)
         v.pstate = torch.empty(int(L.gcp_tile_state_floats(P, W, H)), dtype=torch.float32, device=dev)
         v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-        v.tkeep = torch.empty(max(P, 1) * 32, dtype=torch.float32, device=dev)
+        v.tkeep = torch.empty(max(P, 1) * 32, dtype=torch.float32, device=dev) if keep else None
         temp = _scratch_bytes(dev, "bin", int(L.gcp_tile_bin_bytes(P, W, H)))
         _lib.check(L.gcp_tile_bin(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.plan), _p(v.pgid),
                                   _p(temp), temp.numel(), stream), "gcp_tile_bin")
         _lib.check(L.gcp_tile_render(_p(v.tstart), _p(v.plan), _p(v.pgid), _p(v.rec), P, W, H, _p(image),
-                                     _p(v.tkeep), _p(v.pstate), stream), "gcp_tile_render")
+                                     _p(v.tkeep) if keep else None, _p(v.pstate), stream), "gcp_tile_render")
     return image, v
 
 
@@ -222,6 +223,10 @@ def _render_backward_tiles(v: _TileView, grad_image):
     dev = grad_image.device
     n = v.n
     L = _lib.lib()
+    if v.tkeep is None:
+        raise RuntimeError("this view was rendered without keeping T (no input required a gradient)")
+    if int(L.gcp_tile_piece_pairs()) != v.piece:
+        raise RuntimeError("gcp_tile_set_piece_pairs changed between the forward and the backward of a view")
     g_mean = torch.empty((n, 2), dtype=torch.float32, device=dev)
     g_lam = torch.empty((n, 4), dtype=torch.float32, device=dev)
     g_opac = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -238,12 +243,13 @@ def _render_backward_tiles(v: _TileView, grad_image):
     return g_mean, g_lam, g_opac, g_l
 
 
-def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H) -> tuple:
+def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep=True) -> tuple:
+    """keep=False: a render no backward will follow (tile route: the per-pair T is not stored)."""
     dev = startpoint.device
     if dev.type != "cuda":
         raise RuntimeError("custom_autograd_grouped_cumprod needs CUDA tensors (there is no CPU path)")
     if ROUTE == "tiles":
-        return _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H)
+        return _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep)
     if ROUTE != "lists":
         raise ValueError(f"unknown compositor route {ROUTE!r}")
     L = _lib.lib()
@@ -376,7 +382,7 @@ class custom_autograd_grouped_cumprod(torch.autograd.Function):
                 image_height):
         with torch.no_grad():
             image, view = _render_forward(boxsize, startpoint, endpoint, mean, variance_inverse, opacity, l_d,
-                                          int(image_width), int(image_height))
+                                          int(image_width), int(image_height), keep=any(ctx.needs_input_grad))
         ctx.view = view
         ctx.shapes = (mean.dtype, variance_inverse.shape, opacity.shape)
         return image

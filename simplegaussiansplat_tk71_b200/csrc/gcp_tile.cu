@@ -309,6 +309,7 @@ __device__ __forceinline__ PairEval eval_pair(const float4 &a, const float4 &b, 
 
 constexpr int TILE_WARPS = 8;
 
+template <bool KEEP>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 4)
 k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
               const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
@@ -348,7 +349,7 @@ k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pg
                 const bool cov = (sl[k].mask >> lane) & 1u;
                 const PairEval e = eval_pair(A, B, px, py);
                 const float tin = T * e.x;
-                __stcs(tk + k * 32, T);
+                if (KEEP) __stcs(tk + k * 32, T);   // not kept for a render without backward
                 // branch-free: an element outside the box, or dead (inclusive product 0, gs_model.py:575-578), adds 0
                 const float ta = (cov && tin != 0.0f) ? T * (1.0f - e.x) : 0.0f;
                 c0 = fmaf(ta, B.w, c0);
@@ -796,15 +797,22 @@ PlanView plan_view(int32_t *piece_plan, int64_t P, int W, int H) {
 int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
                     int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream) {
     if (P < 0 || bad_image(W, H) || !tile_start || !piece_plan || !image || !piece_state) return GCP_ERR_INVALID_ARG;
-    if (P > 0 && (!pair_gid || !rec || !t_keep)) return GCP_ERR_INVALID_ARG;
+    if (P > 0 && (!pair_gid || !rec)) return GCP_ERR_INVALID_ARG;   // t_keep may be NULL: forward only
     auto st = reinterpret_cast<cudaStream_t>(stream);
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
     const PlanView pv = plan_view(piece_plan, P, W, H);
     cudaError_t e = cudaMemsetAsync(pv.tickets, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_tile_render<<<walk_grid(reinterpret_cast<const void *>(k_tile_render), pv.cap), TILE_WARPS * 32, 0, st>>>(
-        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), pv.pstart, pv.ptile, pv.tickets, g_piece, ntx,
-        ntiles, W, H, image, t_keep, piece_state);
+    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_tile_render<true>), pv.cap);
+    if (t_keep != nullptr)
+        k_tile_render<true><<<grid, TILE_WARPS * 32, 0, st>>>(tile_start, pair_gid, reinterpret_cast<const int4 *>(rec),
+                                                              pv.pstart, pv.ptile, pv.tickets, g_piece, ntx, ntiles, W,
+                                                              H, image, t_keep, piece_state);
+    else
+        k_tile_render<false><<<grid, TILE_WARPS * 32, 0, st>>>(tile_start, pair_gid,
+                                                               reinterpret_cast<const int4 *>(rec), pv.pstart, pv.ptile,
+                                                               pv.tickets, g_piece, ntx, ntiles, W, H, image, t_keep,
+                                                               piece_state);
     k_tile_combine_fwd<<<blocks_for(ntiles, 8), 256, 0, st>>>(pv.pstart, ntx, ntiles, W, H, piece_state, image);
     return static_cast<int>(cudaGetLastError());
 }

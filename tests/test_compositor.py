@@ -421,3 +421,22 @@ def test_tile_route_with_32_pair_pieces_gpu(name, monkeypatch):
                 assert torch.allclose(a, b, rtol=1e-3, atol=1e-5 * scale), float((a - b).abs().max())
     finally:
         L.gcp_tile_set_piece_pairs(default)
+
+
+@pytest.mark.gpu
+def test_render_without_gradients_skips_the_kept_T_gpu(route):
+    """No input requires a gradient: same image; the tile route then does not store T for a backward."""
+    from simplegaussiansplat_tk71_b200 import compositor
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    case = load_case(np.load(FIX), "dense")
+    want = _run(case, "cuda")[0]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    args = (t(case["boxsize"]), torch.tensor([0]), t(case["sp"]), t(case["ep"]), t(case["mean"]).float(),
+            t(case["lam"]), t(case["opac"]), t(case["l_d"]), case["W"], case["H"])
+    with torch.no_grad():
+        img = F.apply(*args)
+    assert np.array_equal(img.cpu().numpy(), want) or np.allclose(img.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    _, view = compositor._render_forward(*args[:1], *args[2:], keep=False)
+    if route == "tiles":
+        assert view.tkeep is None

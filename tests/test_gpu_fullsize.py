@@ -99,3 +99,37 @@ def test_c4_full_size_properties():
     logsum = torch.zeros(e.k, dtype=torch.float64, device="cuda").index_add_(0, e.inv.long(), torch.log(e.x.double()))
     ok = torch.isclose(last.double(), torch.exp(logsum), rtol=2e-3, atol=1e-30)
     assert bool(ok.all()), int((~ok).sum())
+
+
+def test_splat_step_full_size_routes_agree_and_exact_properties(monkeypatch):
+    """BASELINE.json's splat-step workload at full size (1920x1080, 1 M Gaussians, 37 M elements): the fused tile
+    route against the element-list route (scan ops a1/a3 inside), plus properties that hold exactly:
+      * opacity 0 everywhere -> a black image and zero gradients (T = 1 all along every list);
+      * the tile route is bitwise reproducible (no float atomics)."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    v = wl.splat_view(1920, 1080, 1_000_000, device="cuda")
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+
+    def step(route, opacity):
+        monkeypatch.setattr(compositor, "ROUTE", route)
+        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                        opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+        img.backward(gI)
+        return [img.detach()] + [t.grad for t in (m, lam, o, l)]
+
+    tiles, tiles2, lists = step("tiles", v.opacity), step("tiles", v.opacity), step("lists", v.opacity)
+    for a, b in zip(tiles, tiles2):
+        assert torch.equal(a, b)
+    for name, a, b in zip(("image", "mean", "lambda", "opacity", "l"), tiles, lists):
+        assert torch.isfinite(a).all(), name
+        scale = float(b.abs().max())
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-6 * scale), (name, float((a - b).abs().max()), scale)
+    black = step("tiles", torch.zeros_like(v.opacity))
+    assert float(black[0].abs().max()) == 0.0
+    for g in (black[1], black[2], black[4]):      # d_mean, d_Lambda, d_l carry a factor alpha = 0
+        assert float(g.abs().max()) == 0.0
+    # d_opacity = sum over the box of g * <dL/dI, l> with T = 1 and U = 0: positive, finite
+    assert torch.isfinite(black[3]).all() and float(black[3].min()) >= 0.0
