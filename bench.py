@@ -494,8 +494,13 @@ def splat_legs(args, device, rank, world):
     compositor.ROUTE = default_route
     out = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n, "route": default_route,
            **routes[default_route], "unit": "ms per view (render + backward), median of 9", "routes": routes}
-    # (ii) multi-view step
+    # (ii) multi-view step.  One untimed step first: the first collective of a process sets up NCCL's channels and
+    #      buffers (30 ms at 8 ranks), which is not part of a training step.
     steps = 3
+    bucket.zero_()
+    for i in range(len(mine)):
+        one_view(i, plan_next=True)
+    vw.allreduce_param_grads(bucket)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
