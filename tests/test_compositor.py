@@ -440,3 +440,47 @@ def test_render_without_gradients_skips_the_kept_T_gpu(route):
     _, view = compositor._render_forward(*args[:1], *args[2:], keep=False)
     if route == "tiles":
         assert view.tkeep is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,n,max_half,piece", [
+    (17, 9, 300, 4, 32),        # image sizes that are not multiples of the 8x4 tile; every list in several pieces
+    (31, 33, 900, 12, 32),
+    (64, 3, 500, 40, 64),       # a single tile row, boxes wider than the image
+    (7, 7, 200, 2, 128),        # image smaller than two tiles
+    (100, 50, 3000, 9, 128),
+    (8, 4, 64, 1, 32),          # W+1 = 9, H+1 = 5: the last tile column / row hold one pixel
+])
+def test_native_compositor_ragged_image_sizes_against_oracle_gpu(W, H, n, max_half, piece, route):
+    """Random scenes on awkward image sizes (partial tiles, single rows, degenerate boxes of one pixel column)
+    against the fp64 oracle, for both routes and several piece lengths of the tile route."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from oracle import compositor_oracle as co
+    from simplegaussiansplat_tk71_b200 import _lib
+    import make_compositor_fixture as mk
+
+    boxsize, sp, ep, mean, lam, opac, l_d = mk.make_scene(100 + W, W, H, n, max_half, opaque=n // 20)
+    # a few degenerate boxes: one pixel wide / one pixel high, and one covering the whole image
+    sp[0], ep[0] = torch.tensor([0, 0]), torch.tensor([W, H])
+    ep[1, 0] = sp[1, 0]
+    ep[2, 1] = sp[2, 1]
+    boxsize = torch.prod((ep - sp + 1).to(torch.int64), dim=1)
+    rng = np.random.default_rng(W * 1000 + H)
+    gI = rng.uniform(0.1, 1.0, (H + 1, W + 1, 3)).astype(np.float32)
+    case = dict(boxsize=boxsize.numpy(), sp=sp.numpy(), ep=ep.numpy(), mean=mean.numpy(), lam=lam.numpy(),
+                opac=opac.numpy(), l_d=l_d.numpy(), W=W, H=H, grad_image=gI)
+    img, cache = co.forward(case["boxsize"], case["sp"], case["ep"], case["mean"], case["lam"], case["opac"],
+                            case["l_d"], W, H)
+    gm, gL, go, gl = co.backward(cache, gI)
+    L = _lib.lib()
+    default = L.gcp_tile_piece_pairs()
+    try:
+        assert L.gcp_tile_set_piece_pairs(piece) == 0
+        got = _run(case, "cuda")
+    finally:
+        L.gcp_tile_set_piece_pairs(default)
+    np.testing.assert_allclose(got[0], img, rtol=5e-4, atol=5e-5)
+    for name, a, b in (("mean", got[1], gm), ("lambda", got[2], gL), ("opacity", got[3], go), ("l", got[4], gl)):
+        scale = float(np.abs(b).max())
+        np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4 * scale, err_msg=name)
