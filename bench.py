@@ -318,9 +318,10 @@ def main():
     value = total_elems * args.steps / (max_ms * 1e-3) / 1e9
 
     # ---- e2e: the same step through the public host-buffer API (simplegaussiansplat_tk71_b200.host), pinned HOST
-    #      arrays in, pinned HOST arrays out, every copy inside the timed region.  The streamer uploads x, key and
-    #      grad_out only (the sorted keys double as segment ids), cuts the list at segment boundaries and overlaps
-    #      H2D, the two scan launches and D2H of neighbouring chunks on three streams. ----
+    #      arrays in, pinned HOST arrays out, every copy (and the host-side key packing) inside the timed region.
+    #      The streamer uploads x, grad_out and one run-start bit per element of key (the device rebuilds dense
+    #      segment ids from the bits), cuts the list at segment boundaries and overlaps H2D, the scan launches and
+    #      D2H of neighbouring chunks on three streams. ----
     from simplegaussiansplat_tk71_b200.host import HostStreamer
 
     e2e_steps = max(1, args.e2e_steps)

@@ -280,6 +280,20 @@ size_t gcp_tile_reduce_bytes(int64_t n);   /* scratch: the list of Gaussians wit
 int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,
                     float *g_lam, float *g_opac, float *g_l, void *temp, size_t temp_bytes, gcp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry point helpers (csrc/gcp_host.cu, used by simplegaussiansplat_tk71_b200/host.py).  With the
+ * element arrays in HOST memory the PCIe link bounds the step; the ops only need to know where the runs of equal
+ * adjacent keys start (grouped_cumprod_forward.cu:17-23), so `key` crosses the link as one bit per element.
+ * ------------------------------------------------------------------------------------------------ */
+/* HOST function (OpenMP, `threads` threads): bits[i>>5] bit (i&31) = 1 iff i == 0 or key[i] != key[i-1];
+ * key i32[n] and bits u32[(n+31)/32] are HOST pointers. */
+int gcp_host_boundary_bits(const int32_t *key, int64_t n, uint32_t *bits, int threads);
+/* Device: ids[i] = number of run starts in (0, i] — dense segment ids 0..k-1, usable as `key` of the forward ops
+ * and as `inv` of the backward op.  temp >= gcp_ids_from_bits_bytes(n). */
+size_t gcp_ids_from_bits_bytes(int64_t n);
+int gcp_ids_from_bits(const uint32_t *bits, int64_t n, int32_t *ids, void *temp, size_t temp_bytes,
+                      gcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

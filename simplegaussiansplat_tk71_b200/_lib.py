@@ -32,6 +32,7 @@ SYMBOLS = (
     "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs", "gcp_tile_piece_cap",
     "gcp_tile_plan_ints", "gcp_tile_state_floats", "gcp_tile_prepare_bytes", "gcp_tile_prepare",
     "gcp_tile_pack", "gcp_tile_bin_bytes", "gcp_tile_bin", "gcp_tile_render", "gcp_tile_backward", "gcp_tile_reduce", "gcp_tile_reduce_bytes",
+    "gcp_host_boundary_bits", "gcp_ids_from_bits_bytes", "gcp_ids_from_bits",
 )
 
 
@@ -100,6 +101,12 @@ def lib() -> ctypes.CDLL:
     L.gcp_splat_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]
     L.gcp_splat_bwd_reduce_bytes.argtypes = [i64, i64]
     L.gcp_splat_bwd_reduce_bytes.restype = sz
+    L.gcp_host_boundary_bits.argtypes = [vp, i64, vp, ci]
+    L.gcp_host_boundary_bits.restype = ci
+    L.gcp_ids_from_bits_bytes.argtypes = [i64]
+    L.gcp_ids_from_bits_bytes.restype = sz
+    L.gcp_ids_from_bits.argtypes = [vp, i64, vp, vp, sz, vp]
+    L.gcp_ids_from_bits.restype = ci
     L.gcp_tile_width.restype = ci
     L.gcp_tile_height.restype = ci
     L.gcp_tile_num_tiles.argtypes = [ci, ci]

@@ -17,8 +17,10 @@ SOURCES = {
     "gcp_abi.cu": ["gcp_device.cuh", "gcp_fwd.cuh", "gcp_bwd.cuh", "gcp_blk.cuh"],
     "gcp_splat.cu": [],
     "gcp_tile.cu": [],
+    "gcp_host.cu": [],
 }
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-Xcompiler", "-fopenmp"]   # OpenMP: the host-side key packing of gcp_host.cu
 
 
 def _mtime(p):
@@ -55,7 +57,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed on {src}")
     if relink or any(_mtime(o) > _mtime(LIB_PATH) for o in objs):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH, *objs])
+        subprocess.check_call([nvcc, "-shared", "-Xcompiler", "-fopenmp", "-o", LIB_PATH, *objs])
     return LIB_PATH
 
 

@@ -3,8 +3,11 @@
 The reference never moves the element arrays over PCIe (they are produced on the device, gs_model.py:598-605),
 but a caller that does hold them on the host gets the best the link allows from this streamer:
 
-  * only x, key and grad_out go up (12 B/element): the sorted pixel keys double as segment ids for the
-    backward op (it only compares neighbours), so `inv` / `inv_len` never cross the bus;
+  * only x, grad_out and ONE BIT per element of `key` go up (8.125 B/element): the ops need to know where the
+    runs of equal adjacent keys start and nothing else, so the host packs the run starts into bits
+    (`gcp_host_boundary_bits`: OpenMP + AVX2, memory-bound, ~0.5 ms per 8 Mi-element chunk) and the device rebuilds
+    dense segment ids with one scan (`gcp_ids_from_bits`); those ids serve as `key` of the forward and as `inv` of
+    the backward op, so `inv` / `inv_len` never cross the bus either;
   * the list is cut into chunks at segment boundaries (pixel lists are independent) and the chunks flow through
     three CUDA streams — H2D copies, the two scan launches, D2H copies — with `depth` buffer sets, so the
     uploads, the kernels and the downloads of neighbouring chunks overlap and PCIe runs full duplex.
@@ -13,10 +16,12 @@ All host tensors must be pinned for the copies to be asynchronous.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 def _cut_points(key: torch.Tensor, chunk: int) -> list:
@@ -56,6 +61,12 @@ class HostStreamer:
         mk = lambda dt: [torch.empty(cap, dtype=dt, device=self.device) for _ in range(depth)]  # noqa: E731
         self.dx, self.dg, self.dy, self.dgin = mk(torch.float32), mk(torch.float32), mk(torch.float32), mk(torch.float32)
         self.dk = mk(torch.int32)
+        words = (cap + 31) // 32 + 1
+        self.dbits = [torch.empty(words, dtype=torch.int32, device=self.device) for _ in range(depth)]
+        self.hbits = [torch.empty(words, dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.lib = _lib.lib()
+        self.scan_tmp = torch.empty(int(self.lib.gcp_ids_from_bits_bytes(cap)), dtype=torch.uint8, device=self.device)
+        self.threads = max(1, min(16, os.cpu_count() or 1))
         self.s_up = torch.cuda.Stream(self.device)
         self.s_run = torch.cuda.Stream(self.device)
         self.s_down = torch.cuda.Stream(self.device)
@@ -79,16 +90,25 @@ class HostStreamer:
             if m > self.cap:
                 raise RuntimeError(f"segment longer than the streaming buffers ({m} > {self.cap} elements)")
             i = c % self.depth
+            words = (m + 31) // 32
+            if up_done[i] is not None:
+                up_done[i].synchronize()                    # the pinned bit buffer i has been read by its upload
+            # where the runs of equal keys start, one bit per element (a chunk begins at a segment boundary)
+            _lib.check(self.lib.gcp_host_boundary_bits(key.data_ptr() + 4 * a, m, self.hbits[i].data_ptr(),
+                                                       self.threads), "gcp_host_boundary_bits")
             with torch.cuda.stream(self.s_up):
                 if down_done[i] is not None:
                     self.s_up.wait_event(down_done[i])      # buffer set i is free again
                 self.dx[i][:m].copy_(x[a:b], non_blocking=True)
-                self.dk[i][:m].copy_(key[a:b], non_blocking=True)
+                self.dbits[i][:words].copy_(self.hbits[i][:words], non_blocking=True)
                 self.dg[i][:m].copy_(grad_out[a:b], non_blocking=True)
                 up_done[i] = self.s_up.record_event()
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(up_done[i])
                 xs, ks, gs, ys, gi = self.dx[i][:m], self.dk[i][:m], self.dg[i][:m], self.dy[i][:m], self.dgin[i][:m]
+                _lib.check(self.lib.gcp_ids_from_bits(self.dbits[i].data_ptr(), m, ks.data_ptr(),
+                                                      self.scan_tmp.data_ptr(), self.scan_tmp.numel(),
+                                                      self.s_run.cuda_stream), "gcp_ids_from_bits")
                 ops.grouped_cumprod_forward(xs, ks, ys)
                 ops.grouped_cumprod_backward(xs, ys, gs, ks, gi, self.empty_len)
                 run_done[i] = self.s_run.record_event()
@@ -98,4 +118,4 @@ class HostStreamer:
                 grad_in_out[a:b].copy_(self.dgin[i][:m], non_blocking=True)
                 down_done[i] = self.s_down.record_event()
         cur.wait_stream(self.s_down)
-        return 12 * n, 8 * n
+        return 8 * n + 4 * sum((cuts[c + 1] - cuts[c] + 31) // 32 for c in range(len(cuts) - 1)), 8 * n

@@ -108,3 +108,27 @@ def test_splat_size_helpers_are_pure_host_arithmetic():
         assert L.gcp_splat_set_long_list_threshold(-1) == -1      # GCP_ERR_INVALID_ARG
     finally:
         L.gcp_splat_set_long_list_threshold(8)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 63, 64, 65, 100_000, 1_048_577])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_boundary_bits_match_numpy(n, threads):
+    """The host half of the host-buffer entry point (no GPU involved): one run-start bit per element."""
+    import numpy as np
+
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(n + threads)
+    key = (np.cumsum(rng.uniform(size=n) < 0.1).astype(np.int32) * 3 + 5) if n else np.zeros(0, np.int32)
+    key = np.concatenate([np.zeros(1, np.int32), key])[1:]          # an unaligned view of the data
+    words = (n + 31) // 32
+    bits = np.full(words + 1, 0xDEADBEEF, np.uint32)
+    assert L.gcp_host_boundary_bits(key.ctypes.data, n, bits.ctypes.data, threads) == 0
+    flags = np.ones(n, bool)
+    flags[1:] = key[1:] != key[:-1]
+    want = np.zeros(words, np.uint32)
+    idx = np.flatnonzero(flags)
+    np.bitwise_or.at(want, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    assert np.array_equal(bits[:words], want)
+    assert bits[words] == 0xDEADBEEF

@@ -360,7 +360,8 @@ def test_autograd_function_matches_torch_autograd():
 
 
 def test_host_streamer_matches_resident_ops(oracle):
-    """Host-buffer entry point: chunks cut at segment boundaries, three streams, keys doubling as segment ids."""
+    """Host-buffer entry point: chunks cut at segment boundaries, three streams, the keys crossing the link as one
+    run-start bit per element and rebuilt on the device as dense segment ids."""
     from simplegaussiansplat_tk71_b200.host import HostStreamer, _cut_points
 
     rng = np.random.default_rng(31)
@@ -382,6 +383,33 @@ def test_host_streamer_matches_resident_ops(oracle):
     assert all(key[c] != key[c - 1] for c in cuts[1:-1])    # every cut is a segment boundary
     up, down = st.fwd_bwd(hx, hk, hg, hy, hgin)
     torch.cuda.synchronize()
-    assert (up, down) == (12 * n, 8 * n)
+    assert down == 8 * n and 8 * n + n // 8 <= up <= 8 * n + n // 8 + 4 * len(cuts)
+    # twice more through the same buffers (the pinned bit buffers are reused round-robin)
+    hy.zero_()
+    hgin.zero_()
+    st.fwd_bwd(hx, hk, hg, hy, hgin)
+    torch.cuda.synchronize()
     assert_close(hy.numpy(), oracle.cumprod_fwd(x, key), "streamer fwd")
     assert_close(hgin.numpy(), oracle.cumprod_bwd_exact(x, g, inv), "streamer bwd")
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 4097, 1_000_003])
+def test_ids_from_run_start_bits(n):
+    """gcp_host_boundary_bits (host) + gcp_ids_from_bits (device) rebuild dense segment ids bit-exactly."""
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(n)
+    key = np.cumsum(rng.uniform(size=n) < 0.07).astype(np.int32) * 5 - 11     # runs of equal keys, arbitrary labels
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    assert L.gcp_host_boundary_bits(key.ctypes.data, n, bits.ctypes.data, 4) == 0
+    dbits = torch.from_numpy(bits.view(np.int32)).cuda()
+    ids = torch.full((n + 8,), -7, dtype=torch.int32, device="cuda")
+    tmp = torch.empty(int(L.gcp_ids_from_bits_bytes(n)), dtype=torch.uint8, device="cuda")
+    rc = L.gcp_ids_from_bits(dbits.data_ptr(), n, ids.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    want = np.concatenate([[0], np.cumsum(key[1:] != key[:-1])]).astype(np.int32)
+    got = ids.cpu().numpy()
+    assert np.array_equal(got[:n], want)
+    assert (got[n:] == -7).all()            # nothing written past the end
