@@ -24,12 +24,26 @@ import torch
 from . import _lib, ops
 
 
-def _cut_points(key: torch.Tensor, chunk: int) -> list:
-    """Chunk boundaries near multiples of `chunk`, moved forward to the next segment boundary."""
+def _chunk_sizes(n: int, chunk: int) -> list:
+    """Target chunk sizes: small first and last chunks (chunk/8, /4, /2, ... ramping up to `chunk` and down again).
+    While the first chunk goes up nothing comes down, and while the last one comes down nothing goes up, so short
+    end chunks cut the fill / drain time of the full-duplex pipeline (1.5 ms of a 14 ms step with equal chunks)."""
+    ramp = [max(1, chunk >> s) for s in (3, 2, 1)]
+    if n <= 2 * sum(ramp) + chunk:
+        return [chunk] * max(1, -(-n // chunk))
+    mid = n - 2 * sum(ramp)
+    k = -(-mid // chunk)
+    return ramp + [-(-mid // k)] * k + ramp[::-1]
+
+
+def _cut_points(key: torch.Tensor, chunk: int, ramp: bool = False) -> list:
+    """Chunk boundaries near the targets (multiples of `chunk`, or the ramped sizes of _chunk_sizes), each moved
+    forward to the next segment boundary."""
     n = key.numel()
     cuts = [0]
     k = key.numpy()
-    pos = chunk
+    sizes = _chunk_sizes(n, chunk) if ramp else None
+    pos = sizes[0] if ramp else chunk
     while pos < n:
         # first index >= pos where a new segment starts
         window = 1 << 16
@@ -44,7 +58,7 @@ def _cut_points(key: torch.Tensor, chunk: int) -> list:
         if j >= n:
             break
         cuts.append(j)
-        pos = j + chunk
+        pos = j + (sizes[min(len(cuts) - 1, len(sizes) - 1)] if ramp else chunk)
     cuts.append(n)
     return cuts
 
@@ -77,7 +91,7 @@ class HostStreamer:
         All five are 1-D pinned host tensors (f32, i32, f32, f32, f32).  Returns (h2d_bytes, d2h_bytes)."""
         n = x.numel()
         if cuts is None:
-            cuts = _cut_points(key, self.chunk)
+            cuts = _cut_points(key, self.chunk, ramp=True)
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_up, self.s_run, self.s_down):
             s.wait_stream(cur)
