@@ -89,6 +89,16 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
     return t.clone() if t.data_ptr() % 16 else t
 
 
+def _totals_to_host(totals, dev):
+    """Queue the copy of a prologue's totals into pinned host memory right behind it; returns (host tensor, event).
+    The host waits on the event only after it has queued everything that does not depend on the numbers."""
+    host = torch.empty(totals.numel(), dtype=torch.int64, pin_memory=True)
+    host.copy_(totals, non_blocking=True)
+    event = torch.cuda.Event()
+    event.record(torch.cuda.current_stream(dev))
+    return host, event
+
+
 def _prologue_tiles(L, dev, startpoint, endpoint, n, W, H):
     """(tile, Gaussian) pair offsets per Gaussian and the pair count, on the current stream."""
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -146,10 +156,7 @@ def plan_view(boxsize, startpoint, endpoint, image_width=None, image_height=None
             else:
                 pl.sp, pl.ep, pl.offs, totals = _prologue(L, dev, boxsize, startpoint, endpoint, n)
                 pl.route = ("lists",)
-            pl.host = torch.empty(totals.numel(), dtype=torch.int64, pin_memory=True)
-            pl.host.copy_(totals, non_blocking=True)
-            pl.event = torch.cuda.Event()
-            pl.event.record(side)
+            pl.host, pl.event = _totals_to_host(totals, dev)
     while len(_plans) >= _MAX_PLANS:
         _plans.pop(next(iter(_plans)))
     _plans[(_p(boxsize), _p(startpoint), _p(endpoint), n)] = pl
@@ -183,11 +190,13 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
             plan = None
         if plan is not None:
             cur.wait_event(plan.event)
-            sp, ep, toff, totals = plan.sp, plan.ep, plan.offs, None
+            sp, ep, toff = plan.sp, plan.ep, plan.offs
+            host, event = plan.host, plan.event
             for t_ in (sp, ep, toff):
                 t_.record_stream(cur)
         else:
             sp, ep, toff, totals = _prologue_tiles(L, dev, startpoint, endpoint, n, W, H)
+            host, event = _totals_to_host(totals, dev)
         v.toff = toff
         v.l_d = _aligned(l_d.detach().to(torch.float32))
         mean_ = _aligned(mean.detach().to(torch.float32))
@@ -198,15 +207,14 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
         _lib.check(L.gcp_tile_pack(_p(mean_), _p(lam_), _p(opac_), _p(v.l_d), _p(sp), _p(ep), _p(toff), n, W, H,
                                    _p(v.rec), stream), "gcp_tile_pack")
         image = torch.empty((H + 1, W + 1, 3), dtype=torch.float32, device=dev)  # every pixel is written by its lane
-        if plan is not None:
-            plan.event.synchronize()
-            (P,) = plan.host.tolist()
-        else:
-            (P,) = totals.tolist()   # the one host sync of a view, like the reference's .item() at uitility.py:348
+        v.tstart = torch.empty(int(L.gcp_tile_num_tiles(W, H)) + 1, dtype=torch.int32, device=dev)
+        # the one host sync of a view (like the reference's .item() at uitility.py:348): the pair count was copied
+        # to pinned memory right behind the prologue, so it is usually there by now
+        event.synchronize()
+        (P,) = host.tolist()
         if P >= 2 ** 31 - 64:
             raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
         v.P = P
-        v.tstart = torch.empty(int(L.gcp_tile_num_tiles(W, H)) + 1, dtype=torch.int32, device=dev)
         v.plan = torch.empty(int(L.gcp_tile_plan_ints(P, W, H)), dtype=torch.int32, device=dev)
         v.pstate = torch.empty(int(L.gcp_tile_state_floats(P, W, H)), dtype=torch.float32, device=dev)
         v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
@@ -268,12 +276,14 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
             # planned ahead (plan_view): the prologue ran on a side stream, its totals are in pinned memory
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(plan.event)
-            v.sp, v.ep, offs, totals = plan.sp, plan.ep, plan.offs, None
+            v.sp, v.ep, offs = plan.sp, plan.ep, plan.offs
+            host, event = plan.host, plan.event
             for t_ in (v.sp, v.ep, offs):
                 t_.record_stream(cur)
         else:
             # then one host sync per view for the two totals, like the reference's .item() at uitility.py:348
             v.sp, v.ep, offs, totals = _prologue(L, dev, boxsize, startpoint, endpoint, n)
+            host, event = _totals_to_host(totals, dev)
         goff, poff = offs[0], offs[1]
         v.goff = goff
         v.mean = mean.detach().to(torch.float32).contiguous()
@@ -288,11 +298,8 @@ def _render_forward(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H
         v.rec_b = torch.empty((n, 8), dtype=torch.int32, device=dev)
         _lib.check(L.gcp_splat_pack(_p(v.mean), _p(v.lam), _p(v.opac), _p(v.l_d), _p(sp), _p(ep), _p(goff), n,
                                     _p(v.rec_a), _p(v.rec_b), stream), "gcp_splat_pack")
-        if plan is not None:
-            plan.event.synchronize()
-            N, P = plan.host.tolist()
-        else:
-            N, P = totals.tolist()
+        event.synchronize()
+        N, P = host.tolist()
         v.N = N
         if N == 0:
             v.key_s = v.gid_s = v.x_s = v.incl = None
