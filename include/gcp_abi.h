@@ -114,6 +114,12 @@ int gcp_set_variant(int op, int variant);
  * cross-tile carry from the 128 elements beside the tile and touch the look-back descriptors only
  * for segments longer than that; 0 = always use the decoupled look-back. */
 #define GCP_OPT_HALO 0
+/* option 1 (GCP_OPT_CHAIN): the blocked backward kernel gives every CTA one contiguous range of tiles instead of
+ * tickets and hands each tile's outgoing carry to the next in registers, so that inside a segment spanning many
+ * tiles only the first tile of a CTA's range needs the fix-up phase.  0 = never, 1 = always, 2 (default) = when
+ * more than 1/32 of the tiles of the op that ran last on the workspace (normally the forward over the same list)
+ * lay strictly inside a segment; short lists keep the ticketed order, which is faster for them. */
+#define GCP_OPT_CHAIN 1
 int gcp_set_option(int option, int value);
 int gcp_num_variants(int op);
 const char *gcp_variant_name(int op, int variant);

@@ -17,7 +17,9 @@ using namespace gcp;
 
 thread_local int t_launches = 0;
 int g_variant[2] = {-1, -1};
-int g_option[4] = {1, 0, 0, 0};  // [0] = resolve tile carries from a 128-element halo (1) or always look back (0)
+int g_option[4] = {1, 2, 0, 0};  // [0] = resolve tile carries from the halo window (1) or always look back (0)
+                                 // [1] = blocked backward, contiguous tile range per CTA with carries chained in registers:
+                                 //       0 never, 1 always, 2 (default) when the last op on the workspace saw long segments
 
 struct DeviceInfo {
     bool init = false;
@@ -264,7 +266,8 @@ int launch_bwd_blk(const float *x, const float *y, const float *g, const int32_t
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
     kern<<<grid, threads, L::BYTES, s>>>(tmx, tmg, tmi, x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
-                                         aligned16(gin) ? 1 : 0, g_option[0]);
+                                         aligned16(gin) ? 1 : 0,
+                                         (g_option[0] & 1) | (g_option[1] == 1 ? 2 : 0) | (g_option[1] == 2 ? 4 : 0));
     ++t_launches;
     return static_cast<int>(cudaGetLastError());
 }

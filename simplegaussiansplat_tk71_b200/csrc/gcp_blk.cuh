@@ -194,6 +194,7 @@ __device__ __forceinline__ void fwd_blk_compute(float (&v)[16], const int32_t (&
         slot[0] = pack_desc(epoch, term ? ST_TERM : ST_AGG, ta_f ? 1u : 0u, val);
         slot[1] = static_cast<uint64_t>(lead);
         if (!resolved) ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
+        if (!ta_f) atomicAdd(hdr + HDR_INTERIOR, 1u);   // no head inside: the tile is the interior of a long segment
     }
     // ---- carry into the lane, applied up to its first head ----
     if (!cf) {
@@ -414,7 +415,8 @@ __device__ __forceinline__ void bwd_blk_compute(const float (&x)[16], const floa
                                                 bool resolved, float rn, uint32_t tile, uint32_t epoch,
                                                 uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc,
                                                 uint32_t *__restrict__ ulist, uint32_t *__restrict__ ulist2,
-                                                BwdBlkShared<WARPS> *sh, int warp, int lane, float (&out)[16]) {
+                                                BwdBlkShared<WARPS> *sh, int warp, int lane, float (&out)[16],
+                                                bool &term_out, float &carry_out) {
     static_assert(WARPS < 32, "one lane per warp in the cross-warp step");
     const uint32_t lanes_lt = (1u << lane) - 1u;
     const uint32_t lanes_le = lanes_lt | (1u << lane);
@@ -522,10 +524,16 @@ __device__ __forceinline__ void bwd_blk_compute(const float (&x)[16], const floa
         const int jw = 31 - __clz(lm);
         trail = static_cast<uint32_t>(jw * BLK_WSPAN + __shfl_sync(0xffffffffu, jl, jw) + 1);
     }
+    // the tile's outgoing carry (S of its first element) is final when its own incoming carry was, or when the tile
+    // holds a tail; every thread knows it (ta is broadcast), so a CTA walking contiguous tiles can hand it to the
+    // next (lower) tile without going through the descriptors
+    const bool term = resolved || (ta.a == 0.0f);
+    term_out = term;
+    carry_out = resolved ? apply(ta, rn) : ta.b;
     if (PUBLISH && warp == 0 && lane == 0) {
         uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
-        const bool term = resolved || (ta.a == 0.0f);
-        slot[0] = term ? pack_desc(epoch, ST_TERM, 0u, resolved ? apply(ta, rn) : ta.b)
+        if (ta.a != 0.0f) atomicAdd(hdr + HDR_INTERIOR, 1u);   // no tail inside: interior of a long segment
+        slot[0] = term ? pack_desc(epoch, ST_TERM, 0u, carry_out)
                        : pack_desc(epoch, ST_AGG, 0u, ta.a);
         slot[1] = static_cast<uint64_t>(trail);
         slot[3] = static_cast<uint64_t>(__float_as_uint(ta.b));
@@ -591,6 +599,19 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Chained mode (GCP_OPT_CHAIN): every CTA walks ONE CONTIGUOUS range of tiles (descending) instead of taking
+    // tickets, and hands each tile's outgoing carry to the next one in registers: inside a segment of many tiles
+    // only the first tile of a CTA's range is left for the fix-up phase, not every tile of the segment (C4: backward
+    // 0.73 -> 0.88 of the copy peak).  On short lists the ticketed order is faster (C3: 0.885 vs 0.84: the tiles in
+    // flight form one compact window), so by default (use_halo bit 2) the mode follows the op that ran last on this
+    // workspace — normally the forward over the same list: chained if more than 1/32 of its tiles lay strictly
+    // inside a segment.  The hint only picks a schedule; results do not depend on it beyond fp32 rounding.
+    const uint32_t hint = ld_relaxed_u32(hdr + HDR_HINT);   // rewritten only by the last CTA out
+    const bool chain = (use_halo & 2) != 0 || ((use_halo & 4) != 0 && hint > num_tiles / 32u);
+    use_halo &= 1;
+    const uint32_t per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t first_ticket = blockIdx.x * per_cta;
+    const uint32_t end_ticket = min(num_tiles, first_ticket + per_cta);
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -614,8 +635,13 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             tma_prefetch_desc(&tm_x);
             tma_prefetch_desc(&tm_g);
             tma_prefetch_desc(&tm_i);
-            q0 = atomicAdd(hdr + HDR_TICKET, 1u);
-            q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+            if (chain) {   // tickets past the CTA's range read as "no tile left"
+                q0 = first_ticket < end_ticket ? first_ticket : num_tiles;
+                q1 = first_ticket + 1u < end_ticket ? first_ticket + 1u : num_tiles;
+            } else {
+                q0 = atomicAdd(hdr + HDR_TICKET, 1u);
+                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+            }
         }
         bool pending = false;
         int ps = 0;
@@ -668,7 +694,8 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     mbar_arrive(&ctl->full[s]);
                 }
                 q0 = q1;
-                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+                if (chain) q1 = (q1 + 1u < end_ticket) ? q1 + 1u : num_tiles;
+                else q1 = atomicAdd(hdr + HDR_TICKET, 1u);
                 ip = -1;
                 yp = 1.0f;
                 if (base > 0) {
@@ -684,6 +711,9 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     }
 
     // ===================== consumers =====================
+    bool chain_term = false;        // the tile walked last published a final outgoing carry ...
+    float chain_carry = 0.0f;       // ... this one: S of its first element = the incoming carry of the tile below it
+    uint32_t chain_tile = 0xffffffffu;
     for (uint32_t it = 0;; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
@@ -695,8 +725,12 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int64_t wbase = base + warp * BLK_WSPAN;
         const int64_t wend = wbase + BLK_WSPAN;
         const float y_prev = ctl->yprev[s];
-        const bool resolved = ctl->resolved[s] != 0u;
-        const float rn_res = ctl->rn[s];
+        bool resolved = ctl->resolved[s] != 0u;
+        float rn_res = ctl->rn[s];
+        if (chain && !resolved && chain_term && chain_tile == tile + 1u) {
+            resolved = true;        // the halo window did not reach a tail, but the tile above was walked by this CTA
+            rn_res = chain_carry;
+        }
         const bool staged = ctl->mode[s] != 0u;
         unsigned char *xs = smem + s * L::STAGE_BYTES;
         unsigned char *gs = xs + L::ARR_BYTES;
@@ -735,7 +769,9 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         }
         float out[16];
         bwd_blk_compute<WARPS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc,
-                                     ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out);
+                                     ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out, chain_term,
+                                     chain_carry);
+        chain_tile = tile;
         if (DIRECT_ST) {
             if (staged && out_vec) store_blocked_direct(out, gin + wbase + lane * BLK_EPL);
             else stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
@@ -786,8 +822,11 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             xnext = __ldg(x + wbase + BLK_WSPAN);
         }
         const float y_prev = (base > 0) ? __ldg(y + base - 1) : 1.0f;
+        bool term_unused;
+        float carry_unused;
         bwd_blk_compute<WARPS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, true, R, static_cast<uint32_t>(t), epoch,
-                                      hdr, desc, ulist, ulist, &ctl->sh[k2 & 1u], warp, lane, out);
+                                      hdr, desc, ulist, ulist, &ctl->sh[k2 & 1u], warp, lane, out, term_unused,
+                                      carry_unused);
         if (out_vec) {
             store_blocked_via_smem(gs0, warp, lane, out, gin + wbase);
         } else {

@@ -28,6 +28,8 @@ constexpr int HDR_TICKET = 0;
 constexpr int HDR_DONE = 16;
 constexpr int HDR_EPOCH = 32;
 constexpr int HDR_ABORT = 33;
+constexpr int HDR_INTERIOR = 40;  // blocked kernels: tiles of this op lying strictly inside one segment (no boundary)
+constexpr int HDR_HINT = 41;      // that count for the op that finished last on this workspace (survives finish_op)
 constexpr int HDR_VIOL64 = 20;  // index in u64 units (byte 160)
 constexpr int HDR_UCOUNT = 48;
 constexpr int HDR_UCOUNT2 = 52;  // backward: unresolved tiles with a long trailing run (fixed by a whole CTA)
@@ -208,6 +210,8 @@ __device__ __forceinline__ void finish_op(uint32_t *hdr, uint32_t epoch) {
         hdr[HDR_UCOUNT] = 0u;
         hdr[HDR_UCOUNT2] = 0u;
         hdr[HDR_EXIT] = 0u;
+        hdr[HDR_HINT] = hdr[HDR_INTERIOR];   // a property of the segment layout, not of how the op resolved carries
+        hdr[HDR_INTERIOR] = 0u;
         hdr[HDR_EPOCH] = epoch + 1u;
         __threadfence();
     }

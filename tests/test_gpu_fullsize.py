@@ -17,6 +17,16 @@ from gpu_util import assert_close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[2, 0, 1], ids=["chain-auto", "tickets", "chain"], autouse=True)
+def chain_mode(request):
+    """GCP_OPT_CHAIN of the blocked backward: default (follows the workspace hint), tickets, contiguous ranges."""
+    from simplegaussiansplat_tk71_b200 import ops
+
+    ops.set_option(1, request.param)
+    yield request.param
+    ops.set_option(1, 2)
+
+
 def _ops():
     import grouped_cumprod as gc
     from simplegaussiansplat_tk71_b200 import ops

@@ -20,15 +20,20 @@ def _variants(op):
     return list(range(len(ops.variants(op))))
 
 
-@pytest.fixture(params=[1, 0], ids=["halo", "fixup"], autouse=True)
+@pytest.fixture(params=[(1, 2), (0, 0), (1, 1), (0, 1)], ids=["halo", "fixup", "chain", "chain-nohalo"], autouse=True)
 def carry_mode(request):
-    """Every test runs twice: tile carries resolved from the halo by K1 (default), and with the halo
-    switched off (GCP_OPT_HALO = 0) so that EVERY tile goes through the descriptor walk + fix-up of K2."""
+    """Every test runs four times: tile carries resolved from the halo by K1 (default; the blocked backward picks
+    tickets or chained ranges from the workspace hint), with the halo switched off (GCP_OPT_HALO = 0) so that EVERY
+    tile goes through the descriptor walk + fix-up, and with GCP_OPT_CHAIN forced on (every CTA of the blocked
+    backward walks one contiguous tile range and hands the carries on in registers), with and without the halo."""
     from simplegaussiansplat_tk71_b200 import ops
 
-    ops.set_option(0, request.param)
+    halo, chain = request.param
+    ops.set_option(0, halo)
+    ops.set_option(1, chain)
     yield request.param
     ops.set_option(0, 1)
+    ops.set_option(1, 2)
 
 
 FWD_VARIANTS = list(range(13))
