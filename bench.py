@@ -382,6 +382,7 @@ def main():
         peak, peak_src = _peaks()
         ab = wl.algorithmic_bytes(n, k)
         traffic = _traffic()
+        traffic = traffic if args.workload == "c3" else traffic.get(args.workload, {})   # captured per workload
         bwd_gbs = ab["bwd"] / (bwd_ms * 1e-3) / 1e9
         fwd_gbs = ab["fwd"] / (fwd_ms * 1e-3) / 1e9
         both_gbs = ab["fwd_bwd"] / ((fwd_ms + bwd_ms) * 1e-3) / 1e9
