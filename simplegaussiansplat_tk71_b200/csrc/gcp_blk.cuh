@@ -14,6 +14,7 @@
 // Carry logic, descriptors, halo resolution and the in-kernel fix-up phase are exactly those of
 // gcp_fwd.cuh / gcp_bwd.cuh (the fix-up functions are shared).
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 
 #include "gcp_bwd.cuh"
@@ -627,166 +628,182 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
 
     if (warp == WARPS) {
         // ===================== producer warp =====================
-        // Software pipelined like the forward's: halo loads issued in iteration i are consumed at
-        // the top of iteration i+1; tickets are fetched two iterations ahead.
-        const uint64_t pol = policy_evict_first();
-        uint32_t q0 = 0, q1 = 0;
-        if (lane == 0) {
-            tma_prefetch_desc(&tm_x);
-            tma_prefetch_desc(&tm_g);
-            tma_prefetch_desc(&tm_i);
-            if (chain) {   // tickets past the CTA's range read as "no tile left"
-                q0 = first_ticket < end_ticket ? first_ticket : num_tiles;
-                q1 = first_ticket + 1u < end_ticket ? first_ticket + 1u : num_tiles;
-            } else {
-                q0 = atomicAdd(hdr + HDR_TICKET, 1u);
-                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
-            }
-        }
-        bool pending = false;
-        int ps = 0;
-        HaloSuffixRegs<BLK_HQ> hr;
-        int32_t ip = -1;
-        float yp = 1.0f;
-        for (uint32_t it = 0;; ++it) {
-            if (pending) {
-                float R = 0.0f, xq = 0.0f;
-                int32_t in = -1;
-                const bool res = halo_suffix_finish(hr, lane, use_halo != 0, R, in, xq);
-                if (lane == 0) {
-                    ctl->iprev[ps] = ip;
-                    ctl->yprev[ps] = yp;
-                    ctl->inext[ps] = in;
-                    ctl->xnext[ps] = xq;
-                    ctl->resolved[ps] = res ? 1u : 0u;
-                    ctl->rn[ps] = R;
-                    mbar_arrive(&ctl->full[ps]);
+        // Instantiated per mode like the consumer loop below: with a run-time branch around the ticket fetch the
+        // atomic's result is needed where the two paths merge, i.e. at once, instead of two iterations later —
+        // 1 us of exposed latency per tile in the producer (C3 backward 0.1855 -> 0.1926 ms).
+        auto produce = [&](auto chain_tag) {
+            constexpr bool CHAIN = decltype(chain_tag)::value;
+            // Software pipelined like the forward's: halo loads issued in iteration i are consumed at
+            // the top of iteration i+1; tickets are fetched two iterations ahead.
+            const uint64_t pol = policy_evict_first();
+            uint32_t q0 = 0, q1 = 0;
+            if (lane == 0) {
+                tma_prefetch_desc(&tm_x);
+                tma_prefetch_desc(&tm_g);
+                tma_prefetch_desc(&tm_i);
+                if (CHAIN) {   // tickets past the CTA's range read as "no tile left"
+                    q0 = first_ticket < end_ticket ? first_ticket : num_tiles;
+                    q1 = first_ticket + 1u < end_ticket ? first_ticket + 1u : num_tiles;
+                } else {
+                    q0 = atomicAdd(hdr + HDR_TICKET, 1u);
+                    q1 = atomicAdd(hdr + HDR_TICKET, 1u);
                 }
-                pending = false;
             }
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-            const uint32_t t = __shfl_sync(0xffffffffu, q0, 0);
-            if (t >= num_tiles) {
+            bool pending = false;
+            int ps = 0;
+            HaloSuffixRegs<BLK_HQ> hr;
+            int32_t ip = -1;
+            float yp = 1.0f;
+            for (uint32_t it = 0;; ++it) {
+                if (pending) {
+                    float R = 0.0f, xq = 0.0f;
+                    int32_t in = -1;
+                    const bool res = halo_suffix_finish(hr, lane, use_halo != 0, R, in, xq);
+                    if (lane == 0) {
+                        ctl->iprev[ps] = ip;
+                        ctl->yprev[ps] = yp;
+                        ctl->inext[ps] = in;
+                        ctl->xnext[ps] = xq;
+                        ctl->resolved[ps] = res ? 1u : 0u;
+                        ctl->rn[ps] = R;
+                        mbar_arrive(&ctl->full[ps]);
+                    }
+                    pending = false;
+                }
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
+                const uint32_t t = __shfl_sync(0xffffffffu, q0, 0);
+                if (t >= num_tiles) {
+                    if (lane == 0) {
+                        ctl->tile[s] = t;
+                        mbar_arrive(&ctl->full[s]);
+                        mbar_arrive(&ctl->full[s]);
+                    }
+                    break;
+                }
+                const uint32_t tile = num_tiles - 1u - t;
+                const int64_t base = static_cast<int64_t>(tile) * TILE;
+                const int64_t end = base + TILE;
                 if (lane == 0) {
                     ctl->tile[s] = t;
-                    mbar_arrive(&ctl->full[s]);
-                    mbar_arrive(&ctl->full[s]);
+                    if (end <= n) {
+                        unsigned char *st = smem + s * L::STAGE_BYTES;
+                        const int row0 = static_cast<int>(base >> 5);
+                        mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
+                        tma_load_2d(st, &tm_x, 0, row0, &ctl->full[s], pol);
+                        tma_load_2d(st + L::ARR_BYTES, &tm_g, 0, row0, &ctl->full[s], pol);
+                        tma_load_2d(st + 2 * L::ARR_BYTES, &tm_i, 0, row0, &ctl->full[s], pol);
+                        ctl->mode[s] = 1u;
+                    } else {
+                        ctl->mode[s] = 0u;
+                        mbar_arrive(&ctl->full[s]);
+                    }
+                    q0 = q1;
+                    if (CHAIN) q1 = (q1 + 1u < end_ticket) ? q1 + 1u : num_tiles;
+                    else q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+                    ip = -1;
+                    yp = 1.0f;
+                    if (base > 0) {
+                        ip = __ldg(inv + base - 1);
+                        yp = __ldg(y + base - 1);
+                    }
                 }
-                break;
+                halo_suffix_issue(x, g, inv, end, n, lane, use_halo != 0, hr);
+                pending = true;
+                ps = s;
             }
-            const uint32_t tile = num_tiles - 1u - t;
-            const int64_t base = static_cast<int64_t>(tile) * TILE;
-            const int64_t end = base + TILE;
-            if (lane == 0) {
-                ctl->tile[s] = t;
-                if (end <= n) {
-                    unsigned char *st = smem + s * L::STAGE_BYTES;
-                    const int row0 = static_cast<int>(base >> 5);
-                    mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
-                    tma_load_2d(st, &tm_x, 0, row0, &ctl->full[s], pol);
-                    tma_load_2d(st + L::ARR_BYTES, &tm_g, 0, row0, &ctl->full[s], pol);
-                    tma_load_2d(st + 2 * L::ARR_BYTES, &tm_i, 0, row0, &ctl->full[s], pol);
-                    ctl->mode[s] = 1u;
-                } else {
-                    ctl->mode[s] = 0u;
-                    mbar_arrive(&ctl->full[s]);
-                }
-                q0 = q1;
-                if (chain) q1 = (q1 + 1u < end_ticket) ? q1 + 1u : num_tiles;
-                else q1 = atomicAdd(hdr + HDR_TICKET, 1u);
-                ip = -1;
-                yp = 1.0f;
-                if (base > 0) {
-                    ip = __ldg(inv + base - 1);
-                    yp = __ldg(y + base - 1);
-                }
-            }
-            halo_suffix_issue(x, g, inv, end, n, lane, use_halo != 0, hr);
-            pending = true;
-            ps = s;
-        }
+        };
+        if (chain) produce(std::true_type{});
+        else produce(std::false_type{});
         return;
     }
 
     // ===================== consumers =====================
-    bool chain_term = false;        // the tile walked last published a final outgoing carry ...
-    float chain_carry = 0.0f;       // ... this one: S of its first element = the incoming carry of the tile below it
-    uint32_t chain_tile = 0xffffffffu;
-    for (uint32_t it = 0;; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(&ctl->full[s], ph, hdr);
-        const uint32_t ticket = ctl->tile[s];
-        if (ticket >= num_tiles) break;
-        const uint32_t tile = num_tiles - 1u - ticket;
-        const int64_t base = static_cast<int64_t>(tile) * TILE;
-        const int64_t wbase = base + warp * BLK_WSPAN;
-        const int64_t wend = wbase + BLK_WSPAN;
-        const float y_prev = ctl->yprev[s];
-        bool resolved = ctl->resolved[s] != 0u;
-        float rn_res = ctl->rn[s];
-        if (chain && !resolved && chain_term && chain_tile == tile + 1u) {
-            resolved = true;        // the halo window did not reach a tail, but the tile above was walked by this CTA
-            rn_res = chain_carry;
-        }
-        const bool staged = ctl->mode[s] != 0u;
-        unsigned char *xs = smem + s * L::STAGE_BYTES;
-        unsigned char *gs = xs + L::ARR_BYTES;
-        const unsigned char *is = xs + 2 * L::ARR_BYTES;
-        float xv[16], gv[16];
-        int32_t iv[16];
-        int32_t iprev = -1, inext = -1;
-        float xnext = 0.0f;
-        if (staged) {
-            lds_blocked<float>(xs, warp, lane, xv);
-            lds_blocked<float>(gs, warp, lane, gv);
-            lds_blocked<int32_t>(is, warp, lane, iv);
-            if (lane == 0) {
-                iprev = (warp == 0) ? ctl->iprev[s] : lds_one<int32_t>(is, warp * BLK_WSPAN - 1);
-                if (warp == WARPS - 1) {
-                    inext = ctl->inext[s];
-                    xnext = ctl->xnext[s];
-                } else {
-                    inext = lds_one<int32_t>(is, (warp + 1) * BLK_WSPAN);
-                    xnext = lds_one<float>(xs, (warp + 1) * BLK_WSPAN);
+    // Two instantiations of the same loop: the ticketed one carries no chain state at all (it is the kernel of the
+    // short-list workloads, where a few instructions per tile are measurable), the chained one keeps the previous
+    // tile's outgoing carry in registers.
+    auto consume = [&](auto chain_tag) {
+        constexpr bool CHAIN = decltype(chain_tag)::value;
+        bool chain_term = false;        // the tile walked last published a final outgoing carry ...
+        float chain_carry = 0.0f;       // ... this one: S of its first element = the incoming carry of the tile below it
+        uint32_t chain_tile = 0xffffffffu;
+        for (uint32_t it = 0;; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(&ctl->full[s], ph, hdr);
+            const uint32_t ticket = ctl->tile[s];
+            if (ticket >= num_tiles) break;
+            const uint32_t tile = num_tiles - 1u - ticket;
+            const int64_t base = static_cast<int64_t>(tile) * TILE;
+            const int64_t wbase = base + warp * BLK_WSPAN;
+            const int64_t wend = wbase + BLK_WSPAN;
+            const float y_prev = ctl->yprev[s];
+            bool resolved = ctl->resolved[s] != 0u;
+            float rn_res = ctl->rn[s];
+            if (CHAIN && !resolved && chain_term && chain_tile == tile + 1u) {
+                resolved = true;        // the halo window did not reach a tail, but the tile above was walked by this CTA
+                rn_res = chain_carry;
+            }
+            const bool staged = ctl->mode[s] != 0u;
+            unsigned char *xs = smem + s * L::STAGE_BYTES;
+            unsigned char *gs = xs + L::ARR_BYTES;
+            const unsigned char *is = xs + 2 * L::ARR_BYTES;
+            float xv[16], gv[16];
+            int32_t iv[16];
+            int32_t iprev = -1, inext = -1;
+            float xnext = 0.0f;
+            if (staged) {
+                lds_blocked<float>(xs, warp, lane, xv);
+                lds_blocked<float>(gs, warp, lane, gv);
+                lds_blocked<int32_t>(is, warp, lane, iv);
+                if (lane == 0) {
+                    iprev = (warp == 0) ? ctl->iprev[s] : lds_one<int32_t>(is, warp * BLK_WSPAN - 1);
+                    if (warp == WARPS - 1) {
+                        inext = ctl->inext[s];
+                        xnext = ctl->xnext[s];
+                    } else {
+                        inext = lds_one<int32_t>(is, (warp + 1) * BLK_WSPAN);
+                        xnext = lds_one<float>(xs, (warp + 1) * BLK_WSPAN);
+                    }
+                }
+            } else {
+                ldg_blocked<float>(x, wbase + lane * BLK_EPL, n, 1.0f, xv);
+                ldg_blocked<float>(g, wbase + lane * BLK_EPL, n, 0.0f, gv);
+                ldg_blocked<int32_t>(inv, wbase + lane * BLK_EPL, n, -1, iv);
+                if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
+                if (lane == 0 && wend < n) {
+                    inext = __ldg(inv + wend);
+                    xnext = __ldg(x + wend);
                 }
             }
-        } else {
-            ldg_blocked<float>(x, wbase + lane * BLK_EPL, n, 1.0f, xv);
-            ldg_blocked<float>(g, wbase + lane * BLK_EPL, n, 0.0f, gv);
-            ldg_blocked<int32_t>(inv, wbase + lane * BLK_EPL, n, -1, iv);
-            if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
-            if (lane == 0 && wend < n) {
-                inext = __ldg(inv + wend);
-                xnext = __ldg(x + wend);
+            if (DIRECT_ST) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[s]);
             }
-        }
-        if (DIRECT_ST) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[s]);
-        }
-        float out[16];
-        bwd_blk_compute<WARPS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc,
-                                     ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out, chain_term,
-                                     chain_carry);
-        chain_tile = tile;
-        if (DIRECT_ST) {
-            if (staged && out_vec) store_blocked_direct(out, gin + wbase + lane * BLK_EPL);
-            else stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
-        } else {
-            if (staged && out_vec) {
-                // the g array of the stage is only ever read by the warp that owns the span: reuse it
-                // (x is read across warp boundaries for x_next, inv for the head/tail halos)
-                store_blocked_via_smem(gs, warp, lane, out, gin + wbase);
+            float out[16];
+            bwd_blk_compute<WARPS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc,
+                                         ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out, chain_term,
+                                         chain_carry);
+            chain_tile = tile;
+            if (DIRECT_ST) {
+                if (staged && out_vec) store_blocked_direct(out, gin + wbase + lane * BLK_EPL);
+                else stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
             } else {
-                stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+                if (staged && out_vec) {
+                    // the g array of the stage is only ever read by the warp that owns the span: reuse it
+                    // (x is read across warp boundaries for x_next, inv for the head/tail halos)
+                    store_blocked_via_smem(gs, warp, lane, out, gin + wbase);
+                } else {
+                    stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[s]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
-    }
+    };
+    if (chain) consume(std::true_type{});
+    else consume(std::false_type{});
 
     // ===================== fix-up phase (same launch) =====================
     grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);

@@ -31,6 +31,8 @@ def _workspace(device: torch.device, n: int):
     need = int(L.gcp_workspace_bytes(n))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
+        if not _workspaces:
+            _options_from_env()
         size = max(need, 1 << 20)
         if ws is not None:
             size = max(size, 2 * ws.numel())
@@ -141,8 +143,18 @@ def set_variant(op: str, variant: int) -> None:
 
 
 def set_option(option: int, value: int) -> None:
-    """Tuning hook: option 0 = halo resolution of tile carries (1 on / 0 always look back)."""
+    """Tuning hook: option 0 = halo resolution of tile carries (1 on / 0 always look back); option 1 = chained
+    tile ranges in the blocked backward (0 never / 1 always / 2 from the workspace hint, the default)."""
     _lib.check(_lib.lib().gcp_set_option(int(option), int(value)), "gcp_set_option")
+
+
+def _options_from_env() -> None:
+    """Experiments only: GCP_OPT_HALO / GCP_OPT_CHAIN in the environment override the defaults at first use."""
+    import os
+
+    for name, idx in (("GCP_OPT_HALO", 0), ("GCP_OPT_CHAIN", 1)):
+        if os.environ.get(name, "") != "":
+            set_option(idx, int(os.environ[name]))
 
 
 def variants(op: str) -> list:
