@@ -607,6 +607,9 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     // flight form one compact window), so by default (use_halo bit 2) the mode follows the op that ran last on this
     // workspace — normally the forward over the same list: chained if more than 1/32 of its tiles lay strictly
     // inside a segment.  The hint only picks a schedule; results do not depend on it beyond fp32 rounding.
+    // (Tickets for RUNS of 8 contiguous tiles do not work: a run that starts inside a long segment has no resolved
+    // carry to hand on, so every tile of the segment stays unresolved as with single-tile tickets — measured 0.73.
+    // The range of a CTA has to be long against the segments, which is what one range per CTA gives.)
     const uint32_t hint = ld_relaxed_u32(hdr + HDR_HINT);   // rewritten only by the last CTA out
     const bool chain = (use_halo & 2) != 0 || ((use_halo & 4) != 0 && hint > num_tiles / 32u);
     use_halo &= 1;
