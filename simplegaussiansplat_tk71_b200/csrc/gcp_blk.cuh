@@ -129,7 +129,7 @@ __device__ __forceinline__ void fwd_blk_compute(float (&v)[16], const int32_t (&
                                                 bool resolved, float tp, uint32_t tile, uint32_t epoch,
                                                 uint32_t *__restrict__ hdr, uint64_t *__restrict__ desc,
                                                 uint32_t *__restrict__ ulist, FwdBlkShared<WARPS> *sh, int warp,
-                                                int lane) {
+                                                int lane, bool &term_out, float &carry_out) {
     using O = ScanOp<OP>;
     static_assert(WARPS < 32, "one lane per warp in the cross-warp step");
     const uint32_t lanes_lt = (1u << lane) - 1u;
@@ -183,6 +183,12 @@ __device__ __forceinline__ void fwd_blk_compute(float (&v)[16], const int32_t (&
     const bool wp_f = (fm & ((1u << warp) - 1u)) != 0u;
     const float ta_v = __shfl_sync(0xffffffffu, jv, WARPS - 1);
     const bool ta_f = fm != 0u;
+    // the tile's outgoing carry (inclusive value of its last element) is final when the tile holds a head or its own
+    // incoming carry was final; every thread knows it, so a CTA walking contiguous tiles hands it to the next tile
+    const bool term = ta_f || resolved;
+    const float val = ta_f ? ta_v : (resolved ? O::f(tp, ta_v) : ta_v);
+    term_out = term;
+    carry_out = val;
     if (warp == 0 && lane == 0) {
         uint32_t lead = WARPS * BLK_WSPAN;
         if (ta_f) {
@@ -190,8 +196,6 @@ __device__ __forceinline__ void fwd_blk_compute(float (&v)[16], const int32_t (&
             lead = static_cast<uint32_t>(jw * BLK_WSPAN) + sh->fh[jw];
         }
         uint64_t *slot = desc + static_cast<int64_t>(tile) * 4;
-        const bool term = ta_f || resolved;
-        const float val = ta_f ? ta_v : (resolved ? O::f(tp, ta_v) : ta_v);
         slot[0] = pack_desc(epoch, term ? ST_TERM : ST_AGG, ta_f ? 1u : 0u, val);
         slot[1] = static_cast<uint64_t>(lead);
         if (!resolved) ulist[atomicAdd(hdr + HDR_UCOUNT, 1u)] = tile;
@@ -240,6 +244,17 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Chained mode (GCP_OPT_CHAIN_FWD, see k_bwd_blk): one contiguous ASCENDING range of tiles per CTA, each tile's
+    // outgoing carry handed to the next in registers, the halo window read for the first tile of the range only.
+    // Off by default: unlike the backward, the forward is 5-7 % slower with ranges than with tickets (C3 0.86 vs
+    // 0.93, C4 0.90 vs 0.94 of the copy peak) — its fix-up is a cheap multiply of a leading run, so there is
+    // little to win, and the compact window of the ticketed order is lost.
+    const uint32_t hint = ld_relaxed_u32(hdr + HDR_HINT);
+    const bool chain = (use_halo & 2) != 0 || ((use_halo & 4) != 0 && hint > num_tiles / 32u);
+    use_halo &= 1;
+    const uint32_t per_cta = num_tiles / gridDim.x, rem_cta = num_tiles % gridDim.x;
+    const uint32_t first_ticket = blockIdx.x * per_cta + min(blockIdx.x, rem_cta);
+    const uint32_t end_ticket = first_ticket + per_cta + (blockIdx.x < rem_cta ? 1u : 0u);
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -258,14 +273,23 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         // Software pipelined: the halo loads of tile i are issued right after its TMA copies and
         // consumed at the top of iteration i+1, so their latency overlaps the next tile's issue;
         // tickets are fetched two iterations ahead (lane 0 keeps q0 = ready, q1 = in flight).
+        // One instantiation per mode (a run-time branch around the ticket fetch would expose the atomic's latency).
+        auto produce = [&](auto chain_tag) {
+        constexpr bool CHAIN = decltype(chain_tag)::value;
         const uint64_t pol = policy_evict_first();
         uint32_t q0 = 0, q1 = 0;
         if (lane == 0) {
             tma_prefetch_desc(&tm_x);
             tma_prefetch_desc(&tm_k);
-            q0 = atomicAdd(hdr + HDR_TICKET, 1u);
-            q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+            if (CHAIN) {   // tickets past the CTA's range read as "no tile left"
+                q0 = first_ticket < end_ticket ? first_ticket : num_tiles;
+                q1 = first_ticket + 1u < end_ticket ? first_ticket + 1u : num_tiles;
+            } else {
+                q0 = atomicAdd(hdr + HDR_TICKET, 1u);
+                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+            }
         }
+        bool pend_window = false;
         bool pending = false;
         int ps = 0;
         int64_t pbase = 0;
@@ -276,7 +300,7 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                 float P = O::id();
                 int32_t kprev = 0;
                 bool res;
-                if (use_halo) {
+                if (pend_window) {
                     res = halo_prefix_finish<OP, BLK_HQ>(hp, lane, P, kprev);
                 } else {
                     res = false;
@@ -316,7 +340,8 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     mbar_arrive(&ctl->full[s]);
                 }
                 q0 = q1;
-                q1 = atomicAdd(hdr + HDR_TICKET, 1u);
+                if (CHAIN) q1 = (q1 + 1u < end_ticket) ? q1 + 1u : num_tiles;
+                else q1 = atomicAdd(hdr + HDR_TICKET, 1u);
             }
             if (t == 0u) {
                 if (lane == 0) {
@@ -326,22 +351,33 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     mbar_arrive(&ctl->full[s]);
                 }
             } else {
-                // issue the halo loads now, use them next iteration
-                if (use_halo) {
+                // issue the halo loads now, use them next iteration (chained mode: only the first tile of the range
+                // can use the window, the others take their carry from the tile before them)
+                const bool window = use_halo != 0 && (!CHAIN || t == first_ticket);
+                if (window) {
                     halo_prefix_issue<BLK_HQ>(x, key, base, lane, hp);
                 } else {
                     hp.kfirst = __ldg(key + base - 1);
                 }
+                pend_window = window;
                 pending = true;
                 ps = s;
                 pbase = base;
             }
         }
         (void)pbase;
+        };
+        if (chain) produce(std::true_type{});
+        else produce(std::false_type{});
         return;
     }
 
     // ===================== consumers =====================
+    auto consume = [&](auto chain_tag) {
+    constexpr bool CHAIN = decltype(chain_tag)::value;
+    bool chain_term = false;        // the tile walked last published a final outgoing carry ...
+    float chain_carry = O::id();    // ... this one: the inclusive value of its last element
+    uint32_t chain_tile = 0xffffffffu;
     for (uint32_t it = 0;; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
@@ -350,8 +386,12 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         if (tile >= num_tiles) break;
         const int64_t base = static_cast<int64_t>(tile) * TILE;
         const int64_t wbase = base + warp * BLK_WSPAN;
-        const bool resolved = ctl->resolved[s] != 0u;
-        const float tp_res = ctl->tp[s];
+        bool resolved = ctl->resolved[s] != 0u;
+        float tp_res = ctl->tp[s];
+        if (CHAIN && !resolved && chain_term && chain_tile + 1u == tile) {
+            resolved = true;
+            tp_res = chain_carry;
+        }
         const bool staged = ctl->mode[s] != 0u;
         unsigned char *xs = smem + s * L::STAGE_BYTES;
         const unsigned char *ks = xs + L::ARR_BYTES;
@@ -372,7 +412,8 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
         fwd_blk_compute<OP, WARPS>(v, k, kprev, wbase == 0, resolved, tp_res, tile, epoch, hdr, desc, ulist,
-                                   &ctl->sh[it & 1u], warp, lane);
+                                   &ctl->sh[it & 1u], warp, lane, chain_term, chain_carry);
+        chain_tile = tile;
         if (DIRECT_ST) {
             if (staged && y_vec) store_blocked_direct(v, y + wbase + lane * BLK_EPL);
             else stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v);
@@ -387,6 +428,9 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
     }
+    };
+    if (chain) consume(std::true_type{});
+    else consume(std::false_type{});
 
     // ===================== fix-up phase (same launch) =====================
     grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);
@@ -600,22 +644,27 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Chained mode (GCP_OPT_CHAIN): every CTA walks ONE CONTIGUOUS range of tiles (descending) instead of taking
-    // tickets, and hands each tile's outgoing carry to the next one in registers: inside a segment of many tiles
-    // only the first tile of a CTA's range is left for the fix-up phase, not every tile of the segment (C4: backward
-    // 0.73 -> 0.88 of the copy peak).  On short lists the ticketed order is faster (C3: 0.885 vs 0.84: the tiles in
-    // flight form one compact window), so by default (use_halo bit 2) the mode follows the op that ran last on this
-    // workspace — normally the forward over the same list: chained if more than 1/32 of its tiles lay strictly
-    // inside a segment.  The hint only picks a schedule; results do not depend on it beyond fp32 rounding.
+    // Chained mode (GCP_OPT_CHAIN, the default): every CTA walks ONE CONTIGUOUS range of tiles (descending) instead
+    // of taking tickets, and hands each tile's outgoing carry to the next one in registers.
+    //  * Inside a segment of many tiles only the first tile of a CTA's range is left for the fix-up phase, not
+    //    every tile of the segment (C4: backward 0.73 -> 0.95 of the copy peak).
+    //  * Only the first tile of a range needs the 512-element halo window; the others load two boundary values.
+    //    The window is 12 % of a tile's reads — L2 hits with tickets (the neighbour tile is in flight in another
+    //    CTA), DRAM reads with ranges — and dropping it is what makes ranges faster than tickets on short lists
+    //    too (C3: 0.932 vs 0.925); with the windows kept, ranges were 5 % slower there.
+    // use_halo bit 1 = chained, bit 2 = chained only when the op that ran last on this workspace (normally the
+    // forward over the same list) had more than 1/32 of its tiles strictly inside a segment, 0 = tickets.  The mode
+    // only picks a schedule; results do not depend on it beyond fp32 rounding.
     // (Tickets for RUNS of 8 contiguous tiles do not work: a run that starts inside a long segment has no resolved
     // carry to hand on, so every tile of the segment stays unresolved as with single-tile tickets — measured 0.73.
     // The range of a CTA has to be long against the segments, which is what one range per CTA gives.)
     const uint32_t hint = ld_relaxed_u32(hdr + HDR_HINT);   // rewritten only by the last CTA out
     const bool chain = (use_halo & 2) != 0 || ((use_halo & 4) != 0 && hint > num_tiles / 32u);
     use_halo &= 1;
-    const uint32_t per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t first_ticket = blockIdx.x * per_cta;
-    const uint32_t end_ticket = min(num_tiles, first_ticket + per_cta);
+    // balanced contiguous ranges: the first (num_tiles % grid) CTAs take one tile more
+    const uint32_t per_cta = num_tiles / gridDim.x, rem_cta = num_tiles % gridDim.x;
+    const uint32_t first_ticket = blockIdx.x * per_cta + min(blockIdx.x, rem_cta);
+    const uint32_t end_ticket = first_ticket + per_cta + (blockIdx.x < rem_cta ? 1u : 0u);
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -652,7 +701,7 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     q1 = atomicAdd(hdr + HDR_TICKET, 1u);
                 }
             }
-            bool pending = false;
+            bool pending = false, pend_window = false;
             int ps = 0;
             HaloSuffixRegs<BLK_HQ> hr;
             int32_t ip = -1;
@@ -661,7 +710,7 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                 if (pending) {
                     float R = 0.0f, xq = 0.0f;
                     int32_t in = -1;
-                    const bool res = halo_suffix_finish(hr, lane, use_halo != 0, R, in, xq);
+                    const bool res = halo_suffix_finish(hr, lane, pend_window, R, in, xq);
                     if (lane == 0) {
                         ctl->iprev[ps] = ip;
                         ctl->yprev[ps] = yp;
@@ -712,7 +761,12 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                         yp = __ldg(y + base - 1);
                     }
                 }
-                halo_suffix_issue(x, g, inv, end, n, lane, use_halo != 0, hr);
+                // chained mode: only the first tile of the CTA's range can make use of the halo window — every other
+                // tile takes its carry from the tile above it (or, inside a segment that began above the range, has
+                // no tail within the window anyway); the others load just the two boundary values
+                const bool window = use_halo != 0 && (!CHAIN || t == first_ticket);
+                halo_suffix_issue(x, g, inv, end, n, lane, window, hr);
+                pend_window = window;
                 pending = true;
                 ps = s;
             }

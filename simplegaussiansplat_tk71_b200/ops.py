@@ -144,7 +144,7 @@ def set_variant(op: str, variant: int) -> None:
 
 def set_option(option: int, value: int) -> None:
     """Tuning hook: option 0 = halo resolution of tile carries (1 on / 0 always look back); option 1 = chained
-    tile ranges in the blocked backward (0 never / 1 always / 2 from the workspace hint, the default)."""
+    tile ranges in the blocked backward (0 tickets / 1 always, the default / 2 from the workspace hint)."""
     _lib.check(_lib.lib().gcp_set_option(int(option), int(value)), "gcp_set_option")
 
 
@@ -152,7 +152,7 @@ def _options_from_env() -> None:
     """Experiments only: GCP_OPT_HALO / GCP_OPT_CHAIN in the environment override the defaults at first use."""
     import os
 
-    for name, idx in (("GCP_OPT_HALO", 0), ("GCP_OPT_CHAIN", 1)):
+    for name, idx in (("GCP_OPT_HALO", 0), ("GCP_OPT_CHAIN", 1), ("GCP_OPT_CHAIN_FWD", 2)):
         if os.environ.get(name, "") != "":
             set_option(idx, int(os.environ[name]))
 

@@ -17,14 +17,14 @@ from gpu_util import assert_close
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[2, 0, 1], ids=["chain-auto", "tickets", "chain"], autouse=True)
+@pytest.fixture(params=[1, 0, 2], ids=["chain", "tickets", "chain-by-hint"], autouse=True)
 def chain_mode(request):
     """GCP_OPT_CHAIN of the blocked backward: default (follows the workspace hint), tickets, contiguous ranges."""
     from simplegaussiansplat_tk71_b200 import ops
 
     ops.set_option(1, request.param)
     yield request.param
-    ops.set_option(1, 2)
+    ops.set_option(1, 1)
 
 
 def _ops():

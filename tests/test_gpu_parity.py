@@ -20,20 +20,25 @@ def _variants(op):
     return list(range(len(ops.variants(op))))
 
 
-@pytest.fixture(params=[(1, 2), (0, 0), (1, 1), (0, 1)], ids=["halo", "fixup", "chain", "chain-nohalo"], autouse=True)
+@pytest.fixture(params=[(1, 1, 0), (0, 0, 0), (1, 0, 0), (1, 2, 2), (0, 1, 1), (1, 1, 1)],
+                ids=["default", "tickets-fixup", "tickets-halo", "chain-by-hint", "chain-nohalo", "chain-fwd-too"],
+                autouse=True)
 def carry_mode(request):
-    """Every test runs four times: tile carries resolved from the halo by K1 (default; the blocked backward picks
-    tickets or chained ranges from the workspace hint), with the halo switched off (GCP_OPT_HALO = 0) so that EVERY
-    tile goes through the descriptor walk + fix-up, and with GCP_OPT_CHAIN forced on (every CTA of the blocked
-    backward walks one contiguous tile range and hands the carries on in registers), with and without the halo."""
+    """Every test runs in five carry modes (GCP_OPT_HALO, GCP_OPT_CHAIN): the default (every CTA of the blocked
+    backward walks one contiguous tile range and hands the carries on in registers; halo window on the first tile
+    of a range); tickets with the halo switched off, so that EVERY tile goes through the descriptor walk + fix-up;
+    tickets with the halo; the mode picked from the workspace hint; chained ranges without any halo; chained
+    ranges in the forward kernel as well (GCP_OPT_CHAIN_FWD, off by default)."""
     from simplegaussiansplat_tk71_b200 import ops
 
-    halo, chain = request.param
+    halo, chain, chain_fwd = request.param
     ops.set_option(0, halo)
     ops.set_option(1, chain)
+    ops.set_option(2, chain_fwd)
     yield request.param
     ops.set_option(0, 1)
-    ops.set_option(1, 2)
+    ops.set_option(1, 1)
+    ops.set_option(2, 0)
 
 
 FWD_VARIANTS = list(range(13))

@@ -40,11 +40,21 @@ for name, mk in cases:
         ms = timeit(fb) - fwd_ms      # alternating, as in a training step (the hint comes from the forward)
         st = ops.workspace_status()
         ab = wl.algorithmic_bytes(e.n, e.k)["bwd"]
-        print(f"{name} chain={chain}: bwd {ms:.4f} ms  {ab / ms / 1e6:7.1f} GB/s  frac {ab / ms / 1e6 / 6553.9:.3f}  status {st}", flush=True)
+        abf = wl.algorithmic_bytes(e.n, e.k)["fwd"]
+        print(f"{name} chain={chain}: bwd {ms:.4f} ms  {ab / ms / 1e6:7.1f} GB/s  frac {ab / ms / 1e6 / 6553.9:.3f} | "
+              f"fwd {fwd_ms:.4f} ms  frac {abf / fwd_ms / 1e6 / 6553.9:.3f}  status {st}", flush=True)
         outs.append(gin)
+    ys = []
+    for chain in (0, 1):
+        ops.set_option(2, chain)
+        yy = torch.full_like(e.x, float("nan"))
+        gc.grouped_cumprod_forward(e.x, e.key, yy)
+        ys.append(yy)
+    print(f"   forward: max |diff| {float((ys[0] - ys[1]).abs().max()):.3e}, finite {bool(torch.isfinite(ys[1]).all())}")
     d = (outs[0] - outs[1]).abs()
     ref = outs[0].abs()
     print(f"   max |diff| {float(d.max()):.3e}, max rel (|ref|>1e-6) {float((d / ref.clamp_min(1e-6)).max()):.3e}, "
           f"finite {bool(torch.isfinite(outs[1]).all())}", flush=True)
     del e, y, outs
-ops.set_option(1, 2)
+ops.set_option(1, 1)
+ops.set_option(2, 0)

@@ -17,7 +17,7 @@ ap.add_argument("--halo", type=int, default=1)
 ap.add_argument("--workload", default="c3")
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--reps", type=int, default=4)
-ap.add_argument("--chain", type=int, default=2, help="GCP_OPT_CHAIN of the blocked backward: 0 tickets, 1 chained, 2 auto")
+ap.add_argument("--chain", type=int, default=1, help="GCP_OPT_CHAIN of the blocked backward: 0 tickets, 1 chained, 2 auto")
 a = ap.parse_args()
 e = wl.c4("cuda", scale=a.scale) if a.workload == "c4" else wl.c3("cuda", scale=a.scale)
 y = torch.empty_like(e.x)
