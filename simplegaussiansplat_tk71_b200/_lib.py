@@ -48,6 +48,9 @@ def lib() -> ctypes.CDLL:
             raise ImportError(
                 f"libgcp_b200.so is not built ({e}); run `python -c 'import __graft_entry__ as g; g.build()'`"
             ) from e
+    # the library's only OpenMP region is the host-side key packing (gcp_host.cu): its idle worker threads should
+    # sleep, not spin, between the chunks of a step (they share the cores with the other ranks of the node)
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     L = ctypes.CDLL(path)
     vp, i64, sz, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_int
     L.gcp_abi_version.restype = ci

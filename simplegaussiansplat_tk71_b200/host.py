@@ -80,7 +80,10 @@ class HostStreamer:
         self.hbits = [torch.empty(words, dtype=torch.int32).pin_memory() for _ in range(depth)]
         self.lib = _lib.lib()
         self.scan_tmp = torch.empty(int(self.lib.gcp_ids_from_bits_bytes(cap)), dtype=torch.uint8, device=self.device)
-        self.threads = max(1, min(16, os.cpu_count() or 1))
+        # host threads of the key packing: the cores divided among the ranks of this node (torchrun sets
+        # LOCAL_WORLD_SIZE) — with every rank taking all of them the packing threads of the ranks fight each other
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+        self.threads = max(1, min(16, (os.cpu_count() or 1) // ranks))
         self.s_up = torch.cuda.Stream(self.device)
         self.s_run = torch.cuda.Stream(self.device)
         self.s_down = torch.cuda.Stream(self.device)
