@@ -448,8 +448,9 @@ __device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
     return s;
 }
 
-// partial[q] = {sum g dalpha, sum d, sum coef X0, sum coef X1, sum hc d0 d0, sum hc d0 d1, sum hc d1 d1, 0}
-// over the pixels of pair q (coef = alpha dalpha, hc = -coef/2), see gs_model.py:733-766
+// partial[q] = {sum g dalpha, sum d, sum coef X0', sum coef X1', sum coef d0 d0, sum coef d0 d1, sum coef d1 d1, 0}
+// over the pixels of pair q (coef = alpha dalpha; X' = EXP2_SCALE X), see gs_model.py:733-766; the constant factors
+// -1/2 (d_Lambda) and EXP2_UNSCALE (d_mean) are applied to the per-Gaussian sums by k_tile_reduce
 __global__ void __launch_bounds__(TILE_WARPS * 32, 4)
 k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
                 const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
@@ -459,6 +460,7 @@ k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     PairSlot *sl = slots[wib];
     const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float *const pcomp = partial + comp;   // the component this lane's group ends up holding after reduce8
     const int npieces = __ldg(pstart + ntiles);
     Piece w;
     while (next_piece(ticket, tstart, pstart, ptile, npieces, piece, lane, w)) {
@@ -529,13 +531,13 @@ k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ 
                     const float dalpha = alive ? T * pgl - T * U : 0.0f;
                     const float d = alive ? T * alpha * pgl : 0.0f;
                     U = cov ? fmaf(e.x, U, alive ? alpha * pgl : 0.0f) : U;   // U_{i-1} = w_i + x_i U_i
+                    // per-pixel terms of gs_model.py:733-766 WITHOUT their constant factors (-1/2 for d_Lambda,
+                    // EXP2_UNSCALE for d_mean because X0, X1 carry EXP2_SCALE): k_tile_reduce applies them to the sums
                     const float coef = B.z * e.gk * dalpha;
-                    const float hc = -0.5f * coef;
-                    const float cm = EXP2_UNSCALE * coef;   // e.X0, e.X1 carry the factor EXP2_SCALE
-                    float v[8] = {e.gk * dalpha, d, cm * e.X0, cm * e.X1, hc * e.d0 * e.d0, hc * e.d0 * e.d1,
-                                  hc * e.d1 * e.d1, 0.0f};
+                    const float c0 = coef * e.d0, c1 = coef * e.d1;
+                    float v[8] = {e.gk * dalpha, d, coef * e.X0, coef * e.X1, c0 * e.d0, c0 * e.d1, c1 * e.d1, 0.0f};
                     const float s = reduce8(v, lane);
-                    if ((lane & 3) == 0) partial[static_cast<int64_t>(q) * 8 + comp] = s;
+                    if ((lane & 3) == 0) pcomp[static_cast<int64_t>(q) * 8] = s;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tc[j] = tn[j];
@@ -551,6 +553,9 @@ k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ 
 __device__ __forceinline__ void store_component(int c, float s, int64_t g, const float *__restrict__ l_d,
                                                 float *__restrict__ g_mean, float *__restrict__ g_lam,
                                                 float *__restrict__ g_opac, float *__restrict__ g_l) {
+    // constant factors the backward walk left out of its per-pixel terms
+    if (c == 2 || c == 3) s *= EXP2_UNSCALE;
+    if (c >= 4 && c <= 6) s *= -0.5f;
     switch (c) {
         case 0: g_opac[g] = s; break;
         case 1:
