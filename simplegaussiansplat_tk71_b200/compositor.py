@@ -12,8 +12,21 @@ fits one chunk (sum(boxsize) <= 2**29, gs_model.py:428):
     T_i = prod_{j<i, same pixel} (1 - alpha_j),   alpha = opacity * exp(-1/2 (r-m) Lambda (r-m)^T)
     image[y, x] = sum_i T_i alpha_i l_i           (elements whose inclusive product is 0 contribute nothing, :575)
 
-but not how.  One view = a dozen kernel launches, all through the C ABI (include/gcp_abi.h):
+but not how.  Two routes, `ROUTE` below, both through the C ABI (include/gcp_abi.h) and both checked against the
+fixtures the reference's own Function produced (tests/test_compositor.py):
 
+  "tiles" (default, csrc/gcp_tile.cu) — the fused route: the per-pixel scan is evaluated one pixel per lane, the
+  running T in a register, without materialising the element lists.
+    forward   gcp_tile_prepare   (tile, Gaussian) pair counts, their scan, the pair total (the one host sync)
+              gcp_tile_pack      per-Gaussian tables -> one 64-byte record
+              gcp_tile_bin       pairs, stable sort by 8x4-pixel tile (depth order kept), tile offsets, pieces
+              gcp_tile_render    one warp per piece of a tile's list: alpha, T, colour; T kept per (pair, lane);
+                                 the carries between the pieces of a long list resolved by a combine kernel
+    backward  gcp_tile_backward  the lists walked in reverse: U_i, dL/dalpha_i = T_i <dL/dI, l_i> - T_i U_i and the
+                                 per-element gradients (:733-766) summed per pair
+              gcp_tile_reduce    the pairs of a Gaussian summed in pair order               (:776-783)
+
+  "lists" (csrc/gcp_splat.cu + the scan ops a1 / a3) — the element-list route:
     forward   gcp_splat_pack     per-Gaussian tables -> two 32-byte records (one L2 sector per gather)
               gcp_splat_place    boxes -> the pixel-sorted (key, Gaussian id) element list, built directly by a
                                  counting placement per image row — no sort of the N elements
