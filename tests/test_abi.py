@@ -132,3 +132,32 @@ def test_host_boundary_bits_match_numpy(n, threads):
     np.bitwise_or.at(want, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
     assert np.array_equal(bits[:words], want)
     assert bits[words] == 0xDEADBEEF
+
+
+def test_tile_size_helpers_are_pure_host_arithmetic():
+    """Sizing helpers of the fused compositor route (csrc/gcp_tile.cu), no GPU involved: 8x4-pixel tiles over the
+    inclusive pixel grid [0,W] x [0,H]; work units (pieces) of at most gcp_tile_piece_pairs() pairs."""
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    tw, th = L.gcp_tile_width(), L.gcp_tile_height()
+    assert (tw, th) == (8, 4) and tw * th == 32
+    assert L.gcp_tile_num_tiles(1920, 1080) == ((1920 + tw) // tw) * ((1080 + th) // th) == 241 * 271
+    assert L.gcp_tile_num_tiles(7, 3) == 1 and L.gcp_tile_num_tiles(8, 4) == 4      # W+1 = 9, H+1 = 5 pixels
+    assert L.gcp_tile_num_tiles(-1, 10) == 0 and L.gcp_tile_num_tiles(40000, 10) == 0
+    piece = L.gcp_tile_piece_pairs()
+    assert piece == 128
+    P, W, H = 3_579_735, 1920, 1080
+    nt = L.gcp_tile_num_tiles(W, H)
+    cap = L.gcp_tile_piece_cap(P, W, H)
+    assert cap == nt + P // piece + 1                       # >= sum over tiles of max(1, ceil(len / piece))
+    assert L.gcp_tile_plan_ints(P, W, H) == nt + 1 + cap + 4
+    assert L.gcp_tile_state_floats(P, W, H) == cap * 192
+    assert L.gcp_tile_bin_bytes(P, W, H) > 3 * 4 * P and L.gcp_tile_bin_bytes(-1, W, H) == 0
+    assert L.gcp_tile_reduce_bytes(1000) >= 4 * 1000
+    try:
+        for bad in (0, 31, 33, 100, 1 << 21):
+            assert L.gcp_tile_set_piece_pairs(bad) == -1    # GCP_ERR_INVALID_ARG: a multiple of 32 in [32, 2**20]
+        assert L.gcp_tile_set_piece_pairs(64) == 0 and L.gcp_tile_piece_cap(P, W, H) == nt + P // 64 + 1
+    finally:
+        L.gcp_tile_set_piece_pairs(piece)
