@@ -301,39 +301,41 @@ def test_planned_view_equals_unplanned_gpu(route):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
 def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
-    """Integer side of the tile route: the (tile, Gaussian) pairs, their stable order by tile and the tile offsets
-    against numpy (argsort(kind="stable") of the Gaussian-major pair list)."""
+    """Integer side of the tile route: the (tile, Gaussian) pairs, their stable order by tile, the tile offsets
+    and the piece plan against the numpy restatement (oracle/tile_oracle.py, itself pinned on CPU to the
+    reference's sorted element list by tests/test_compositor_oracle.py)."""
+    from oracle import tile_oracle as to
     from simplegaussiansplat_tk71_b200 import _lib, compositor
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
     case = load_case(np.load(FIX), name)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
-    _, view = compositor._render_forward(t(case["boxsize"]), t(case["sp"]), t(case["ep"]), t(case["mean"]).float(),
-                                         t(case["lam"]), t(case["opac"]), t(case["l_d"]), case["W"], case["H"])
     L = _lib.lib()
-    tw, th = L.gcp_tile_width(), L.gcp_tile_height()
+    default = L.gcp_tile_piece_pairs()
     W, H = case["W"], case["H"]
-    ntx = (W + tw) // tw
-    ntiles = ntx * ((H + th) // th)
+    assert (L.gcp_tile_width(), L.gcp_tile_height()) == (to.TW, to.TH)
+    ntx, nty = to.num_tiles(W, H)
+    ntiles = ntx * nty
     assert ntiles == L.gcp_tile_num_tiles(W, H)
-    tiles, gids, counts = [], [], []
-    for g, ((sx, sy), (ex, ey)) in enumerate(zip(case["sp"].tolist(), case["ep"].tolist())):
-        sx, sy, ex, ey = max(sx, 0), max(sy, 0), min(ex, W), min(ey, H)
-        c = 0
-        if ex >= sx and ey >= sy:
-            for ty in range(sy // th, ey // th + 1):
-                for tx in range(sx // tw, ex // tw + 1):
-                    tiles.append(ty * ntx + tx)
-                    gids.append(g)
-                    c += 1
-        counts.append(c)
-    tiles, gids = np.asarray(tiles, np.int64), np.asarray(gids, np.int32)
-    assert view.P == len(tiles)
-    assert np.array_equal(view.toff.cpu().numpy(), np.concatenate([[0], np.cumsum(counts)]))
-    order = np.argsort(tiles, kind="stable")
-    assert np.array_equal(view.pgid.cpu().numpy()[:view.P], gids[order])
-    start = np.searchsorted(tiles[order], np.arange(ntiles + 1), side="left")
-    assert np.array_equal(view.tstart.cpu().numpy(), start.astype(np.int32))
+    tiles, gids, toff = to.tile_pairs(case["sp"], case["ep"], W, H)
+    gid_s, start, _ = to.sort_by_tile(tiles, gids, ntiles)
+    try:
+        for piece in (32, default):
+            assert L.gcp_tile_set_piece_pairs(piece) == 0
+            _, view = compositor._render_forward(t(case["boxsize"]), t(case["sp"]), t(case["ep"]),
+                                                 t(case["mean"]).float(), t(case["lam"]), t(case["opac"]),
+                                                 t(case["l_d"]), W, H)
+            assert view.P == len(tiles)
+            assert np.array_equal(view.toff.cpu().numpy(), toff)
+            assert np.array_equal(view.pgid.cpu().numpy()[:view.P], gid_s)
+            assert np.array_equal(view.tstart.cpu().numpy(), start)
+            pstart, ptile = to.piece_plan(start, piece)
+            plan = view.plan.cpu().numpy()
+            assert np.array_equal(plan[:ntiles + 1], pstart)
+            assert np.array_equal(plan[ntiles + 1:ntiles + 1 + len(ptile)], ptile)
+            assert len(ptile) <= L.gcp_tile_piece_cap(view.P, W, H)
+    finally:
+        L.gcp_tile_set_piece_pairs(default)
 
 
 def _both_routes(v, gI, monkeypatch, repeats=1):

@@ -47,3 +47,38 @@ def test_chunked_reference_render_differs_only_by_its_boundary_carry():
     assert one.shape == three.shape
     assert np.all(three >= one - 1e-4)          # a missing (1-alpha) <= 1 factor can only brighten
     assert np.abs(three - one).max() > 1e-3      # and it is visible
+
+
+@pytest.mark.parametrize("name", ["small", "wide", "dense"])
+def test_tile_binning_visits_every_pixel_list_in_reference_order(name):
+    """The fused route bins (tile, Gaussian) pairs instead of sorting elements.  Walking a tile's pairs in their
+    stable order must give, for every pixel, exactly the Gaussian sequence of the reference's sorted element list
+    (expansion + stable sort by pixel key, gs_model.py:538-548) — nothing missing, nothing twice, same order."""
+    from oracle import compositor_oracle as co
+    from oracle import tile_oracle as to
+
+    c = load_case(np.load(FIX), name)
+    gid, px, py = co.expand(c["boxsize"], c["sp"], c["ep"])
+    key = (py * 10000 + px).astype(np.int64)
+    order = np.argsort(key, kind="stable")
+    ref = {}
+    for k, g in zip(key[order].tolist(), gid[order].tolist()):
+        ref.setdefault(k, []).append(g)
+    got = to.pixel_lists_from_pairs(c["sp"], c["ep"], c["W"], c["H"])
+    assert got == ref
+    # and the piece plan covers every tile's list exactly once
+    ntx, nty = to.num_tiles(c["W"], c["H"])
+    tiles, gids, toff = to.tile_pairs(c["sp"], c["ep"], c["W"], c["H"])
+    assert toff[-1] == len(tiles)
+    _, start, _ = to.sort_by_tile(tiles, gids, ntx * nty)
+    for piece in (32, 128):
+        pstart, ptile = to.piece_plan(start, piece)
+        assert pstart[-1] == len(ptile) and np.all(np.diff(pstart) >= 1)
+        covered = 0
+        for p, t in enumerate(ptile.tolist()):
+            k = p - pstart[t]
+            lo = start[t] + k * piece
+            hi = min(start[t + 1], lo + piece)
+            assert lo <= hi and (hi > lo or start[t] == start[t + 1])
+            covered += hi - lo
+        assert covered == len(tiles)
