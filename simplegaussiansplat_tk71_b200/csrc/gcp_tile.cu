@@ -33,7 +33,6 @@ namespace {
 constexpr int TSX = 3, TSY = 2;                 // tile = 8 x 4 pixels, lane = (y & 3) * 8 + (x & 7)
 constexpr int TW = 1 << TSX, TH = 1 << TSY;
 static_assert(TW * TH == 32, "one tile is one warp");
-constexpr int REC_WORDS = 16;                   // per-Gaussian record: 64 bytes = two 32-byte sectors
 
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
@@ -677,6 +676,18 @@ inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >
 inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
 inline int tiles_y(int H) { return (H + TH) >> TSY; }
 
+// views into the piece_plan buffer: piece_start[ntiles+1] | piece_tile[cap] | 4 counter words
+struct PlanView {
+    const int32_t *pstart, *ptile;
+    unsigned int *tickets;
+    int64_t cap;
+};
+PlanView plan_view(int32_t *piece_plan, int64_t P, int W, int H) {
+    const int ntiles = tiles_x(W) * tiles_y(H);
+    const int64_t cap = gcp_tile_piece_cap(P, W, H);
+    return PlanView{piece_plan, piece_plan + ntiles + 1,
+                    reinterpret_cast<unsigned int *>(piece_plan + ntiles + 1 + cap), cap};
+}
 }  // namespace
 
 extern "C" {
@@ -784,20 +795,6 @@ int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int6
     k_tile_pieces<<<blocks_for(ntiles, 256), 256, 0, st>>>(pstart, ntiles, piece_tile);
     return static_cast<int>(cudaGetLastError());
 }
-
-namespace {
-struct PlanView {
-    const int32_t *pstart, *ptile;
-    unsigned int *tickets;
-    int64_t cap;
-};
-PlanView plan_view(int32_t *piece_plan, int64_t P, int W, int H) {
-    const int ntiles = tiles_x(W) * tiles_y(H);
-    const int64_t cap = gcp_tile_piece_cap(P, W, H);
-    return PlanView{piece_plan, piece_plan + ntiles + 1,
-                    reinterpret_cast<unsigned int *>(piece_plan + ntiles + 1 + cap), cap};
-}
-}  // namespace
 
 int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
                     int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream) {
