@@ -82,3 +82,35 @@ def test_tile_binning_visits_every_pixel_list_in_reference_order(name):
             assert lo <= hi and (hi > lo or start[t] == start[t + 1])
             covered += hi - lo
         assert covered == len(tiles)
+
+
+def test_tile_binning_random_boxes_and_image_sizes():
+    """Random image sizes (partial tiles, single rows / columns) and random clamped boxes, including one-pixel and
+    whole-image ones: the tile walk order equals the stable pixel sort for every pixel."""
+    from oracle import compositor_oracle as co
+    from oracle import tile_oracle as to
+
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        W, H = int(rng.integers(0, 41)), int(rng.integers(0, 23))
+        n = int(rng.integers(1, 40))
+        x0 = rng.integers(0, W + 1, n)
+        y0 = rng.integers(0, H + 1, n)
+        x1 = np.minimum(W, x0 + rng.integers(0, W + 2, n) * (rng.uniform(size=n) < 0.7))
+        y1 = np.minimum(H, y0 + rng.integers(0, H + 2, n) * (rng.uniform(size=n) < 0.7))
+        sp = np.stack([x0, y0], 1).astype(np.int32)
+        ep = np.stack([x1, y1], 1).astype(np.int32)
+        if trial % 7 == 0:
+            sp[0], ep[0] = (0, 0), (W, H)
+        boxsize = ((ep[:, 0] - sp[:, 0] + 1) * (ep[:, 1] - sp[:, 1] + 1)).astype(np.int64)
+        gid, px, py = co.expand(boxsize, sp, ep)
+        key = (py * 10000 + px).astype(np.int64)
+        order = np.argsort(key, kind="stable")
+        ref = {}
+        for k, g in zip(key[order].tolist(), gid[order].tolist()):
+            ref.setdefault(k, []).append(g)
+        assert to.pixel_lists_from_pairs(sp, ep, W, H) == ref, (trial, W, H)
+        tiles, gids, toff = to.tile_pairs(sp, ep, W, H)
+        ntx, nty = to.num_tiles(W, H)
+        assert tiles.size == 0 or (tiles.min() >= 0 and tiles.max() < ntx * nty)
+        assert np.array_equal(np.diff(toff), np.bincount(gids, minlength=n))
