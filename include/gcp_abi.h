@@ -276,6 +276,14 @@ size_t gcp_tile_bin_bytes(int64_t P, int W, int H);
 int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
                  int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
                  gcp_stream_t stream);
+/* The same without waiting for the pair count: `cap` is a guessed capacity (pair_gid i32[cap], temp >=
+ * gcp_tile_bin_bytes(cap, W, H), piece_plan / piece_state / t_keep / partial sized for cap) and every later call of
+ * the view passes cap as P.  The real count stays on the device (toff[n]); slots behind it are padded with a key that
+ * sorts last.  The caller must compare the count with cap afterwards (it is in `totals` of gcp_tile_prepare): if it
+ * was larger, the pairs beyond cap were dropped and the view has to be redone with gcp_tile_bin. */
+int gcp_tile_bin_speculative(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t cap, int W,
+                             int H, int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp,
+                             size_t temp_bytes, gcp_stream_t stream);
 /* image f32[(H+1)*(W+1)*3] is written completely (no need to zero it).  t_keep may be NULL when no backward will
  * follow (a render without gradients skips the 128 B per pair).  gcp_tile_piece_pairs() must not change between
  * gcp_tile_bin and the last walk of the same view. */

@@ -31,7 +31,7 @@ SYMBOLS = (
     "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
     "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs", "gcp_tile_piece_cap",
     "gcp_tile_plan_ints", "gcp_tile_state_floats", "gcp_tile_prepare_bytes", "gcp_tile_prepare",
-    "gcp_tile_pack", "gcp_tile_bin_bytes", "gcp_tile_bin", "gcp_tile_render", "gcp_tile_backward", "gcp_tile_reduce", "gcp_tile_reduce_bytes",
+    "gcp_tile_pack", "gcp_tile_bin_bytes", "gcp_tile_bin", "gcp_tile_bin_speculative", "gcp_tile_render", "gcp_tile_backward", "gcp_tile_reduce", "gcp_tile_reduce_bytes",
     "gcp_host_boundary_bits", "gcp_ids_from_bits_bytes", "gcp_ids_from_bits",
 )
 
@@ -127,6 +127,8 @@ def lib() -> ctypes.CDLL:
     L.gcp_tile_bin_bytes.argtypes = [i64, ci, ci]
     L.gcp_tile_bin_bytes.restype = sz
     L.gcp_tile_bin.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, sz, vp]
+    L.gcp_tile_bin_speculative.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, sz, vp]
+    L.gcp_tile_bin_speculative.restype = ci
     L.gcp_tile_render.argtypes = [vp, vp, vp, vp, i64, ci, ci, vp, vp, vp, vp]
     L.gcp_tile_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
     L.gcp_tile_reduce.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]

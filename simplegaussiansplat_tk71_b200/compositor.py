@@ -67,6 +67,14 @@ USE_PLACEMENT = True
 # "lists": the element-list route — placement, alpha, the scan ops a1/a3 (gcp_cumprod_fwd/bwd), colour, un-sort.
 # Same image and gradients within fp32 rounding (tests/test_compositor.py runs every case through both).
 ROUTE = "tiles"
+# Tile route, views rendered without plan_view: queue the whole forward on a GUESSED pair capacity (the count of the
+# last view of the same shape + 25 %) and only then wait for the real count; a guess that turns out too small costs a
+# second, exact pass.  Off by default: measured, it gains nothing — the forward of a single view is bound by the
+# host's enqueue path (~190 us for ~20 launches) followed by the render kernel, not by the wait for the count (4 us
+# once the prologue has been copied to pinned memory right behind it), and the padded sort costs what the removed
+# wait saved (0.51 ms either way at 1080p).  Kept because it is exact, tested, and the right tool once the launches
+# are captured in a graph.
+SPECULATE = False
 
 
 def _p(t):
@@ -181,13 +189,17 @@ class _View:
                  "goff", "rec_a", "rec_b", "seg_off", "cstart", "pgid", "btab", "P")
 
 
+_pair_counts = {}   # (device, n, W, H) -> pair count of the last view of that shape (tile route, SPECULATE)
+
+
 class _TileView:
     """Tile route: the tile-sorted pair list, the packed tables and the exclusive T of every (pair, lane)
     (128 B per pair) kept for the backward."""
     __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "plan", "pstate", "pgid", "tkeep", "l_d", "piece")
 
 
-def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep=True) -> tuple:
+def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep=True,
+                          speculate=None) -> tuple:
     dev = startpoint.device
     L = _lib.lib()
     v = _TileView()
@@ -221,22 +233,42 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
                                    _p(v.rec), stream), "gcp_tile_pack")
         image = torch.empty((H + 1, W + 1, 3), dtype=torch.float32, device=dev)  # every pixel is written by its lane
         v.tstart = torch.empty(int(L.gcp_tile_num_tiles(W, H)) + 1, dtype=torch.int32, device=dev)
-        # the one host sync of a view (like the reference's .item() at uitility.py:348): the pair count was copied
-        # to pinned memory right behind the prologue, so it is usually there by now
-        event.synchronize()
-        (P,) = host.tolist()
-        if P >= 2 ** 31 - 64:
-            raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
+        shape_key = (dev.index, n, W, H)
+        last = _pair_counts.get(shape_key)
+        if speculate is None:
+            speculate = SPECULATE
+        speculate = bool(speculate) and plan is None and last is not None
+        if speculate:
+            P = min(last + last // 4 + 4096, 2 ** 31 - 65)      # a capacity: the count itself is still on its way
+        else:
+            # the one host sync of a view (like the reference's .item() at uitility.py:348): the pair count was
+            # copied to pinned memory right behind the prologue
+            event.synchronize()
+            (P,) = host.tolist()
+            _pair_counts[shape_key] = P
+            if P >= 2 ** 31 - 64:
+                raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
         v.P = P
         v.plan = torch.empty(int(L.gcp_tile_plan_ints(P, W, H)), dtype=torch.int32, device=dev)
         v.pstate = torch.empty(int(L.gcp_tile_state_floats(P, W, H)), dtype=torch.float32, device=dev)
         v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
         v.tkeep = torch.empty(max(P, 1) * 32, dtype=torch.float32, device=dev) if keep else None
         temp = _scratch_bytes(dev, "bin", int(L.gcp_tile_bin_bytes(P, W, H)))
-        _lib.check(L.gcp_tile_bin(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.plan), _p(v.pgid),
-                                  _p(temp), temp.numel(), stream), "gcp_tile_bin")
+        bin_fn = L.gcp_tile_bin_speculative if speculate else L.gcp_tile_bin
+        _lib.check(bin_fn(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.plan), _p(v.pgid), _p(temp),
+                          temp.numel(), stream), "gcp_tile_bin")
         _lib.check(L.gcp_tile_render(_p(v.tstart), _p(v.plan), _p(v.pgid), _p(v.rec), P, W, H, _p(image),
                                      _p(v.tkeep) if keep else None, _p(v.pstate), stream), "gcp_tile_render")
+        if speculate:
+            # everything is queued; the count arrived long ago.  v.P stays the capacity: it is what the buffers of
+            # this view are laid out for.
+            event.synchronize()
+            (actual,) = host.tolist()
+            _pair_counts[shape_key] = actual
+            if actual > P:   # guessed too low: pairs were dropped, render again with the exact count
+                del v, image
+                return _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep,
+                                             speculate=False)
     return image, v
 
 

@@ -103,7 +103,7 @@ k_tile_pack(const float *__restrict__ mean, const float *__restrict__ lam, const
 // than 32 tiles is written by the whole warp afterwards.
 __global__ void __launch_bounds__(256)
 k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
-             int64_t n, int W, int H, int ntx, int32_t *__restrict__ ptile, int32_t *__restrict__ pgid) {
+             int64_t n, int64_t cap, int W, int H, int ntx, int32_t *__restrict__ ptile, int32_t *__restrict__ pgid) {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int64_t beg = 0;
@@ -116,8 +116,8 @@ k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, con
     }
     if (cnt <= 32) {
         int r = 0, c = 0;
-        for (int i = 0; i < cnt; ++i) {
-            ptile[beg + i] = (ty0 + r) * ntx + tx0 + c;
+        for (int i = 0; i < cnt && beg + i < cap; ++i) {   // cap: the buffers' capacity (>= the pair count,
+            ptile[beg + i] = (ty0 + r) * ntx + tx0 + c;      // except in a speculative call that guessed too low)
             pgid[beg + i] = static_cast<int32_t>(g);
             if (++c == nx) { c = 0; ++r; }
         }
@@ -131,7 +131,7 @@ k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, con
         const int btx0 = __shfl_sync(0xffffffffu, tx0, src), bty0 = __shfl_sync(0xffffffffu, ty0, src);
         const int bnx = __shfl_sync(0xffffffffu, nx, src);
         const int32_t bg = static_cast<int32_t>(g - lane + src);
-        for (int i = lane; i < bcnt; i += 32) {
+        for (int i = lane; i < bcnt && bbeg + i < cap; i += 32) {
             const int r = i / bnx;
             ptile[bbeg + i] = (bty0 + r) * ntx + btx0 + (i - r * bnx);
             pgid[bbeg + i] = bg;
@@ -155,9 +155,11 @@ __device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, i
 constexpr int CHP = 8;
 __global__ void __launch_bounds__(256)
 k_tile_pairs_flat(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
-                  int64_t n, int64_t P, int W, int H, int ntx, int32_t *__restrict__ ptile,
+                  int64_t n, int64_t cap, int W, int H, int ntx, int32_t *__restrict__ ptile,
                   int32_t *__restrict__ pgid) {
     const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CHP;
+    const int64_t total = __ldg(toff + n);          // the pair count lives on the device; cap = buffer capacity
+    const int64_t P = total < cap ? total : cap;
     if (p0 >= P) return;
     int64_t g = find_owner(toff, n, p0);
     int64_t gbeg = __ldg(toff + g), gend = __ldg(toff + g + 1);
@@ -176,6 +178,19 @@ k_tile_pairs_flat(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep
         const int r = local / nx;
         ptile[p] = (ty0 + r) * ntx + tx0 + (local - r * nx);
         pgid[p] = static_cast<int32_t>(g);
+    }
+}
+
+// speculative binning (the host guessed a capacity instead of waiting for the pair count): the slots behind the
+// real pairs get the key `ntiles`, which sorts behind every tile and is what k_tile_start expects after the last pair
+__global__ void __launch_bounds__(256)
+k_tile_pad(const int64_t *__restrict__ toff, int64_t n, int64_t cap, int ntiles, int32_t *__restrict__ ptile,
+           int32_t *__restrict__ pgid) {
+    const int64_t total = __ldg(toff + n);
+    for (int64_t p = total + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < cap;
+         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        ptile[p] = ntiles;
+        pgid[p] = 0;
     }
 }
 
@@ -756,9 +771,9 @@ size_t gcp_tile_bin_bytes(int64_t P, int W, int H) {
     return (P < 0 || bad_image(W, H)) ? 0 : bin_layout(P, tiles_x(W) * tiles_y(H)).total;
 }
 
-int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
-                 int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
-                 gcp_stream_t stream) {
+static int tile_bin_impl(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W,
+                         int H, int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp,
+                         size_t temp_bytes, gcp_stream_t stream, bool speculative) {
     if (n < 0 || P < 0 || P >= (int64_t(1) << 31) - 64 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
     if (!tile_start || !piece_plan || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid)))
         return GCP_ERR_INVALID_ARG;
@@ -772,9 +787,11 @@ int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int6
     cudaError_t e;
     if (P > 0) {
         if (P <= 6 * n)   // small boxes: a thread per Gaussian; boxes of many tiles: parallel over the pairs
-            k_tile_pairs<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, toff, n, W, H, ntx, ptile, pgid);
+            k_tile_pairs<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
         else
             k_tile_pairs_flat<<<blocks_for(P, 256 * CHP), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
+        if (speculative)   // P is a capacity here: mark the slots behind the real pairs
+            k_tile_pad<<<blocks_for(P / 4 + 1, 256, 1024), 256, 0, st>>>(toff, n, P, ntiles, ptile, pgid);
         size_t cb = L.cub_bytes;
         // stable LSD radix sort on the tile bits only: inside a tile the Gaussians keep their (depth) order
         e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, ptile, ptile_s, pgid, pair_gid, P, 0, key_bits(ntiles), st);
@@ -794,6 +811,18 @@ int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int6
     if (e != cudaSuccess) return static_cast<int>(e);
     k_tile_pieces<<<blocks_for(ntiles, 256), 256, 0, st>>>(pstart, ntiles, piece_tile);
     return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
+                 int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
+                 gcp_stream_t stream) {
+    return tile_bin_impl(sp, ep, toff, n, P, W, H, tile_start, piece_plan, pair_gid, temp, temp_bytes, stream, false);
+}
+
+int gcp_tile_bin_speculative(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t cap, int W,
+                             int H, int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp,
+                             size_t temp_bytes, gcp_stream_t stream) {
+    return tile_bin_impl(sp, ep, toff, n, cap, W, H, tile_start, piece_plan, pair_gid, temp, temp_bytes, stream, true);
 }
 
 int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,

@@ -308,6 +308,7 @@ def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
     from simplegaussiansplat_tk71_b200 import _lib, compositor
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    monkeypatch.setattr(compositor, "SPECULATE", False)     # exact pair count: view.P is the count, no padding
     case = load_case(np.load(FIX), name)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
     L = _lib.lib()
@@ -486,3 +487,40 @@ def test_native_compositor_ragged_image_sizes_against_oracle_gpu(W, H, n, max_ha
     for name, a, b in (("mean", got[1], gm), ("lambda", got[2], gL), ("opacity", got[3], go), ("l", got[4], gl)):
         scale = float(np.abs(b).max())
         np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4 * scale, err_msg=name)
+
+
+@pytest.mark.gpu
+def test_speculative_forward_equals_exact_forward_gpu(monkeypatch):
+    """Tile route without plan_view: from the second view of a shape on, the forward is queued on a guessed pair
+    capacity before the count is known (compositor.SPECULATE).  Same bits as the exact pass; a guess that is too
+    small is detected and the view rendered again."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    v = wl.splat_view(640, 360, 60_000, seed=5, device="cuda")
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+    key = (v.startpoint.device.index, v.n, v.width, v.height)
+
+    def step():
+        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                        v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+        img.backward(gI)
+        return [img.detach().clone()] + [t.grad.clone() for t in (m, lam, o, l)]
+
+    compositor._pair_counts.pop(key, None)
+    monkeypatch.setattr(compositor, "SPECULATE", False)
+    exact = step()
+    count = compositor._pair_counts[key]
+    assert count > 10_000
+    monkeypatch.setattr(compositor, "SPECULATE", True)
+    spec = step()                                   # capacity = count * 1.25 + 4096
+    compositor._pair_counts[key] = 100              # a guess far too small: dropped pairs -> detected -> exact pass
+    redo = step()
+    assert compositor._pair_counts[key] == count
+    compositor._pair_counts[key] = 4 * count        # far too large: only padding
+    padded = step()
+    for other in (spec, redo, padded):
+        for a, b in zip(exact, other):
+            assert torch.equal(a, b)
