@@ -114,6 +114,19 @@ class ClockSampler:
         return out
 
 
+L2_BYTES = 126e6
+
+
+def config_for(e, world: int) -> dict:
+    """The `config` object of the JSON line — the same keys and values in both arms (ours / --impl reference)."""
+    ws = 4 * e.n * 4   # x, key/inv, grad_out/y in, one array out per op
+    l2 = ("inputs exceed L2 (3 x %.0f MB read + %.0f MB written per op), no flush needed" % (e.n * 4 / 1e6, e.n * 4 / 1e6)
+          if ws > 2 * L2_BYTES else
+          "working set %.0f MB fits the 126 MB L2: a 256 MB buffer is rewritten between timed ops (L2 flush)" % (ws / 1e6))
+    return {"workload": e.name, "elements_per_gpu": e.n, "segments_per_gpu": e.k, "l2": l2,
+            "parallelism": f"views x{world} (no data-path collective)"}
+
+
 def make_workload(name: str, device, view: int):
     from simplegaussiansplat_tk71_b200 import workloads as wl
 
@@ -195,7 +208,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": e.name, "elements": e.n, "segments": e.k},
+        "config": config_for(e, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"whole view ({e.n} elements, {e.k} segments) per step; pure-PyTorch CPU path "
                                    "(length-bucketed torch.cumprod + autograd backward, oracle/torch_cpu_path.py) — "
@@ -226,6 +239,8 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="time every kernel variant (stderr table), then exit")
     ap.add_argument("--views", type=int, default=64, help="views per training step for the multi-view leg (C5)")
     ap.add_argument("--no-splat", action="store_true", help="skip the splat-step / multi-view legs")
+    ap.add_argument("--no-reference-legs", action="store_true",
+                    help="skip timing the reference's CUDA ops and its compositor Function beside ours")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly the JSON line(s) this script prints: everything libraries write to file descriptor 1
@@ -289,23 +304,33 @@ def main():
     assert ops.workspace_status(device) == 0, "watchdog fired during warm-up"
 
     # ---- timed region: K steps, CUDA events on the launching (current) stream ----
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    # L2-resident workloads (C1): a 256 MB buffer is rewritten before every timed op, outside the op's event pair
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=device) if 16 * n <= 2 * L2_BYTES else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps + 1)]
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
     barrier()
     ev[0].record()
     for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(1.0)
+        ev[4 * i + 1].record()
         gc.grouped_cumprod_forward(e.x, e.key, y)
-        ev[2 * i + 1].record()
+        ev[4 * i + 2].record()
+        if flush is not None:
+            flush.fill_(2.0)
+        ev[4 * i + 3].record()
         gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
-        ev[2 * i + 2].record()
+        ev[4 * i + 4].record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    fwd_ms = sum(ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps)) / args.steps
+    bwd_ms = sum(ev[4 * i + 3].elapsed_time(ev[4 * i + 4]) for i in range(args.steps)) / args.steps
+    # no flush: the whole bracket (K back-to-back steps); with the flush: the ops' own event pairs
+    total_ms = ev[0].elapsed_time(ev[-1]) if flush is None else (fwd_ms + bwd_ms) * args.steps
     time.sleep(0.15)
     clocks = sampler.stop()
-    fwd_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
-    bwd_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    del flush
     assert ops.workspace_status(device) == 0, "watchdog fired during the timed region"
 
     t = torch.tensor([total_ms], device=device, dtype=torch.float64)
@@ -352,6 +377,23 @@ def main():
         splat = splat_legs(args, device, rank, world)
         hx, hk, hi, hs, hg = (t_.cpu() for t_ in (e.x, e.key, e.inv, e.seg_end, e.grad_out))
 
+    # ---- the reference on the same box (rank 0, N == 1 only): its CUDA ops beside ours, and its own compositor
+    #      Function with its ops / with the drop-in behind it ----
+    ref_ops = ref_fn = None
+    if rank == 0 and world == 1 and not args.no_reference_legs:
+        try:
+            ref_ops = ref_cuda_ops_leg(device, e)
+        except Exception as ex:  # noqa: BLE001
+            ref_ops = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        if not args.no_splat:
+            try:
+                ref_fn = reference_function_leg(device)
+            except Exception as ex:  # noqa: BLE001
+                ref_fn = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+            if splat is not None and isinstance(ref_fn, dict) and "c3_1080p" in ref_fn:
+                splat["reference_function_ms"] = ref_fn["c3_1080p"].get("reference_function_ms")
+                splat["reference_function_with_dropin_ms"] = ref_fn["c3_1080p"].get("reference_function_with_dropin_ms")
+
     # ---- CPU baseline (rank 0, N == 1 only): the oracle's C/OpenMP port on the same inputs ----
     cpu = None
     cpu_c = None
@@ -390,11 +432,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": e.name, "elements_per_gpu": n, "segments_per_gpu": k,
-                       "l2": "inputs exceed L2 (3 x %.0f MB read + %.0f MB written per op)" % (n * 4 / 1e6, n * 4 / 1e6),
-                       "variant_fwd": ops.variants("fwd")[args.variant_fwd] if args.variant_fwd >= 0 else "default",
-                       "variant_bwd": ops.variants("bwd")[args.variant_bwd] if args.variant_bwd >= 0 else "default",
-                       "parallelism": f"views x{world} (no data-path collective)"},
+            "config": config_for(e, world),
+            "variants": {"fwd": ops.variants("fwd")[args.variant_fwd] if args.variant_fwd >= 0 else "default",
+                         "bwd": ops.variants("bwd")[args.variant_bwd] if args.variant_bwd >= 0 else "default"},
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "roofline": {"bound": "hbm", "kernel": "grouped_cumprod_backward (k_bwd_*)", "achieved": bwd_gbs,
                          "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic.get("bwd"),
@@ -410,6 +450,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "splat_step": splat,
+            "ref_cuda_ops": ref_ops,
+            "reference_function": ref_fn,
         }
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
@@ -623,6 +665,131 @@ def c2_leg(device):
             "scan_on_view0": {"elements": n, "pixel_lists": k, "mean_list_length": n / max(k, 1), "fwd_ms": tf,
                               "bwd_ms": tb, "Gelem_s": n / ((tf + tb) * 1e-3) / 1e9,
                               "frac_of_measured_hbm": ab["fwd_bwd"] / ((tf + tb) * 1e-3) / 1e9 / peak}}
+
+
+def _median_ms(fn, reps, warm=2, flush=None):
+    """Median device time of fn() over `reps` calls (CUDA events on the current stream, one pair per call)."""
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def ref_cuda_ops_leg(device, e_c3):
+    """The reference's own CUDA ops (oracle/_ref/grouped_cumprod_ref.so: its four native sources compiled unchanged
+    for sm_100a — thrust::inclusive_scan_by_key x2, grouped_cumprod_forward.cu:17-23 / grouped_cumsum_forward.cu:17-23,
+    and the O(sum L^2) backward kernel, grouped_cumprod_backward.cu:9-41) timed beside ours on the SAME device
+    arrays with the same CUDA-event harness: C1, C3, and C4 with its deep segments capped at 16 Ki elements (the
+    reference backward walks every segment tail per element: the uncapped 262 144-element segments alone would
+    take minutes).  L2-resident C1 is timed with an L2 flush before every call."""
+    import torch
+
+    import grouped_cumprod as ours
+    from oracle import ref_function as rf
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    ref = rf.reference_ops()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/grouped_cumprod_ref.so not built"}
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=device)
+    out = {"harness": "median of per-call CUDA-event pairs on the default stream, same arrays for both; the "
+                      "reference's thrust calls include their cudaMalloc/cudaFree + host sync (that is the op)"}
+
+    def one(e, reps, use_flush, ref_bwd_reps):
+        y, s, gin = (torch.empty_like(e.x) for _ in range(3))
+        fl = flush if use_flush else None
+        r = {"elements": e.n, "segments": e.k, "l2_flush": bool(use_flush)}
+        for name, mod in (("ours", ours), ("reference", ref)):
+            rb = reps if name == "ours" else ref_bwd_reps
+            f = _median_ms(lambda: mod.grouped_cumprod_forward(e.x, e.key, y), reps, flush=fl)
+            c = _median_ms(lambda: mod.grouped_cumsum_forward(e.grad_out, e.key, s), reps, flush=fl)
+            b = _median_ms(lambda: mod.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end), rb,
+                           warm=1, flush=fl)
+            r[name] = {"fwd_ms": f, "cumsum_ms": c, "bwd_ms": b, "fwd_bwd_Gelem_s": e.n / ((f + b) * 1e-3) / 1e9}
+        r["speedup"] = {k: r["reference"][k] / r["ours"][k] for k in ("fwd_ms", "cumsum_ms", "bwd_ms")}
+        return r
+
+    out["c1"] = one(wl.c1(device), 15, True, 15)
+    out["c3"] = one(e_c3, 7, False, 3)
+    try:
+        L, is_deep = wl.lengths_c4(3840 * 2160, 2160, deep=512, deep_lo=8192, deep_hi=16384)
+        import numpy as np
+
+        e4 = wl.build("C4 3840x2160 lognormal(ln30,1)+512 deep segments capped at 16Ki", L, 3840, 2160, 2160, device,
+                      alpha_scale_per_seg=np.where(is_deep, 1e-3, 1.0))
+        out["c4_capped"] = one(e4, 5, False, 2)
+        del e4
+    except Exception as ex:  # noqa: BLE001
+        out["c4_capped"] = {"error": str(ex)[:200]}
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_function_leg(device):
+    """The reference's own compositor Function (baseline/_ref/gs_model.py:477-820, unmodified; loader
+    oracle/ref_function.py) forward + backward on the GPU: (a) with its own CUDA ops, (b) with this repo's drop-in
+    `grouped_cumprod` module behind the same Python, (c) the native compositor — same scenes, same harness."""
+    import torch
+
+    from oracle import ref_function as rf
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    if not rf.available():
+        return {"unavailable": "baseline/_ref/gs_model.py not shipped"}
+    if rf.reference_ops() is None:
+        return {"unavailable": "oracle/_ref/grouped_cumprod_ref.so not built"}
+    out = {}
+    scenes = [("c3_1080p", lambda: wl.splat_view(1920, 1080, 1_000_000, seed=1080, device=device)),
+              ("c3_sixteenth", lambda: wl.splat_view(480, 270, 62_500, seed=1080, device=device)),
+              ("c2_bundled_view0", lambda: wl.bundled_views(device, n_views=1)[0])]
+    for tag, make in scenes:
+        try:
+            sc = make()
+            scene = (sc.boxsize, sc.startpoint, sc.endpoint, sc.mean, sc.lam, sc.opacity, sc.l_d)
+            gI = torch.rand(sc.height + 1, sc.width + 1, 3, device=device) + 0.1
+            r = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n}
+            res = {}
+            for ops_name in ("ref", "dropin"):
+                def go(ops_name=ops_name):
+                    res[ops_name] = rf.run(ops_name, scene, sc.width, sc.height, gI)
+                r["reference_function_ms" if ops_name == "ref" else "reference_function_with_dropin_ms"] = \
+                    _median_ms(go, 3, warm=1)
+            m, lam, o, l = (sc.mean.float().requires_grad_(True), sc.lam.clone().requires_grad_(True),
+                            sc.opacity.clone().requires_grad_(True), sc.l_d.clone().requires_grad_(True))
+
+            def native():
+                for t_ in (m, lam, o, l):
+                    t_.grad = None
+                img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, sc.width,
+                              sc.height)
+                img.backward(gI)
+                res["native"] = img.detach()
+            r["native_ms"] = _median_ms(native, 7, warm=2)
+            r["speedup_vs_reference_function"] = r["reference_function_ms"] / r["native_ms"]
+            ia, ib, ic = res["ref"][0], res["dropin"][0], res["native"]
+            r["max_abs_image_diff_dropin_vs_ref_ops"] = float((ia - ib).abs().max())
+            r["max_abs_image_diff_native_vs_ref_function"] = float((ia - ic).abs().max())
+            out[tag] = r
+            del res, sc, scene, gI, m, lam, o, l
+        except Exception as ex:  # noqa: BLE001
+            out[tag] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        torch.cuda.empty_cache()
+    return out
 
 
 def sweep(args, e, y, gin, gc, ops):

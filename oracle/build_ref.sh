@@ -15,7 +15,8 @@
 # unset (setup.py:4,17).  This recipe is the equivalent nvcc command line.
 #
 # Used by tests/ (-m gpu) as a second parity checker beside the fp64 oracle,
-# and by tests/ref_ops_timing.py to time the reference ops on the same box.
+# (tests/test_gpu_parity.py, tests/test_reference_function.py) and by bench.py's `ref_cuda_ops` /
+# `reference_function` legs, which time the reference ops beside ours on the same box.
 set -euo pipefail
 REF=${REF:-/root/reference/cuda_kernel}
 HERE="$(cd "$(dirname "$0")" && pwd)"
