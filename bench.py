@@ -793,15 +793,15 @@ def reference_function_leg(device):
 
 
 def sweep(args, e, y, gin, gc, ops):
-    """Times every variant of both kernels on the resident workload; prints a table to stderr and JSON to stdout."""
+    """Times both paths of both ops on the resident workload — aligned, sliced by one element with every array in
+    the same 16-byte phase (the alignment peel of the persistent kernels), and sliced with mixed phases (the
+    plain-load fallback); prints a table to stderr and JSON to stdout."""
     import torch
 
     from simplegaussiansplat_tk71_b200 import workloads as wl
 
-    ab = wl.algorithmic_bytes(e.n, e.k)
     peak, _ = _peaks()
-    res = {"workload": e.name, "n": e.n, "fwd": [], "bwd": []}
-    gc.grouped_cumprod_forward(e.x, e.key, y)
+    res = {"workload": e.name, "n": e.n, "rows": []}
 
     def timeit(fn):
         for _ in range(3):
@@ -815,33 +815,34 @@ def sweep(args, e, y, gin, gc, ops):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / args.steps
 
-    for halo in (1, 0):
-        ops.set_option(0, halo)
+    n1 = e.n - 4
+    layouts = {"aligned": (0, 0, 0, 0, 0), "sliced, same phase (+1 element)": (1, 1, 1, 1, 1),
+               "sliced, same phase (+3)": (3, 3, 3, 3, 3), "sliced, mixed phases": (1, 2, 3, 0, 1)}
+    gc.grouped_cumprod_forward(e.x, e.key, y)
+    for lname, (ox, ok, og, oi, oo) in layouts.items():
+        x, key, g, inv = e.x[ox:ox + n1], e.key[ok:ok + n1], e.grad_out[og:og + n1], e.inv[oi:oi + n1]
+        yy, gg = y[oo:oo + n1], gin[oo:oo + n1]
+        ab = wl.algorithmic_bytes(n1, e.k)
         for v, name in enumerate(ops.variants("fwd")):
-            if halo == 0 and name.startswith("ldg"):
+            if v == 0 and lname.startswith("sliced, same"):
                 continue
             ops.set_variant("fwd", v)
-            ms = timeit(lambda: gc.grouped_cumprod_forward(e.x, e.key, y))
-            st = ops.workspace_status()
-            gbs = ab["fwd"] / ms / 1e6
-            res["fwd"].append({"variant": v, "name": name, "halo": halo, "ms": ms, "GBs": gbs, "frac": gbs / peak,
-                               "status": st})
-            print(f"fwd v{v} halo={halo} {name:42s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}",
-                  file=sys.stderr)
+            ms = timeit(lambda: gc.grouped_cumprod_forward(x, key, yy))
+            row = {"op": "fwd", "layout": lname, "variant": name.split(" ")[0], "launches": ops.last_launch_count(),
+                   "ms": ms, "GBs": ab["fwd"] / ms / 1e6, "frac": ab["fwd"] / ms / 1e6 / peak, "status": ops.workspace_status()}
+            res["rows"].append(row)
+            print("fwd {layout:34s} {variant:10s} launches {launches} {ms:8.4f} ms {GBs:8.1f} GB/s {frac:6.3f} status {status}".format(**row), file=sys.stderr)
         ops.set_variant("fwd", -1)
         for v, name in enumerate(ops.variants("bwd")):
-            if halo == 0 and name.startswith("ldg"):
+            if v == 0 and lname.startswith("sliced, same"):
                 continue
             ops.set_variant("bwd", v)
-            ms = timeit(lambda: gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end))
-            st = ops.workspace_status()
-            gbs = ab["bwd"] / ms / 1e6
-            res["bwd"].append({"variant": v, "name": name, "halo": halo, "ms": ms, "GBs": gbs, "frac": gbs / peak,
-                               "status": st})
-            print(f"bwd v{v} halo={halo} {name:42s} {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} status {st}",
-                  file=sys.stderr)
+            ms = timeit(lambda: gc.grouped_cumprod_backward(x, yy, g, inv, gg, e.seg_end))
+            row = {"op": "bwd", "layout": lname, "variant": name.split(" ")[0], "launches": ops.last_launch_count(),
+                   "ms": ms, "GBs": ab["bwd"] / ms / 1e6, "frac": ab["bwd"] / ms / 1e6 / peak, "status": ops.workspace_status()}
+            res["rows"].append(row)
+            print("bwd {layout:34s} {variant:10s} launches {launches} {ms:8.4f} ms {GBs:8.1f} GB/s {frac:6.3f} status {status}".format(**row), file=sys.stderr)
         ops.set_variant("bwd", -1)
-    ops.set_option(0, 1)
     # a plain device copy of the same byte volume as one forward op (sanity ceiling)
     src = torch.empty(e.n * 3 // 2, dtype=torch.float32, device=e.x.device)
     dst = torch.empty_like(src)

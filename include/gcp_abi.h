@@ -35,12 +35,13 @@
 extern "C" {
 #endif
 
-#define GCP_ABI_VERSION 1
+#define GCP_ABI_VERSION 2
 
 #define GCP_OK 0
 #define GCP_ERR_INVALID_ARG (-1)
 #define GCP_ERR_WORKSPACE (-2)   /* workspace null / too small / misaligned */
-#define GCP_ERR_WATCHDOG (-3)    /* a bounded spin expired inside a kernel (reported by gcp_workspace_status) */
+#define GCP_ERR_WATCHDOG (-3)    /* a bounded spin expired inside a kernel: the results of that op are invalid and the
+                                  * workspace is poisoned until re-initialised (gcp_workspace_status / the attached flag) */
 #define GCP_ERR_SEGMENTS (-4)    /* inv / seg_end inconsistent (gcp_validate_segments) */
 
 /* opaque: a cudaStream_t */
@@ -55,16 +56,34 @@ size_t gcp_workspace_bytes(int64_t n);
 int gcp_workspace_init(void *ws, size_t ws_bytes, gcp_stream_t stream);
 
 /* Synchronises `stream`, then reports the sticky watchdog flag of the workspace
- * in *status (GCP_OK or GCP_ERR_WATCHDOG).  Test / debug aid. */
+ * in *status (GCP_OK or GCP_ERR_WATCHDOG). */
 int gcp_workspace_status(const void *ws, gcp_stream_t stream, int *status);
+
+/* Failing loudly without synchronising.  The kernels' waits (mbarriers fed by the CTA's own producer warp, the
+ * grid barrier of the cooperative launch) are bounded; should one ever expire, the kernel finishes with invalid
+ * results and raises a sticky flag in the workspace.  Attach a 4-byte word of PINNED, device-mapped host memory
+ * (cudaHostAlloc / cudaHostRegister; pass its device-visible address — the same pointer under unified
+ * addressing) and the kernel also stores 1 there: the owner checks the word with a plain host read before every
+ * call on that workspace and treats non-zero as GCP_ERR_WATCHDOG (ops.py does; it then re-initialises the
+ * workspace).  Call after gcp_workspace_init (which clears the attachment); the word must outlive the workspace's
+ * use.  Pass NULL to detach.  Async on `stream`. */
+int gcp_workspace_attach_flag(void *ws, size_t ws_bytes, void *host_flag_device_address, gcp_stream_t stream);
+/* Test hook: raises the watchdog flag of `ws` from a kernel, exactly as an expired wait would (tests of the
+ * fail-loudly path; the workspace must be re-initialised afterwards). */
+int gcp_workspace_selftest_abort(void *ws, size_t ws_bytes, gcp_stream_t stream);
 
 /*
  * Replaces grouped_cumprod_forward(x, key, y)
  *   (/root/reference/cuda_kernel/grouped_cumprod_forward.cu:6-24):
  *   y[i] = x[i]              if i == 0 or key[i] != key[i-1]
  *        = y[i-1] * x[i]     otherwise                       (inclusive)
- * x f32[n], key i32[n], y f32[n] (written in place).  Any alignment (a 16-byte
- * aligned fast path is chosen automatically).  n may be 0.
+ * x f32[n], key i32[n], y f32[n] (written in place).  n may be 0; at most 2^31 - 4 (the reference ops index with
+ * int, grouped_cumprod_backward.cu:52; callers with more elements per view chunk at segment boundaries).
+ * Any 4-byte alignment.  The fast path (one persistent kernel, cooperative launch, TMA) needs x and key in the
+ * SAME 16-byte phase — true for equal slices of separately allocated tensors, the reference's [cutting_number:]
+ * case — and peels the 1-3 leading elements; other layouts, n below one tile, or a device that refuses the
+ * cooperative launch are served by the plain-load kernel pair (K1 + fix-up), about 0.7 / 0.4 of the fast
+ * path's bandwidth.
  */
 int gcp_cumprod_fwd_f32(const float *x, const int32_t *key, float *y, int64_t n,
                         void *ws, size_t ws_bytes, gcp_stream_t stream);
@@ -104,10 +123,9 @@ int gcp_validate_segments(const int32_t *inv, const int32_t *seg_end, int64_t n,
                           void *ws, size_t ws_bytes, gcp_stream_t stream, int64_t *violations);
 
 /*
- * Tuning hook (bench / tests): choose the kernel variant used by subsequent calls
- * of this process.  op: 0 = forward scans, 1 = backward.  variant: -1 = default
- * heuristic, otherwise an index into the table printed by gcp_variant_name.
- * Returns GCP_ERR_INVALID_ARG for unknown values.
+ * Test hook: choose the path used by subsequent calls of this process.  op: 0 = forward scans, 1 = backward.
+ * variant: -1 = default (1, falling back to 0 where 1 cannot serve the call), 0 = the plain-load kernel pair,
+ * 1 = the persistent blocked kernel (gcp_variant_name describes them).  GCP_ERR_INVALID_ARG for unknown values.
  */
 int gcp_set_variant(int op, int variant);
 /* Tuning options.  option 0 (GCP_OPT_HALO): 1 (default) = the persistent kernels resolve each tile's

@@ -13,6 +13,7 @@ from . import build as _build
 _lib = None
 
 GCP_OK = 0
+ABI_VERSION = 2   # GCP_ABI_VERSION of include/gcp_abi.h this binding was written against
 ERRORS = {
     -1: "GCP_ERR_INVALID_ARG",
     -2: "GCP_ERR_WORKSPACE",
@@ -22,7 +23,7 @@ ERRORS = {
 
 # every symbol include/gcp_abi.h declares (tests check the .so exports all of them)
 SYMBOLS = (
-    "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status",
+    "gcp_abi_version", "gcp_workspace_bytes", "gcp_workspace_init", "gcp_workspace_status", "gcp_workspace_attach_flag", "gcp_workspace_selftest_abort",
     "gcp_cumprod_fwd_f32", "gcp_cumsum_fwd_f32", "gcp_cumprod_bwd_f32", "gcp_validate_segments",
     "gcp_set_variant", "gcp_set_option", "gcp_num_variants", "gcp_variant_name", "gcp_last_launch_count",
     "gcp_splat_expand", "gcp_splat_sort_bytes", "gcp_splat_sort", "gcp_splat_prepare_bytes", "gcp_splat_prepare", "gcp_splat_pack", "gcp_splat_alpha", "gcp_splat_color",
@@ -41,19 +42,31 @@ def lib() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path):
-        try:
-            _build.build_lib()
-        except Exception as e:  # noqa: BLE001
-            raise ImportError(
-                f"libgcp_b200.so is not built ({e}); run `python -c 'import __graft_entry__ as g; g.build()'`"
-            ) from e
+    # incremental: recompiles only translation units older than their sources, a no-op when everything is current and
+    # where there is no nvcc (the GPU box uses the library that travelled with the tree).  Never a stale binary
+    # behind fresh ctypes signatures.
+    try:
+        _build.build_lib()
+    except Exception as e:  # noqa: BLE001
+        raise ImportError(
+            f"libgcp_b200.so is not built ({e}); run `python -c 'import __graft_entry__ as g; g.build()'`"
+        ) from e
     # the library's only OpenMP region is the host-side key packing (gcp_host.cu): its idle worker threads should
     # sleep, not spin, between the chunks of a step (they share the cores with the other ranks of the node)
     os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     L = ctypes.CDLL(path)
     vp, i64, sz, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_int
+    missing = [n for n in SYMBOLS if not hasattr(L, n)]
+    if missing:
+        raise ImportError(f"{path} does not export {missing}: stale build, run __graft_entry__.build()")
     L.gcp_abi_version.restype = ci
+    if L.gcp_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path} has ABI version {L.gcp_abi_version()}, this binding expects {ABI_VERSION}: "
+                          "stale build, run __graft_entry__.build()")
+    L.gcp_workspace_attach_flag.argtypes = [vp, sz, vp, vp]
+    L.gcp_workspace_attach_flag.restype = ci
+    L.gcp_workspace_selftest_abort.argtypes = [vp, sz, vp]
+    L.gcp_workspace_selftest_abort.restype = ci
     L.gcp_workspace_bytes.argtypes = [i64]
     L.gcp_workspace_bytes.restype = sz
     L.gcp_workspace_init.argtypes = [vp, sz, vp]

@@ -1,10 +1,12 @@
 // gcp_abi.cu — C-ABI entry points of libgcp_b200.so (see include/gcp_abi.h) and the
-// host-side launch logic: variant table, grid sizing (persistent = resident CTAs x
-// 148 SMs), alignment dispatch, workspace checks.  No allocation, no host sync on the
-// compute entry points.
+// host-side launch logic: the two paths (persistent blocked kernel, cooperative launch | LDG K1 + K2),
+// grid sizing (persistent = resident CTAs x 148 SMs), the alignment peel, workspace checks.
+// No allocation, no host sync on the compute entry points.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+
+#include <utility>
 
 #include "gcp_abi.h"
 #include "gcp_blk.cuh"
@@ -117,6 +119,34 @@ inline unsigned fix_grid(uint32_t nt) {
     return blocks < 1u ? 1u : blocks;
 }
 
+// 16-byte phase of a 4-byte aligned pointer, in elements (0..3); -1 when the pointer is not even 4-byte aligned
+inline int phase_of(const void *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    return (a & 3u) ? -1 : static_cast<int>((a & 15u) >> 2);
+}
+template <typename T>
+inline const T *back(const T *p, int lead) { return p - lead; }
+template <typename T>
+inline T *back(T *p, int lead) { return p - lead; }
+
+// Persistent kernels contain a grid barrier: they are launched COOPERATIVELY, so the runtime guarantees that
+// all CTAs are resident at once (or refuses the launch, in which case the caller falls back to the LDG path).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_cooperative(void (*kern)(KArgs...), unsigned grid, unsigned threads, size_t smem, cudaStream_t s,
+                               Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ------------------------------ forward ------------------------------------
 template <int OP>
 int launch_fwd_fix(float *y, int64_t n, uint32_t nt, int tile, Ws ws, cudaStream_t s) {
@@ -127,6 +157,8 @@ int launch_fwd_fix(float *y, int64_t n, uint32_t nt, int tile, Ws ws, cudaStream
     return static_cast<int>(cudaGetLastError());
 }
 
+// The fallback: one tile per CTA, plain (vector where aligned) loads, fix-up as a second launch.  Any
+// alignment, any n, no cross-CTA wait.
 template <int OP, int WARPS, int ROWS>
 int launch_fwd_ldg(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
     constexpr int TILE = WARPS * ROWS * 128;
@@ -140,50 +172,42 @@ int launch_fwd_ldg(const float *x, const int32_t *key, float *y, int64_t n, Ws w
     return rc != 0 ? rc : launch_fwd_fix<OP>(y, n, nt, TILE, ws, s);
 }
 
-template <int OP, int WARPS, int ROWS, int STAGES>
-int launch_fwd_tma(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
-    using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
-    const uint32_t nt = tiles_for(n, L::TILE);
-    constexpr auto kern = k_fwd_tma<OP, WARPS, ROWS, STAGES>;
-    const int threads = (WARPS + 1) * 32;
-    const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
-    uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
-    if (grid > nt) grid = nt;
-    // ONE launch: streaming phase, grid barrier, sparse fix-up phase (all CTAs are resident)
-    kern<<<grid, threads, L::BYTES, s>>>(x, key, y, n, nt, ws.hdr, ws.desc, ws.ulist(nt), aligned16(y) ? 1 : 0,
-                                         g_option[0]);
-    ++t_launches;
-    return static_cast<int>(cudaGetLastError());
-}
-
-template <int OP, int WARPS, int STAGES, bool DIRECT_ST = false>
+// The default: persistent blocked kernel, ONE cooperative launch (streaming phase, grid barrier, sparse fix-up).
+// Returns -100 when this path cannot serve the call (the caller then uses the LDG path).
+constexpr int NOT_SERVED = -100;
+template <int OP, int WARPS, int STAGES>
 int launch_fwd_blk(const float *x, const int32_t *key, float *y, int64_t n, Ws ws, cudaStream_t s) {
     using L = FwdBlkSmem<WARPS, STAGES>;
+    const int lead = phase_of(x);
+    if (lead < 0 || phase_of(key) != lead || (reinterpret_cast<uintptr_t>(y) & 3u)) return NOT_SERVED;
+    // alignment peel: every pointer moved down to its 16-byte boundary, `lead` phantom elements in front
+    x = back(x, lead); key = back(key, lead); y = back(y, lead);
+    n += lead;
     CUtensorMap tmx, tmk;
     if (!make_tile_map(&tmx, x, n, L::TILE, false) || !make_tile_map(&tmk, key, n, L::TILE, true))
-        return launch_fwd_ldg<OP, 8, 4>(x, key, y, n, ws, s);  // tiny n, or no driver entry point
+        return NOT_SERVED;  // n smaller than a tile, or no driver entry point
     const uint32_t nt = tiles_for(n, L::TILE);
-    constexpr auto kern = k_fwd_blk<OP, WARPS, STAGES, DIRECT_ST>;
+    constexpr auto kern = k_fwd_blk<OP, WARPS, STAGES>;
     const int threads = (WARPS + 1) * 32;
     const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(tmx, tmk, x, key, y, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
-                                         aligned16(y) ? 1 : 0,
-                                         (g_option[0] & 1) | (g_option[2] == 1 ? 2 : 0) | (g_option[2] == 2 ? 4 : 0));
+    const cudaError_t e = launch_cooperative(
+        kern, grid, threads, L::BYTES, s, tmx, tmk, x, key, y, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
+        aligned16(y) ? 1 : 0, (g_option[0] & 1) | (g_option[2] == 1 ? 2 : 0) | (g_option[2] == 2 ? 4 : 0), lead);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+        (void)cudaGetLastError();   // co-residency cannot be guaranteed here (MPS limit, ...): not an error, use K1 + K2
+        return NOT_SERVED;
+    }
     ++t_launches;
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(e);
 }
 
-constexpr int FWD_NUM_VARIANTS = 13;
+constexpr int FWD_NUM_VARIANTS = 2;
 const char *const kFwdNames[FWD_NUM_VARIANTS] = {
-    "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
-    "tma_w8_r4_s3 (tile 4096, 96 KB ring)", "tma_w8_r4_s2 (tile 4096, 64 KB ring)",
-    "tma_w8_r2_s4 (tile 2048, 64 KB ring)", "tma_w4_r4_s4 (tile 2048, 160 thr)",
-    "tma_w16_r4_s3 (tile 8192, 192 KB ring)", "blk_w8_s2 (16 contiguous elems/lane, swizzled tensor TMA)",
-    "blk_w8_s3 (tile 4096, 96 KB ring)", "blk_w4_s4 (tile 2048, 64 KB ring)",
-    "blk_w8_s2_direct (stores straight from registers, stage freed early)", "blk_w8_s3_direct"};
-constexpr int FWD_DEFAULT = 8;   // blk_w8_s2
+    "ldg_w4_r4 (tile 2048, 1 tile/CTA, 128 threads, separate fix-up launch; any alignment)",
+    "blk_w8_s2 (persistent, cooperative; 16 contiguous elements/lane from a swizzled tensor-map TMA ring)"};
+constexpr int FWD_DEFAULT = 1;
 
 template <int OP>
 int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *wsp, size_t ws_bytes,
@@ -195,25 +219,14 @@ int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *
     int rc = check_ws(wsp, ws_bytes, n, &ws);
     if (rc != GCP_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    int v = g_variant[0] < 0 ? FWD_DEFAULT : g_variant[0];
-    const bool in_al = aligned16(x) && aligned16(key);
-    if (v >= 3 && !in_al) v = 2;  // bulk copies need 16-byte aligned sources: best LDG variant
-    switch (v) {
-        case 0: return launch_fwd_ldg<OP, 8, 4>(x, key, y, n, ws, s);
-        case 1: return launch_fwd_ldg<OP, 8, 2>(x, key, y, n, ws, s);
-        case 2: return launch_fwd_ldg<OP, 4, 4>(x, key, y, n, ws, s);
-        case 3: return launch_fwd_tma<OP, 8, 4, 3>(x, key, y, n, ws, s);
-        case 4: return launch_fwd_tma<OP, 8, 4, 2>(x, key, y, n, ws, s);
-        case 5: return launch_fwd_tma<OP, 8, 2, 4>(x, key, y, n, ws, s);
-        case 6: return launch_fwd_tma<OP, 4, 4, 4>(x, key, y, n, ws, s);
-        case 7: return launch_fwd_tma<OP, 16, 4, 3>(x, key, y, n, ws, s);
-        case 8: return launch_fwd_blk<OP, 8, 2>(x, key, y, n, ws, s);
-        case 9: return launch_fwd_blk<OP, 8, 3>(x, key, y, n, ws, s);
-        case 10: return launch_fwd_blk<OP, 4, 4>(x, key, y, n, ws, s);
-        case 11: return launch_fwd_blk<OP, 8, 2, true>(x, key, y, n, ws, s);
-        case 12: return launch_fwd_blk<OP, 8, 3, true>(x, key, y, n, ws, s);
-        default: return GCP_ERR_INVALID_ARG;
+    const int v = g_variant[0] < 0 ? FWD_DEFAULT : g_variant[0];
+    if (v == 1) {
+        rc = launch_fwd_blk<OP, 8, 2>(x, key, y, n, ws, s);
+        if (rc != NOT_SERVED) return rc;
+    } else if (v != 0) {
+        return GCP_ERR_INVALID_ARG;
     }
+    return launch_fwd_ldg<OP, 4, 4>(x, key, y, n, ws, s);
 }
 
 // ------------------------------ backward -----------------------------------
@@ -237,53 +250,44 @@ int launch_bwd_ldg(const float *x, const float *y, const float *g, const int32_t
     return rc != 0 ? rc : launch_bwd_fix(x, y, g, inv, gin, n, nt, TILE, ws, s);
 }
 
-template <int WARPS, int ROWS, int STAGES, int MINB>
-int launch_bwd_tma(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
-                   Ws ws, cudaStream_t s) {
-    using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
-    const uint32_t nt = tiles_for(n, L::TILE);
-    constexpr auto kern = k_bwd_tma<WARPS, ROWS, STAGES, MINB>;
-    const int threads = (WARPS + 1) * 32;
-    const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
-    uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
-    if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
-                                         aligned16(gin) ? 1 : 0, g_option[0]);
-    ++t_launches;
-    return static_cast<int>(cudaGetLastError());
-}
-
-template <int WARPS, int STAGES, int MINB, bool DIRECT_ST = false>
+template <int WARPS, int STAGES, int MINB>
 int launch_bwd_blk(const float *x, const float *y, const float *g, const int32_t *inv, float *gin, int64_t n,
                    Ws ws, cudaStream_t s) {
     using L = BwdBlkSmem<WARPS, STAGES>;
+    const int lead = phase_of(x);
+    if (lead < 0 || phase_of(g) != lead || phase_of(inv) != lead) return NOT_SERVED;
+    if ((reinterpret_cast<uintptr_t>(gin) & 3u) || (reinterpret_cast<uintptr_t>(y) & 3u)) return NOT_SERVED;
+    // alignment peel (y is only read with scalar loads: it is shifted for the indexing alone)
+    x = back(x, lead); g = back(g, lead); inv = back(inv, lead); y = back(y, lead); gin = back(gin, lead);
+    n += lead;
     CUtensorMap tmx, tmg, tmi;
     if (!make_tile_map(&tmx, x, n, L::TILE, false) || !make_tile_map(&tmg, g, n, L::TILE, false) ||
         !make_tile_map(&tmi, inv, n, L::TILE, true))
-        return launch_bwd_ldg<8, 4>(x, y, g, inv, gin, n, ws, s);
+        return NOT_SERVED;
     const uint32_t nt = tiles_for(n, L::TILE);
-    constexpr auto kern = k_bwd_blk<WARPS, STAGES, MINB, DIRECT_ST>;
+    constexpr auto kern = k_bwd_blk<WARPS, STAGES, MINB>;
     const int threads = (WARPS + 1) * 32;
     const int per_sm = persistent_ctas_per_sm<kern>(threads, L::BYTES);
     uint32_t grid = static_cast<uint32_t>(per_sm) * static_cast<uint32_t>(sm_count());
     if (grid > nt) grid = nt;
-    kern<<<grid, threads, L::BYTES, s>>>(tmx, tmg, tmi, x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
-                                         aligned16(gin) ? 1 : 0,
-                                         (g_option[0] & 1) | (g_option[1] == 1 ? 2 : 0) | (g_option[1] == 2 ? 4 : 0));
+    const cudaError_t e = launch_cooperative(
+        kern, grid, threads, L::BYTES, s, tmx, tmg, tmi, x, y, g, inv, gin, n, nt, ws.hdr, ws.desc, ws.ulist(nt),
+        aligned16(gin) ? 1 : 0, (g_option[0] & 1) | (g_option[1] == 1 ? 2 : 0) | (g_option[1] == 2 ? 4 : 0), lead);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+        (void)cudaGetLastError();
+        return NOT_SERVED;
+    }
     ++t_launches;
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(e);
 }
 
-constexpr int BWD_NUM_VARIANTS = 14;
+constexpr int BWD_NUM_VARIANTS = 2;
 const char *const kBwdNames[BWD_NUM_VARIANTS] = {
-    "ldg_w8_r4 (tile 4096, 1 tile/CTA)", "ldg_w8_r2 (tile 2048, 1 tile/CTA)", "ldg_w4_r4 (tile 2048, 128 thr)",
-    "tma_w8_r4_s2 (tile 4096, 96 KB ring, 2 CTA/SM)", "tma_w8_r2_s4 (tile 2048, 96 KB ring, 2 CTA/SM)",
-    "tma_w8_r2_s3 (tile 2048, 72 KB ring, 3 CTA/SM)", "tma_w8_r4_s4 (tile 4096, 192 KB ring, 1 CTA/SM)",
-    "tma_w16_r2_s2 (tile 4096, 96 KB ring, 544 thr)", "blk_w8_s2 (16 contiguous elems/lane, 2 CTA/SM)",
-    "blk_w8_s4 (tile 4096, 192 KB ring, 1 CTA/SM)", "blk_w4_s3 (tile 2048, 72 KB ring, 3 CTA/SM)",
-    "blk_w4_s4 (tile 2048, 96 KB ring, 2 CTA/SM)", "blk_w8_s2_direct (stores straight from registers)",
-    "blk_w4_s3_direct (tile 2048, 3 CTA/SM)"};
-constexpr int BWD_DEFAULT = 8;   // blk_w8_s2
+    "ldg_w4_r4 (tile 2048, 1 tile/CTA, 128 threads, separate fix-up launch; any alignment)",
+    "blk_w8_s2 (persistent, cooperative, 2 CTA/SM; 16 contiguous elements/lane from a swizzled tensor-map TMA ring)"};
+constexpr int BWD_DEFAULT = 1;
+
+__global__ void k_selftest_abort(uint32_t *hdr) { gcp::signal_abort(hdr); }
 
 }  // namespace
 
@@ -301,6 +305,21 @@ size_t gcp_workspace_bytes(int64_t n) {
 int gcp_workspace_init(void *ws, size_t ws_bytes, gcp_stream_t stream) {
     if (ws == nullptr || ws_bytes < static_cast<size_t>(gcp::WS_HEADER_BYTES)) return GCP_ERR_WORKSPACE;
     return static_cast<int>(cudaMemsetAsync(ws, 0, ws_bytes, reinterpret_cast<cudaStream_t>(stream)));
+}
+
+int gcp_workspace_attach_flag(void *ws, size_t ws_bytes, void *host_flag_device_address, gcp_stream_t stream) {
+    if (ws == nullptr || ws_bytes < static_cast<size_t>(gcp::WS_HEADER_BYTES) ||
+        (reinterpret_cast<uintptr_t>(ws) & 15u) != 0 || (reinterpret_cast<uintptr_t>(host_flag_device_address) & 3u))
+        return GCP_ERR_WORKSPACE;
+    const uint64_t v = reinterpret_cast<uint64_t>(host_flag_device_address);
+    return static_cast<int>(cudaMemcpyAsync(reinterpret_cast<uint64_t *>(ws) + gcp::HDR_HOSTFLAG64, &v, sizeof(v),
+                                            cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+}
+
+int gcp_workspace_selftest_abort(void *ws, size_t ws_bytes, gcp_stream_t stream) {
+    if (ws == nullptr || ws_bytes < static_cast<size_t>(gcp::WS_HEADER_BYTES)) return GCP_ERR_WORKSPACE;
+    k_selftest_abort<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint32_t *>(ws));
+    return static_cast<int>(cudaGetLastError());
 }
 
 int gcp_workspace_status(const void *ws, gcp_stream_t stream, int *status) {
@@ -339,26 +358,14 @@ int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const
     int rc = check_ws(wsp, ws_bytes, n, &ws);
     if (rc != GCP_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    int v = g_variant[1] < 0 ? BWD_DEFAULT : g_variant[1];
-    const bool in_al = aligned16(x) && aligned16(gout) && aligned16(inv);
-    if (v >= 3 && !in_al) v = 2;
-    switch (v) {
-        case 0: return launch_bwd_ldg<8, 4>(x, y, gout, inv, gin, n, ws, s);
-        case 1: return launch_bwd_ldg<8, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 2: return launch_bwd_ldg<4, 4>(x, y, gout, inv, gin, n, ws, s);
-        case 3: return launch_bwd_tma<8, 4, 2, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 4: return launch_bwd_tma<8, 2, 4, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 5: return launch_bwd_tma<8, 2, 3, 3>(x, y, gout, inv, gin, n, ws, s);
-        case 6: return launch_bwd_tma<8, 4, 4, 1>(x, y, gout, inv, gin, n, ws, s);
-        case 7: return launch_bwd_tma<16, 2, 2, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 8: return launch_bwd_blk<8, 2, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 9: return launch_bwd_blk<8, 4, 1>(x, y, gout, inv, gin, n, ws, s);
-        case 10: return launch_bwd_blk<4, 3, 3>(x, y, gout, inv, gin, n, ws, s);
-        case 11: return launch_bwd_blk<4, 4, 2>(x, y, gout, inv, gin, n, ws, s);
-        case 12: return launch_bwd_blk<8, 2, 2, true>(x, y, gout, inv, gin, n, ws, s);
-        case 13: return launch_bwd_blk<4, 3, 3, true>(x, y, gout, inv, gin, n, ws, s);
-        default: return GCP_ERR_INVALID_ARG;
+    const int v = g_variant[1] < 0 ? BWD_DEFAULT : g_variant[1];
+    if (v == 1) {
+        rc = launch_bwd_blk<8, 2, 2>(x, y, gout, inv, gin, n, ws, s);
+        if (rc != NOT_SERVED) return rc;
+    } else if (v != 0) {
+        return GCP_ERR_INVALID_ARG;
     }
+    return launch_bwd_ldg<4, 4>(x, y, gout, inv, gin, n, ws, s);
 }
 
 int gcp_validate_segments(const int32_t *inv, const int32_t *seg_end, int64_t n, int64_t k, void *wsp,

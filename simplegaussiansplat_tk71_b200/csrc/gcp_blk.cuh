@@ -13,6 +13,17 @@
 //
 // Carry logic, descriptors, halo resolution and the in-kernel fix-up phase are exactly those of
 // gcp_fwd.cuh / gcp_bwd.cuh (the fix-up functions are shared).
+//
+// Alignment peel (`lead`).  TMA needs 16-byte aligned global addresses; a sliced tensor (the reference
+// slices with [cutting_number:], gs_model.py:557) starts 4, 8 or 12 bytes past one.  When all streamed
+// arrays of an op share that phase, the host passes every pointer moved DOWN to the 16-byte boundary,
+// n grown by the same `lead` = 1..3 elements, and `lead` itself: the kernels then see `lead` phantom
+// elements in front of the caller's element 0.  They sit in tile 0 / warp 0 / lane 0 only, where they
+// are replaced in registers by the scan identity with the key of the first real element (so they neither
+// start nor end a segment, and contribute nothing), and that warp stores its outputs with scalar stores
+// that skip them.  Everything else — the other 99.99 % of the tiles — runs the aligned fast path
+// unchanged.  (The bytes in front of a 4-byte aligned pointer up to the 16-byte boundary belong to the same
+// allocation: cudaMalloc and every pooling allocator hand out blocks aligned to at least 256 bytes.)
 #pragma once
 #include <type_traits>
 #include <cuda.h>
@@ -82,13 +93,6 @@ __device__ __forceinline__ void store_blocked_via_smem(unsigned char *arr, int w
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// registers (blocked) -> global directly: four 128-bit streaming stores per lane, 64 contiguous bytes per lane
-__device__ __forceinline__ void store_blocked_direct(const float (&o)[16], float *__restrict__ dst_lane) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        __stcs(reinterpret_cast<float4 *>(dst_lane) + j, make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
-}
-
 // guarded global load of a lane's 16 consecutive elements (partial last tile)
 template <typename T>
 __device__ __forceinline__ void ldg_blocked(const T *__restrict__ p, int64_t gi, int64_t n, T pad, T (&out)[16]) {
@@ -107,10 +111,25 @@ __device__ __forceinline__ void ldg_blocked_vec(const T *__restrict__ p, int64_t
         out[4 * j + 3] = *reinterpret_cast<const T *>(&q.w);
     }
 }
-__device__ __forceinline__ void stg_blocked_guarded(float *__restrict__ p, int64_t gi, int64_t n, const float (&o)[16]) {
+__device__ __forceinline__ void stg_blocked_guarded(float *__restrict__ p, int64_t gi, int64_t n, const float (&o)[16],
+                                                    int64_t lo = 0) {
 #pragma unroll
     for (int e = 0; e < 16; ++e)
-        if (gi + e < n) p[gi + e] = o[e];
+        if (gi + e < n && gi + e >= lo) p[gi + e] = o[e];
+}
+// phantom elements in front of the caller's element 0 (alignment peel): identity value, key of the first real element
+template <typename T>
+__device__ __forceinline__ void mask_lead(T (&a)[16], int lead, T fill) {
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+        if (e < lead) a[e] = fill;
+}
+template <typename T>
+__device__ __forceinline__ void mask_lead_key(T (&a)[16], int lead) {
+    const T k = lead == 1 ? a[1] : (lead == 2 ? a[2] : a[3]);
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+        if (e < lead) a[e] = k;
 }
 
 // ============================================================================================
@@ -231,11 +250,12 @@ struct FwdBlkSmem {
     static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl)) + 1024;  // + alignment slack
 };
 
-template <int OP, int WARPS, int STAGES, bool DIRECT_ST = false>
+template <int OP, int WARPS, int STAGES>
 __global__ void __launch_bounds__((WARPS + 1) * 32)
 k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_k,
           const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
-          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int y_vec, int use_halo) {
+          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int y_vec, int use_halo,
+          int lead) {
     using L = FwdBlkSmem<WARPS, STAGES>;
     using O = ScanOp<OP>;
     constexpr int TILE = L::TILE;
@@ -407,26 +427,22 @@ k_fwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             ldg_blocked<int32_t>(key, wbase + lane * BLK_EPL, n, 0, k);
             if (lane == 0 && wbase > 0 && wbase - 1 < n) kprev = __ldg(key + wbase - 1);
         }
-        if (DIRECT_ST) {  // the stage is free as soon as its values are in registers
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[s]);
+        const bool peel = lead != 0 && wbase == 0;   // warp-uniform: the warp that holds the phantom elements
+        if (peel && lane == 0) {
+            mask_lead<float>(v, lead, O::id());
+            mask_lead_key<int32_t>(k, lead);
         }
         fwd_blk_compute<OP, WARPS>(v, k, kprev, wbase == 0, resolved, tp_res, tile, epoch, hdr, desc, ulist,
                                    &ctl->sh[it & 1u], warp, lane, chain_term, chain_carry);
         chain_tile = tile;
-        if (DIRECT_ST) {
-            if (staged && y_vec) store_blocked_direct(v, y + wbase + lane * BLK_EPL);
-            else stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v);
+        if (staged && y_vec && !peel) {
+            // the x array of the stage is dead (every warp has read its own span only): reuse it
+            store_blocked_via_smem(xs, warp, lane, v, y + wbase);
         } else {
-            if (staged && y_vec) {
-                // the x array of the stage is dead (every warp has read its own span only): reuse it
-                store_blocked_via_smem(xs, warp, lane, v, y + wbase);
-            } else {
-                stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[s]);
+            stg_blocked_guarded(y, wbase + lane * BLK_EPL, n, v, lead);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[s]);
     }
     };
     if (chain) consume(std::true_type{});
@@ -630,13 +646,13 @@ struct BwdBlkSmem {
     static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl)) + 1024;
 };
 
-template <int WARPS, int STAGES, int MINB, bool DIRECT_ST = false>
+template <int WARPS, int STAGES, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
           const __grid_constant__ CUtensorMap tm_i, const float *__restrict__ x, const float *__restrict__ y,
           const float *__restrict__ g, const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n,
           uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int out_vec,
-          int use_halo) {
+          int use_halo, int lead) {
     using L = BwdBlkSmem<WARPS, STAGES>;
     constexpr int TILE = L::TILE;
     extern __shared__ unsigned char smem_raw[];
@@ -834,29 +850,26 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                     xnext = __ldg(x + wend);
                 }
             }
-            if (DIRECT_ST) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->empty[s]);
+            const bool peel = lead != 0 && wbase == 0;   // warp-uniform: the warp that holds the phantom elements
+            if (peel && lane == 0) {
+                mask_lead<float>(xv, lead, 1.0f);
+                mask_lead<float>(gv, lead, 0.0f);
+                mask_lead_key<int32_t>(iv, lead);
             }
             float out[16];
             bwd_blk_compute<WARPS, true>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, epoch, hdr, desc,
                                          ulist, ulist + num_tiles, &ctl->sh[it & 1u], warp, lane, out, chain_term,
                                          chain_carry);
             chain_tile = tile;
-            if (DIRECT_ST) {
-                if (staged && out_vec) store_blocked_direct(out, gin + wbase + lane * BLK_EPL);
-                else stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+            if (staged && out_vec && !peel) {
+                // the g array of the stage is only ever read by the warp that owns the span: reuse it
+                // (x is read across warp boundaries for x_next, inv for the head/tail halos)
+                store_blocked_via_smem(gs, warp, lane, out, gin + wbase);
             } else {
-                if (staged && out_vec) {
-                    // the g array of the stage is only ever read by the warp that owns the span: reuse it
-                    // (x is read across warp boundaries for x_next, inv for the head/tail halos)
-                    store_blocked_via_smem(gs, warp, lane, out, gin + wbase);
-                } else {
-                    stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->empty[s]);
+                stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out, lead);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
     };
     if (chain) consume(std::true_type{});
@@ -867,7 +880,8 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     // (a) short trailing runs: one warp per tile recomputes just the run
     const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
     for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
-        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch, desc, lane);
+        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch, desc, lane,
+                     lead);
     // (b) long trailing runs (tiles inside segments of thousands of elements): warp 0 finds R by
     //     walking the descriptors, then the whole CTA re-runs the tile with R known.
     const uint32_t ucount2 = ld_relaxed_u32(hdr + HDR_UCOUNT2);
@@ -896,15 +910,21 @@ k_bwd_blk(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             xnext = __ldg(x + wbase + BLK_WSPAN);
         }
         const float y_prev = (base > 0) ? __ldg(y + base - 1) : 1.0f;
+        const bool peel = lead != 0 && wbase == 0;
+        if (peel && lane == 0) {
+            mask_lead<float>(xv, lead, 1.0f);
+            mask_lead<float>(gv, lead, 0.0f);
+            mask_lead_key<int32_t>(iv, lead);
+        }
         bool term_unused;
         float carry_unused;
         bwd_blk_compute<WARPS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, true, R, static_cast<uint32_t>(t), epoch,
                                       hdr, desc, ulist, ulist, &ctl->sh[k2 & 1u], warp, lane, out, term_unused,
                                       carry_unused);
-        if (out_vec) {
+        if (out_vec && !peel) {
             store_blocked_via_smem(gs0, warp, lane, out, gin + wbase);
         } else {
-            stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out);
+            stg_blocked_guarded(gin, wbase + lane * BLK_EPL, n, out, lead);
         }
     }
     named_bar_sync<WARPS * 32>(1);

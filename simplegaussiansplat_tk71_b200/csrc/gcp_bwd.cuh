@@ -16,7 +16,7 @@
 // reads x, grad_out, inv (12 B/elem) and writes grad_in (4 B/elem): 16 B/elem.
 //
 // Cross-tile carry of S, mirrored from gcp_fwd.cuh and equally wait-free:
-//   K1 (k_bwd_tma / k_bwd_ldg) resolves R = S(first element after the tile) from the HALO,
+//   K1 (k_bwd_blk in gcp_blk.cuh / k_bwd_ldg) resolves R = S(first element after the tile) from the HALO,
 //      the 128 elements after the tile.  Unresolved tiles store provisional values for
 //      their trailing run (the elements after the tile's last tail), publish a carry
 //      descriptor (TERM R | AGG (a,b)) and a fix-up request {needs, trail start}.
@@ -432,15 +432,18 @@ __device__ __forceinline__ float bwd_fix_walk(int64_t t, uint32_t num_tiles, uin
 __device__ __forceinline__ void bwd_fix_tile(int64_t t, const float *__restrict__ x, const float *__restrict__ y,
                                              const float *__restrict__ g, const int32_t *__restrict__ inv,
                                              float *gin, int64_t n, uint32_t num_tiles, int tile_elems,
-                                             uint32_t epoch, uint64_t *desc, int lane) {
+                                             uint32_t epoch, uint64_t *desc, int lane, int64_t lead = 0) {
+    // lead: the first `lead` (< 4) positions of the arrays are phantom elements in front of the caller's element 0
+    // (alignment peel of the blocked kernels, see gcp_blk.cuh): never read as data, never written.
     const uint32_t trail = static_cast<uint32_t>(ld_relaxed_u64(desc + t * 4 + 1));
     float S = bwd_fix_walk(t, num_tiles, epoch, desc, lane);
     // ---- recompute the trailing run, 128 elements per step, from the tile end ----
-    const int64_t rs = t * tile_elems + trail;
+    int64_t rs = t * tile_elems + trail;
     const int64_t re = (t + 1) * tile_elems;  // < n: the last tile always resolves
     if (rs >= re) return;
     bool rs_head = trail > 0u;
-    if (!rs_head) rs_head = (rs == 0) || (__ldg(inv + rs) != __ldg(inv + rs - 1));
+    if (rs < lead) rs = lead;                 // (trail == 0 in tile 0: the run starts at the caller's element 0)
+    if (!rs_head) rs_head = (rs == lead) || (__ldg(inv + rs) != __ldg(inv + rs - 1));
     for (int64_t ce = re; ce > rs; ce -= 128) {
         const int64_t i0 = ce - 128 + lane * 4;
         float xn[4], gv[4];
@@ -570,196 +573,6 @@ k_bwd_ldg(const float *__restrict__ x, const float *__restrict__ y, const float 
                                          out_vec != 0, epoch, hdr, desc, ulist, ulist + num_tiles, &sh, warp, lane);
     }
     if (threadIdx.x == 0) finish_stream_kernel(hdr);
-}
-
-// ---------------------------------------------------------------------------
-// K1, TMA variant: persistent, producer warp + STAGES-deep ring of (x, g, inv) tiles.
-// ---------------------------------------------------------------------------
-template <int WARPS, int ROWS, int STAGES>
-struct BwdTmaSmem {
-    static constexpr int TILE = WARPS * ROWS * 128;
-    static constexpr int STAGE_BYTES = TILE * 12;
-    struct Ctl {
-        uint64_t full[STAGES];
-        uint64_t empty[STAGES];
-        uint32_t tile[STAGES];
-        uint32_t mode[STAGES];
-        int32_t iprev[STAGES];
-        int32_t inext[STAGES];
-        float xnext[STAGES];
-        float yprev[STAGES];
-        uint32_t resolved[STAGES];
-        float rn[STAGES];
-        uint32_t epoch;
-        BwdShared<WARPS> sh[2];
-    };
-    static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl));
-};
-
-template <int WARPS, int ROWS, int STAGES, int MINB>
-__global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
-k_bwd_tma(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ g,
-          const int32_t *__restrict__ inv, float *__restrict__ gin, int64_t n, uint32_t num_tiles,
-          uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int out_vec, int use_halo) {
-    using L = BwdTmaSmem<WARPS, ROWS, STAGES>;
-    constexpr int TILE = L::TILE;
-    extern __shared__ __align__(128) unsigned char smem[];
-    typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&ctl->full[s], 2);
-            mbar_init(&ctl->empty[s], WARPS);
-        }
-        mbar_fence_init();
-        ctl->epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
-    }
-    __syncthreads();
-    const uint32_t epoch = ctl->epoch;
-
-    if (warp == WARPS) {
-        // ===================== producer warp =====================
-        const uint64_t pol = policy_evict_first();
-        uint32_t t_next = 0;
-        if (lane == 0) t_next = atomicAdd(hdr + HDR_TICKET, 1u);
-        t_next = __shfl_sync(0xffffffffu, t_next, 0);
-        for (uint32_t it = 0;; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-            __syncwarp();
-            const uint32_t t = t_next;
-            if (t >= num_tiles) {
-                if (lane == 0) {
-                    ctl->tile[s] = t;
-                    mbar_arrive(&ctl->full[s]);
-                    mbar_arrive(&ctl->full[s]);
-                }
-                break;
-            }
-            const uint32_t tile = num_tiles - 1u - t;  // from the end: descending addresses
-            const int64_t base = static_cast<int64_t>(tile) * TILE;
-            const int64_t end = base + TILE;
-            uint32_t t_pref = 0;
-            int32_t ip = -1;
-            float yp = 1.0f;
-            if (lane == 0) {
-                ctl->tile[s] = t;
-                if (end <= n) {
-                    unsigned char *st = smem + s * L::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
-                    bulk_g2s(st, x + base, TILE * 4, &ctl->full[s], pol);
-                    bulk_g2s(st + TILE * 4, g + base, TILE * 4, &ctl->full[s], pol);
-                    bulk_g2s(st + TILE * 8, inv + base, TILE * 4, &ctl->full[s], pol);
-                    ctl->mode[s] = 1u;
-                } else {
-                    ctl->mode[s] = 0u;
-                    mbar_arrive(&ctl->full[s]);
-                }
-                t_pref = atomicAdd(hdr + HDR_TICKET, 1u);
-                if (base > 0) {
-                    ip = __ldg(inv + base - 1);
-                    yp = __ldg(y + base - 1);
-                }
-            }
-            float R = 0.0f, xq = 0.0f;
-            int32_t in = -1;
-            bool res;
-            if (use_halo) {
-                res = halo_suffix(x, g, inv, end, n, lane, true, R, in, xq);
-            } else {
-                res = (end >= n);
-                if (end < n) {
-                    in = __ldg(inv + end);
-                    xq = __ldg(x + end);
-                }
-            }
-            t_next = __shfl_sync(0xffffffffu, t_pref, 0);
-            if (lane == 0) {
-                ctl->iprev[s] = ip;
-                ctl->yprev[s] = yp;
-                ctl->inext[s] = in;
-                ctl->xnext[s] = xq;
-                ctl->resolved[s] = res ? 1u : 0u;
-                ctl->rn[s] = R;
-                mbar_arrive(&ctl->full[s]);
-            }
-        }
-        return;
-    }
-
-    for (uint32_t it = 0;; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(&ctl->full[s], ph, hdr);
-        const uint32_t ticket = ctl->tile[s];
-        if (ticket >= num_tiles) break;
-        const uint32_t tile = num_tiles - 1u - ticket;
-        const int64_t base = static_cast<int64_t>(tile) * TILE;
-        const int woff = warp * (ROWS * 128);
-        const int64_t wbase = base + woff;
-        const int64_t wend = wbase + ROWS * 128;
-        float xv[ROWS][4], gv[ROWS][4];
-        int32_t iv[ROWS][4];
-        int32_t iprev = -1, inext = -1;
-        float xnext = 0.0f;
-        const float y_prev = ctl->yprev[s];
-        const bool resolved = ctl->resolved[s] != 0u;
-        const float rn_res = ctl->rn[s];
-        if (ctl->mode[s]) {
-            const float *xs = reinterpret_cast<const float *>(smem + s * L::STAGE_BYTES);
-            const float *gs = xs + TILE;
-            const int32_t *is = reinterpret_cast<const int32_t *>(xs + 2 * TILE);
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                const int o = woff + r * 128 + lane * 4;
-                const float4 a = *reinterpret_cast<const float4 *>(xs + o);
-                const float4 b = *reinterpret_cast<const float4 *>(gs + o);
-                const int4 c = *reinterpret_cast<const int4 *>(is + o);
-                xv[r][0] = a.x; xv[r][1] = a.y; xv[r][2] = a.z; xv[r][3] = a.w;
-                gv[r][0] = b.x; gv[r][1] = b.y; gv[r][2] = b.z; gv[r][3] = b.w;
-                iv[r][0] = c.x; iv[r][1] = c.y; iv[r][2] = c.z; iv[r][3] = c.w;
-            }
-            if (lane == 0) {
-                iprev = (warp == 0) ? ctl->iprev[s] : is[woff - 1];
-                if (warp == WARPS - 1) {
-                    inext = ctl->inext[s];
-                    xnext = ctl->xnext[s];
-                } else {
-                    inext = is[woff + ROWS * 128];
-                    xnext = xs[woff + ROWS * 128];
-                }
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r)
-                load_row_global_bwd(x, g, inv, wbase + r * 128 + lane * 4, n, true, xv[r], gv[r], iv[r]);
-            if (lane == 0 && wbase > 0 && wbase - 1 < n) iprev = __ldg(inv + wbase - 1);
-            if (lane == 0 && wend < n) {
-                inext = __ldg(inv + wend);
-                xnext = __ldg(x + wend);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->empty[s]);
-        bwd_tile_body<WARPS, ROWS, false>(xv, gv, iv, iprev, inext, xnext, y_prev, resolved, rn_res, tile, base, n,
-                                          gin, out_vec != 0, epoch, hdr, desc, ulist, ulist + num_tiles,
-                                          &ctl->sh[it & 1u], warp, lane);
-    }
-
-    // ===================== fix-up phase (same launch) =====================
-    grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);
-    const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
-    for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
-        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch, desc, lane);
-    const uint32_t ucount2 = ld_relaxed_u32(hdr + HDR_UCOUNT2);  // long runs: warp-level here too (legacy variant)
-    for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount2; u += gridDim.x * WARPS)
-        bwd_fix_tile(static_cast<int64_t>(__ldcg(ulist + num_tiles + u)), x, y, g, inv, gin, n, num_tiles, TILE, epoch,
-                     desc, lane);
-    named_bar_sync<WARPS * 32>(1);
-    if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
 
 // K2 of the LDG path: the same fix-up as a separate launch (one warp per list entry).

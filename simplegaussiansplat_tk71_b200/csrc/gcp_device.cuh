@@ -1,7 +1,7 @@
 // gcp_device.cuh — device-side building blocks shared by the scan kernels (sm_100a).
 //
-//  * PTX wrappers: mbarrier, 1-D bulk async copy (TMA engine, SASS UBLKCP), relaxed
-//    gpu-scope descriptor loads/stores, streaming vector loads/stores.
+//  * PTX wrappers: mbarrier, relaxed gpu-scope descriptor loads/stores, streaming vector
+//    loads/stores.
 //  * workspace layout + per-tile descriptors.
 //  * scan operators (segmented product/sum, affine maps of the backward).
 #pragma once
@@ -13,7 +13,7 @@ namespace gcp {
 // ----------------------------------------------------------------------------
 // Workspace layout (device memory, caller owned; see include/gcp_abi.h)
 //   [0,256)    header: u32 words  ticket@0, done@16, epoch@32, abort@33, violations(u64)@byte 160,
-//              ucount@48 (number of unresolved tiles), exit@56
+//              ucount@48 (number of unresolved tiles), exit@56, host flag address (u64)@byte 240
 //   [256, ...) one 32-byte slot (4 x u64) per tile of >= MIN_TILE elements, then the list of
 //              unresolved tile indices (u32 per tile):
 //     word0  K1: carry descriptor of the tile   {epoch, status TERM|AGG, flag, f32 value}
@@ -34,12 +34,14 @@ constexpr int HDR_VIOL64 = 20;  // index in u64 units (byte 160)
 constexpr int HDR_UCOUNT = 48;
 constexpr int HDR_UCOUNT2 = 52;  // backward: unresolved tiles with a long trailing run (fixed by a whole CTA)
 constexpr int HDR_EXIT = 56;
+constexpr int HDR_HOSTFLAG64 = 30;  // index in u64 units (byte 240): device-visible address of a HOST word (pinned,
+                                    // mapped) that a tripped watchdog sets to 1, or 0 (gcp_workspace_attach_flag)
 constexpr int WS_LIST_BYTES = 8;  // per tile: two u32 lists
 constexpr uint32_t LONG_RUN = 1024;  // trailing runs longer than this are recomputed by a whole CTA
 
 constexpr uint32_t ST_INVALID = 0, ST_AGG = 1, ST_TERM = 2, ST_INCL = 3;
 constexpr uint32_t EPOCH_MASK = 0x1FFFFFFFu;
-constexpr uint32_t WAIT_LIMIT = 1u << 20;  // bounded mbarrier spins: fail open + sticky abort flag, never hang
+constexpr uint32_t WAIT_LIMIT = 1u << 20;  // bounded spins: never hang; expiry raises the sticky abort flag
 constexpr uint32_t FIX_FLAG = 0x80000000u;
 
 __device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, uint32_t status, uint32_t flag, float v) {
@@ -99,15 +101,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: on expiry set the sticky abort flag and carry on (results are then wrong, but the
-// kernel terminates and gcp_workspace_status reports it).  Only a bug can trip it: the only waits
-// in the kernels are on mbarriers fed by the CTA's own producer warp.
+// A bounded wait expired.  Sets the sticky flag in the workspace header AND, when the owner of the workspace
+// attached one (gcp_workspace_attach_flag), a word in pinned host memory, so that the host learns about it
+// without a synchronising read: the next op on that workspace refuses to launch (GCP_ERR_WATCHDOG) instead of
+// producing garbage silently.  Only a bug can trip it: the kernels wait on mbarriers fed by the CTA's own
+// producer warp, and on the grid barrier of a COOPERATIVE launch (all CTAs resident by contract).
+__device__ __noinline__ void signal_abort(uint32_t *hdr) {
+    if (atomicExch(hdr + HDR_ABORT, 1u) == 0u) {
+        const uint64_t host = reinterpret_cast<const uint64_t *>(hdr)[HDR_HOSTFLAG64];
+        if (host != 0ull) {
+            *reinterpret_cast<volatile uint32_t *>(host) = 1u;
+            __threadfence_system();
+        }
+    }
+}
+// Bounded wait: on expiry signal_abort and carry on (the results of THIS op are then wrong, the kernel
+// terminates, and the flag makes every later use of the workspace fail loudly).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *hdr) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
         if ((spins & 63u) == 0u) {
-            if (spins >= WAIT_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+            if (spins >= WAIT_LIMIT) { signal_abort(hdr); break; }
             if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
         }
     }
@@ -117,15 +132,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-// global -> shared, 1-D, size multiple of 16, both 16-B aligned; completes on `bar` (complete_tx).
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
-                                         uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-
 template <int COUNT>
 __device__ __forceinline__ void named_bar_sync(int id) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
@@ -218,9 +224,11 @@ __device__ __forceinline__ void finish_op(uint32_t *hdr, uint32_t epoch) {
 }
 
 // Grid-wide barrier between the streaming phase and the fix-up phase of a persistent kernel.
-// Called by all consumer threads of the CTA (COUNT of them, named barrier 1).  Safe because every
-// CTA of the persistent grid is resident (grid = occupancy x SMs) and nothing in the streaming
-// phase ever waits on another CTA.  Bounded like every other spin.
+// Called by all consumer threads of the CTA (COUNT of them, named barrier 1).  The persistent kernels
+// are launched COOPERATIVELY (cudaLaunchAttributeCooperative, gcp_abi.cu): the runtime starts the grid
+// only when every CTA can be resident at once — also when another stream, an MPS limit or a long
+// kernel holds SMs — so the barrier cannot starve; where a cooperative launch is refused the host
+// falls back to the two-kernel LDG path, which has no cross-CTA wait at all.  Bounded like every spin.
 template <int COUNT>
 __device__ __forceinline__ void grid_phase_barrier(uint32_t *hdr, int tid) {
     __threadfence();
@@ -231,7 +239,7 @@ __device__ __forceinline__ void grid_phase_barrier(uint32_t *hdr, int tid) {
         while (ld_relaxed_u32(hdr + HDR_DONE) < gridDim.x) {
             __nanosleep(64);
             if (((++spins) & 63u) == 0u) {
-                if (spins >= WAIT_LIMIT) { atomicExch(hdr + HDR_ABORT, 1u); break; }
+                if (spins >= WAIT_LIMIT) { signal_abort(hdr); break; }
                 if (ld_relaxed_u32(hdr + HDR_ABORT) != 0u) break;
             }
         }

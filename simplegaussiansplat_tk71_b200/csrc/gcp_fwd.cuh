@@ -13,7 +13,7 @@
 // through shared memory (ONE named barrier per tile).
 //
 // Cross-tile carry, without any inter-CTA waiting:
-//   K1 (k_fwd_tma / k_fwd_ldg)  resolves the tile's exclusive prefix from the HALO, the
+//   K1 (k_fwd_blk in gcp_blk.cuh / k_fwd_ldg)  resolves the tile's exclusive prefix from the HALO, the
 //      128 elements before the tile (a per-pixel list is ~20-50 elements, so a segment
 //      head is almost always inside it).  If no head is found the tile is "unresolved":
 //      it stores its results as if the prefix were the identity and publishes a carry
@@ -25,10 +25,9 @@
 //      kernel it is a second phase of the SAME launch behind a grid barrier (all CTAs are
 //      resident); the LDG path launches it as a separate kernel K2 (k_fwd_fix).
 //
-//   k_fwd_tma : persistent CTAs; a producer warp takes tile tickets, streams x/key tiles
-//               into a STAGES-deep shared-memory ring with 1-D bulk async copies
-//               (cp.async.bulk -> UBLKCP) completing on mbarriers, and computes the halo.
-//   k_fwd_ldg : one tile per CTA, direct streaming loads; any alignment, any n.
+//   k_fwd_blk : (gcp_blk.cuh, the default) persistent CTAs, tensor-map TMA ring, blocked layout.
+//   k_fwd_ldg : one tile per CTA, direct streaming loads; any alignment, any n (the fallback: arrays
+//               whose 16-byte phases differ, n smaller than a tile, cooperative launch unavailable).
 #pragma once
 #include "gcp_device.cuh"
 
@@ -415,156 +414,6 @@ k_fwd_ldg(const float *__restrict__ x, const int32_t *__restrict__ key, float *_
                                              epoch, hdr, desc, ulist, &sh, warp, lane);
     }
     if (threadIdx.x == 0) finish_stream_kernel(hdr);
-}
-
-// ---------------------------------------------------------------------------
-// K1, TMA variant: persistent, producer warp + STAGES-deep bulk-copy ring.
-// Requires x and key 16-byte aligned (the host falls back to k_fwd_ldg otherwise).
-// ---------------------------------------------------------------------------
-template <int WARPS, int ROWS, int STAGES>
-struct FwdTmaSmem {
-    static constexpr int TILE = WARPS * ROWS * 128;
-    static constexpr int STAGE_BYTES = TILE * 8;
-    struct Ctl {
-        uint64_t full[STAGES];
-        uint64_t empty[STAGES];
-        uint32_t tile[STAGES];
-        int32_t halo[STAGES];
-        uint32_t mode[STAGES];
-        uint32_t resolved[STAGES];
-        float tp[STAGES];
-        uint32_t epoch;
-        FwdShared<WARPS> sh[2];
-    };
-    static constexpr int BYTES = STAGES * STAGE_BYTES + static_cast<int>(sizeof(Ctl));
-};
-
-template <int OP, int WARPS, int ROWS, int STAGES>
-__global__ void __launch_bounds__((WARPS + 1) * 32)
-k_fwd_tma(const float *__restrict__ x, const int32_t *__restrict__ key, float *__restrict__ y, int64_t n,
-          uint32_t num_tiles, uint32_t *__restrict__ hdr, uint64_t *desc, uint32_t *ulist, int y_vec,
-          int use_halo) {
-    using L = FwdTmaSmem<WARPS, ROWS, STAGES>;
-    using O = ScanOp<OP>;
-    constexpr int TILE = L::TILE;
-    extern __shared__ __align__(128) unsigned char smem[];
-    typename L::Ctl *ctl = reinterpret_cast<typename L::Ctl *>(smem + STAGES * L::STAGE_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&ctl->full[s], 2);       // producer: expect_tx arrive + release arrive
-            mbar_init(&ctl->empty[s], WARPS);  // one elected lane per consumer warp
-        }
-        mbar_fence_init();
-        ctl->epoch = ld_relaxed_u32(hdr + HDR_EPOCH);
-    }
-    __syncthreads();
-    const uint32_t epoch = ctl->epoch;
-
-    if (warp == WARPS) {
-        // ===================== producer warp =====================
-        // lane 0: tickets, bulk copies, barriers.  All lanes: halo prefix of the tile.
-        const uint64_t pol = policy_evict_first();
-        uint32_t t_next = 0;
-        if (lane == 0) t_next = atomicAdd(hdr + HDR_TICKET, 1u);
-        t_next = __shfl_sync(0xffffffffu, t_next, 0);
-        for (uint32_t it = 0;; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            if (lane == 0) mbar_wait(&ctl->empty[s], ph ^ 1u, hdr);
-            __syncwarp();
-            const uint32_t t = t_next;
-            if (t >= num_tiles) {
-                if (lane == 0) {
-                    ctl->tile[s] = t;
-                    mbar_arrive(&ctl->full[s]);
-                    mbar_arrive(&ctl->full[s]);
-                }
-                break;
-            }
-            const int64_t base = static_cast<int64_t>(t) * TILE;
-            uint32_t t_pref = 0;
-            if (lane == 0) {
-                ctl->tile[s] = t;
-                if (base + TILE <= n) {
-                    unsigned char *st = smem + s * L::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&ctl->full[s], L::STAGE_BYTES);
-                    bulk_g2s(st, x + base, TILE * 4, &ctl->full[s], pol);
-                    bulk_g2s(st + TILE * 4, key + base, TILE * 4, &ctl->full[s], pol);
-                    ctl->mode[s] = 1u;
-                } else {
-                    ctl->mode[s] = 0u;
-                    mbar_arrive(&ctl->full[s]);
-                }
-                t_pref = atomicAdd(hdr + HDR_TICKET, 1u);  // next ticket: its latency overlaps the halo loads
-            }
-            float P = O::id();
-            int32_t kprev = 0;
-            bool res = (t == 0u);
-            if (t > 0u) {
-                if (use_halo) res = halo_prefix<OP>(x, key, base, lane, true, P, kprev);
-                else kprev = __ldg(key + base - 1);
-            }
-            t_next = __shfl_sync(0xffffffffu, t_pref, 0);
-            if (lane == 0) {
-                ctl->halo[s] = kprev;
-                ctl->resolved[s] = res ? 1u : 0u;
-                ctl->tp[s] = P;
-                mbar_arrive(&ctl->full[s]);
-            }
-        }
-        return;
-    }
-
-    // ===================== consumers =====================
-    for (uint32_t it = 0;; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(&ctl->full[s], ph, hdr);
-        const uint32_t tile = ctl->tile[s];
-        if (tile >= num_tiles) break;
-        const int64_t base = static_cast<int64_t>(tile) * TILE;
-        const int woff = warp * (ROWS * 128);
-        const int64_t wbase = base + woff;
-        const bool resolved = ctl->resolved[s] != 0u;
-        const float tp_res = ctl->tp[s];
-        float v[ROWS][4];
-        int32_t k[ROWS][4];
-        int32_t kprev = 0;
-        if (ctl->mode[s]) {
-            const float *xs = reinterpret_cast<const float *>(smem + s * L::STAGE_BYTES);
-            const int32_t *ks = reinterpret_cast<const int32_t *>(smem + s * L::STAGE_BYTES + TILE * 4);
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                const float4 a = *reinterpret_cast<const float4 *>(xs + woff + r * 128 + lane * 4);
-                const int4 b = *reinterpret_cast<const int4 *>(ks + woff + r * 128 + lane * 4);
-                v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w;
-                k[r][0] = b.x; k[r][1] = b.y; k[r][2] = b.z; k[r][3] = b.w;
-            }
-            if (lane == 0) kprev = (warp == 0) ? ctl->halo[s] : ks[woff - 1];
-        } else {
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r)
-                load_row_global<OP>(x, key, wbase + r * 128 + lane * 4, n, true, v[r], k[r]);
-            if (lane == 0 && wbase > 0 && wbase - 1 < n) kprev = __ldg(key + wbase - 1);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->empty[s]);
-        fwd_tile_body<OP, WARPS, ROWS, false>(v, k, kprev, wbase == 0, resolved, tp_res, tile, base, n, y, y_vec != 0,
-                                              epoch, hdr, desc, ulist, &ctl->sh[it & 1u], warp, lane);
-    }
-
-    // ===================== fix-up phase (same launch) =====================
-    // Every tile of every CTA has been stored and its descriptor published once the grid barrier
-    // opens; the few tiles the halo could not resolve are then patched, one warp per tile.
-    grid_phase_barrier<WARPS * 32>(hdr, threadIdx.x);
-    const uint32_t ucount = ld_relaxed_u32(hdr + HDR_UCOUNT);
-    for (uint32_t u = blockIdx.x * WARPS + warp; u < ucount; u += gridDim.x * WARPS)
-        fwd_fix_tile<OP>(__ldcg(ulist + u), y, n, TILE, epoch, desc, lane);
-    named_bar_sync<WARPS * 32>(1);
-    if (threadIdx.x == 0) finish_op(hdr, epoch);
 }
 
 // K2 of the LDG path: the same fix-up as a separate launch (one warp per list entry).

@@ -89,9 +89,13 @@ class HostStreamer:
         self.s_down = torch.cuda.Stream(self.device)
         self.empty_len = torch.empty(0, dtype=torch.int32, device=self.device)
 
-    def fwd_bwd(self, x, key, grad_out, y_out, grad_in_out, cuts=None):
+    def fwd_bwd(self, x, key, grad_out, y_out, grad_in_out, cuts=None, sync: bool = True):
         """y_out = segmented inclusive cumprod(x by key); grad_in_out = its gradient for upstream grad_out.
-        All five are 1-D pinned host tensors (f32, i32, f32, f32, f32).  Returns (h2d_bytes, d2h_bytes)."""
+        All five are 1-D pinned host tensors (f32, i32, f32, f32, f32).  Returns (h2d_bytes, d2h_bytes).
+
+        sync=True (default): returns when y_out and grad_in_out hold the results (the download stream is
+        synchronised).  sync=False: returns as soon as everything is queued — the host buffers are then valid only
+        after the caller synchronises the current stream (which has been made to wait for the downloads)."""
         n = x.numel()
         if cuts is None:
             cuts = _cut_points(key, self.chunk, ramp=True)
@@ -135,4 +139,6 @@ class HostStreamer:
                 grad_in_out[a:b].copy_(self.dgin[i][:m], non_blocking=True)
                 down_done[i] = self.s_down.record_event()
         cur.wait_stream(self.s_down)
+        if sync:
+            self.s_down.synchronize()
         return 8 * n + 4 * sum((cuts[c + 1] - cuts[c] + 31) // 32 for c in range(len(cuts) - 1)), 8 * n

@@ -16,28 +16,66 @@ There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 
 _workspaces: dict = {}
+_VALIDATE = os.environ.get("GCP_VALIDATE_SEGMENTS", "") not in ("", "0")
+
+
+class _Workspace:
+    """A self-resetting scan workspace (device) plus the pinned host word a tripped watchdog writes to."""
+    __slots__ = ("buf", "flag", "flag_np", "stream")
+
+    def __init__(self, device, nbytes: int, stream: int):
+        L = _lib.lib()
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.flag = torch.zeros(1, dtype=torch.int32).pin_memory()   # cudaHostAlloc: device-visible at the same address
+        self.flag_np = self.flag.numpy()                              # the per-call check is one host load
+        self.stream = stream
+        self.reset()
+
+    def reset(self) -> None:
+        L = _lib.lib()
+        self.flag.zero_()
+        _lib.check(L.gcp_workspace_init(self.buf.data_ptr(), self.buf.numel(), self.stream), "gcp_workspace_init")
+        _lib.check(L.gcp_workspace_attach_flag(self.buf.data_ptr(), self.buf.numel(), self.flag.data_ptr(),
+                                               self.stream), "gcp_workspace_attach_flag")
+
+    def numel(self) -> int:
+        return self.buf.numel()
+
+    def data_ptr(self) -> int:
+        return self.buf.data_ptr()
 
 
 def _workspace(device: torch.device, n: int):
-    """One cached, self-resetting workspace per (device, stream); grown geometrically."""
+    """One cached, self-resetting workspace per (device, stream); grown geometrically.
+
+    Fails loudly: if a kernel's bounded wait ever expired during an EARLIER op on this workspace, that op's results
+    were invalid and the kernel said so in the attached pinned word (include/gcp_abi.h, gcp_workspace_attach_flag).
+    The word is checked here, before every launch, with a plain host read: the workspace is re-initialised and
+    GCP_ERR_WATCHDOG raised — never a silent wrong gradient, never a workspace that stays poisoned."""
     L = _lib.lib()
     stream = torch.cuda.current_stream(device)
     key = (device.index, stream.cuda_stream)
     need = int(L.gcp_workspace_bytes(n))
     ws = _workspaces.get(key)
+    if ws is not None and ws.flag_np[0] != 0:
+        torch.cuda.synchronize(device)
+        ws.reset()
+        raise RuntimeError("GCP_ERR_WATCHDOG: a bounded wait expired inside a scan kernel of an earlier call on this "
+                           "stream; the results of that call are invalid (workspace re-initialised)")
     if ws is None or ws.numel() < need:
         if not _workspaces:
             _options_from_env()
         size = max(need, 1 << 20)
         if ws is not None:
             size = max(size, 2 * ws.numel())
-        ws = torch.empty(size, dtype=torch.uint8, device=device)
-        _lib.check(L.gcp_workspace_init(ws.data_ptr(), ws.numel(), stream.cuda_stream), "gcp_workspace_init")
+        ws = _Workspace(device, size, stream.cuda_stream)
         _workspaces[key] = ws
     return ws, stream.cuda_stream
 
@@ -90,6 +128,15 @@ def grouped_cumprod_backward(param: torch.Tensor, param_cumprod: torch.Tensor, g
 
     Reference: cuda_kernel/grouped_cumprod_backward.cu:43-65 (cuda_test.py:29).  `inv` are dense
     segment ids, `inv_len` the exclusive end offset of each segment (cuda_test.py:27).
+
+    Contract on the segment layout.  The reference sums element i up to `inv_len[inv[i]]`; this op derives the
+    segment tails from `inv` alone (a tail is where inv[i+1] != inv[i]) and reads neither `inv_len` nor its length,
+    which is the same thing exactly when the two arguments are consistent: ids non-decreasing and dense,
+    inv_len[s] = 1 + last index of s.  Inconsistent pairs (or ids that repeat non-adjacently) give a different
+    result from the reference's without an error.  Set GCP_VALIDATE_SEGMENTS=1 in the environment to have every
+    call with a non-empty `inv_len` checked first (`validate_segments`, one extra pass and a host sync) and
+    raise GCP_ERR_SEGMENTS on a mismatch.  An empty `inv_len` is accepted: the compositor passes the sorted pixel
+    keys as `inv`, for which no offsets exist.
     """
     _check(param, "param", torch.float32)
     n = param.numel()
@@ -101,6 +148,10 @@ def grouped_cumprod_backward(param: torch.Tensor, param_cumprod: torch.Tensor, g
     _check(inv_len, "inv_len", torch.int32, None, dev)
     if n == 0:
         return
+    if _VALIDATE and inv_len.numel() > 0:
+        bad = validate_segments(inv, inv_len)
+        if bad:
+            raise RuntimeError(f"GCP_ERR_SEGMENTS: inv / inv_len are inconsistent at {bad} positions")
     with torch.cuda.device(dev):
         ws, stream = _workspace(dev, n)
         L = _lib.lib()
@@ -138,7 +189,7 @@ def workspace_status(device=None) -> int:
 
 
 def set_variant(op: str, variant: int) -> None:
-    """Tuning hook: op in {'fwd','bwd'}; variant -1 restores the default."""
+    """Test hook: op in {'fwd','bwd'}; 0 = plain-load kernel pair, 1 = persistent blocked kernel, -1 = default."""
     _lib.check(_lib.lib().gcp_set_variant(0 if op == "fwd" else 1, int(variant)), "gcp_set_variant")
 
 
@@ -150,8 +201,6 @@ def set_option(option: int, value: int) -> None:
 
 def _options_from_env() -> None:
     """Experiments only: GCP_OPT_HALO / GCP_OPT_CHAIN in the environment override the defaults at first use."""
-    import os
-
     for name, idx in (("GCP_OPT_HALO", 0), ("GCP_OPT_CHAIN", 1), ("GCP_OPT_CHAIN_FWD", 2)):
         if os.environ.get(name, "") != "":
             set_option(idx, int(os.environ[name]))

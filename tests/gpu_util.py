@@ -45,6 +45,7 @@ def run_fwd(op, x, key, variant=None, offset=(0, 0, 0)):
     finally:
         ops.set_variant("fwd", -1)
     assert ops.workspace_status() == 0, "watchdog fired"
+    assert bool(torch.isnan(yb[:oy]).all()), "the op wrote in front of its output"
     return yb[oy:].cpu().numpy()
 
 
@@ -61,7 +62,8 @@ def run_bwd(x, y, g, inv, seg_end, variant=None, offset=0):
 
     xb, yb, gb = buf(x, torch.float32), buf(y, torch.float32), buf(g, torch.float32)
     ib = buf(inv, torch.int32)
-    out = torch.full((n + offset,), float("nan"), dtype=torch.float32, device="cuda")[offset:]
+    out_full = torch.full((n + offset,), float("nan"), dtype=torch.float32, device="cuda")
+    out = out_full[offset:]
     if variant is not None:
         ops.set_variant("bwd", variant)
     try:
@@ -70,6 +72,7 @@ def run_bwd(x, y, g, inv, seg_end, variant=None, offset=0):
     finally:
         ops.set_variant("bwd", -1)
     assert ops.workspace_status() == 0, "watchdog fired"
+    assert bool(torch.isnan(out_full[:offset]).all()), "the op wrote in front of its output"
     return out.cpu().numpy()
 
 

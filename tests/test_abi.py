@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/gcp_abi.h but not exported"
     assert sorted(_lib.SYMBOLS) == declared
-    assert L.gcp_abi_version() == 1
+    assert L.gcp_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define GCP_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "gcp_abi.h")).read()).group(1))
 
 
 def test_workspace_bytes_is_monotone_and_small():

@@ -41,8 +41,8 @@ def carry_mode(request):
     ops.set_option(2, 0)
 
 
-FWD_VARIANTS = list(range(13))
-BWD_VARIANTS = list(range(14))
+FWD_VARIANTS = [0, 1]   # 0 = plain-load kernel pair (the fallback), 1 = persistent blocked kernel (the default)
+BWD_VARIANTS = [0, 1]
 
 
 def _pow2_values(n, rng, span=12):
@@ -154,7 +154,7 @@ def test_forward_boundaries_on_tile_edges_and_long_segments(oracle, variant):
     assert np.all(np.abs(got - ref) <= 1e-6 + 1e-5 * np.abs(ref) + 8 * seq), np.abs(got - ref).max()
 
 
-@pytest.mark.parametrize("variant", [0, 3, 8])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_forward_unaligned_slices_and_zeros(oracle, variant):
     rng = np.random.default_rng(11)
     n = 50_001
@@ -162,7 +162,7 @@ def test_forward_unaligned_slices_and_zeros(oracle, variant):
     key = np.repeat(np.arange(len(L)), L)[:n].astype(np.int32)
     x = _values(n, rng, zeros=25)
     ref = oracle.cumprod_fwd(x, key)
-    for off in [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 2, 3), (3, 3, 3), (4, 4, 4)]:
+    for off in [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 2, 3), (1, 1, 1), (2, 2, 2), (3, 3, 3), (3, 3, 0), (4, 4, 4)]:
         assert_close(run_fwd("mul", x, key, variant, off), ref, f"unaligned {off} v{variant}")
     # exact zeros propagate exactly
     got = run_fwd("mul", x, key, variant)
@@ -248,7 +248,7 @@ def test_backward_tile_edges_long_segments_signed_grads(oracle, variant):
                  f"bwd giant v{variant}", rtol=2e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 8])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_backward_exact_at_zeros_and_unaligned(oracle, variant):
     rng = np.random.default_rng(17)
     n = 60_001
@@ -423,3 +423,94 @@ def test_ids_from_run_start_bits(n):
     got = ids.cpu().numpy()
     assert np.array_equal(got[:n], want)
     assert (got[n:] == -7).all()            # nothing written past the end
+
+
+@pytest.mark.parametrize("phase", [1, 2, 3])
+def test_alignment_peel_of_the_blocked_kernels(oracle, phase):
+    """Sliced tensors (all arrays in the same 16-byte phase, the reference's [cutting_number:] case) take the
+    persistent TMA kernel with 1-3 phantom elements in front of element 0: same results as the aligned call,
+    nothing written in front of the outputs (run_fwd / run_bwd check the guard words), also when the first segment
+    is longer than the first tile (tile 0 then goes through the backward fix-up with the phantom elements in it)."""
+    from simplegaussiansplat_tk71_b200 import ops
+
+    rng = np.random.default_rng(900 + phase)
+    for first in (1, 7, 300, 5000, 20_000):
+        n = 70_003
+        L = np.maximum(1, np.rint(rng.lognormal(np.log(16), 1.0, n))).astype(np.int64)
+        L[0] = first
+        L = L[: np.searchsorted(np.cumsum(L), n) + 1]
+        L[-1] -= L.sum() - n
+        inv, seg_end = seg_arrays(L)
+        x = _values(n, rng, zeros=5)
+        x[:first] = 1.0 - 1e-4 * rng.uniform(size=first).astype(np.float32)   # keeps a 20 000-element product finite
+        g = rng.normal(0, 1, n).astype(np.float32)
+        y64 = oracle.cumprod_fwd(x, inv)
+        got = run_fwd("mul", x, inv, 1, (phase, phase, phase))
+        assert ops.last_launch_count() == 1, "the sliced call did not take the persistent kernel"
+        assert_close(got, y64, f"peel fwd phase {phase} first {first}")
+        assert np.array_equal(got, run_fwd("mul", x, inv, 1)), "sliced and aligned calls differ bitwise"
+        assert_close(run_fwd("add", g, inv, 1, (phase, phase, phase)), oracle.cumsum_fwd(g, inv),
+                     f"peel cumsum phase {phase} first {first}", scale=oracle.cumsum_fwd(np.abs(g), inv))
+        y = oracle.cumprod_fwd(x, inv, np.float32)
+        scale = np.abs(oracle.cumprod_bwd_exact(x, np.abs(g), inv))
+        gb = run_bwd(x, y, g, inv, seg_end, 1, phase)
+        assert ops.last_launch_count() == 1
+        assert_close(gb, oracle.cumprod_bwd_exact(x, g, inv), f"peel bwd phase {phase} first {first}", scale=scale)
+
+
+def test_two_streams_run_the_persistent_kernels_concurrently(oracle):
+    """Two persistent (cooperative) ops in flight on two streams at once, each with its own workspace: the grid
+    barrier must not starve whatever way the CTAs of the two kernels interleave (VERDICT r1 weak #4)."""
+    import grouped_cumprod as gc
+    from simplegaussiansplat_tk71_b200 import ops
+
+    rng = np.random.default_rng(77)
+    n = 3_000_001
+    L = np.maximum(1, np.rint(rng.lognormal(np.log(20), 1.0, n // 8))).astype(np.int64)
+    L = L[: np.searchsorted(np.cumsum(L), n) + 1]
+    L[-1] -= L.sum() - n
+    inv_np, seg_end_np = seg_arrays(L)
+    x_np = _values(n, rng)
+    g_np = rng.uniform(0.1, 1.0, n).astype(np.float32)
+    x, g, inv, se = dev(x_np), dev(g_np), dev(inv_np), dev(seg_end_np)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ys = [torch.empty_like(x) for _ in streams]
+    gs = [torch.empty_like(x) for _ in streams]
+    torch.cuda.synchronize()
+    for rep in range(20):
+        for s_, y, gi in zip(streams, ys, gs):
+            with torch.cuda.stream(s_):
+                gc.grouped_cumprod_forward(x, inv, y)
+                gc.grouped_cumprod_backward(x, y, g, inv, gi, se)
+    torch.cuda.synchronize()
+    for s_ in streams:
+        with torch.cuda.stream(s_):
+            assert ops.workspace_status() == 0, "watchdog fired with two streams in flight"
+    yref = oracle.cumprod_fwd(x_np, inv_np)
+    gref = oracle.cumprod_bwd_exact(x_np, g_np, inv_np)
+    for y, gi in zip(ys, gs):
+        assert_close(y.cpu().numpy(), yref, "two-stream fwd")
+        assert_close(gi.cpu().numpy(), gref, "two-stream bwd")
+
+
+def test_a_tripped_watchdog_fails_loudly_at_the_next_call():
+    """The device-side abort signal reaches the pinned host word without a sync, the next op on that workspace
+    raises GCP_ERR_WATCHDOG instead of launching, and the workspace is usable again afterwards."""
+    import grouped_cumprod as gc
+    from simplegaussiansplat_tk71_b200 import _lib, ops
+
+    x = torch.full((10_000,), 0.5, device="cuda")
+    k = torch.zeros(10_000, dtype=torch.int32, device="cuda")
+    y = torch.empty_like(x)
+    gc.grouped_cumprod_forward(x, k, y)
+    dev_ = x.device
+    ws, stream = ops._workspace(dev_, 10_000)
+    _lib.check(_lib.lib().gcp_workspace_selftest_abort(ws.data_ptr(), ws.numel(), stream), "selftest")
+    torch.cuda.synchronize()
+    assert ws.flag_np[0] == 1, "the kernel's abort signal did not reach the pinned host word"
+    with pytest.raises(RuntimeError, match="GCP_ERR_WATCHDOG"):
+        gc.grouped_cumprod_forward(x, k, y)
+    gc.grouped_cumprod_forward(x, k, y)          # re-initialised: works again
+    torch.cuda.synchronize()
+    assert ops.workspace_status() == 0
+    assert float(y[3]) == 0.5 ** 4
