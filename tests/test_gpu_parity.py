@@ -428,8 +428,8 @@ def test_ids_from_run_start_bits(n):
 @pytest.mark.parametrize("phase", [1, 2, 3])
 def test_alignment_peel_of_the_blocked_kernels(oracle, phase):
     """Sliced tensors (all arrays in the same 16-byte phase, the reference's [cutting_number:] case) take the
-    persistent TMA kernel with 1-3 phantom elements in front of element 0: same results as the aligned call,
-    nothing written in front of the outputs (run_fwd / run_bwd check the guard words), also when the first segment
+    persistent TMA kernel with 1-3 phantom elements in front of element 0: same results as the aligned call up to
+    fp32 association order (the tile grid is shifted by the phantom elements), nothing written in front of the outputs (run_fwd / run_bwd check the guard words), also when the first segment
     is longer than the first tile (tile 0 then goes through the backward fix-up with the phantom elements in it)."""
     from simplegaussiansplat_tk71_b200 import ops
 
@@ -448,7 +448,6 @@ def test_alignment_peel_of_the_blocked_kernels(oracle, phase):
         got = run_fwd("mul", x, inv, 1, (phase, phase, phase))
         assert ops.last_launch_count() == 1, "the sliced call did not take the persistent kernel"
         assert_close(got, y64, f"peel fwd phase {phase} first {first}")
-        assert np.array_equal(got, run_fwd("mul", x, inv, 1)), "sliced and aligned calls differ bitwise"
         assert_close(run_fwd("add", g, inv, 1, (phase, phase, phase)), oracle.cumsum_fwd(g, inv),
                      f"peel cumsum phase {phase} first {first}", scale=oracle.cumsum_fwd(np.abs(g), inv))
         y = oracle.cumprod_fwd(x, inv, np.float32)
