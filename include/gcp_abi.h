@@ -256,64 +256,68 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
                         float *g_opac, float *g_l, gcp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused compositor route (csrc/gcp_tile.cu; SURVEY.md §8f rank 1).  The same per-pixel segmented scan —
+ * Fused compositor route (csrc/gcp_tile.cu; SURVEY.md §8f ranks 1-4).  The same per-pixel segmented scan —
  * T_i = prod_{j<i}(1-alpha_j), C = sum T_i alpha_i l_i, gs_model.py:544-566 + :498-514 forward, :627-663 +
  * :733-783 backward — evaluated one pixel per lane without materialising the element lists: the image is cut
  * into tiles of gcp_tile_width() x gcp_tile_height() = 32 pixels, a box contributes one (tile, Gaussian) pair
- * per tile it touches, the pairs are stably sorted by tile (Gaussian = depth order kept inside a tile, hence
- * inside every pixel: the order of torch.sort at gs_model.py:547), and one warp walks each tile's list.
- * No float atomics: results are bitwise reproducible.  Boxes are clipped to [0,W] x [0,H].
- *   toff       i64[n+1]  exclusive offsets of the Gaussians' pairs (Gaussian-major, row-major over its tiles)
- *   rec        32-byte aligned, 64 bytes per Gaussian (packed tables)
- *   tile_start i32[gcp_tile_num_tiles(W,H)+1], pair_gid i32[P]: the tile-sorted pair list
- *   piece_plan i32[gcp_tile_plan_ints(P,W,H)]: the walk kernels' work units.  A PIECE is at most
- *              gcp_tile_piece_pairs() (default 128) consecutive pairs of one tile; a longer list is cut into
- *              several pieces walked by different warps, and the per-pixel carries between them (T forward,
- *              U backward — the segmented scan's cross-block carries) are resolved by two small combine kernels
- *   piece_state f32[gcp_tile_state_floats(P,W,H)]: aggregate, colour and carries of the pieces (forward -> backward)
- *   t_keep     f32[P*32]: exclusive T (local to its piece) of every (pair, lane), kept for the backward
- *   partial    f32[P*8]: per-pair gradient sums, Gaussian-major
+ * per tile it touches, every tile's pairs are put in Gaussian (= depth) order — the order of the reference's
+ * torch.sort at gs_model.py:547, hence the order inside every pixel list — and one warp walks each tile's list.
+ * No float atomics: results are bitwise reproducible.  No library (CUB / thrust) kernels.  Boxes are clipped
+ * to [0,W] x [0,H].
+ *
+ * A view is THREE calls — gcp_view_plan, gcp_view_render (or both at once: gcp_view_forward), gcp_view_backward —
+ * replacing custom_autograd_grouped_cumprod.forward / .backward (gs_model.py:666-692, :786-820), and lives in two
+ * caller-owned device arenas (256-byte aligned; nothing is allocated, freed or retained by the library):
+ *   plan arena  gcp_view_plan_bytes(n, W, H): pair counts / offsets per Gaussian and per tile, packed records,
+ *               work lists.  Written by gcp_view_plan + gcp_view_render, read by gcp_view_backward.
+ *   pair arena  gcp_view_pair_bytes(pair_cap, W, H): the tile-ordered pair list (every tile's segment padded to a
+ *               multiple of 16), one checkpoint of T per 16 pairs (all the backward keeps of the forward walk:
+ *               8 B per pair), the state of the pieces of long lists, the gradient partials (32 B per pair).
+ *               pair_cap >= the PADDED pair count of the view.
+ * gcp_view_plan also stores {pairs, padded pairs} into totals_host[0..1] — a pointer the DEVICE can write: pinned,
+ * mapped host memory (cudaHostAlloc; the same address under unified addressing), or NULL.  The host waits for
+ * the plan (an event behind it) and sizes the pair arena from totals_host[1]; this is the one host sync of a
+ * view, the counterpart of the reference's .item() at uitility.py:348.  A caller that already owns a pair
+ * arena it believes large enough may skip the wait and call gcp_view_forward: when the view turns out to have
+ * more padded pairs than pair_cap the render kernels do nothing (the image is NOT written) and the caller must
+ * compare totals_host[1] with pair_cap before using any result, and redo the view with a larger arena.
+ * A PIECE is at most gcp_tile_piece_pairs() (default 128) consecutive pairs of one tile: longer lists are cut
+ * into pieces walked by different warps, the per-pixel carries between them (T forward, U backward — the
+ * segmented scan's cross-block carries) resolved by two small combine kernels; the setting must not change
+ * between the render and the backward of a view.
+ * Inputs: sp/ep i32[n,2] (8-byte aligned), mean f32[n,2], lam f32[n,4], opac f32[n], l_d f32[n,3] (any 4-byte
+ * alignment), grad_image / image f32[(H+1)*(W+1)*3].  image is written completely (no need to zero it); so are
+ * g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3] (d_l = (sum d)/l, gs_model.py:763-766).  keep = 0: a render no
+ * backward will follow (no checkpoints are written).  n < 2^31 - 64, pairs < 2^31 - 64 per view: more Gaussians
+ * than that are rendered by the caller in depth-ordered chunks with the reference's per-pixel carry
+ * (gs_model.py:582-594; compositor.py does that).
  * ------------------------------------------------------------------------------------------------ */
 int gcp_tile_width(void);
 int gcp_tile_height(void);
 int gcp_tile_num_tiles(int W, int H);
 int gcp_tile_set_piece_pairs(int pairs);   /* tuning / tests: multiple of 32 */
 int gcp_tile_piece_pairs(void);
-int64_t gcp_tile_piece_cap(int64_t P, int W, int H);
-int64_t gcp_tile_plan_ints(int64_t P, int W, int H);
-int64_t gcp_tile_state_floats(int64_t P, int W, int H);
-/* toff and totals i64[1] = {P} (device memory) from the boxes; temp >= gcp_tile_prepare_bytes(n). */
-size_t gcp_tile_prepare_bytes(int64_t n);
-int gcp_tile_prepare(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, int64_t *toff, int64_t *totals,
-                     void *temp, size_t temp_bytes, gcp_stream_t stream);
-int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
-                  const int32_t *ep, const int64_t *toff, int64_t n, int W, int H, int32_t *rec,
-                  gcp_stream_t stream);
-/* pair emission + stable sort by tile + tile offsets; temp >= gcp_tile_bin_bytes(P, W, H). */
-size_t gcp_tile_bin_bytes(int64_t P, int W, int H);
-int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
-                 int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
-                 gcp_stream_t stream);
-/* The same without waiting for the pair count: `cap` is a guessed capacity (pair_gid i32[cap], temp >=
- * gcp_tile_bin_bytes(cap, W, H), piece_plan / piece_state / t_keep / partial sized for cap) and every later call of
- * the view passes cap as P.  The real count stays on the device (toff[n]); slots behind it are padded with a key that
- * sorts last.  The caller must compare the count with cap afterwards (it is in `totals` of gcp_tile_prepare): if it
- * was larger, the pairs beyond cap were dropped and the view has to be redone with gcp_tile_bin. */
-int gcp_tile_bin_speculative(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t cap, int W,
-                             int H, int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp,
-                             size_t temp_bytes, gcp_stream_t stream);
-/* image f32[(H+1)*(W+1)*3] is written completely (no need to zero it).  t_keep may be NULL when no backward will
- * follow (a render without gradients skips the 128 B per pair).  gcp_tile_piece_pairs() must not change between
- * gcp_tile_bin and the last walk of the same view. */
-int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
-                    int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream);
-int gcp_tile_backward(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
-                      const float *t_keep, float *piece_state, const float *grad_image, int64_t P, int W, int H,
-                      float *partial, gcp_stream_t stream);
-/* g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3] written completely (d_l = (sum d)/l, gs_model.py:763-766). */
-size_t gcp_tile_reduce_bytes(int64_t n);   /* scratch: the list of Gaussians with many pairs */
-int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,
-                    float *g_lam, float *g_opac, float *g_l, void *temp, size_t temp_bytes, gcp_stream_t stream);
+size_t gcp_view_plan_bytes(int64_t n, int W, int H);
+size_t gcp_view_pair_bytes(int64_t pair_cap, int W, int H);
+int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, void *plan, size_t plan_bytes,
+                  int64_t *totals_host, gcp_stream_t stream);
+int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, const float *lam, const float *opac,
+                    const float *l_d, int64_t n, int W, int H, void *plan, size_t plan_bytes, void *pairs,
+                    size_t pair_bytes, int64_t pair_cap, int keep, float *image, gcp_stream_t stream);
+int gcp_view_forward(const int32_t *sp, const int32_t *ep, const float *mean, const float *lam, const float *opac,
+                     const float *l_d, int64_t n, int W, int H, void *plan, size_t plan_bytes, void *pairs,
+                     size_t pair_bytes, int64_t pair_cap, int keep, float *image, int64_t *totals_host,
+                     gcp_stream_t stream);
+int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
+                      const float *grad_image, int64_t n, int W, int H, float *g_mean, float *g_lam, float *g_opac,
+                      float *g_l, gcp_stream_t stream);
+/* Test aid: byte offsets of the integer arrays the tests compare bit for bit with oracle/tile_oracle.py.
+ * out[0..5] (plan arena): toff i32[n+1] (Gaussian-major pair offsets), tile_count i32[tiles], tile_start
+ * i32[tiles+1] (padded), piece_extra i32[tiles], header, records; out[6..7] (pair arena): pair_gid i32[cap],
+ * extra-piece table i32[out[8]]. */
+int gcp_view_layout(int64_t n, int W, int H, int64_t pair_cap, int64_t *out);
+/* kernels launched by the last gcp_view_* call of this thread (bench.py's gpu_launches) */
+int gcp_view_last_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point helpers (csrc/gcp_host.cu, used by simplegaussiansplat_tk71_b200/host.py).  With the

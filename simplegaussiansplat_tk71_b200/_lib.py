@@ -30,9 +30,9 @@ SYMBOLS = (
     "gcp_splat_bwd_w", "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce", "gcp_splat_bwd_reduce_bytes",
     "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_set_long_list_threshold", "gcp_splat_seg_shift",
     "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
-    "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs", "gcp_tile_piece_cap",
-    "gcp_tile_plan_ints", "gcp_tile_state_floats", "gcp_tile_prepare_bytes", "gcp_tile_prepare",
-    "gcp_tile_pack", "gcp_tile_bin_bytes", "gcp_tile_bin", "gcp_tile_bin_speculative", "gcp_tile_render", "gcp_tile_backward", "gcp_tile_reduce", "gcp_tile_reduce_bytes",
+    "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs",
+    "gcp_view_plan_bytes", "gcp_view_pair_bytes", "gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward",
+    "gcp_view_backward", "gcp_view_last_launch_count",
     "gcp_host_boundary_bits", "gcp_ids_from_bits_bytes", "gcp_ids_from_bits",
 )
 
@@ -130,25 +130,17 @@ def lib() -> ctypes.CDLL:
     L.gcp_tile_set_piece_pairs.argtypes = [ci]
     L.gcp_tile_set_piece_pairs.restype = ci
     L.gcp_tile_piece_pairs.restype = ci
-    for name in ("gcp_tile_piece_cap", "gcp_tile_plan_ints", "gcp_tile_state_floats"):
-        getattr(L, name).argtypes = [i64, ci, ci]
-        getattr(L, name).restype = i64
-    L.gcp_tile_prepare_bytes.argtypes = [i64]
-    L.gcp_tile_prepare_bytes.restype = sz
-    L.gcp_tile_prepare.argtypes = [vp, vp, i64, ci, ci, vp, vp, vp, sz, vp]
-    L.gcp_tile_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
-    L.gcp_tile_bin_bytes.argtypes = [i64, ci, ci]
-    L.gcp_tile_bin_bytes.restype = sz
-    L.gcp_tile_bin.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, sz, vp]
-    L.gcp_tile_bin_speculative.argtypes = [vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp, sz, vp]
-    L.gcp_tile_bin_speculative.restype = ci
-    L.gcp_tile_render.argtypes = [vp, vp, vp, vp, i64, ci, ci, vp, vp, vp, vp]
-    L.gcp_tile_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, vp]
-    L.gcp_tile_reduce.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
-    L.gcp_tile_reduce_bytes.argtypes = [i64]
-    L.gcp_tile_reduce_bytes.restype = sz
-    for name in ("gcp_tile_prepare", "gcp_tile_pack", "gcp_tile_bin", "gcp_tile_render", "gcp_tile_backward",
-                 "gcp_tile_reduce"):
+    L.gcp_view_plan_bytes.argtypes = [i64, ci, ci]
+    L.gcp_view_plan_bytes.restype = sz
+    L.gcp_view_pair_bytes.argtypes = [i64, ci, ci]
+    L.gcp_view_pair_bytes.restype = sz
+    L.gcp_view_layout.argtypes = [i64, ci, ci, i64, ctypes.POINTER(i64)]
+    L.gcp_view_plan.argtypes = [vp, vp, i64, ci, ci, vp, sz, vp, vp]
+    L.gcp_view_render.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, sz, i64, ci, vp, vp]
+    L.gcp_view_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, sz, i64, ci, vp, vp, vp]
+    L.gcp_view_backward.argtypes = [vp, sz, vp, sz, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp]
+    for name in ("gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward", "gcp_view_backward",
+                 "gcp_view_last_launch_count"):
         getattr(L, name).restype = ci
     for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",
                  "gcp_splat_bwd_grads", "gcp_splat_bwd_elem", "gcp_splat_bwd_reduce"):

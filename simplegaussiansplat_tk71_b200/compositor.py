@@ -16,15 +16,16 @@ but not how.  Two routes, `ROUTE` below, both through the C ABI (include/gcp_abi
 fixtures the reference's own Function produced (tests/test_compositor.py):
 
   "tiles" (default, csrc/gcp_tile.cu) — the fused route: the per-pixel scan is evaluated one pixel per lane, the
-  running T in a register, without materialising the element lists.
-    forward   gcp_tile_prepare   (tile, Gaussian) pair counts, their scan, the pair total (the one host sync)
-              gcp_tile_pack      per-Gaussian tables -> one 64-byte record
-              gcp_tile_bin       pairs, stable sort by 8x4-pixel tile (depth order kept), tile offsets, pieces
-              gcp_tile_render    one warp per piece of a tile's list: alpha, T, colour; T kept per (pair, lane);
-                                 the carries between the pieces of a long list resolved by a combine kernel
-    backward  gcp_tile_backward  the lists walked in reverse: U_i, dL/dalpha_i = T_i <dL/dI, l_i> - T_i U_i and the
-                                 per-element gradients (:733-766) summed per pair
-              gcp_tile_reduce    the pairs of a Gaussian summed in pair order               (:776-783)
+  running T in a register, without materialising the element lists.  Three C-ABI calls per view, all of them
+  working inside two pooled arenas (nothing is allocated per view but the image and the four gradients):
+    forward   gcp_view_plan      (tile, Gaussian) pair counts per Gaussian and per 8x4-pixel tile, their offsets, the
+                                 pair total (the one number the host needs: it sizes the pair arena)
+              gcp_view_render    packed records; the pairs dropped into their tiles and every tile's list put in
+                                 Gaussian (= depth) order; one warp per piece of a tile's list: alpha, T, colour; a
+                                 checkpoint of T every 16 pairs is all the backward keeps (8 B per pair)
+    backward  gcp_view_backward  per 16 pairs T is recomputed from its checkpoint, then the list is walked in
+                                 reverse: U_i, dL/dalpha_i = T_i (<dL/dI, l_i> - U_i), the moments of g*dalpha over
+                                 each pair's pixels (:733-766), the pairs of a Gaussian summed in pair order (:776-783)
 
   "lists" (csrc/gcp_splat.cu + the scan ops a1 / a3) — the element-list route:
     forward   gcp_splat_pack     per-Gaussian tables -> two 32-byte records (one L2 sector per gather)
@@ -67,14 +68,6 @@ USE_PLACEMENT = True
 # "lists": the element-list route — placement, alpha, the scan ops a1/a3 (gcp_cumprod_fwd/bwd), colour, un-sort.
 # Same image and gradients within fp32 rounding (tests/test_compositor.py runs every case through both).
 ROUTE = "tiles"
-# Tile route, views rendered without plan_view: queue the whole forward on a GUESSED pair capacity (the count of the
-# last view of the same shape + 25 %) and only then wait for the real count; a guess that turns out too small costs a
-# second, exact pass.  Off by default: measured, it gains nothing — the forward of a single view is bound by the
-# host's enqueue path (~190 us for ~20 launches) followed by the render kernel, not by the wait for the count (4 us
-# once the prologue has been copied to pinned memory right behind it), and the padded sort costs what the removed
-# wait saved (0.51 ms either way at 1080p).  Kept because it is exact, tested, and the right tool once the launches
-# are captured in a graph.
-SPECULATE = False
 
 
 def _p(t):
@@ -101,7 +94,7 @@ _side_streams = {}
 
 
 class _Plan:
-    __slots__ = ("boxsize", "startpoint", "endpoint", "sp", "ep", "offs", "host", "event", "route")
+    __slots__ = ("boxsize", "startpoint", "endpoint", "sp", "ep", "offs", "host", "event", "route", "arena")
 
 
 def _aligned(t: torch.Tensor) -> torch.Tensor:
@@ -120,22 +113,94 @@ def _totals_to_host(totals, dev):
     return host, event
 
 
-def _prologue_tiles(L, dev, startpoint, endpoint, n, W, H):
-    """(tile, Gaussian) pair offsets per Gaussian and the pair count, on the current stream."""
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    sp = _aligned(startpoint.to(torch.int32))
-    ep = _aligned(endpoint.to(torch.int32))
-    toff = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    totals = torch.empty(1, dtype=torch.int64, device=dev)
-    temp = _scratch_bytes(dev, "prepare", int(L.gcp_tile_prepare_bytes(n)))
-    _lib.check(L.gcp_tile_prepare(_p(sp), _p(ep), n, W, H, _p(toff), _p(totals), _p(temp), temp.numel(), stream),
-               "gcp_tile_prepare")
-    return sp, ep, toff, totals
+# ---- tile route: pooled arenas ------------------------------------------------------------------------------
+# A view lives in two device buffers: the PLAN arena (sized by the number of Gaussians and tiles: counts, offsets,
+# packed records, work lists) and the PAIR arena (sized by the number of (tile, Gaussian) pairs: the tile-ordered
+# pair list, T checkpoints, piece state, gradient partials).  Both come from per-(device, stream) free lists and
+# go back when the view's autograd state is dropped, so a training loop allocates them once.
+class _PlanArena:
+    __slots__ = ("buf", "totals", "totals_np")
+
+    def __init__(self, dev, nbytes):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.totals = torch.zeros(2, dtype=torch.int64).pin_memory()   # {pairs, padded pairs}: the kernel writes here
+        self.totals_np = self.totals.numpy()
+
+
+class _PairArena:
+    __slots__ = ("buf", "cap")
+
+    def __init__(self, dev, cap, nbytes):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.cap = cap
+
+
+_free_plan = {}   # (device, stream) -> [_PlanArena]
+_free_pair = {}   # (device, stream) -> [_PairArena]
+
+
+def _pool_key(dev):
+    return (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _take_plan_arena(L, dev, n, W, H, key=None) -> _PlanArena:
+    need = int(L.gcp_view_plan_bytes(n, W, H))
+    free = _free_plan.setdefault(key or _pool_key(dev), [])
+    for i, a in enumerate(free):
+        if a.buf.numel() >= need:
+            return free.pop(i)
+    if free:
+        free.pop()   # too small for this view: let it go instead of hoarding
+    return _PlanArena(dev, need + need // 8)
+
+
+def _take_pair_arena(L, dev, pairs_padded, W, H) -> _PairArena:
+    free = _free_pair.setdefault(_pool_key(dev), [])
+    for i, a in enumerate(free):
+        if a.cap >= pairs_padded:
+            return free.pop(i)
+    if free:
+        free.pop()
+    cap = pairs_padded + pairs_padded // 4 + 4096      # head room: the next views of a scene fit without a new block
+    if cap >= 2 ** 31 - 64:
+        cap = max(pairs_padded, 16)
+    return _PairArena(dev, cap, int(L.gcp_view_pair_bytes(cap, W, H)))
+
+
+class _TileView:
+    """Tile route: the two arenas of a rendered view, held until its autograd state is dropped."""
+    __slots__ = ("n", "P", "Ppad", "W", "H", "plan", "pairs", "key", "piece", "keep")
+
+    def __del__(self):
+        try:
+            if self.plan is not None:
+                _free_plan.setdefault(self.key, []).append(self.plan)
+            if self.pairs is not None:
+                _free_pair.setdefault(self.key, []).append(self.pairs)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def _plan_tiles(L, dev, startpoint, endpoint, n, W, H, key=None):
+    """Queue the plan of a view (pair counts and offsets) on the current stream; returns (sp, ep, arena, event)."""
+    stream = torch.cuda.current_stream(dev)
+    sp = startpoint.to(torch.int32).contiguous()
+    ep = endpoint.to(torch.int32).contiguous()
+    if sp.data_ptr() % 8:
+        sp = sp.clone()
+    if ep.data_ptr() % 8:
+        ep = ep.clone()
+    arena = _take_plan_arena(L, dev, n, W, H, key)
+    _lib.check(L.gcp_view_plan(_p(sp), _p(ep), n, W, H, _p(arena.buf), arena.buf.numel(), _p(arena.totals),
+                               stream.cuda_stream), "gcp_view_plan")
+    event = torch.cuda.Event()
+    event.record(stream)
+    return sp, ep, arena, event
 
 
 def _prologue(L, dev, boxsize, startpoint, endpoint, n):
-    """Element offsets per Gaussian and (cell, Gaussian) pair offsets (placement cells: one image row x 2^S pixels;
-    a box contributes rows x strips-it-touches pairs) in one call, on the current stream."""
+    """List route: element offsets per Gaussian and (cell, Gaussian) pair offsets (placement cells: one image row x
+    2^S pixels; a box contributes rows x strips-it-touches pairs) in one call, on the current stream."""
     stream = torch.cuda.current_stream(dev).cuda_stream
     sp = startpoint.to(torch.int32).contiguous()
     ep = endpoint.to(torch.int32).contiguous()
@@ -169,17 +234,23 @@ def plan_view(boxsize, startpoint, endpoint, image_width=None, image_height=None
         side.wait_stream(torch.cuda.current_stream(dev))  # the inputs may still be in production
         pl = _Plan()
         pl.boxsize, pl.startpoint, pl.endpoint = boxsize, startpoint, endpoint  # keep the addresses alive
+        pl.arena = None
+        key = _pool_key(dev)   # the arena belongs to the stream that will render the view
         with torch.cuda.stream(side):
             if tiles:
-                pl.sp, pl.ep, pl.offs, totals = _prologue_tiles(L, dev, startpoint, endpoint, n, int(image_width),
-                                                                int(image_height))
+                pl.sp, pl.ep, pl.arena, pl.event = _plan_tiles(L, dev, startpoint, endpoint, n, int(image_width),
+                                                               int(image_height), key)
+                pl.offs = pl.host = None
                 pl.route = ("tiles", int(image_width), int(image_height))
             else:
                 pl.sp, pl.ep, pl.offs, totals = _prologue(L, dev, boxsize, startpoint, endpoint, n)
                 pl.route = ("lists",)
-            pl.host, pl.event = _totals_to_host(totals, dev)
+                pl.host, pl.event = _totals_to_host(totals, dev)
     while len(_plans) >= _MAX_PLANS:
-        _plans.pop(next(iter(_plans)))
+        old = _plans.pop(next(iter(_plans)))
+        if old.arena is not None:
+            old.event.synchronize()
+            _free_plan.setdefault(key, []).append(old.arena)
     _plans[(_p(boxsize), _p(startpoint), _p(endpoint), n)] = pl
 
 
@@ -189,86 +260,52 @@ class _View:
                  "goff", "rec_a", "rec_b", "seg_off", "cstart", "pgid", "btab", "P")
 
 
-_pair_counts = {}   # (device, n, W, H) -> pair count of the last view of that shape (tile route, SPECULATE)
+def _f32(t, shape=None):
+    t = t.detach().to(torch.float32)
+    if shape is not None:
+        t = t.reshape(shape)
+    return t.contiguous()
 
 
-class _TileView:
-    """Tile route: the tile-sorted pair list, the packed tables and the exclusive T of every (pair, lane)
-    (128 B per pair) kept for the backward."""
-    __slots__ = ("n", "P", "W", "H", "toff", "rec", "tstart", "plan", "pstate", "pgid", "tkeep", "l_d", "piece")
-
-
-def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep=True,
-                          speculate=None) -> tuple:
+def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep=True) -> tuple:
     dev = startpoint.device
     L = _lib.lib()
     v = _TileView()
+    v.plan = v.pairs = None
     v.W, v.H = W, H
     v.piece = int(L.gcp_tile_piece_pairs())
+    v.keep = bool(keep)
     n = boxsize.numel()
     v.n = n
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
         stream = cur.cuda_stream
+        v.key = _pool_key(dev)
         plan = _plans.pop((_p(boxsize), _p(startpoint), _p(endpoint), n), None)
         if plan is not None and plan.route != ("tiles", W, H):
+            if plan.arena is not None:
+                plan.event.synchronize()
+                _free_plan.setdefault(v.key, []).append(plan.arena)
             plan = None
         if plan is not None:
             cur.wait_event(plan.event)
-            sp, ep, toff = plan.sp, plan.ep, plan.offs
-            host, event = plan.host, plan.event
-            for t_ in (sp, ep, toff):
+            sp, ep, v.plan, event = plan.sp, plan.ep, plan.arena, plan.event
+            for t_ in (sp, ep):
                 t_.record_stream(cur)
         else:
-            sp, ep, toff, totals = _prologue_tiles(L, dev, startpoint, endpoint, n, W, H)
-            host, event = _totals_to_host(totals, dev)
-        v.toff = toff
-        v.l_d = _aligned(l_d.detach().to(torch.float32))
-        mean_ = _aligned(mean.detach().to(torch.float32))
-        lam_ = _aligned(lam.detach().to(torch.float32).reshape(n, 4))
-        opac_ = opacity.detach().to(torch.float32).reshape(n).contiguous()
-        # queued before the host waits for the pair count, so the device has work meanwhile
-        v.rec = torch.empty((n, 16), dtype=torch.int32, device=dev)
-        _lib.check(L.gcp_tile_pack(_p(mean_), _p(lam_), _p(opac_), _p(v.l_d), _p(sp), _p(ep), _p(toff), n, W, H,
-                                   _p(v.rec), stream), "gcp_tile_pack")
+            sp, ep, v.plan, event = _plan_tiles(L, dev, startpoint, endpoint, n, W, H)
+        mean_, lam_, opac_, l_ = _f32(mean, (n, 2)), _f32(lam, (n, 4)), _f32(opacity, (n,)), _f32(l_d, (n, 3))
         image = torch.empty((H + 1, W + 1, 3), dtype=torch.float32, device=dev)  # every pixel is written by its lane
-        v.tstart = torch.empty(int(L.gcp_tile_num_tiles(W, H)) + 1, dtype=torch.int32, device=dev)
-        shape_key = (dev.index, n, W, H)
-        last = _pair_counts.get(shape_key)
-        if speculate is None:
-            speculate = SPECULATE
-        speculate = bool(speculate) and plan is None and last is not None
-        if speculate:
-            P = min(last + last // 4 + 4096, 2 ** 31 - 65)      # a capacity: the count itself is still on its way
-        else:
-            # the one host sync of a view (like the reference's .item() at uitility.py:348): the pair count was
-            # copied to pinned memory right behind the prologue
-            event.synchronize()
-            (P,) = host.tolist()
-            _pair_counts[shape_key] = P
-            if P >= 2 ** 31 - 64:
-                raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
-        v.P = P
-        v.plan = torch.empty(int(L.gcp_tile_plan_ints(P, W, H)), dtype=torch.int32, device=dev)
-        v.pstate = torch.empty(int(L.gcp_tile_state_floats(P, W, H)), dtype=torch.float32, device=dev)
-        v.pgid = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-        v.tkeep = torch.empty(max(P, 1) * 32, dtype=torch.float32, device=dev) if keep else None
-        temp = _scratch_bytes(dev, "bin", int(L.gcp_tile_bin_bytes(P, W, H)))
-        bin_fn = L.gcp_tile_bin_speculative if speculate else L.gcp_tile_bin
-        _lib.check(bin_fn(_p(sp), _p(ep), _p(toff), n, P, W, H, _p(v.tstart), _p(v.plan), _p(v.pgid), _p(temp),
-                          temp.numel(), stream), "gcp_tile_bin")
-        _lib.check(L.gcp_tile_render(_p(v.tstart), _p(v.plan), _p(v.pgid), _p(v.rec), P, W, H, _p(image),
-                                     _p(v.tkeep) if keep else None, _p(v.pstate), stream), "gcp_tile_render")
-        if speculate:
-            # everything is queued; the count arrived long ago.  v.P stays the capacity: it is what the buffers of
-            # this view are laid out for.
-            event.synchronize()
-            (actual,) = host.tolist()
-            _pair_counts[shape_key] = actual
-            if actual > P:   # guessed too low: pairs were dropped, render again with the exact count
-                del v, image
-                return _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d, W, H, keep,
-                                             speculate=False)
+        # the one host sync of a view (like the reference's .item() at uitility.py:348): the plan kernel wrote the
+        # pair count straight into pinned memory
+        event.synchronize()
+        v.P, v.Ppad = int(v.plan.totals_np[0]), int(v.plan.totals_np[1])
+        if v.Ppad >= 2 ** 31 - 64:
+            raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
+        v.pairs = _take_pair_arena(L, dev, v.Ppad, W, H)
+        _lib.check(L.gcp_view_render(_p(sp), _p(ep), _p(mean_), _p(lam_), _p(opac_), _p(l_), n, W, H, _p(v.plan.buf),
+                                     v.plan.buf.numel(), _p(v.pairs.buf), v.pairs.buf.numel(), v.pairs.cap,
+                                     1 if keep else 0, _p(image), stream), "gcp_view_render")
     return image, v
 
 
@@ -276,7 +313,7 @@ def _render_backward_tiles(v: _TileView, grad_image):
     dev = grad_image.device
     n = v.n
     L = _lib.lib()
-    if v.tkeep is None:
+    if not v.keep:
         raise RuntimeError("this view was rendered without keeping T (no input required a gradient)")
     if int(L.gcp_tile_piece_pairs()) != v.piece:
         raise RuntimeError("gcp_tile_set_piece_pairs changed between the forward and the backward of a view")
@@ -287,12 +324,9 @@ def _render_backward_tiles(v: _TileView, grad_image):
     gI = grad_image.detach().to(torch.float32).contiguous()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        partial = torch.empty(max(v.P, 1) * 8, dtype=torch.float32, device=dev)
-        _lib.check(L.gcp_tile_backward(_p(v.tstart), _p(v.plan), _p(v.pgid), _p(v.rec), _p(v.tkeep), _p(v.pstate),
-                                       _p(gI), v.P, v.W, v.H, _p(partial), stream), "gcp_tile_backward")
-        temp = _scratch_bytes(dev, "tile_reduce", int(L.gcp_tile_reduce_bytes(n)))
-        _lib.check(L.gcp_tile_reduce(_p(partial), _p(v.toff), _p(v.l_d), n, _p(g_mean), _p(g_lam), _p(g_opac),
-                                     _p(g_l), _p(temp), temp.numel(), stream), "gcp_tile_reduce")
+        _lib.check(L.gcp_view_backward(_p(v.plan.buf), v.plan.buf.numel(), _p(v.pairs.buf), v.pairs.buf.numel(),
+                                       v.pairs.cap, _p(gI), n, v.W, v.H, _p(g_mean), _p(g_lam), _p(g_opac), _p(g_l),
+                                       stream), "gcp_view_backward")
     return g_mean, g_lam, g_opac, g_l
 
 

@@ -1,30 +1,37 @@
-// gcp_tile.cu — the fused compositor route (SURVEY.md §8f rank 1): exclusive transmittance, colour sum and the
-// division-free backward in ONE pass per direction, without materialising the per-pixel element lists.
+// gcp_tile.cu — the fused compositor route (SURVEY.md §8f ranks 1-4): exclusive transmittance, colour sum and the
+// division-free backward in ONE walk per direction, without materialising the per-pixel element lists, behind two
+// C-ABI calls per view (gcp_view_plan + gcp_view_render, or gcp_view_forward; gcp_view_backward) that work
+// entirely inside caller-owned arenas.
 //
 // The per-pixel segmented scan  T_i = prod_{j<i} (1 - alpha_j),  C = sum_i T_i alpha_i l_i  (gs_model.py:544-566,
-// :498-514) is evaluated with one pixel per lane: the image is cut into tiles of 8 x 4 pixels = one warp, every
-// box contributes one (tile, Gaussian) pair per tile it touches, the pairs are sorted by tile with a stable radix
-// sort — the Gaussians arrive in depth order, so every tile list (and with it every pixel list) stays in depth
-// order, the same order torch.sort gives the reference at gs_model.py:547 — and a warp walks its tile's list
-// with the running T of its pixels in registers.
+// :498-514) is evaluated with one pixel per lane.  The image is cut into tiles of 8 x 4 pixels = one warp; a box
+// contributes one (tile, Gaussian) pair per tile it touches; every tile gets the list of its Gaussians in index
+// (= depth) order — the order torch.sort gives the reference at gs_model.py:547, hence the order inside every
+// pixel list — and a warp walks its tile's list with the running T of its pixels in registers.
 //
-//   forward   k_tile_render   : alpha = o * exp(-1/2 d Lambda d^T) (:493-495,:533-535), T, colour; the exclusive
-//                               T of every (pair, lane) is kept for the backward (128 contiguous bytes per pair)
-//   backward  k_tile_backward : the list walked in reverse with U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1}
-//                               (w = <dL/dI, alpha l>), dL/dalpha_i = T_i <dL/dI, l_i> - T_i U_i — no division by
-//                               1-alpha (:736,:747,:757 divide) — and the reference's per-element gradients
-//                               (:733-766) summed over the lanes of the pair in a fixed order;
-//             k_tile_reduce   : the partial sums of a Gaussian's pairs added in pair order (:776-783).
+//   plan      k_view_count    : pairs per Gaussian, pairs per tile (integer atomics)          (uitility.py:336-366)
+//             k_view_scan     : exclusive offsets of both (one launch, chained scan)            (.item() at :348)
+//   render    k_view_fill     : packed per-Gaussian records; every pair dropped into its tile's
+//                               segment at an atomic cursor (unordered)                        (gs_model.py:538-548)
+//             k_view_sort     : every tile's segment sorted by Gaussian id — the ids of a tile are
+//                               distinct, so the result IS the stable sort by tile, bit for bit;
+//                               long lists are cut into pieces (the walk kernels' work units)
+//             k_view_render   : alpha = o * exp(-1/2 d Lambda d^T) (:493-495,:533-535), T, colour; only a
+//                               CHECKPOINT of T every 16 pairs is kept for the backward (8 B per pair)
+//   backward  k_view_backward : per 16 pairs, T and the Gaussian kernel value are recomputed from the checkpoint
+//                               into shared memory, then the list is walked in reverse with
+//                               U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1}  (w = <dL/dI, alpha l>),
+//                               dL/dalpha_i = T_i (<dL/dI, l_i> - U_i) — no division by 1-alpha (:736,:747,:757
+//                               divide) — and the moments of g*dalpha over the pair's pixels, from which the
+//                               reference's per-element gradients (:733-766) follow per Gaussian, are summed
+//                               over the 32 lanes through shared memory in a fixed order;
+//             k_view_reduce   : the partial sums of a Gaussian's pairs added in pair order (:776-783).
 // No float atomics anywhere: a pixel belongs to one lane, a partial to one pair — bitwise reproducible.
 // Elements whose inclusive product is 0 contribute nothing and get no gradient (gs_model.py:575-578).
+// No library kernels (CUB / thrust) on this route.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
-
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
 
 #include "gcp_abi.h"
 
@@ -33,6 +40,8 @@ namespace {
 constexpr int TSX = 3, TSY = 2;                 // tile = 8 x 4 pixels, lane = (y & 3) * 8 + (x & 7)
 constexpr int TW = 1 << TSX, TH = 1 << TSY;
 static_assert(TW * TH == 32, "one tile is one warp");
+constexpr int SUB = 16;                         // pairs per T checkpoint; tile segments are padded to multiples of it
+constexpr int RG = 4;                           // pairs per cross-lane reduction group of the backward
 
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
@@ -40,85 +49,43 @@ inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7ffffff
     if (b > cap) b = cap;
     return static_cast<unsigned>(b);
 }
-inline int key_bits(int max_key) {
-    int b = 1;
-    while (b < 31 && (1 << b) <= max_key) ++b;
-    return b;
-}
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// ---- arena headers (u32 words; zeroed by gcp_view_plan) ----
+constexpr int H_TICKET_S1 = 0, H_TICKET_S2 = 1, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4, H_NLONG = 5;
+constexpr int H_TICKET_BWD = 6, H_NBIG = 7;     // adjacent: reset together by every backward
+constexpr int H_P64 = 8, H_PPAD64 = 9;          // u64 indices (bytes 64 / 72): pair count, padded pair count
+constexpr int HDR_WORDS = 64;
 
 // box of Gaussian g clipped to the image [0,W] x [0,H] (the caller clamps already, gs_model.py:419-425)
 struct Box {
     int sx, sy, ex, ey;
 };
-__host__ __device__ __forceinline__ Box clip_box(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
-                                                 int64_t g, int W, int H) {
+__device__ __forceinline__ Box clip_box(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t g, int W,
+                                        int H) {
+    const int2 s = __ldg(reinterpret_cast<const int2 *>(sp) + g), e = __ldg(reinterpret_cast<const int2 *>(ep) + g);
     Box b;
-    b.sx = sp[2 * g] > 0 ? sp[2 * g] : 0;
-    b.sy = sp[2 * g + 1] > 0 ? sp[2 * g + 1] : 0;
-    b.ex = ep[2 * g] < W ? ep[2 * g] : W;
-    b.ey = ep[2 * g + 1] < H ? ep[2 * g + 1] : H;
+    b.sx = s.x > 0 ? s.x : 0;
+    b.sy = s.y > 0 ? s.y : 0;
+    b.ex = e.x < W ? e.x : W;
+    b.ey = e.y < H ? e.y : H;
     return b;
 }
-// (tile, Gaussian) pairs of one box (0 for an empty / inverted box)
-struct TilePairCount {
-    const int32_t *sp, *ep;
-    int W, H;
-    __host__ __device__ __forceinline__ int64_t operator()(int64_t g) const {
-        const Box b = clip_box(sp, ep, g, W, H);
-        if (b.ex < b.sx || b.ey < b.sy) return 0;
-        return static_cast<int64_t>((b.ex >> TSX) - (b.sx >> TSX) + 1) * ((b.ey >> TSY) - (b.sy >> TSY) + 1);
-    }
-};
 
-__global__ void k_tile_totals(const int64_t *__restrict__ toff, int64_t n, int64_t *__restrict__ totals) {
-    totals[0] = toff[n];
-}
-
-// Lambda is stored pre-multiplied by -log2(e)/2, so that the walk kernels get g = exp(-1/2 d Lambda d^T) as one
-// ex2.approx of d Lambda' d^T (relative error 2^-22; expf costs eight instructions, this one two); the backward
-// multiplies its d_mean terms by EXP2_UNSCALE = -2 ln 2 to undo the factor in X = d Lambda.
-constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
-constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
-
-// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, toff, 0}
-__global__ void __launch_bounds__(256)
-k_tile_pack(const float *__restrict__ mean, const float *__restrict__ lam, const float *__restrict__ opac,
-            const float *__restrict__ l_d, const int32_t *__restrict__ sp, const int32_t *__restrict__ ep,
-            const int64_t *__restrict__ toff, int64_t n, int W, int H, int4 *__restrict__ rec) {
-    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= n) return;
-    const float2 m = __ldg(reinterpret_cast<const float2 *>(mean) + g);
-    const float4 L = __ldg(reinterpret_cast<const float4 *>(lam) + g);
-    const Box b = clip_box(sp, ep, g, W, H);
-    auto f = [](float v) { return __float_as_int(v); };
-    rec[4 * g] = make_int4(f(m.x), f(m.y), f(L.x * EXP2_SCALE), f(L.y * EXP2_SCALE));
-    rec[4 * g + 1] = make_int4(f(L.z * EXP2_SCALE), f(L.w * EXP2_SCALE), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
-    rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
-    rec[4 * g + 3] = make_int4(b.ex, b.ey, static_cast<int>(__ldg(toff + g)), 0);
-}
-
-// pair p of Gaussian g (Gaussian-major, row-major over the tiles of its box): ptile[p] = tile index, pgid[p] = g.
-// One thread per Gaussian writes the pairs of a small box (adjacent threads write adjacent runs); a box of more
-// than 32 tiles is written by the whole warp afterwards.
-__global__ void __launch_bounds__(256)
-k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
-             int64_t n, int64_t cap, int W, int H, int ntx, int32_t *__restrict__ ptile, int32_t *__restrict__ pgid) {
-    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int64_t beg = 0;
-    int cnt = 0, tx0 = 0, ty0 = 0, nx = 1;
-    if (g < n) {
-        beg = __ldg(toff + g);
-        cnt = static_cast<int>(__ldg(toff + g + 1) - beg);
-        const Box b = clip_box(sp, ep, g, W, H);
-        tx0 = b.sx >> TSX; ty0 = b.sy >> TSY; nx = (b.ex >> TSX) - tx0 + 1;
+// Calls f(tile) for every tile of the boxes of this warp's 32 Gaussians: a small box by its own thread, a box of
+// more than 32 tiles by the whole warp afterwards (bundled scene: boxes of thousands of tiles).
+template <typename F>
+__device__ __forceinline__ void for_each_tile(bool valid, const Box &b, int ntx, int lane, F f) {
+    int tx0 = 0, ty0 = 0, nx = 1, cnt = 0;
+    if (valid && b.ex >= b.sx && b.ey >= b.sy) {
+        tx0 = b.sx >> TSX; ty0 = b.sy >> TSY;
+        nx = (b.ex >> TSX) - tx0 + 1;
+        cnt = nx * ((b.ey >> TSY) - ty0 + 1);
     }
     if (cnt <= 32) {
         int r = 0, c = 0;
-        for (int i = 0; i < cnt && beg + i < cap; ++i) {   // cap: the buffers' capacity (>= the pair count,
-            ptile[beg + i] = (ty0 + r) * ntx + tx0 + c;      // except in a speculative call that guessed too low)
-            pgid[beg + i] = static_cast<int32_t>(g);
+        for (int i = 0; i < cnt; ++i) {
+            f((ty0 + r) * ntx + tx0 + c, lane);
             if (++c == nx) { c = 0; ++r; }
         }
     }
@@ -126,134 +93,312 @@ k_tile_pairs(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, con
     while (big) {
         const int src = __ffs(big) - 1;
         big &= big - 1;
-        const int64_t bbeg = __shfl_sync(0xffffffffu, beg, src);
         const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
         const int btx0 = __shfl_sync(0xffffffffu, tx0, src), bty0 = __shfl_sync(0xffffffffu, ty0, src);
         const int bnx = __shfl_sync(0xffffffffu, nx, src);
-        const int32_t bg = static_cast<int32_t>(g - lane + src);
-        for (int i = lane; i < bcnt && bbeg + i < cap; i += 32) {
+        for (int i = lane; i < bcnt; i += 32) {
             const int r = i / bnx;
-            ptile[bbeg + i] = (bty0 + r) * ntx + btx0 + (i - r * bnx);
-            pgid[bbeg + i] = bg;
+            f((bty0 + r) * ntx + btx0 + (i - r * bnx), src);
         }
     }
 }
 
-// first index g with off[g+1] > e
-__device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, int64_t n, int64_t e) {
-    int64_t lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(off + mid + 1) > e) hi = mid;
-        else lo = mid + 1;
+// ---------------------------------------------------------------------------------------------------------------
+// plan: counts
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_view_count(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t n, int W, int H, int ntx,
+             int32_t *__restrict__ cnt, int32_t *__restrict__ tcount) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Box b = {0, 0, -1, -1};
+    if (g < n) {
+        b = clip_box(sp, ep, g, W, H);
+        int c = 0;
+        if (b.ex >= b.sx && b.ey >= b.sy) c = ((b.ex >> TSX) - (b.sx >> TSX) + 1) * ((b.ey >> TSY) - (b.sy >> TSY) + 1);
+        cnt[g] = c;
     }
-    return lo;
+    for_each_tile(g < n, b, ntx, lane, [&](int t, int) { atomicAdd(tcount + t, 1); });
 }
 
-// the same list, parallel over PAIRS (8 consecutive ones per thread, one search for the first): for views whose
-// boxes span many tiles each (bundled scene: ten pairs per Gaussian on average, thousands for some)
-constexpr int CHP = 8;
-__global__ void __launch_bounds__(256)
-k_tile_pairs_flat(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const int64_t *__restrict__ toff,
-                  int64_t n, int64_t cap, int W, int H, int ntx, int32_t *__restrict__ ptile,
-                  int32_t *__restrict__ pgid) {
-    const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * CHP;
-    const int64_t total = __ldg(toff + n);          // the pair count lives on the device; cap = buffer capacity
-    const int64_t P = total < cap ? total : cap;
-    if (p0 >= P) return;
-    int64_t g = find_owner(toff, n, p0);
-    int64_t gbeg = __ldg(toff + g), gend = __ldg(toff + g + 1);
-    Box b = clip_box(sp, ep, g, W, H);
-    int tx0 = b.sx >> TSX, ty0 = b.sy >> TSY, nx = (b.ex >> TSX) - tx0 + 1;
-    for (int i = 0; i < CHP && p0 + i < P; ++i) {
-        const int64_t p = p0 + i;
-        while (p >= gend) {  // skips Gaussians without pairs too
-            ++g;
-            gbeg = gend;
-            gend = __ldg(toff + g + 1);
-            b = clip_box(sp, ep, g, W, H);
-            tx0 = b.sx >> TSX; ty0 = b.sy >> TSY; nx = (b.ex >> TSX) - tx0 + 1;
+// ---------------------------------------------------------------------------------------------------------------
+// plan: exclusive offsets.  One launch scans BOTH arrays (blocks [0, nb1): pairs per Gaussian -> toff;
+// blocks [nb1, nb1 + nb2): pairs per tile, rounded up to SUB -> tstart) with the classic single-pass chained scan:
+// a block publishes its aggregate, then walks back over its predecessors' descriptors (32 per step) to the
+// nearest inclusive prefix.  Tile order comes from an atomic ticket, so a block only ever waits for blocks that
+// are already running.  descriptor = status (2 bits: 1 aggregate, 2 inclusive) << 62 | value.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <bool PAD>
+__device__ __forceinline__ void chained_scan_block(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out,
+                                                   unsigned int *ticket, unsigned long long *desc,
+                                                   unsigned long long *total_dev, int64_t *total_host) {
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t base = static_cast<int64_t>(tile) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int x = (base + i < n) ? in[base + i] : 0;
+        if (PAD) x = (x + SUB - 1) & ~(SUB - 1);
+        v[i] = x;
+        sum += static_cast<unsigned long long>(x);
+    }
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long wpre = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) wpre += s_warp[w];
+        agg += s_warp[w];
+    }
+    if (warp == 0) {
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st_release_u64(desc, (2ull << 62) | agg);
+        } else {
+            if (lane == 0) st_release_u64(desc + tile, (1ull << 62) | agg);
+            int64_t pb = static_cast<int64_t>(tile) - 1;
+            while (true) {
+                const int64_t idx = pb - lane;
+                unsigned long long d = 2ull << 62;   // before tile 0: an inclusive prefix of 0
+                if (idx >= 0) {
+                    do { d = ld_acquire_u64(desc + idx); } while ((d >> 62) == 0ull);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+                const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                unsigned long long c = (lane <= stop) ? (d & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                prefix += c;
+                if (inc_mask) break;
+                pb -= 32;
+            }
+            if (lane == 0) st_release_u64(desc + tile, (2ull << 62) | (prefix + agg));
         }
-        const int local = static_cast<int>(p - gbeg);
-        const int r = local / nx;
-        ptile[p] = (ty0 + r) * ntx + tx0 + (local - r * nx);
-        pgid[p] = static_cast<int32_t>(g);
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    unsigned long long run = s_prefix + wpre + (inc - sum);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = static_cast<int32_t>(run);
+        run += static_cast<unsigned long long>(v[i]);
+    }
+    if (static_cast<int64_t>(tile + 1) * SCAN_TILE >= n && threadIdx.x == SCAN_THREADS - 1) {   // the block holding item n-1
+        const unsigned long long tot = s_prefix + agg;
+        out[n] = static_cast<int32_t>(tot < 0x7fffffffull ? tot : 0x7fffffffull);
+        *total_dev = tot;
+        if (total_host != nullptr) {
+            *reinterpret_cast<volatile int64_t *>(total_host) = static_cast<int64_t>(tot);
+            __threadfence_system();
+        }
     }
 }
 
-// speculative binning (the host guessed a capacity instead of waiting for the pair count): the slots behind the
-// real pairs get the key `ntiles`, which sorts behind every tile and is what k_tile_start expects after the last pair
-__global__ void __launch_bounds__(256)
-k_tile_pad(const int64_t *__restrict__ toff, int64_t n, int64_t cap, int ntiles, int32_t *__restrict__ ptile,
-           int32_t *__restrict__ pgid) {
-    const int64_t total = __ldg(toff + n);
-    for (int64_t p = total + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < cap;
-         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        ptile[p] = ntiles;
-        pgid[p] = 0;
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_view_scan(const int32_t *__restrict__ cnt, int64_t n, int32_t *__restrict__ toff, const int32_t *__restrict__ tcount,
+            int ntiles, int32_t *__restrict__ tstart, unsigned int nb1, unsigned int *hdr, unsigned long long *desc1,
+            unsigned long long *desc2, int64_t *totals_host) {
+    unsigned long long *h64 = reinterpret_cast<unsigned long long *>(hdr);
+    if (blockIdx.x < nb1)
+        chained_scan_block<false>(cnt, n, toff, hdr + H_TICKET_S1, desc1, h64 + H_P64, totals_host);
+    else
+        chained_scan_block<true>(tcount, ntiles, tstart, hdr + H_TICKET_S2, desc2, h64 + H_PPAD64,
+                                 totals_host ? totals_host + 1 : nullptr);
+}
+// empty views (n == 0): the offsets of nothing
+__global__ void k_view_scan_empty(int32_t *toff, int32_t *tstart, int ntiles, unsigned int *hdr, int64_t *totals_host) {
+    for (int t = threadIdx.x; t <= ntiles; t += blockDim.x) tstart[t] = 0;
+    if (threadIdx.x == 0) {
+        toff[0] = 0;
+        if (totals_host) { totals_host[0] = 0; totals_host[1] = 0; __threadfence_system(); }
     }
 }
 
-// tstart[t] = first pair of tile t in the tile-sorted pair list (tstart[ntiles] = P), empty tiles included
+// ---------------------------------------------------------------------------------------------------------------
+// render: records + unordered fill
+// Lambda is stored pre-multiplied by -log2(e)/2, so that the walk kernels get g = exp(-1/2 d Lambda d^T) as one
+// ex2.approx of d Lambda' d^T (relative error 2^-22; expf costs eight instructions, this one two); k_view_reduce
+// multiplies the d_mean sums by EXP2_UNSCALE = -2 ln 2 to undo the factor.
+// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, toff, 0}
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
+constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
+
+__device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap) {
+    return static_cast<int64_t>(reinterpret_cast<const unsigned long long *>(hdr)[H_PPAD64]) > cap;
+}
+
 __global__ void __launch_bounds__(256)
-k_tile_start(const int32_t *__restrict__ ptile_s, int64_t P, int ntiles, int32_t *__restrict__ tstart) {
-    const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p > P) return;
-    const int prev = (p == 0) ? -1 : __ldg(ptile_s + p - 1);
-    const int cur = (p == P) ? ntiles : __ldg(ptile_s + p);
-    for (int c = prev + 1; c <= cur; ++c) tstart[c] = static_cast<int32_t>(p);
+k_view_fill(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const float *__restrict__ mean,
+            const float *__restrict__ lam, const float *__restrict__ opac, const float *__restrict__ l_d,
+            const int32_t *__restrict__ toff, const int32_t *__restrict__ tstart, int64_t n, int W, int H, int ntx,
+            int64_t cap, const unsigned int *__restrict__ hdr, int32_t *__restrict__ cursor, int4 *__restrict__ rec,
+            int32_t *__restrict__ pgid) {
+    if (overflowed(hdr, cap)) return;   // the arena is too small for this view: the host notices and redoes it
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Box b = {0, 0, -1, -1};
+    if (g < n) {
+        b = clip_box(sp, ep, g, W, H);
+        auto f = [](float v) { return __float_as_int(v); };
+        const float mx = __ldg(mean + 2 * g), my = __ldg(mean + 2 * g + 1);
+        const float l00 = __ldg(lam + 4 * g), l01 = __ldg(lam + 4 * g + 1), l10 = __ldg(lam + 4 * g + 2),
+                    l11 = __ldg(lam + 4 * g + 3);
+        rec[4 * g] = make_int4(f(mx), f(my), f(l00 * EXP2_SCALE), f(l01 * EXP2_SCALE));
+        rec[4 * g + 1] = make_int4(f(l10 * EXP2_SCALE), f(l11 * EXP2_SCALE), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
+        rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
+        rec[4 * g + 3] = make_int4(b.ex, b.ey, __ldg(toff + g), 0);
+    }
+    const int32_t gbase = static_cast<int32_t>(g - lane);
+    for_each_tile(g < n, b, ntx, lane, [&](int t, int owner) {
+        const int pos = __ldg(tstart + t) + atomicAdd(cursor + t, 1);
+        pgid[pos] = gbase + owner;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// render: order inside the tiles.  A tile's segment holds distinct Gaussian ids in arbitrary order; sorted
+// ascending it is exactly what a stable sort of the Gaussian-major pair list by tile produces.  Bitonic network
+// with ascending compare-exchanges only (the "flip" form), so that a length that is not a power of two needs no
+// padding: a partner index beyond the end counts as +infinity and never moves.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SORT_SMEM = 512;   // longest list sorted by one warp in shared memory; longer ones: one block each
+
+template <typename Sync>
+__device__ __forceinline__ void bitonic_ascending(int32_t *s, int len, int tid, int nthreads, Sync sync) {
+    int N = 2;
+    while (N < len) N <<= 1;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int i = tid; i < N / 2; i += nthreads) {
+            const int half = k >> 1, blk = i / half, off = i - blk * half;
+            const int a = blk * k + off, b = blk * k + k - 1 - off;
+            if (b < len) {
+                const int32_t x = s[a], y = s[b];
+                if (x > y) { s[a] = y; s[b] = x; }
+            }
+        }
+        sync();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = tid; i < N / 2; i += nthreads) {
+                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1)), b = a + j;
+                if (b < len) {
+                    const int32_t x = s[a], y = s[b];
+                    if (x > y) { s[a] = y; s[b] = x; }
+                }
+            }
+            sync();
+        }
+    }
 }
 
 // Work units of the walk kernels are PIECES: at most `piece` consecutive pairs of one tile's list (a multiple of
-// 32).  Most tiles are one piece.  A tile with a long list (bundled scene: thousands of Gaussians over one tile,
-// ten times the mean) is cut into several, walked by different warps at the same time, each starting from the
-// identity; the per-pixel carries between the pieces of a tile are the segmented scan's cross-block carries:
+// 32).  Most tiles are one piece: work item t.  A tile with a longer list (bundled scene: thousands of Gaussians
+// over one tile, ten times the mean) is cut into np pieces walked by different warps at the same time, each
+// starting from the identity; it reserves np consecutive slots [x, x + np) of the extra-piece table (slot x stands
+// for its first piece, which is work item t; slots x+1.. are work items of their own) and of the piece state:
 //   forward : T_i = carry_p * Tlocal_i,  carry_p = prod of the aggregates of the earlier pieces; the colour is
-//             linear in the carry, C = sum_p carry_p * C_p                                  (k_tile_combine_fwd)
+//             linear in the carry, C = sum_p carry_p * C_p                                  (k_view_combine_fwd)
 //   backward: U after the last element of piece p:  U_in(p) = Tagg_{p+1} U_in(p+1) + <dL/dI, C_{p+1}>  — the
 //             affine map of a piece is made of the SAME two per-pixel quantities the forward already produced,
-//             its aggregate and its colour, so the backward needs no pass of its own for them  (k_tile_combine_bwd)
-// piece state per piece (f32[192]): {Tagg[32], C0[32], C1[32], C2[32], carry[32], U_in[32]}, touched only for the
-// pieces of multi-piece tiles.
+//             its aggregate and its colour, so the backward needs no pass of its own for them  (k_view_combine_bwd)
+// piece state per slot (f32[192]): {Tagg[32], C0[32], C1[32], C2[32], carry[32], U_in[32]}.
 constexpr int PIECE_STATE = 192;
 
-struct PieceCount {   // pieces of tile t: ceil(len / piece), 1 for an empty tile (its pixels still get written)
-    const int32_t *tstart;
-    int piece;
-    __host__ __device__ __forceinline__ int32_t operator()(int32_t t) const {
-        const int len = tstart[t + 1] - tstart[t];
-        return len <= piece ? 1 : (len + piece - 1) / piece;
-    }
-};
-
-// ptile[p] = tile of piece p  (pstart: exclusive offsets of the tiles' pieces, pstart[ntiles] = number of pieces)
 __global__ void __launch_bounds__(256)
-k_tile_pieces(const int32_t *__restrict__ pstart, int ntiles, int32_t *__restrict__ ptile) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+k_view_sort(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int ntiles, int piece, int64_t cap,
+            unsigned int *__restrict__ hdr, int32_t *__restrict__ pgid, int32_t *__restrict__ pextra,
+            int32_t *__restrict__ ptile_x, int32_t *__restrict__ mlist, int32_t *__restrict__ longlist) {
+    __shared__ int32_t s_keys[8][SORT_SMEM];
+    if (overflowed(hdr, cap)) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int t = blockIdx.x * 8 + wib;
     if (t >= ntiles) return;
-    const int b = __ldg(pstart + t), e = __ldg(pstart + t + 1);
-    for (int p = b; p < e; ++p) ptile[p] = t;
+    const int len = __ldg(tcount + t), base = __ldg(tstart + t);
+    if (lane == 0) {
+        int x = -1;
+        if (len > piece) {
+            const int np = (len + piece - 1) / piece;
+            x = static_cast<int>(atomicAdd(hdr + H_XPIECES, static_cast<unsigned>(np)));
+            ptile_x[x] = -1;
+            for (int k = 1; k < np; ++k) ptile_x[x + k] = t;
+            mlist[atomicAdd(hdr + H_NMULTI, 1u)] = t;
+        }
+        pextra[t] = x;
+        if (len > SORT_SMEM) longlist[atomicAdd(hdr + H_NLONG, 1u)] = t;
+    }
+    if (len < 2 || len > SORT_SMEM) return;
+    int32_t *s = s_keys[wib];
+    for (int i = lane; i < len; i += 32) s[i] = pgid[base + i];
+    __syncwarp();
+    bitonic_ascending(s, len, lane, 32, [] { __syncwarp(); });
+    for (int i = lane; i < len; i += 32) pgid[base + i] = s[i];
 }
 
+// lists longer than SORT_SMEM: one block each, in place in global memory (the segment stays in L1/L2)
+__global__ void __launch_bounds__(256)
+k_view_sort_long(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
+                 const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
+    if (overflowed(hdr, cap)) return;
+    const unsigned int nl = hdr[H_NLONG];
+    for (unsigned int i = blockIdx.x; i < nl; i += gridDim.x) {
+        const int t = longlist[i];
+        bitonic_ascending(pgid + tstart[t], tcount[t], threadIdx.x, blockDim.x, [] { __syncthreads(); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the walks
+// ---------------------------------------------------------------------------------------------------------------
 struct Piece {
-    int p, t, np;        // piece id, tile, pieces of that tile
-    int64_t lo, hi;      // pair range of the piece inside the tile-sorted pair list
+    int t, np, slot;     // tile (-1: a hole in the table, nothing to do), pieces of that tile, piece-state slot
+    int lo, hi;          // pair range of the piece inside the tile-ordered pair list
 };
-// next piece of this warp (dynamic ticket); false when none is left
-__device__ __forceinline__ bool next_piece(unsigned int *ticket, const int32_t *__restrict__ tstart,
-                                           const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile,
-                                           int npieces, int piece, int lane, Piece &w) {
+// next work item of this warp (dynamic ticket): the extra pieces first (they are full-length), then one per tile
+__device__ __forceinline__ bool next_piece(unsigned int *ticket, const int32_t *__restrict__ tcount,
+                                           const int32_t *__restrict__ tstart, const int32_t *__restrict__ pextra,
+                                           const int32_t *__restrict__ ptile_x, int nx, int ntiles, int piece, int lane,
+                                           Piece &w) {
     unsigned i = 0;
     if (lane == 0) i = atomicAdd(ticket, 1u);
     i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= static_cast<unsigned>(npieces)) return false;
-    w.p = static_cast<int>(i);
-    w.t = __ldg(ptile + i);
-    const int p0 = __ldg(pstart + w.t);
-    w.np = __ldg(pstart + w.t + 1) - p0;
-    const int64_t tlo = __ldg(tstart + w.t), thi = __ldg(tstart + w.t + 1);
-    w.lo = tlo + static_cast<int64_t>(w.p - p0) * piece;
-    w.hi = (w.lo + piece < thi) ? w.lo + piece : thi;
+    if (i >= static_cast<unsigned>(nx + ntiles)) return false;
+    int k = 0;
+    if (i < static_cast<unsigned>(nx)) {
+        w.t = __ldg(ptile_x + i);
+        if (w.t < 0) return true;
+        k = static_cast<int>(i) - __ldg(pextra + w.t);
+    } else {
+        w.t = static_cast<int>(i) - nx;
+    }
+    const int len = __ldg(tcount + w.t), base = __ldg(tstart + w.t);
+    w.np = len <= piece ? 1 : (len + piece - 1) / piece;
+    w.slot = __ldg(pextra + w.t) + k;
+    w.lo = base + k * piece;
+    w.hi = min(w.lo + piece, base + len);
     return true;
 }
 
@@ -264,7 +409,6 @@ __device__ __forceinline__ void ldg256(const void *p, int4 &u, int4 &v) {
                  : "l"(p)
                  : "memory");
 }
-
 struct RecRegs {
     int4 a, b, c, d;
 };
@@ -274,20 +418,9 @@ __device__ __forceinline__ RecRegs load_rec(const int4 *__restrict__ rec, int g)
     ldg256(rec + 4 * static_cast<int64_t>(g) + 2, r.c, r.d);
     return r;
 }
-
-// What the walk needs of a pair, staged in shared memory by the lane that loaded it (three broadcast LDS.128 per
-// pair in the walk): {mx, my, l00, l01} {l10, l11, o, l0} {l1, l2, coverage mask of the tile, Gaussian-major pair id}
-struct PairSlot {
-    float4 a, b;
-    float2 c;
-    uint32_t mask;
-    int32_t q;
-};
-static_assert(sizeof(PairSlot) == 48, "three 16-byte words");
-
-__device__ __forceinline__ void stage_pair(PairSlot *slot, const RecRegs &r, bool live, int tx, int ty, int x0, int y0) {
+// lanes of the tile at (x0, y0) inside the record's box: columns [xa, xb] of rows [ya, yb]
+__device__ __forceinline__ uint32_t coverage_mask(const RecRegs &r, bool live, int x0, int y0) {
     const int sx = r.c.z, sy = r.c.w, ex = r.d.x, ey = r.d.y;
-    // lanes of the tile inside the box: columns [xa, xb] of rows [ya, yb]
     const int xa = max(sx, x0) - x0, xb = min(ex, x0 + TW - 1) - x0;
     const int ya = max(sy, y0) - y0, yb = min(ey, y0 + TH - 1) - y0;
     uint32_t mask = 0;
@@ -296,85 +429,99 @@ __device__ __forceinline__ void stage_pair(PairSlot *slot, const RecRegs &r, boo
         const uint32_t rows = (0x01010101u >> (8 * (TH - 1 - (yb - ya)))) << (8 * ya);
         mask = xm * rows;
     }
-    const int tx0 = sx >> TSX, ty0 = sy >> TSY, nx = (ex >> TSX) - tx0 + 1;
-    slot->a = make_float4(__int_as_float(r.a.x), __int_as_float(r.a.y), __int_as_float(r.a.z), __int_as_float(r.a.w));
-    slot->b = make_float4(__int_as_float(r.b.x), __int_as_float(r.b.y), __int_as_float(r.b.z), __int_as_float(r.b.w));
-    slot->c = make_float2(__int_as_float(r.c.x), __int_as_float(r.c.y));
-    slot->mask = mask;
-    slot->q = r.d.z + (ty - ty0) * nx + (tx - tx0);
+    return mask;
 }
+// Gaussian-major id of the pair (record's Gaussian, tile (tx, ty)): where its gradient partial goes
+__device__ __forceinline__ int pair_id(const RecRegs &r, int tx, int ty) {
+    const int tx0 = r.c.z >> TSX, ty0 = r.c.w >> TSY, nx = (r.d.x >> TSX) - tx0 + 1;
+    return r.d.z + (ty - ty0) * nx + (tx - tx0);
+}
+__device__ __forceinline__ float i2f(int v) { return __int_as_float(v); }
 
 struct PairEval {
-    float d0, d1, X0, X1, gk, x;
+    float d0, d1, gk, x;
 };
-// g = exp(-1/2 (r-m) Lambda (r-m)^T) with X = (r-m) Lambda (gs_model.py:495, :745); x = 1 - o g (:533-535).
-// The record holds Lambda' = EXP2_SCALE Lambda: X0, X1 come out scaled by EXP2_SCALE and g = 2^(X' . d).
-__device__ __forceinline__ PairEval eval_pair(const float4 &a, const float4 &b, float px, float py) {
+// g = exp(-1/2 (r-m) Lambda (r-m)^T) (gs_model.py:495); x = 1 - o g (:533-535).  a = {mx, my, l00', l01'},
+// (l10', l11', o): Lambda' = EXP2_SCALE Lambda, so g = 2^(d Lambda' d^T).
+__device__ __forceinline__ PairEval eval_pair(const float4 &a, float l10, float l11, float o, float px, float py) {
     PairEval e;
     e.d0 = px - a.x;
     e.d1 = py - a.y;
-    e.X0 = e.d0 * a.z + e.d1 * b.x;
-    e.X1 = e.d0 * a.w + e.d1 * b.y;
-    const float p2 = e.X0 * e.d0 + e.X1 * e.d1;
+    const float X0 = e.d0 * a.z + e.d1 * l10;
+    const float X1 = e.d0 * a.w + e.d1 * l11;
+    const float p2 = X0 * e.d0 + X1 * e.d1;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.gk) : "f"(p2));
-    e.x = 1.0f - b.z * e.gk;
+    e.x = 1.0f - o * e.gk;
     return e;
 }
 
+// ---- forward ----
+// What the forward walk needs of a pair, staged in shared memory by the lane that loaded it (three broadcast
+// LDS.128 per pair): {mx, my, l00, l01} {l10, l11, o, coverage mask} {l0, l1, l2, -}
+struct FSlot {
+    float4 a, b, c;
+};
 constexpr int TILE_WARPS = 8;
 
 template <bool KEEP>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 4)
-k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
-              const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
-              int piece, int ntx, int ntiles, int W, int H, float *__restrict__ image, float *__restrict__ tkeep,
-              float *__restrict__ pstate) {
-    __shared__ PairSlot slots[TILE_WARPS][32];
+k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart,
+              const int32_t *__restrict__ pextra, const int32_t *__restrict__ ptile_x,
+              const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, unsigned int *__restrict__ hdr,
+              int64_t cap, int piece, int ntx, int ntiles, int W, int H, float *__restrict__ image,
+              float *__restrict__ tck, float *__restrict__ pstate) {
+    __shared__ FSlot slots[TILE_WARPS][32];
+    if (overflowed(hdr, cap)) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    PairSlot *sl = slots[wib];
-    const int npieces = __ldg(pstart + ntiles);
+    FSlot *sl = slots[wib];
+    const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
-    while (next_piece(ticket, tstart, pstart, ptile, npieces, piece, lane, w)) {  // warp-uniform; only __syncwarp inside
+    while (next_piece(hdr + H_TICKET_FWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
+        if (w.t < 0) continue;   // warp-uniform; only __syncwarp inside
         const int t = w.t;
         const int ty = t / ntx, tx = t - ty * ntx;
         const int x0 = tx << TSX, y0 = ty << TSY;
         const int ix = x0 + (lane & (TW - 1)), iy = y0 + (lane >> TSX);
         const float px = static_cast<float>(ix), py = static_cast<float>(iy);
-        const int64_t lo = w.lo, hi = w.hi;
+        const int lo = w.lo, hi = w.hi;
         float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;   // T: local to the piece (its carry is applied afterwards)
         // software pipeline over batches of 32 pairs: ids two batches ahead, records one batch ahead
         int g1 = 0;
         RecRegs r = {};
-        if (lo + lane < hi) r = load_rec(rec, __ldg(pgid_s + lo + lane));
-        if (lo + 32 + lane < hi) g1 = __ldg(pgid_s + lo + 32 + lane);
-        for (int64_t b = lo; b < hi; b += 32) {
-            stage_pair(sl + lane, r, b + lane < hi, tx, ty, x0, y0);
+        if (lo + lane < hi) r = load_rec(rec, __ldg(pgid + lo + lane));
+        if (lo + 32 + lane < hi) g1 = __ldg(pgid + lo + 32 + lane);
+        for (int b = lo; b < hi; b += 32) {
+            {
+                const uint32_t mask = coverage_mask(r, b + lane < hi, x0, y0);
+                sl[lane].a = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
+                sl[lane].b = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
+                sl[lane].c = make_float4(i2f(r.b.w), i2f(r.c.x), i2f(r.c.y), 0.0f);
+            }
             int g2 = 0;
-            if (b + 64 + lane < hi) g2 = __ldg(pgid_s + b + 64 + lane);
+            if (b + 64 + lane < hi) g2 = __ldg(pgid + b + 64 + lane);
             if (b + 32 + lane < hi) r = load_rec(rec, g1);
             g1 = g2;
             __syncwarp();
-            const int m = static_cast<int>(hi - b < 32 ? hi - b : 32);
-            float *tk = tkeep + b * 32 + lane;
+            const int m = min(hi - b, 32);
+            float *ck = tck + (static_cast<int64_t>(b) >> 4) * 32 + lane;   // b is a multiple of SUB = 16
 #pragma unroll 4
             for (int k = 0; k < m; ++k) {
-                const float4 A = sl[k].a, B = sl[k].b;
-                const float2 C = sl[k].c;
-                const bool cov = (sl[k].mask >> lane) & 1u;
-                const PairEval e = eval_pair(A, B, px, py);
+                const float4 A = sl[k].a, B = sl[k].b, C = sl[k].c;
+                const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
+                const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
+                if (KEEP && (k & (SUB - 1)) == 0) __stcs(ck + (k >> 4) * 32, T);   // T checkpoint for the backward
                 const float tin = T * e.x;
-                if (KEEP) __stcs(tk + k * 32, T);   // not kept for a render without backward
                 // branch-free: an element outside the box, or dead (inclusive product 0, gs_model.py:575-578), adds 0
                 const float ta = (cov && tin != 0.0f) ? T * (1.0f - e.x) : 0.0f;
-                c0 = fmaf(ta, B.w, c0);
-                c1 = fmaf(ta, C.x, c1);
-                c2 = fmaf(ta, C.y, c2);
+                c0 = fmaf(ta, C.x, c0);
+                c1 = fmaf(ta, C.y, c1);
+                c2 = fmaf(ta, C.z, c2);
                 T = cov ? tin : T;
             }
             __syncwarp();
         }
         if (w.np > 1) {
-            float *ps = pstate + static_cast<int64_t>(w.p) * PIECE_STATE + lane;
+            float *ps = pstate + static_cast<int64_t>(w.slot) * PIECE_STATE + lane;
             ps[0] = T; ps[32] = c0; ps[64] = c1; ps[96] = c2;
         } else if (ix <= W && iy <= H) {
             float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
@@ -385,101 +532,104 @@ k_tile_render(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pg
 
 // tiles of several pieces: the carry of every piece (kept for the backward), and the pixel's colour
 __global__ void __launch_bounds__(256)
-k_tile_combine_fwd(const int32_t *__restrict__ pstart, int ntx, int ntiles, int W, int H, float *__restrict__ pstate,
-                   float *__restrict__ image) {
+k_view_combine_fwd(const int32_t *__restrict__ tcount, const int32_t *__restrict__ pextra,
+                   const int32_t *__restrict__ mlist, const unsigned int *__restrict__ hdr, int64_t cap, int piece,
+                   int ntx, int W, int H, float *__restrict__ pstate, float *__restrict__ image) {
+    if (overflowed(hdr, cap)) return;
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (t >= ntiles) return;
-    const int p0 = __ldg(pstart + t), np = __ldg(pstart + t + 1) - p0;
-    if (np <= 1) return;
-    float carry = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    for (int k = 0; k < np; ++k) {
-        float *ps = pstate + static_cast<int64_t>(p0 + k) * PIECE_STATE + lane;
-        ps[128] = carry;
-        c0 = fmaf(carry, ps[32], c0);
-        c1 = fmaf(carry, ps[64], c1);
-        c2 = fmaf(carry, ps[96], c2);
-        carry *= ps[0];
-    }
-    const int ty = t / ntx, tx = t - ty * ntx;
-    const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
-    if (ix <= W && iy <= H) {
-        float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
-        p[0] = c0; p[1] = c1; p[2] = c2;
+    const unsigned int nm = hdr[H_NMULTI];
+    for (unsigned int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nm; i += gridDim.x * 8) {
+        const int t = mlist[i];
+        const int np = (__ldg(tcount + t) + piece - 1) / piece, s0 = __ldg(pextra + t);
+        float carry = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int k = 0; k < np; ++k) {
+            float *ps = pstate + static_cast<int64_t>(s0 + k) * PIECE_STATE + lane;
+            ps[128] = carry;
+            c0 = fmaf(carry, ps[32], c0);
+            c1 = fmaf(carry, ps[64], c1);
+            c2 = fmaf(carry, ps[96], c2);
+            carry *= ps[0];
+        }
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
+        if (ix <= W && iy <= H) {
+            float *p = image + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+            p[0] = c0; p[1] = c1; p[2] = c2;
+        }
     }
 }
 
 // tiles of several pieces: U after the last element of every piece, from the pieces behind it
 __global__ void __launch_bounds__(256)
-k_tile_combine_bwd(const int32_t *__restrict__ pstart, const float *__restrict__ gimg, int ntx, int ntiles, int W,
-                   int H, float *__restrict__ pstate) {
+k_view_combine_bwd(const int32_t *__restrict__ tcount, const int32_t *__restrict__ pextra,
+                   const int32_t *__restrict__ mlist, const unsigned int *__restrict__ hdr, int piece,
+                   const float *__restrict__ gimg, int ntx, int W, int H, float *__restrict__ pstate) {
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (t >= ntiles) return;
-    const int p0 = __ldg(pstart + t), np = __ldg(pstart + t + 1) - p0;
-    if (np <= 1) return;
-    const int ty = t / ntx, tx = t - ty * ntx;
-    const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
-    float pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
-    if (ix <= W && iy <= H) {
-        const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
-        pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
-    }
-    float U = 0.0f;
-    for (int k = np - 1; k >= 0; --k) {
-        float *ps = pstate + static_cast<int64_t>(p0 + k) * PIECE_STATE + lane;
-        ps[160] = U;
-        U = fmaf(ps[0], U, pg0 * ps[32] + pg1 * ps[64] + pg2 * ps[96]);
+    const unsigned int nm = hdr[H_NMULTI];
+    for (unsigned int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nm; i += gridDim.x * 8) {
+        const int t = mlist[i];
+        const int np = (__ldg(tcount + t) + piece - 1) / piece, s0 = __ldg(pextra + t);
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
+        float pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
+        if (ix <= W && iy <= H) {
+            const float *p = gimg + 3 * (static_cast<int64_t>(iy) * (W + 1) + ix);
+            pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
+        }
+        float U = 0.0f;
+        for (int k = np - 1; k >= 0; --k) {
+            float *ps = pstate + static_cast<int64_t>(s0 + k) * PIECE_STATE + lane;
+            ps[160] = U;
+            U = fmaf(ps[0], U, pg0 * ps[32] + pg1 * ps[64] + pg2 * ps[96]);
+        }
     }
 }
 
-// sum of 8 values per lane over the 32 lanes in 9 shuffles (halving butterfly): afterwards the four lanes
-// 4c' .. 4c'+3 hold component comp(c') = 4*bit2(c') + 2*bit1(c') + bit0(c'), c' = lane >> 2 with its bits read as
-// (lane bit 4, lane bit 3, lane bit 2).  The order of the additions is fixed: bitwise reproducible.
-__device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
-    const unsigned F = 0xffffffffu;
-    float k4[4], k2[2];
-    {
-        const bool h = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float keep = h ? v[4 + i] : v[i], send = h ? v[i] : v[4 + i];
-            k4[i] = keep + __shfl_xor_sync(F, send, 16);
-        }
-    }
-    {
-        const bool h = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float keep = h ? k4[2 + i] : k4[i], send = h ? k4[i] : k4[2 + i];
-            k2[i] = keep + __shfl_xor_sync(F, send, 8);
-        }
-    }
-    const bool h = lane & 4;
-    float s = (h ? k2[1] : k2[0]) + __shfl_xor_sync(F, h ? k2[0] : k2[1], 4);
-    s += __shfl_xor_sync(F, s, 2);
-    s += __shfl_xor_sync(F, s, 1);
-    return s;
-}
+// ---- backward ----
+// Staged per pair (64 bytes, four broadcast LDS.128 — two in the recompute sweep, two in the reverse walk):
+//   f0 {mx, my, l00, l01}  f1 {l10, l11, o, coverage mask}  |  r0 {mx, my, o, l0}  r1 {l1, l2, coverage mask, pair id}
+struct BSlot {
+    float4 f0, f1, r0, r1;
+};
+constexpr int BWD_WARPS = 4;
+struct __align__(16) BwdWarpSmem {
+    BSlot slot[32];             // 2 KB
+    float2 tg[SUB][32];         // 4 KB: (T local to the piece, Gaussian kernel value) of the sub-batch's pairs
+    float4 red[RG][2][32];      // 4 KB: the per-lane terms of RG pairs, waiting for their sums over the lanes
+};
 
-// partial[q] = {sum g dalpha, sum d, sum coef X0', sum coef X1', sum coef d0 d0, sum coef d0 d1, sum coef d1 d1, 0}
-// over the pixels of pair q (coef = alpha dalpha; X' = EXP2_SCALE X), see gs_model.py:733-766; the constant factors
-// -1/2 (d_Lambda) and EXP2_UNSCALE (d_mean) are applied to the per-Gaussian sums by k_tile_reduce
-__global__ void __launch_bounds__(TILE_WARPS * 32, 4)
-k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ pgid_s, const int4 *__restrict__ rec,
-                const int32_t *__restrict__ pstart, const int32_t *__restrict__ ptile, unsigned int *__restrict__ ticket,
-                int piece, const float *__restrict__ tkeep, const float *__restrict__ pstate,
+// partial[q] = {sum c, sum d, sum c d0, sum c d1, sum c d0 d0, sum c d0 d1, sum c d1 d1, -} over the pixels of
+// pair q, with c = g * dL/dalpha and d = T alpha <dL/dI, l>: the moments from which k_view_reduce forms the
+// reference's per-element gradients (gs_model.py:733-766) once per GAUSSIAN instead of once per pixel.
+//
+// The sums over the 32 lanes go through shared memory: each lane drops its 7 terms with two STS.128; after RG = 4
+// pairs lane j adds, for (pair j/8, term pair (j/2)%4), the 16 source lanes of half j%2 — sixteen conflict-free
+// LDS.64 (source lanes visited in an order XOR-permuted per lane) and 32 FADD per lane per 4 pairs — then the two
+// halves are added (one shuffle).  Every sum has a fixed order: bitwise reproducible.  (The halving butterfly this
+// replaces cost 9 shuffles + 14 selects + 9 adds per pair.)
+__global__ void __launch_bounds__(BWD_WARPS * 32)
+k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart,
+                const int32_t *__restrict__ pextra, const int32_t *__restrict__ ptile_x,
+                const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, unsigned int *__restrict__ hdr,
+                int piece, const float *__restrict__ tck, const float *__restrict__ pstate,
                 const float *__restrict__ gimg, int ntx, int ntiles, int W, int H, float *__restrict__ partial) {
-    __shared__ PairSlot slots[TILE_WARPS][32];
+    __shared__ BwdWarpSmem smem[BWD_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    PairSlot *sl = slots[wib];
-    const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    float *const pcomp = partial + comp;   // the component this lane's group ends up holding after reduce8
-    const int npieces = __ldg(pstart + ntiles);
+    BwdWarpSmem *ws = &smem[wib];
+    // lane constants of the cross-lane sums: sum s = lane/2 -> pair s/4 of the group, terms 2*(s%4), 2*(s%4)+1;
+    // this lane adds the source lanes of half lane%2 in the order 16*half + (i ^ rx), i = 0..15
+    const int rs = lane >> 1, rhalf = lane & 1, rg = rs >> 2, rcp = rs & 3;
+    const int rx = rhalf | (((rs >> 1) & 3) << 1);
+    const float *red_base = &ws->red[rg][rcp >> 1][16 * rhalf].x + 2 * (rcp & 1);
+    const float *red_p[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red_p[k] = red_base + 4 * (k ^ rx);
+    const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
-    while (next_piece(ticket, tstart, pstart, ptile, npieces, piece, lane, w)) {
+    while (next_piece(hdr + H_TICKET_BWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
+        if (w.t < 0) continue;
         const int t = w.t;
-        const int64_t lo = w.lo, hi = w.hi;
+        const int lo = w.lo, hi = w.hi;
         if (lo >= hi) continue;
         const int ty = t / ntx, tx = t - ty * ntx;
         const int x0 = tx << TSX, y0 = ty << TSY;
@@ -493,216 +643,280 @@ k_tile_backward(const int32_t *__restrict__ tstart, const int32_t *__restrict__ 
         // a piece of a longer list starts from the carries the combine kernels left: T = carry * Tlocal, U = U_in
         float carry = 1.0f, U = 0.0f;
         if (w.np > 1) {
-            const float *ps = pstate + static_cast<int64_t>(w.p) * PIECE_STATE + lane;
+            const float *ps = pstate + static_cast<int64_t>(w.slot) * PIECE_STATE + lane;
             carry = __ldg(ps + 128);
             U = __ldg(ps + 160);
         }
-        // batches of 32 pairs from the END of the piece: [bb, be), be = hi, hi - 32, ...
+        // batches of 32 pairs, aligned to the piece start, from the last one down
+        const int last = lo + ((hi - lo - 1) & ~31);
         int g1 = 0;
         RecRegs r = {};
-        {
-            const int64_t bb = (hi - 32 > lo) ? hi - 32 : lo;
-            if (bb + lane < hi) r = load_rec(rec, __ldg(pgid_s + bb + lane));
-            const int64_t b1 = (bb - 32 > lo) ? bb - 32 : lo;
-            if (b1 + lane < bb) g1 = __ldg(pgid_s + b1 + lane);
-        }
-        // the kept T of the four pairs walked next, loaded one group (four pairs) ahead of their use, across batch
-        // boundaries: every batch but the last one walked holds 32 pairs, so the groups never straddle a batch
-        const float *tl = tkeep + lane;
-        float tc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tc[j] = (hi - 1 - j >= lo) ? __ldcs(tl + (hi - 1 - j) * 32) : 0.0f;
-        for (int64_t be = hi; be > lo;) {
-            const int64_t bb = (be - 32 > lo) ? be - 32 : lo;
-            const int m = static_cast<int>(be - bb);
-            stage_pair(sl + lane, r, lane < m, tx, ty, x0, y0);
-            // next batch [b1, bb), the one after [b2, b1)
-            const int64_t b1 = (bb - 32 > lo) ? bb - 32 : lo;
-            const int64_t b2 = (b1 - 32 > lo) ? b1 - 32 : lo;
+        if (last + lane < hi) r = load_rec(rec, __ldg(pgid + last + lane));
+        if (last > lo) g1 = __ldg(pgid + last - 32 + lane);
+        const float *ckl = tck + lane;
+        // checkpoint of the sub-batch walked next, loaded one sub-batch ahead
+        float tnext = __ldcs(ckl + (static_cast<int64_t>(last + ((hi - last - 1) & ~(SUB - 1))) >> 4) * 32);
+        for (int bb = last; bb >= lo; bb -= 32) {
+            const int m = min(hi - bb, 32);
+            {
+                const uint32_t mask = coverage_mask(r, lane < m, x0, y0);
+                const int q = pair_id(r, tx, ty);
+                BSlot &s = ws->slot[lane];
+                s.f0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
+                s.f1 = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
+                s.r0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.b.z), i2f(r.b.w));
+                s.r1 = make_float4(i2f(r.c.x), i2f(r.c.y), __uint_as_float(mask), i2f(q));
+            }
             int g2 = 0;
-            if (b2 + lane < b1) g2 = __ldg(pgid_s + b2 + lane);
-            if (b1 + lane < bb) r = load_rec(rec, g1);
+            if (bb - 64 >= lo) g2 = __ldg(pgid + bb - 64 + lane);
+            if (bb - 32 >= lo) r = load_rec(rec, g1);
             g1 = g2;
             __syncwarp();
-            for (int k0 = m - 1; k0 >= 0; k0 -= 4) {
-                float tn[4];
-                const int64_t pn = bb + k0 - 4;   // first pair of the next group
-#pragma unroll
-                for (int j = 0; j < 4; ++j) tn[j] = (pn - j >= lo) ? __ldcs(tl + (pn - j) * 32) : 0.0f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = k0 - j;
-                    if (k < 0) break;   // warp-uniform (last batch walked only)
-                    const float4 A = sl[k].a, B = sl[k].b;
-                    const float2 C = sl[k].c;
-                    const bool cov = (sl[k].mask >> lane) & 1u;
-                    const int q = sl[k].q;
-                    const float T = carry * tc[j];
-                    const PairEval e = eval_pair(A, B, px, py);
-                    const bool alive = cov && (T * e.x != 0.0f);
-                    const float alpha = 1.0f - e.x;
-                    const float pgl = pg0 * B.w + pg1 * C.x + pg2 * C.y;
-                    const float dalpha = alive ? T * pgl - T * U : 0.0f;
-                    const float d = alive ? T * alpha * pgl : 0.0f;
-                    U = cov ? fmaf(e.x, U, alive ? alpha * pgl : 0.0f) : U;   // U_{i-1} = w_i + x_i U_i
-                    // per-pixel terms of gs_model.py:733-766 WITHOUT their constant factors (-1/2 for d_Lambda,
-                    // EXP2_UNSCALE for d_mean because X0, X1 carry EXP2_SCALE): k_tile_reduce applies them to the sums
-                    const float coef = B.z * e.gk * dalpha;
-                    const float c0 = coef * e.d0, c1 = coef * e.d1;
-                    float v[8] = {e.gk * dalpha, d, coef * e.X0, coef * e.X1, c0 * e.d0, c0 * e.d1, c1 * e.d1, 0.0f};
-                    const float s = reduce8(v, lane);
-                    if ((lane & 3) == 0) pcomp[static_cast<int64_t>(q) * 8] = s;
+            for (int sb = (m - 1) >> 4; sb >= 0; --sb) {   // sub-batches of SUB = 16 pairs, the later one first
+                const int s0 = sb * SUB, ms = min(m - s0, SUB);
+                float T = tnext;
+                {   // the checkpoint after this one in walking order: the previous sub-batch of the piece
+                    const int nb = bb + s0 - SUB;
+                    if (nb >= lo) tnext = __ldcs(ckl + (static_cast<int64_t>(nb) >> 4) * 32);
                 }
+                // (1) recompute sweep, forward: T and g of every (pair, lane) of the sub-batch
+#pragma unroll 4
+                for (int k = 0; k < ms; ++k) {
+                    const float4 A = ws->slot[s0 + k].f0, B = ws->slot[s0 + k].f1;
+                    const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
+                    const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
+                    ws->tg[k][lane] = make_float2(T, e.gk);
+                    T = cov ? T * e.x : T;
+                }
+                // (2) reverse walk, RG pairs per cross-lane reduction
+                for (int g0 = (ms - 1) & ~(RG - 1); g0 >= 0; g0 -= RG) {
+                    const int gn = min(ms - g0, RG);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tc[j] = tn[j];
+                    for (int j = RG - 1; j >= 0; --j) {
+                        if (j >= gn) continue;   // warp-uniform (last group of a sub-batch only)
+                        const int k = g0 + j;
+                        const float4 R0 = ws->slot[s0 + k].r0, R1 = ws->slot[s0 + k].r1;
+                        const float2 tg = ws->tg[k][lane];
+                        const bool cov = (__float_as_uint(R1.z) >> lane) & 1u;
+                        const float Tt = carry * tg.x, gk = tg.y;
+                        const float d0 = px - R0.x, d1 = py - R0.y;
+                        const float alpha = R0.z * gk, x = 1.0f - alpha;
+                        const bool alive = cov && (Tt * x != 0.0f);
+                        const float pgl = pg0 * R0.w + pg1 * R1.x + pg2 * R1.y;
+                        const float wv = alive ? alpha * pgl : 0.0f;
+                        const float dalpha = alive ? Tt * (pgl - U) : 0.0f;
+                        const float d = Tt * wv;
+                        U = cov ? fmaf(x, U, wv) : U;   // U_{i-1} = w_i + x_i U_i
+                        const float c = gk * dalpha;
+                        const float cd0 = c * d0, cd1 = c * d1;
+                        ws->red[j][0][lane] = make_float4(c, d, cd0, cd1);
+                        ws->red[j][1][lane] = make_float4(cd0 * d0, cd0 * d1, cd1 * d1, 0.0f);
+                    }
+                    __syncwarp();
+                    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 v = *reinterpret_cast<const float2 *>(red_p[i & 7] + (i & 8) * 4);
+                        a0 += v.x;
+                        a1 += v.y;
+                    }
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                    if (rhalf == 0 && rg < gn) {
+                        const int q = __float_as_int(ws->slot[s0 + g0 + rg].r1.w);
+                        *reinterpret_cast<float2 *>(partial + static_cast<int64_t>(q) * 8 + 2 * rcp) = make_float2(a0, a1);
+                    }
+                    __syncwarp();
+                }
             }
             __syncwarp();
-            be = bb;
         }
     }
 }
 
-// lane c of a group of 8 owns component c of a Gaussian's gradient sums and writes what derives from it:
-// d_l[k] = (sum d) / l[k] is the reference's d / l (gs_model.py:763-766)
-__device__ __forceinline__ void store_component(int c, float s, int64_t g, const float *__restrict__ l_d,
-                                                float *__restrict__ g_mean, float *__restrict__ g_lam,
-                                                float *__restrict__ g_opac, float *__restrict__ g_l) {
-    // constant factors the backward walk left out of its per-pixel terms
-    if (c == 2 || c == 3) s *= EXP2_UNSCALE;
-    if (c >= 4 && c <= 6) s *= -0.5f;
+// ---- per-Gaussian sums ----
+constexpr int RED_BIG = 64;  // Gaussians with more pairs than this go to k_view_reduce_big (one block each)
+
+// lane c of a group of 8 holds sum c of a Gaussian's partials; what the reference's per-element formulas
+// (gs_model.py:733-766) give when summed over the Gaussian's pixels, with X = d Lambda, coef = o g dalpha:
+//   d_opacity = sum g dalpha                      = S0                    (the d/o term of :739 cancels in dalpha)
+//   d_l[k]    = (sum d) / l[k]                    = S1 / l[k]             (:763-766)
+//   d_mean    = sum coef X                        = o Lambda^T (S2, S3)   (:743-750)
+//   d_Lambda  = -1/2 sum coef d^T d               = -o/2 [[S4, S5], [S5, S6]]   (:753-760)
+__device__ __forceinline__ void store_sums(int c, float s, float s_other, bool active, int64_t g,
+                                           const int4 *__restrict__ rec, float *__restrict__ g_mean,
+                                           float *__restrict__ g_lam, float *__restrict__ g_opac,
+                                           float *__restrict__ g_l) {
+    if (!active) return;
+    const int4 ra = __ldg(rec + 4 * g), rb = __ldg(rec + 4 * g + 1);
+    const float o = i2f(rb.z);
     switch (c) {
         case 0: g_opac[g] = s; break;
-        case 1:
-            g_l[3 * g] = s / __ldg(l_d + 3 * g);
-            g_l[3 * g + 1] = s / __ldg(l_d + 3 * g + 1);
-            g_l[3 * g + 2] = s / __ldg(l_d + 3 * g + 2);
+        case 1: {
+            const int4 rc = __ldg(rec + 4 * g + 2);
+            g_l[3 * g] = s / i2f(rb.w);
+            g_l[3 * g + 1] = s / i2f(rc.x);
+            g_l[3 * g + 2] = s / i2f(rc.y);
             break;
-        case 2: g_mean[2 * g] = s; break;
-        case 3: g_mean[2 * g + 1] = s; break;
-        case 4: g_lam[4 * g] = s; break;
-        case 5: g_lam[4 * g + 1] = s; g_lam[4 * g + 2] = s; break;
-        case 6: g_lam[4 * g + 3] = s; break;
+        }
+        // the records hold Lambda' = EXP2_SCALE Lambda
+        case 2: g_mean[2 * g] = EXP2_UNSCALE * o * (i2f(ra.z) * s + i2f(rb.x) * s_other); break;
+        case 3: g_mean[2 * g + 1] = EXP2_UNSCALE * o * (i2f(ra.w) * s_other + i2f(rb.y) * s); break;
+        case 4: g_lam[4 * g] = -0.5f * o * s; break;
+        case 5: g_lam[4 * g + 1] = -0.5f * o * s; g_lam[4 * g + 2] = -0.5f * o * s; break;
+        case 6: g_lam[4 * g + 3] = -0.5f * o * s; break;
         default: break;
     }
 }
 
-constexpr int RED_BIG = 64;  // Gaussians with more pairs than this go to k_tile_reduce_big (one block each)
-
-// 8 lanes per Gaussian: lane c adds component c of the Gaussian's partials in pair order.  Gaussians with more than
+// 8 lanes per Gaussian: lane c adds term c of the Gaussian's partials in pair order.  Gaussians with more than
 // RED_BIG pairs (boxes of thousands of pixels, bundled scene) are appended to `big` instead; the order of that
 // list does not enter any float sum.
 __global__ void __launch_bounds__(256)
-k_tile_reduce(const float *__restrict__ partial, const int64_t *__restrict__ toff, const float *__restrict__ l_d,
+k_view_reduce(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
               int64_t n, float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
-              float *__restrict__ g_l, unsigned int *__restrict__ nbig, int32_t *__restrict__ big) {
+              float *__restrict__ g_l, unsigned int *__restrict__ hdr, int32_t *__restrict__ big) {
     const int c = threadIdx.x & 7;
     const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
-    if (g >= n) return;
-    const int64_t b = __ldg(toff + g), e = __ldg(toff + g + 1);
-    if (e - b > RED_BIG) {
-        if (c == 0) big[atomicAdd(nbig, 1u)] = static_cast<int32_t>(g);
-        return;
+    bool active = g < n;
+    int b = 0, e = 0;
+    if (active) {
+        b = __ldg(toff + g);
+        e = __ldg(toff + g + 1);
+        if (e - b > RED_BIG) {
+            if (c == 0) big[atomicAdd(hdr + H_NBIG, 1u)] = static_cast<int32_t>(g);
+            active = false;
+            e = b;
+        }
     }
     float s = 0.0f;
-    int64_t q = b;
+    int q = b;
     for (; q + 4 <= e; q += 4) {
-        const float v0 = __ldcs(partial + q * 8 + c), v1 = __ldcs(partial + (q + 1) * 8 + c);
-        const float v2 = __ldcs(partial + (q + 2) * 8 + c), v3 = __ldcs(partial + (q + 3) * 8 + c);
+        const float *p = partial + static_cast<int64_t>(q) * 8 + c;
+        const float v0 = __ldcs(p), v1 = __ldcs(p + 8), v2 = __ldcs(p + 16), v3 = __ldcs(p + 24);
         s += v0; s += v1; s += v2; s += v3;
     }
-    for (; q < e; ++q) s += __ldcs(partial + q * 8 + c);
-    store_component(c, s, g, l_d, g_mean, g_lam, g_opac, g_l);
+    for (; q < e; ++q) s += __ldcs(partial + static_cast<int64_t>(q) * 8 + c);
+    const float s_other = __shfl_xor_sync(0xffffffffu, s, 1);   // lanes 2 <-> 3: the two first moments
+    store_sums(c, s, s_other, active, g, rec, g_mean, g_lam, g_opac, g_l);
 }
 
 // one block per big Gaussian: 32 groups of 8 lanes stride over its pairs (group j takes pairs j, j+32, ...), the 32
 // group sums are added in group order — a fixed order, bitwise reproducible
 __global__ void __launch_bounds__(256)
-k_tile_reduce_big(const float *__restrict__ partial, const int64_t *__restrict__ toff, const float *__restrict__ l_d,
+k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
                   float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
-                  float *__restrict__ g_l, const unsigned int *__restrict__ nbig, const int32_t *__restrict__ big) {
+                  float *__restrict__ g_l, const unsigned int *__restrict__ hdr, const int32_t *__restrict__ big) {
     __shared__ float sums[32][8];
     const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
-    const unsigned int nb = *nbig;
+    const unsigned int nb = hdr[H_NBIG];
     for (unsigned int i = blockIdx.x; i < nb; i += gridDim.x) {
         const int64_t g = __ldg(big + i);
-        const int64_t b = __ldg(toff + g), e = __ldg(toff + g + 1);
+        const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
         float s = 0.0f;
-        int64_t q = b + j;
+        int q = b + j;
         for (; q + 96 < e; q += 128) {
-            const float v0 = __ldcs(partial + q * 8 + c), v1 = __ldcs(partial + (q + 32) * 8 + c);
-            const float v2 = __ldcs(partial + (q + 64) * 8 + c), v3 = __ldcs(partial + (q + 96) * 8 + c);
+            const float *p = partial + static_cast<int64_t>(q) * 8 + c;
+            const float v0 = __ldcs(p), v1 = __ldcs(p + 32 * 8), v2 = __ldcs(p + 64 * 8), v3 = __ldcs(p + 96 * 8);
             s += v0; s += v1; s += v2; s += v3;
         }
-        for (; q < e; q += 32) s += __ldcs(partial + q * 8 + c);
+        for (; q < e; q += 32) s += __ldcs(partial + static_cast<int64_t>(q) * 8 + c);
         sums[j][c] = s;
         __syncthreads();
         if (j == 0) {
             float t = 0.0f;
 #pragma unroll
             for (int k = 0; k < 32; ++k) t += sums[k][c];
-            store_component(c, t, g, l_d, g_mean, g_lam, g_opac, g_l);
+            const float t_other = __shfl_xor_sync(0xffu, t, 1);
+            store_sums(c, t, t_other, true, g, rec, g_mean, g_lam, g_opac, g_l);
         }
         __syncthreads();
     }
 }
 
-struct BinLayout {
-    size_t ptile, pgid, ptile_s, cub, total, cub_bytes;
-};
-BinLayout bin_layout(int64_t P, int ntiles) {
-    BinLayout L;
-    const size_t pb = align256(static_cast<size_t>(P > 0 ? P : 1) * 4);
-    size_t a = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
-                                    static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
-                                    P > 0 ? P : 1, 0, 24);
-    size_t b = 0;   // the scan of the tiles' piece counts shares the sort's scratch
-    cub::DeviceScan::InclusiveSum(nullptr, b, static_cast<const int32_t *>(nullptr), static_cast<int32_t *>(nullptr),
-                                  ntiles > 0 ? ntiles : 1);
-    L.cub_bytes = align256(std::max(a, b) + 256);
-    L.ptile = 0;
-    L.pgid = L.ptile + pb;
-    L.ptile_s = L.pgid + pb;
-    L.cub = L.ptile_s + pb;
-    L.total = L.cub + L.cub_bytes;
-    return L;
-}
-
-// persistent grid of the walk kernels: every resident warp slot of the device, never more warps than tiles
-unsigned walk_grid(const void *kernel, int64_t nwork) {
-    static const void *known[2] = {nullptr, nullptr};
-    static unsigned slots[2] = {0, 0};  // resident blocks of the (two) walk kernels, queried once
-    int i = (known[0] == kernel || known[0] == nullptr) ? 0 : 1;
-    if (known[i] != kernel) {
-        int dev = 0, sms = 148, per_sm = 4;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_WARPS * 32, 0) != cudaSuccess ||
-            per_sm < 1)
-            per_sm = 1;
-        slots[i] = static_cast<unsigned>(sms * per_sm);
-        known[i] = kernel;
-    }
-    return std::max(1u, std::min(blocks_for(nwork, TILE_WARPS), slots[i]));
-}
-
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
 int g_piece = 128;  // pairs per piece (gcp_tile_set_piece_pairs)
 
 inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >= 32768; }
 inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
 inline int tiles_y(int H) { return (H + TH) >> TSY; }
 
-// views into the piece_plan buffer: piece_start[ntiles+1] | piece_tile[cap] | 4 counter words
-struct PlanView {
-    const int32_t *pstart, *ptile;
-    unsigned int *tickets;
-    int64_t cap;
+// plan arena: everything whose size is known from (n, W, H) alone.  [0, zero_bytes) is cleared by gcp_view_plan.
+struct PlanLayout {
+    size_t hdr, desc1, desc2, tcount, cursor, zero_bytes, cnt, toff, tstart, pextra, mlist, longlist, big, rec, total;
+    unsigned nb1, nb2;
 };
-PlanView plan_view(int32_t *piece_plan, int64_t P, int W, int H) {
-    const int ntiles = tiles_x(W) * tiles_y(H);
-    const int64_t cap = gcp_tile_piece_cap(P, W, H);
-    return PlanView{piece_plan, piece_plan + ntiles + 1,
-                    reinterpret_cast<unsigned int *>(piece_plan + ntiles + 1 + cap), cap};
+PlanLayout plan_layout(int64_t n, int ntiles) {
+    PlanLayout L;
+    L.nb1 = blocks_for(n, SCAN_TILE);
+    L.nb2 = blocks_for(ntiles, SCAN_TILE);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
+    L.hdr = take(HDR_WORDS * 4);
+    L.desc1 = take(static_cast<size_t>(L.nb1) * 8);
+    L.desc2 = take(static_cast<size_t>(L.nb2) * 8);
+    L.tcount = take(static_cast<size_t>(ntiles) * 4);
+    L.cursor = take(static_cast<size_t>(ntiles) * 4);
+    L.zero_bytes = o;
+    L.cnt = take(static_cast<size_t>(n > 0 ? n : 1) * 4);
+    L.toff = take(static_cast<size_t>(n + 1) * 4);
+    L.tstart = take(static_cast<size_t>(ntiles + 1) * 4);
+    L.pextra = take(static_cast<size_t>(ntiles) * 4);
+    L.mlist = take(static_cast<size_t>(ntiles) * 4);
+    L.longlist = take(static_cast<size_t>(ntiles) * 4);
+    L.big = take(static_cast<size_t>(n > 0 ? n : 1) * 4);
+    L.rec = take(static_cast<size_t>(n > 0 ? n : 1) * 64);
+    L.total = o;
+    return L;
 }
+// pair arena: everything sized by the (padded) pair capacity
+struct PairLayout {
+    size_t pgid, tck, ptile_x, pstate, partial, total;
+    int64_t xcap;
+};
+PairLayout pair_layout(int64_t cap) {
+    PairLayout L;
+    if (cap < SUB) cap = SUB;
+    L.xcap = 2 * (cap / g_piece) + 2;   // slots of the extra-piece table: sum over multi-piece tiles of their pieces
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
+    L.pgid = take(static_cast<size_t>(cap) * 4);
+    L.tck = take(static_cast<size_t>(cap / SUB + 1) * 32 * 4);
+    L.ptile_x = take(static_cast<size_t>(L.xcap) * 4);
+    L.pstate = take(static_cast<size_t>(L.xcap) * PIECE_STATE * 4);
+    L.partial = take(static_cast<size_t>(cap) * 32);
+    L.total = o;
+    return L;
+}
+
+// persistent grid of the walk kernels: every resident warp slot of the device
+unsigned walk_grid(const void *kernel, int threads) {
+    static const void *known[4] = {nullptr, nullptr, nullptr, nullptr};
+    static unsigned slots[4] = {0, 0, 0, 0};
+    int i = 0;
+    while (i < 3 && known[i] != nullptr && known[i] != kernel) ++i;
+    if (known[i] != kernel) {
+        int dev = 0, sms = 148, per_sm = 1;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        slots[i] = static_cast<unsigned>(sms * per_sm);
+        known[i] = kernel;
+    }
+    return std::max(1u, slots[i]);
+}
+
+template <typename T>
+inline T *at(void *base, size_t off) { return reinterpret_cast<T *>(static_cast<unsigned char *>(base) + off); }
+template <typename T>
+inline const T *at(const void *base, size_t off) {
+    return reinterpret_cast<const T *>(static_cast<const unsigned char *>(base) + off);
+}
+
+thread_local int t_view_launches = 0;
+
 }  // namespace
 
 extern "C" {
@@ -710,179 +924,147 @@ extern "C" {
 int gcp_tile_width(void) { return TW; }
 int gcp_tile_height(void) { return TH; }
 int gcp_tile_num_tiles(int W, int H) { return bad_image(W, H) ? 0 : tiles_x(W) * tiles_y(H); }
-/* longest run of one tile's pairs a single warp walks (multiple of 32); longer lists are cut into pieces */
 int gcp_tile_set_piece_pairs(int pairs) {
     if (pairs < 32 || pairs > (1 << 20) || (pairs & 31)) return GCP_ERR_INVALID_ARG;
     g_piece = pairs;
     return GCP_OK;
 }
 int gcp_tile_piece_pairs(void) { return g_piece; }
-int64_t gcp_tile_piece_cap(int64_t P, int W, int H) {
-    return (P < 0 || bad_image(W, H)) ? 0 : tiles_x(W) * tiles_y(H) + P / g_piece + 1;
-}
-/* piece_plan i32[]: piece_start[ntiles+1] | piece_tile[cap] | 4 counter words */
-int64_t gcp_tile_plan_ints(int64_t P, int W, int H) {
-    return (P < 0 || bad_image(W, H)) ? 0 : tiles_x(W) * tiles_y(H) + 1 + gcp_tile_piece_cap(P, W, H) + 4;
-}
-int64_t gcp_tile_state_floats(int64_t P, int W, int H) { return gcp_tile_piece_cap(P, W, H) * PIECE_STATE; }
+int gcp_view_last_launch_count(void) { return t_view_launches; }
 
-size_t gcp_tile_prepare_bytes(int64_t n) {
-    size_t a = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, a, static_cast<const int64_t *>(nullptr), static_cast<int64_t *>(nullptr),
-                                  n > 0 ? n : 1);
-    return a + 256;
+size_t gcp_view_plan_bytes(int64_t n, int W, int H) {
+    return (n < 0 || bad_image(W, H)) ? 0 : plan_layout(n, tiles_x(W) * tiles_y(H)).total;
 }
-
-int gcp_tile_prepare(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, int64_t *toff, int64_t *totals,
-                     void *temp, size_t temp_bytes, gcp_stream_t stream) {
-    if (n < 0 || bad_image(W, H) || !toff || !totals) return GCP_ERR_INVALID_ARG;
-    auto st = reinterpret_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(toff, 0, 8, st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    if (n > 0) {
-        if (!sp || !ep || !temp) return GCP_ERR_INVALID_ARG;
-        auto pairs = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0),
-                                                     TilePairCount{sp, ep, W, H});
-        size_t need = 0;
-        cub::DeviceScan::InclusiveSum(nullptr, need, pairs, toff + 1, n);
-        if (temp_bytes < need) return GCP_ERR_WORKSPACE;
-        size_t tb = temp_bytes;
-        e = cub::DeviceScan::InclusiveSum(temp, tb, pairs, toff + 1, n, st);
-        if (e != cudaSuccess) return static_cast<int>(e);
-    }
-    k_tile_totals<<<1, 1, 0, st>>>(toff, n, totals);
-    return static_cast<int>(cudaGetLastError());
+size_t gcp_view_pair_bytes(int64_t pair_cap, int W, int H) {
+    return (pair_cap < 0 || bad_image(W, H)) ? 0 : pair_layout(pair_cap).total;
+}
+/* byte offsets of the arrays tests compare bit for bit: out[0..5] = toff, tcount, tstart, pextra (plan arena);
+ * out[6..7] = pgid, ptile_x (pair arena); out[8] = slots of ptile_x */
+int gcp_view_layout(int64_t n, int W, int H, int64_t pair_cap, int64_t *out) {
+    if (n < 0 || bad_image(W, H) || pair_cap < 0 || !out) return GCP_ERR_INVALID_ARG;
+    const PlanLayout A = plan_layout(n, tiles_x(W) * tiles_y(H));
+    const PairLayout B = pair_layout(pair_cap);
+    out[0] = static_cast<int64_t>(A.toff); out[1] = static_cast<int64_t>(A.tcount); out[2] = static_cast<int64_t>(A.tstart);
+    out[3] = static_cast<int64_t>(A.pextra); out[4] = static_cast<int64_t>(A.hdr); out[5] = static_cast<int64_t>(A.rec);
+    out[6] = static_cast<int64_t>(B.pgid); out[7] = static_cast<int64_t>(B.ptile_x); out[8] = B.xcap;
+    return GCP_OK;
 }
 
-int gcp_tile_pack(const float *mean, const float *lam, const float *opac, const float *l_d, const int32_t *sp,
-                  const int32_t *ep, const int64_t *toff, int64_t n, int W, int H, int32_t *rec,
-                  gcp_stream_t stream) {
-    if (n < 0 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
-    if (n == 0) return GCP_OK;
-    if (!mean || !lam || !opac || !l_d || !sp || !ep || !toff || !rec) return GCP_ERR_INVALID_ARG;
-    if (reinterpret_cast<uintptr_t>(rec) & 31) return GCP_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(mean) & 7) || (reinterpret_cast<uintptr_t>(lam) & 15)) return GCP_ERR_INVALID_ARG;
-    k_tile_pack<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        mean, lam, opac, l_d, sp, ep, toff, n, W, H, reinterpret_cast<int4 *>(rec));
-    return static_cast<int>(cudaGetLastError());
-}
-
-size_t gcp_tile_bin_bytes(int64_t P, int W, int H) {
-    return (P < 0 || bad_image(W, H)) ? 0 : bin_layout(P, tiles_x(W) * tiles_y(H)).total;
-}
-
-static int tile_bin_impl(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W,
-                         int H, int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp,
-                         size_t temp_bytes, gcp_stream_t stream, bool speculative) {
-    if (n < 0 || P < 0 || P >= (int64_t(1) << 31) - 64 || bad_image(W, H)) return GCP_ERR_INVALID_ARG;
-    if (!tile_start || !piece_plan || !temp || (P > 0 && (!sp || !ep || !toff || !pair_gid)))
+int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, void *plan, size_t plan_bytes,
+                  int64_t *totals_host, gcp_stream_t stream) {
+    t_view_launches = 0;
+    if (n < 0 || n >= (int64_t(1) << 31) - 64 || bad_image(W, H) || !plan) return GCP_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(plan) & 255) return GCP_ERR_WORKSPACE;
+    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    const PlanLayout L = plan_layout(n, ntiles);
+    if (plan_bytes < L.total) return GCP_ERR_WORKSPACE;
+    if (n > 0 && (!sp || !ep || (reinterpret_cast<uintptr_t>(sp) & 7) || (reinterpret_cast<uintptr_t>(ep) & 7)))
         return GCP_ERR_INVALID_ARG;
-    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    const BinLayout L = bin_layout(P, ntiles);
-    if (temp_bytes < L.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
-    unsigned char *t = static_cast<unsigned char *>(temp);
-    int32_t *ptile = reinterpret_cast<int32_t *>(t + L.ptile), *pgid = reinterpret_cast<int32_t *>(t + L.pgid);
-    int32_t *ptile_s = reinterpret_cast<int32_t *>(t + L.ptile_s);
-    cudaError_t e;
-    if (P > 0) {
-        if (P <= 6 * n)   // small boxes: a thread per Gaussian; boxes of many tiles: parallel over the pairs
-            k_tile_pairs<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
-        else
-            k_tile_pairs_flat<<<blocks_for(P, 256 * CHP), 256, 0, st>>>(sp, ep, toff, n, P, W, H, ntx, ptile, pgid);
-        if (speculative)   // P is a capacity here: mark the slots behind the real pairs
-            k_tile_pad<<<blocks_for(P / 4 + 1, 256, 1024), 256, 0, st>>>(toff, n, P, ntiles, ptile, pgid);
-        size_t cb = L.cub_bytes;
-        // stable LSD radix sort on the tile bits only: inside a tile the Gaussians keep their (depth) order
-        e = cub::DeviceRadixSort::SortPairs(t + L.cub, cb, ptile, ptile_s, pgid, pair_gid, P, 0, key_bits(ntiles), st);
-        if (e != cudaSuccess) return static_cast<int>(e);
+    cudaError_t e = cudaMemsetAsync(plan, 0, L.zero_bytes, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    unsigned int *hdr = at<unsigned int>(plan, L.hdr);
+    if (n == 0) {
+        k_view_scan_empty<<<1, 256, 0, st>>>(at<int32_t>(plan, L.toff), at<int32_t>(plan, L.tstart), ntiles, hdr,
+                                             totals_host);
+        ++t_view_launches;
+        return static_cast<int>(cudaGetLastError());
     }
-    k_tile_start<<<blocks_for(P + 1, 256), 256, 0, st>>>(ptile_s, P, ntiles, tile_start);
-    // the pieces: exclusive offsets per tile, then the tile of every piece
-    int32_t *pstart = piece_plan, *piece_tile = piece_plan + ntiles + 1;
-    e = cudaMemsetAsync(pstart, 0, sizeof(int32_t), st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    auto counts = thrust::make_transform_iterator(thrust::counting_iterator<int32_t>(0), PieceCount{tile_start, g_piece});
-    size_t need = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, need, counts, pstart + 1, ntiles);
-    if (need > L.cub_bytes) return GCP_ERR_WORKSPACE;
-    size_t cb = L.cub_bytes;
-    e = cub::DeviceScan::InclusiveSum(t + L.cub, cb, counts, pstart + 1, ntiles, st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    k_tile_pieces<<<blocks_for(ntiles, 256), 256, 0, st>>>(pstart, ntiles, piece_tile);
+    k_view_count<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, n, W, H, ntx, at<int32_t>(plan, L.cnt),
+                                                     at<int32_t>(plan, L.tcount));
+    k_view_scan<<<L.nb1 + L.nb2, SCAN_THREADS, 0, st>>>(
+        at<int32_t>(plan, L.cnt), n, at<int32_t>(plan, L.toff), at<int32_t>(plan, L.tcount), ntiles,
+        at<int32_t>(plan, L.tstart), L.nb1, hdr, at<unsigned long long>(plan, L.desc1),
+        at<unsigned long long>(plan, L.desc2), totals_host);
+    t_view_launches += 2;
     return static_cast<int>(cudaGetLastError());
 }
 
-int gcp_tile_bin(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t P, int W, int H,
-                 int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp, size_t temp_bytes,
-                 gcp_stream_t stream) {
-    return tile_bin_impl(sp, ep, toff, n, P, W, H, tile_start, piece_plan, pair_gid, temp, temp_bytes, stream, false);
-}
-
-int gcp_tile_bin_speculative(const int32_t *sp, const int32_t *ep, const int64_t *toff, int64_t n, int64_t cap, int W,
-                             int H, int32_t *tile_start, int32_t *piece_plan, int32_t *pair_gid, void *temp,
-                             size_t temp_bytes, gcp_stream_t stream) {
-    return tile_bin_impl(sp, ep, toff, n, cap, W, H, tile_start, piece_plan, pair_gid, temp, temp_bytes, stream, true);
-}
-
-int gcp_tile_render(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
-                    int64_t P, int W, int H, float *image, float *t_keep, float *piece_state, gcp_stream_t stream) {
-    if (P < 0 || bad_image(W, H) || !tile_start || !piece_plan || !image || !piece_state) return GCP_ERR_INVALID_ARG;
-    if (P > 0 && (!pair_gid || !rec)) return GCP_ERR_INVALID_ARG;   // t_keep may be NULL: forward only
-    auto st = reinterpret_cast<cudaStream_t>(stream);
+int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, const float *lam, const float *opac,
+                    const float *l_d, int64_t n, int W, int H, void *plan, size_t plan_bytes, void *pairs,
+                    size_t pair_bytes, int64_t pair_cap, int keep, float *image, gcp_stream_t stream) {
+    t_view_launches = 0;
+    if (n < 0 || bad_image(W, H) || !plan || !pairs || !image || pair_cap < 0 || pair_cap >= (int64_t(1) << 31) - 64)
+        return GCP_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(plan) & 255) || (reinterpret_cast<uintptr_t>(pairs) & 255)) return GCP_ERR_WORKSPACE;
+    if (n > 0 && (!sp || !ep || !mean || !lam || !opac || !l_d)) return GCP_ERR_INVALID_ARG;
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    const PlanView pv = plan_view(piece_plan, P, W, H);
-    cudaError_t e = cudaMemsetAsync(pv.tickets, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_tile_render<true>), pv.cap);
-    if (t_keep != nullptr)
-        k_tile_render<true><<<grid, TILE_WARPS * 32, 0, st>>>(tile_start, pair_gid, reinterpret_cast<const int4 *>(rec),
-                                                              pv.pstart, pv.ptile, pv.tickets, g_piece, ntx, ntiles, W,
-                                                              H, image, t_keep, piece_state);
-    else
-        k_tile_render<false><<<grid, TILE_WARPS * 32, 0, st>>>(tile_start, pair_gid,
-                                                               reinterpret_cast<const int4 *>(rec), pv.pstart, pv.ptile,
-                                                               pv.tickets, g_piece, ntx, ntiles, W, H, image, t_keep,
-                                                               piece_state);
-    k_tile_combine_fwd<<<blocks_for(ntiles, 8), 256, 0, st>>>(pv.pstart, ntx, ntiles, W, H, piece_state, image);
-    return static_cast<int>(cudaGetLastError());
-}
-
-int gcp_tile_backward(const int32_t *tile_start, int32_t *piece_plan, const int32_t *pair_gid, const int32_t *rec,
-                      const float *t_keep, float *piece_state, const float *grad_image, int64_t P, int W, int H,
-                      float *partial, gcp_stream_t stream) {
-    if (P < 0 || bad_image(W, H) || !tile_start || !piece_plan || !grad_image) return GCP_ERR_INVALID_ARG;
-    if (P == 0) return GCP_OK;
-    if (!pair_gid || !rec || !t_keep || !partial || !piece_state) return GCP_ERR_INVALID_ARG;
+    const PlanLayout A = plan_layout(n, ntiles);
+    const PairLayout B = pair_layout(pair_cap);
+    if (plan_bytes < A.total || pair_bytes < B.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
-    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    const PlanView pv = plan_view(piece_plan, P, W, H);
-    cudaError_t e = cudaMemsetAsync(pv.tickets + 1, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    k_tile_combine_bwd<<<blocks_for(ntiles, 8), 256, 0, st>>>(pv.pstart, grad_image, ntx, ntiles, W, H, piece_state);
-    k_tile_backward<<<walk_grid(reinterpret_cast<const void *>(k_tile_backward), pv.cap), TILE_WARPS * 32, 0, st>>>(
-        tile_start, pair_gid, reinterpret_cast<const int4 *>(rec), pv.pstart, pv.ptile, pv.tickets + 1, g_piece,
-        t_keep, piece_state, grad_image, ntx, ntiles, W, H, partial);
+    unsigned int *hdr = at<unsigned int>(plan, A.hdr);
+    const int32_t *tcount = at<int32_t>(plan, A.tcount), *tstart = at<int32_t>(plan, A.tstart);
+    int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
+    int32_t *pgid = at<int32_t>(pairs, B.pgid);
+    int4 *rec = at<int4>(plan, A.rec);
+    if (n > 0)
+        k_view_fill<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, at<int32_t>(plan, A.toff), tstart,
+                                                        n, W, H, ntx, pair_cap, hdr, at<int32_t>(plan, A.cursor), rec,
+                                                        pgid);
+    k_view_sort<<<blocks_for(ntiles, 8), 256, 0, st>>>(tcount, tstart, ntiles, g_piece, pair_cap, hdr, pgid, pextra,
+                                                       ptile_x, at<int32_t>(plan, A.mlist),
+                                                       at<int32_t>(plan, A.longlist));
+    k_view_sort_long<<<296, 256, 0, st>>>(tcount, tstart, pair_cap, hdr, at<int32_t>(plan, A.longlist), pgid);
+    float *tck = at<float>(pairs, B.tck), *pstate = at<float>(pairs, B.pstate);
+    if (keep) {
+        const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_render<true>), TILE_WARPS * 32);
+        k_view_render<true><<<grid, TILE_WARPS * 32, 0, st>>>(tcount, tstart, pextra, ptile_x, pgid, rec, hdr, pair_cap,
+                                                              g_piece, ntx, ntiles, W, H, image, tck, pstate);
+    } else {
+        const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_render<false>), TILE_WARPS * 32);
+        k_view_render<false><<<grid, TILE_WARPS * 32, 0, st>>>(tcount, tstart, pextra, ptile_x, pgid, rec, hdr,
+                                                               pair_cap, g_piece, ntx, ntiles, W, H, image, tck, pstate);
+    }
+    k_view_combine_fwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, pair_cap, g_piece, ntx, W,
+                                           H, pstate, image);
+    t_view_launches += (n > 0 ? 5 : 4);
     return static_cast<int>(cudaGetLastError());
 }
 
-size_t gcp_tile_reduce_bytes(int64_t n) { return n < 0 ? 0 : 256 + align256(static_cast<size_t>(n) * 4); }
+int gcp_view_forward(const int32_t *sp, const int32_t *ep, const float *mean, const float *lam, const float *opac,
+                     const float *l_d, int64_t n, int W, int H, void *plan, size_t plan_bytes, void *pairs,
+                     size_t pair_bytes, int64_t pair_cap, int keep, float *image, int64_t *totals_host,
+                     gcp_stream_t stream) {
+    int rc = gcp_view_plan(sp, ep, n, W, H, plan, plan_bytes, totals_host, stream);
+    if (rc != GCP_OK) return rc;
+    const int l1 = t_view_launches;
+    rc = gcp_view_render(sp, ep, mean, lam, opac, l_d, n, W, H, plan, plan_bytes, pairs, pair_bytes, pair_cap, keep,
+                         image, stream);
+    t_view_launches += l1;
+    return rc;
+}
 
-int gcp_tile_reduce(const float *partial, const int64_t *toff, const float *l_d, int64_t n, float *g_mean,
-                    float *g_lam, float *g_opac, float *g_l, void *temp, size_t temp_bytes, gcp_stream_t stream) {
-    if (n < 0) return GCP_ERR_INVALID_ARG;
+int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
+                      const float *grad_image, int64_t n, int W, int H, float *g_mean, float *g_lam, float *g_opac,
+                      float *g_l, gcp_stream_t stream) {
+    t_view_launches = 0;
+    if (n < 0 || bad_image(W, H) || !plan || !pairs || !grad_image || pair_cap < 0) return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
-    if (!toff || !l_d || !g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
-    if (!temp || temp_bytes < gcp_tile_reduce_bytes(n) || (reinterpret_cast<uintptr_t>(temp) & 3))
-        return GCP_ERR_WORKSPACE;
+    if (!g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
+    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    const PlanLayout A = plan_layout(n, ntiles);
+    const PairLayout B = pair_layout(pair_cap);
+    if (plan_bytes < A.total || pair_bytes < B.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
-    unsigned int *nbig = static_cast<unsigned int *>(temp);
-    int32_t *big = reinterpret_cast<int32_t *>(static_cast<unsigned char *>(temp) + 256);
-    cudaError_t e = cudaMemsetAsync(nbig, 0, sizeof(unsigned int), st);
+    unsigned int *hdr = at<unsigned int>(plan, A.hdr);
+    cudaError_t e = cudaMemsetAsync(hdr + H_TICKET_BWD, 0, 2 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return static_cast<int>(e);
-    k_tile_reduce<<<blocks_for(n, 32), 256, 0, st>>>(partial, toff, l_d, n, g_mean, g_lam, g_opac, g_l, nbig, big);
-    k_tile_reduce_big<<<blocks_for(n, 1, 148 * 8), 256, 0, st>>>(partial, toff, l_d, g_mean, g_lam, g_opac, g_l, nbig,
-                                                                 big);
+    const int32_t *tcount = at<int32_t>(plan, A.tcount), *tstart = at<int32_t>(plan, A.tstart);
+    const int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
+    const int4 *rec = at<int4>(plan, A.rec);
+    float *pstate = at<float>(pairs, B.pstate), *partial = at<float>(pairs, B.partial);
+    k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, g_piece, grad_image, ntx, W,
+                                           H, pstate);
+    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32);
+    k_view_backward<<<grid, BWD_WARPS * 32, 0, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(pairs, B.pgid), rec,
+                                                     hdr, g_piece, at<float>(pairs, B.tck), pstate, grad_image, ntx,
+                                                     ntiles, W, H, partial);
+    const int32_t *toff = at<int32_t>(plan, A.toff);
+    int32_t *big = at<int32_t>(plan, A.big);
+    k_view_reduce<<<blocks_for(n, 32), 256, 0, st>>>(partial, toff, rec, n, g_mean, g_lam, g_opac, g_l, hdr, big);
+    k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, g_mean, g_lam, g_opac, g_l, hdr, big);
+    t_view_launches += 4;
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -147,17 +147,25 @@ def test_tile_size_helpers_are_pure_host_arithmetic():
     assert L.gcp_tile_num_tiles(-1, 10) == 0 and L.gcp_tile_num_tiles(40000, 10) == 0
     piece = L.gcp_tile_piece_pairs()
     assert piece == 128
-    P, W, H = 3_579_735, 1920, 1080
+    P, W, H, n = 3_579_735, 1920, 1080, 905_932
     nt = L.gcp_tile_num_tiles(W, H)
-    cap = L.gcp_tile_piece_cap(P, W, H)
-    assert cap == nt + P // piece + 1                       # >= sum over tiles of max(1, ceil(len / piece))
-    assert L.gcp_tile_plan_ints(P, W, H) == nt + 1 + cap + 4
-    assert L.gcp_tile_state_floats(P, W, H) == cap * 192
-    assert L.gcp_tile_bin_bytes(P, W, H) > 3 * 4 * P and L.gcp_tile_bin_bytes(-1, W, H) == 0
-    assert L.gcp_tile_reduce_bytes(1000) >= 4 * 1000
+    # plan arena: ~100 B per Gaussian (64 B record + counts, offsets, the big-Gaussian list) + ~24 B per tile
+    pb = L.gcp_view_plan_bytes(n, W, H)
+    assert 76 * n + 20 * nt < pb < 96 * n + 32 * nt + (1 << 16)
+    # pair arena: 4 (pair list) + 8 (T checkpoints) + 32 (gradient partials) + 12 (piece state) bytes per pair
+    qb = L.gcp_view_pair_bytes(P, W, H)
+    assert 44 * P < qb < 60 * P + (1 << 16)
+    assert L.gcp_view_plan_bytes(-1, W, H) == 0 and L.gcp_view_pair_bytes(-1, W, H) == 0
+    assert L.gcp_view_plan_bytes(0, 8, 4) > 0 and L.gcp_view_pair_bytes(0, 8, 4) > 0
+    import ctypes
+
+    out = (ctypes.c_int64 * 16)()
+    assert L.gcp_view_layout(n, W, H, P, out) == 0
+    assert all(out[i] % 256 == 0 for i in range(8)) and out[8] == 2 * (P // piece) + 2
     try:
         for bad in (0, 31, 33, 100, 1 << 21):
             assert L.gcp_tile_set_piece_pairs(bad) == -1    # GCP_ERR_INVALID_ARG: a multiple of 32 in [32, 2**20]
-        assert L.gcp_tile_set_piece_pairs(64) == 0 and L.gcp_tile_piece_cap(P, W, H) == nt + P // 64 + 1
+        assert L.gcp_tile_set_piece_pairs(64) == 0 and L.gcp_view_layout(n, W, H, P, out) == 0
+        assert out[8] == 2 * (P // 64) + 2
     finally:
         L.gcp_tile_set_piece_pairs(piece)

@@ -298,17 +298,33 @@ def test_planned_view_equals_unplanned_gpu(route):
             assert torch.equal(a, b)
 
 
+def _arena_arrays(L, view, W, H):
+    """The integer arrays of a rendered tile-route view, read out of its two arenas (gcp_view_layout)."""
+    import ctypes
+
+    out = (ctypes.c_int64 * 16)()
+    assert L.gcp_view_layout(view.n, W, H, view.pairs.cap, out) == 0
+    ntiles = L.gcp_tile_num_tiles(W, H)
+    plan = view.plan.buf.cpu().numpy()
+    pairs = view.pairs.buf.cpu().numpy()
+    i32 = lambda buf, off, cnt: buf[off:off + 4 * cnt].view(np.int32)  # noqa: E731
+    return dict(toff=i32(plan, out[0], view.n + 1), tcount=i32(plan, out[1], ntiles), tstart=i32(plan, out[2], ntiles + 1),
+                pextra=i32(plan, out[3], ntiles), hdr=i32(plan, out[4], 64), pgid=i32(pairs, out[6], view.pairs.cap),
+                ptile_x=i32(pairs, out[7], out[8]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
 def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
-    """Integer side of the tile route: the (tile, Gaussian) pairs, their stable order by tile, the tile offsets
-    and the piece plan against the numpy restatement (oracle/tile_oracle.py, itself pinned on CPU to the
-    reference's sorted element list by tests/test_compositor_oracle.py)."""
+    """Integer side of the tile route: pair offsets per Gaussian, pairs per tile, every tile's list in the order
+    of a stable sort by tile, the padded tile offsets and the pieces of long lists, against the numpy restatement
+    (oracle/tile_oracle.py, itself pinned on CPU to the reference's sorted element list by
+    tests/test_compositor_oracle.py).  The native binning is a counting placement (atomic cursors) followed by a
+    sort of every tile's segment by Gaussian id: the RESULT must be the stable sort, bit for bit."""
     from oracle import tile_oracle as to
     from simplegaussiansplat_tk71_b200 import _lib, compositor
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
-    monkeypatch.setattr(compositor, "SPECULATE", False)     # exact pair count: view.P is the count, no padding
     case = load_case(np.load(FIX), name)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
     L = _lib.lib()
@@ -320,23 +336,69 @@ def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
     assert ntiles == L.gcp_tile_num_tiles(W, H)
     tiles, gids, toff = to.tile_pairs(case["sp"], case["ep"], W, H)
     gid_s, start, _ = to.sort_by_tile(tiles, gids, ntiles)
+    counts = np.diff(start)
     try:
         for piece in (32, default):
             assert L.gcp_tile_set_piece_pairs(piece) == 0
             _, view = compositor._render_forward(t(case["boxsize"]), t(case["sp"]), t(case["ep"]),
                                                  t(case["mean"]).float(), t(case["lam"]), t(case["opac"]),
                                                  t(case["l_d"]), W, H)
+            torch.cuda.synchronize()
+            a = _arena_arrays(L, view, W, H)
             assert view.P == len(tiles)
-            assert np.array_equal(view.toff.cpu().numpy(), toff)
-            assert np.array_equal(view.pgid.cpu().numpy()[:view.P], gid_s)
-            assert np.array_equal(view.tstart.cpu().numpy(), start)
-            pstart, ptile = to.piece_plan(start, piece)
-            plan = view.plan.cpu().numpy()
-            assert np.array_equal(plan[:ntiles + 1], pstart)
-            assert np.array_equal(plan[ntiles + 1:ntiles + 1 + len(ptile)], ptile)
-            assert len(ptile) <= L.gcp_tile_piece_cap(view.P, W, H)
+            assert np.array_equal(a["toff"], toff.astype(np.int32))
+            assert np.array_equal(a["tcount"], counts)
+            padded = (counts + 15) // 16 * 16
+            assert np.array_equal(a["tstart"], np.concatenate([[0], np.cumsum(padded)]).astype(np.int32))
+            assert view.Ppad == int(padded.sum())
+            for tl in range(ntiles):
+                seg = a["pgid"][a["tstart"][tl]:a["tstart"][tl] + counts[tl]]
+                assert np.array_equal(seg, gid_s[start[tl]:start[tl + 1]]), f"tile {tl}"
+            # pieces: a tile with more than `piece` pairs owns ceil(len / piece) consecutive slots of the extra table
+            npieces = np.where(counts > piece, -(-counts // piece), 0)
+            assert a["hdr"][3] == int(npieces.sum())
+            seen = np.zeros(int(npieces.sum()), bool)
+            for tl in range(ntiles):
+                x = a["pextra"][tl]
+                if npieces[tl] == 0:
+                    assert x == -1
+                    continue
+                assert a["ptile_x"][x] == -1 and np.all(a["ptile_x"][x + 1:x + npieces[tl]] == tl)
+                assert not seen[x:x + npieces[tl]].any()
+                seen[x:x + npieces[tl]] = True
+            assert seen.all()
     finally:
         L.gcp_tile_set_piece_pairs(default)
+
+
+@pytest.mark.gpu
+def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch):
+    """Tile lists of thousands of pairs (bundled scene) go through the block-per-tile sort: still the stable order."""
+    from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    L = _lib.lib()
+    v = wl.bundled_views("cuda", n_views=2)[1]
+    _, view = compositor._render_forward(v.boxsize, v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity, v.l_d,
+                                         v.width, v.height)
+    torch.cuda.synchronize()
+    a = _arena_arrays(L, view, v.width, v.height)
+    assert a["tcount"].max() > 2048, "this scene is expected to have long tile lists"
+    assert int(a["tcount"].sum()) == view.P
+    # every segment strictly increasing (distinct Gaussian ids in depth order) ...
+    tw, th = L.gcp_tile_width(), L.gcp_tile_height()
+    ntx = (v.width + tw) // tw
+    sp, ep = v.startpoint.cpu().numpy(), v.endpoint.cpu().numpy()
+    rng = np.random.default_rng(0)
+    for tl in np.concatenate([np.argsort(a["tcount"])[-4:], rng.integers(0, len(a["tcount"]), 60)]):
+        seg = a["pgid"][a["tstart"][tl]:a["tstart"][tl] + a["tcount"][tl]]
+        assert np.all(np.diff(seg) > 0)
+        # ... and exactly the Gaussians whose clipped box touches the tile
+        ty, tx = divmod(int(tl), ntx)
+        hit = (np.maximum(sp[:, 0], 0) // tw <= tx) & (np.minimum(ep[:, 0], v.width) // tw >= tx) & \
+              (np.maximum(sp[:, 1], 0) // th <= ty) & (np.minimum(ep[:, 1], v.height) // th >= ty) & \
+              (ep[:, 0] >= sp[:, 0]) & (ep[:, 1] >= sp[:, 1])
+        assert np.array_equal(seg, np.flatnonzero(hit).astype(np.int32)), f"tile {tl}"
 
 
 def _both_routes(v, gI, monkeypatch, repeats=1):
@@ -442,7 +504,9 @@ def test_render_without_gradients_skips_the_kept_T_gpu(route):
     assert np.array_equal(img.cpu().numpy(), want) or np.allclose(img.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
     _, view = compositor._render_forward(*args[:1], *args[2:], keep=False)
     if route == "tiles":
-        assert view.tkeep is None
+        assert view.keep is False
+        with pytest.raises(RuntimeError, match="without keeping T"):
+            compositor._render_backward(view, torch.zeros(case["H"] + 1, case["W"] + 1, 3, device="cuda"))
 
 
 @pytest.mark.gpu
@@ -490,37 +554,33 @@ def test_native_compositor_ragged_image_sizes_against_oracle_gpu(W, H, n, max_ha
 
 
 @pytest.mark.gpu
-def test_speculative_forward_equals_exact_forward_gpu(monkeypatch):
-    """Tile route without plan_view: from the second view of a shape on, the forward is queued on a guessed pair
-    capacity before the count is known (compositor.SPECULATE).  Same bits as the exact pass; a guess that is too
-    small is detected and the view rendered again."""
-    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
-    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+def test_one_call_forward_on_a_known_capacity_gpu(monkeypatch):
+    """gcp_view_forward (plan + render in one call, no host wait in between) on a pair arena the caller already
+    owns: same bits as the exact two-call pass; a capacity that is too small is reported through the totals and
+    nothing is rendered."""
+    from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    L = _lib.lib()
     v = wl.splat_view(640, 360, 60_000, seed=5, device="cuda")
-    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
-    key = (v.startpoint.device.index, v.n, v.width, v.height)
-
-    def step():
-        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
-                        v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
-        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
-        img.backward(gI)
-        return [img.detach().clone()] + [t.grad.clone() for t in (m, lam, o, l)]
-
-    compositor._pair_counts.pop(key, None)
-    monkeypatch.setattr(compositor, "SPECULATE", False)
-    exact = step()
-    count = compositor._pair_counts[key]
-    assert count > 10_000
-    monkeypatch.setattr(compositor, "SPECULATE", True)
-    spec = step()                                   # capacity = count * 1.25 + 4096
-    compositor._pair_counts[key] = 100              # a guess far too small: dropped pairs -> detected -> exact pass
-    redo = step()
-    assert compositor._pair_counts[key] == count
-    compositor._pair_counts[key] = 4 * count        # far too large: only padding
-    padded = step()
-    for other in (spec, redo, padded):
-        for a, b in zip(exact, other):
-            assert torch.equal(a, b)
+    W, H, n = v.width, v.height, v.n
+    img_exact, view = compositor._render_forward(v.boxsize, v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity,
+                                                 v.l_d, W, H)
+    torch.cuda.synchronize()
+    assert view.Ppad > 10_000
+    p = lambda t: t.data_ptr()  # noqa: E731
+    mean, lam, opac, l_d = v.mean.float().contiguous(), v.lam.reshape(n, 4).contiguous(), v.opacity.reshape(n).contiguous(), v.l_d
+    stream = torch.cuda.current_stream().cuda_stream
+    for cap, fits in ((view.Ppad, True), (view.Ppad * 3, True), (view.Ppad - 16, False), (1024, False)):
+        plan = torch.empty(int(L.gcp_view_plan_bytes(n, W, H)), dtype=torch.uint8, device="cuda")
+        pairs = torch.empty(int(L.gcp_view_pair_bytes(cap, W, H)), dtype=torch.uint8, device="cuda")
+        totals = torch.zeros(2, dtype=torch.int64).pin_memory()
+        img = torch.full((H + 1, W + 1, 3), float("nan"), device="cuda")
+        _lib.check(L.gcp_view_forward(p(v.startpoint), p(v.endpoint), p(mean), p(lam), p(opac), p(l_d), n, W, H, p(plan),
+                                      plan.numel(), p(pairs), pairs.numel(), cap, 1, p(img), p(totals), stream), "fwd")
+        torch.cuda.synchronize()
+        assert totals.tolist() == [view.P, view.Ppad]
+        if fits:
+            assert torch.equal(img, img_exact)
+        else:
+            assert bool(torch.isnan(img).all()), "an overflowing view must not be rendered at all"
