@@ -270,17 +270,16 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
  * caller-owned device arenas (256-byte aligned; nothing is allocated, freed or retained by the library):
  *   plan arena  gcp_view_plan_bytes(n, W, H): pair counts / offsets per Gaussian and per tile, packed records,
  *               work lists.  Written by gcp_view_plan + gcp_view_render, read by gcp_view_backward.
- *   pair arena  gcp_view_pair_bytes(pair_cap, W, H): the tile-ordered pair list (every tile's segment padded to a
- *               multiple of 16), one checkpoint of T per 16 pairs (all the backward keeps of the forward walk:
- *               8 B per pair), the state of the pieces of long lists, the gradient partials (32 B per pair).
- *               pair_cap >= the PADDED pair count of the view.
- * gcp_view_plan also stores {pairs, padded pairs} into totals_host[0..1] — a pointer the DEVICE can write: pinned,
- * mapped host memory (cudaHostAlloc; the same address under unified addressing), or NULL.  The host waits for
- * the plan (an event behind it) and sizes the pair arena from totals_host[1]; this is the one host sync of a
- * view, the counterpart of the reference's .item() at uitility.py:348.  A caller that already owns a pair
- * arena it believes large enough may skip the wait and call gcp_view_forward: when the view turns out to have
- * more padded pairs than pair_cap the render kernels do nothing (the image is NOT written) and the caller must
- * compare totals_host[1] with pair_cap before using any result, and redo the view with a larger arena.
+ *   pair arena  gcp_view_pair_bytes(pair_cap, W, H): the tile-ordered pair list, one checkpoint of T per 8 pairs
+ *               (all the backward keeps of the forward walk: 16 B per pair), the state of the pieces of long
+ *               lists, the gradient partials (32 B per pair).  pair_cap >= the pair count of the view.
+ * gcp_view_plan also stores the pair count into totals_host[0] — a pointer the DEVICE can write: pinned, mapped
+ * host memory (cudaHostAlloc; the same address under unified addressing), int64[2], or NULL.  The host waits
+ * for the plan (an event behind it) and sizes the pair arena from it; this is the one host sync of a view, the
+ * counterpart of the reference's .item() at uitility.py:348.  A caller that already owns a pair arena it
+ * believes large enough may skip the wait and call gcp_view_forward: when the view turns out to have more
+ * pairs than pair_cap the render kernels do nothing (the image is NOT written) and the caller must compare
+ * totals_host[0] with pair_cap before using any result, and redo the view with a larger arena.
  * A PIECE is at most gcp_tile_piece_pairs() (default 128) consecutive pairs of one tile: longer lists are cut
  * into pieces walked by different warps, the per-pixel carries between them (T forward, U backward — the
  * segmented scan's cross-block carries) resolved by two small combine kernels; the setting must not change
@@ -313,7 +312,7 @@ int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_by
                       float *g_l, gcp_stream_t stream);
 /* Test aid: byte offsets of the integer arrays the tests compare bit for bit with oracle/tile_oracle.py.
  * out[0..5] (plan arena): toff i32[n+1] (Gaussian-major pair offsets), tile_count i32[tiles], tile_start
- * i32[tiles+1] (padded), piece_extra i32[tiles], header, records; out[6..7] (pair arena): pair_gid i32[cap],
+ * i32[tiles+1], piece_extra i32[tiles], header, records; out[6..7] (pair arena): pair_gid i32[cap],
  * extra-piece table i32[out[8]]. */
 int gcp_view_layout(int64_t n, int W, int H, int64_t pair_cap, int64_t *out);
 /* kernels launched by the last gcp_view_* call of this thread (bench.py's gpu_launches) */

@@ -123,7 +123,7 @@ class _PlanArena:
 
     def __init__(self, dev, nbytes):
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.totals = torch.zeros(2, dtype=torch.int64).pin_memory()   # {pairs, padded pairs}: the kernel writes here
+        self.totals = torch.zeros(2, dtype=torch.int64).pin_memory()   # [0] = pair count: the plan kernel writes here
         self.totals_np = self.totals.numpy()
 
 
@@ -154,22 +154,23 @@ def _take_plan_arena(L, dev, n, W, H, key=None) -> _PlanArena:
     return _PlanArena(dev, need + need // 8)
 
 
-def _take_pair_arena(L, dev, pairs_padded, W, H) -> _PairArena:
+def _take_pair_arena(L, dev, pairs, W, H) -> _PairArena:
     free = _free_pair.setdefault(_pool_key(dev), [])
     for i, a in enumerate(free):
-        if a.cap >= pairs_padded:
+        # (the bytes a capacity needs also depend on the image size and on gcp_tile_set_piece_pairs)
+        if a.cap >= pairs and a.buf.numel() >= int(L.gcp_view_pair_bytes(a.cap, W, H)):
             return free.pop(i)
     if free:
         free.pop()
-    cap = pairs_padded + pairs_padded // 4 + 4096      # head room: the next views of a scene fit without a new block
+    cap = pairs + pairs // 4 + 4096      # head room: the next views of a scene fit without a new block
     if cap >= 2 ** 31 - 64:
-        cap = max(pairs_padded, 16)
+        cap = max(pairs, 16)
     return _PairArena(dev, cap, int(L.gcp_view_pair_bytes(cap, W, H)))
 
 
 class _TileView:
     """Tile route: the two arenas of a rendered view, held until its autograd state is dropped."""
-    __slots__ = ("n", "P", "Ppad", "W", "H", "plan", "pairs", "key", "piece", "keep")
+    __slots__ = ("n", "P", "W", "H", "plan", "pairs", "key", "piece", "keep")
 
     def __del__(self):
         try:
@@ -299,10 +300,10 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
         # the one host sync of a view (like the reference's .item() at uitility.py:348): the plan kernel wrote the
         # pair count straight into pinned memory
         event.synchronize()
-        v.P, v.Ppad = int(v.plan.totals_np[0]), int(v.plan.totals_np[1])
-        if v.Ppad >= 2 ** 31 - 64:
+        v.P = int(v.plan.totals_np[0])
+        if v.P >= 2 ** 31 - 64:
             raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
-        v.pairs = _take_pair_arena(L, dev, v.Ppad, W, H)
+        v.pairs = _take_pair_arena(L, dev, v.P, W, H)
         _lib.check(L.gcp_view_render(_p(sp), _p(ep), _p(mean_), _p(lam_), _p(opac_), _p(l_), n, W, H, _p(v.plan.buf),
                                      v.plan.buf.numel(), _p(v.pairs.buf), v.pairs.buf.numel(), v.pairs.cap,
                                      1 if keep else 0, _p(image), stream), "gcp_view_render")

@@ -9,22 +9,25 @@
 // (= depth) order — the order torch.sort gives the reference at gs_model.py:547, hence the order inside every
 // pixel list — and a warp walks its tile's list with the running T of its pixels in registers.
 //
-//   plan      k_view_count    : pairs per Gaussian, pairs per tile (integer atomics)          (uitility.py:336-366)
-//             k_view_scan     : exclusive offsets of both (one launch, chained scan)            (.item() at :348)
-//   render    k_view_fill     : packed per-Gaussian records; every pair dropped into its tile's
-//                               segment at an atomic cursor (unordered)                        (gs_model.py:538-548)
-//             k_view_sort     : every tile's segment sorted by Gaussian id — the ids of a tile are
-//                               distinct, so the result IS the stable sort by tile, bit for bit;
-//                               long lists are cut into pieces (the walk kernels' work units)
+//   plan      k_view_cnt      : pairs per Gaussian                                              (uitility.py:336-366)
+//             k_view_scan     : their exclusive offsets (chained scan); the pair total goes to the host (.item() :348)
+//   render    k_view_pack     : packed per-Gaussian records
+//             k_view_slots    : one thread per 4 pairs: the pair's tile and its slot in that tile's list, taken
+//                               from an atomic counter per tile (unordered)                    (gs_model.py:538-548)
+//             k_view_scan     : tile offsets
+//             k_view_scatter  : every pair's Gaussian id dropped at tile offset + slot
+//             k_view_sort     : every tile's segment sorted by Gaussian id (bitonic network in registers) — the
+//                               ids of a tile are distinct, so the result IS the stable sort by tile, bit for
+//                               bit; long lists are cut into pieces (the walk kernels' work units)
 //             k_view_render   : alpha = o * exp(-1/2 d Lambda d^T) (:493-495,:533-535), T, colour; only a
-//                               CHECKPOINT of T every 16 pairs is kept for the backward (8 B per pair)
-//   backward  k_view_backward : per 16 pairs, T and the Gaussian kernel value are recomputed from the checkpoint
-//                               into shared memory, then the list is walked in reverse with
+//                               CHECKPOINT of T every 8 pairs is kept for the backward (16 B per pair)
+//   backward  k_view_backward : per 8 pairs, T and the Gaussian kernel value are recomputed from the checkpoint
+//                               into registers, then the pairs are walked in reverse with
 //                               U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1}  (w = <dL/dI, alpha l>),
 //                               dL/dalpha_i = T_i (<dL/dI, l_i> - U_i) — no division by 1-alpha (:736,:747,:757
 //                               divide) — and the moments of g*dalpha over the pair's pixels, from which the
 //                               reference's per-element gradients (:733-766) follow per Gaussian, are summed
-//                               over the 32 lanes through shared memory in a fixed order;
+//                               over the 32 lanes in a fixed order;
 //             k_view_reduce   : the partial sums of a Gaussian's pairs added in pair order (:776-783).
 // No float atomics anywhere: a pixel belongs to one lane, a partial to one pair — bitwise reproducible.
 // Elements whose inclusive product is 0 contribute nothing and get no gradient (gs_model.py:575-578).
@@ -40,8 +43,8 @@ namespace {
 constexpr int TSX = 3, TSY = 2;                 // tile = 8 x 4 pixels, lane = (y & 3) * 8 + (x & 7)
 constexpr int TW = 1 << TSX, TH = 1 << TSY;
 static_assert(TW * TH == 32, "one tile is one warp");
-constexpr int SUB = 16;                         // pairs per T checkpoint; tile segments are padded to multiples of it
-constexpr int RG = 4;                           // pairs per cross-lane reduction group of the backward
+constexpr int SUB = 8;                          // pairs per T checkpoint
+constexpr int SUB_SHIFT = 3;
 
 inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7fffffffu) {
     int64_t b = (work + per_block - 1) / per_block;
@@ -54,7 +57,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 // ---- arena headers (u32 words; zeroed by gcp_view_plan) ----
 constexpr int H_TICKET_S1 = 0, H_TICKET_S2 = 1, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4, H_NLONG = 5;
 constexpr int H_TICKET_BWD = 6, H_NBIG = 7;     // adjacent: reset together by every backward
-constexpr int H_P64 = 8, H_PPAD64 = 9;          // u64 indices (bytes 64 / 72): pair count, padded pair count
+constexpr int H_P64 = 8, H_T64 = 9;             // u64 indices (bytes 64 / 72): pair count; the tile scan's total (= it)
 constexpr int HDR_WORDS = 64;
 
 // box of Gaussian g clipped to the image [0,W] x [0,H] (the caller clamps already, gs_model.py:419-425)
@@ -72,60 +75,48 @@ __device__ __forceinline__ Box clip_box(const int32_t *__restrict__ sp, const in
     return b;
 }
 
-// Calls f(tile) for every tile of the boxes of this warp's 32 Gaussians: a small box by its own thread, a box of
-// more than 32 tiles by the whole warp afterwards (bundled scene: boxes of thousands of tiles).
-template <typename F>
-__device__ __forceinline__ void for_each_tile(bool valid, const Box &b, int ntx, int lane, F f) {
-    int tx0 = 0, ty0 = 0, nx = 1, cnt = 0;
-    if (valid && b.ex >= b.sx && b.ey >= b.sy) {
-        tx0 = b.sx >> TSX; ty0 = b.sy >> TSY;
-        nx = (b.ex >> TSX) - tx0 + 1;
-        cnt = nx * ((b.ey >> TSY) - ty0 + 1);
-    }
-    if (cnt <= 32) {
-        int r = 0, c = 0;
-        for (int i = 0; i < cnt; ++i) {
-            f((ty0 + r) * ntx + tx0 + c, lane);
-            if (++c == nx) { c = 0; ++r; }
-        }
-    }
-    unsigned big = __ballot_sync(0xffffffffu, cnt > 32);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
-        const int btx0 = __shfl_sync(0xffffffffu, tx0, src), bty0 = __shfl_sync(0xffffffffu, ty0, src);
-        const int bnx = __shfl_sync(0xffffffffu, nx, src);
-        for (int i = lane; i < bcnt; i += 32) {
-            const int r = i / bnx;
-            f((bty0 + r) * ntx + btx0 + (i - r * bnx), src);
-        }
-    }
-}
+// ---------------------------------------------------------------------------------------------------------------
+// plan: pairs per Gaussian + packed records
+// Lambda is stored pre-multiplied by -log2(e)/2, so that the walk kernels get g = exp(-1/2 d Lambda d^T) as one
+// ex2.approx of d Lambda' d^T (relative error 2^-22; expf costs eight instructions, this one two); k_view_reduce
+// multiplies the d_mean sums by EXP2_UNSCALE = -2 ln 2 to undo the factor.
+// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, -, -}
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
+constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
 
-// ---------------------------------------------------------------------------------------------------------------
-// plan: counts
-// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_view_count(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t n, int W, int H, int ntx,
-             int32_t *__restrict__ cnt, int32_t *__restrict__ tcount) {
+k_view_cnt(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t n, int W, int H,
+           int32_t *__restrict__ cnt) {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    Box b = {0, 0, -1, -1};
-    if (g < n) {
-        b = clip_box(sp, ep, g, W, H);
-        int c = 0;
-        if (b.ex >= b.sx && b.ey >= b.sy) c = ((b.ex >> TSX) - (b.sx >> TSX) + 1) * ((b.ey >> TSY) - (b.sy >> TSY) + 1);
-        cnt[g] = c;
-    }
-    for_each_tile(g < n, b, ntx, lane, [&](int t, int) { atomicAdd(tcount + t, 1); });
+    if (g >= n) return;
+    const Box b = clip_box(sp, ep, g, W, H);
+    int c = 0;
+    if (b.ex >= b.sx && b.ey >= b.sy) c = ((b.ex >> TSX) - (b.sx >> TSX) + 1) * ((b.ey >> TSY) - (b.sy >> TSY) + 1);
+    cnt[g] = c;
+}
+
+__global__ void __launch_bounds__(256)
+k_view_pack(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const float *__restrict__ mean,
+            const float *__restrict__ lam, const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
+            int W, int H, int4 *__restrict__ rec) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const Box b = clip_box(sp, ep, g, W, H);
+    auto f = [](float v) { return __float_as_int(v); };
+    const float mx = __ldg(mean + 2 * g), my = __ldg(mean + 2 * g + 1);
+    const float l00 = __ldg(lam + 4 * g), l01 = __ldg(lam + 4 * g + 1), l10 = __ldg(lam + 4 * g + 2),
+                l11 = __ldg(lam + 4 * g + 3);
+    rec[4 * g] = make_int4(f(mx), f(my), f(l00 * EXP2_SCALE), f(l01 * EXP2_SCALE));
+    rec[4 * g + 1] = make_int4(f(l10 * EXP2_SCALE), f(l11 * EXP2_SCALE), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
+    rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
+    rec[4 * g + 3] = make_int4(b.ex, b.ey, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// plan: exclusive offsets.  One launch scans BOTH arrays (blocks [0, nb1): pairs per Gaussian -> toff;
-// blocks [nb1, nb1 + nb2): pairs per tile, rounded up to SUB -> tstart) with the classic single-pass chained scan:
-// a block publishes its aggregate, then walks back over its predecessors' descriptors (32 per step) to the
-// nearest inclusive prefix.  Tile order comes from an atomic ticket, so a block only ever waits for blocks that
+// exclusive offsets (pairs per Gaussian -> toff in the plan, pairs per tile -> tstart in the render): the classic
+// single-pass chained scan — a block publishes its aggregate, then walks back over its predecessors' descriptors
+// (32 per step) to the nearest inclusive prefix.  Tile order comes from an atomic ticket, so a block only ever waits for blocks that
 // are already running.  descriptor = status (2 bits: 1 aggregate, 2 inclusive) << 62 | value.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
@@ -139,7 +130,6 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <bool PAD>
 __device__ __forceinline__ void chained_scan_block(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out,
                                                    unsigned int *ticket, unsigned long long *desc,
                                                    unsigned long long *total_dev, int64_t *total_host) {
@@ -155,8 +145,7 @@ __device__ __forceinline__ void chained_scan_block(const int32_t *__restrict__ i
     unsigned long long sum = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int x = (base + i < n) ? in[base + i] : 0;
-        if (PAD) x = (x + SUB - 1) & ~(SUB - 1);
+        const int x = (base + i < n) ? in[base + i] : 0;
         v[i] = x;
         sum += static_cast<unsigned long long>(x);
     }
@@ -219,82 +208,157 @@ __device__ __forceinline__ void chained_scan_block(const int32_t *__restrict__ i
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_view_scan(const int32_t *__restrict__ cnt, int64_t n, int32_t *__restrict__ toff, const int32_t *__restrict__ tcount,
-            int ntiles, int32_t *__restrict__ tstart, unsigned int nb1, unsigned int *hdr, unsigned long long *desc1,
-            unsigned long long *desc2, int64_t *totals_host) {
-    unsigned long long *h64 = reinterpret_cast<unsigned long long *>(hdr);
-    if (blockIdx.x < nb1)
-        chained_scan_block<false>(cnt, n, toff, hdr + H_TICKET_S1, desc1, h64 + H_P64, totals_host);
-    else
-        chained_scan_block<true>(tcount, ntiles, tstart, hdr + H_TICKET_S2, desc2, h64 + H_PPAD64,
-                                 totals_host ? totals_host + 1 : nullptr);
+k_view_scan(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out, unsigned int *ticket,
+            unsigned long long *desc, unsigned long long *total_dev, int64_t *total_host) {
+    chained_scan_block(in, n, out, ticket, desc, total_dev, total_host);
 }
 // empty views (n == 0): the offsets of nothing
-__global__ void k_view_scan_empty(int32_t *toff, int32_t *tstart, int ntiles, unsigned int *hdr, int64_t *totals_host) {
-    for (int t = threadIdx.x; t <= ntiles; t += blockDim.x) tstart[t] = 0;
+__global__ void k_view_scan_empty(int32_t *toff, unsigned int *hdr, int64_t *totals_host) {
     if (threadIdx.x == 0) {
         toff[0] = 0;
-        if (totals_host) { totals_host[0] = 0; totals_host[1] = 0; __threadfence_system(); }
+        if (totals_host) { totals_host[0] = 0; __threadfence_system(); }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// render: records + unordered fill
-// Lambda is stored pre-multiplied by -log2(e)/2, so that the walk kernels get g = exp(-1/2 d Lambda d^T) as one
-// ex2.approx of d Lambda' d^T (relative error 2^-22; expf costs eight instructions, this one two); k_view_reduce
-// multiplies the d_mean sums by EXP2_UNSCALE = -2 ln 2 to undo the factor.
-// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, toff, 0}
+// render: binning.  Pair q (Gaussian-major, row-major over the tiles of its box) goes to tile t(q); its place in
+// the tile's segment is tstart[t] + slot, the slot taken from an atomic counter per tile.  One thread handles
+// four consecutive pairs (one binary search for the owner of the first, then a walk), so that a warp issues
+// full-width atomics with four independent ones in flight per thread — a thread per Gaussian would leave most
+// lanes idle behind the largest box of the warp.  Two passes, because the tile offsets need the counts first.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
-constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
-
 __device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap) {
-    return static_cast<int64_t>(reinterpret_cast<const unsigned long long *>(hdr)[H_PPAD64]) > cap;
+    return static_cast<int64_t>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]) > cap;
+}
+// first index g with off[g+1] > e
+__device__ __forceinline__ int64_t find_owner(const int32_t *__restrict__ off, int64_t n, int e) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid + 1) > e) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+constexpr int QPT = 4;   // pairs per thread
+
+__global__ void __launch_bounds__(256)
+k_view_slots(const int4 *__restrict__ rec, const int32_t *__restrict__ toff, int64_t n, int ntx, int64_t cap,
+             const unsigned int *__restrict__ hdr, int32_t *__restrict__ tcount, int32_t *__restrict__ pg,
+             int32_t *__restrict__ pt, int32_t *__restrict__ ps) {
+    if (overflowed(hdr, cap)) return;   // the arena is too small for this view: the host notices and redoes it
+    const int P = __ldg(toff + n);
+    const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * QPT;
+    if (q0 >= P) return;
+    int64_t g = find_owner(toff, n, q0);
+    int gbeg = __ldg(toff + g), gend = __ldg(toff + g + 1);
+    int4 bx = __ldg(rec + 4 * g + 2), by = __ldg(rec + 4 * g + 3);   // {.., .., sx, sy} {ex, ey, .., ..}
+    int tx0 = bx.z >> TSX, ty0 = bx.w >> TSY, nx = (by.x >> TSX) - tx0 + 1;
+    int gi[QPT], t[QPT], sl[QPT];
+#pragma unroll
+    for (int i = 0; i < QPT; ++i) {
+        const int q = q0 + i;
+        gi[i] = 0; t[i] = -1;
+        if (q < P) {
+            while (q >= gend) {   // skips Gaussians without pairs too
+                ++g;
+                gbeg = gend;
+                gend = __ldg(toff + g + 1);
+                if (q < gend) {
+                    bx = __ldg(rec + 4 * g + 2); by = __ldg(rec + 4 * g + 3);
+                    tx0 = bx.z >> TSX; ty0 = bx.w >> TSY; nx = (by.x >> TSX) - tx0 + 1;
+                }
+            }
+            const int local = q - gbeg, r = local / nx;
+            t[i] = (ty0 + r) * ntx + tx0 + (local - r * nx);
+            gi[i] = static_cast<int>(g);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < QPT; ++i) sl[i] = t[i] >= 0 ? atomicAdd(tcount + t[i], 1) : 0;
+    *reinterpret_cast<int4 *>(pg + q0) = make_int4(gi[0], gi[1], gi[2], gi[3]);   // the arrays are padded to QPT
+    *reinterpret_cast<int4 *>(pt + q0) = make_int4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<int4 *>(ps + q0) = make_int4(sl[0], sl[1], sl[2], sl[3]);
 }
 
 __global__ void __launch_bounds__(256)
-k_view_fill(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const float *__restrict__ mean,
-            const float *__restrict__ lam, const float *__restrict__ opac, const float *__restrict__ l_d,
-            const int32_t *__restrict__ toff, const int32_t *__restrict__ tstart, int64_t n, int W, int H, int ntx,
-            int64_t cap, const unsigned int *__restrict__ hdr, int32_t *__restrict__ cursor, int4 *__restrict__ rec,
-            int32_t *__restrict__ pgid) {
-    if (overflowed(hdr, cap)) return;   // the arena is too small for this view: the host notices and redoes it
-    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    Box b = {0, 0, -1, -1};
-    if (g < n) {
-        b = clip_box(sp, ep, g, W, H);
-        auto f = [](float v) { return __float_as_int(v); };
-        const float mx = __ldg(mean + 2 * g), my = __ldg(mean + 2 * g + 1);
-        const float l00 = __ldg(lam + 4 * g), l01 = __ldg(lam + 4 * g + 1), l10 = __ldg(lam + 4 * g + 2),
-                    l11 = __ldg(lam + 4 * g + 3);
-        rec[4 * g] = make_int4(f(mx), f(my), f(l00 * EXP2_SCALE), f(l01 * EXP2_SCALE));
-        rec[4 * g + 1] = make_int4(f(l10 * EXP2_SCALE), f(l11 * EXP2_SCALE), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
-        rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
-        rec[4 * g + 3] = make_int4(b.ex, b.ey, __ldg(toff + g), 0);
-    }
-    const int32_t gbase = static_cast<int32_t>(g - lane);
-    for_each_tile(g < n, b, ntx, lane, [&](int t, int owner) {
-        const int pos = __ldg(tstart + t) + atomicAdd(cursor + t, 1);
-        pgid[pos] = gbase + owner;
-    });
+k_view_scatter(const int32_t *__restrict__ pg, const int32_t *__restrict__ pt, const int32_t *__restrict__ ps,
+               const int32_t *__restrict__ tstart, int64_t cap, const unsigned int *__restrict__ hdr,
+               int32_t *__restrict__ pgid) {
+    if (overflowed(hdr, cap)) return;
+    const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
+    const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * QPT;
+    if (q0 >= P) return;
+    const int4 g = __ldcs(reinterpret_cast<const int4 *>(pg + q0)), t = __ldcs(reinterpret_cast<const int4 *>(pt + q0)),
+               sl = __ldcs(reinterpret_cast<const int4 *>(ps + q0));
+    if (t.x >= 0) pgid[__ldg(tstart + t.x) + sl.x] = g.x;
+    if (t.y >= 0) pgid[__ldg(tstart + t.y) + sl.y] = g.y;
+    if (t.z >= 0) pgid[__ldg(tstart + t.z) + sl.z] = g.z;
+    if (t.w >= 0) pgid[__ldg(tstart + t.w) + sl.w] = g.w;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // render: order inside the tiles.  A tile's segment holds distinct Gaussian ids in arbitrary order; sorted
-// ascending it is exactly what a stable sort of the Gaussian-major pair list by tile produces.  Bitonic network
-// with ascending compare-exchanges only (the "flip" form), so that a length that is not a power of two needs no
-// padding: a partner index beyond the end counts as +infinity and never moves.
+// ascending it is exactly what a stable sort of the Gaussian-major pair list by tile produces.
+//  * lists of up to SORT_REGS = 512 ids: one warp, the ids in registers (E = 1..16 per lane, index e*32 + lane,
+//    padded with INT_MAX), the classic bitonic network — partners in another lane through SHFL.BFLY, partners in
+//    the same lane as register compare-exchanges; ~3 instructions per id and step, no shared memory;
+//  * longer lists (bundled scene: thousands of Gaussians over one tile): one block each, the flip form of the
+//    network in place in global memory (ascending compare-exchanges only, so a length that is not a power of two
+//    needs no padding: a partner index beyond the end counts as +infinity and never moves).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SORT_SMEM = 512;   // longest list sorted by one warp in shared memory; longer ones: one block each
+constexpr int SORT_REGS = 512;
+
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(int32_t (&v)[E], int lane) {
+    constexpr int N = 32 * E;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {   // partner in the same lane: registers e and e ^ (j / 32)
+                const int je = j >> 5;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & je) == 0) {
+                        const bool asc = ((e * 32) & k) == 0;   // k >= 64 here: the direction depends on e only
+                        const int32_t a = v[e], b = v[e | je];
+                        const int32_t lo = min(a, b), hi = max(a, b);
+                        v[e] = asc ? lo : hi;
+                        v[e | je] = asc ? hi : lo;
+                    }
+                }
+            } else {
+                const bool upper = (lane & j) != 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const bool asc = (((e * 32) | lane) & k) == 0;
+                    const int32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
+                    v[e] = (asc != upper) ? min(v[e], o) : max(v[e], o);
+                }
+            }
+        }
+    }
+}
+template <int E>
+__device__ __forceinline__ void sort_segment(int32_t *seg, int len, int lane) {
+    int32_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = (e * 32 + lane < len) ? seg[e * 32 + lane] : 0x7fffffff;
+    warp_bitonic_sort<E>(v, lane);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (e * 32 + lane < len) seg[e * 32 + lane] = v[e];
+}
 
 template <typename Sync>
 __device__ __forceinline__ void bitonic_ascending(int32_t *s, int len, int tid, int nthreads, Sync sync) {
     int N = 2;
     while (N < len) N <<= 1;
     for (int k = 2; k <= N; k <<= 1) {
+        const int hs = 31 - __clz(k >> 1);   // log2(k / 2)
         for (int i = tid; i < N / 2; i += nthreads) {
-            const int half = k >> 1, blk = i / half, off = i - blk * half;
+            const int blk = i >> hs, off = i & ((k >> 1) - 1);
             const int a = blk * k + off, b = blk * k + k - 1 - off;
             if (b < len) {
                 const int32_t x = s[a], y = s[b];
@@ -332,10 +396,9 @@ __global__ void __launch_bounds__(256)
 k_view_sort(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int ntiles, int piece, int64_t cap,
             unsigned int *__restrict__ hdr, int32_t *__restrict__ pgid, int32_t *__restrict__ pextra,
             int32_t *__restrict__ ptile_x, int32_t *__restrict__ mlist, int32_t *__restrict__ longlist) {
-    __shared__ int32_t s_keys[8][SORT_SMEM];
     if (overflowed(hdr, cap)) return;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int t = blockIdx.x * 8 + wib;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (t >= ntiles) return;
     const int len = __ldg(tcount + t), base = __ldg(tstart + t);
     if (lane == 0) {
@@ -348,17 +411,18 @@ k_view_sort(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tsta
             mlist[atomicAdd(hdr + H_NMULTI, 1u)] = t;
         }
         pextra[t] = x;
-        if (len > SORT_SMEM) longlist[atomicAdd(hdr + H_NLONG, 1u)] = t;
+        if (len > SORT_REGS) longlist[atomicAdd(hdr + H_NLONG, 1u)] = t;
     }
-    if (len < 2 || len > SORT_SMEM) return;
-    int32_t *s = s_keys[wib];
-    for (int i = lane; i < len; i += 32) s[i] = pgid[base + i];
-    __syncwarp();
-    bitonic_ascending(s, len, lane, 32, [] { __syncwarp(); });
-    for (int i = lane; i < len; i += 32) pgid[base + i] = s[i];
+    int32_t *seg = pgid + base;
+    if (len < 2 || len > SORT_REGS) return;   // warp-uniform
+    if (len <= 32) sort_segment<1>(seg, len, lane);
+    else if (len <= 64) sort_segment<2>(seg, len, lane);
+    else if (len <= 128) sort_segment<4>(seg, len, lane);
+    else if (len <= 256) sort_segment<8>(seg, len, lane);
+    else sort_segment<16>(seg, len, lane);
 }
 
-// lists longer than SORT_SMEM: one block each, in place in global memory (the segment stays in L1/L2)
+// lists longer than SORT_REGS: one block each, in place in global memory (the segment stays in L1/L2)
 __global__ void __launch_bounds__(256)
 k_view_sort_long(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
                  const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
@@ -431,10 +495,10 @@ __device__ __forceinline__ uint32_t coverage_mask(const RecRegs &r, bool live, i
     }
     return mask;
 }
-// Gaussian-major id of the pair (record's Gaussian, tile (tx, ty)): where its gradient partial goes
-__device__ __forceinline__ int pair_id(const RecRegs &r, int tx, int ty) {
+// Gaussian-major id of the pair (record's Gaussian with pair offset goff, tile (tx, ty)): where its partial goes
+__device__ __forceinline__ int pair_id(const RecRegs &r, int goff, int tx, int ty) {
     const int tx0 = r.c.z >> TSX, ty0 = r.c.w >> TSY, nx = (r.d.x >> TSX) - tx0 + 1;
-    return r.d.z + (ty - ty0) * nx + (tx - tx0);
+    return goff + (ty - ty0) * nx + (tx - tx0);
 }
 __device__ __forceinline__ float i2f(int v) { return __int_as_float(v); }
 
@@ -503,13 +567,15 @@ k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ ts
             g1 = g2;
             __syncwarp();
             const int m = min(hi - b, 32);
-            float *ck = tck + (static_cast<int64_t>(b) >> 4) * 32 + lane;   // b is a multiple of SUB = 16
+            // checkpoint rows: row (b >> 3) + t for the 8 pairs from b on (b - tile start is a multiple of 8): the
+            // rows of a tile are distinct and below the first row of the next tile
+            float *ck = tck + ((static_cast<int64_t>(b) >> SUB_SHIFT) + t) * 32 + lane;
 #pragma unroll 4
             for (int k = 0; k < m; ++k) {
                 const float4 A = sl[k].a, B = sl[k].b, C = sl[k].c;
                 const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
                 const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
-                if (KEEP && (k & (SUB - 1)) == 0) __stcs(ck + (k >> 4) * 32, T);   // T checkpoint for the backward
+                if (KEEP && (k & (SUB - 1)) == 0) __stcs(ck + (k >> SUB_SHIFT) * 32, T);   // T checkpoint for the backward
                 const float tin = T * e.x;
                 // branch-free: an element outside the box, or dead (inclusive product 0, gs_model.py:575-578), adds 0
                 const float ta = (cov && tin != 0.0f) ? T * (1.0f - e.x) : 0.0f;
@@ -591,39 +657,54 @@ k_view_combine_bwd(const int32_t *__restrict__ tcount, const int32_t *__restrict
 struct BSlot {
     float4 f0, f1, r0, r1;
 };
-constexpr int BWD_WARPS = 4;
-struct __align__(16) BwdWarpSmem {
-    BSlot slot[32];             // 2 KB
-    float2 tg[SUB][32];         // 4 KB: (T local to the piece, Gaussian kernel value) of the sub-batch's pairs
-    float4 red[RG][2][32];      // 4 KB: the per-lane terms of RG pairs, waiting for their sums over the lanes
-};
+constexpr int BWD_WARPS = 8;
+
+// sum of 8 values per lane over the 32 lanes in 9 shuffles (halving butterfly): afterwards the four lanes
+// 4c' .. 4c'+3 hold term comp(c') = 4*bit2(c') + 2*bit1(c') + bit0(c'), c' = lane >> 2 with its bits read as
+// (lane bit 4, lane bit 3, lane bit 2).  The order of the additions is fixed: bitwise reproducible.
+__device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
+    const unsigned F = 0xffffffffu;
+    float k4[4], k2[2];
+    {
+        const bool h = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = h ? v[4 + i] : v[i], send = h ? v[i] : v[4 + i];
+            k4[i] = keep + __shfl_xor_sync(F, send, 16);
+        }
+    }
+    {
+        const bool h = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = h ? k4[2 + i] : k4[i], send = h ? k4[i] : k4[2 + i];
+            k2[i] = keep + __shfl_xor_sync(F, send, 8);
+        }
+    }
+    const bool h = lane & 4;
+    float s = (h ? k2[1] : k2[0]) + __shfl_xor_sync(F, h ? k2[0] : k2[1], 4);
+    s += __shfl_xor_sync(F, s, 2);
+    s += __shfl_xor_sync(F, s, 1);
+    return s;
+}
 
 // partial[q] = {sum c, sum d, sum c d0, sum c d1, sum c d0 d0, sum c d0 d1, sum c d1 d1, -} over the pixels of
 // pair q, with c = g * dL/dalpha and d = T alpha <dL/dI, l>: the moments from which k_view_reduce forms the
 // reference's per-element gradients (gs_model.py:733-766) once per GAUSSIAN instead of once per pixel.
-//
-// The sums over the 32 lanes go through shared memory: each lane drops its 7 terms with two STS.128; after RG = 4
-// pairs lane j adds, for (pair j/8, term pair (j/2)%4), the 16 source lanes of half j%2 — sixteen conflict-free
-// LDS.64 (source lanes visited in an order XOR-permuted per lane) and 32 FADD per lane per 4 pairs — then the two
-// halves are added (one shuffle).  Every sum has a fixed order: bitwise reproducible.  (The halving butterfly this
-// replaces cost 9 shuffles + 14 selects + 9 adds per pair.)
-__global__ void __launch_bounds__(BWD_WARPS * 32)
+// Nothing of the forward walk is read back but one T per lane and 8 pairs: the sweep (1) re-evaluates the 8
+// pairs forward from the checkpoint and keeps their T and g in registers for the reverse walk (2).
+__global__ void __launch_bounds__(BWD_WARPS * 32, 3)
 k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart,
                 const int32_t *__restrict__ pextra, const int32_t *__restrict__ ptile_x,
-                const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, unsigned int *__restrict__ hdr,
-                int piece, const float *__restrict__ tck, const float *__restrict__ pstate,
-                const float *__restrict__ gimg, int ntx, int ntiles, int W, int H, float *__restrict__ partial) {
-    __shared__ BwdWarpSmem smem[BWD_WARPS];
+                const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, const int32_t *__restrict__ toff,
+                unsigned int *__restrict__ hdr, int piece, const float *__restrict__ tck,
+                const float *__restrict__ pstate, const float *__restrict__ gimg, int ntx, int ntiles, int W, int H,
+                float *__restrict__ partial) {
+    __shared__ BSlot slots[BWD_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    BwdWarpSmem *ws = &smem[wib];
-    // lane constants of the cross-lane sums: sum s = lane/2 -> pair s/4 of the group, terms 2*(s%4), 2*(s%4)+1;
-    // this lane adds the source lanes of half lane%2 in the order 16*half + (i ^ rx), i = 0..15
-    const int rs = lane >> 1, rhalf = lane & 1, rg = rs >> 2, rcp = rs & 3;
-    const int rx = rhalf | (((rs >> 1) & 3) << 1);
-    const float *red_base = &ws->red[rg][rcp >> 1][16 * rhalf].x + 2 * (rcp & 1);
-    const float *red_p[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) red_p[k] = red_base + 4 * (k ^ rx);
+    BSlot *sl = slots[wib];
+    const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float *const pcomp = partial + comp;   // the term this lane's group ends up holding after reduce8
     const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
     while (next_piece(hdr + H_TICKET_BWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
@@ -647,21 +728,26 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
             carry = __ldg(ps + 128);
             U = __ldg(ps + 160);
         }
-        // batches of 32 pairs, aligned to the piece start, from the last one down
+        // batches of 32 pairs, aligned to the piece start, from the last one down; ids two batches ahead, records
+        // (and the Gaussian's pair offset) one batch ahead
         const int last = lo + ((hi - lo - 1) & ~31);
-        int g1 = 0;
+        int g1 = 0, goff = 0;
         RecRegs r = {};
-        if (last + lane < hi) r = load_rec(rec, __ldg(pgid + last + lane));
+        if (last + lane < hi) {
+            const int g = __ldg(pgid + last + lane);
+            r = load_rec(rec, g);
+            goff = __ldg(toff + g);
+        }
         if (last > lo) g1 = __ldg(pgid + last - 32 + lane);
-        const float *ckl = tck + lane;
+        const float *ckl = tck + static_cast<int64_t>(t) * 32 + lane;
         // checkpoint of the sub-batch walked next, loaded one sub-batch ahead
-        float tnext = __ldcs(ckl + (static_cast<int64_t>(last + ((hi - last - 1) & ~(SUB - 1))) >> 4) * 32);
+        float tnext = __ldcs(ckl + (static_cast<int64_t>(last + ((hi - last - 1) & ~(SUB - 1))) >> SUB_SHIFT) * 32);
         for (int bb = last; bb >= lo; bb -= 32) {
             const int m = min(hi - bb, 32);
             {
                 const uint32_t mask = coverage_mask(r, lane < m, x0, y0);
-                const int q = pair_id(r, tx, ty);
-                BSlot &s = ws->slot[lane];
+                const int q = pair_id(r, goff, tx, ty);
+                BSlot &s = sl[lane];
                 s.f0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
                 s.f1 = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
                 s.r0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.b.z), i2f(r.b.w));
@@ -669,64 +755,53 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
             }
             int g2 = 0;
             if (bb - 64 >= lo) g2 = __ldg(pgid + bb - 64 + lane);
-            if (bb - 32 >= lo) r = load_rec(rec, g1);
+            if (bb - 32 >= lo) {
+                r = load_rec(rec, g1);
+                goff = __ldg(toff + g1);
+            }
             g1 = g2;
             __syncwarp();
-            for (int sb = (m - 1) >> 4; sb >= 0; --sb) {   // sub-batches of SUB = 16 pairs, the later one first
+            for (int sb = (m - 1) >> SUB_SHIFT; sb >= 0; --sb) {   // sub-batches of SUB = 8 pairs, the last one first
                 const int s0 = sb * SUB, ms = min(m - s0, SUB);
                 float T = tnext;
                 {   // the checkpoint after this one in walking order: the previous sub-batch of the piece
                     const int nb = bb + s0 - SUB;
-                    if (nb >= lo) tnext = __ldcs(ckl + (static_cast<int64_t>(nb) >> 4) * 32);
+                    if (nb >= lo) tnext = __ldcs(ckl + (static_cast<int64_t>(nb) >> SUB_SHIFT) * 32);
                 }
                 // (1) recompute sweep, forward: T and g of every (pair, lane) of the sub-batch
-#pragma unroll 4
-                for (int k = 0; k < ms; ++k) {
-                    const float4 A = ws->slot[s0 + k].f0, B = ws->slot[s0 + k].f1;
-                    const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
-                    const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
-                    ws->tg[k][lane] = make_float2(T, e.gk);
-                    T = cov ? T * e.x : T;
-                }
-                // (2) reverse walk, RG pairs per cross-lane reduction
-                for (int g0 = (ms - 1) & ~(RG - 1); g0 >= 0; g0 -= RG) {
-                    const int gn = min(ms - g0, RG);
+                float Tk[SUB], Gk[SUB];
 #pragma unroll
-                    for (int j = RG - 1; j >= 0; --j) {
-                        if (j >= gn) continue;   // warp-uniform (last group of a sub-batch only)
-                        const int k = g0 + j;
-                        const float4 R0 = ws->slot[s0 + k].r0, R1 = ws->slot[s0 + k].r1;
-                        const float2 tg = ws->tg[k][lane];
+                for (int k = 0; k < SUB; ++k) {
+                    Tk[k] = 0.0f; Gk[k] = 0.0f;
+                    if (k < ms) {   // warp-uniform
+                        const float4 A = sl[s0 + k].f0, B = sl[s0 + k].f1;
+                        const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
+                        const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
+                        Tk[k] = T;
+                        Gk[k] = e.gk;
+                        T = cov ? T * e.x : T;
+                    }
+                }
+                // (2) reverse walk
+#pragma unroll
+                for (int k = SUB - 1; k >= 0; --k) {
+                    if (k < ms) {   // warp-uniform
+                        const float4 R0 = sl[s0 + k].r0, R1 = sl[s0 + k].r1;
                         const bool cov = (__float_as_uint(R1.z) >> lane) & 1u;
-                        const float Tt = carry * tg.x, gk = tg.y;
+                        const float Tt = carry * Tk[k], gk = Gk[k];
                         const float d0 = px - R0.x, d1 = py - R0.y;
                         const float alpha = R0.z * gk, x = 1.0f - alpha;
                         const bool alive = cov && (Tt * x != 0.0f);
                         const float pgl = pg0 * R0.w + pg1 * R1.x + pg2 * R1.y;
                         const float wv = alive ? alpha * pgl : 0.0f;
                         const float dalpha = alive ? Tt * (pgl - U) : 0.0f;
-                        const float d = Tt * wv;
                         U = cov ? fmaf(x, U, wv) : U;   // U_{i-1} = w_i + x_i U_i
                         const float c = gk * dalpha;
                         const float cd0 = c * d0, cd1 = c * d1;
-                        ws->red[j][0][lane] = make_float4(c, d, cd0, cd1);
-                        ws->red[j][1][lane] = make_float4(cd0 * d0, cd0 * d1, cd1 * d1, 0.0f);
+                        const float v[8] = {c, Tt * wv, cd0, cd1, cd0 * d0, cd0 * d1, cd1 * d1, 0.0f};
+                        const float sum = reduce8(v, lane);
+                        if ((lane & 3) == 0) pcomp[static_cast<int64_t>(__float_as_int(R1.w)) * 8] = sum;
                     }
-                    __syncwarp();
-                    float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 v = *reinterpret_cast<const float2 *>(red_p[i & 7] + (i & 8) * 4);
-                        a0 += v.x;
-                        a1 += v.y;
-                    }
-                    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-                    if (rhalf == 0 && rg < gn) {
-                        const int q = __float_as_int(ws->slot[s0 + g0 + rg].r1.w);
-                        *reinterpret_cast<float2 *>(partial + static_cast<int64_t>(q) * 8 + 2 * rcp) = make_float2(a0, a1);
-                    }
-                    __syncwarp();
                 }
             }
             __syncwarp();
@@ -845,7 +920,7 @@ inline int tiles_y(int H) { return (H + TH) >> TSY; }
 
 // plan arena: everything whose size is known from (n, W, H) alone.  [0, zero_bytes) is cleared by gcp_view_plan.
 struct PlanLayout {
-    size_t hdr, desc1, desc2, tcount, cursor, zero_bytes, cnt, toff, tstart, pextra, mlist, longlist, big, rec, total;
+    size_t hdr, desc1, desc2, tcount, zero_bytes, cnt, toff, tstart, pextra, mlist, longlist, big, rec, total;
     unsigned nb1, nb2;
 };
 PlanLayout plan_layout(int64_t n, int ntiles) {
@@ -858,7 +933,6 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
     L.desc1 = take(static_cast<size_t>(L.nb1) * 8);
     L.desc2 = take(static_cast<size_t>(L.nb2) * 8);
     L.tcount = take(static_cast<size_t>(ntiles) * 4);
-    L.cursor = take(static_cast<size_t>(ntiles) * 4);
     L.zero_bytes = o;
     L.cnt = take(static_cast<size_t>(n > 0 ? n : 1) * 4);
     L.toff = take(static_cast<size_t>(n + 1) * 4);
@@ -871,22 +945,28 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
     L.total = o;
     return L;
 }
-// pair arena: everything sized by the (padded) pair capacity
+// pair arena: everything sized by the pair capacity.  The three binning arrays (Gaussian, tile, slot of every
+// pair: 12 B per pair, dead once the pair list is built) share the space of the backward's partials (32 B per pair).
 struct PairLayout {
-    size_t pgid, tck, ptile_x, pstate, partial, total;
+    size_t pgid, tck, ptile_x, pstate, partial, bin_pg, bin_pt, bin_ps, total;
     int64_t xcap;
 };
-PairLayout pair_layout(int64_t cap) {
+PairLayout pair_layout(int64_t cap, int ntiles) {
     PairLayout L;
-    if (cap < SUB) cap = SUB;
+    if (cap < 16) cap = 16;
     L.xcap = 2 * (cap / g_piece) + 2;   // slots of the extra-piece table: sum over multi-piece tiles of their pieces
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
     L.pgid = take(static_cast<size_t>(cap) * 4);
-    L.tck = take(static_cast<size_t>(cap / SUB + 1) * 32 * 4);
+    L.tck = take((static_cast<size_t>(cap >> SUB_SHIFT) + ntiles + 2) * 32 * 4);
     L.ptile_x = take(static_cast<size_t>(L.xcap) * 4);
     L.pstate = take(static_cast<size_t>(L.xcap) * PIECE_STATE * 4);
     L.partial = take(static_cast<size_t>(cap) * 32);
+    const size_t third = align256(static_cast<size_t>(cap + QPT) * 4);   // 3 * third <= 32 * cap for cap >= 16
+    L.bin_pg = L.partial;
+    L.bin_pt = L.partial + third;
+    L.bin_ps = L.partial + 2 * third;
+    if (3 * third > align256(static_cast<size_t>(cap) * 32)) o = L.partial + 3 * third;
     L.total = o;
     return L;
 }
@@ -936,14 +1016,13 @@ size_t gcp_view_plan_bytes(int64_t n, int W, int H) {
     return (n < 0 || bad_image(W, H)) ? 0 : plan_layout(n, tiles_x(W) * tiles_y(H)).total;
 }
 size_t gcp_view_pair_bytes(int64_t pair_cap, int W, int H) {
-    return (pair_cap < 0 || bad_image(W, H)) ? 0 : pair_layout(pair_cap).total;
+    return (pair_cap < 0 || bad_image(W, H)) ? 0 : pair_layout(pair_cap, tiles_x(W) * tiles_y(H)).total;
 }
-/* byte offsets of the arrays tests compare bit for bit: out[0..5] = toff, tcount, tstart, pextra (plan arena);
- * out[6..7] = pgid, ptile_x (pair arena); out[8] = slots of ptile_x */
 int gcp_view_layout(int64_t n, int W, int H, int64_t pair_cap, int64_t *out) {
     if (n < 0 || bad_image(W, H) || pair_cap < 0 || !out) return GCP_ERR_INVALID_ARG;
-    const PlanLayout A = plan_layout(n, tiles_x(W) * tiles_y(H));
-    const PairLayout B = pair_layout(pair_cap);
+    const int ntiles = tiles_x(W) * tiles_y(H);
+    const PlanLayout A = plan_layout(n, ntiles);
+    const PairLayout B = pair_layout(pair_cap, ntiles);
     out[0] = static_cast<int64_t>(A.toff); out[1] = static_cast<int64_t>(A.tcount); out[2] = static_cast<int64_t>(A.tstart);
     out[3] = static_cast<int64_t>(A.pextra); out[4] = static_cast<int64_t>(A.hdr); out[5] = static_cast<int64_t>(A.rec);
     out[6] = static_cast<int64_t>(B.pgid); out[7] = static_cast<int64_t>(B.ptile_x); out[8] = B.xcap;
@@ -955,7 +1034,7 @@ int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H,
     t_view_launches = 0;
     if (n < 0 || n >= (int64_t(1) << 31) - 64 || bad_image(W, H) || !plan) return GCP_ERR_INVALID_ARG;
     if (reinterpret_cast<uintptr_t>(plan) & 255) return GCP_ERR_WORKSPACE;
-    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
+    const int ntiles = tiles_x(W) * tiles_y(H);
     const PlanLayout L = plan_layout(n, ntiles);
     if (plan_bytes < L.total) return GCP_ERR_WORKSPACE;
     if (n > 0 && (!sp || !ep || (reinterpret_cast<uintptr_t>(sp) & 7) || (reinterpret_cast<uintptr_t>(ep) & 7)))
@@ -965,17 +1044,14 @@ int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H,
     if (e != cudaSuccess) return static_cast<int>(e);
     unsigned int *hdr = at<unsigned int>(plan, L.hdr);
     if (n == 0) {
-        k_view_scan_empty<<<1, 256, 0, st>>>(at<int32_t>(plan, L.toff), at<int32_t>(plan, L.tstart), ntiles, hdr,
-                                             totals_host);
+        k_view_scan_empty<<<1, 32, 0, st>>>(at<int32_t>(plan, L.toff), hdr, totals_host);
         ++t_view_launches;
         return static_cast<int>(cudaGetLastError());
     }
-    k_view_count<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, n, W, H, ntx, at<int32_t>(plan, L.cnt),
-                                                     at<int32_t>(plan, L.tcount));
-    k_view_scan<<<L.nb1 + L.nb2, SCAN_THREADS, 0, st>>>(
-        at<int32_t>(plan, L.cnt), n, at<int32_t>(plan, L.toff), at<int32_t>(plan, L.tcount), ntiles,
-        at<int32_t>(plan, L.tstart), L.nb1, hdr, at<unsigned long long>(plan, L.desc1),
-        at<unsigned long long>(plan, L.desc2), totals_host);
+    k_view_cnt<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, n, W, H, at<int32_t>(plan, L.cnt));
+    k_view_scan<<<L.nb1, SCAN_THREADS, 0, st>>>(at<int32_t>(plan, L.cnt), n, at<int32_t>(plan, L.toff),
+                                                hdr + H_TICKET_S1, at<unsigned long long>(plan, L.desc1),
+                                                reinterpret_cast<unsigned long long *>(hdr) + H_P64, totals_host);
     t_view_launches += 2;
     return static_cast<int>(cudaGetLastError());
 }
@@ -990,18 +1066,28 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     if (n > 0 && (!sp || !ep || !mean || !lam || !opac || !l_d)) return GCP_ERR_INVALID_ARG;
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
     const PlanLayout A = plan_layout(n, ntiles);
-    const PairLayout B = pair_layout(pair_cap);
+    const PairLayout B = pair_layout(pair_cap, ntiles);
     if (plan_bytes < A.total || pair_bytes < B.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
     unsigned int *hdr = at<unsigned int>(plan, A.hdr);
-    const int32_t *tcount = at<int32_t>(plan, A.tcount), *tstart = at<int32_t>(plan, A.tstart);
+    int32_t *tcount = at<int32_t>(plan, A.tcount), *tstart = at<int32_t>(plan, A.tstart);
     int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
     int32_t *pgid = at<int32_t>(pairs, B.pgid);
     int4 *rec = at<int4>(plan, A.rec);
-    if (n > 0)
-        k_view_fill<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, at<int32_t>(plan, A.toff), tstart,
-                                                        n, W, H, ntx, pair_cap, hdr, at<int32_t>(plan, A.cursor), rec,
-                                                        pgid);
+    if (n > 0) {
+        int32_t *pg = at<int32_t>(pairs, B.bin_pg), *pt = at<int32_t>(pairs, B.bin_pt), *ps = at<int32_t>(pairs, B.bin_ps);
+        k_view_pack<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, n, W, H, rec);
+        k_view_slots<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(rec, at<int32_t>(plan, A.toff), n, ntx, pair_cap,
+                                                                      hdr, tcount, pg, pt, ps);
+        k_view_scan<<<A.nb2, SCAN_THREADS, 0, st>>>(tcount, ntiles, tstart, hdr + H_TICKET_S2,
+                                                    at<unsigned long long>(plan, A.desc2),
+                                                    reinterpret_cast<unsigned long long *>(hdr) + H_T64, nullptr);
+        k_view_scatter<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(pg, pt, ps, tstart, pair_cap, hdr, pgid);
+        t_view_launches += 4;
+    } else {
+        cudaError_t e = cudaMemsetAsync(tstart, 0, static_cast<size_t>(ntiles + 1) * 4, st);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
     k_view_sort<<<blocks_for(ntiles, 8), 256, 0, st>>>(tcount, tstart, ntiles, g_piece, pair_cap, hdr, pgid, pextra,
                                                        ptile_x, at<int32_t>(plan, A.mlist),
                                                        at<int32_t>(plan, A.longlist));
@@ -1018,7 +1104,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     }
     k_view_combine_fwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, pair_cap, g_piece, ntx, W,
                                            H, pstate, image);
-    t_view_launches += (n > 0 ? 5 : 4);
+    t_view_launches += 4;
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -1044,7 +1130,7 @@ int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_by
     if (!g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
     const PlanLayout A = plan_layout(n, ntiles);
-    const PairLayout B = pair_layout(pair_cap);
+    const PairLayout B = pair_layout(pair_cap, ntiles);
     if (plan_bytes < A.total || pair_bytes < B.total) return GCP_ERR_WORKSPACE;
     auto st = reinterpret_cast<cudaStream_t>(stream);
     unsigned int *hdr = at<unsigned int>(plan, A.hdr);
@@ -1053,14 +1139,14 @@ int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_by
     const int32_t *tcount = at<int32_t>(plan, A.tcount), *tstart = at<int32_t>(plan, A.tstart);
     const int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
     const int4 *rec = at<int4>(plan, A.rec);
+    const int32_t *toff = at<int32_t>(plan, A.toff);
     float *pstate = at<float>(pairs, B.pstate), *partial = at<float>(pairs, B.partial);
     k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, g_piece, grad_image, ntx, W,
                                            H, pstate);
     const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32);
     k_view_backward<<<grid, BWD_WARPS * 32, 0, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(pairs, B.pgid), rec,
-                                                     hdr, g_piece, at<float>(pairs, B.tck), pstate, grad_image, ntx,
-                                                     ntiles, W, H, partial);
-    const int32_t *toff = at<int32_t>(plan, A.toff);
+                                                     toff, hdr, g_piece, at<float>(pairs, B.tck), pstate, grad_image,
+                                                     ntx, ntiles, W, H, partial);
     int32_t *big = at<int32_t>(plan, A.big);
     k_view_reduce<<<blocks_for(n, 32), 256, 0, st>>>(partial, toff, rec, n, g_mean, g_lam, g_opac, g_l, hdr, big);
     k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, g_mean, g_lam, g_opac, g_l, hdr, big);

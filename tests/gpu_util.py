@@ -83,7 +83,9 @@ def assert_close(got, ref, what, scale=None, rtol=RTOL, atol=ATOL):
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     if got.size == 0:
         return
-    assert np.all(np.isfinite(got) == np.isfinite(ref)), f"{what}: non-finite mismatch"
+    nf = np.flatnonzero(np.isfinite(got) != np.isfinite(ref))
+    assert nf.size == 0, (f"{what}: non-finite mismatch at {nf.size} positions, first {nf[:8].tolist()} last "
+                          f"{nf[-3:].tolist()} of {got.size}: got {got[nf[:4]].tolist()} ref {ref[nf[:4]].tolist()}")
     m = np.isfinite(ref)
     bound = atol + rtol * (np.abs(ref[m]) if scale is None else np.asarray(scale, dtype=np.float64)[m])
     err = np.abs(got[m] - ref[m])

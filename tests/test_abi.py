@@ -152,9 +152,10 @@ def test_tile_size_helpers_are_pure_host_arithmetic():
     # plan arena: ~100 B per Gaussian (64 B record + counts, offsets, the big-Gaussian list) + ~24 B per tile
     pb = L.gcp_view_plan_bytes(n, W, H)
     assert 76 * n + 20 * nt < pb < 96 * n + 32 * nt + (1 << 16)
-    # pair arena: 4 (pair list) + 8 (T checkpoints) + 32 (gradient partials) + 12 (piece state) bytes per pair
+    # pair arena: 4 (pair list) + 16 (T checkpoints) + 32 (gradient partials) + 12 (piece state) bytes per pair
+    # + one checkpoint row (128 B) per tile
     qb = L.gcp_view_pair_bytes(P, W, H)
-    assert 44 * P < qb < 60 * P + (1 << 16)
+    assert 52 * P + 128 * nt < qb < 68 * P + 128 * nt + (1 << 16)
     assert L.gcp_view_plan_bytes(-1, W, H) == 0 and L.gcp_view_pair_bytes(-1, W, H) == 0
     assert L.gcp_view_plan_bytes(0, 8, 4) > 0 and L.gcp_view_pair_bytes(0, 8, 4) > 0
     import ctypes

@@ -317,7 +317,7 @@ def _arena_arrays(L, view, W, H):
 @pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
 def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
     """Integer side of the tile route: pair offsets per Gaussian, pairs per tile, every tile's list in the order
-    of a stable sort by tile, the padded tile offsets and the pieces of long lists, against the numpy restatement
+    of a stable sort by tile, the tile offsets and the pieces of long lists, against the numpy restatement
     (oracle/tile_oracle.py, itself pinned on CPU to the reference's sorted element list by
     tests/test_compositor_oracle.py).  The native binning is a counting placement (atomic cursors) followed by a
     sort of every tile's segment by Gaussian id: the RESULT must be the stable sort, bit for bit."""
@@ -348,9 +348,7 @@ def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
             assert view.P == len(tiles)
             assert np.array_equal(a["toff"], toff.astype(np.int32))
             assert np.array_equal(a["tcount"], counts)
-            padded = (counts + 15) // 16 * 16
-            assert np.array_equal(a["tstart"], np.concatenate([[0], np.cumsum(padded)]).astype(np.int32))
-            assert view.Ppad == int(padded.sum())
+            assert np.array_equal(a["tstart"], start)
             for tl in range(ntiles):
                 seg = a["pgid"][a["tstart"][tl]:a["tstart"][tl] + counts[tl]]
                 assert np.array_equal(seg, gid_s[start[tl]:start[tl + 1]]), f"tile {tl}"
@@ -567,11 +565,11 @@ def test_one_call_forward_on_a_known_capacity_gpu(monkeypatch):
     img_exact, view = compositor._render_forward(v.boxsize, v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity,
                                                  v.l_d, W, H)
     torch.cuda.synchronize()
-    assert view.Ppad > 10_000
+    assert view.P > 10_000
     p = lambda t: t.data_ptr()  # noqa: E731
     mean, lam, opac, l_d = v.mean.float().contiguous(), v.lam.reshape(n, 4).contiguous(), v.opacity.reshape(n).contiguous(), v.l_d
     stream = torch.cuda.current_stream().cuda_stream
-    for cap, fits in ((view.Ppad, True), (view.Ppad * 3, True), (view.Ppad - 16, False), (1024, False)):
+    for cap, fits in ((view.P, True), (view.P * 3, True), (view.P - 1, False), (1024, False)):
         plan = torch.empty(int(L.gcp_view_plan_bytes(n, W, H)), dtype=torch.uint8, device="cuda")
         pairs = torch.empty(int(L.gcp_view_pair_bytes(cap, W, H)), dtype=torch.uint8, device="cuda")
         totals = torch.zeros(2, dtype=torch.int64).pin_memory()
@@ -579,7 +577,7 @@ def test_one_call_forward_on_a_known_capacity_gpu(monkeypatch):
         _lib.check(L.gcp_view_forward(p(v.startpoint), p(v.endpoint), p(mean), p(lam), p(opac), p(l_d), n, W, H, p(plan),
                                       plan.numel(), p(pairs), pairs.numel(), cap, 1, p(img), p(totals), stream), "fwd")
         torch.cuda.synchronize()
-        assert totals.tolist() == [view.P, view.Ppad]
+        assert int(totals[0]) == view.P
         if fits:
             assert torch.equal(img, img_exact)
         else:
