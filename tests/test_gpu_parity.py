@@ -442,11 +442,15 @@ def test_alignment_peel_of_the_blocked_kernels(oracle, phase):
         L[-1] -= L.sum() - n
         inv, seg_end = seg_arrays(L)
         x = _values(n, rng, zeros=5)
-        x[:first] = 1.0 - 1e-4 * rng.uniform(size=first).astype(np.float32)   # keeps a 20 000-element product finite
+        # the long first segment holds powers of two: every contiguous product is exact in fp32 whatever the
+        # association order, so a carry that skips or repeats ONE element shows bit for bit (a 5000-element product
+        # of values within 1e-4 of 1 drifts by 2e-5 in any tree order: (1-a)(1-b) always rounds the +ab term away)
+        x[:first] = _pow2_values(first, rng, span=6)
         g = rng.normal(0, 1, n).astype(np.float32)
         y64 = oracle.cumprod_fwd(x, inv)
         got = run_fwd("mul", x, inv, 1, (phase, phase, phase))
         assert ops.last_launch_count() == 1, "the sliced call did not take the persistent kernel"
+        assert np.array_equal(got[:first].astype(np.float64), y64[:first]), f"peel fwd phase {phase} first {first}: carry"
         assert_close(got, y64, f"peel fwd phase {phase} first {first}")
         assert_close(run_fwd("add", g, inv, 1, (phase, phase, phase)), oracle.cumsum_fwd(g, inv),
                      f"peel cumsum phase {phase} first {first}", scale=oracle.cumsum_fwd(np.abs(g), inv))
