@@ -310,6 +310,14 @@ int gcp_view_forward(const int32_t *sp, const int32_t *ep, const float *mean, co
 int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
                       const float *grad_image, int64_t n, int W, int H, float *g_mean, float *g_lam, float *g_opac,
                       float *g_l, gcp_stream_t stream);
+/* The same backward with the view's gradients ADDED into parameter-sized arrays: row index[g] of g_mean f32[*,2]
+ * (8-byte aligned), g_lam f32[*,4] (16-byte aligned), g_opac f32[*], g_l f32[*,3] receives Gaussian g's gradient.
+ * This is what autograd makes of the reference's per-view selection `param[mask]` (gs_model.py:405-413) when the
+ * views of a batch are summed (gs_control.py:180-185): a scatter-add per view.  index holds distinct rows;
+ * index == NULL is gcp_view_backward (row g of view-sized arrays, overwritten). */
+int gcp_view_backward_scatter(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
+                              const float *grad_image, int64_t n, int W, int H, const int32_t *index, float *g_mean,
+                              float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream);
 /* Test aid: byte offsets of the integer arrays the tests compare bit for bit with oracle/tile_oracle.py.
  * out[0..5] (plan arena): toff i32[n+1] (Gaussian-major pair offsets), tile_count i32[tiles], tile_start
  * i32[tiles+1], piece_extra i32[tiles], header, records; out[6..7] (pair arena): pair_gid i32[cap],

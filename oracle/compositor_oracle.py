@@ -65,8 +65,13 @@ def forward(boxsize, sp, ep, mean, lam, opac, l_d, W, H):
     return image, cache
 
 
-def backward(cache, grad_image):
-    """gs_model.py:627-663 (_backward_batch), :733-766 (grad_*), :776-783 (scatter to Gaussians)."""
+def backward(cache, grad_image, scales=False):
+    """gs_model.py:627-663 (_backward_batch), :733-766 (grad_*), :776-783 (scatter to Gaussians).
+
+    scales=True additionally returns, for each of the four gradients, the sum of the ABSOLUTE values of the terms
+    it is made of (every product, suffix sum and box sum evaluated with |.|): the condition-aware scale the fp32
+    tolerance is stated against, |got - ref| <= 1e-6 + 1e-5 * scale (scale >= |ref|; the two coincide when no
+    cancellation occurs).  The ops' own tests use the same form (tests/gpu_util.assert_close, scale=...)."""
     c = cache
     alive = c["alive"]
     pg = np.asarray(grad_image, dtype=np.float64)[c["py"], c["px"], :]      # :703-706
@@ -106,4 +111,43 @@ def backward(cache, grad_image):
     out_o = np.zeros((n, 1)); np.add.at(out_o, gid, go[:, None])
     out_l = np.zeros((n, 3)); np.add.at(out_l, gid, gl)
     del incl
-    return out_m, out_L.reshape(n, 2, 2), out_o, out_l
+    if not scales:
+        return out_m, out_L.reshape(n, 2, 2), out_o, out_l
+    d_abs = np.where(alive, (np.abs(pg) * np.abs(c["p"])).sum(1), 0.0)
+    das = d_abs[order]
+    tot_a = np.zeros_like(tot)
+    np.add.at(tot_a, seg, das)
+    csum_a = np.cumsum(das)
+    s_abs = (tot_a[seg] - (csum_a - np.r_[0.0, csum_a[:-1]][head][seg]))[inv_order]
+    s_abs = np.maximum(s_abs, 0.0)
+    go_a = np.where(alive, (g / np.abs(xsafe)) * s_abs + d_abs / np.abs(o), 0.0)
+    gl_a = np.where(alive[:, None], d_abs[:, None] / np.abs(l), 0.0)
+    coef_a = np.where(alive, ((np.abs(o) * g) / np.abs(xsafe)) * s_abs + d_abs, 0.0)
+    gm_a = np.stack((coef_a * np.abs(X0), coef_a * np.abs(X1)), 1)
+    gL_a = 0.5 * coef_a[:, None] * np.abs(dd)
+    sc_m = np.zeros((n, 2)); np.add.at(sc_m, gid, gm_a)
+    sc_L = np.zeros((n, 4)); np.add.at(sc_L, gid, gL_a)
+    sc_o = np.zeros((n, 1)); np.add.at(sc_o, gid, go_a[:, None])
+    sc_l = np.zeros((n, 3)); np.add.at(sc_l, gid, gl_a)
+    return (out_m, out_L.reshape(n, 2, 2), out_o, out_l), (sc_m, sc_L.reshape(n, 2, 2), sc_o, sc_l)
+
+
+def image_scale(cache, W, H):
+    """Sum of |terms| of every pixel colour (equals the image where all colours are positive)."""
+    sc = np.zeros((H + 1, W + 1, 3))
+    np.add.at(sc, (cache["py"], cache["px"]), np.abs(cache["p"]))
+    return sc
+
+
+def error_table(got, ref, scales, rtol=1e-5, atol=1e-6):
+    """Per output: max |err|, max |err| / (atol + rtol |ref|) and max |err| / (atol + rtol scale).  A ratio <= 1
+    is a pass of the north star's tolerance in its plain / its condition-aware form."""
+    rows = []
+    for name, a, b, sc in zip(("image", "grad_mean", "grad_lambda", "grad_opacity", "grad_l"), got, ref, scales):
+        a = np.asarray(a, np.float64).reshape(np.asarray(b).shape)
+        b = np.asarray(b, np.float64)
+        err = np.abs(a - b)
+        rows.append((name, float(err.max()) if err.size else 0.0,
+                     float((err / (atol + rtol * np.abs(b))).max()) if err.size else 0.0,
+                     float((err / (atol + rtol * np.asarray(sc, np.float64).reshape(b.shape))).max()) if err.size else 0.0))
+    return rows

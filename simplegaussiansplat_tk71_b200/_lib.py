@@ -32,7 +32,7 @@ SYMBOLS = (
     "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
     "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs",
     "gcp_view_plan_bytes", "gcp_view_pair_bytes", "gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward",
-    "gcp_view_backward", "gcp_view_last_launch_count",
+    "gcp_view_backward", "gcp_view_backward_scatter", "gcp_view_last_launch_count",
     "gcp_host_boundary_bits", "gcp_ids_from_bits_bytes", "gcp_ids_from_bits",
 )
 
@@ -139,7 +139,9 @@ def lib() -> ctypes.CDLL:
     L.gcp_view_render.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, sz, i64, ci, vp, vp]
     L.gcp_view_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, sz, i64, ci, vp, vp, vp]
     L.gcp_view_backward.argtypes = [vp, sz, vp, sz, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp]
+    L.gcp_view_backward_scatter.argtypes = [vp, sz, vp, sz, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp, vp]
     for name in ("gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward", "gcp_view_backward",
+                 "gcp_view_backward_scatter",
                  "gcp_view_last_launch_count"):
         getattr(L, name).restype = ci
     for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",

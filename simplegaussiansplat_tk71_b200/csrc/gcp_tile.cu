@@ -80,7 +80,7 @@ __device__ __forceinline__ Box clip_box(const int32_t *__restrict__ sp, const in
 // Lambda is stored pre-multiplied by -log2(e)/2, so that the walk kernels get g = exp(-1/2 d Lambda d^T) as one
 // ex2.approx of d Lambda' d^T (relative error 2^-22; expf costs eight instructions, this one two); k_view_reduce
 // multiplies the d_mean sums by EXP2_UNSCALE = -2 ln 2 to undo the factor.
-// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, -, -}
+// rec[g] = {mx, my, l00', l01' | l10', l11', o, l0 || l1, l2, sx, sy | ex, ey, pair offset, -}
 // ---------------------------------------------------------------------------------------------------------------
 constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
 constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
@@ -99,7 +99,7 @@ k_view_cnt(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64
 __global__ void __launch_bounds__(256)
 k_view_pack(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const float *__restrict__ mean,
             const float *__restrict__ lam, const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
-            int W, int H, int4 *__restrict__ rec) {
+            int W, int H, const int32_t *__restrict__ toff, int4 *__restrict__ rec) {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const Box b = clip_box(sp, ep, g, W, H);
@@ -110,7 +110,7 @@ k_view_pack(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, cons
     rec[4 * g] = make_int4(f(mx), f(my), f(l00 * EXP2_SCALE), f(l01 * EXP2_SCALE));
     rec[4 * g + 1] = make_int4(f(l10 * EXP2_SCALE), f(l11 * EXP2_SCALE), f(__ldg(opac + g)), f(__ldg(l_d + 3 * g)));
     rec[4 * g + 2] = make_int4(f(__ldg(l_d + 3 * g + 1)), f(__ldg(l_d + 3 * g + 2)), b.sx, b.sy);
-    rec[4 * g + 3] = make_int4(b.ex, b.ey, 0, 0);
+    rec[4 * g + 3] = make_int4(b.ex, b.ey, __ldg(toff + g), 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -422,15 +422,31 @@ k_view_sort(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tsta
     else sort_segment<16>(seg, len, lane);
 }
 
-// lists longer than SORT_REGS: one block each, in place in global memory (the segment stays in L1/L2)
-__global__ void __launch_bounds__(256)
+// lists longer than SORT_REGS: one block each.  The list is copied into shared memory (up to SORT_SMEM ids; the
+// bundled scene's longest tile list has 7 656), sorted there by the same network and copied back; a list that
+// does not fit is sorted in place in global memory (it stays in L1/L2).
+constexpr int SORT_LONG_THREADS = 512;
+constexpr int SORT_SMEM = 24576;   // ids = 96 KB of dynamic shared memory
+
+__global__ void __launch_bounds__(SORT_LONG_THREADS)
 k_view_sort_long(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
                  const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
+    extern __shared__ int32_t s_ids[];
     if (overflowed(hdr, cap)) return;
     const unsigned int nl = hdr[H_NLONG];
     for (unsigned int i = blockIdx.x; i < nl; i += gridDim.x) {
         const int t = longlist[i];
-        bitonic_ascending(pgid + tstart[t], tcount[t], threadIdx.x, blockDim.x, [] { __syncthreads(); });
+        const int len = tcount[t];
+        int32_t *seg = pgid + tstart[t];
+        if (len <= SORT_SMEM) {
+            for (int k = threadIdx.x; k < len; k += blockDim.x) s_ids[k] = seg[k];
+            __syncthreads();
+            bitonic_ascending(s_ids, len, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+            for (int k = threadIdx.x; k < len; k += blockDim.x) seg[k] = s_ids[k];
+            __syncthreads();
+        } else {
+            bitonic_ascending(seg, len, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+        }
     }
 }
 
@@ -496,10 +512,20 @@ __device__ __forceinline__ uint32_t coverage_mask(const RecRegs &r, bool live, i
     return mask;
 }
 // Gaussian-major id of the pair (record's Gaussian with pair offset goff, tile (tx, ty)): where its partial goes
-__device__ __forceinline__ int pair_id(const RecRegs &r, int goff, int tx, int ty) {
+__device__ __forceinline__ int pair_id(const RecRegs &r, int tx, int ty) {
     const int tx0 = r.c.z >> TSX, ty0 = r.c.w >> TSY, nx = (r.d.x >> TSX) - tx0 + 1;
-    return goff + (ty - ty0) * nx + (tx - tx0);
+    return r.d.z + (ty - ty0) * nx + (tx - tx0);
 }
+// the record of Gaussian g copied into shared memory without passing through registers (LDGSTS, 4 x 16 bytes)
+__device__ __forceinline__ void copy_rec_async(int4 *dst, const int4 *__restrict__ rec, int g) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+    const int4 *src = rec + 4 * static_cast<int64_t>(g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16 * i), "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void copy_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void copy_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float i2f(int v) { return __int_as_float(v); }
 
 struct PairEval {
@@ -652,59 +678,129 @@ k_view_combine_bwd(const int32_t *__restrict__ tcount, const int32_t *__restrict
 }
 
 // ---- backward ----
-// Staged per pair (64 bytes, four broadcast LDS.128 — two in the recompute sweep, two in the reverse walk):
-//   f0 {mx, my, l00, l01}  f1 {l10, l11, o, coverage mask}  |  r0 {mx, my, o, l0}  r1 {l1, l2, coverage mask, pair id}
+// Staged per pair (64 bytes, broadcast LDS.128: two in the recompute sweep, one in the reverse walk, one per
+// pair in the moment phase):
+//   f0 {mx, my, l00, l01}  f1 {l10, l11, o, coverage mask}  |  r0 {o, l0, l1, l2}  r1 {mx, my, pair id, -}
 struct BSlot {
     float4 f0, f1, r0, r1;
 };
 constexpr int BWD_WARPS = 8;
-
-// sum of 8 values per lane over the 32 lanes in 9 shuffles (halving butterfly): afterwards the four lanes
-// 4c' .. 4c'+3 hold term comp(c') = 4*bit2(c') + 2*bit1(c') + bit0(c'), c' = lane >> 2 with its bits read as
-// (lane bit 4, lane bit 3, lane bit 2).  The order of the additions is fixed: bitwise reproducible.
-__device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
-    const unsigned F = 0xffffffffu;
-    float k4[4], k2[2];
-    {
-        const bool h = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float keep = h ? v[4 + i] : v[i], send = h ? v[i] : v[4 + i];
-            k4[i] = keep + __shfl_xor_sync(F, send, 16);
-        }
-    }
-    {
-        const bool h = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float keep = h ? k4[2 + i] : k4[i], send = h ? k4[i] : k4[2 + i];
-            k2[i] = keep + __shfl_xor_sync(F, send, 8);
-        }
-    }
-    const bool h = lane & 4;
-    float s = (h ? k2[1] : k2[0]) + __shfl_xor_sync(F, h ? k2[0] : k2[1], 4);
-    s += __shfl_xor_sync(F, s, 2);
-    s += __shfl_xor_sync(F, s, 1);
-    return s;
-}
+// exchange buffer of a warp: for each of the SUB pairs of a sub-batch, c[32] and dv[32] of its pixels.  The pair
+// stride of 68 words keeps the moment phase's LDS.128 (lanes = 8 pairs x 4 tile rows) free of bank conflicts.
+constexpr int XCH_STRIDE = 68;
+constexpr int BWD_SMEM_PER_WARP = 32 * 64 + 2 * 32 * 64 + SUB * XCH_STRIDE * 4;
+constexpr int BWD_SMEM = BWD_WARPS * BWD_SMEM_PER_WARP;
 
 // partial[q] = {sum c, sum d, sum c d0, sum c d1, sum c d0 d0, sum c d0 d1, sum c d1 d1, -} over the pixels of
 // pair q, with c = g * dL/dalpha and d = T alpha <dL/dI, l>: the moments from which k_view_reduce forms the
 // reference's per-element gradients (gs_model.py:733-766) once per GAUSSIAN instead of once per pixel.
-// Nothing of the forward walk is read back but one T per lane and 8 pairs: the sweep (1) re-evaluates the 8
-// pairs forward from the checkpoint and keeps their T and g in registers for the reverse walk (2).
+// Nothing of the forward walk is read back but one T per lane and 8 pairs.  A sub-batch of 8 pairs goes through
+// three phases:
+//   (1) sweep, lane = pixel   : the 8 pairs re-evaluated forward from the checkpoint; T and g stay in registers
+//   (2) reverse, lane = pixel : U, dL/dalpha -> c and d of every (pair, pixel) dropped into shared memory
+//   (3) moments, lane = (pair, tile row): a lane reads the 8 pixels of its row and pair, forms the row's sums of
+//       c {1, d0, d0 d0} and of d in registers (d1 is constant along a row), and the 4 rows of a pair are added
+//       by a two-level halving exchange that leaves lane r with terms {2r, 2r+1}: one 8-byte store per lane.
+// Against summing 8 values over the 32 lanes of every pair with shuffles (the previous version: 32 of its 96
+// instructions per pair), the cross-lane traffic per pair is 2 STS + 4/8 LDS.128 + 6/8 SHFL.  The order of every
+// sum is fixed: bitwise reproducible.
+template <bool FULL>
+__device__ __forceinline__ void backward_sub_batch(const BSlot *__restrict__ sl, float *__restrict__ xch, int s0, int ms,
+                                                   int lane, float px, float py, float pg0, float pg1, float pg2,
+                                                   float T, float &U, int x0, int y0, float *__restrict__ partial) {
+    // (1) recompute sweep, forward: T and g of every (pair, lane) of the sub-batch; coverage bits kept per lane
+    float Tk[SUB], Gk[SUB];
+    unsigned covbits = 0;
+#pragma unroll
+    for (int k = 0; k < SUB; ++k) {
+        Tk[k] = 0.0f; Gk[k] = 0.0f;
+        if (FULL || k < ms) {   // warp-uniform
+            const float4 A = sl[s0 + k].f0, B = sl[s0 + k].f1;
+            const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
+            const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
+            Tk[k] = T;
+            Gk[k] = e.gk;
+            T = cov ? T * e.x : T;
+            covbits |= cov ? (1u << k) : 0u;
+        }
+    }
+    // (2) reverse walk
+#pragma unroll
+    for (int k = SUB - 1; k >= 0; --k) {
+        if (FULL || k < ms) {   // warp-uniform
+            const float4 R0 = sl[s0 + k].r0;
+            const bool cov = (covbits >> k) & 1u;
+            const float Tt = Tk[k], gk = Gk[k];
+            const float alpha = R0.x * gk, x = 1.0f - alpha;
+            const bool alive = cov && (Tt * x != 0.0f);
+            const float pgl = pg0 * R0.y + pg1 * R0.z + pg2 * R0.w;
+            const float wv = alive ? alpha * pgl : 0.0f;
+            const float dalpha = alive ? Tt * (pgl - U) : 0.0f;
+            U = cov ? fmaf(x, U, wv) : U;   // U_{i-1} = w_i + x_i U_i
+            xch[k * XCH_STRIDE + lane] = gk * dalpha;
+            xch[k * XCH_STRIDE + 32 + lane] = Tt * wv;
+        }
+    }
+    __syncwarp();
+    // (3) moments: lane = (pair p of the sub-batch, row r of the tile)
+    {
+        const int p = lane >> 2, r = lane & 3;
+        const float4 R1 = sl[s0 + p].r1;
+        const float *xc = xch + p * XCH_STRIDE + r * TW;
+        const float4 ca = *reinterpret_cast<const float4 *>(xc), cb = *reinterpret_cast<const float4 *>(xc + 4);
+        const float4 da = *reinterpret_cast<const float4 *>(xc + 32), db = *reinterpret_cast<const float4 *>(xc + 36);
+        const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        const float d1 = static_cast<float>(y0 + r) - R1.y;
+        float R_0 = 0.0f, R_1 = 0.0f, R_2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float d0 = static_cast<float>(x0 + i) - R1.x;
+            const float cd0 = c[i] * d0;
+            R_0 += c[i];
+            R_1 += cd0;
+            R_2 = fmaf(cd0, d0, R_2);
+        }
+        const float Rd = ((da.x + da.y) + (da.z + da.w)) + ((db.x + db.y) + (db.z + db.w));
+        const float d1R0 = d1 * R_0;
+        // terms 0..7 of this row; rows added by halving: after xor 2 a lane keeps terms 4*bit1..4*bit1+3, after
+        // xor 1 terms 2r, 2r+1
+        const float v[8] = {R_0, Rd, R_1, d1R0, R_2, d1 * R_1, d1 * d1R0, 0.0f};
+        const unsigned F = 0xffffffffu;
+        float k2[4];
+        {
+            const bool h = r & 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float keep = h ? v[4 + i] : v[i], send = h ? v[i] : v[4 + i];
+                k2[i] = keep + __shfl_xor_sync(F, send, 2);
+            }
+        }
+        float2 out;
+        {
+            const bool h = r & 1;
+            out.x = (h ? k2[2] : k2[0]) + __shfl_xor_sync(F, h ? k2[0] : k2[2], 1);
+            out.y = (h ? k2[3] : k2[1]) + __shfl_xor_sync(F, h ? k2[1] : k2[3], 1);
+        }
+        if (FULL || p < ms)
+            *reinterpret_cast<float2 *>(partial + static_cast<int64_t>(__float_as_int(R1.z)) * 8 + 2 * r) = out;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(BWD_WARPS * 32, 3)
 k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart,
                 const int32_t *__restrict__ pextra, const int32_t *__restrict__ ptile_x,
-                const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, const int32_t *__restrict__ toff,
-                unsigned int *__restrict__ hdr, int piece, const float *__restrict__ tck,
-                const float *__restrict__ pstate, const float *__restrict__ gimg, int ntx, int ntiles, int W, int H,
-                float *__restrict__ partial) {
-    __shared__ BSlot slots[BWD_WARPS][32];
+                const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, unsigned int *__restrict__ hdr,
+                int piece, const float *__restrict__ tck, const float *__restrict__ pstate,
+                const float *__restrict__ gimg, int ntx, int ntiles, int W, int H, float *__restrict__ partial) {
+    // dynamic shared memory, per warp: 32 staged slots | 2 x 32 raw records (the next batch's arrive here by
+    // cp.async) | the exchange buffer
+    extern __shared__ __align__(16) unsigned char bwd_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    BSlot *sl = slots[wib];
-    const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    float *const pcomp = partial + comp;   // the term this lane's group ends up holding after reduce8
+    unsigned char *wbase = bwd_smem + static_cast<size_t>(wib) * BWD_SMEM_PER_WARP;
+    BSlot *sl = reinterpret_cast<BSlot *>(wbase);
+    int4 *raw = reinterpret_cast<int4 *>(wbase + 32 * sizeof(BSlot));          // [2][32][4]
+    float *xch = reinterpret_cast<float *>(wbase + 32 * sizeof(BSlot) + 2 * 32 * 64);
     const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
     while (next_piece(hdr + H_TICKET_BWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
@@ -729,80 +825,46 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
             U = __ldg(ps + 160);
         }
         // batches of 32 pairs, aligned to the piece start, from the last one down; ids two batches ahead, records
-        // (and the Gaussian's pair offset) one batch ahead
+        // one batch ahead — straight into shared memory, so that no register holds them during the walk
         const int last = lo + ((hi - lo - 1) & ~31);
-        int g1 = 0, goff = 0;
-        RecRegs r = {};
-        if (last + lane < hi) {
-            const int g = __ldg(pgid + last + lane);
-            r = load_rec(rec, g);
-            goff = __ldg(toff + g);
-        }
+        int buf = 0, g1 = 0;
+        if (last + lane < hi) copy_rec_async(raw + lane * 4, rec, __ldg(pgid + last + lane));
+        copy_commit();
         if (last > lo) g1 = __ldg(pgid + last - 32 + lane);
         const float *ckl = tck + static_cast<int64_t>(t) * 32 + lane;
         // checkpoint of the sub-batch walked next, loaded one sub-batch ahead
         float tnext = __ldcs(ckl + (static_cast<int64_t>(last + ((hi - last - 1) & ~(SUB - 1))) >> SUB_SHIFT) * 32);
         for (int bb = last; bb >= lo; bb -= 32) {
             const int m = min(hi - bb, 32);
+            copy_wait_all();   // a lane reads back only what it copied itself
             {
+                RecRegs r = {};
+                if (lane < m) {
+                    const int4 *rr = raw + (buf * 32 + lane) * 4;
+                    r.a = rr[0]; r.b = rr[1]; r.c = rr[2]; r.d = rr[3];
+                }
                 const uint32_t mask = coverage_mask(r, lane < m, x0, y0);
-                const int q = pair_id(r, goff, tx, ty);
+                const int q = pair_id(r, tx, ty);
                 BSlot &s = sl[lane];
                 s.f0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
                 s.f1 = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
-                s.r0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.b.z), i2f(r.b.w));
-                s.r1 = make_float4(i2f(r.c.x), i2f(r.c.y), __uint_as_float(mask), i2f(q));
+                s.r0 = make_float4(i2f(r.b.z), i2f(r.b.w), i2f(r.c.x), i2f(r.c.y));
+                s.r1 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(q), 0.0f);
             }
-            int g2 = 0;
-            if (bb - 64 >= lo) g2 = __ldg(pgid + bb - 64 + lane);
-            if (bb - 32 >= lo) {
-                r = load_rec(rec, g1);
-                goff = __ldg(toff + g1);
-            }
-            g1 = g2;
+            buf ^= 1;
+            if (bb - 32 >= lo) copy_rec_async(raw + (buf * 32 + lane) * 4, rec, g1);
+            copy_commit();
+            g1 = (bb - 64 >= lo) ? __ldg(pgid + bb - 64 + lane) : 0;
             __syncwarp();
             for (int sb = (m - 1) >> SUB_SHIFT; sb >= 0; --sb) {   // sub-batches of SUB = 8 pairs, the last one first
                 const int s0 = sb * SUB, ms = min(m - s0, SUB);
-                float T = tnext;
+                const float T = carry * tnext;
                 {   // the checkpoint after this one in walking order: the previous sub-batch of the piece
                     const int nb = bb + s0 - SUB;
                     if (nb >= lo) tnext = __ldcs(ckl + (static_cast<int64_t>(nb) >> SUB_SHIFT) * 32);
                 }
-                // (1) recompute sweep, forward: T and g of every (pair, lane) of the sub-batch
-                float Tk[SUB], Gk[SUB];
-#pragma unroll
-                for (int k = 0; k < SUB; ++k) {
-                    Tk[k] = 0.0f; Gk[k] = 0.0f;
-                    if (k < ms) {   // warp-uniform
-                        const float4 A = sl[s0 + k].f0, B = sl[s0 + k].f1;
-                        const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
-                        const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
-                        Tk[k] = T;
-                        Gk[k] = e.gk;
-                        T = cov ? T * e.x : T;
-                    }
-                }
-                // (2) reverse walk
-#pragma unroll
-                for (int k = SUB - 1; k >= 0; --k) {
-                    if (k < ms) {   // warp-uniform
-                        const float4 R0 = sl[s0 + k].r0, R1 = sl[s0 + k].r1;
-                        const bool cov = (__float_as_uint(R1.z) >> lane) & 1u;
-                        const float Tt = carry * Tk[k], gk = Gk[k];
-                        const float d0 = px - R0.x, d1 = py - R0.y;
-                        const float alpha = R0.z * gk, x = 1.0f - alpha;
-                        const bool alive = cov && (Tt * x != 0.0f);
-                        const float pgl = pg0 * R0.w + pg1 * R1.x + pg2 * R1.y;
-                        const float wv = alive ? alpha * pgl : 0.0f;
-                        const float dalpha = alive ? Tt * (pgl - U) : 0.0f;
-                        U = cov ? fmaf(x, U, wv) : U;   // U_{i-1} = w_i + x_i U_i
-                        const float c = gk * dalpha;
-                        const float cd0 = c * d0, cd1 = c * d1;
-                        const float v[8] = {c, Tt * wv, cd0, cd1, cd0 * d0, cd0 * d1, cd1 * d1, 0.0f};
-                        const float sum = reduce8(v, lane);
-                        if ((lane & 3) == 0) pcomp[static_cast<int64_t>(__float_as_int(R1.w)) * 8] = sum;
-                    }
-                }
+                if (ms == SUB) backward_sub_batch<true>(sl, xch, s0, ms, lane, px, py, pg0, pg1, pg2, T, U, x0, y0, partial);
+                else backward_sub_batch<false>(sl, xch, s0, ms, lane, px, py, pg0, pg1, pg2, T, U, x0, y0, partial);
             }
             __syncwarp();
         }
@@ -812,76 +874,92 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
 // ---- per-Gaussian sums ----
 constexpr int RED_BIG = 64;  // Gaussians with more pairs than this go to k_view_reduce_big (one block each)
 
-// lane c of a group of 8 holds sum c of a Gaussian's partials; what the reference's per-element formulas
+// Where the four gradients of a view go.  index == nullptr: row g of the view's own arrays (the autograd contract,
+// gs_model.py:820).  index != nullptr: row index[g] of parameter-sized arrays, ADDED to what is there — the
+// multi-view step: the reference's boolean-mask selection of a view's Gaussians (gs_model.py:405-413) turns, in
+// autograd's backward, into exactly this scatter-add of the view's gradients into the parameters' .grad.  A view's
+// index holds distinct rows and views follow each other on the stream, so the sums have a fixed order.
+struct GradOut {
+    float *g_mean, *g_lam, *g_opac, *g_l;
+    const int32_t *index;
+};
+
+// S[0..6] = the seven sums of a Gaussian's partials; what the reference's per-element formulas
 // (gs_model.py:733-766) give when summed over the Gaussian's pixels, with X = d Lambda, coef = o g dalpha:
 //   d_opacity = sum g dalpha                      = S0                    (the d/o term of :739 cancels in dalpha)
 //   d_l[k]    = (sum d) / l[k]                    = S1 / l[k]             (:763-766)
 //   d_mean    = sum coef X                        = o Lambda^T (S2, S3)   (:743-750)
 //   d_Lambda  = -1/2 sum coef d^T d               = -o/2 [[S4, S5], [S5, S6]]   (:753-760)
-__device__ __forceinline__ void store_sums(int c, float s, float s_other, bool active, int64_t g,
-                                           const int4 *__restrict__ rec, float *__restrict__ g_mean,
-                                           float *__restrict__ g_lam, float *__restrict__ g_opac,
-                                           float *__restrict__ g_l) {
-    if (!active) return;
-    const int4 ra = __ldg(rec + 4 * g), rb = __ldg(rec + 4 * g + 1);
+__device__ __forceinline__ void store_sums(const float (&S)[7], int64_t g, const int4 *__restrict__ rec,
+                                           const GradOut &out) {
+    int4 ra, rb;
+    ldg256(rec + 4 * g, ra, rb);
+    const int4 rc = __ldg(rec + 4 * g + 2);
     const float o = i2f(rb.z);
-    switch (c) {
-        case 0: g_opac[g] = s; break;
-        case 1: {
-            const int4 rc = __ldg(rec + 4 * g + 2);
-            g_l[3 * g] = s / i2f(rb.w);
-            g_l[3 * g + 1] = s / i2f(rc.x);
-            g_l[3 * g + 2] = s / i2f(rc.y);
-            break;
-        }
-        // the records hold Lambda' = EXP2_SCALE Lambda
-        case 2: g_mean[2 * g] = EXP2_UNSCALE * o * (i2f(ra.z) * s + i2f(rb.x) * s_other); break;
-        case 3: g_mean[2 * g + 1] = EXP2_UNSCALE * o * (i2f(ra.w) * s_other + i2f(rb.y) * s); break;
-        case 4: g_lam[4 * g] = -0.5f * o * s; break;
-        case 5: g_lam[4 * g + 1] = -0.5f * o * s; g_lam[4 * g + 2] = -0.5f * o * s; break;
-        case 6: g_lam[4 * g + 3] = -0.5f * o * s; break;
-        default: break;
+    // the records hold Lambda' = EXP2_SCALE Lambda
+    const float2 gm = make_float2(EXP2_UNSCALE * o * (i2f(ra.z) * S[2] + i2f(rb.x) * S[3]),
+                                  EXP2_UNSCALE * o * (i2f(ra.w) * S[2] + i2f(rb.y) * S[3]));
+    const float h = -0.5f * o;
+    const float4 gL = make_float4(h * S[4], h * S[5], h * S[5], h * S[6]);
+    const float gl0 = S[1] / i2f(rb.w), gl1 = S[1] / i2f(rc.x), gl2 = S[1] / i2f(rc.y);
+    if (out.index == nullptr) {
+        reinterpret_cast<float2 *>(out.g_mean)[g] = gm;
+        reinterpret_cast<float4 *>(out.g_lam)[g] = gL;
+        out.g_opac[g] = S[0];
+        out.g_l[3 * g] = gl0; out.g_l[3 * g + 1] = gl1; out.g_l[3 * g + 2] = gl2;
+    } else {
+        const int64_t j = __ldg(out.index + g);
+        float2 *pm = reinterpret_cast<float2 *>(out.g_mean) + j;
+        float4 *pL = reinterpret_cast<float4 *>(out.g_lam) + j;
+        const float2 m0 = *pm;
+        const float4 L0 = *pL;
+        *pm = make_float2(m0.x + gm.x, m0.y + gm.y);
+        *pL = make_float4(L0.x + gL.x, L0.y + gL.y, L0.z + gL.z, L0.w + gL.w);
+        out.g_opac[j] += S[0];
+        out.g_l[3 * j] += gl0; out.g_l[3 * j + 1] += gl1; out.g_l[3 * j + 2] += gl2;
     }
 }
 
-// 8 lanes per Gaussian: lane c adds term c of the Gaussian's partials in pair order.  Gaussians with more than
-// RED_BIG pairs (boxes of thousands of pixels, bundled scene) are appended to `big` instead; the order of that
-// list does not enter any float sum.
+__device__ __forceinline__ void add_partial(float (&S)[7], const int4 &u, const int4 &v) {
+    S[0] += i2f(u.x); S[1] += i2f(u.y); S[2] += i2f(u.z); S[3] += i2f(u.w);
+    S[4] += i2f(v.x); S[5] += i2f(v.y); S[6] += i2f(v.z);
+}
+
+// one thread per Gaussian: its pairs' partials (32 bytes each, contiguous in pair order — consecutive lanes read
+// consecutive ranges) are added in pair order, four pairs = four LDG.256 in flight at a time.  Gaussians with more
+// than RED_BIG pairs (boxes of thousands of pixels, bundled scene) are appended to `big` instead; the order of
+// that list does not enter any float sum.
 __global__ void __launch_bounds__(256)
 k_view_reduce(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
-              int64_t n, float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
-              float *__restrict__ g_l, unsigned int *__restrict__ hdr, int32_t *__restrict__ big) {
-    const int c = threadIdx.x & 7;
-    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
-    bool active = g < n;
-    int b = 0, e = 0;
-    if (active) {
-        b = __ldg(toff + g);
-        e = __ldg(toff + g + 1);
-        if (e - b > RED_BIG) {
-            if (c == 0) big[atomicAdd(hdr + H_NBIG, 1u)] = static_cast<int32_t>(g);
-            active = false;
-            e = b;
+              int64_t n, GradOut out, unsigned int *__restrict__ hdr, int32_t *__restrict__ big) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
+    if (e - b > RED_BIG) {
+        big[atomicAdd(hdr + H_NBIG, 1u)] = static_cast<int32_t>(g);
+        return;
+    }
+    float S[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int4 zero = make_int4(0, 0, 0, 0);
+    for (int q = b; q < e; q += 4) {
+        int4 u[4], v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            u[i] = zero; v[i] = zero;
+            if (q + i < e) ldg256(partial + static_cast<int64_t>(q + i) * 8, u[i], v[i]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (q + i < e) add_partial(S, u[i], v[i]);
     }
-    float s = 0.0f;
-    int q = b;
-    for (; q + 4 <= e; q += 4) {
-        const float *p = partial + static_cast<int64_t>(q) * 8 + c;
-        const float v0 = __ldcs(p), v1 = __ldcs(p + 8), v2 = __ldcs(p + 16), v3 = __ldcs(p + 24);
-        s += v0; s += v1; s += v2; s += v3;
-    }
-    for (; q < e; ++q) s += __ldcs(partial + static_cast<int64_t>(q) * 8 + c);
-    const float s_other = __shfl_xor_sync(0xffffffffu, s, 1);   // lanes 2 <-> 3: the two first moments
-    store_sums(c, s, s_other, active, g, rec, g_mean, g_lam, g_opac, g_l);
+    store_sums(S, g, rec, out);
 }
 
 // one block per big Gaussian: 32 groups of 8 lanes stride over its pairs (group j takes pairs j, j+32, ...), the 32
 // group sums are added in group order — a fixed order, bitwise reproducible
 __global__ void __launch_bounds__(256)
 k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
-                  float *__restrict__ g_mean, float *__restrict__ g_lam, float *__restrict__ g_opac,
-                  float *__restrict__ g_l, const unsigned int *__restrict__ hdr, const int32_t *__restrict__ big) {
+                  GradOut out, const unsigned int *__restrict__ hdr, const int32_t *__restrict__ big) {
     __shared__ float sums[32][8];
     const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
     const unsigned int nb = hdr[H_NBIG];
@@ -898,12 +976,16 @@ k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__
         for (; q < e; q += 32) s += __ldcs(partial + static_cast<int64_t>(q) * 8 + c);
         sums[j][c] = s;
         __syncthreads();
-        if (j == 0) {
-            float t = 0.0f;
+        if (threadIdx.x == 0) {
+            float S[7];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) t += sums[k][c];
-            const float t_other = __shfl_xor_sync(0xffu, t, 1);
-            store_sums(c, t, t_other, true, g, rec, g_mean, g_lam, g_opac, g_l);
+            for (int cc = 0; cc < 7; ++cc) {
+                float t = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) t += sums[k][cc];
+                S[cc] = t;
+            }
+            store_sums(S, g, rec, out);
         }
         __syncthreads();
     }
@@ -972,7 +1054,7 @@ PairLayout pair_layout(int64_t cap, int ntiles) {
 }
 
 // persistent grid of the walk kernels: every resident warp slot of the device
-unsigned walk_grid(const void *kernel, int threads) {
+unsigned walk_grid(const void *kernel, int threads, int dyn_smem = 0) {
     static const void *known[4] = {nullptr, nullptr, nullptr, nullptr};
     static unsigned slots[4] = {0, 0, 0, 0};
     int i = 0;
@@ -980,7 +1062,8 @@ unsigned walk_grid(const void *kernel, int threads) {
     if (known[i] != kernel) {
         int dev = 0, sms = 148, per_sm = 1;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+        if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         slots[i] = static_cast<unsigned>(sms * per_sm);
         known[i] = kernel;
@@ -1076,7 +1159,8 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     int4 *rec = at<int4>(plan, A.rec);
     if (n > 0) {
         int32_t *pg = at<int32_t>(pairs, B.bin_pg), *pt = at<int32_t>(pairs, B.bin_pt), *ps = at<int32_t>(pairs, B.bin_ps);
-        k_view_pack<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, n, W, H, rec);
+        k_view_pack<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, n, W, H, at<int32_t>(plan, A.toff),
+                                                        rec);
         k_view_slots<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(rec, at<int32_t>(plan, A.toff), n, ntx, pair_cap,
                                                                       hdr, tcount, pg, pt, ps);
         k_view_scan<<<A.nb2, SCAN_THREADS, 0, st>>>(tcount, ntiles, tstart, hdr + H_TICKET_S2,
@@ -1091,7 +1175,15 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     k_view_sort<<<blocks_for(ntiles, 8), 256, 0, st>>>(tcount, tstart, ntiles, g_piece, pair_cap, hdr, pgid, pextra,
                                                        ptile_x, at<int32_t>(plan, A.mlist),
                                                        at<int32_t>(plan, A.longlist));
-    k_view_sort_long<<<296, 256, 0, st>>>(tcount, tstart, pair_cap, hdr, at<int32_t>(plan, A.longlist), pgid);
+    {
+        static bool attr_set = false;   // (per process; the attribute is per device, set again costs nothing)
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_view_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM * 4);
+            attr_set = true;
+        }
+        k_view_sort_long<<<296, SORT_LONG_THREADS, SORT_SMEM * 4, st>>>(tcount, tstart, pair_cap, hdr,
+                                                                       at<int32_t>(plan, A.longlist), pgid);
+    }
     float *tck = at<float>(pairs, B.tck), *pstate = at<float>(pairs, B.pstate);
     if (keep) {
         const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_render<true>), TILE_WARPS * 32);
@@ -1121,13 +1213,14 @@ int gcp_view_forward(const int32_t *sp, const int32_t *ep, const float *mean, co
     return rc;
 }
 
-int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
-                      const float *grad_image, int64_t n, int W, int H, float *g_mean, float *g_lam, float *g_opac,
-                      float *g_l, gcp_stream_t stream) {
+int gcp_view_backward_scatter(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
+                              const float *grad_image, int64_t n, int W, int H, const int32_t *index, float *g_mean,
+                              float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
     t_view_launches = 0;
     if (n < 0 || bad_image(W, H) || !plan || !pairs || !grad_image || pair_cap < 0) return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
     if (!g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(g_mean) & 7) || (reinterpret_cast<uintptr_t>(g_lam) & 15)) return GCP_ERR_INVALID_ARG;
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
     const PlanLayout A = plan_layout(n, ntiles);
     const PairLayout B = pair_layout(pair_cap, ntiles);
@@ -1143,15 +1236,23 @@ int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_by
     float *pstate = at<float>(pairs, B.pstate), *partial = at<float>(pairs, B.partial);
     k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, g_piece, grad_image, ntx, W,
                                            H, pstate);
-    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32);
-    k_view_backward<<<grid, BWD_WARPS * 32, 0, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(pairs, B.pgid), rec,
-                                                     toff, hdr, g_piece, at<float>(pairs, B.tck), pstate, grad_image,
-                                                     ntx, ntiles, W, H, partial);
+    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32, BWD_SMEM);
+    k_view_backward<<<grid, BWD_WARPS * 32, BWD_SMEM, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(pairs, B.pgid), rec,
+                                                     hdr, g_piece, at<float>(pairs, B.tck), pstate, grad_image, ntx,
+                                                     ntiles, W, H, partial);
     int32_t *big = at<int32_t>(plan, A.big);
-    k_view_reduce<<<blocks_for(n, 32), 256, 0, st>>>(partial, toff, rec, n, g_mean, g_lam, g_opac, g_l, hdr, big);
-    k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, g_mean, g_lam, g_opac, g_l, hdr, big);
+    const GradOut out = {g_mean, g_lam, g_opac, g_l, index};
+    k_view_reduce<<<blocks_for(n, 256), 256, 0, st>>>(partial, toff, rec, n, out, hdr, big);
+    k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, out, hdr, big);
     t_view_launches += 4;
     return static_cast<int>(cudaGetLastError());
+}
+
+int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
+                      const float *grad_image, int64_t n, int W, int H, float *g_mean, float *g_lam, float *g_opac,
+                      float *g_l, gcp_stream_t stream) {
+    return gcp_view_backward_scatter(plan, plan_bytes, pairs, pair_bytes, pair_cap, grad_image, n, W, H, nullptr, g_mean,
+                                     g_lam, g_opac, g_l, stream);
 }
 
 }  // extern "C"
