@@ -422,14 +422,110 @@ k_view_sort(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tsta
     else sort_segment<16>(seg, len, lane);
 }
 
-// lists longer than SORT_REGS: one block each.  The list is copied into shared memory (up to SORT_SMEM ids; the
-// bundled scene's longest tile list has 7 656), sorted there by the same network and copied back; a list that
-// does not fit is sorted in place in global memory (it stays in L1/L2).
-constexpr int SORT_LONG_THREADS = 512;
-constexpr int SORT_SMEM = 24576;   // ids = 96 KB of dynamic shared memory
+// lists longer than SORT_REGS.  Up to SORT_BLOCK = 8 warps x 512 ids: one block, the ids in registers.  Every
+// warp sorts its 512-id chunk with the register network, alternating directions, then the chunks are merged: in a
+// merge stage the partners at distance >= 512 sit in another warp (same lane, same register) and are exchanged
+// through shared memory, the distances below 512 are the register / shuffle steps again.  Only as many warps as
+// the list needs take part (a power of two).  Longer lists (the bundled scene's longest has 7 656 ids) go through
+// shared memory as a whole (up to SORT_SMEM ids), and what does not fit is sorted in place in global memory.
+constexpr int SORT_WARPS = 8;
+constexpr int SORT_BLOCK = SORT_WARPS * SORT_REGS;   // 4096
+constexpr int SORT_SMEM = 24576;                     // ids = 96 KB of dynamic shared memory (k_view_sort_huge)
 
-__global__ void __launch_bounds__(SORT_LONG_THREADS)
+// the steps j = 256 .. 1 of a merge stage whose direction is the same for the whole warp
+template <int E>
+__device__ __forceinline__ void warp_bitonic_merge(int32_t (&v)[E], int lane, bool asc) {
+#pragma unroll
+    for (int j = (32 * E) >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {
+            const int je = j >> 5;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if ((e & je) == 0) {
+                    const int32_t a = v[e], b = v[e | je];
+                    const int32_t lo = min(a, b), hi = max(a, b);
+                    v[e] = asc ? lo : hi;
+                    v[e | je] = asc ? hi : lo;
+                }
+            }
+        } else {
+            const bool upper = (lane & j) != 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
+                v[e] = (asc != upper) ? min(v[e], o) : max(v[e], o);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SORT_WARPS * 32)
 k_view_sort_long(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
+                 const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
+    constexpr int E = SORT_REGS / 32;
+    __shared__ int32_t s_x[SORT_BLOCK];
+    if (overflowed(hdr, cap)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int nl = hdr[H_NLONG];
+    for (unsigned int i = blockIdx.x; i < nl; i += gridDim.x) {
+        const int t = longlist[i];
+        const int len = tcount[t];
+        if (len > SORT_BLOCK) continue;   // k_view_sort_huge
+        int32_t *seg = pgid + tstart[t];
+        int nw = 2;
+        while (nw * SORT_REGS < len) nw <<= 1;
+        const bool active = warp < nw;   // warp-uniform
+        int32_t v[E];
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int k = warp * SORT_REGS + e * 32 + lane;
+                v[e] = k < len ? seg[k] : 0x7fffffff;
+            }
+            warp_bitonic_sort<E>(v, lane);                 // ascending ...
+            if (warp & 1) {                                // ... odd chunks descending: reverse them
+#pragma unroll
+                for (int e = 0; e < E / 2; ++e) {
+                    const int32_t a = __shfl_sync(0xffffffffu, v[e], 31 - lane);
+                    const int32_t b = __shfl_sync(0xffffffffu, v[E - 1 - e], 31 - lane);
+                    v[e] = b; v[E - 1 - e] = a;
+                }
+            }
+        }
+        for (int k = 2 * SORT_REGS; k <= nw * SORT_REGS; k <<= 1) {
+            const bool asc = ((warp * SORT_REGS) & k) == 0;
+            for (int j = k >> 1; j >= SORT_REGS; j >>= 1) {
+                if (active) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) s_x[warp * SORT_REGS + e * 32 + lane] = v[e];
+                }
+                __syncthreads();
+                if (active) {
+                    const int pw = warp ^ (j / SORT_REGS);
+                    const bool upper = (warp * SORT_REGS) & j;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int32_t o = s_x[pw * SORT_REGS + e * 32 + lane];
+                        v[e] = (asc != upper) ? min(v[e], o) : max(v[e], o);
+                    }
+                }
+                __syncthreads();
+            }
+            if (active) warp_bitonic_merge<E>(v, lane, asc);
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int k = warp * SORT_REGS + e * 32 + lane;
+                if (k < len) seg[k] = v[e];
+            }
+        }
+    }
+}
+
+constexpr int SORT_HUGE_THREADS = 1024;
+__global__ void __launch_bounds__(SORT_HUGE_THREADS)
+k_view_sort_huge(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
                  const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
     extern __shared__ int32_t s_ids[];
     if (overflowed(hdr, cap)) return;
@@ -437,6 +533,7 @@ k_view_sort_long(const int32_t *__restrict__ tcount, const int32_t *__restrict__
     for (unsigned int i = blockIdx.x; i < nl; i += gridDim.x) {
         const int t = longlist[i];
         const int len = tcount[t];
+        if (len <= SORT_BLOCK) continue;   // k_view_sort_long
         int32_t *seg = pgid + tstart[t];
         if (len <= SORT_SMEM) {
             for (int k = threadIdx.x; k < len; k += blockDim.x) s_ids[k] = seg[k];
@@ -517,12 +614,14 @@ __device__ __forceinline__ int pair_id(const RecRegs &r, int tx, int ty) {
     return r.d.z + (ty - ty0) * nx + (tx - tx0);
 }
 // the record of Gaussian g copied into shared memory without passing through registers (LDGSTS, 4 x 16 bytes)
+// quarter i of the record lands in dst[i * 32]: with dst = plane base + lane, the 32 lanes of a warp write
+// consecutive 16-byte words per quarter (no bank conflicts)
 __device__ __forceinline__ void copy_rec_async(int4 *dst, const int4 *__restrict__ rec, int g) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
     const int4 *src = rec + 4 * static_cast<int64_t>(g);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16 * i), "l"(src + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 512 * i), "l"(src + i) : "memory");
 }
 __device__ __forceinline__ void copy_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void copy_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -548,8 +647,10 @@ __device__ __forceinline__ PairEval eval_pair(const float4 &a, float l10, float 
 // ---- forward ----
 // What the forward walk needs of a pair, staged in shared memory by the lane that loaded it (three broadcast
 // LDS.128 per pair): {mx, my, l00, l01} {l10, l11, o, coverage mask} {l0, l1, l2, -}
+// (component planes: lane l writes a[l], b[l], c[l] — consecutive 16-byte words, no bank conflicts; an
+// array of 48-byte structs costs a 12-way conflict per staging store)
 struct FSlot {
-    float4 a, b, c;
+    float4 a[32], b[32], c[32];
 };
 constexpr int TILE_WARPS = 8;
 
@@ -560,10 +661,10 @@ k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ ts
               const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, unsigned int *__restrict__ hdr,
               int64_t cap, int piece, int ntx, int ntiles, int W, int H, float *__restrict__ image,
               float *__restrict__ tck, float *__restrict__ pstate) {
-    __shared__ FSlot slots[TILE_WARPS][32];
+    __shared__ FSlot slots[TILE_WARPS];
     if (overflowed(hdr, cap)) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    FSlot *sl = slots[wib];
+    FSlot &sl = slots[wib];
     const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
     while (next_piece(hdr + H_TICKET_FWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
@@ -583,9 +684,9 @@ k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ ts
         for (int b = lo; b < hi; b += 32) {
             {
                 const uint32_t mask = coverage_mask(r, b + lane < hi, x0, y0);
-                sl[lane].a = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
-                sl[lane].b = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
-                sl[lane].c = make_float4(i2f(r.b.w), i2f(r.c.x), i2f(r.c.y), 0.0f);
+                sl.a[lane] = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
+                sl.b[lane] = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
+                sl.c[lane] = make_float4(i2f(r.b.w), i2f(r.c.x), i2f(r.c.y), 0.0f);
             }
             int g2 = 0;
             if (b + 64 + lane < hi) g2 = __ldg(pgid + b + 64 + lane);
@@ -598,7 +699,7 @@ k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ ts
             float *ck = tck + ((static_cast<int64_t>(b) >> SUB_SHIFT) + t) * 32 + lane;
 #pragma unroll 4
             for (int k = 0; k < m; ++k) {
-                const float4 A = sl[k].a, B = sl[k].b, C = sl[k].c;
+                const float4 A = sl.a[k], B = sl.b[k], C = sl.c[k];
                 const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
                 const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
                 if (KEEP && (k & (SUB - 1)) == 0) __stcs(ck + (k >> SUB_SHIFT) * 32, T);   // T checkpoint for the backward
@@ -681,14 +782,16 @@ k_view_combine_bwd(const int32_t *__restrict__ tcount, const int32_t *__restrict
 // Staged per pair (64 bytes, broadcast LDS.128: two in the recompute sweep, one in the reverse walk, one per
 // pair in the moment phase):
 //   f0 {mx, my, l00, l01}  f1 {l10, l11, o, coverage mask}  |  r0 {o, l0, l1, l2}  r1 {mx, my, pair id, -}
+// Component planes (lane l stages f0[l], f1[l], r0[l], r1[l]: consecutive 16-byte words, conflict-free; as an
+// array of 64-byte structs every staging store was a 16-way bank conflict).
 struct BSlot {
-    float4 f0, f1, r0, r1;
+    float4 f0[32], f1[32], r0[32], r1[32];
 };
 constexpr int BWD_WARPS = 8;
 // exchange buffer of a warp: for each of the SUB pairs of a sub-batch, c[32] and dv[32] of its pixels.  The pair
 // stride of 68 words keeps the moment phase's LDS.128 (lanes = 8 pairs x 4 tile rows) free of bank conflicts.
 constexpr int XCH_STRIDE = 68;
-constexpr int BWD_SMEM_PER_WARP = 32 * 64 + 2 * 32 * 64 + SUB * XCH_STRIDE * 4;
+constexpr int BWD_SMEM_PER_WARP = static_cast<int>(sizeof(BSlot)) + 2 * 32 * 64 + SUB * XCH_STRIDE * 4;
 constexpr int BWD_SMEM = BWD_WARPS * BWD_SMEM_PER_WARP;
 
 // partial[q] = {sum c, sum d, sum c d0, sum c d1, sum c d0 d0, sum c d0 d1, sum c d1 d1, -} over the pixels of
@@ -705,7 +808,7 @@ constexpr int BWD_SMEM = BWD_WARPS * BWD_SMEM_PER_WARP;
 // instructions per pair), the cross-lane traffic per pair is 2 STS + 4/8 LDS.128 + 6/8 SHFL.  The order of every
 // sum is fixed: bitwise reproducible.
 template <bool FULL>
-__device__ __forceinline__ void backward_sub_batch(const BSlot *__restrict__ sl, float *__restrict__ xch, int s0, int ms,
+__device__ __forceinline__ void backward_sub_batch(const BSlot &sl, float *__restrict__ xch, int s0, int ms,
                                                    int lane, float px, float py, float pg0, float pg1, float pg2,
                                                    float T, float &U, int x0, int y0, float *__restrict__ partial) {
     // (1) recompute sweep, forward: T and g of every (pair, lane) of the sub-batch; coverage bits kept per lane
@@ -715,7 +818,7 @@ __device__ __forceinline__ void backward_sub_batch(const BSlot *__restrict__ sl,
     for (int k = 0; k < SUB; ++k) {
         Tk[k] = 0.0f; Gk[k] = 0.0f;
         if (FULL || k < ms) {   // warp-uniform
-            const float4 A = sl[s0 + k].f0, B = sl[s0 + k].f1;
+            const float4 A = sl.f0[s0 + k], B = sl.f1[s0 + k];
             const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
             const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
             Tk[k] = T;
@@ -728,7 +831,7 @@ __device__ __forceinline__ void backward_sub_batch(const BSlot *__restrict__ sl,
 #pragma unroll
     for (int k = SUB - 1; k >= 0; --k) {
         if (FULL || k < ms) {   // warp-uniform
-            const float4 R0 = sl[s0 + k].r0;
+            const float4 R0 = sl.r0[s0 + k];
             const bool cov = (covbits >> k) & 1u;
             const float Tt = Tk[k], gk = Gk[k];
             const float alpha = R0.x * gk, x = 1.0f - alpha;
@@ -745,7 +848,7 @@ __device__ __forceinline__ void backward_sub_batch(const BSlot *__restrict__ sl,
     // (3) moments: lane = (pair p of the sub-batch, row r of the tile)
     {
         const int p = lane >> 2, r = lane & 3;
-        const float4 R1 = sl[s0 + p].r1;
+        const float4 R1 = sl.r1[s0 + p];
         const float *xc = xch + p * XCH_STRIDE + r * TW;
         const float4 ca = *reinterpret_cast<const float4 *>(xc), cb = *reinterpret_cast<const float4 *>(xc + 4);
         const float4 da = *reinterpret_cast<const float4 *>(xc + 32), db = *reinterpret_cast<const float4 *>(xc + 36);
@@ -798,9 +901,9 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
     extern __shared__ __align__(16) unsigned char bwd_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char *wbase = bwd_smem + static_cast<size_t>(wib) * BWD_SMEM_PER_WARP;
-    BSlot *sl = reinterpret_cast<BSlot *>(wbase);
-    int4 *raw = reinterpret_cast<int4 *>(wbase + 32 * sizeof(BSlot));          // [2][32][4]
-    float *xch = reinterpret_cast<float *>(wbase + 32 * sizeof(BSlot) + 2 * 32 * 64);
+    BSlot &sl = *reinterpret_cast<BSlot *>(wbase);
+    int4 *raw = reinterpret_cast<int4 *>(wbase + sizeof(BSlot));          // [2 buffers][4 quarters][32 lanes]
+    float *xch = reinterpret_cast<float *>(wbase + sizeof(BSlot) + 2 * 32 * 64);
     const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
     while (next_piece(hdr + H_TICKET_BWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
@@ -828,7 +931,7 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
         // one batch ahead — straight into shared memory, so that no register holds them during the walk
         const int last = lo + ((hi - lo - 1) & ~31);
         int buf = 0, g1 = 0;
-        if (last + lane < hi) copy_rec_async(raw + lane * 4, rec, __ldg(pgid + last + lane));
+        if (last + lane < hi) copy_rec_async(raw + lane, rec, __ldg(pgid + last + lane));
         copy_commit();
         if (last > lo) g1 = __ldg(pgid + last - 32 + lane);
         const float *ckl = tck + static_cast<int64_t>(t) * 32 + lane;
@@ -840,19 +943,18 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
             {
                 RecRegs r = {};
                 if (lane < m) {
-                    const int4 *rr = raw + (buf * 32 + lane) * 4;
-                    r.a = rr[0]; r.b = rr[1]; r.c = rr[2]; r.d = rr[3];
+                    const int4 *rr = raw + buf * 128 + lane;
+                    r.a = rr[0]; r.b = rr[32]; r.c = rr[64]; r.d = rr[96];
                 }
                 const uint32_t mask = coverage_mask(r, lane < m, x0, y0);
                 const int q = pair_id(r, tx, ty);
-                BSlot &s = sl[lane];
-                s.f0 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
-                s.f1 = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
-                s.r0 = make_float4(i2f(r.b.z), i2f(r.b.w), i2f(r.c.x), i2f(r.c.y));
-                s.r1 = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(q), 0.0f);
+                sl.f0[lane] = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(r.a.z), i2f(r.a.w));
+                sl.f1[lane] = make_float4(i2f(r.b.x), i2f(r.b.y), i2f(r.b.z), __uint_as_float(mask));
+                sl.r0[lane] = make_float4(i2f(r.b.z), i2f(r.b.w), i2f(r.c.x), i2f(r.c.y));
+                sl.r1[lane] = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(q), 0.0f);
             }
             buf ^= 1;
-            if (bb - 32 >= lo) copy_rec_async(raw + (buf * 32 + lane) * 4, rec, g1);
+            if (bb - 32 >= lo) copy_rec_async(raw + buf * 128 + lane, rec, g1);
             copy_commit();
             g1 = (bb - 64 >= lo) ? __ldg(pgid + bb - 64 + lane) : 0;
             __syncwarp();
@@ -1176,13 +1278,14 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
                                                        ptile_x, at<int32_t>(plan, A.mlist),
                                                        at<int32_t>(plan, A.longlist));
     {
-        static bool attr_set = false;   // (per process; the attribute is per device, set again costs nothing)
+        static bool attr_set = false;   // (per process; setting the attribute again costs nothing)
         if (!attr_set) {
-            cudaFuncSetAttribute(k_view_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM * 4);
+            cudaFuncSetAttribute(k_view_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM * 4);
             attr_set = true;
         }
-        k_view_sort_long<<<296, SORT_LONG_THREADS, SORT_SMEM * 4, st>>>(tcount, tstart, pair_cap, hdr,
-                                                                       at<int32_t>(plan, A.longlist), pgid);
+        const int32_t *ll = at<int32_t>(plan, A.longlist);
+        k_view_sort_long<<<148 * 4, SORT_WARPS * 32, 0, st>>>(tcount, tstart, pair_cap, hdr, ll, pgid);
+        k_view_sort_huge<<<148, SORT_HUGE_THREADS, SORT_SMEM * 4, st>>>(tcount, tstart, pair_cap, hdr, ll, pgid);
     }
     float *tck = at<float>(pairs, B.tck), *pstate = at<float>(pairs, B.pstate);
     if (keep) {
@@ -1196,7 +1299,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     }
     k_view_combine_fwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, pair_cap, g_piece, ntx, W,
                                            H, pstate, image);
-    t_view_launches += 4;
+    t_view_launches += 5;
     return static_cast<int>(cudaGetLastError());
 }
 

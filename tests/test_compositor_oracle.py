@@ -18,24 +18,24 @@ def load_case(f, name):
                 grad_l=g("grad_l"))
 
 
-def close(a, b, rtol=2e-4, atol=2e-5):
-    # the reference computed in fp32 (torch CPU) with its own association order; the oracle is fp64
-    return np.allclose(a, b, rtol=rtol, atol=atol)
-
-
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_reproduces_reference_function(name):
+    """The reference's own fp32 Function (the fixture) lies within the north star's tolerance of the fp64 oracle,
+    |fixture - fp64| <= 1e-6 + 1e-5 * scale with scale = sum of |terms| (worst measured ratio 0.16): the oracle
+    is pinned, and the same bound is what the native compositor is held to (tests/test_compositor.py)."""
     from oracle import compositor_oracle as co
 
     c = load_case(np.load(FIX), name)
     img, cache = co.forward(c["boxsize"], c["sp"], c["ep"], c["mean"], c["lam"], c["opac"], c["l_d"], c["W"], c["H"])
     assert img.shape == c["image"].shape == (c["H"] + 1, c["W"] + 1, 3)
-    assert close(img, c["image"]), np.abs(img - c["image"]).max()
-    gm, gL, go, gl = co.backward(cache, c["grad_image"])
-    assert close(gm, c["grad_mean"], rtol=1e-3, atol=1e-4), np.abs(gm - c["grad_mean"]).max()
-    assert close(gL, c["grad_lambda"], rtol=1e-3, atol=1e-3), np.abs(gL - c["grad_lambda"]).max()
-    assert close(go, c["grad_opacity"], rtol=1e-3, atol=1e-4), np.abs(go - c["grad_opacity"]).max()
-    assert close(gl, c["grad_l"], rtol=1e-3, atol=1e-4), np.abs(gl - c["grad_l"]).max()
+    grads, sc = co.backward(cache, c["grad_image"], scales=True)
+    ref = (img,) + tuple(grads)
+    scales = (co.image_scale(cache, c["W"], c["H"]),) + tuple(sc)
+    fix = (c["image"], c["grad_mean"], c["grad_lambda"], c["grad_opacity"], c["grad_l"])
+    for out, e, plain, cond in co.error_table(fix, ref, scales):
+        assert cond <= 1.0, (out, e, plain, cond)
+    # without cancellation the scale IS |ref|: the image meets the plain form of the tolerance too
+    assert co.error_table(fix, ref, scales)[0][2] <= 1.0
 
 
 def test_chunked_reference_render_differs_only_by_its_boundary_carry():
