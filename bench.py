@@ -472,9 +472,8 @@ def splat_legs(args, device, rank, world):
     from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
 
     mine = vw.views_for_rank(args.views, rank, world)
-    distinct = max(1, min(2, len(mine)))           # scene generation is host-side numpy: reuse a few views
-    scenes = [wl.splat_view(1920, 1080, 1_000_000, seed=1080 + mine[i] if mine else 1080, device=device)
-              for i in range(distinct)]
+    distinct = 1                                   # the single-view legs: view 0 of the splat-route workload (numpy rng)
+    scenes = [wl.splat_view(1920, 1080, 1_000_000, seed=1080, device=device)]
     n_param = 1_000_000
     bucket = torch.zeros(n_param * vw.PARAM_FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
     leaves = []
@@ -538,51 +537,17 @@ def splat_legs(args, device, rank, world):
     compositor.ROUTE = default_route
     out = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n, "route": default_route,
            **routes[default_route], "unit": "ms per view (render + backward), median of 9", "routes": routes}
-    # (ii) multi-view step.  One untimed step first: the first collective of a process sets up NCCL's channels and
-    #      buffers (30 ms at 8 ranks), which is not part of a training step.
-    steps = 3
-    bucket.zero_()
-    for i in range(len(mine)):
-        one_view(i, plan_next=True)
-    vw.allreduce_param_grads(bucket)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0, t1, t2 = ev(), ev(), ev()
-    step_ms = ar_ms = 0.0
-    elems = 0
-    for _ in range(steps):
-        bucket.zero_()
-        t0.record()
-        marks = []
-        elems = 0
-        host_t0 = time.perf_counter()
-        for i in range(len(mine)):
-            if os.environ.get("BENCH_MV_TRACE") and i % 8 == 0:
-                marks.append(ev())
-                marks[-1].record()
-            elems += one_view(i, plan_next=True)
-        host_ms = (time.perf_counter() - host_t0) * 1e3
-        t1.record()
-        vw.allreduce_param_grads(bucket)
-        t2.record()
-        torch.cuda.synchronize()
-        step_ms += t0.elapsed_time(t2)
-        ar_ms += t1.elapsed_time(t2)
-        print(f"multi-view step: {t0.elapsed_time(t2):.2f} ms (host enqueue loop {host_ms:.2f} ms) " +
-              " ".join(f"{marks[j].elapsed_time(marks[j + 1]) / 8:.3f}" for j in range(len(marks) - 1)), file=sys.stderr)
-    tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
-    _, max_ar = vw.aggregate_throughput(0, ar_ms / steps, device)
-    # the rank that arrives last waits for nobody: its time is the collective itself
-    min_ar = torch.tensor([ar_ms / steps], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(min_ar, op=dist.ReduceOp.MIN)
-    min_ar = float(min_ar.item())
-    out["multi_view"] = {"views": args.views, "views_per_rank": len(mine), "distinct_scenes_per_rank": distinct,
-                         "step_ms": max_ms, "allreduce_ms": min_ar, "allreduce_plus_wait_for_slowest_rank_ms": max_ar,
-                         "bucket_bytes": bucket.numel() * 4,
-                         "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
-                         "collective": "nccl all_reduce(sum) of the parameter-gradient bucket" if world > 1 else "none (1 rank)"}
+    # (ii) multi-view training step (BASELINE.json configs[4]): this rank's share of `--views` DISTINCT views (seed
+    #      1080 + view id, drawn on the device), one native call per step (views.NativeViewBatch -> gcp_views_step:
+    #      render, MSE-loss gradient, backward, scatter-add into the bucket), and the all-reduce of the bucket hidden
+    #      behind the last view: the bucket of views 0..V-2 is reduced on a side stream while view V-1 runs into a
+    #      small bucket of its own (the 10 floats per Gaussian the compositor produces), which is reduced and added
+    #      at the end.
+    del scenes, leaves
+    torch.cuda.empty_cache()
+    out["multi_view"] = multi_view_leg(args, device, rank, world, mine, n_param, bucket)
+    if rank == 0 and world == 1 and not os.environ.get("BENCH_SKIP_PY_LOOP"):
+        out["multi_view_python_loop"] = python_loop_leg(args, device, mine[: min(len(mine), 16)], n_param, bucket)
     # (iii) C2: the scene bundled with the reference (BASELINE.json configs[1]; poses synthesised), rank 0 only:
     #       splat step per view, and the two scan ops on the element list of view 0 (per-pixel lists of ~350)
     if rank == 0:
@@ -591,6 +556,142 @@ def splat_legs(args, device, rank, world):
         except Exception as ex:  # noqa: BLE001
             out["c2_bundled"] = {"error": str(ex)}
     return out
+
+
+def _sections(bucket, n_param):
+    """The four compositor sections of a DDP-like flat bucket (one contiguous section per parameter tensor):
+    mean [n,2] | Lambda [n,4] | opacity [n] | l [n,3] | (the 28 remaining floats per Gaussian follow)."""
+    return (bucket[0:2 * n_param].view(n_param, 2), bucket[2 * n_param:6 * n_param].view(n_param, 4),
+            bucket[6 * n_param:7 * n_param], bucket[7 * n_param:10 * n_param].view(n_param, 3))
+
+
+def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
+    import torch
+    import torch.distributed as dist
+
+    from simplegaussiansplat_tk71_b200 import views as vw
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    W, H = 1920, 1080
+    lanes = int(os.environ.get("BENCH_MV_LANES", "2"))
+    views = [wl.splat_view_device(W, H, n_param, seed=1080 + v, device=device) for v in mine]
+    elems = sum(v.elements for v in views)
+    target = torch.rand(H + 1, W + 1, 3, device=device)
+    head, tail = views[:-1], views[-1:]
+    bA = vw.NativeViewBatch(head, W, H, targets=[target] * len(head), lanes=lanes) if head else None
+    bB = vw.NativeViewBatch(tail, W, H, targets=[target], lanes=1)
+    small = torch.zeros(10 * n_param, dtype=torch.float32, device=device)     # the last view's own bucket
+    loss = torch.zeros(1, device=device)
+    comm = torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+    secA, secB = _sections(bucket, n_param), _sections(small, n_param)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(marks=None):
+        bucket.zero_()
+        small.zero_()
+        loss.zero_()
+        if bA is not None:
+            bA.step(*secA, loss)
+        if world > 1:
+            done_a = torch.cuda.Event()
+            done_a.record(cur)
+            comm.wait_event(done_a)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(bucket, op=dist.ReduceOp.SUM)          # overlaps the last view
+        bB.step(*secB, loss)
+        if marks is not None:
+            marks[0].record(cur)
+        if world > 1:
+            dist.all_reduce(small, op=dist.ReduceOp.SUM)
+            cur.wait_stream(comm)
+        bucket[:10 * n_param] += small
+
+    def checked_step():
+        for _ in range(3):
+            step()
+            torch.cuda.synchronize()
+            if (bA is None or bA.finish()) & bB.finish():
+                return
+        raise RuntimeError("the view batch did not fit its arenas after two enlargements")
+
+    checked_step()     # sizes the arenas; the first collective of a process also sets up NCCL's channels (untimed)
+    checked_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = 3
+    t0, t1, t2 = ev(), ev(), ev()
+    step_ms = tail_ms = host_ms = 0.0
+    for _ in range(steps):
+        t0.record()
+        h0 = time.perf_counter()
+        step(marks=[t1])
+        host_ms += (time.perf_counter() - h0) * 1e3
+        t2.record()
+        torch.cuda.synchronize()
+        assert (bA is None or bA.finish()) and bB.finish()
+        step_ms += t0.elapsed_time(t2)
+        tail_ms += t1.elapsed_time(t2)
+    print(f"multi-view step (native, lanes={lanes}): {step_ms / steps:.2f} ms, host enqueue {host_ms / steps:.2f} ms, "
+          f"after the last view {tail_ms / steps:.3f} ms, loss {float(loss):.5f}", file=sys.stderr)
+    tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
+    _, max_tail = vw.aggregate_throughput(0, tail_ms / steps, device)
+    launches = (bA.launches if bA is not None else 0) + bB.launches
+    return {"views": args.views, "views_per_rank": len(mine), "distinct_views_per_rank": len(views), "lanes": lanes,
+            "step_ms": max_ms, "host_enqueue_ms": host_ms / steps,
+            "exposed_after_last_view_ms": max_tail,
+            "collective": ("nccl all_reduce(sum): the bucket of views 0..V-2 on a side stream during the last view, "
+                           "then the last view's 10 floats per Gaussian") if world > 1 else "none (1 rank)",
+            "bucket_bytes": bucket.numel() * 4, "tail_bucket_bytes": small.numel() * 4, "loss": "mean squared error",
+            "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
+            "gpu_launches_per_step": launches}
+
+
+def python_loop_leg(args, device, mine, n_param, bucket):
+    """The same step driven view by view through the drop-in autograd Function (round 1's loop): host-bound."""
+    import torch
+
+    from simplegaussiansplat_tk71_b200 import compositor
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    W, H = 1920, 1080
+    views = [wl.splat_view_device(W, H, n_param, seed=1080 + v, device=device) for v in mine]
+    leaves = [[sc.mean.float().requires_grad_(True), sc.lam.clone().requires_grad_(True),
+               sc.opacity.clone().requires_grad_(True), sc.l_d.clone().requires_grad_(True)] for sc in views]
+    gI = torch.rand(H + 1, W + 1, 3, device=device) + 0.1
+    Wt, Ht = torch.tensor(W), torch.tensor(H)
+    sec = _sections(bucket, n_param)
+
+    def one(i):
+        sc, (m, lam, o, l) = views[i], leaves[i]
+        nx = views[(i + 1) % len(views)]
+        compositor.plan_view(nx.boxsize, nx.startpoint, nx.endpoint, W, H)
+        for t_ in (m, lam, o, l):
+            t_.grad = None
+        img = F.apply(sc.boxsize, torch.tensor([sc.n]), sc.startpoint, sc.endpoint, m, lam, o, l, Wt, Ht)
+        img.backward(gI)
+        idx = sc.index.long()
+        sec[0].index_add_(0, idx, m.grad)
+        sec[1].index_add_(0, idx, lam.grad.reshape(-1, 4))
+        sec[2].index_add_(0, idx, o.grad.reshape(-1))
+        sec[3].index_add_(0, idx, l.grad)
+
+    for i in range(len(views)):
+        one(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bucket.zero_()
+    a.record()
+    h0 = time.perf_counter()
+    for i in range(len(views)):
+        one(i)
+    host_ms = (time.perf_counter() - h0) * 1e3
+    b.record()
+    torch.cuda.synchronize()
+    return {"views": len(views), "step_ms": a.elapsed_time(b), "ms_per_view": a.elapsed_time(b) / len(views),
+            "host_enqueue_ms": host_ms}
 
 
 def c2_leg(device):

@@ -318,6 +318,32 @@ int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_by
 int gcp_view_backward_scatter(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
                               const float *grad_image, int64_t n, int W, int H, const int32_t *index, float *g_mean,
                               float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream);
+/* A batch of views in ONE call: the per-view loop of gs_model.py:402-449 around the compositor — render, loss
+ * gradient, backward — with every view's gradients added into the parameters' gradient arrays (gcp_view_backward_scatter).
+ * Nothing waits for the device: every view is rendered on the caller's pair capacity, its pair count is stored in
+ * totals_host[v] (pinned, device-writable), and a view with more pairs than pair_cap is skipped as a whole — the
+ * caller reads the counts after its next synchronisation and repeats the step on larger arenas if any exceeds
+ * pair_cap.  Views alternate between `lanes` streams (lane 0 = the caller's stream), each lane with its own plan
+ * and pair arena (plan[lane], pairs[lane], sized for the largest view: gcp_view_plan_bytes(max n),
+ * gcp_view_pair_bytes(pair_cap)); the scatter-adds are chained in view order, so every sum has a fixed order.
+ * On return the caller's stream waits for all lanes. */
+#define GCP_VIEWS_MAX_LANES 4
+typedef struct gcp_view_desc {
+    const int32_t *sp, *ep;      /* i32[n,2] inclusive box corners, clamped to the image (gs_model.py:419-425) */
+    const float *mean, *lam, *opac, *l_d;   /* f32[n,2], f32[n,4], f32[n], f32[n,3], depth order = index order */
+    const int32_t *index;        /* i32[n] parameter row of every Gaussian (the view's selection), or NULL: row g */
+    const float *target;         /* f32[(H+1)(W+1)3] or NULL.  Not NULL: grad_image is WRITTEN as the gradient of
+                                    mean((image - target)^2) and *loss += that mean; NULL: grad_image is an input */
+    float *grad_image;           /* f32[(H+1)(W+1)3] dL/d image */
+    float *image;                /* f32[(H+1)(W+1)3] out (views of the same lane may share one buffer) */
+    int64_t n;
+} gcp_view_desc;
+typedef struct gcp_views_ctx gcp_views_ctx;   /* the side streams and ordering events of a batch */
+int gcp_views_ctx_create(int lanes, gcp_views_ctx **out);
+void gcp_views_ctx_destroy(gcp_views_ctx *ctx);
+int gcp_views_step(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, int W, int H, void *const *plan,
+                   size_t plan_bytes, void *const *pairs, size_t pair_bytes, int64_t pair_cap, float *g_mean,
+                   float *g_lam, float *g_opac, float *g_l, float *loss, int64_t *totals_host, gcp_stream_t stream);
 /* Test aid: byte offsets of the integer arrays the tests compare bit for bit with oracle/tile_oracle.py.
  * out[0..5] (plan arena): toff i32[n+1] (Gaussian-major pair offsets), tile_count i32[tiles], tile_start
  * i32[tiles+1], piece_extra i32[tiles], header, records; out[6..7] (pair arena): pair_gid i32[cap],

@@ -33,8 +33,17 @@ SYMBOLS = (
     "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs",
     "gcp_view_plan_bytes", "gcp_view_pair_bytes", "gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward",
     "gcp_view_backward", "gcp_view_backward_scatter", "gcp_view_last_launch_count",
+    "gcp_views_ctx_create", "gcp_views_ctx_destroy", "gcp_views_step",
     "gcp_host_boundary_bits", "gcp_ids_from_bits_bytes", "gcp_ids_from_bits",
 )
+
+
+class ViewDesc(ctypes.Structure):
+    """gcp_view_desc of include/gcp_abi.h: one view of a gcp_views_step batch."""
+    _fields_ = [("sp", ctypes.c_void_p), ("ep", ctypes.c_void_p), ("mean", ctypes.c_void_p), ("lam", ctypes.c_void_p),
+                ("opac", ctypes.c_void_p), ("l_d", ctypes.c_void_p), ("index", ctypes.c_void_p),
+                ("target", ctypes.c_void_p), ("grad_image", ctypes.c_void_p), ("image", ctypes.c_void_p),
+                ("n", ctypes.c_int64)]
 
 
 def lib() -> ctypes.CDLL:
@@ -140,8 +149,13 @@ def lib() -> ctypes.CDLL:
     L.gcp_view_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, sz, i64, ci, vp, vp, vp]
     L.gcp_view_backward.argtypes = [vp, sz, vp, sz, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp]
     L.gcp_view_backward_scatter.argtypes = [vp, sz, vp, sz, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp, vp]
+    L.gcp_views_ctx_create.argtypes = [ci, ctypes.POINTER(vp)]
+    L.gcp_views_ctx_destroy.argtypes = [vp]
+    L.gcp_views_ctx_destroy.restype = None
+    L.gcp_views_step.argtypes = [vp, ctypes.POINTER(ViewDesc), ci, ci, ci, ctypes.POINTER(vp), sz, ctypes.POINTER(vp), sz,
+                                 i64, vp, vp, vp, vp, vp, vp, vp]
     for name in ("gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward", "gcp_view_backward",
-                 "gcp_view_backward_scatter",
+                 "gcp_view_backward_scatter", "gcp_views_ctx_create", "gcp_views_step",
                  "gcp_view_last_launch_count"):
         getattr(L, name).restype = ci
     for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",

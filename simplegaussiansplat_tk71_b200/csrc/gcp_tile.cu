@@ -35,6 +35,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
+#include <new>
 
 #include "gcp_abi.h"
 
@@ -755,8 +756,9 @@ k_view_combine_fwd(const int32_t *__restrict__ tcount, const int32_t *__restrict
 // tiles of several pieces: U after the last element of every piece, from the pieces behind it
 __global__ void __launch_bounds__(256)
 k_view_combine_bwd(const int32_t *__restrict__ tcount, const int32_t *__restrict__ pextra,
-                   const int32_t *__restrict__ mlist, const unsigned int *__restrict__ hdr, int piece,
+                   const int32_t *__restrict__ mlist, const unsigned int *__restrict__ hdr, int64_t cap, int piece,
                    const float *__restrict__ gimg, int ntx, int W, int H, float *__restrict__ pstate) {
+    if (overflowed(hdr, cap)) return;   // a view that did not fit its arena was not rendered: nothing to walk back
     const int lane = threadIdx.x & 31;
     const unsigned int nm = hdr[H_NMULTI];
     for (unsigned int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nm; i += gridDim.x * 8) {
@@ -894,8 +896,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 3)
 k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart,
                 const int32_t *__restrict__ pextra, const int32_t *__restrict__ ptile_x,
                 const int32_t *__restrict__ pgid, const int4 *__restrict__ rec, unsigned int *__restrict__ hdr,
-                int piece, const float *__restrict__ tck, const float *__restrict__ pstate,
+                int64_t cap, int piece, const float *__restrict__ tck, const float *__restrict__ pstate,
                 const float *__restrict__ gimg, int ntx, int ntiles, int W, int H, float *__restrict__ partial) {
+    if (overflowed(hdr, cap)) return;
     // dynamic shared memory, per warp: 32 staged slots | 2 x 32 raw records (the next batch's arrive here by
     // cp.async) | the exchange buffer
     extern __shared__ __align__(16) unsigned char bwd_smem[];
@@ -1033,9 +1036,9 @@ __device__ __forceinline__ void add_partial(float (&S)[7], const int4 &u, const 
 // that list does not enter any float sum.
 __global__ void __launch_bounds__(256)
 k_view_reduce(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
-              int64_t n, GradOut out, unsigned int *__restrict__ hdr, int32_t *__restrict__ big) {
+              int64_t n, GradOut out, unsigned int *__restrict__ hdr, int64_t cap, int32_t *__restrict__ big) {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= n) return;
+    if (g >= n || overflowed(hdr, cap)) return;
     const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
     if (e - b > RED_BIG) {
         big[atomicAdd(hdr + H_NBIG, 1u)] = static_cast<int32_t>(g);
@@ -1061,8 +1064,9 @@ k_view_reduce(const float *__restrict__ partial, const int32_t *__restrict__ tof
 // group sums are added in group order — a fixed order, bitwise reproducible
 __global__ void __launch_bounds__(256)
 k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
-                  GradOut out, const unsigned int *__restrict__ hdr, const int32_t *__restrict__ big) {
+                  GradOut out, const unsigned int *__restrict__ hdr, int64_t cap, const int32_t *__restrict__ big) {
     __shared__ float sums[32][8];
+    if (overflowed(hdr, cap)) return;
     const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
     const unsigned int nb = hdr[H_NBIG];
     for (unsigned int i = blockIdx.x; i < nb; i += gridDim.x) {
@@ -1316,39 +1320,78 @@ int gcp_view_forward(const int32_t *sp, const int32_t *ep, const float *mean, co
     return rc;
 }
 
+}  // extern "C"
+
+namespace {
+
+struct BackwardArgs {
+    void *plan, *pairs;
+    int64_t pair_cap, n;
+    const float *grad_image;
+    int W, H;
+    GradOut out;
+};
+int check_backward(const BackwardArgs &a, size_t plan_bytes, size_t pair_bytes) {
+    if (a.n < 0 || bad_image(a.W, a.H) || !a.plan || !a.pairs || !a.grad_image || a.pair_cap < 0) return GCP_ERR_INVALID_ARG;
+    if (a.n == 0) return GCP_OK;
+    if (!a.out.g_mean || !a.out.g_lam || !a.out.g_opac || !a.out.g_l) return GCP_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(a.out.g_mean) & 7) || (reinterpret_cast<uintptr_t>(a.out.g_lam) & 15)) return GCP_ERR_INVALID_ARG;
+    const int ntiles = tiles_x(a.W) * tiles_y(a.H);
+    if (plan_bytes < plan_layout(a.n, ntiles).total || pair_bytes < pair_layout(a.pair_cap, ntiles).total) return GCP_ERR_WORKSPACE;
+    return GCP_OK;
+}
+// the reverse walk: carries of multi-piece tiles, then the pieces -> one partial per pair
+int launch_backward_walk(const BackwardArgs &a, cudaStream_t st) {
+    const int ntx = tiles_x(a.W), ntiles = ntx * tiles_y(a.H);
+    const PlanLayout A = plan_layout(a.n, ntiles);
+    const PairLayout B = pair_layout(a.pair_cap, ntiles);
+    unsigned int *hdr = at<unsigned int>(a.plan, A.hdr);
+    cudaError_t e = cudaMemsetAsync(hdr + H_TICKET_BWD, 0, 2 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int32_t *tcount = at<int32_t>(a.plan, A.tcount), *tstart = at<int32_t>(a.plan, A.tstart);
+    const int32_t *pextra = at<int32_t>(a.plan, A.pextra), *ptile_x = at<int32_t>(a.pairs, B.ptile_x);
+    float *pstate = at<float>(a.pairs, B.pstate);
+    k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(a.plan, A.mlist), hdr, a.pair_cap, g_piece,
+                                           a.grad_image, ntx, a.W, a.H, pstate);
+    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32, BWD_SMEM);
+    k_view_backward<<<grid, BWD_WARPS * 32, BWD_SMEM, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(a.pairs, B.pgid),
+                                                            at<int4>(a.plan, A.rec), hdr, a.pair_cap, g_piece,
+                                                            at<float>(a.pairs, B.tck), pstate, a.grad_image, ntx,
+                                                            ntiles, a.W, a.H, at<float>(a.pairs, B.partial));
+    t_view_launches += 2;
+    return static_cast<int>(cudaGetLastError());
+}
+// the partials of every Gaussian's pairs summed and turned into the four gradients
+int launch_backward_reduce(const BackwardArgs &a, cudaStream_t st) {
+    const int ntiles = tiles_x(a.W) * tiles_y(a.H);
+    const PlanLayout A = plan_layout(a.n, ntiles);
+    const PairLayout B = pair_layout(a.pair_cap, ntiles);
+    unsigned int *hdr = at<unsigned int>(a.plan, A.hdr);
+    const int4 *rec = at<int4>(a.plan, A.rec);
+    const int32_t *toff = at<int32_t>(a.plan, A.toff);
+    const float *partial = at<float>(a.pairs, B.partial);
+    int32_t *big = at<int32_t>(a.plan, A.big);
+    k_view_reduce<<<blocks_for(a.n, 256), 256, 0, st>>>(partial, toff, rec, a.n, a.out, hdr, a.pair_cap, big);
+    k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, a.out, hdr, a.pair_cap, big);
+    t_view_launches += 2;
+    return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
 int gcp_view_backward_scatter(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
                               const float *grad_image, int64_t n, int W, int H, const int32_t *index, float *g_mean,
                               float *g_lam, float *g_opac, float *g_l, gcp_stream_t stream) {
     t_view_launches = 0;
-    if (n < 0 || bad_image(W, H) || !plan || !pairs || !grad_image || pair_cap < 0) return GCP_ERR_INVALID_ARG;
-    if (n == 0) return GCP_OK;
-    if (!g_mean || !g_lam || !g_opac || !g_l) return GCP_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(g_mean) & 7) || (reinterpret_cast<uintptr_t>(g_lam) & 15)) return GCP_ERR_INVALID_ARG;
-    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    const PlanLayout A = plan_layout(n, ntiles);
-    const PairLayout B = pair_layout(pair_cap, ntiles);
-    if (plan_bytes < A.total || pair_bytes < B.total) return GCP_ERR_WORKSPACE;
+    const BackwardArgs a = {plan, pairs, pair_cap, n, grad_image, W, H, {g_mean, g_lam, g_opac, g_l, index}};
+    int rc = check_backward(a, plan_bytes, pair_bytes);
+    if (rc != GCP_OK || n == 0) return rc;
     auto st = reinterpret_cast<cudaStream_t>(stream);
-    unsigned int *hdr = at<unsigned int>(plan, A.hdr);
-    cudaError_t e = cudaMemsetAsync(hdr + H_TICKET_BWD, 0, 2 * sizeof(unsigned int), st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    const int32_t *tcount = at<int32_t>(plan, A.tcount), *tstart = at<int32_t>(plan, A.tstart);
-    const int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
-    const int4 *rec = at<int4>(plan, A.rec);
-    const int32_t *toff = at<int32_t>(plan, A.toff);
-    float *pstate = at<float>(pairs, B.pstate), *partial = at<float>(pairs, B.partial);
-    k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, g_piece, grad_image, ntx, W,
-                                           H, pstate);
-    const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32, BWD_SMEM);
-    k_view_backward<<<grid, BWD_WARPS * 32, BWD_SMEM, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(pairs, B.pgid), rec,
-                                                     hdr, g_piece, at<float>(pairs, B.tck), pstate, grad_image, ntx,
-                                                     ntiles, W, H, partial);
-    int32_t *big = at<int32_t>(plan, A.big);
-    const GradOut out = {g_mean, g_lam, g_opac, g_l, index};
-    k_view_reduce<<<blocks_for(n, 256), 256, 0, st>>>(partial, toff, rec, n, out, hdr, big);
-    k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, out, hdr, big);
-    t_view_launches += 4;
-    return static_cast<int>(cudaGetLastError());
+    rc = launch_backward_walk(a, st);
+    if (rc != GCP_OK) return rc;
+    return launch_backward_reduce(a, st);
 }
 
 int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_bytes, int64_t pair_cap,
@@ -1356,6 +1399,149 @@ int gcp_view_backward(void *plan, size_t plan_bytes, void *pairs, size_t pair_by
                       float *g_l, gcp_stream_t stream) {
     return gcp_view_backward_scatter(plan, plan_bytes, pairs, pair_bytes, pair_cap, grad_image, n, W, H, nullptr, g_mean,
                                      g_lam, g_opac, g_l, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A batch of views in one call (the per-view loop of gs_model.py:402-449 around the compositor, forward AND
+// backward, with the views' gradients summed into the parameters' gradient arrays as autograd does for the
+// reference, gs_control.py:180-185).  The host enqueues everything without waiting for the device: every view is
+// rendered on the pair capacity the caller provides (gcp_view_forward), its pair count lands in totals_host[v], a
+// view that does not fit is skipped entirely (forward and backward) and the caller, who sees the count, repeats
+// the step on larger arenas.  Views alternate between `lanes` streams with their own arenas, so that the binning
+// kernels of one view (bound by memory latency) share the device with the walk kernels of another (bound by
+// instruction issue); the scatter-adds into the shared gradient arrays are chained by events in view order, which
+// keeps every float sum in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+struct gcp_views_ctx {
+    int lanes;
+    cudaStream_t side[GCP_VIEWS_MAX_LANES];      // lane 0 is the caller's stream
+    cudaEvent_t ev_in, ev_reduced[GCP_VIEWS_MAX_LANES], ev_done[GCP_VIEWS_MAX_LANES];
+};
+
+}  // extern "C"
+
+namespace {
+// grad_image = d/d image of mean((image - target)^2); the loss itself is added to *loss (float atomics: the
+// reported number only, no gradient depends on it)
+__global__ void __launch_bounds__(256)
+k_view_mse_grad(const float *__restrict__ image, const float *__restrict__ target, int64_t count, float scale,
+                const unsigned int *__restrict__ hdr, int64_t cap, float *__restrict__ gimg, float *loss) {
+    if (overflowed(hdr, cap)) return;
+    float acc = 0.0f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float d = image[i] - __ldg(target + i);
+        gimg[i] = scale * d;
+        acc = fmaf(d, d, acc);
+    }
+    if (loss != nullptr) {
+        __shared__ float s_acc[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.0f;
+            for (int w = 0; w < 8; ++w) t += s_acc[w];
+            atomicAdd(loss, t * (0.5f * scale));
+        }
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int gcp_views_ctx_create(int lanes, gcp_views_ctx **out) {
+    if (!out || lanes < 1 || lanes > GCP_VIEWS_MAX_LANES) return GCP_ERR_INVALID_ARG;
+    gcp_views_ctx *c = new (std::nothrow) gcp_views_ctx();
+    if (!c) return GCP_ERR_INVALID_ARG;
+    c->lanes = lanes;
+    cudaError_t e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    for (int l = 0; l < lanes && e == cudaSuccess; ++l) {
+        c->side[l] = nullptr;
+        if (l > 0) e = cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_reduced[l], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[l], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { delete c; return static_cast<int>(e); }
+    *out = c;
+    return GCP_OK;
+}
+
+void gcp_views_ctx_destroy(gcp_views_ctx *c) {
+    if (!c) return;
+    cudaEventDestroy(c->ev_in);
+    for (int l = 0; l < c->lanes; ++l) {
+        if (l > 0) cudaStreamDestroy(c->side[l]);
+        cudaEventDestroy(c->ev_reduced[l]);
+        cudaEventDestroy(c->ev_done[l]);
+    }
+    delete c;
+}
+
+int gcp_views_step(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, int W, int H, void *const *plan,
+                   size_t plan_bytes, void *const *pairs, size_t pair_bytes, int64_t pair_cap, float *g_mean,
+                   float *g_lam, float *g_opac, float *g_l, float *loss, int64_t *totals_host, gcp_stream_t stream) {
+    if (!ctx || n_views < 0 || (n_views > 0 && !views) || bad_image(W, H) || !plan || !pairs || !totals_host)
+        return GCP_ERR_INVALID_ARG;
+    auto main_st = reinterpret_cast<cudaStream_t>(stream);
+    const int lanes = ctx->lanes;
+    int launches = 0;
+    cudaError_t e = cudaSuccess;
+    if (lanes > 1) {
+        e = cudaEventRecord(ctx->ev_in, main_st);
+        for (int l = 1; l < lanes && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(ctx->side[l], ctx->ev_in, 0);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    const int64_t count = static_cast<int64_t>(W + 1) * (H + 1) * 3;
+    const int ntiles = tiles_x(W) * tiles_y(H);
+    for (int v = 0; v < n_views; ++v) {
+        const gcp_view_desc &d = views[v];
+        const int lane = v % lanes;
+        cudaStream_t st = lane == 0 ? main_st : ctx->side[lane];
+        if (!d.image || !d.grad_image) return GCP_ERR_INVALID_ARG;
+        int rc = gcp_view_forward(d.sp, d.ep, d.mean, d.lam, d.opac, d.l_d, d.n, W, H, plan[lane], plan_bytes, pairs[lane],
+                                  pair_bytes, pair_cap, 1, d.image, totals_host + v, st);
+        if (rc != GCP_OK) return rc;
+        launches += t_view_launches;
+        if (d.n > 0) {
+            const unsigned int *hdr = at<unsigned int>(plan[lane], plan_layout(d.n, ntiles).hdr);
+            if (d.target != nullptr) {
+                k_view_mse_grad<<<148 * 8, 256, 0, st>>>(d.image, d.target, count, 2.0f / static_cast<float>(count), hdr,
+                                                         pair_cap, d.grad_image, loss);
+                ++launches;
+            }
+            const BackwardArgs a = {plan[lane], pairs[lane], pair_cap, d.n, d.grad_image, W, H,
+                                    {g_mean, g_lam, g_opac, g_l, d.index}};
+            rc = check_backward(a, plan_bytes, pair_bytes);
+            if (rc != GCP_OK) return rc;
+            t_view_launches = 0;
+            rc = launch_backward_walk(a, st);
+            if (rc != GCP_OK) return rc;
+            // the sums into the shared gradient arrays follow each other in view order
+            if (lanes > 1 && v > 0) {
+                e = cudaStreamWaitEvent(st, ctx->ev_reduced[(v - 1) % lanes], 0);
+                if (e != cudaSuccess) return static_cast<int>(e);
+            }
+            rc = launch_backward_reduce(a, st);
+            if (rc != GCP_OK) return rc;
+            launches += t_view_launches;
+        } else if (lanes > 1 && v > 0) {
+            e = cudaStreamWaitEvent(st, ctx->ev_reduced[(v - 1) % lanes], 0);   // keeps the chain of events unbroken
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        if (lanes > 1) {
+            e = cudaEventRecord(ctx->ev_reduced[lane], st);
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+    }
+    for (int l = 1; l < lanes; ++l) {
+        e = cudaEventRecord(ctx->ev_done[l], ctx->side[l]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(main_st, ctx->ev_done[l], 0);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    t_view_launches = launches;
+    return GCP_OK;
 }
 
 }  // extern "C"

@@ -104,3 +104,137 @@ def render_views(mean_pixel, box_half, z, lam, opacity, l_d, width: int, height:
     if not out:
         return torch.zeros((0, 3, height, width), device=mean_pixel.device)
     return torch.stack(out, dim=0)[:, 1:, 1:, :].reshape(-1, 3, height, width)
+
+
+# --------------------------------------------------------------------------------------------
+# The same loop as ONE native call per training step (include/gcp_abi.h: gcp_views_step): render, loss gradient
+# and backward of every view of this rank, the views' gradients summed into the parameters' gradient arrays.
+# The Python loop above costs ~0.85 ms of host time per view (autograd Function, allocations, ctypes calls) against
+# ~0.65 ms of device time; here the host enqueues a whole step in a few milliseconds and never waits.
+# --------------------------------------------------------------------------------------------
+class NativeViewBatch:
+    """The views one rank renders in a training step, prepared once.
+
+    views: sequence of objects with .startpoint .endpoint .mean .lam .opacity .l_d (a workloads.SplatView, or the
+    per-view slices gs_model.py:405-425 produces) and optionally .index (i32[n], the parameter row of each of the
+    view's Gaussians: the reference's boolean-mask selection as row numbers).  targets: per-view images
+    f32[H+1,W+1,3] for the built-in mean-squared-error loss, or grad_images: per-view dL/d image.
+    step(...) enqueues the whole batch on the current stream; finish() (after the caller synchronised) tells
+    whether every view fitted the pair arenas — if not they have been enlarged and the step must be repeated."""
+
+    def __init__(self, views, width: int, height: int, targets=None, grad_images=None, lanes: int = 2,
+                 keep_images: bool = False):
+        import ctypes
+
+        from . import _lib
+
+        if (targets is None) == (grad_images is None):
+            raise ValueError("give either targets (built-in MSE loss) or grad_images")
+        self.L = L = _lib.lib()
+        self.W, self.H, self.lanes = int(width), int(height), int(lanes)
+        self.V = len(views)
+        dev = views[0].startpoint.device if self.V else torch.device("cuda")
+        if dev.type != "cuda":
+            raise RuntimeError("NativeViewBatch needs CUDA tensors (there is no CPU path)")
+        self.dev = dev
+        f32 = lambda t, shape: t.detach().to(torch.float32).reshape(shape).contiguous()  # noqa: E731
+        self._keep = []          # every tensor a descriptor points at
+        self.desc = (_lib.ViewDesc * max(self.V, 1))()
+        shape = (self.H + 1, self.W + 1, 3)
+        n_img = self.V if keep_images else min(self.lanes, max(self.V, 1))
+        self.images = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(n_img)]
+        self.gscratch = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(self.lanes)] \
+            if targets is not None else []
+        self.n_max = 1
+        for v, sc in enumerate(views):
+            n = int(sc.startpoint.shape[0])
+            self.n_max = max(self.n_max, n)
+            sp = sc.startpoint.to(torch.int32).contiguous()
+            ep = sc.endpoint.to(torch.int32).contiguous()
+            t = [sp, ep, f32(sc.mean, (n, 2)), f32(sc.lam, (n, 4)), f32(sc.opacity, (n,)), f32(sc.l_d, (n, 3))]
+            idx = getattr(sc, "index", None)
+            if idx is not None:
+                idx = idx.to(device=dev, dtype=torch.int32).contiguous()
+                if idx.numel() != n:
+                    raise ValueError("index must name one parameter row per Gaussian of the view")
+            d = self.desc[v]
+            d.sp, d.ep, d.mean, d.lam, d.opac, d.l_d = (x.data_ptr() for x in t)
+            d.index = idx.data_ptr() if idx is not None else None
+            if targets is not None:
+                tg = f32(targets[v], shape)
+                d.target, d.grad_image = tg.data_ptr(), self.gscratch[v % self.lanes].data_ptr()
+            else:
+                tg = f32(grad_images[v], shape)
+                d.target, d.grad_image = None, tg.data_ptr()
+            d.image = self.images[v if keep_images else v % self.lanes].data_ptr()
+            d.n = n
+            self._keep.append((t, idx, tg))
+        ctx = ctypes.c_void_p()
+        _lib.check(L.gcp_views_ctx_create(self.lanes, ctypes.byref(ctx)), "gcp_views_ctx_create")
+        self.ctx = ctx
+        self.totals = torch.zeros(max(self.V, 1), dtype=torch.int64).pin_memory()
+        self.totals_np = self.totals.numpy()
+        self.plan_bytes = int(L.gcp_view_plan_bytes(self.n_max, self.W, self.H))
+        self.plans = [torch.empty(self.plan_bytes, dtype=torch.uint8, device=dev) for _ in range(self.lanes)]
+        self.cap = 0
+        self.pairs = []
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                torch.cuda.synchronize(self.dev)
+                self.L.gcp_views_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def _arenas(self, cap: int):
+        import ctypes
+
+        self.cap = int(cap)
+        self.pair_bytes = int(self.L.gcp_view_pair_bytes(self.cap, self.W, self.H))
+        self.pairs = [torch.empty(self.pair_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.lanes)]
+        vp = ctypes.c_void_p
+        self._plan_ptrs = (vp * self.lanes)(*[p.data_ptr() for p in self.plans])
+        self._pair_ptrs = (vp * self.lanes)(*[p.data_ptr() for p in self.pairs])
+
+    def size(self):
+        """One pass of the plan kernels over all views (pair counts only) and ONE host sync: sizes the pair arenas
+        for the largest view plus 10 %.  step() calls it when there are no arenas yet."""
+        from . import _lib
+
+        stream = torch.cuda.current_stream(self.dev)
+        for v in range(self.V):
+            d = self.desc[v]
+            _lib.check(self.L.gcp_view_plan(d.sp, d.ep, d.n, self.W, self.H, self.plans[0].data_ptr(), self.plan_bytes,
+                                            self.totals.data_ptr() + 8 * v, stream.cuda_stream), "gcp_view_plan")
+        stream.synchronize()
+        most = int(self.totals_np[: self.V].max()) if self.V else 0
+        self._arenas(most + most // 10 + 4096)
+
+    def step(self, g_mean, g_lam, g_opac, g_l, loss=None):
+        """Enqueue render + loss gradient + backward of all views on the current stream; the views' gradients are
+        ADDED into g_mean f32[*,2], g_lam f32[*,4], g_opac f32[*], g_l f32[*,3] (rows = desc.index).  Returns at
+        once; call finish() after synchronising."""
+        from . import _lib
+
+        if not self.pairs:
+            self.size()
+        with torch.cuda.device(self.dev):
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(self.L.gcp_views_step(self.ctx, self.desc, self.V, self.W, self.H, self._plan_ptrs, self.plan_bytes,
+                                             self._pair_ptrs, self.pair_bytes, self.cap, g_mean.data_ptr(),
+                                             g_lam.data_ptr(), g_opac.data_ptr(), g_l.data_ptr(),
+                                             loss.data_ptr() if loss is not None else None, self.totals.data_ptr(),
+                                             stream), "gcp_views_step")
+        self.launches = int(self.L.gcp_view_last_launch_count())
+
+    def finish(self) -> bool:
+        """After the step's stream was synchronised: True when every view fitted its arena.  False: the arenas have
+        been enlarged; zero the gradients and run the step again (views that did not fit were skipped)."""
+        most = int(self.totals_np[: self.V].max()) if self.V else 0
+        if most <= self.cap:
+            return True
+        self._arenas(most + most // 10 + 4096)
+        return False

@@ -185,6 +185,8 @@ class SplatView:
     l_d: torch.Tensor          # f32[n,3]
     width: int
     height: int
+    index: torch.Tensor = None  # i32[n] row of every visible Gaussian in the scene's parameter arrays (the
+    #                             reference's boolean-mask selection, gs_model.py:405-413, as row numbers), or None
 
     @property
     def n(self) -> int:
@@ -236,6 +238,48 @@ def splat_view(width: int = 1920, height: int = 1080, n: int = 1_000_000, seed: 
     return SplatView(f"splat {width}x{height} n={m} seed{seed}", t(boxsize, torch.int64), t(sp, torch.int32),
                      t(ep, torch.int32), t(mean, torch.int32), t(lam, torch.float32), t(opac, torch.float32),
                      t(l_d, torch.float32), width, height)
+
+
+def splat_view_device(width: int = 1920, height: int = 1080, n: int = 1_000_000, seed: int = 1080, device="cuda",
+                      clusters: int = 256) -> SplatView:
+    """The same view distribution as splat_view (SURVEY.md §8d, C3 splat route), drawn with torch's generator ON
+    the device: a 64-view training batch (C5: seed = 1080 + view id) is ready in milliseconds instead of minutes of
+    host numpy.  Also returns `index`, the parameter row of every visible Gaussian (rows of the n-Gaussian scene)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    U = lambda *shape: torch.rand(*shape, generator=g, device=dev)      # noqa: E731
+    N = lambda *shape: torch.randn(*shape, generator=g, device=dev)     # noqa: E731
+    n_cl = int(0.7 * n)
+    cc = torch.stack((U(clusters) * width, U(clusters) * height), 1)
+    which = torch.randint(0, clusters, (n_cl,), generator=g, device=dev)
+    c1 = cc[which] + N(n_cl, 2) * (0.05 * min(width, height))
+    c2 = torch.stack(((U(n - n_cl) * 1.1 - 0.05) * width, (U(n - n_cl) * 1.1 - 0.05) * height), 1)
+    ctr = torch.cat((c1, c2), 0)[torch.randperm(n, generator=g, device=dev)]   # depth order independent of position
+    hw_max = 10 * 0.04 * math.sqrt(width * height)                             # gs_model.py:364-365
+    hw = torch.exp(N(n, 2) * 0.9 + math.log(2.0)).floor().clamp(1, hw_max)
+    mean = ctr.floor().to(torch.int64)
+    hwi = hw.to(torch.int64)
+    vis = (mean[:, 0] - hwi[:, 0] < width) & (mean[:, 0] + hwi[:, 0] > 0) & \
+          (mean[:, 1] - hwi[:, 1] < height) & (mean[:, 1] + hwi[:, 1] > 0)     # gs_model.py:406
+    index = torch.nonzero(vis).reshape(-1).to(torch.int32)
+    mean, hwi, hw = mean[vis], hwi[vis], hw[vis]
+    sp = torch.stack(((mean[:, 0] - hwi[:, 0]).clamp(0, width), (mean[:, 1] - hwi[:, 1]).clamp(0, height)), 1)
+    ep = torch.stack(((mean[:, 0] + hwi[:, 0]).clamp(0, width), (mean[:, 1] + hwi[:, 1]).clamp(0, height)), 1)
+    boxsize = torch.prod(ep - sp + 1, dim=1)
+    m = mean.shape[0]
+    sx = (hw[:, 0] / 3.0).clamp(min=0.5)                                       # the box is the 3-sigma extent
+    sy = (hw[:, 1] / 3.0).clamp(min=0.5)
+    rho = U(m) * 1.2 - 0.6
+    det = 1 - rho * rho
+    lam = torch.empty((m, 2, 2), dtype=torch.float32, device=dev)
+    lam[:, 0, 0] = 1.0 / (sx * sx * det)
+    lam[:, 1, 1] = 1.0 / (sy * sy * det)
+    lam[:, 0, 1] = lam[:, 1, 0] = -rho / (sx * sy * det)
+    opac = torch.sigmoid(N(m, 1) * OPACITY_LOGIT_STD + OPACITY_LOGIT_MEAN)
+    l_d = U(m, 3) * 0.9 + 0.05
+    return SplatView(f"splat {width}x{height} n={m} seed{seed} (device rng)", boxsize, sp.to(torch.int32),
+                     ep.to(torch.int32), mean.to(torch.int32), lam, opac, l_d, width, height, index)
 
 
 # --------------------------------------------------------------------------------------------
