@@ -537,6 +537,18 @@ def splat_legs(args, device, rank, world):
     compositor.ROUTE = default_route
     out = {"workload": sc.name, "elements": sc.elements, "gaussians": sc.n, "route": default_route,
            **routes[default_route], "unit": "ms per view (render + backward), median of 9", "routes": routes}
+    # the same view through the batch entry point (gcp_views_step, one view): no host wait for the pair count
+    nb = vw.NativeViewBatch([sc], 1920, 1080, grad_images=[gI], lanes=1)
+    gsec = _sections(bucket, n_param)
+    nb.step(*gsec)
+    torch.cuda.synchronize()
+    assert nb.finish()
+    out["native_call_ms"] = _median_ms(lambda: nb.step(*gsec), reps, warm=2)
+    out["native_call_launches"] = nb.launches
+    del nb
+    # end to end from HOST tables to a HOST image and HOST gradients (pinned memory both ways, every copy inside
+    # the timed region): what a caller pays who keeps the Gaussians on the host
+    out["e2e_host_tables"] = e2e_splat_leg(sc, gI, device)
     # (ii) multi-view training step (BASELINE.json configs[4]): this rank's share of `--views` DISTINCT views (seed
     #      1080 + view id, drawn on the device), one native call per step (views.NativeViewBatch -> gcp_views_step:
     #      render, MSE-loss gradient, backward, scatter-add into the bucket), and the all-reduce of the bucket hidden
@@ -556,6 +568,34 @@ def splat_legs(args, device, rank, world):
         except Exception as ex:  # noqa: BLE001
             out["c2_bundled"] = {"error": str(ex)}
     return out
+
+
+def e2e_splat_leg(sc, gI, device):
+    import torch
+
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    host_in = [t.cpu().pin_memory() for t in (sc.boxsize, sc.startpoint, sc.endpoint, sc.mean.float(), sc.lam, sc.opacity,
+                                              sc.l_d, gI)]
+    n = sc.n
+    host_out = [torch.empty(s_, dtype=torch.float32).pin_memory() for s_ in ((sc.height + 1, sc.width + 1, 3), (n, 2),
+                                                                             (n, 2, 2), (n, 1), (n, 3))]
+    W, H = torch.tensor(sc.width), torch.tensor(sc.height)
+
+    def once():
+        b, sp, ep, m, lam, o, l, g = (t.to(device, non_blocking=True) for t in host_in)
+        m, lam, o, l = (t.requires_grad_(True) for t in (m, lam, o, l))
+        img = F.apply(b, torch.tensor([n]), sp, ep, m, lam, o, l, W, H)
+        img.backward(g)
+        for dst, src in zip(host_out, (img.detach(), m.grad, lam.grad, o.grad, l.grad)):
+            dst.copy_(src, non_blocking=True)
+
+    ms = _median_ms(once, 7, warm=2)
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    return {"ms": ms, "h2d_bytes": h2d, "d2h_bytes": d2h,
+            "what": "custom_autograd_grouped_cumprod.apply + backward, per-Gaussian tables and dL/dimage from pinned host "
+                    "memory, image and the four gradients back to pinned host memory"}
 
 
 def _sections(bucket, n_param):
