@@ -793,7 +793,7 @@ constexpr int BWD_WARPS = 8;
 // exchange buffer of a warp: for each of the SUB pairs of a sub-batch, c[32] and dv[32] of its pixels.  The pair
 // stride of 68 words keeps the moment phase's LDS.128 (lanes = 8 pairs x 4 tile rows) free of bank conflicts.
 constexpr int XCH_STRIDE = 68;
-constexpr int BWD_SMEM_PER_WARP = static_cast<int>(sizeof(BSlot)) + 2 * 32 * 64 + SUB * XCH_STRIDE * 4;
+constexpr int BWD_SMEM_PER_WARP = static_cast<int>(sizeof(BSlot)) + 32 * 64 + SUB * XCH_STRIDE * 4;
 constexpr int BWD_SMEM = BWD_WARPS * BWD_SMEM_PER_WARP;
 
 // partial[q] = {sum c, sum d, sum c d0, sum c d1, sum c d0 d0, sum c d0 d1, sum c d1 d1, -} over the pixels of
@@ -899,14 +899,14 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
                 int64_t cap, int piece, const float *__restrict__ tck, const float *__restrict__ pstate,
                 const float *__restrict__ gimg, int ntx, int ntiles, int W, int H, float *__restrict__ partial) {
     if (overflowed(hdr, cap)) return;
-    // dynamic shared memory, per warp: 32 staged slots | 2 x 32 raw records (the next batch's arrive here by
-    // cp.async) | the exchange buffer
+    // dynamic shared memory, per warp: 32 staged slots | 32 raw records (the next batch's arrive here by cp.async;
+    // a lane reads back and overwrites only its own record, so one buffer is enough) | the exchange buffer
     extern __shared__ __align__(16) unsigned char bwd_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char *wbase = bwd_smem + static_cast<size_t>(wib) * BWD_SMEM_PER_WARP;
     BSlot &sl = *reinterpret_cast<BSlot *>(wbase);
-    int4 *raw = reinterpret_cast<int4 *>(wbase + sizeof(BSlot));          // [2 buffers][4 quarters][32 lanes]
-    float *xch = reinterpret_cast<float *>(wbase + sizeof(BSlot) + 2 * 32 * 64);
+    int4 *raw = reinterpret_cast<int4 *>(wbase + sizeof(BSlot));          // [4 quarters][32 lanes]
+    float *xch = reinterpret_cast<float *>(wbase + sizeof(BSlot) + 32 * 64);
     const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
     while (next_piece(hdr + H_TICKET_BWD, tcount, tstart, pextra, ptile_x, nx, ntiles, piece, lane, w)) {
@@ -933,7 +933,7 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
         // batches of 32 pairs, aligned to the piece start, from the last one down; ids two batches ahead, records
         // one batch ahead — straight into shared memory, so that no register holds them during the walk
         const int last = lo + ((hi - lo - 1) & ~31);
-        int buf = 0, g1 = 0;
+        int g1 = 0;
         if (last + lane < hi) copy_rec_async(raw + lane, rec, __ldg(pgid + last + lane));
         copy_commit();
         if (last > lo) g1 = __ldg(pgid + last - 32 + lane);
@@ -946,7 +946,7 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
             {
                 RecRegs r = {};
                 if (lane < m) {
-                    const int4 *rr = raw + buf * 128 + lane;
+                    const int4 *rr = raw + lane;
                     r.a = rr[0]; r.b = rr[32]; r.c = rr[64]; r.d = rr[96];
                 }
                 const uint32_t mask = coverage_mask(r, lane < m, x0, y0);
@@ -956,8 +956,7 @@ k_view_backward(const int32_t *__restrict__ tcount, const int32_t *__restrict__ 
                 sl.r0[lane] = make_float4(i2f(r.b.z), i2f(r.b.w), i2f(r.c.x), i2f(r.c.y));
                 sl.r1[lane] = make_float4(i2f(r.a.x), i2f(r.a.y), i2f(q), 0.0f);
             }
-            buf ^= 1;
-            if (bb - 32 >= lo) copy_rec_async(raw + buf * 128 + lane, rec, g1);
+            if (bb - 32 >= lo) copy_rec_async(raw + lane, rec, g1);
             copy_commit();
             g1 = (bb - 64 >= lo) ? __ldg(pgid + bb - 64 + lane) : 0;
             __syncwarp();
@@ -1353,6 +1352,7 @@ int launch_backward_walk(const BackwardArgs &a, cudaStream_t st) {
     float *pstate = at<float>(a.pairs, B.pstate);
     k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(a.plan, A.mlist), hdr, a.pair_cap, g_piece,
                                            a.grad_image, ntx, a.W, a.H, pstate);
+    // (3 resident CTAs per SM; 2 and 4 — 114 / 64 registers — were measured within 5 %: 284 / 280 vs 270 us)
     const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32, BWD_SMEM);
     k_view_backward<<<grid, BWD_WARPS * 32, BWD_SMEM, st>>>(tcount, tstart, pextra, ptile_x, at<int32_t>(a.pairs, B.pgid),
                                                             at<int4>(a.plan, A.rec), hdr, a.pair_cap, g_piece,

@@ -80,6 +80,9 @@ def chunk_ends(boxsize: torch.Tensor) -> torch.Tensor:
     return torch.cumsum(split_by_cumsum_parallel(boxsize / 1024, (1024 ** 3 * 6 / 12) / 1024), dim=0)
 
 
+_ONE_CHUNK = torch.zeros(1, dtype=torch.int64)   # placeholder for the ignored `batch` argument
+
+
 def render_views(mean_pixel, box_half, z, lam, opacity, l_d, width: int, height: int):
     """The per-view loop of gs_model.py:402-454 over V views whose Gaussians are already z-sorted:
     inputs [V,n,...]; returns images [V',3,H,W] (views without any visible Gaussian are skipped, :414-417) —
@@ -99,7 +102,9 @@ def render_views(mean_pixel, box_half, z, lam, opacity, l_d, width: int, height:
                 plan_view(nxt[3], nxt[1], nxt[2], width, height)
         if sp.shape[0] == 0:
             continue
-        out.append(F.apply(boxsize, chunk_ends(boxsize), sp, ep, mean_pixel[v][mask], lam[v][mask], opacity[v][mask],
+        # `batch` (the chunk ends, gs_model.py:428) is accepted and ignored by the native compositor — a view is one
+        # pass — so it is not computed here: chunk_ends() costs a cumsum, a torch.unique and a host sync per view
+        out.append(F.apply(boxsize, _ONE_CHUNK, sp, ep, mean_pixel[v][mask], lam[v][mask], opacity[v][mask],
                            l_d[v][mask], width, height))
     if not out:
         return torch.zeros((0, 3, height, width), device=mean_pixel.device)

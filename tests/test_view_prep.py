@@ -39,6 +39,65 @@ def test_visible_boxes_cull_and_inclusive_clamp():
     assert views.chunk_ends(bs).tolist() == [3]               # far below 2**29 elements: one chunk
 
 
+VIEW_FIX = os.path.join(ROOT, "tests", "golden", "view_loop_fixture.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_view_preparation_matches_the_reference_loop(tag):
+    """tests/golden/view_loop_fixture.npz holds what the reference's OWN per-view loop (gs_model.py:399-454,
+    executed from the reference file by tests/golden/make_view_loop_fixture.py) handed to the compositor for every
+    view: the integer side — visibility mask, corners, box sizes, chunk ends — must be reproduced bit for bit."""
+    from simplegaussiansplat_tk71_b200 import views
+
+    f = np.load(VIEW_FIX)
+    W, H = (int(v) for v in f[f"{tag}/WH"])
+    t = lambda k: torch.from_numpy(f[f"{tag}/in/{k}"])  # noqa: E731
+    mean_pixel, box, z = t("mean_pixel"), t("box"), t("mean_camera")[:, :, 2].clone()
+    empty = int(f[f"{tag}/empty_view"][0])
+    if empty >= 0:
+        z[empty] = -1.0
+    call = 0
+    kept = []
+    for v in range(mean_pixel.shape[0]):
+        mask, sp, ep, boxsize = views.visible_boxes(mean_pixel[v], box[v], z[v], W, H)
+        if sp.shape[0] == 0:
+            continue                                   # gs_model.py:414-417
+        kept.append(v)
+        g = lambda k: f[f"{tag}/call{call}/{k}"]  # noqa: E731
+        assert np.array_equal(sp.numpy(), g("sp")) and np.array_equal(ep.numpy(), g("ep"))
+        assert np.array_equal(boxsize.numpy(), g("boxsize"))
+        assert np.array_equal(views.chunk_ends(boxsize).numpy(), g("batch"))
+        assert np.array_equal(mean_pixel[v][mask].numpy(), g("mean"))
+        assert np.array_equal(t("lam")[v][mask].numpy(), g("lam"))
+        assert np.array_equal(t("opac")[v][mask].numpy(), g("opac"))
+        call += 1
+    assert call == int(f[f"{tag}/n_calls"][0])
+    assert kept == f[f"{tag}/kept_samples"].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_render_views_reproduces_the_reference_image_batch_gpu(tag):
+    """views.render_views (cull + clamp + chunker + native compositor + the reference's final reshape, :454) against
+    the image batch the reference's own loop and Function produced for the same inputs (fp32, CPU): within twice the
+    north star's tolerance (both are fp32 evaluations of the same sums; scale = the images themselves, all terms
+    are positive)."""
+    from simplegaussiansplat_tk71_b200 import views
+
+    f = np.load(VIEW_FIX)
+    W, H = (int(v) for v in f[f"{tag}/WH"])
+    t = lambda k: torch.from_numpy(f[f"{tag}/in/{k}"]).cuda()  # noqa: E731
+    z = t("mean_camera")[:, :, 2].clone()
+    empty = int(f[f"{tag}/empty_view"][0])
+    if empty >= 0:
+        z[empty] = -1.0
+    imgs = views.render_views(t("mean_pixel"), t("box"), z, t("lam"), t("opac"), t("l_d"), W, H)
+    want = f[f"{tag}/images"]
+    assert tuple(imgs.shape) == want.shape
+    err = np.abs(imgs.cpu().numpy().astype(np.float64) - want)
+    assert np.all(err <= 2 * (1e-6 + 1e-5 * np.abs(want))), float((err / (1e-6 + 1e-5 * np.abs(want))).max())
+
+
 @pytest.mark.gpu
 def test_render_views_shapes_and_skip_empty_gpu():
     from simplegaussiansplat_tk71_b200 import views
