@@ -613,7 +613,7 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
     from simplegaussiansplat_tk71_b200 import workloads as wl
 
     W, H = 1920, 1080
-    lanes = int(os.environ.get("BENCH_MV_LANES", "2"))
+    lanes = int(os.environ.get("BENCH_MV_LANES", "4"))
     views = [wl.splat_view_device(W, H, n_param, seed=1080 + v, device=device) for v in mine]
     elems = sum(v.elements for v in views)
     target = torch.rand(H + 1, W + 1, 3, device=device)

@@ -127,7 +127,7 @@ class NativeViewBatch:
     step(...) enqueues the whole batch on the current stream; finish() (after the caller synchronised) tells
     whether every view fitted the pair arenas — if not they have been enlarged and the step must be repeated."""
 
-    def __init__(self, views, width: int, height: int, targets=None, grad_images=None, lanes: int = 2,
+    def __init__(self, views, width: int, height: int, targets=None, grad_images=None, lanes: int = 4,
                  keep_images: bool = False):
         import ctypes
 

@@ -45,7 +45,7 @@ def _by_function(views, W, H, n_param, gIs=None, targets=None):
     return g, loss, imgs
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 3])
+@pytest.mark.parametrize("lanes", [1, 2, 3, 4])
 def test_native_batch_equals_the_view_by_view_function_gpu(lanes):
     from simplegaussiansplat_tk71_b200.views import NativeViewBatch
 
