@@ -57,7 +57,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 
 // ---- arena headers (u32 words; zeroed by gcp_view_plan) ----
 constexpr int H_TICKET_S1 = 0, H_TICKET_S2 = 1, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4, H_NLONG = 5;
-constexpr int H_TICKET_BWD = 6, H_NBIG = 7;     // adjacent: reset together by every backward
+constexpr int H_TICKET_BWD = 6, H_NBIG = 7, H_TICKET_RED = 8;   // adjacent u32 words: reset together by every backward
 constexpr int H_P64 = 8, H_T64 = 9;             // u64 indices (bytes 64 / 72): pair count; the tile scan's total (= it)
 constexpr int HDR_WORDS = 64;
 
@@ -757,13 +757,20 @@ k_view_combine_fwd(const int32_t *__restrict__ tcount, const int32_t *__restrict
         const int t = mlist[i];
         const int np = (__ldg(tcount + t) + piece - 1) / piece, s0 = __ldg(pextra + t);
         float carry = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        float *ps = pstate + static_cast<int64_t>(s0) * PIECE_STATE + lane;
+        float a0 = ps[0], a1 = ps[32], a2 = ps[64], a3 = ps[96];   // the next piece's state is loaded a piece ahead
         for (int k = 0; k < np; ++k) {
-            float *ps = pstate + static_cast<int64_t>(s0 + k) * PIECE_STATE + lane;
+            const float t0 = a0, t1 = a1, t2 = a2, t3 = a3;
+            if (k + 1 < np) {
+                const float *pn = ps + PIECE_STATE;
+                a0 = pn[0]; a1 = pn[32]; a2 = pn[64]; a3 = pn[96];
+            }
             ps[128] = carry;
-            c0 = fmaf(carry, ps[32], c0);
-            c1 = fmaf(carry, ps[64], c1);
-            c2 = fmaf(carry, ps[96], c2);
-            carry *= ps[0];
+            c0 = fmaf(carry, t1, c0);
+            c1 = fmaf(carry, t2, c1);
+            c2 = fmaf(carry, t3, c2);
+            carry *= t0;
+            ps += PIECE_STATE;
         }
         const int ty = t / ntx, tx = t - ty * ntx;
         const int ix = (tx << TSX) + (lane & (TW - 1)), iy = (ty << TSY) + (lane >> TSX);
@@ -793,10 +800,17 @@ k_view_combine_bwd(const int32_t *__restrict__ tcount, const int32_t *__restrict
             pg0 = __ldg(p); pg1 = __ldg(p + 1); pg2 = __ldg(p + 2);
         }
         float U = 0.0f;
+        float *ps = pstate + static_cast<int64_t>(s0 + np - 1) * PIECE_STATE + lane;
+        float a0 = ps[0], a1 = ps[32], a2 = ps[64], a3 = ps[96];   // the next piece's state is loaded a piece ahead
         for (int k = np - 1; k >= 0; --k) {
-            float *ps = pstate + static_cast<int64_t>(s0 + k) * PIECE_STATE + lane;
+            const float t0 = a0, t1 = a1, t2 = a2, t3 = a3;
+            if (k > 0) {
+                const float *pn = ps - PIECE_STATE;
+                a0 = pn[0]; a1 = pn[32]; a2 = pn[64]; a3 = pn[96];
+            }
             ps[160] = U;
-            U = fmaf(ps[0], U, pg0 * ps[32] + pg1 * ps[64] + pg2 * ps[96]);
+            U = fmaf(t0, U, pg0 * t1 + pg1 * t2 + pg2 * t3);
+            ps -= PIECE_STATE;
         }
     }
 }
@@ -1080,40 +1094,76 @@ k_view_reduce(const float *__restrict__ partial, const int32_t *__restrict__ tof
     store_sums(S, g, rec, out);
 }
 
-// one block per big Gaussian: 32 groups of 8 lanes stride over its pairs (group j takes pairs j, j+32, ...), the 32
-// group sums are added in group order — a fixed order, bitwise reproducible
+// Big Gaussians.  Up to RED_HUGE pairs: one warp each (ticket) — lane l adds the partials of pairs l, l+32, ... (one
+// LDG.256 per pair, four in flight) and the 32 lane sums are added by a butterfly.  More pairs than that (the
+// bundled scene has boxes of 5 000 tiles): a whole block each, thread t takes pairs t, t+256, ..., the warps'
+// butterfly sums are added in warp order.  Fixed orders: bitwise reproducible.
+constexpr int RED_HUGE = 1024;
+
+template <int STRIDE>
+__device__ __forceinline__ void sum_partials_strided(const float *__restrict__ partial, int first, int e, float (&S)[7]) {
+    const int4 zero = make_int4(0, 0, 0, 0);
+    for (int q = first; q < e; q += 4 * STRIDE) {
+        int4 u[4], v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u[k] = zero; v[k] = zero;
+            if (q + STRIDE * k < e) ldg256(partial + static_cast<int64_t>(q + STRIDE * k) * 8, u[k], v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (q + STRIDE * k < e) add_partial(S, u[k], v[k]);
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) S[c] += __shfl_xor_sync(0xffffffffu, S[c], o);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
-                  GradOut out, const unsigned int *__restrict__ hdr, int64_t cap, const int32_t *__restrict__ big) {
-    __shared__ float sums[32][8];
+                  GradOut out, unsigned int *__restrict__ hdr, int64_t cap, const int32_t *__restrict__ big) {
+    __shared__ float s_w[8][8];
     if (overflowed(hdr, cap)) return;
-    const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int nb = hdr[H_NBIG];
+    // (1) the huge ones, a block each
     for (unsigned int i = blockIdx.x; i < nb; i += gridDim.x) {
         const int64_t g = __ldg(big + i);
         const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
-        float s = 0.0f;
-        int q = b + j;
-        for (; q + 96 < e; q += 128) {
-            const float *p = partial + static_cast<int64_t>(q) * 8 + c;
-            const float v0 = __ldcs(p), v1 = __ldcs(p + 32 * 8), v2 = __ldcs(p + 64 * 8), v3 = __ldcs(p + 96 * 8);
-            s += v0; s += v1; s += v2; s += v3;
+        if (e - b <= RED_HUGE) continue;   // block-uniform
+        float S[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        sum_partials_strided<256>(partial, b + threadIdx.x, e, S);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) s_w[warp][c] = S[c];
         }
-        for (; q < e; q += 32) s += __ldcs(partial + static_cast<int64_t>(q) * 8 + c);
-        sums[j][c] = s;
         __syncthreads();
         if (threadIdx.x == 0) {
-            float S[7];
 #pragma unroll
-            for (int cc = 0; cc < 7; ++cc) {
+            for (int c = 0; c < 7; ++c) {
                 float t = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) t += sums[k][cc];
-                S[cc] = t;
+                for (int w = 0; w < 8; ++w) t += s_w[w][c];
+                S[c] = t;
             }
             store_sums(S, g, rec, out);
         }
         __syncthreads();
+    }
+    // (2) the others, a warp each
+    while (true) {
+        unsigned i = 0;
+        if (lane == 0) i = atomicAdd(hdr + H_TICKET_RED, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nb) return;
+        const int64_t g = __ldg(big + i);
+        const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
+        if (e - b > RED_HUGE) continue;
+        float S[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        sum_partials_strided<32>(partial, b + lane, e, S);
+        if (lane == 0) store_sums(S, g, rec, out);
     }
 }
 
@@ -1333,7 +1383,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
         k_view_render<false><<<grid, TILE_WARPS * 32, 0, st>>>(tcount, tstart, pextra, ptile_x, pgid, rec, hdr,
                                                                pair_cap, g_piece, ntx, ntiles, W, H, image, tck, pstate);
     }
-    k_view_combine_fwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, pair_cap, g_piece, ntx, W,
+    k_view_combine_fwd<<<296, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, pair_cap, g_piece, ntx, W,
                                            H, pstate, image);
     t_view_launches += 5;
     return static_cast<int>(cudaGetLastError());
@@ -1378,12 +1428,12 @@ int launch_backward_walk(const BackwardArgs &a, cudaStream_t st) {
     const PlanLayout A = plan_layout(a.n, ntiles);
     const PairLayout B = pair_layout(a.pair_cap, ntiles);
     unsigned int *hdr = at<unsigned int>(a.plan, A.hdr);
-    cudaError_t e = cudaMemsetAsync(hdr + H_TICKET_BWD, 0, 2 * sizeof(unsigned int), st);
+    cudaError_t e = cudaMemsetAsync(hdr + H_TICKET_BWD, 0, 3 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return static_cast<int>(e);
     const int32_t *tcount = at<int32_t>(a.plan, A.tcount), *tstart = at<int32_t>(a.plan, A.tstart);
     const int32_t *pextra = at<int32_t>(a.plan, A.pextra), *ptile_x = at<int32_t>(a.pairs, B.ptile_x);
     float *pstate = at<float>(a.pairs, B.pstate);
-    k_view_combine_bwd<<<64, 256, 0, st>>>(tcount, pextra, at<int32_t>(a.plan, A.mlist), hdr, a.pair_cap, g_piece,
+    k_view_combine_bwd<<<296, 256, 0, st>>>(tcount, pextra, at<int32_t>(a.plan, A.mlist), hdr, a.pair_cap, g_piece,
                                            a.grad_image, ntx, a.W, a.H, pstate);
     // (3 resident CTAs per SM; 2 and 4 — 114 / 64 registers — were measured within 5 %: 284 / 280 vs 270 us)
     const unsigned grid = walk_grid(reinterpret_cast<const void *>(k_view_backward), BWD_WARPS * 32, BWD_SMEM);
