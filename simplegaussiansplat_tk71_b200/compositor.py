@@ -288,6 +288,15 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
                 plan.event.synchronize()
                 _free_plan.setdefault(v.key, []).append(plan.arena)
             plan = None
+        mean_, lam_, opac_, l_ = _f32(mean, (n, 2)), _f32(lam, (n, 4)), _f32(opacity, (n,)), _f32(l_d, (n, 3))
+        image = torch.empty((H + 1, W + 1, 3), dtype=torch.float32, device=dev)  # every pixel is written by its lane
+        if plan is None and SPECULATE and _free_pair.get(v.key):
+            # A pair arena of an earlier view is at hand: plan AND render are queued in one call on its capacity, the
+            # host then reads the pair count the plan kernel drops into pinned memory.  The device never idles between
+            # the plan and the render waiting for the host (that gap was 60-90 us of a 0.4 ms forward); a view that
+            # turns out larger than the arena was not rendered at all (every kernel checks) and is redone below.
+            if _forward_speculative(L, v, dev, startpoint, endpoint, mean_, lam_, opac_, l_, n, W, H, keep, image, cur):
+                return image, v
         if plan is not None:
             cur.wait_event(plan.event)
             sp, ep, v.plan, event = plan.sp, plan.ep, plan.arena, plan.event
@@ -295,8 +304,6 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
                 t_.record_stream(cur)
         else:
             sp, ep, v.plan, event = _plan_tiles(L, dev, startpoint, endpoint, n, W, H)
-        mean_, lam_, opac_, l_ = _f32(mean, (n, 2)), _f32(lam, (n, 4)), _f32(opacity, (n,)), _f32(l_d, (n, 3))
-        image = torch.empty((H + 1, W + 1, 3), dtype=torch.float32, device=dev)  # every pixel is written by its lane
         # the one host sync of a view (like the reference's .item() at uitility.py:348): the plan kernel wrote the
         # pair count straight into pinned memory
         event.synchronize()
@@ -308,6 +315,51 @@ def _render_forward_tiles(boxsize, startpoint, endpoint, mean, lam, opacity, l_d
                                      v.plan.buf.numel(), _p(v.pairs.buf), v.pairs.buf.numel(), v.pairs.cap,
                                      1 if keep else 0, _p(image), stream), "gcp_view_render")
     return image, v
+
+
+# True: a view whose plan was not queued ahead (plan_view) is rendered on the capacity of a pooled pair arena
+# without waiting for its pair count first (see _render_forward_tiles).  Exact either way.
+SPECULATE = True
+
+
+def _forward_speculative(L, v, dev, startpoint, endpoint, mean_, lam_, opac_, l_, n, W, H, keep, image, cur) -> bool:
+    import time
+
+    sp = startpoint.to(torch.int32).contiguous()
+    ep = endpoint.to(torch.int32).contiguous()
+    if sp.data_ptr() % 8:
+        sp = sp.clone()
+    if ep.data_ptr() % 8:
+        ep = ep.clone()
+    free = _free_pair[v.key]
+    pairs = max(free, key=lambda a: a.cap)
+    if pairs.buf.numel() < int(L.gcp_view_pair_bytes(pairs.cap, W, H)):
+        return False        # sized for another image / piece length
+    free.remove(pairs)
+    v.plan = _take_plan_arena(L, dev, n, W, H)
+    v.pairs = pairs
+    v.plan.totals_np[0] = -1
+    _lib.check(L.gcp_view_forward(_p(sp), _p(ep), _p(mean_), _p(lam_), _p(opac_), _p(l_), n, W, H, _p(v.plan.buf),
+                                  v.plan.buf.numel(), _p(pairs.buf), pairs.buf.numel(), pairs.cap, 1 if keep else 0,
+                                  _p(image), _p(v.plan.totals), cur.cuda_stream), "gcp_view_forward")
+    # the count arrives a few microseconds after the plan's scan kernel: poll the pinned word, fall back to a sync
+    t0 = time.perf_counter()
+    while v.plan.totals_np[0] < 0:
+        if time.perf_counter() - t0 > 2e-3:
+            cur.synchronize()
+            break
+    v.P = int(v.plan.totals_np[0])
+    if v.P >= 2 ** 31 - 64:
+        raise RuntimeError("a view is limited to 2**31 (tile, Gaussian) pairs")
+    if v.P <= pairs.cap:
+        return True
+    # too small: nothing was rendered.  Let the arena go and run the view again on one that fits.
+    cur.synchronize()
+    v.pairs = _take_pair_arena(L, dev, v.P, W, H)
+    _lib.check(L.gcp_view_forward(_p(sp), _p(ep), _p(mean_), _p(lam_), _p(opac_), _p(l_), n, W, H, _p(v.plan.buf),
+                                  v.plan.buf.numel(), _p(v.pairs.buf), v.pairs.buf.numel(), v.pairs.cap,
+                                  1 if keep else 0, _p(image), _p(v.plan.totals), cur.cuda_stream), "gcp_view_forward")
+    return True
 
 
 def _render_backward_tiles(v: _TileView, grad_image):

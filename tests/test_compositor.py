@@ -594,3 +594,42 @@ def test_one_call_forward_on_a_known_capacity_gpu(monkeypatch):
             assert torch.equal(img, img_exact)
         else:
             assert bool(torch.isnan(img).all()), "an overflowing view must not be rendered at all"
+
+
+@pytest.mark.gpu
+def test_speculative_forward_equals_the_synchronous_one_gpu(monkeypatch):
+    """compositor.SPECULATE: plan and render queued in one call on a pooled arena's capacity, the pair count read from
+    pinned memory afterwards.  Same bits as the plan / wait / render sequence — also when the pooled arena is too
+    small and the view has to be rendered again (the first attempt must leave nothing behind)."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    small = wl.splat_view(640, 360, 5_000, seed=11, device="cuda")
+    big = wl.splat_view(640, 360, 80_000, seed=12, device="cuda")
+    gI = torch.rand(361, 641, 3, device="cuda") + 0.1
+
+    def run(v):
+        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                        v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+        img.backward(gI)
+        torch.cuda.synchronize()
+        return [img.detach().clone()] + [t.grad.clone() for t in (m, lam, o, l)]
+
+    monkeypatch.setattr(compositor, "SPECULATE", False)
+    want_small, want_big = run(small), run(big)
+    monkeypatch.setattr(compositor, "SPECULATE", True)
+    compositor._free_pair.clear()
+    compositor._free_plan.clear()
+    run(small)                                   # leaves a small pair arena in the pool
+    key = compositor._pool_key(torch.device("cuda", torch.cuda.current_device()))
+    assert compositor._free_pair.get(key), "the small view's arena should be back in the pool"
+    cap_small = max(a.cap for a in compositor._free_pair[key])
+    got_big = run(big)                           # speculates on it, overflows, is rendered again
+    assert max(a.cap for a in compositor._free_pair[key]) > cap_small
+    got_big2 = run(big)                          # now fits: the one-call path
+    got_small = run(small)                       # a much larger arena than needed
+    for got, want in ((got_big, want_big), (got_big2, want_big), (got_small, want_small)):
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
