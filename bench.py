@@ -617,9 +617,10 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
     views = [wl.splat_view_device(W, H, n_param, seed=1080 + v, device=device) for v in mine]
     elems = sum(v.elements for v in views)
     target = torch.rand(H + 1, W + 1, 3, device=device)
-    head, tail = views[:-1], views[-1:]
+    n_tail = int(os.environ.get("BENCH_MV_TAIL", "2")) if len(views) >= 4 else 1
+    head, tail = views[:-n_tail], views[-n_tail:]
     bA = vw.NativeViewBatch(head, W, H, targets=[target] * len(head), lanes=lanes) if head else None
-    bB = vw.NativeViewBatch(tail, W, H, targets=[target], lanes=1)
+    bB = vw.NativeViewBatch(tail, W, H, targets=[target] * len(tail), lanes=min(lanes, len(tail)))
     small = torch.zeros(10 * n_param, dtype=torch.float32, device=device)     # the last view's own bucket
     loss = torch.zeros(1, device=device)
     comm = torch.cuda.Stream(device)
@@ -681,8 +682,9 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
     return {"views": args.views, "views_per_rank": len(mine), "distinct_views_per_rank": len(views), "lanes": lanes,
             "step_ms": max_ms, "host_enqueue_ms": host_ms / steps,
             "exposed_after_last_view_ms": max_tail,
-            "collective": ("nccl all_reduce(sum): the bucket of views 0..V-2 on a side stream during the last view, "
-                           "then the last view's 10 floats per Gaussian") if world > 1 else "none (1 rank)",
+            "tail_views": len(tail),
+            "collective": (f"nccl all_reduce(sum): the bucket of the first {len(head)} views on a side stream during the "
+                           f"last {len(tail)}, then the 10 floats per Gaussian of those") if world > 1 else "none (1 rank)",
             "bucket_bytes": bucket.numel() * 4, "tail_bucket_bytes": small.numel() * 4, "loss": "mean squared error",
             "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
             "gpu_launches_per_step": launches}
@@ -923,6 +925,7 @@ def reference_function_leg(device):
             r["native_ms"] = _median_ms(native, 7, warm=2)
             r["speedup_vs_reference_function"] = r["reference_function_ms"] / r["native_ms"]
             ia, ib, ic = res["ref"][0], res["dropin"][0], res["native"]
+            r["image_sums_ref_dropin_native"] = [float(ia.double().sum()), float(ib.double().sum()), float(ic.double().sum())]
             r["max_abs_image_diff_dropin_vs_ref_ops"] = float((ia - ib).abs().max())
             r["max_abs_image_diff_native_vs_ref_function"] = float((ia - ic).abs().max())
             out[tag] = r
