@@ -546,6 +546,22 @@ def splat_legs(args, device, rank, world):
     out["native_call_ms"] = _median_ms(lambda: nb.step(*gsec), reps, warm=2)
     out["native_call_launches"] = nb.launches
     del nb
+    # roofline of the splat step: the view's kernels are bound by instruction issue (the two walk kernels run at
+    # 68-78 % issue-slot utilisation), not by HBM: warp-instructions and DRAM bytes of the committed ncu capture of
+    # this very view (profiles/traffic.json: tile_view_1080p) over the live time of the native call
+    tv = _traffic().get("tile_view_1080p")
+    if tv and default_route == "tiles":
+        peak_hbm, _ = _peaks()
+        sm_hz = 1.965e9
+        issue_peak = 148 * 4 * sm_hz / 1e9           # G warp-instructions / s: 4 schedulers per SM, one per clock
+        t_s = out["native_call_ms"] * 1e-3
+        out["roofline"] = {"bound": "issue", "achieved": tv["warp_instructions"] / t_s / 1e9, "peak": issue_peak,
+                           "unit": "G warp-instructions/s", "frac": tv["warp_instructions"] / t_s / 1e9 / issue_peak,
+                           "warp_instructions_per_view": tv["warp_instructions"],
+                           "hbm": {"achieved": tv["dram_bytes"] / t_s / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                                   "frac": tv["dram_bytes"] / t_s / 1e9 / peak_hbm, "traffic": tv["dram_bytes"]},
+                           "time": "native_call_ms (gcp_views_step, one view)",
+                           "note": "the walk kernels alone: backward 68 %, render 78 % of their issue slots (ncu)"}
     # end to end from HOST tables to a HOST image and HOST gradients (pinned memory both ways, every copy inside
     # the timed region): what a caller pays who keeps the Gaussians on the host
     out["e2e_host_tables"] = e2e_splat_leg(sc, gI, device)

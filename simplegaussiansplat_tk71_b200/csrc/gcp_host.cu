@@ -2,26 +2,106 @@
 // arrays live in HOST memory the PCIe link bounds the step, so the segment keys do not cross it as 4 bytes per
 // element.  A segment is a run of equal adjacent keys (grouped_cumprod_forward.cu:17-23), so all the scan ops need
 // of `key` is where the runs start: the host packs that into one BIT per element (OpenMP, memory-bound), 1/32 of
-// the bytes go up, and the device rebuilds dense segment ids with one scan.
+// the bytes go up, and the device rebuilds dense segment ids with one scan (k_ids_from_bits: a hand-written
+// single-pass chained scan over the bit words, no library kernel).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
 
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
-
 #include "gcp_abi.h"
 
 namespace {
-struct BitAt {   // 1 where element i starts a run; element 0 contributes 0 so that the ids start at 0
-    const uint32_t *bits;
-    __host__ __device__ __forceinline__ int32_t operator()(int64_t i) const {
-        return i == 0 ? 0 : static_cast<int32_t>((bits[i >> 5] >> (i & 31)) & 1u);
+// ids[i] = number of run starts in elements 1..i (element 0 starts the first run and counts as id 0).  One thread
+// per 32-bit word: its popcount is the word's aggregate; the block scans its 256 aggregates, publishes the block
+// aggregate and walks back over the predecessors' descriptors to the nearest inclusive prefix (blocks take their
+// tile from an atomic ticket, so a block only waits for blocks that are already running); then every warp expands
+// its 32 words one after the other, lane = element, 128 contiguous bytes per store.
+// descriptor = status (1 aggregate, 2 inclusive) << 62 | value;  temp = {ticket u32, pad} + one descriptor per block.
+constexpr int IDS_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(IDS_THREADS)
+k_ids_from_bits(const uint32_t *__restrict__ bits, int64_t n, int32_t *__restrict__ ids, unsigned int *ticket,
+                unsigned long long *desc) {
+    __shared__ unsigned int s_warp[IDS_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t words = (n + 31) >> 5;
+    const int64_t w = static_cast<int64_t>(tile) * IDS_THREADS + threadIdx.x;
+    uint32_t word = 0;
+    if (w < words) {
+        word = bits[w];
+        const int64_t left = n - (w << 5);
+        if (left < 32) word &= (1u << left) - 1u;     // the ragged tail
+        if (w == 0) word &= ~1u;                      // element 0 is id 0
     }
-};
+    const unsigned int cnt = __popc(word);
+    unsigned int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned int wpre = 0, agg = 0;
+#pragma unroll
+    for (int k = 0; k < IDS_THREADS / 32; ++k) {
+        if (k < warp) wpre += s_warp[k];
+        agg += s_warp[k];
+    }
+    if (warp == 0) {
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st_release_u64(desc, (2ull << 62) | agg);
+        } else {
+            if (lane == 0) st_release_u64(desc + tile, (1ull << 62) | agg);
+            int64_t pb = static_cast<int64_t>(tile) - 1;
+            while (true) {
+                const int64_t idx = pb - lane;
+                unsigned long long d = 2ull << 62;   // before tile 0: an inclusive prefix of 0
+                if (idx >= 0) {
+                    do { d = ld_acquire_u64(desc + idx); } while ((d >> 62) == 0ull);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+                const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                unsigned long long c = (lane <= stop) ? (d & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                prefix += c;
+                if (inc_mask) break;
+                pb -= 32;
+            }
+            if (lane == 0) st_release_u64(desc + tile, (2ull << 62) | (prefix + agg));
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const unsigned int before = static_cast<unsigned int>(s_prefix) + wpre + (inc - cnt);   // run starts before my word
+    const int64_t w0 = w - lane;                                                             // the warp's first word
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t wk = __shfl_sync(0xffffffffu, word, k);
+        const unsigned int bk = __shfl_sync(0xffffffffu, before, k);
+        const int64_t i = ((w0 + k) << 5) + lane;
+        if (i < n) ids[i] = static_cast<int32_t>(bk + __popc(wk & ((2u << lane) - 1u)));
+    }
+}
+
 // run-start bits of the (up to 32) elements of word w
 inline uint32_t word_scalar(const int32_t *key, int64_t n, int64_t w) {
     const int64_t i0 = w << 5;
@@ -86,23 +166,26 @@ int gcp_host_boundary_bits(const int32_t *key, int64_t n, uint32_t *bits, int th
 }
 
 size_t gcp_ids_from_bits_bytes(int64_t n) {
-    size_t a = 0;
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), BitAt{nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, a, it, static_cast<int32_t *>(nullptr), n > 0 ? n : 1);
-    return a + 256;
+    const int64_t words = n > 0 ? (n + 31) >> 5 : 1;
+    const int64_t blocks = (words + IDS_THREADS - 1) / IDS_THREADS;
+    return 256 + static_cast<size_t>(blocks) * 8;
 }
 
 int gcp_ids_from_bits(const uint32_t *bits, int64_t n, int32_t *ids, void *temp, size_t temp_bytes,
                       gcp_stream_t stream) {
     if (n < 0) return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
-    if (!bits || !ids || !temp) return GCP_ERR_INVALID_ARG;
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), BitAt{bits});
-    size_t need = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, need, it, ids, n);
+    if (!bits || !ids || !temp || (reinterpret_cast<uintptr_t>(temp) & 7)) return GCP_ERR_INVALID_ARG;
+    const size_t need = gcp_ids_from_bits_bytes(n);
     if (temp_bytes < need) return GCP_ERR_WORKSPACE;
-    size_t tb = temp_bytes;
-    return static_cast<int>(cub::DeviceScan::InclusiveSum(temp, tb, it, ids, n, reinterpret_cast<cudaStream_t>(stream)));
+    auto st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(temp, 0, need, st);     // ticket + descriptors
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int64_t words = (n + 31) >> 5;
+    const unsigned blocks = static_cast<unsigned>((words + IDS_THREADS - 1) / IDS_THREADS);
+    k_ids_from_bits<<<blocks, IDS_THREADS, 0, st>>>(bits, n, ids, static_cast<unsigned int *>(temp),
+                                                    reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(temp) + 256));
+    return static_cast<int>(cudaGetLastError());
 }
 
 }  // extern "C"
