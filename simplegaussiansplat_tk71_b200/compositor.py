@@ -16,16 +16,18 @@ but not how.  Two routes, `ROUTE` below, both through the C ABI (include/gcp_abi
 fixtures the reference's own Function produced (tests/test_compositor.py):
 
   "tiles" (default, csrc/gcp_tile.cu) — the fused route: the per-pixel scan is evaluated one pixel per lane, the
-  running T in a register, without materialising the element lists.  Three C-ABI calls per view, all of them
-  working inside two pooled arenas (nothing is allocated per view but the image and the four gradients):
+  running T in a register, without materialising the element lists.  Two or three C-ABI calls per view, all of
+  them working inside two pooled arenas (nothing is allocated per view but the image and the four gradients):
     forward   gcp_view_plan      (tile, Gaussian) pair counts per Gaussian and per 8x4-pixel tile, their offsets, the
                                  pair total (the one number the host needs: it sizes the pair arena)
               gcp_view_render    packed records; the pairs dropped into their tiles and every tile's list put in
                                  Gaussian (= depth) order; one warp per piece of a tile's list: alpha, T, colour; a
-                                 checkpoint of T every 16 pairs is all the backward keeps (8 B per pair)
-    backward  gcp_view_backward  per 16 pairs T is recomputed from its checkpoint, then the list is walked in
+                                 checkpoint of T every 8 pairs is all the backward keeps (16 B per pair)
+              gcp_view_forward   = plan + render in one call on a pooled arena's capacity (SPECULATE below)
+    backward  gcp_view_backward  per 8 pairs T is recomputed from its checkpoint, then the list is walked in
                                  reverse: U_i, dL/dalpha_i = T_i (<dL/dI, l_i> - U_i), the moments of g*dalpha over
                                  each pair's pixels (:733-766), the pairs of a Gaussian summed in pair order (:776-783)
+  A whole batch of views in one call: views.NativeViewBatch (gcp_views_step).
 
   "lists" (csrc/gcp_splat.cu + the scan ops a1 / a3) — the element-list route:
     forward   gcp_splat_pack     per-Gaussian tables -> two 32-byte records (one L2 sector per gather)

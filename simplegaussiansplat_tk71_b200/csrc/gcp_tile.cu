@@ -1,7 +1,7 @@
 // gcp_tile.cu — the fused compositor route: exclusive transmittance, colour sum and the
 // division-free backward in ONE walk per direction, without materialising the per-pixel element lists, behind two
-// C-ABI calls per view (gcp_view_plan + gcp_view_render, or gcp_view_forward; gcp_view_backward) that work
-// entirely inside caller-owned arenas.
+// or three C-ABI calls per view (gcp_view_plan + gcp_view_render, or gcp_view_forward; gcp_view_backward) that work
+// entirely inside caller-owned arenas, and one call per batch of views (gcp_views_step).
 //
 // The per-pixel segmented scan  T_i = prod_{j<i} (1 - alpha_j),  C = sum_i T_i alpha_i l_i  (gs_model.py:544-566,
 // :498-514) is evaluated with one pixel per lane.  The image is cut into tiles of 8 x 4 pixels = one warp; a box
@@ -16,19 +16,23 @@
 //                               from an atomic counter per tile (unordered)                    (gs_model.py:538-548)
 //             k_view_scan     : tile offsets
 //             k_view_scatter  : every pair's Gaussian id dropped at tile offset + slot
-//             k_view_sort     : every tile's segment sorted by Gaussian id (bitonic network in registers) — the
-//                               ids of a tile are distinct, so the result IS the stable sort by tile, bit for
-//                               bit; long lists are cut into pieces (the walk kernels' work units)
+//             k_view_sort     : every tile's segment sorted by Gaussian id (bitonic network in registers; lists of
+//             k_view_sort_long  513-4096 ids by a block, longer ones through shared memory) — the ids of a tile are
+//             k_view_sort_huge  distinct, so the result IS the stable sort by tile, bit for bit; long lists are cut
+//                               into pieces (the walk kernels' work units)
 //             k_view_render   : alpha = o * exp(-1/2 d Lambda d^T) (:493-495,:533-535), T, colour; only a
 //                               CHECKPOINT of T every 8 pairs is kept for the backward (16 B per pair)
-//   backward  k_view_backward : per 8 pairs, T and the Gaussian kernel value are recomputed from the checkpoint
-//                               into registers, then the pairs are walked in reverse with
+//             k_view_combine_fwd / _bwd : carries between the pieces of a long list          (:582-594)
+//   backward  k_view_backward : per 8 pairs, (1) T and the Gaussian kernel value are recomputed from the checkpoint
+//                               into registers, (2) the pairs are walked in reverse with
 //                               U_i = w_{i+1} + (1-alpha_{i+1}) U_{i+1}  (w = <dL/dI, alpha l>),
 //                               dL/dalpha_i = T_i (<dL/dI, l_i> - U_i) — no division by 1-alpha (:736,:747,:757
-//                               divide) — and the moments of g*dalpha over the pair's pixels, from which the
+//                               divide), (3) the moments of g*dalpha over the pair's pixels, from which the
 //                               reference's per-element gradients (:733-766) follow per Gaussian, are summed
-//                               over the 32 lanes in a fixed order;
-//             k_view_reduce   : the partial sums of a Gaussian's pairs added in pair order (:776-783).
+//                               through shared memory (lane = pair x tile row) in a fixed order;
+//             k_view_reduce (+ _big) : the partial sums of a Gaussian's pairs added in pair order (:776-783),
+//                               written to the view's gradients or scatter-added into the parameters' (gcp_views_step)
+//   batch     gcp_views_step  : all views of a training step in one call over alternating stream lanes
 // No float atomics anywhere: a pixel belongs to one lane, a partial to one pair — bitwise reproducible.
 // Elements whose inclusive product is 0 contribute nothing and get no gradient (gs_model.py:575-578).
 // No library kernels (CUB / thrust) on this route.
