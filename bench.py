@@ -359,7 +359,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(e2e_steps):
-        streamer.fwd_bwd(hx, hk, hg, hy, hgin)
+        # sync=False: the call returns when everything is queued, the current stream waits for the downloads —
+        # consecutive steps pipeline (download of step i beside the upload of step i+1), the events bracket it all
+        streamer.fwd_bwd(hx, hk, hg, hy, hgin, sync=False)
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -367,7 +369,12 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_val = total_elems * e2e_steps / (float(t2.item()) * 1e-3) / 1e9
     # the host results of the streamed step equal the resident ones
-    assert torch.equal(hy[: 1 << 16], y[: 1 << 16].cpu()), "streamed forward differs from the resident forward"
+    # the chunks shift the tile grid, so the fp32 association differs from the resident call's: compared at twice
+    # the north star's tolerance (forward) / in relative L2 norm (backward: sums with cancellation)
+    yc, gc_ = y.cpu(), gin.cpu()
+    assert torch.allclose(hy, yc, rtol=2e-5, atol=2e-6), "streamed forward differs from the resident forward"
+    assert float((hgin - gc_).norm() / gc_.norm()) < 1e-5, "streamed backward differs from the resident backward"
+    del yc, gc_
     del streamer
 
     # ---- splat step @1080p and the multi-view step (BASELINE.json configs[4]) ----
