@@ -1075,27 +1075,31 @@ __device__ __forceinline__ void add_partial(float (&S)[7], const int4 &u, const 
 __global__ void __launch_bounds__(256)
 k_view_reduce(const float *__restrict__ partial, const int32_t *__restrict__ toff, const int4 *__restrict__ rec,
               int64_t n, GradOut out, unsigned int *__restrict__ hdr, int64_t cap, int32_t *__restrict__ big) {
-    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= n || overflowed(hdr, cap)) return;
-    const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
-    if (e - b > RED_BIG) {
-        big[atomicAdd(hdr + H_NBIG, 1u)] = static_cast<int32_t>(g);
-        return;
-    }
-    float S[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (overflowed(hdr, cap)) return;
     const int4 zero = make_int4(0, 0, 0, 0);
-    for (int q = b; q < e; q += 4) {
-        int4 u[4], v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            u[i] = zero; v[i] = zero;
-            if (q + i < e) ldg256(partial + static_cast<int64_t>(q + i) * 8, u[i], v[i]);
+    // grid-stride: resident blocks that live for the whole kernel keep the memory system fuller than 3 500 blocks
+    // of a few microseconds each (ncu: 50 % of the warp slots active, 2.8 TB/s)
+    for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n;
+         g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int b = __ldg(toff + g), e = __ldg(toff + g + 1);
+        if (e - b > RED_BIG) {
+            big[atomicAdd(hdr + H_NBIG, 1u)] = static_cast<int32_t>(g);
+            continue;
         }
+        float S[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int q = b; q < e; q += 4) {
+            int4 u[4], v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (q + i < e) add_partial(S, u[i], v[i]);
+            for (int i = 0; i < 4; ++i) {
+                u[i] = zero; v[i] = zero;
+                if (q + i < e) ldg256(partial + static_cast<int64_t>(q + i) * 8, u[i], v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (q + i < e) add_partial(S, u[i], v[i]);
+        }
+        store_sums(S, g, rec, out);
     }
-    store_sums(S, g, rec, out);
 }
 
 // Big Gaussians.  Up to RED_HUGE pairs: one warp each (ticket) — lane l adds the partials of pairs l, l+32, ... (one
@@ -1458,7 +1462,7 @@ int launch_backward_reduce(const BackwardArgs &a, cudaStream_t st) {
     const int32_t *toff = at<int32_t>(a.plan, A.toff);
     const float *partial = at<float>(a.pairs, B.partial);
     int32_t *big = at<int32_t>(a.plan, A.big);
-    k_view_reduce<<<blocks_for(a.n, 256), 256, 0, st>>>(partial, toff, rec, a.n, a.out, hdr, a.pair_cap, big);
+    k_view_reduce<<<blocks_for(a.n, 256, 148 * 8), 256, 0, st>>>(partial, toff, rec, a.n, a.out, hdr, a.pair_cap, big);
     k_view_reduce_big<<<148 * 4, 256, 0, st>>>(partial, toff, rec, a.out, hdr, a.pair_cap, big);
     t_view_launches += 2;
     return static_cast<int>(cudaGetLastError());

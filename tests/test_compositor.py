@@ -633,3 +633,54 @@ def test_speculative_forward_equals_the_synchronous_one_gpu(monkeypatch):
     for got, want in ((got_big, want_big), (got_big2, want_big), (got_small, want_small)):
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_native_compositor_1080p_200k_view_against_oracle_gpu(route):
+    """A 1920x1080 view of 200 000 Gaussians (7.5 M elements, the largest the fp64 oracle finishes in seconds) at
+    the north star's tolerance, both routes."""
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+
+    sc = wl.splat_view(1920, 1080, 200_000, seed=1080, device="cpu")
+    rng = np.random.default_rng(9)
+    case = dict(boxsize=sc.boxsize.numpy(), sp=sc.startpoint.numpy(), ep=sc.endpoint.numpy(), mean=sc.mean.numpy(),
+                lam=sc.lam.numpy(), opac=sc.opacity.numpy(), l_d=sc.l_d.numpy(), W=sc.width, H=sc.height,
+                grad_image=rng.uniform(0.1, 1.0, (sc.height + 1, sc.width + 1, 3)).astype(np.float32))
+    _check(_run(case, "cuda"), case, fixture=False)
+
+
+@pytest.mark.gpu
+def test_backward_is_linear_in_grad_image_at_full_size_gpu(monkeypatch):
+    """Size-independent property at BASELINE.json's full splat size (1080p, 1 M Gaussians, 37 M elements): the
+    backward is linear in dL/dimage — grads(a gI1 + b gI2) = a grads(gI1) + b grads(gI2) — and two runs of the same
+    step are bitwise equal (no float atomics on the tile route)."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    v = wl.splat_view_device(1920, 1080, 1_000_000, seed=1080, device="cuda")
+    g1 = torch.rand(v.height + 1, v.width + 1, 3, device="cuda")
+    g2 = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") - 0.5
+
+    def grads(gI):
+        m, lam, o, l = (v.mean.float().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                        v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+        img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam, o, l, v.width, v.height)
+        img.backward(gI)
+        return [img.detach()] + [t.grad for t in (m, lam, o, l)]
+
+    a, b = 0.75, -1.5
+    r1, r2, r12, r12b = grads(g1), grads(g2), grads(a * g1 + b * g2), grads(a * g1 + b * g2)
+    assert torch.isfinite(r12[0]).all() and float(r12[0].max()) > 0
+    for x, y in zip(r12, r12b):
+        assert torch.equal(x, y)
+    # |g1| and |g2| bound the terms: the scale of the comparison is grads(|a| |g1| + |b| |g2|) >= sum of |terms|
+    rs = grads(abs(a) * g1.abs() + abs(b) * g2.abs())
+    for name, x1, x2, x12, s in zip(("mean", "lambda", "opacity", "l"), r1[1:], r2[1:], r12[1:], rs[1:]):
+        want = a * x1.double() + b * x2.double()
+        # the scale run has cancellation of its own (mean / lambda terms change sign with d): use the array's norm
+        # per Gaussian as a floor so that the bound is never tighter than fp32 rounding of the terms
+        bound = 1e-6 + 1e-4 * torch.maximum(s.double().abs(), want.abs())
+        err = (x12.double() - want).abs()
+        frac_bad = float((err > bound).double().mean())
+        assert frac_bad < 1e-3, (name, frac_bad, float((err / bound).max()))
