@@ -690,6 +690,7 @@ k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ ts
     __shared__ FSlot slots[TILE_WARPS];
     if (overflowed(hdr, cap)) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lanebit = 1u << lane;
     FSlot &sl = slots[wib];
     const int nx = static_cast<int>(hdr[H_XPIECES]);
     Piece w;
@@ -726,12 +727,13 @@ k_view_render(const int32_t *__restrict__ tcount, const int32_t *__restrict__ ts
 #pragma unroll 4
             for (int k = 0; k < m; ++k) {
                 const float4 A = sl.a[k], B = sl.b[k], C = sl.c[k];
-                const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
+                const bool cov = (__float_as_uint(B.w) & lanebit) != 0u;   // one LOP3 into a predicate
                 const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
                 if (KEEP && (k & (SUB - 1)) == 0) __stcs(ck + (k >> SUB_SHIFT) * 32, T);   // T checkpoint for the backward
                 const float tin = T * e.x;
                 // branch-free: an element outside the box, or dead (inclusive product 0, gs_model.py:575-578), adds 0
-                const float ta = (cov && tin != 0.0f) ? T * (1.0f - e.x) : 0.0f;
+                const bool alive = cov & (tin != 0.0f);
+                const float ta = alive ? T * (1.0f - e.x) : 0.0f;
                 c0 = fmaf(ta, C.x, c0);
                 c1 = fmaf(ta, C.y, c1);
                 c2 = fmaf(ta, C.z, c2);
@@ -855,12 +857,13 @@ __device__ __forceinline__ void backward_sub_batch(const BSlot &sl, float *__res
     // (1) recompute sweep, forward: T and g of every (pair, lane) of the sub-batch; coverage bits kept per lane
     float Tk[SUB], Gk[SUB];
     unsigned covbits = 0;
+    const unsigned lanebit = 1u << lane;
 #pragma unroll
     for (int k = 0; k < SUB; ++k) {
         Tk[k] = 0.0f; Gk[k] = 0.0f;
         if (FULL || k < ms) {   // warp-uniform
             const float4 A = sl.f0[s0 + k], B = sl.f1[s0 + k];
-            const bool cov = (__float_as_uint(B.w) >> lane) & 1u;
+            const bool cov = (__float_as_uint(B.w) & lanebit) != 0u;
             const PairEval e = eval_pair(A, B.x, B.y, B.z, px, py);
             Tk[k] = T;
             Gk[k] = e.gk;
@@ -876,7 +879,7 @@ __device__ __forceinline__ void backward_sub_batch(const BSlot &sl, float *__res
             const bool cov = (covbits >> k) & 1u;
             const float Tt = Tk[k], gk = Gk[k];
             const float alpha = R0.x * gk, x = 1.0f - alpha;
-            const bool alive = cov && (Tt * x != 0.0f);
+            const bool alive = cov & (Tt * x != 0.0f);
             const float pgl = pg0 * R0.y + pg1 * R0.z + pg2 * R0.w;
             const float wv = alive ? alpha * pgl : 0.0f;
             const float dalpha = alive ? Tt * (pgl - U) : 0.0f;
