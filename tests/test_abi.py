@@ -170,3 +170,64 @@ def test_tile_size_helpers_are_pure_host_arithmetic():
         assert out[8] == 2 * (P // 64) + 2
     finally:
         L.gcp_tile_set_piece_pairs(piece)
+
+
+def test_view_entry_points_validate_their_arguments_without_device():
+    """Every check of the view / batch entry points that precedes the first CUDA call: bad sizes and pointers give
+    GCP_ERR_INVALID_ARG / GCP_ERR_WORKSPACE, never a crash (the reference's raw kernel launches are unchecked,
+    grouped_cumprod_backward.cu:56-64)."""
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    INVALID, WORKSPACE = -1, -2
+    assert (_lib.ERRORS[INVALID], _lib.ERRORS[WORKSPACE]) == ("GCP_ERR_INVALID_ARG", "GCP_ERR_WORKSPACE")
+    buf = ctypes.create_string_buffer(1 << 16)
+    base = (ctypes.addressof(buf) + 255) & ~255          # a 256-byte aligned fake arena (never dereferenced)
+    W, H, n = 64, 32, 10
+    need = L.gcp_view_plan_bytes(n, W, H)
+    assert 0 < need < (1 << 16) - 256
+    totals = (ctypes.c_int64 * 2)()
+    # plan: negative n, image too large, no arena, misaligned arena, arena too small, misaligned boxes
+    assert L.gcp_view_plan(base, base, -1, W, H, base, need, totals, None) == INVALID
+    assert L.gcp_view_plan(base, base, n, 40000, H, base, need, totals, None) == INVALID
+    assert L.gcp_view_plan(base, base, n, W, H, None, need, totals, None) == INVALID
+    assert L.gcp_view_plan(base, base, n, W, H, base + 8, need, totals, None) == WORKSPACE
+    assert L.gcp_view_plan(base, base, n, W, H, base, need - 1, totals, None) == WORKSPACE
+    assert L.gcp_view_plan(base + 4, base, n, W, H, base, need, totals, None) == INVALID
+    # render / backward: capacity out of range, missing tables, arenas too small
+    pair_need = L.gcp_view_pair_bytes(1000, W, H)
+    args = (base, base, base, base, base, base, n, W, H, base, need, base, pair_need, 1000, 1, base, None)
+    assert L.gcp_view_render(*args[:13], 2 ** 31, *args[14:]) == INVALID
+    assert L.gcp_view_render(*args[:2], None, *args[3:]) == INVALID
+    assert L.gcp_view_render(*args[:12], pair_need - 1, *args[13:]) == WORKSPACE
+    bw = (base, need, base, pair_need, 1000, base, n, W, H, base, base, base, base, None)
+    assert L.gcp_view_backward(*bw[:5], None, *bw[6:]) == INVALID                     # no grad_image
+    assert L.gcp_view_backward(*bw[:9], None, *bw[10:]) == INVALID                    # no output
+    assert L.gcp_view_backward(*bw[:9], base + 4, *bw[10:]) == INVALID                # g_mean must be 8-byte aligned
+    assert L.gcp_view_backward(*bw[:3], pair_need - 1, *bw[4:]) == WORKSPACE
+    assert L.gcp_view_backward(*bw[:6], 0, *bw[7:]) == 0                              # an empty view: nothing to do
+    # batch: lanes out of range, no context
+    ctx = ctypes.c_void_p()
+    assert L.gcp_views_ctx_create(0, ctypes.byref(ctx)) == INVALID
+    assert L.gcp_views_ctx_create(5, ctypes.byref(ctx)) == INVALID
+    assert L.gcp_views_ctx_create(1, None) == INVALID
+    plans = (ctypes.c_void_p * 1)(base)
+    assert L.gcp_views_step(None, None, 0, W, H, plans, need, plans, pair_need, 1000, base, base, base, base, None,
+                            totals, None) == INVALID
+    L.gcp_views_ctx_destroy(None)                                                       # a no-op
+
+
+def test_native_view_batch_refuses_cpu_tensors_and_bad_arguments():
+    import torch
+
+    from simplegaussiansplat_tk71_b200 import workloads as wl
+    from simplegaussiansplat_tk71_b200.views import NativeViewBatch
+
+    v = wl.splat_view(64, 48, 200, seed=1, device="cpu")
+    g = torch.zeros(49, 65, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        NativeViewBatch([v], 64, 48, grad_images=[g])
+    with pytest.raises(ValueError, match="either targets"):
+        NativeViewBatch([v], 64, 48)
+    with pytest.raises(ValueError, match="either targets"):
+        NativeViewBatch([v], 64, 48, targets=[g], grad_images=[g])
