@@ -640,30 +640,29 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
     views = [wl.splat_view_device(W, H, n_param, seed=1080 + v, device=device) for v in mine]
     elems = sum(v.elements for v in views)
     target = torch.rand(H + 1, W + 1, 3, device=device)
-    n_tail = int(os.environ.get("BENCH_MV_TAIL", "2")) if len(views) >= 4 else 1
-    head, tail = views[:-n_tail], views[-n_tail:]
-    bA = vw.NativeViewBatch(head, W, H, targets=[target] * len(head), lanes=lanes) if head else None
-    bB = vw.NativeViewBatch(tail, W, H, targets=[target] * len(tail), lanes=min(lanes, len(tail)))
-    small = torch.zeros(10 * n_param, dtype=torch.float32, device=device)     # the last view's own bucket
+    n_tail = min(int(os.environ.get("BENCH_MV_TAIL", "2")), max(len(views) - 1, 1))
+    first_tail = len(views) - n_tail
+    batch = vw.NativeViewBatch(views, W, H, targets=[target] * len(views), lanes=lanes)
+    small = torch.zeros(10 * n_param, dtype=torch.float32, device=device)     # the tail views' own bucket
     loss = torch.zeros(1, device=device)
     comm = torch.cuda.Stream(device)
     cur = torch.cuda.current_stream(device)
     secA, secB = _sections(bucket, n_param), _sections(small, n_param)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    head_done = torch.cuda.Event()
+    head_done.record(cur)                  # materialises the CUDA event the native call records in mid-batch
 
     def step(marks=None):
         bucket.zero_()
         small.zero_()
         loss.zero_()
-        if bA is not None:
-            bA.step(*secA, loss)
+        # ONE native call for all views of this rank; the views in front of the tail add into the bucket, whose
+        # all-reduce starts on `head_done` — recorded inside the batch — beside the tail views
+        batch.step(*secA, loss, tail=(first_tail, secB, head_done))
         if world > 1:
-            done_a = torch.cuda.Event()
-            done_a.record(cur)
-            comm.wait_event(done_a)
+            comm.wait_event(head_done)
             with torch.cuda.stream(comm):
-                dist.all_reduce(bucket, op=dist.ReduceOp.SUM)          # overlaps the last view
-        bB.step(*secB, loss)
+                dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
         if marks is not None:
             marks[0].record(cur)
         if world > 1:
@@ -675,7 +674,7 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
         for _ in range(3):
             step()
             torch.cuda.synchronize()
-            if (bA is None or bA.finish()) & bB.finish():
+            if batch.finish():
                 return
         raise RuntimeError("the view batch did not fit its arenas after two enlargements")
 
@@ -694,20 +693,21 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
         host_ms += (time.perf_counter() - h0) * 1e3
         t2.record()
         torch.cuda.synchronize()
-        assert (bA is None or bA.finish()) and bB.finish()
+        assert batch.finish()
         step_ms += t0.elapsed_time(t2)
         tail_ms += t1.elapsed_time(t2)
     print(f"multi-view step (native, lanes={lanes}): {step_ms / steps:.2f} ms, host enqueue {host_ms / steps:.2f} ms, "
           f"after the last view {tail_ms / steps:.3f} ms, loss {float(loss):.5f}", file=sys.stderr)
     tot_e, max_ms = vw.aggregate_throughput(elems, step_ms / steps, device)
     _, max_tail = vw.aggregate_throughput(0, tail_ms / steps, device)
-    launches = (bA.launches if bA is not None else 0) + bB.launches
+    launches = batch.launches
     return {"views": args.views, "views_per_rank": len(mine), "distinct_views_per_rank": len(views), "lanes": lanes,
             "step_ms": max_ms, "host_enqueue_ms": host_ms / steps,
             "exposed_after_last_view_ms": max_tail,
-            "tail_views": len(tail),
-            "collective": (f"nccl all_reduce(sum): the bucket of the first {len(head)} views on a side stream during the "
-                           f"last {len(tail)}, then the 10 floats per Gaussian of those") if world > 1 else "none (1 rank)",
+            "tail_views": n_tail,
+            "collective": (f"nccl all_reduce(sum): the bucket of the first {first_tail} views on a side stream during the "
+                           f"last {n_tail} (event recorded inside the batch), then the 10 floats per Gaussian of those")
+            if world > 1 else "none (1 rank)",
             "bucket_bytes": bucket.numel() * 4, "tail_bucket_bytes": small.numel() * 4, "loss": "mean squared error",
             "elements_per_step": tot_e, "Gelem_s": tot_e / (max_ms * 1e-3) / 1e9 if max_ms else None,
             "gpu_launches_per_step": launches}

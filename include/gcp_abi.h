@@ -344,6 +344,20 @@ void gcp_views_ctx_destroy(gcp_views_ctx *ctx);
 int gcp_views_step(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, int W, int H, void *const *plan,
                    size_t plan_bytes, void *const *pairs, size_t pair_bytes, int64_t pair_cap, float *g_mean,
                    float *g_lam, float *g_opac, float *g_l, float *loss, int64_t *totals_host, gcp_stream_t stream);
+/* The same batch with a TAIL: views first_tail_view.. add their gradients into a second set of arrays, and `event`
+ * (a cudaEvent_t, or NULL) is recorded as soon as the last view in front of the tail has been added to the main
+ * arrays — while the tail views are still running.  A data-parallel caller starts the all-reduce of the main
+ * bucket on that event and only has the tail's small arrays left to reduce when the batch ends (bench.py,
+ * multi_view_leg); the lanes stay full across the split, which two separate batches cannot do. */
+typedef struct gcp_views_split {
+    int first_tail_view;
+    float *g_mean, *g_lam, *g_opac, *g_l;   /* the tail's arrays, same shapes and alignment rules as the main ones */
+    void *event;                            /* cudaEvent_t or NULL */
+} gcp_views_split;
+int gcp_views_step_split(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, int W, int H, void *const *plan,
+                         size_t plan_bytes, void *const *pairs, size_t pair_bytes, int64_t pair_cap, float *g_mean,
+                         float *g_lam, float *g_opac, float *g_l, float *loss, int64_t *totals_host,
+                         const gcp_views_split *split, gcp_stream_t stream);
 /* Test aid: byte offsets of the integer arrays the tests compare bit for bit with oracle/tile_oracle.py.
  * out[0..5] (plan arena): toff i32[n+1] (Gaussian-major pair offsets), tile_count i32[tiles], tile_start
  * i32[tiles+1], piece_extra i32[tiles], header, records; out[6..7] (pair arena): pair_gid i32[cap],

@@ -33,7 +33,7 @@ SYMBOLS = (
     "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs",
     "gcp_view_plan_bytes", "gcp_view_pair_bytes", "gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward",
     "gcp_view_backward", "gcp_view_backward_scatter", "gcp_view_last_launch_count",
-    "gcp_views_ctx_create", "gcp_views_ctx_destroy", "gcp_views_step",
+    "gcp_views_ctx_create", "gcp_views_ctx_destroy", "gcp_views_step", "gcp_views_step_split",
     "gcp_host_boundary_bits", "gcp_ids_from_bits_bytes", "gcp_ids_from_bits",
 )
 
@@ -44,6 +44,12 @@ class ViewDesc(ctypes.Structure):
                 ("opac", ctypes.c_void_p), ("l_d", ctypes.c_void_p), ("index", ctypes.c_void_p),
                 ("target", ctypes.c_void_p), ("grad_image", ctypes.c_void_p), ("image", ctypes.c_void_p),
                 ("n", ctypes.c_int64)]
+
+
+class ViewsSplit(ctypes.Structure):
+    """gcp_views_split of include/gcp_abi.h: the tail of a batch and the event in front of it."""
+    _fields_ = [("first_tail_view", ctypes.c_int), ("g_mean", ctypes.c_void_p), ("g_lam", ctypes.c_void_p),
+                ("g_opac", ctypes.c_void_p), ("g_l", ctypes.c_void_p), ("event", ctypes.c_void_p)]
 
 
 def lib() -> ctypes.CDLL:
@@ -154,8 +160,10 @@ def lib() -> ctypes.CDLL:
     L.gcp_views_ctx_destroy.restype = None
     L.gcp_views_step.argtypes = [vp, ctypes.POINTER(ViewDesc), ci, ci, ci, ctypes.POINTER(vp), sz, ctypes.POINTER(vp), sz,
                                  i64, vp, vp, vp, vp, vp, vp, vp]
+    L.gcp_views_step_split.argtypes = [vp, ctypes.POINTER(ViewDesc), ci, ci, ci, ctypes.POINTER(vp), sz, ctypes.POINTER(vp),
+                                       sz, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ViewsSplit), vp]
     for name in ("gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward", "gcp_view_backward",
-                 "gcp_view_backward_scatter", "gcp_views_ctx_create", "gcp_views_step",
+                 "gcp_view_backward_scatter", "gcp_views_ctx_create", "gcp_views_step", "gcp_views_step_split",
                  "gcp_view_last_launch_count"):
         getattr(L, name).restype = ci
     for name in ("gcp_splat_expand", "gcp_splat_sort", "gcp_splat_alpha", "gcp_splat_color", "gcp_splat_bwd_w",

@@ -1576,8 +1576,19 @@ void gcp_views_ctx_destroy(gcp_views_ctx *c) {
 int gcp_views_step(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, int W, int H, void *const *plan,
                    size_t plan_bytes, void *const *pairs, size_t pair_bytes, int64_t pair_cap, float *g_mean,
                    float *g_lam, float *g_opac, float *g_l, float *loss, int64_t *totals_host, gcp_stream_t stream) {
+    return gcp_views_step_split(ctx, views, n_views, W, H, plan, plan_bytes, pairs, pair_bytes, pair_cap, g_mean, g_lam,
+                                g_opac, g_l, loss, totals_host, nullptr, stream);
+}
+
+int gcp_views_step_split(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, int W, int H, void *const *plan,
+                         size_t plan_bytes, void *const *pairs, size_t pair_bytes, int64_t pair_cap, float *g_mean,
+                         float *g_lam, float *g_opac, float *g_l, float *loss, int64_t *totals_host,
+                         const gcp_views_split *split, gcp_stream_t stream) {
     if (!ctx || n_views < 0 || (n_views > 0 && !views) || bad_image(W, H) || !plan || !pairs || !totals_host)
         return GCP_ERR_INVALID_ARG;
+    if (split && (split->first_tail_view < 0 || !split->g_mean || !split->g_lam || !split->g_opac || !split->g_l))
+        return GCP_ERR_INVALID_ARG;
+    const int first_tail = split ? split->first_tail_view : n_views;
     auto main_st = reinterpret_cast<cudaStream_t>(stream);
     const int lanes = ctx->lanes;
     int launches = 0;
@@ -1609,8 +1620,10 @@ int gcp_views_step(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, 
                                                          pair_cap, d.grad_image, loss);
                 ++launches;
             }
+            const bool tail = v >= first_tail;   // the last views add into arrays of their own (see gcp_views_split)
             const BackwardArgs a = {plan[lane], pairs[lane], pair_cap, d.n, d.grad_image, W, H,
-                                    {g_mean, g_lam, g_opac, g_l, d.index}};
+                                    {tail ? split->g_mean : g_mean, tail ? split->g_lam : g_lam,
+                                     tail ? split->g_opac : g_opac, tail ? split->g_l : g_l, d.index}};
             rc = check_backward(a, plan_bytes, pair_bytes);
             if (rc != GCP_OK) return rc;
             t_view_launches = 0;
@@ -1632,6 +1645,16 @@ int gcp_views_step(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_views, 
             e = cudaEventRecord(ctx->ev_reduced[lane], st);
             if (e != cudaSuccess) return static_cast<int>(e);
         }
+        // the main arrays are complete once the last view in front of the tail has been added: the caller's event
+        // fires here, in the middle of the batch (the reduces are chained in view order)
+        if (split && split->event && v == first_tail - 1) {
+            e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(split->event), st);
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+    }
+    if (split && split->event && (first_tail <= 0 || first_tail > n_views)) {   // no view in front of the tail
+        e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(split->event), main_st);
+        if (e != cudaSuccess) return static_cast<int>(e);
     }
     for (int l = 1; l < lanes; ++l) {
         e = cudaEventRecord(ctx->ev_done[l], ctx->side[l]);

@@ -218,21 +218,35 @@ class NativeViewBatch:
         most = int(self.totals_np[: self.V].max()) if self.V else 0
         self._arenas(most + most // 10 + 4096)
 
-    def step(self, g_mean, g_lam, g_opac, g_l, loss=None):
+    def step(self, g_mean, g_lam, g_opac, g_l, loss=None, tail=None):
         """Enqueue render + loss gradient + backward of all views on the current stream; the views' gradients are
         ADDED into g_mean f32[*,2], g_lam f32[*,4], g_opac f32[*], g_l f32[*,3] (rows = desc.index).  Returns at
-        once; call finish() after synchronising."""
+        once; call finish() after synchronising.
+
+        tail = (first_tail_view, (t_mean, t_lam, t_opac, t_l), event): the views from first_tail_view on add into
+        the second set of arrays, and `event` (a torch.cuda.Event that has been recorded at least once, or None) is
+        recorded as soon as the main arrays are complete — the caller's all-reduce of the main bucket can start
+        there, beside the tail views (gcp_views_step_split)."""
+        import ctypes
+
         from . import _lib
 
         if not self.pairs:
             self.size()
+        split = None
+        if tail is not None:
+            first, arrays, event = tail
+            split = _lib.ViewsSplit(int(first), arrays[0].data_ptr(), arrays[1].data_ptr(), arrays[2].data_ptr(),
+                                    arrays[3].data_ptr(), event.cuda_event if event is not None else None)
         with torch.cuda.device(self.dev):
             stream = torch.cuda.current_stream(self.dev).cuda_stream
-            _lib.check(self.L.gcp_views_step(self.ctx, self.desc, self.V, self.W, self.H, self._plan_ptrs, self.plan_bytes,
-                                             self._pair_ptrs, self.pair_bytes, self.cap, g_mean.data_ptr(),
-                                             g_lam.data_ptr(), g_opac.data_ptr(), g_l.data_ptr(),
-                                             loss.data_ptr() if loss is not None else None, self.totals.data_ptr(),
-                                             stream), "gcp_views_step")
+            _lib.check(self.L.gcp_views_step_split(self.ctx, self.desc, self.V, self.W, self.H, self._plan_ptrs,
+                                                   self.plan_bytes, self._pair_ptrs, self.pair_bytes, self.cap,
+                                                   g_mean.data_ptr(), g_lam.data_ptr(), g_opac.data_ptr(),
+                                                   g_l.data_ptr(), loss.data_ptr() if loss is not None else None,
+                                                   self.totals.data_ptr(),
+                                                   ctypes.byref(split) if split is not None else None, stream),
+                       "gcp_views_step_split")
         self.launches = int(self.L.gcp_view_last_launch_count())
 
     def finish(self) -> bool:

@@ -114,3 +114,57 @@ def test_native_batch_with_an_empty_view_gpu():
     for a, b in zip(got, want):
         assert torch.equal(a, b)
     assert float(batch.images[1].abs().sum()) == 0.0     # a view without Gaussians is a black image
+
+
+def test_tail_split_and_rank_shards_sum_to_the_single_batch_gpu():
+    """(a) gcp_views_step_split: the views in front of the tail add into the main arrays, the tail into its own, the
+    event in between fires; main + tail equals the unsplit batch up to the order of the final addition.
+    (b) C5 parity (BASELINE.json configs[4]): the buckets of two 'ranks' (views 0,2,4 / 1,3,5: views_for_rank) summed
+    — what the all-reduce computes — equal the bucket one rank builds from all six views, to fp32 rounding."""
+    from simplegaussiansplat_tk71_b200.views import NativeViewBatch, views_for_rank
+
+    W, H, n_param = 320, 200, 20_000
+    views = _scene(6, W, H, n_param, seed0=120)
+    gIs = [torch.rand(H + 1, W + 1, 3, device="cuda") + 0.1 for _ in views]
+    shapes = ((n_param, 2), (n_param, 4), (n_param,), (n_param, 3))
+    zeros = lambda: [torch.zeros(s, device="cuda") for s in shapes]  # noqa: E731
+
+    whole = zeros()
+    b = NativeViewBatch(views, W, H, grad_images=gIs, lanes=3)
+    b.step(*whole)
+    torch.cuda.synchronize()
+    assert b.finish()
+
+    main, tail = zeros(), zeros()
+    ev = torch.cuda.Event()
+    ev.record()
+    side = torch.cuda.Stream()
+    b.step(*main, tail=(4, tail, ev))
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        snapshot = [t.clone() for t in main]        # what an all-reduce started on the event would read
+    torch.cuda.synchronize()
+    assert b.finish()
+    head = zeros()
+    b4 = NativeViewBatch(views[:4], W, H, grad_images=gIs[:4], lanes=3)
+    b4.step(*head)
+    torch.cuda.synchronize()
+    for a, s_, h in zip(main, snapshot, head):
+        assert torch.equal(a, h) and torch.equal(s_, h)        # complete at the event, untouched by the tail
+    for w, a, t in zip(whole, main, tail):
+        assert float(t.abs().max()) > 0
+        scale = float(w.abs().max())
+        assert torch.allclose(a + t, w, rtol=1e-5, atol=1e-6 * max(scale, 1.0))
+
+    ranks = []
+    for r in range(2):
+        mine = views_for_rank(len(views), r, 2)
+        acc = zeros()
+        br = NativeViewBatch([views[i] for i in mine], W, H, grad_images=[gIs[i] for i in mine], lanes=2)
+        br.step(*acc)
+        torch.cuda.synchronize()
+        assert br.finish()
+        ranks.append(acc)
+    for w, a, c in zip(whole, ranks[0], ranks[1]):
+        scale = float(w.abs().max())
+        assert torch.allclose(a + c, w, rtol=1e-5, atol=1e-6 * max(scale, 1.0))
