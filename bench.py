@@ -309,7 +309,13 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps + 1)]
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    # the timed region itself lasts a few milliseconds, the sampler ticks every 100 ms: the same step runs untimed
+    # for ~0.4 s in front of it, so that the clocks line describes the GPU under THIS load, not an idle one
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.4:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     barrier()
     ev[0].record()
     for i in range(args.steps):
