@@ -23,6 +23,24 @@ def views_for_rank(num_views: int, rank: int, world: int) -> list:
     return list(range(rank, num_views, world))
 
 
+def views_for_rank_balanced(costs, rank: int, world: int) -> list:
+    """Cost-aware ownership: every rank computes the same assignment from the same per-view costs (e.g. the pair
+    counts `NativeViewBatch.totals_np` of the previous step): views in order of decreasing cost, each to the rank
+    with the least work so far (ties to the lower rank).  The step of a data-parallel batch ends with the slowest
+    rank; with round-robin the ranks' totals differ by the spread of 64/world random views."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    order = sorted(range(len(costs)), key=lambda v: (-float(costs[v]), v))
+    load = [0.0] * world
+    mine = []
+    for v in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += float(costs[v])
+        if r == rank:
+            mine.append(v)
+    return sorted(mine)
+
+
 def aggregate_throughput(elements_local: float, ms_local: float, device=None):
     """(total elements over ranks, max time over ranks).  Works on nccl (cuda tensors) and gloo (cpu)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

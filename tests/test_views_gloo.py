@@ -60,3 +60,19 @@ def test_views_for_rank_covers_all_views_once():
     for world in (1, 2, 4, 8):
         seen = sorted(v for r in range(world) for v in views.views_for_rank(64, r, world))
         assert seen == list(range(64))
+
+
+def test_balanced_view_ownership_is_a_partition_and_evens_out_the_load():
+    import random
+
+    from simplegaussiansplat_tk71_b200 import views
+
+    rnd = random.Random(5)
+    costs = [rnd.lognormvariate(0.0, 0.6) for _ in range(64)]
+    for world in (1, 2, 3, 8):
+        parts = [views.views_for_rank_balanced(costs, r, world) for r in range(world)]
+        assert sorted(v for p in parts for v in p) == list(range(64))
+        loads = [sum(costs[v] for v in p) for p in parts]
+        rr = [sum(costs[v] for v in views.views_for_rank(64, r, world)) for r in range(world)]
+        assert max(loads) <= max(rr) + 1e-12          # never worse than round-robin on the slowest rank
+        assert max(loads) - min(loads) <= max(costs) + 1e-12
