@@ -121,12 +121,13 @@ def _totals_to_host(totals, dev):
 # pair list, T checkpoints, piece state, gradient partials).  Both come from per-(device, stream) free lists and
 # go back when the view's autograd state is dropped, so a training loop allocates them once.
 class _PlanArena:
-    __slots__ = ("buf", "totals", "totals_np")
+    __slots__ = ("buf", "totals", "totals_np", "busy")
 
     def __init__(self, dev, nbytes):
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.totals = torch.zeros(2, dtype=torch.int64).pin_memory()   # [0] = pair count: the plan kernel writes here
         self.totals_np = self.totals.numpy()
+        self.busy = None    # event behind the last one-call forward that used this arena (see _forward_speculative)
 
 
 class _PairArena:
@@ -340,10 +341,17 @@ def _forward_speculative(L, v, dev, startpoint, endpoint, mean_, lam_, opac_, l_
     free.remove(pairs)
     v.plan = _take_plan_arena(L, dev, n, W, H)
     v.pairs = pairs
+    # The pinned count word is written by the DEVICE, asynchronously: a plan kernel of the arena's previous view that
+    # is still queued (a host running ahead of the device, e.g. a no_grad render loop) would drop ITS count there
+    # after the host has reset the word.  The previous one-call forward on this arena must have finished first.
+    if v.plan.busy is not None:
+        v.plan.busy.synchronize()
     v.plan.totals_np[0] = -1
     _lib.check(L.gcp_view_forward(_p(sp), _p(ep), _p(mean_), _p(lam_), _p(opac_), _p(l_), n, W, H, _p(v.plan.buf),
                                   v.plan.buf.numel(), _p(pairs.buf), pairs.buf.numel(), pairs.cap, 1 if keep else 0,
                                   _p(image), _p(v.plan.totals), cur.cuda_stream), "gcp_view_forward")
+    v.plan.busy = torch.cuda.Event()
+    v.plan.busy.record(cur)
     # the count arrives a few microseconds after the plan's scan kernel: poll the pinned word, fall back to a sync
     t0 = time.perf_counter()
     while v.plan.totals_np[0] < 0:
@@ -361,6 +369,8 @@ def _forward_speculative(L, v, dev, startpoint, endpoint, mean_, lam_, opac_, l_
     _lib.check(L.gcp_view_forward(_p(sp), _p(ep), _p(mean_), _p(lam_), _p(opac_), _p(l_), n, W, H, _p(v.plan.buf),
                                   v.plan.buf.numel(), _p(v.pairs.buf), v.pairs.buf.numel(), v.pairs.cap,
                                   1 if keep else 0, _p(image), _p(v.plan.totals), cur.cuda_stream), "gcp_view_forward")
+    v.plan.busy = torch.cuda.Event()
+    v.plan.busy.record(cur)
     return True
 
 

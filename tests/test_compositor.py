@@ -684,3 +684,36 @@ def test_backward_is_linear_in_grad_image_at_full_size_gpu(monkeypatch):
         err = (x12.double() - want).abs()
         frac_bad = float((err > bound).double().mean())
         assert frac_bad < 1e-3, (name, frac_bad, float((err / bound).max()))
+
+
+@pytest.mark.gpu
+def test_speculative_forward_in_an_unsynchronised_render_loop_gpu(monkeypatch):
+    """A no_grad render loop never synchronises and drops every view's arenas at once, so the host runs views ahead
+    of the device and the pooled arenas (with their pinned pair-count word) are reused while earlier plan kernels
+    are still queued: every image must still be the one of its own view (sizes alternate, so a count read from the
+    wrong view would overflow or mis-size the arena)."""
+    from simplegaussiansplat_tk71_b200 import compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    views = [wl.splat_view_device(640, 360, n, seed=200 + i, device="cuda")
+             for i, n in enumerate((3_000, 90_000, 6_000, 120_000, 2_000, 60_000))]
+
+    def render(v):
+        with torch.no_grad():
+            return F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity,
+                           v.l_d, v.width, v.height)
+
+    monkeypatch.setattr(compositor, "SPECULATE", False)
+    want = []
+    for v in views:
+        want.append(render(v).clone())
+        torch.cuda.synchronize()
+    monkeypatch.setattr(compositor, "SPECULATE", True)
+    compositor._free_pair.clear()
+    compositor._free_plan.clear()
+    for rep in range(3):
+        got = [render(v) for v in views]            # no synchronisation in between
+        torch.cuda.synchronize()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), rep
