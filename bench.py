@@ -311,29 +311,40 @@ def main():
     sampler.start()
     time.sleep(0.1)
     barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        if flush is not None:
+    if flush is None:
+        # two events per step (step boundary, forward | backward): every record between two kernels costs ~4 us
+        # of device idle, so no more of them than the per-kernel durations of the roofline need
+        ev[0].record()
+        for i in range(args.steps):
+            gc.grouped_cumprod_forward(e.x, e.key, y)
+            ev[2 * i + 1].record()
+            gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
+            ev[2 * i + 2].record()
+        barrier()
+        fwd_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+        bwd_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+        total_ms = ev[0].elapsed_time(ev[2 * args.steps])          # the whole bracket: K back-to-back steps
+    else:
+        ev[0].record()
+        for i in range(args.steps):
             flush.fill_(1.0)
-        ev[4 * i + 1].record()
-        gc.grouped_cumprod_forward(e.x, e.key, y)
-        ev[4 * i + 2].record()
-        if flush is not None:
+            ev[4 * i + 1].record()
+            gc.grouped_cumprod_forward(e.x, e.key, y)
+            ev[4 * i + 2].record()
             flush.fill_(2.0)
-        ev[4 * i + 3].record()
-        gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
-        ev[4 * i + 4].record()
-    barrier()
-    fwd_ms = sum(ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps)) / args.steps
-    bwd_ms = sum(ev[4 * i + 3].elapsed_time(ev[4 * i + 4]) for i in range(args.steps)) / args.steps
-    # no flush: the whole bracket (K back-to-back steps); with the flush: the ops' own event pairs
-    total_ms = ev[0].elapsed_time(ev[-1]) if flush is None else (fwd_ms + bwd_ms) * args.steps
+            ev[4 * i + 3].record()
+            gc.grouped_cumprod_backward(e.x, y, e.grad_out, e.inv, gin, e.seg_end)
+            ev[4 * i + 4].record()
+        barrier()
+        fwd_ms = sum(ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps)) / args.steps
+        bwd_ms = sum(ev[4 * i + 3].elapsed_time(ev[4 * i + 4]) for i in range(args.steps)) / args.steps
+        total_ms = (fwd_ms + bwd_ms) * args.steps                   # the ops' own event pairs (flush excluded)
     time.sleep(0.05)
     clocks = sampler.stop()
-    # The timed region above is K steps = a few milliseconds: a BURST, like the copy MEASURED_PEAKS.json's hbm_gbs
-    # was taken from (best of 10), and too short for more than a sample or two of the clocks.  The same step run
-    # back to back for half a second is the SUSTAINED figure, with its own clock samples: on this pool the GPU then
-    # sits at its software power cap (sm ~1830 of 1965 MHz) and the step is ~3 % slower.
+    # The timed region above is K steps = a few milliseconds, too short for more than a few samples of the clocks.
+    # The same step run back to back for half a second, no events inside, is reported beside it with its own clock
+    # samples (`sustained`): the GPU then touches its software power cap, and the step is still a little FASTER than
+    # in the timed region, because nothing separates the kernels.
     sustained = None
     if flush is None:
         s2 = ClockSampler(local)
