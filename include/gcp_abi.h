@@ -44,6 +44,9 @@ extern "C" {
                                   * workspace is poisoned until re-initialised (gcp_workspace_status / the attached flag) */
 #define GCP_ERR_SEGMENTS (-4)    /* inv / seg_end inconsistent (gcp_validate_segments) */
 
+/* elements per call of the three scan ops (int32 indexing like the reference, minus the alignment peel) */
+#define GCP_MAX_ELEMENTS 2147483644LL
+
 /* opaque: a cudaStream_t */
 typedef void *gcp_stream_t;
 
@@ -77,8 +80,10 @@ int gcp_workspace_selftest_abort(void *ws, size_t ws_bytes, gcp_stream_t stream)
  *   (/root/reference/cuda_kernel/grouped_cumprod_forward.cu:6-24):
  *   y[i] = x[i]              if i == 0 or key[i] != key[i-1]
  *        = y[i-1] * x[i]     otherwise                       (inclusive)
- * x f32[n], key i32[n], y f32[n] (written in place).  n may be 0; at most 2^31 - 4 (the reference ops index with
- * int, grouped_cumprod_backward.cu:52; callers with more elements per view chunk at segment boundaries).
+ * x f32[n], key i32[n], y f32[n] (written in place).  n may be 0; at most GCP_MAX_ELEMENTS = 2^31 - 4 per call
+ * (the reference ops index with int, grouped_cumprod_backward.cu:52; more is GCP_ERR_INVALID_ARG).  Longer arrays
+ * are cut at segment boundaries into independent calls — ops.py does that (the counterpart of the reference's
+ * chunk loop, gs_model.py:428, :675; no per-pixel carry is needed because no segment is ever split).
  * Any 4-byte alignment.  The fast path (one persistent kernel, cooperative launch, TMA) needs x and key in the
  * SAME 16-byte phase — true for equal slices of separately allocated tensors, the reference's [cutting_number:]
  * case — and peels the 1-3 leading elements; other layouts, n below one tile, or a device that refuses the

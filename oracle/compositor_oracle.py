@@ -14,6 +14,15 @@ import numpy as np
 from . import oracle as orc
 
 
+def _scatter_sum(index, values, size):
+    """out[index[i]] += values[i] in element order (what np.add.at does, column by column through np.bincount:
+    the same sequential fp64 sums, ~20x faster)."""
+    values = np.asarray(values, dtype=np.float64)
+    if values.ndim == 1:
+        return np.bincount(index, weights=values, minlength=size)
+    return np.stack([np.bincount(index, weights=values[:, k], minlength=size) for k in range(values.shape[1])], 1)
+
+
 def expand(boxsize, sp, ep):
     """make_rect_points_parallel (uitility.py:336-366): element order = Gaussian-major, row-major inside a box."""
     boxsize = np.asarray(boxsize, dtype=np.int64)
@@ -58,8 +67,7 @@ def forward(boxsize, sp, ep, mean, lam, opac, l_d, W, H):
     T = T_s[inv_order]
     alive = alive_s[inv_order]
     p = np.where(alive[:, None], T[:, None] * l * (o * g)[:, None], 0.0)   # :500
-    image = np.zeros((H + 1, W + 1, 3))
-    np.add.at(image, (py, px), p)                      # :510-514
+    image = _scatter_sum(py * (W + 1) + px, p, (H + 1) * (W + 1)).reshape(H + 1, W + 1, 3)   # :510-514
     cache = dict(gid=gid, px=px, py=py, o=o, l=l, g=g, x=x, d0=d0, d1=d1, L=L, key=key, order=order,
                  inv_order=inv_order, alive=alive, p=p, n=len(boxsize))
     return image, cache
@@ -84,8 +92,8 @@ def backward(cache, grad_image, scales=False):
     # use fp64 directly for the oracle: segment totals
     head = np.r_[True, ks[1:] != ks[:-1]]
     seg = np.cumsum(head) - 1
-    tot = np.zeros(seg[-1] + 1 if seg.size else 0)
-    np.add.at(tot, seg, ds)
+    nseg = int(seg[-1]) + 1 if seg.size else 0
+    tot = _scatter_sum(seg, ds, nseg)
     pref = np.zeros_like(ds)
     # inclusive prefix in fp64
     csum = np.cumsum(ds)
@@ -106,17 +114,14 @@ def backward(cache, grad_image, scales=False):
     gL = coefL[:, None] * dd
     n = c["n"]
     gid = c["gid"]
-    out_m = np.zeros((n, 2)); np.add.at(out_m, gid, gm)
-    out_L = np.zeros((n, 4)); np.add.at(out_L, gid, gL)
-    out_o = np.zeros((n, 1)); np.add.at(out_o, gid, go[:, None])
-    out_l = np.zeros((n, 3)); np.add.at(out_l, gid, gl)
+    out_m, out_L = _scatter_sum(gid, gm, n), _scatter_sum(gid, gL, n)
+    out_o, out_l = _scatter_sum(gid, go[:, None], n), _scatter_sum(gid, gl, n)
     del incl
     if not scales:
         return out_m, out_L.reshape(n, 2, 2), out_o, out_l
     d_abs = np.where(alive, (np.abs(pg) * np.abs(c["p"])).sum(1), 0.0)
     das = d_abs[order]
-    tot_a = np.zeros_like(tot)
-    np.add.at(tot_a, seg, das)
+    tot_a = _scatter_sum(seg, das, nseg)
     csum_a = np.cumsum(das)
     s_abs = (tot_a[seg] - (csum_a - np.r_[0.0, csum_a[:-1]][head][seg]))[inv_order]
     s_abs = np.maximum(s_abs, 0.0)
@@ -125,18 +130,15 @@ def backward(cache, grad_image, scales=False):
     coef_a = np.where(alive, ((np.abs(o) * g) / np.abs(xsafe)) * s_abs + d_abs, 0.0)
     gm_a = np.stack((coef_a * np.abs(X0), coef_a * np.abs(X1)), 1)
     gL_a = 0.5 * coef_a[:, None] * np.abs(dd)
-    sc_m = np.zeros((n, 2)); np.add.at(sc_m, gid, gm_a)
-    sc_L = np.zeros((n, 4)); np.add.at(sc_L, gid, gL_a)
-    sc_o = np.zeros((n, 1)); np.add.at(sc_o, gid, go_a[:, None])
-    sc_l = np.zeros((n, 3)); np.add.at(sc_l, gid, gl_a)
+    sc_m, sc_L = _scatter_sum(gid, gm_a, n), _scatter_sum(gid, gL_a, n)
+    sc_o, sc_l = _scatter_sum(gid, go_a[:, None], n), _scatter_sum(gid, gl_a, n)
     return (out_m, out_L.reshape(n, 2, 2), out_o, out_l), (sc_m, sc_L.reshape(n, 2, 2), sc_o, sc_l)
 
 
 def image_scale(cache, W, H):
     """Sum of |terms| of every pixel colour (equals the image where all colours are positive)."""
-    sc = np.zeros((H + 1, W + 1, 3))
-    np.add.at(sc, (cache["py"], cache["px"]), np.abs(cache["p"]))
-    return sc
+    return _scatter_sum(cache["py"] * (W + 1) + cache["px"], np.abs(cache["p"]),
+                        (H + 1) * (W + 1)).reshape(H + 1, W + 1, 3)
 
 
 def error_table(got, ref, scales, rtol=1e-5, atol=1e-6):

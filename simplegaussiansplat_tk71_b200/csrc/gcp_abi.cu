@@ -213,7 +213,8 @@ template <int OP>
 int dispatch_fwd(const float *x, const int32_t *key, float *y, int64_t n, void *wsp, size_t ws_bytes,
                  gcp_stream_t stream) {
     t_launches = 0;
-    if (n < 0 || (n > 0 && (x == nullptr || key == nullptr || y == nullptr))) return GCP_ERR_INVALID_ARG;
+    if (n < 0 || n > GCP_MAX_ELEMENTS || (n > 0 && (x == nullptr || key == nullptr || y == nullptr)))
+        return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;
     Ws ws;
     int rc = check_ws(wsp, ws_bytes, n, &ws);
@@ -350,7 +351,7 @@ int gcp_cumprod_bwd_f32(const float *x, const float *y, const float *gout, const
                         gcp_stream_t stream) {
     t_launches = 0;
     (void)seg_end;  // implied by inv (tail <=> inv[i+1] != inv[i]); see gcp_validate_segments
-    if (n < 0 || k < 0) return GCP_ERR_INVALID_ARG;
+    if (n < 0 || n > GCP_MAX_ELEMENTS || k < 0) return GCP_ERR_INVALID_ARG;
     if (n > 0 && (x == nullptr || y == nullptr || gout == nullptr || inv == nullptr || gin == nullptr))
         return GCP_ERR_INVALID_ARG;
     if (n == 0) return GCP_OK;

@@ -23,6 +23,7 @@ import torch
 from . import _lib
 
 _workspaces: dict = {}
+MAX_ELEMENTS = 2 ** 31 - 4   # GCP_MAX_ELEMENTS (include/gcp_abi.h): elements per call of the C ABI
 _VALIDATE = os.environ.get("GCP_VALIDATE_SEGMENTS", "") not in ("", "0")
 
 
@@ -96,6 +97,34 @@ def _check(t: torch.Tensor, name: str, dtype: torch.dtype, n: int | None = None,
         raise RuntimeError(f"{name} is on {t.device}, expected {device}")
 
 
+def segment_cuts(ids: torch.Tensor, limit: int | None = None) -> list:
+    """[0, c1, ..., n]: cut points of an array longer than one call of the C ABI takes, every inner one at a segment
+    boundary (ids[c] != ids[c-1]) and at most `limit` elements after the one before.
+
+    The counterpart of the reference's chunk loop (gs_model.py:428, :675, chunks of 2**29 elements made by
+    uitility.py:478-488) for the int32-indexed ops: because no segment is split, the chunks are independent calls
+    and nothing like the per-pixel carry of gs_model.py:582-594 is needed.  One small host sync per cut (the
+    position of a boundary); arrays of up to `limit` elements return [0, n] without touching the device."""
+    limit = MAX_ELEMENTS if limit is None else int(limit)
+    n = ids.numel()
+    cuts = [0]
+    while n - cuts[-1] > limit:
+        hi = cuts[-1] + limit            # the next cut is the last boundary at or below hi
+        window, cut = 1 << 16, None
+        while cut is None:
+            lo = max(cuts[-1] + 1, hi - window)
+            w = ids[lo - 1:hi + 1]
+            at = (w[1:] != w[:-1]).nonzero()
+            if at.numel():
+                cut = lo + int(at[-1])
+            elif lo == cuts[-1] + 1:
+                raise RuntimeError(f"a segment of more than {limit} elements cannot be cut at a segment boundary")
+            window *= 16
+        cuts.append(cut)
+    cuts.append(n)
+    return cuts
+
+
 def _scan(fn_name: str, x: torch.Tensor, key: torch.Tensor, y: torch.Tensor) -> None:
     _check(x, "x", torch.float32)
     n = x.numel()
@@ -104,9 +133,12 @@ def _scan(fn_name: str, x: torch.Tensor, key: torch.Tensor, y: torch.Tensor) -> 
     if n == 0:
         return
     with torch.cuda.device(x.device):
-        ws, stream = _workspace(x.device, n)
+        cuts = segment_cuts(key) if n > MAX_ELEMENTS else [0, n]
+        ws, stream = _workspace(x.device, max(b - a for a, b in zip(cuts, cuts[1:])))
         fn = getattr(_lib.lib(), fn_name)
-        _lib.check(fn(x.data_ptr(), key.data_ptr(), y.data_ptr(), n, ws.data_ptr(), ws.numel(), stream), fn_name)
+        for a, b in zip(cuts, cuts[1:]):
+            _lib.check(fn(x.data_ptr() + 4 * a, key.data_ptr() + 4 * a, y.data_ptr() + 4 * a, b - a, ws.data_ptr(),
+                          ws.numel(), stream), fn_name)
 
 
 def grouped_cumprod_forward(x: torch.Tensor, key: torch.Tensor, y: torch.Tensor) -> None:
@@ -137,6 +169,9 @@ def grouped_cumprod_backward(param: torch.Tensor, param_cumprod: torch.Tensor, g
     call with a non-empty `inv_len` checked first (`validate_segments`, one extra pass and a host sync) and
     raise GCP_ERR_SEGMENTS on a mismatch.  An empty `inv_len` is accepted: the compositor passes the sorted pixel
     keys as `inv`, for which no offsets exist.
+
+    More than MAX_ELEMENTS = 2**31 - 4 elements (beyond what the reference's int-indexed kernel can address) are
+    served as independent calls on chunks cut at segment boundaries (`segment_cuts`).
     """
     _check(param, "param", torch.float32)
     n = param.numel()
@@ -149,16 +184,20 @@ def grouped_cumprod_backward(param: torch.Tensor, param_cumprod: torch.Tensor, g
     if n == 0:
         return
     if _VALIDATE and inv_len.numel() > 0:
+        if n > MAX_ELEMENTS:
+            raise RuntimeError("GCP_VALIDATE_SEGMENTS checks arrays of up to 2**31 - 4 elements")
         bad = validate_segments(inv, inv_len)
         if bad:
             raise RuntimeError(f"GCP_ERR_SEGMENTS: inv / inv_len are inconsistent at {bad} positions")
     with torch.cuda.device(dev):
-        ws, stream = _workspace(dev, n)
+        cuts = segment_cuts(inv) if n > MAX_ELEMENTS else [0, n]
+        ws, stream = _workspace(dev, max(b - a for a, b in zip(cuts, cuts[1:])))
         L = _lib.lib()
-        _lib.check(L.gcp_cumprod_bwd_f32(param.data_ptr(), param_cumprod.data_ptr(), grad_out.data_ptr(),
-                                         inv.data_ptr(), inv_len.data_ptr(), grad_in.data_ptr(), n,
-                                         inv_len.numel(), ws.data_ptr(), ws.numel(), stream),
-                   "gcp_cumprod_bwd_f32")
+        for a, b in zip(cuts, cuts[1:]):
+            _lib.check(L.gcp_cumprod_bwd_f32(param.data_ptr() + 4 * a, param_cumprod.data_ptr() + 4 * a,
+                                             grad_out.data_ptr() + 4 * a, inv.data_ptr() + 4 * a, inv_len.data_ptr(),
+                                             grad_in.data_ptr() + 4 * a, b - a, inv_len.numel(), ws.data_ptr(),
+                                             ws.numel(), stream), "gcp_cumprod_bwd_f32")
 
 
 def validate_segments(inv: torch.Tensor, inv_len: torch.Tensor) -> int:

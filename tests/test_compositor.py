@@ -717,3 +717,70 @@ def test_speculative_forward_in_an_unsynchronised_render_loop_gpu(monkeypatch):
         torch.cuda.synchronize()
         for a, b in zip(got, want):
             assert torch.equal(a, b), rep
+
+
+def _deep_view(W=2047, H=2047, n=535_000, half=32, seed=231):
+    """A view of MORE THAN 2**31 elements: n boxes of (2 half + 1)^2 pixels, all inside the image, ~520 Gaussians
+    over every pixel, opacities small enough that T is still ~0.2 at the end of a list."""
+    rng = np.random.default_rng(seed)
+    cx = rng.integers(half, W - half + 1, n)
+    cy = rng.integers(half, H - half + 1, n)
+    sp = np.stack((cx - half, cy - half), 1).astype(np.int32)
+    ep = np.stack((cx + half, cy + half), 1).astype(np.int32)
+    mean = (np.stack((cx, cy), 1) + rng.uniform(-0.5, 0.5, (n, 2))).astype(np.float32)
+    s0, s1 = rng.uniform(8.0, 16.0, n), rng.uniform(8.0, 16.0, n)
+    rho = rng.uniform(-0.4, 0.4, n)
+    det = (s0 * s1) ** 2 * (1 - rho ** 2)
+    lam = np.stack((s1 ** 2 / det, -rho * s0 * s1 / det, -rho * s0 * s1 / det, s0 ** 2 / det), 1).reshape(n, 2, 2)
+    boxsize = np.full(n, (2 * half + 1) ** 2, dtype=np.int64)
+    return dict(boxsize=boxsize, sp=sp, ep=ep, mean=mean, lam=lam.astype(np.float32),
+                opac=rng.uniform(0.002, 0.02, (n, 1)).astype(np.float32),
+                l_d=rng.uniform(0.2, 1.0, (n, 3)).astype(np.float32), W=W, H=H)
+
+
+def _sub_scene(case, j):
+    """Everything the outputs of Gaussian j depend on: the Gaussians whose boxes meet box j, in depth order, with
+    their boxes clipped to box j (the pixel lists inside box j are complete, nothing outside it matters to j)."""
+    sp, ep = case["sp"], case["ep"]
+    hit = np.flatnonzero((sp[:, 0] <= ep[j, 0]) & (ep[:, 0] >= sp[j, 0]) & (sp[:, 1] <= ep[j, 1]) & (ep[:, 1] >= sp[j, 1]))
+    sps, eps = np.maximum(sp[hit], sp[j]), np.minimum(ep[hit], ep[j])
+    sub = dict(boxsize=((eps[:, 0] - sps[:, 0] + 1).astype(np.int64) * (eps[:, 1] - sps[:, 1] + 1)), sp=sps, ep=eps,
+               mean=case["mean"][hit], lam=case["lam"][hit], opac=case["opac"][hit], l_d=case["l_d"][hit],
+               W=case["W"], H=case["H"], grad_image=case["grad_image"])
+    return sub, int(np.searchsorted(hit, j))
+
+
+@pytest.mark.gpu
+def test_a_view_of_more_than_2_31_elements_is_one_pass_gpu(monkeypatch):
+    """Row a6 (gs_model.py:428, :582-594, :611-615, :726-730): the reference cuts a view into chunks of 2**29 elements
+    and carries T per pixel between them; the tile route never forms elements, so a view of 2.26e9 elements (more
+    than any int32-indexed op could take) is ONE pass.  Checked at the north star's tolerance against the fp64
+    oracle on complete sub-scenes: for three Gaussians (front, middle, back of the depth order) the image over the
+    Gaussian's box and its four gradients depend only on the Gaussians meeting that box — the oracle evaluates
+    exactly those.  The list route (int32 element indices, like the reference's ops) refuses the view."""
+    from simplegaussiansplat_tk71_b200 import compositor
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    case = _deep_view()
+    n = case["boxsize"].size
+    assert int(case["boxsize"].sum()) > 2 ** 31
+    rng = np.random.default_rng(5)
+    case["grad_image"] = rng.uniform(0.1, 1.0, (case["H"] + 1, case["W"] + 1, 3)).astype(np.float32)
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    img, g_mean, g_lam, g_opac, g_l = _run(case, "cuda")
+    assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() > 0.5
+    for j in (3, n // 2, n - 2):
+        sub, k = _sub_scene(case, j)
+        (ref_img, ref_m, ref_L, ref_o, ref_l), (sc_img, sc_m, sc_L, sc_o, sc_l) = _oracle(sub)
+        (x0, y0), (x1, y1) = case["sp"][j], case["ep"][j]
+        box = np.s_[y0:y1 + 1, x0:x1 + 1]
+        for name, a, b, sc in (("image", img[box], ref_img[box], sc_img[box]),
+                               ("grad_mean", g_mean[j], ref_m[k], sc_m[k]), ("grad_lambda", g_lam[j], ref_L[k], sc_L[k]),
+                               ("grad_opacity", g_opac[j], ref_o[k], sc_o[k]), ("grad_l", g_l[j], ref_l[k], sc_l[k])):
+            a = np.asarray(a, np.float64).reshape(b.shape)
+            bound = ATOL + RTOL * np.asarray(sc).reshape(b.shape)
+            err = np.abs(a - b)
+            assert np.all(err <= bound), (j, name, float((err / bound).max()), float(err.max()))
+    monkeypatch.setattr(compositor, "ROUTE", "lists")
+    with pytest.raises(RuntimeError, match="2\\*\\*31"):
+        _run(case, "cuda")
