@@ -292,15 +292,20 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
  * Inputs: sp/ep i32[n,2] (8-byte aligned), mean f32[n,2], lam f32[n,4], opac f32[n], l_d f32[n,3] (any 4-byte
  * alignment), grad_image / image f32[(H+1)*(W+1)*3].  image is written completely (no need to zero it); so are
  * g_mean[n,2], g_lam[n,4], g_opac[n], g_l[n,3] (d_l = (sum d)/l, gs_model.py:763-766).  keep = 0: a render no
- * backward will follow (no checkpoints are written).  n < 2^31 - 64, pairs < 2^31 - 64 per view: more Gaussians
- * than that are rendered by the caller in depth-ordered chunks with the reference's per-pixel carry
- * (gs_model.py:582-594; compositor.py does that).
+ * backward will follow (no checkpoints are written).  n < 2^31 - 64, pairs < 2^31 - 64 per view, any number of
+ * ELEMENTS (the reference's 2^29-element chunks and their per-pixel carry, gs_model.py:428, :582-594, have no
+ * counterpart: a view is one pass); the arenas of a view at that limit would exceed 100 GB, compositor.py raises.
+ * Binning (gcp_tile_set_binning): 1 (default) = the Gaussian-major pair list is put in tile order by a stable
+ * radix sort on the tile id (no atomics, nothing to sort afterwards); 0 = a slot per pair from an atomic counter
+ * per tile, then every tile's list sorted by Gaussian id.  Same pair list, bit for bit.
  * ------------------------------------------------------------------------------------------------ */
 int gcp_tile_width(void);
 int gcp_tile_height(void);
 int gcp_tile_num_tiles(int W, int H);
 int gcp_tile_set_piece_pairs(int pairs);   /* tuning / tests: multiple of 32 */
 int gcp_tile_piece_pairs(void);
+int gcp_tile_set_binning(int mode);        /* tuning / tests: 0 or 1 */
+int gcp_tile_binning(void);
 size_t gcp_view_plan_bytes(int64_t n, int W, int H);
 size_t gcp_view_pair_bytes(int64_t pair_cap, int W, int H);
 int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, void *plan, size_t plan_bytes,

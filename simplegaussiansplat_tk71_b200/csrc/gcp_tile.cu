@@ -62,7 +62,9 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 // ---- arena headers (u32 words; zeroed by gcp_view_plan) ----
 constexpr int H_TICKET_S1 = 0, H_TICKET_S2 = 1, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4, H_NLONG = 5;
 constexpr int H_TICKET_BWD = 6, H_NBIG = 7, H_TICKET_RED = 8;   // adjacent u32 words: reset together by every backward
+constexpr int H_TICKET_BIN = 10;                // .. 12: scan tickets of the (up to three) radix passes of the binning
 constexpr int H_P64 = 8, H_T64 = 9;             // u64 indices (bytes 64 / 72): pair count; the tile scan's total (= it)
+constexpr int H_B64 = 12;                       // u64 index (byte 96): sink for the totals of the radix passes' scans
 constexpr int HDR_WORDS = 64;
 
 // box of Gaussian g clipped to the image [0,W] x [0,H] (the caller clamps already, gs_model.py:419-425)
@@ -92,29 +94,41 @@ constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
 
 __global__ void __launch_bounds__(256)
 k_view_cnt(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t n, int W, int H,
-           int32_t *__restrict__ cnt) {
+           int32_t *__restrict__ cnt, int2 *__restrict__ tbox) {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const Box b = clip_box(sp, ep, g, W, H);
+    const int tx0 = b.sx >> TSX, ty0 = b.sy >> TSY, nx = (b.ex >> TSX) - tx0 + 1;
     int c = 0;
-    if (b.ex >= b.sx && b.ey >= b.sy) c = ((b.ex >> TSX) - (b.sx >> TSX) + 1) * ((b.ey >> TSY) - (b.sy >> TSY) + 1);
+    if (b.ex >= b.sx && b.ey >= b.sy) c = nx * ((b.ey >> TSY) - ty0 + 1);
     cnt[g] = c;
+    tbox[g] = make_int2(tx0 | (ty0 << 16), nx);   // first tile and tiles per row of the box: what the binning needs
 }
 
 // VEC: mean / lam are 8- / 16-byte aligned (whole tensors; a sliced view may not be) and are read as float2 /
 // float4.  The records of a block's 256 Gaussians are one contiguous 16 KB range: they are staged in shared memory
 // (quarter planes, one 16-byte word per lane and store) and written out as consecutive 16-byte words — a store of
 // a record's quarter straight from its thread touches 32 different 64-byte records per instruction.
+constexpr int BIN_CHUNK_SHIFT = 12;   // the binning's blocks of 4096 pairs (BIN_CHUNK below)
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_view_pack(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const float *__restrict__ mean,
             const float *__restrict__ lam, const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
-            int W, int H, const int32_t *__restrict__ toff, int4 *__restrict__ rec) {
+            int W, int H, const int32_t *__restrict__ toff, int4 *__restrict__ rec, int32_t *__restrict__ bstart,
+            int bcount) {
     __shared__ int4 stage[4][257];
     const int64_t g0 = static_cast<int64_t>(blockIdx.x) * 256;
     const int64_t g = g0 + threadIdx.x;
     if (g < n) {
         const Box b = clip_box(sp, ep, g, W, H);
+        if (bstart != nullptr) {
+            // bstart[m] = the Gaussian that owns pair m * 4096: k_view_pairs' block m starts there (saves it a search)
+            const int q0 = __ldg(toff + g), q1 = __ldg(toff + g + 1);
+            // (m < bcount: a view with more pairs than the arena holds is not rendered, but must not write outside)
+            for (int m = (q0 + (1 << BIN_CHUNK_SHIFT) - 1) >> BIN_CHUNK_SHIFT; m < bcount && (m << BIN_CHUNK_SHIFT) < q1; ++m)
+                bstart[m] = static_cast<int32_t>(g);
+        }
         auto f = [](float v) { return __float_as_int(v); };
         float mx, my, l00, l01, l10, l11;
         if (VEC) {
@@ -321,6 +335,347 @@ k_view_scatter(const int32_t *__restrict__ pg, const int32_t *__restrict__ pt, c
     if (t.y >= 0) pgid[__ldg(tstart + t.y) + sl.y] = g.y;
     if (t.z >= 0) pgid[__ldg(tstart + t.z) + sl.z] = g.z;
     if (t.w >= 0) pgid[__ldg(tstart + t.w) + sl.w] = g.w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// render: binning, sort-free (the default).  The Gaussian-major pair list is put in tile order by a STABLE
+// least-significant-digit radix sort on the tile id — stable, so inside a tile the pairs keep the Gaussian (= depth)
+// order they were emitted in: exactly the reference's stable torch.sort of the expanded list (gs_model.py:547),
+// bit for bit, with no atomic on a tile counter (3.6 M returning atomics cost the slot route ~45 us per 1080p view,
+// twice that on the bundled scene whose 8 600 tiles are hit ~500 times each) and no sort afterwards.
+//   k_view_pairs        : pair q -> (tile, Gaussian), 16 consecutive pairs per thread (one binary search for the
+//                         owner of the first, then a walk); per-block histogram of the first digit
+//   per digit           : k_view_scan over the [digit][block] counts -> where every block's run of every digit
+//                         value starts; k_view_bin_scatter moves the block's 4096 pairs there, ranked inside the
+//                         block in list order (a warp takes 512 consecutive pairs, 32 per round: MATCH.ANY gives the
+//                         lanes holding the same digit, the lowest of them bumps the warp's running counter of that
+//                         digit — no atomics; the warps' counters are then offset in warp order); k_view_bin_hist
+//                         counts the next digit
+//   k_view_tiles        : every tile's range in the sorted list (lower bound of its id) and its pieces
+// Digits: ceil(log2(tiles) / passes) bits each, at most 10 (1080p: 2 x 8, 4K: 2 x 9, the largest image: 3 x 9).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BIN_THREADS = 256, BIN_WARPS = BIN_THREADS / 32, BIN_ROUNDS = 16;
+constexpr int BIN_PER_WARP = 32 * BIN_ROUNDS;             // 512 consecutive pairs per warp
+constexpr int BIN_CHUNK = BIN_THREADS * BIN_ROUNDS;       // 4096 pairs per block
+static_assert(BIN_CHUNK == 1 << BIN_CHUNK_SHIFT, "k_view_pack marks the first Gaussian of every block of pairs");
+constexpr int BIN_MAX_BITS = 9;
+
+constexpr int PW_GAUSS = BIN_CHUNK + 64;   // Gaussians a block of k_view_pairs can stage
+constexpr int PW_SMEM = (PW_GAUSS + 2) * 4 + PW_GAUSS * 8 + (4 << BIN_MAX_BITS);
+
+// Where k_view_pairs reads the pair offsets and tile boxes of Gaussian g_lo + j: shared memory (staged) or global.
+struct PairSourceShared {
+    const int *toff;      // [ng + 1]
+    const int2 *box;      // [ng] {tx0 | ty0 << 16, nx}
+    __device__ __forceinline__ int off(int j) const { return toff[j]; }
+    __device__ __forceinline__ int2 tiles(int j) const { return box[j]; }
+};
+struct PairSourceGlobal {
+    const int32_t *toff;  // + g_lo
+    const int2 *tbox;     // + g_lo
+    __device__ __forceinline__ int off(int j) const { return __ldg(toff + j); }
+    __device__ __forceinline__ int2 tiles(int j) const { return __ldg(tbox + j); }
+};
+__device__ __forceinline__ PairSourceGlobal gsrc_of(const int32_t *toff, const int2 *tbox, int g_lo) {
+    return PairSourceGlobal{toff + g_lo, tbox + g_lo};
+}
+constexpr int PPT = 8;    // consecutive pairs per thread of k_view_pairs
+constexpr int PAIR_THREADS = BIN_CHUNK / PPT;   // 512: twice the warps per block for the same shared memory — the
+                                                // kernel is a chain of memory latencies, the warps are what hides them
+constexpr int PAIR_PAD = 16;                    // padding of the pair buffers (pairs)
+
+// PPT consecutive pairs from q0 on: one binary search for the owner of the first, then a walk — the tile id of the
+// next pair of a box is the previous one + 1, or the start of the next tile row (no division per pair)
+template <typename Source>
+__device__ __forceinline__ void emit_pairs(const Source &src, int ng, int g_lo, int q0, int P, int ntx, int mask,
+                                           int *__restrict__ s_cnt, int2 *__restrict__ out) {
+    int lo = 0, hi = ng - 1;   // first j with off(j + 1) > q0
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (src.off(mid + 1) > q0) hi = mid;
+        else lo = mid + 1;
+    }
+    int j = lo, end = src.off(j + 1);
+    int2 box = src.tiles(j);
+    int nx = box.y;
+    const int local = q0 - src.off(j), row = local / nx;
+    int col = local - row * nx;
+    int t = ((box.x >> 16) + row) * ntx + (box.x & 0xffff) + col;
+    int2 v[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int q = q0 + i;
+        v[i] = make_int2(-1, 0);
+        if (q < P) {
+            while (q >= end) {   // skips Gaussians without pairs too
+                ++j;
+                end = src.off(j + 1);
+                if (q < end) {
+                    box = src.tiles(j);
+                    nx = box.y;
+                    col = 0;
+                    t = (box.x >> 16) * ntx + (box.x & 0xffff);
+                }
+            }
+            v[i] = make_int2(t, g_lo + j);
+            atomicAdd(&s_cnt[t & mask], 1);
+            if (++col == nx) { col = 0; t += ntx - nx + 1; }
+            else ++t;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; i += 2)   // 16-byte stores; the buffers are padded
+        *reinterpret_cast<int4 *>(out + q0 + i) = make_int4(v[i].x, v[i].y, v[i + 1].x, v[i + 1].y);
+}
+
+// pair {tile, Gaussian}: one 8-byte word, so that a pair moves with ONE store (scattered stores cost per request,
+// not per byte).  A block emits 4096 consecutive pairs of the Gaussian-major numbering:
+// the Gaussian of its first pair was marked by k_view_pack (bstart), the block stages the pair offsets and tile boxes
+// of its Gaussians in shared memory (coalesced loads, four in flight per thread), and every thread emits 16
+// consecutive pairs from there — no dependent global loads per pair.  (A range holding more than PW_GAUSS Gaussians — long runs of Gaussians without any pair — is
+// walked in global memory instead.)  Also counts the first digit of the block's pairs.
+__global__ void __launch_bounds__(PAIR_THREADS, 3)
+k_view_pairs(const int2 *__restrict__ tbox, const int32_t *__restrict__ toff, const int32_t *__restrict__ bstart,
+             int64_t n, int ntx, int64_t cap, const unsigned int *__restrict__ hdr, int bits, int nb,
+             int2 *__restrict__ out, int32_t *__restrict__ hist, unsigned long long *__restrict__ desc,
+             int desc_words) {
+    extern __shared__ __align__(16) int s_dyn[];
+    int *s_toff = s_dyn;                                               // [PW_GAUSS + 1]
+    int2 *s_box = reinterpret_cast<int2 *>(s_dyn + PW_GAUSS + 2);      // [PW_GAUSS] {tx0 | ty0 << 16, nx}
+    int *s_cnt = s_dyn + PW_GAUSS + 2 + 2 * PW_GAUSS;                  // [nbins]
+    // the descriptors of the digit scans (used by later kernels of this view only)
+    for (int i = blockIdx.x * PAIR_THREADS + threadIdx.x; i < desc_words; i += gridDim.x * PAIR_THREADS) desc[i] = 0ull;
+    if (overflowed(hdr, cap)) return;
+    const int nbins = 1 << bits;
+    for (int d = threadIdx.x; d < nbins; d += PAIR_THREADS) s_cnt[d] = 0;
+    const int P = __ldg(toff + n);
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * BIN_CHUNK;
+    if (base < P) {   // block-uniform
+        // Gaussians of the block's pairs: from the owner of its first pair to (at most) the owner of the next block's
+        const int g_lo = __ldg(bstart + blockIdx.x);
+        const int g_hi = base + BIN_CHUNK < P ? __ldg(bstart + blockIdx.x + 1) : static_cast<int>(n - 1);
+        const int ng = g_hi - g_lo + 1;
+        const int q0 = static_cast<int>(base) + threadIdx.x * PPT;
+        if (ng <= PW_GAUSS) {
+            const PairSourceGlobal gsrc = gsrc_of(toff, tbox, g_lo);
+            for (int j0 = 0; j0 <= ng; j0 += 4 * PAIR_THREADS) {   // up to four loads of each kind in flight per thread
+                int o[4];
+                int2 bx[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = j0 + k * PAIR_THREADS + threadIdx.x;
+                    if (j <= ng) o[k] = gsrc.off(j);
+                    if (j < ng) bx[k] = gsrc.tiles(j);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = j0 + k * PAIR_THREADS + threadIdx.x;
+                    if (j <= ng) s_toff[j] = o[k];
+                    if (j < ng) s_box[j] = bx[k];
+                }
+            }
+            __syncthreads();
+            if (q0 < P) emit_pairs(PairSourceShared{s_toff, s_box}, ng, g_lo, q0, P, ntx, nbins - 1, s_cnt, out);
+        } else {
+            __syncthreads();   // s_cnt is zero
+            if (q0 < P) emit_pairs(gsrc_of(toff, tbox, g_lo), ng, g_lo, q0, P, ntx, nbins - 1, s_cnt, out);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < nbins; d += PAIR_THREADS) hist[static_cast<int64_t>(d) * nb + blockIdx.x] = s_cnt[d];
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+k_view_bin_hist(const int2 *__restrict__ in, int shift, int bits, int nb, int64_t cap,
+                const unsigned int *__restrict__ hdr, int32_t *__restrict__ hist) {
+    __shared__ int s_cnt[1 << BIN_MAX_BITS];
+    if (overflowed(hdr, cap)) return;
+    const int nbins = 1 << bits;
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_cnt[d] = 0;
+    __syncthreads();
+    const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * BIN_CHUNK;
+#pragma unroll 4
+    for (int r = 0; r < BIN_ROUNDS; ++r) {
+        const int64_t i = base + r * BIN_THREADS + threadIdx.x;
+        if (i < P) atomicAdd(&s_cnt[(__ldg(&in[i].x) >> shift) & (nbins - 1)], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) hist[static_cast<int64_t>(d) * nb + blockIdx.x] = s_cnt[d];
+}
+
+// One digit pass over the block's 4096 pairs.  The block first sorts them by the digit in shared memory (stable:
+// rank inside the warp's 512 pairs from MATCH.ANY + a running counter per warp and digit value, warps in order,
+// digit values in order), then copies them out: the pairs of one digit value are one contiguous run of the output,
+// so consecutive threads write consecutive addresses — a pair thrown straight at its final address costs one
+// memory request per pair (measured: 75 us per pass at 1080p against ~12 this way).
+// LAST: the final pass writes the Gaussian ids (the tile-ordered pair list) and the tile ids as two int arrays.
+template <bool LAST, int BITS>   // BITS: ballots per rank (>= the digit's bits; 7, 8 or 9)
+__global__ void __launch_bounds__(BIN_THREADS, 3)
+k_view_bin_scatter(const int2 *__restrict__ in, const int32_t *__restrict__ gbase, int shift, int bits, int nb,
+                   int64_t cap, const unsigned int *__restrict__ hdr, int2 *__restrict__ out,
+                   int32_t *__restrict__ out_keys, int32_t *__restrict__ out_gid) {
+    // [BIN_WARPS][nbins] running count per warp and digit value, then its offset | [nbins] start of the digit's run
+    // inside the block | [nbins] start of the block's run of the digit in the output | the sorted pairs
+    extern __shared__ __align__(16) int s_dyn[];
+    if (overflowed(hdr, cap)) return;
+    const int nbins = 1 << bits;
+    int *s_wcnt = s_dyn, *s_lstart = s_dyn + BIN_WARPS * nbins, *s_gbase = s_lstart + nbins;
+    int2 *s_stage = reinterpret_cast<int2 *>(s_gbase + nbins);
+    __shared__ int s_wsum[BIN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * BIN_CHUNK;
+    if (base >= P) return;
+    const int count = static_cast<int>(min(static_cast<int64_t>(BIN_CHUNK), P - base));
+    for (int d = threadIdx.x; d < BIN_WARPS * nbins; d += BIN_THREADS) s_wcnt[d] = 0;
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_gbase[d] = __ldg(gbase + static_cast<int64_t>(d) * nb + blockIdx.x);
+    __syncthreads();
+    int *mine = s_wcnt + warp * nbins;
+    const unsigned lt = (1u << lane) - 1u;
+    int2 it[BIN_ROUNDS];
+    int rank[BIN_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < BIN_ROUNDS; ++r) {
+        const int i = warp * BIN_PER_WARP + r * 32 + lane;
+        it[r] = make_int2(-1, 0);
+        if (i < count) it[r] = __ldcs(in + base + i);
+    }
+#pragma unroll
+    for (int r = 0; r < BIN_ROUNDS; ++r) {
+        const bool valid = it[r].x >= 0;
+        const int d = valid ? ((it[r].x >> shift) & (nbins - 1)) : 0;
+        // the lanes holding the same digit value: one ballot per digit bit (MATCH.ANY gives the same mask but
+        // iterates over the distinct values of the warp — measured 40 us per pass against the ballots' fixed cost)
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {   // bits above the digit are 0 in every lane: no-ops
+            const bool bit = (d & (1 << b)) != 0;
+            const unsigned has = __ballot_sync(0xffffffffu, bit);
+            if (bit) peers &= has;
+            else peers &= ~has;
+        }
+        if (!valid) peers = 1u << lane;
+        const int before = __popc(peers & lt);
+        int old = 0;
+        if (valid && before == 0) {   // the lowest lane of the group
+            old = mine[d];
+            mine[d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+        rank[r] = old + before;
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit value: the warps' offsets inside its run; then the runs' starts inside the block (exclusive scan
+    // over the digit values: thread t owns values [t K, t K + K), K = nbins / 256 rounded up)
+    {
+        const int K = (nbins + BIN_THREADS - 1) / BIN_THREADS;
+        int tot[(1 << BIN_MAX_BITS) / BIN_THREADS > 0 ? (1 << BIN_MAX_BITS) / BIN_THREADS : 1];
+        int mysum = 0;
+#pragma unroll
+        for (int k = 0; k < (1 << BIN_MAX_BITS) / BIN_THREADS; ++k) {
+            const int d = threadIdx.x * K + k;
+            tot[k] = 0;
+            if (k < K && d < nbins) {
+                int run = 0;
+#pragma unroll
+                for (int w = 0; w < BIN_WARPS; ++w) {
+                    const int c = s_wcnt[w * nbins + d];
+                    s_wcnt[w * nbins + d] = run;
+                    run += c;
+                }
+                tot[k] = run;
+                mysum += run;
+            }
+        }
+        int inc = mysum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        int pre = inc - mysum;
+#pragma unroll
+        for (int w = 0; w < BIN_WARPS; ++w)
+            if (w < warp) pre += s_wsum[w];
+#pragma unroll
+        for (int k = 0; k < (1 << BIN_MAX_BITS) / BIN_THREADS; ++k) {
+            const int d = threadIdx.x * K + k;
+            if (k < K && d < nbins) {
+                s_lstart[d] = pre;
+                pre += tot[k];
+            }
+        }
+    }
+    __syncthreads();
+    // s_gbase[d] becomes (start of the block's run of d in the output) - (start of d's run inside the block)
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_gbase[d] -= s_lstart[d];
+#pragma unroll
+    for (int r = 0; r < BIN_ROUNDS; ++r) {
+        if (it[r].x >= 0) {
+            const int d = (it[r].x >> shift) & (nbins - 1);
+            s_stage[s_lstart[d] + mine[d] + rank[r]] = it[r];
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < BIN_ROUNDS; ++r) {
+        const int i = r * BIN_THREADS + threadIdx.x;
+        if (i < count) {
+            const int2 v = s_stage[i];
+            const int d = (v.x >> shift) & (nbins - 1);
+            const int pos = s_gbase[d] + i;
+            if (LAST) {
+                out_keys[pos] = v.x;
+                out_gid[pos] = v.y;
+            } else {
+                out[pos] = v;
+            }
+        }
+    }
+}
+
+// first index i in [0, P) with keys[i] >= t (P if none)
+__device__ __forceinline__ int lower_bound_tile(const int32_t *__restrict__ keys, int P, int t) {
+    int lo = 0, hi = P;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (__ldg(keys + mid) < t) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per tile: its range in the tile-ordered pair list and its pieces (see "Work units" below)
+__global__ void __launch_bounds__(256)
+k_view_tiles(const int32_t *__restrict__ keys, int ntiles, int piece, int64_t cap, unsigned int *__restrict__ hdr,
+             int32_t *__restrict__ tcount, int32_t *__restrict__ tstart, int32_t *__restrict__ pextra,
+             int32_t *__restrict__ ptile_x, int32_t *__restrict__ mlist) {
+    if (overflowed(hdr, cap)) return;
+    const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int tt = t < ntiles ? t : ntiles;
+    const int lo = lower_bound_tile(keys, P, tt);
+    int hi = __shfl_down_sync(0xffffffffu, lo, 1);          // the next tile's lower bound ...
+    if (lane == 31) hi = lower_bound_tile(keys, P, tt + 1);  // ... which the last lane has to find itself
+    if (t > ntiles) return;
+    tstart[t] = lo;
+    if (t == ntiles) return;
+    const int len = hi - lo;
+    tcount[t] = len;
+    int x = -1;
+    if (len > piece) {
+        const int np = (len + piece - 1) / piece;
+        x = static_cast<int>(atomicAdd(hdr + H_XPIECES, static_cast<unsigned>(np)));
+        ptile_x[x] = -1;
+        for (int k = 1; k < np; ++k) ptile_x[x + k] = t;
+        mlist[atomicAdd(hdr + H_NMULTI, 1u)] = t;
+    }
+    pextra[t] = x;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1182,6 +1537,7 @@ k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 int g_piece = 128;  // pairs per piece (gcp_tile_set_piece_pairs)
+int g_binning = 1;  // 1: stable radix sort by tile (default); 0: atomic slots + per-tile sort (gcp_tile_set_binning)
 
 inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >= 32768; }
 inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
@@ -1189,7 +1545,7 @@ inline int tiles_y(int H) { return (H + TH) >> TSY; }
 
 // plan arena: everything whose size is known from (n, W, H) alone.  [0, zero_bytes) is cleared by gcp_view_plan.
 struct PlanLayout {
-    size_t hdr, desc1, desc2, tcount, zero_bytes, cnt, toff, tstart, pextra, mlist, longlist, big, rec, total;
+    size_t hdr, desc1, desc2, tcount, zero_bytes, cnt, tbox, toff, tstart, pextra, mlist, longlist, big, rec, total;
     unsigned nb1, nb2;
 };
 PlanLayout plan_layout(int64_t n, int ntiles) {
@@ -1204,6 +1560,7 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
     L.tcount = take(static_cast<size_t>(ntiles) * 4);
     L.zero_bytes = o;
     L.cnt = take(static_cast<size_t>(n > 0 ? n : 1) * 4);
+    L.tbox = take(static_cast<size_t>(n > 0 ? n : 1) * 8);
     L.toff = take(static_cast<size_t>(n + 1) * 4);
     L.tstart = take(static_cast<size_t>(ntiles + 1) * 4);
     L.pextra = take(static_cast<size_t>(ntiles) * 4);
@@ -1214,10 +1571,26 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
     L.total = o;
     return L;
 }
-// pair arena: everything sized by the pair capacity.  The three binning arrays (Gaussian, tile, slot of every
-// pair: 12 B per pair, dead once the pair list is built) share the space of the backward's partials (32 B per pair).
+// pair arena: everything sized by the pair capacity.  What the binning needs (dead once the pair list is built) shares
+// the space of the backward's partials (32 B per pair): the radix route's two (tile, Gaussian) buffers, digit counts,
+// their scanned offsets and the scans' descriptors; the slot route's Gaussian, tile and slot of every pair.
+struct BinPlan {
+    int passes, bits, nb;        // digit passes, bits per digit, blocks of BIN_CHUNK pairs
+    unsigned nscan;              // blocks of one digit scan
+};
+BinPlan bin_plan(int64_t cap, int ntiles) {
+    int total = 1;
+    while ((int64_t(1) << total) < ntiles) ++total;
+    BinPlan b;
+    b.passes = (total + BIN_MAX_BITS - 1) / BIN_MAX_BITS;   // <= BIN_MAX_PASSES: tiles < 2^30 (bad_image)
+    b.bits = (total + b.passes - 1) / b.passes;
+    b.nb = static_cast<int>(blocks_for(cap, BIN_CHUNK));
+    b.nscan = blocks_for((int64_t(1) << b.bits) * b.nb, SCAN_TILE);
+    return b;
+}
 struct PairLayout {
     size_t pgid, tck, ptile_x, pstate, partial, bin_pg, bin_pt, bin_ps, total;
+    size_t rb[2], rb_hist, rb_base, rb_desc, rb_bstart;   // radix route
     int64_t xcap;
 };
 PairLayout pair_layout(int64_t cap, int ntiles) {
@@ -1231,11 +1604,25 @@ PairLayout pair_layout(int64_t cap, int ntiles) {
     L.ptile_x = take(static_cast<size_t>(L.xcap) * 4);
     L.pstate = take(static_cast<size_t>(L.xcap) * PIECE_STATE * 4);
     L.partial = take(static_cast<size_t>(cap) * 32);
+    const size_t end_partial = o;
     const size_t third = align256(static_cast<size_t>(cap + QPT) * 4);   // 3 * third <= 32 * cap for cap >= 16
     L.bin_pg = L.partial;
     L.bin_pt = L.partial + third;
     L.bin_ps = L.partial + 2 * third;
-    if (3 * third > align256(static_cast<size_t>(cap) * 32)) o = L.partial + 3 * third;
+    if (L.partial + 3 * third > o) o = L.partial + 3 * third;
+    {
+        const BinPlan b = bin_plan(cap, ntiles);
+        const size_t cells = (static_cast<size_t>(1) << b.bits) * b.nb;
+        size_t r = L.partial;
+        auto rtake = [&](size_t bytes) { const size_t at = r; r += align256(bytes); return at; };
+        for (int k = 0; k < 2; ++k) L.rb[k] = rtake(static_cast<size_t>(cap + PAIR_PAD) * 8);
+        L.rb_hist = rtake(cells * 4);
+        L.rb_base = rtake((cells + 1) * 4);
+        L.rb_desc = rtake(static_cast<size_t>(b.passes) * b.nscan * 8);
+        L.rb_bstart = rtake(static_cast<size_t>(b.nb + 1) * 4);
+        if (r > o) o = r;
+    }
+    (void)end_partial;
     L.total = o;
     return L;
 }
@@ -1273,6 +1660,34 @@ inline const T *at(const void *base, size_t off) {
     return reinterpret_cast<const T *>(static_cast<const unsigned char *>(base) + off);
 }
 
+// one digit pass: the instantiation with just enough ballots for the digit
+template <bool LAST, int BITS>
+void launch_bin_scatter_as(const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *gbase, int shift,
+                           int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_view_bin_scatter<LAST, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ((BIN_WARPS + 2) << BIN_MAX_BITS) * 4 + BIN_CHUNK * 8);
+        attr_set = true;
+    }
+    k_view_bin_scatter<LAST, BITS><<<bp.nb, BIN_THREADS, smem, st>>>(in, gbase, shift, bp.bits, bp.nb, cap, hdr,
+                                                                     LAST ? nullptr : out,
+                                                                     LAST ? reinterpret_cast<int32_t *>(out) : nullptr,
+                                                                     LAST ? pgid : nullptr);
+}
+template <bool LAST>
+void launch_bin_scatter_last(const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *gbase,
+                             int shift, int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
+    if (bp.bits <= 7) launch_bin_scatter_as<LAST, 7>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+    else if (bp.bits == 8) launch_bin_scatter_as<LAST, 8>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+    else launch_bin_scatter_as<LAST, 9>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+}
+void launch_bin_scatter(bool last, const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *gbase,
+                        int shift, int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
+    if (last) launch_bin_scatter_last<true>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+    else launch_bin_scatter_last<false>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+}
+
 thread_local int t_view_launches = 0;
 
 }  // namespace
@@ -1288,6 +1703,12 @@ int gcp_tile_set_piece_pairs(int pairs) {
     return GCP_OK;
 }
 int gcp_tile_piece_pairs(void) { return g_piece; }
+int gcp_tile_set_binning(int mode) {
+    if (mode != 0 && mode != 1) return GCP_ERR_INVALID_ARG;
+    g_binning = mode;
+    return GCP_OK;
+}
+int gcp_tile_binning(void) { return g_binning; }
 int gcp_view_last_launch_count(void) { return t_view_launches; }
 
 size_t gcp_view_plan_bytes(int64_t n, int W, int H) {
@@ -1326,7 +1747,7 @@ int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H,
         ++t_view_launches;
         return static_cast<int>(cudaGetLastError());
     }
-    k_view_cnt<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, n, W, H, at<int32_t>(plan, L.cnt));
+    k_view_cnt<<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, n, W, H, at<int32_t>(plan, L.cnt), at<int2>(plan, L.tbox));
     k_view_scan<<<L.nb1, SCAN_THREADS, 0, st>>>(at<int32_t>(plan, L.cnt), n, at<int32_t>(plan, L.toff),
                                                 hdr + H_TICKET_S1, at<unsigned long long>(plan, L.desc1),
                                                 reinterpret_cast<unsigned long long *>(hdr) + H_P64, totals_host);
@@ -1352,29 +1773,70 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
     int32_t *pgid = at<int32_t>(pairs, B.pgid);
     int4 *rec = at<int4>(plan, A.rec);
+    int32_t *bstart = g_binning == 1 ? at<int32_t>(pairs, B.rb_bstart) : nullptr;
+    const int bcount = bin_plan(pair_cap < 16 ? 16 : pair_cap, ntiles).nb + 1;
     if (n > 0) {
-        int32_t *pg = at<int32_t>(pairs, B.bin_pg), *pt = at<int32_t>(pairs, B.bin_pt), *ps = at<int32_t>(pairs, B.bin_ps);
         if (((reinterpret_cast<uintptr_t>(mean) & 7) | (reinterpret_cast<uintptr_t>(lam) & 15)) == 0)
             k_view_pack<true><<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, n, W, H,
-                                                                  at<int32_t>(plan, A.toff), rec);
+                                                                  at<int32_t>(plan, A.toff), rec, bstart, bcount);
         else
             k_view_pack<false><<<blocks_for(n, 256), 256, 0, st>>>(sp, ep, mean, lam, opac, l_d, n, W, H,
-                                                                   at<int32_t>(plan, A.toff), rec);
-        k_view_slots<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(rec, at<int32_t>(plan, A.toff), n, ntx, pair_cap,
-                                                                      hdr, tcount, pg, pt, ps);
-        k_view_scan<<<A.nb2, SCAN_THREADS, 0, st>>>(tcount, ntiles, tstart, hdr + H_TICKET_S2,
-                                                    at<unsigned long long>(plan, A.desc2),
-                                                    reinterpret_cast<unsigned long long *>(hdr) + H_T64, nullptr);
-        k_view_scatter<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(pg, pt, ps, tstart, pair_cap, hdr, pgid);
-        t_view_launches += 4;
-    } else {
-        cudaError_t e = cudaMemsetAsync(tstart, 0, static_cast<size_t>(ntiles + 1) * 4, st);
-        if (e != cudaSuccess) return static_cast<int>(e);
+                                                                   at<int32_t>(plan, A.toff), rec, bstart, bcount);
+        ++t_view_launches;
     }
-    k_view_sort<<<blocks_for(ntiles, 8), 256, 0, st>>>(tcount, tstart, ntiles, g_piece, pair_cap, hdr, pgid, pextra,
-                                                       ptile_x, at<int32_t>(plan, A.mlist),
-                                                       at<int32_t>(plan, A.longlist));
-    {
+    if (n > 0 && g_binning == 1) {
+        // stable radix sort of the pair list by tile: no atomics on tile counters, no sort afterwards
+        const BinPlan bp = bin_plan(pair_cap < 16 ? 16 : pair_cap, ntiles);
+        const int nbins = 1 << bp.bits;
+        const int64_t cells = static_cast<int64_t>(nbins) * bp.nb;
+        int32_t *hist = at<int32_t>(pairs, B.rb_hist), *gbase = at<int32_t>(pairs, B.rb_base);
+        unsigned long long *desc = at<unsigned long long>(pairs, B.rb_desc);
+        unsigned long long *sink = reinterpret_cast<unsigned long long *>(hdr) + H_B64;
+        const size_t smem = (static_cast<size_t>(BIN_WARPS + 2) * nbins) * 4 + static_cast<size_t>(BIN_CHUNK) * 8;
+        {
+            static bool attr_set = false;   // (per process; setting the attribute again costs nothing)
+            if (!attr_set) {
+                cudaFuncSetAttribute(k_view_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM);
+                attr_set = true;
+            }
+        }
+        k_view_pairs<<<bp.nb, PAIR_THREADS, PW_SMEM, st>>>(at<int2>(plan, A.tbox), at<int32_t>(plan, A.toff), bstart, n, ntx, pair_cap, hdr, bp.bits, bp.nb,
+                                                    at<int2>(pairs, B.rb[0]), hist, desc,
+                                                    static_cast<int>(bp.passes * bp.nscan));
+        ++t_view_launches;
+        for (int k = 0; k < bp.passes; ++k) {
+            const int2 *in = at<int2>(pairs, B.rb[k & 1]);
+            int2 *out = at<int2>(pairs, B.rb[(k + 1) & 1]);
+            if (k > 0) {
+                k_view_bin_hist<<<bp.nb, BIN_THREADS, 0, st>>>(in, k * bp.bits, bp.bits, bp.nb, pair_cap, hdr, hist);
+                ++t_view_launches;
+            }
+            k_view_scan<<<bp.nscan, SCAN_THREADS, 0, st>>>(hist, cells, gbase, hdr + H_TICKET_BIN + k,
+                                                           desc + static_cast<size_t>(k) * bp.nscan, sink, nullptr);
+            launch_bin_scatter(k + 1 == bp.passes, bp, smem, st, in, gbase, k * bp.bits, pair_cap, hdr, out, pgid);
+            t_view_launches += 2;
+        }
+        k_view_tiles<<<blocks_for(ntiles + 1, 256), 256, 0, st>>>(at<int32_t>(pairs, B.rb[bp.passes & 1]), ntiles,
+                                                                  g_piece, pair_cap, hdr, tcount, tstart, pextra, ptile_x,
+                                                                  at<int32_t>(plan, A.mlist));
+        ++t_view_launches;
+    } else {
+        if (n > 0) {
+            int32_t *pg = at<int32_t>(pairs, B.bin_pg), *pt = at<int32_t>(pairs, B.bin_pt), *ps = at<int32_t>(pairs, B.bin_ps);
+            k_view_slots<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(rec, at<int32_t>(plan, A.toff), n, ntx, pair_cap,
+                                                                          hdr, tcount, pg, pt, ps);
+            k_view_scan<<<A.nb2, SCAN_THREADS, 0, st>>>(tcount, ntiles, tstart, hdr + H_TICKET_S2,
+                                                        at<unsigned long long>(plan, A.desc2),
+                                                        reinterpret_cast<unsigned long long *>(hdr) + H_T64, nullptr);
+            k_view_scatter<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(pg, pt, ps, tstart, pair_cap, hdr, pgid);
+            t_view_launches += 3;
+        } else {
+            cudaError_t e = cudaMemsetAsync(tstart, 0, static_cast<size_t>(ntiles + 1) * 4, st);
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        k_view_sort<<<blocks_for(ntiles, 8), 256, 0, st>>>(tcount, tstart, ntiles, g_piece, pair_cap, hdr, pgid, pextra,
+                                                           ptile_x, at<int32_t>(plan, A.mlist),
+                                                           at<int32_t>(plan, A.longlist));
         static bool attr_set = false;   // (per process; setting the attribute again costs nothing)
         if (!attr_set) {
             cudaFuncSetAttribute(k_view_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM * 4);
@@ -1383,6 +1845,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
         const int32_t *ll = at<int32_t>(plan, A.longlist);
         k_view_sort_long<<<148 * 4, SORT_WARPS * 32, 0, st>>>(tcount, tstart, pair_cap, hdr, ll, pgid);
         k_view_sort_huge<<<148, SORT_HUGE_THREADS, SORT_SMEM * 4, st>>>(tcount, tstart, pair_cap, hdr, ll, pgid);
+        t_view_launches += 3;
     }
     float *tck = at<float>(pairs, B.tck), *pstate = at<float>(pairs, B.pstate);
     if (keep) {
@@ -1396,7 +1859,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     }
     k_view_combine_fwd<<<296, 256, 0, st>>>(tcount, pextra, at<int32_t>(plan, A.mlist), hdr, pair_cap, g_piece, ntx, W,
                                            H, pstate, image);
-    t_view_launches += 5;
+    t_view_launches += 2;
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -310,6 +310,18 @@ def test_planned_view_equals_unplanned_gpu(route):
             assert torch.equal(a, b)
 
 
+@pytest.fixture(params=[1, 0], ids=["radix", "slots"])
+def binning(request):
+    """gcp_tile_set_binning: 1 = stable radix sort of the pair list by tile (the default), 0 = atomic slots + a sort
+    of every tile's list."""
+    from simplegaussiansplat_tk71_b200 import _lib
+
+    L = _lib.lib()
+    assert L.gcp_tile_set_binning(request.param) == 0
+    yield request.param
+    L.gcp_tile_set_binning(1)
+
+
 def _arena_arrays(L, view, W, H):
     """The integer arrays of a rendered tile-route view, read out of its two arenas (gcp_view_layout)."""
     import ctypes
@@ -327,12 +339,13 @@ def _arena_arrays(L, view, W, H):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
-def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
+def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch, binning):
     """Integer side of the tile route: pair offsets per Gaussian, pairs per tile, every tile's list in the order
     of a stable sort by tile, the tile offsets and the pieces of long lists, against the numpy restatement
     (oracle/tile_oracle.py, itself pinned on CPU to the reference's sorted element list by
-    tests/test_compositor_oracle.py).  The native binning is a counting placement (atomic cursors) followed by a
-    sort of every tile's segment by Gaussian id: the RESULT must be the stable sort, bit for bit."""
+    tests/test_compositor_oracle.py).  The native binning is a stable radix sort of the Gaussian-major pair list by
+    tile (or, binning 0, atomic slots followed by a sort of every tile's segment by Gaussian id): the RESULT must be
+    the stable sort, bit for bit."""
     from oracle import tile_oracle as to
     from simplegaussiansplat_tk71_b200 import _lib, compositor
 
@@ -382,8 +395,9 @@ def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch):
-    """Tile lists of thousands of pairs (bundled scene) go through the block-per-tile sort: still the stable order."""
+def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch, binning):
+    """Tile lists of thousands of pairs (bundled scene; with binning 0 they go through the block-per-tile sorts):
+    still the stable order."""
     from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
@@ -420,6 +434,64 @@ def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch):
               (np.maximum(sp[:, 1], 0) // th <= ty) & (np.minimum(ep[:, 1], v.height) // th >= ty) & \
               (ep[:, 0] >= sp[:, 0]) & (ep[:, 1] >= sp[:, 1])
         assert np.array_equal(seg, np.flatnonzero(hit).astype(np.int32)), f"tile {tl}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,n,max_half", [(1920, 1080, 200_000, None), (3840, 2160, 300_000, None),
+                                            (16383, 4095, 20_000, 40), (5, 3, 40, 3), (2047, 2047, 3_000, 600),
+                                            (1279, 719, 30_000, 12)],
+                         ids=["1080p-2x8bit", "4k-2x9bit", "2M-tiles-3x7bit", "one-tile-1bit", "big-boxes", "holes"])
+def test_radix_binning_equals_slot_binning_bitwise_gpu(W, H, n, max_half, monkeypatch):
+    """The two binnings of the tile route build the same tile-ordered pair list, bit for bit, whatever the number of
+    digit passes the tile count asks for (1080p: 2 x 8 bits, 4K: 2 x 9, 2 Mi tiles: 3 x 7, one tile: 1 x 1), and so
+    the same image and gradients."""
+    from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
+    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
+
+    monkeypatch.setattr(compositor, "ROUTE", "tiles")
+    L = _lib.lib()
+    if max_half is None:
+        v = wl.splat_view(W, H, n, seed=7, device="cuda")
+    else:
+        rng = np.random.default_rng(W + H)
+        half = rng.integers(1, max_half + 1, (n, 2))
+        c = np.stack((rng.integers(-2, W + 3, n), rng.integers(-2, H + 3, n)), 1)
+        sp = np.clip(c - half, 0, [W, H]).astype(np.int32)
+        ep = np.clip(c + half, 0, [W, H]).astype(np.int32)
+        if (W, H) == (1279, 719):
+            # 15 000 consecutive Gaussians without any pair (empty boxes): the 4096 pairs of a block of k_view_pairs
+            # then span more Gaussians than it stages in shared memory — its global-memory path
+            ep[5_000:20_000, 0] = sp[5_000:20_000, 0] - 1
+        sig = half.astype(np.float64) / 3.0 + 0.5
+        lam = np.zeros((n, 2, 2), np.float32)
+        lam[:, 0, 0], lam[:, 1, 1] = 1.0 / sig[:, 0] ** 2, 1.0 / sig[:, 1] ** 2
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+        v = wl.SplatView(name=f"boxes {W}x{H}", boxsize=t(np.maximum(ep - sp + 1, 0).astype(np.int64).prod(1)), startpoint=t(sp),
+                         endpoint=t(ep), mean=t(c.astype(np.float32)), lam=t(lam),
+                         opacity=t(rng.uniform(0.01, 0.3, (n, 1)).astype(np.float32)),
+                         l_d=t(rng.uniform(0.2, 1.0, (n, 3)).astype(np.float32)), width=W, height=H)
+    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
+    res = []
+    try:
+        for mode in (0, 1):
+            assert L.gcp_tile_set_binning(mode) == 0 and L.gcp_tile_binning() == mode
+            m, lam_, o, l = (v.mean.float().clone().requires_grad_(True), v.lam.clone().requires_grad_(True),
+                             v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
+            img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam_, o, l, v.width, v.height)
+            view = img.grad_fn.view
+            torch.cuda.synchronize()
+            a = _arena_arrays(L, view, v.width, v.height)
+            ints = [a["tcount"].copy(), a["tstart"].copy(), a["pgid"][:view.P].copy()]
+            img.backward(gI)
+            res.append((ints, [img.detach().clone()] + [t_.grad.clone() for t_ in (m, lam_, o, l)]))
+            del img, view
+    finally:
+        L.gcp_tile_set_binning(1)
+    assert int(res[0][0][0].sum()) > 0
+    for x, y in zip(res[0][0], res[1][0]):
+        assert np.array_equal(x, y)
+    for x, y in zip(res[0][1], res[1][1]):
+        assert torch.equal(x, y)
 
 
 def _both_routes(v, gI, monkeypatch, repeats=1):
