@@ -672,7 +672,7 @@ def multi_view_leg(args, device, rank, world, mine, n_param, bucket):
     lanes = int(os.environ.get("BENCH_MV_LANES", "4"))
     views = [wl.splat_view_device(W, H, n_param, seed=1080 + v, device=device) for v in mine]
     elems = sum(v.elements for v in views)
-    target = torch.rand(H + 1, W + 1, 3, device=device)
+    target = torch.rand(H + 1, W + 1, 3, device=device, generator=torch.Generator(device=device).manual_seed(64))
     # the tail = as many views as there are lanes: the views of the tail run side by side, so the event in front of
     # them fires about one tail's worth of time before the batch ends — enough for the all-reduce of the big bucket
     # (8 GPUs, 8 views per rank: tail 2 / 3 / 4 -> 5.31 / 5.23 / 5.09 ms)

@@ -295,17 +295,15 @@ int gcp_splat_bwd_grads(const float *incl, const float *x_s, const float *tu, co
  * backward will follow (no checkpoints are written).  n < 2^31 - 64, pairs < 2^31 - 64 per view, any number of
  * ELEMENTS (the reference's 2^29-element chunks and their per-pixel carry, gs_model.py:428, :582-594, have no
  * counterpart: a view is one pass); the arenas of a view at that limit would exceed 100 GB, compositor.py raises.
- * Binning (gcp_tile_set_binning): 1 (default) = the Gaussian-major pair list is put in tile order by a stable
- * radix sort on the tile id (no atomics, nothing to sort afterwards); 0 = a slot per pair from an atomic counter
- * per tile, then every tile's list sorted by Gaussian id.  Same pair list, bit for bit.
+ * Binning: the Gaussian-major pair list is put in tile order by a stable radix sort on the tile id (no atomics,
+ * nothing to sort afterwards) — inside a tile the Gaussians keep their depth order, as after the reference's stable
+ * torch.sort (gs_model.py:547).
  * ------------------------------------------------------------------------------------------------ */
 int gcp_tile_width(void);
 int gcp_tile_height(void);
 int gcp_tile_num_tiles(int W, int H);
 int gcp_tile_set_piece_pairs(int pairs);   /* tuning / tests: multiple of 32 */
 int gcp_tile_piece_pairs(void);
-int gcp_tile_set_binning(int mode);        /* tuning / tests: 0 or 1 */
-int gcp_tile_binning(void);
 size_t gcp_view_plan_bytes(int64_t n, int W, int H);
 size_t gcp_view_pair_bytes(int64_t pair_cap, int W, int H);
 int gcp_view_plan(const int32_t *sp, const int32_t *ep, int64_t n, int W, int H, void *plan, size_t plan_bytes,

@@ -31,7 +31,6 @@ SYMBOLS = (
     "gcp_splat_place_bytes", "gcp_splat_place", "gcp_splat_set_fill_blocks", "gcp_splat_set_long_list_threshold", "gcp_splat_seg_shift",
     "gcp_splat_num_cells", "gcp_splat_long_lists", "gcp_splat_bwd_elem_cells", "gcp_splat_batch_table_ints",
     "gcp_tile_width", "gcp_tile_height", "gcp_tile_num_tiles", "gcp_tile_set_piece_pairs", "gcp_tile_piece_pairs",
-    "gcp_tile_set_binning", "gcp_tile_binning",
     "gcp_view_plan_bytes", "gcp_view_pair_bytes", "gcp_view_layout", "gcp_view_plan", "gcp_view_render", "gcp_view_forward",
     "gcp_view_backward", "gcp_view_backward_scatter", "gcp_view_last_launch_count",
     "gcp_views_ctx_create", "gcp_views_ctx_destroy", "gcp_views_step", "gcp_views_step_split",
@@ -146,9 +145,6 @@ def lib() -> ctypes.CDLL:
     L.gcp_tile_set_piece_pairs.argtypes = [ci]
     L.gcp_tile_set_piece_pairs.restype = ci
     L.gcp_tile_piece_pairs.restype = ci
-    L.gcp_tile_set_binning.argtypes = [ci]
-    L.gcp_tile_set_binning.restype = ci
-    L.gcp_tile_binning.restype = ci
     L.gcp_view_plan_bytes.argtypes = [i64, ci, ci]
     L.gcp_view_plan_bytes.restype = sz
     L.gcp_view_pair_bytes.argtypes = [i64, ci, ci]

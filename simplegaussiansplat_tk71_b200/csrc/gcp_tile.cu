@@ -12,14 +12,12 @@
 //   plan      k_view_cnt      : pairs per Gaussian                                              (uitility.py:336-366)
 //             k_view_scan     : their exclusive offsets (chained scan); the pair total goes to the host (.item() :348)
 //   render    k_view_pack     : packed per-Gaussian records
-//             k_view_slots    : one thread per 4 pairs: the pair's tile and its slot in that tile's list, taken
-//                               from an atomic counter per tile (unordered)                    (gs_model.py:538-548)
-//             k_view_scan     : tile offsets
-//             k_view_scatter  : every pair's Gaussian id dropped at tile offset + slot
-//             k_view_sort     : every tile's segment sorted by Gaussian id (bitonic network in registers; lists of
-//             k_view_sort_long  513-4096 ids by a block, longer ones through shared memory) — the ids of a tile are
-//             k_view_sort_huge  distinct, so the result IS the stable sort by tile, bit for bit; long lists are cut
-//                               into pieces (the walk kernels' work units)
+//             k_view_pairs    : pair q of the Gaussian-major numbering -> {tile, Gaussian}
+//             k_view_scan + k_view_bin_scatter (+ k_view_bin_hist) per digit: a STABLE radix sort of the pairs by
+//                               tile id — inside a tile the pairs keep the Gaussian (= depth) order, which is the
+//                               stable torch.sort of the reference, bit for bit                (gs_model.py:538-548)
+//             k_view_tiles    : every tile's range in the sorted list; long lists are cut into pieces (the walk
+//                               kernels' work units)
 //             k_view_render   : alpha = o * exp(-1/2 d Lambda d^T) (:493-495,:533-535), T, colour; only a
 //                               CHECKPOINT of T every 8 pairs is kept for the backward (16 B per pair)
 //             k_view_combine_fwd / _bwd : carries between the pieces of a long list          (:582-594)
@@ -60,10 +58,10 @@ inline unsigned blocks_for(int64_t work, int per_block, unsigned cap = 0x7ffffff
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 // ---- arena headers (u32 words; zeroed by gcp_view_plan) ----
-constexpr int H_TICKET_S1 = 0, H_TICKET_S2 = 1, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4, H_NLONG = 5;
+constexpr int H_TICKET_S1 = 0, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4;
 constexpr int H_TICKET_BWD = 6, H_NBIG = 7, H_TICKET_RED = 8;   // adjacent u32 words: reset together by every backward
 constexpr int H_TICKET_BIN = 10;                // .. 12: scan tickets of the (up to three) radix passes of the binning
-constexpr int H_P64 = 8, H_T64 = 9;             // u64 indices (bytes 64 / 72): pair count; the tile scan's total (= it)
+constexpr int H_P64 = 8;                        // u64 index (byte 64): the pair count of the view
 constexpr int H_B64 = 12;                       // u64 index (byte 96): sink for the totals of the radix passes' scans
 constexpr int HDR_WORDS = 64;
 
@@ -261,88 +259,19 @@ __global__ void k_view_scan_empty(int32_t *toff, unsigned int *hdr, int64_t *tot
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// render: binning.  Pair q (Gaussian-major, row-major over the tiles of its box) goes to tile t(q); its place in
-// the tile's segment is tstart[t] + slot, the slot taken from an atomic counter per tile.  One thread handles
-// four consecutive pairs (one binary search for the owner of the first, then a walk), so that a warp issues
-// full-width atomics with four independent ones in flight per thread — a thread per Gaussian would leave most
-// lanes idle behind the largest box of the warp.  Two passes, because the tile offsets need the counts first.
+// render: binning
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap) {
     return static_cast<int64_t>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]) > cap;
 }
-// first index g with off[g+1] > e
-__device__ __forceinline__ int64_t find_owner(const int32_t *__restrict__ off, int64_t n, int e) {
-    int64_t lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(off + mid + 1) > e) hi = mid;
-        else lo = mid + 1;
-    }
-    return lo;
-}
-constexpr int QPT = 4;   // pairs per thread
-
-__global__ void __launch_bounds__(256)
-k_view_slots(const int4 *__restrict__ rec, const int32_t *__restrict__ toff, int64_t n, int ntx, int64_t cap,
-             const unsigned int *__restrict__ hdr, int32_t *__restrict__ tcount, int32_t *__restrict__ pg,
-             int32_t *__restrict__ pt, int32_t *__restrict__ ps) {
-    if (overflowed(hdr, cap)) return;   // the arena is too small for this view: the host notices and redoes it
-    const int P = __ldg(toff + n);
-    const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * QPT;
-    if (q0 >= P) return;
-    int64_t g = find_owner(toff, n, q0);
-    int gbeg = __ldg(toff + g), gend = __ldg(toff + g + 1);
-    int4 bx = __ldg(rec + 4 * g + 2), by = __ldg(rec + 4 * g + 3);   // {.., .., sx, sy} {ex, ey, .., ..}
-    int tx0 = bx.z >> TSX, ty0 = bx.w >> TSY, nx = (by.x >> TSX) - tx0 + 1;
-    int gi[QPT], t[QPT], sl[QPT];
-#pragma unroll
-    for (int i = 0; i < QPT; ++i) {
-        const int q = q0 + i;
-        gi[i] = 0; t[i] = -1;
-        if (q < P) {
-            while (q >= gend) {   // skips Gaussians without pairs too
-                ++g;
-                gbeg = gend;
-                gend = __ldg(toff + g + 1);
-                if (q < gend) {
-                    bx = __ldg(rec + 4 * g + 2); by = __ldg(rec + 4 * g + 3);
-                    tx0 = bx.z >> TSX; ty0 = bx.w >> TSY; nx = (by.x >> TSX) - tx0 + 1;
-                }
-            }
-            const int local = q - gbeg, r = local / nx;
-            t[i] = (ty0 + r) * ntx + tx0 + (local - r * nx);
-            gi[i] = static_cast<int>(g);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < QPT; ++i) sl[i] = t[i] >= 0 ? atomicAdd(tcount + t[i], 1) : 0;
-    *reinterpret_cast<int4 *>(pg + q0) = make_int4(gi[0], gi[1], gi[2], gi[3]);   // the arrays are padded to QPT
-    *reinterpret_cast<int4 *>(pt + q0) = make_int4(t[0], t[1], t[2], t[3]);
-    *reinterpret_cast<int4 *>(ps + q0) = make_int4(sl[0], sl[1], sl[2], sl[3]);
-}
-
-__global__ void __launch_bounds__(256)
-k_view_scatter(const int32_t *__restrict__ pg, const int32_t *__restrict__ pt, const int32_t *__restrict__ ps,
-               const int32_t *__restrict__ tstart, int64_t cap, const unsigned int *__restrict__ hdr,
-               int32_t *__restrict__ pgid) {
-    if (overflowed(hdr, cap)) return;
-    const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
-    const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * QPT;
-    if (q0 >= P) return;
-    const int4 g = __ldcs(reinterpret_cast<const int4 *>(pg + q0)), t = __ldcs(reinterpret_cast<const int4 *>(pt + q0)),
-               sl = __ldcs(reinterpret_cast<const int4 *>(ps + q0));
-    if (t.x >= 0) pgid[__ldg(tstart + t.x) + sl.x] = g.x;
-    if (t.y >= 0) pgid[__ldg(tstart + t.y) + sl.y] = g.y;
-    if (t.z >= 0) pgid[__ldg(tstart + t.z) + sl.z] = g.z;
-    if (t.w >= 0) pgid[__ldg(tstart + t.w) + sl.w] = g.w;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// render: binning, sort-free (the default).  The Gaussian-major pair list is put in tile order by a STABLE
+// The Gaussian-major pair list (pair q of a Gaussian = tile q of its box, row-major) is put in tile order by a STABLE
 // least-significant-digit radix sort on the tile id — stable, so inside a tile the pairs keep the Gaussian (= depth)
 // order they were emitted in: exactly the reference's stable torch.sort of the expanded list (gs_model.py:547),
-// bit for bit, with no atomic on a tile counter (3.6 M returning atomics cost the slot route ~45 us per 1080p view,
-// twice that on the bundled scene whose 8 600 tiles are hit ~500 times each) and no sort afterwards.
+// bit for bit, with no atomic on a tile counter and no sort afterwards.  (Round 2's first binning took a slot per
+// pair from an atomic counter per tile and then sorted every tile's list by Gaussian id: 3.6 M returning atomics cost
+// ~45 us per 1080p view, twice that on the bundled scene whose 8 600 tiles are hit ~500 times each, and the lists of
+// thousands of ids needed block-wide sorts — 126 / 228 us against 102 / 104 us now.)
 //   k_view_pairs        : pair q -> (tile, Gaussian), 16 consecutive pairs per thread (one binary search for the
 //                         owner of the first, then a walk); per-block histogram of the first digit
 //   per digit           : k_view_scan over the [digit][block] counts -> where every block's run of every digit
@@ -638,9 +567,8 @@ k_view_bin_scatter(const int2 *__restrict__ in, const int32_t *__restrict__ gbas
     }
 }
 
-// first index i in [0, P) with keys[i] >= t (P if none)
-__device__ __forceinline__ int lower_bound_tile(const int32_t *__restrict__ keys, int P, int t) {
-    int lo = 0, hi = P;
+// first index i in [lo, hi) with keys[i] >= t (hi if none)
+__device__ __forceinline__ int lower_bound_in(const int32_t *__restrict__ keys, int lo, int hi, int t) {
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
         if (__ldg(keys + mid) < t) lo = mid + 1;
@@ -648,20 +576,32 @@ __device__ __forceinline__ int lower_bound_tile(const int32_t *__restrict__ keys
     }
     return lo;
 }
+// where the pairs of tile t start in the sorted list: searched only inside the run of t's last digit, whose bounds
+// the last pass's scan left in gbase ([digit][block] offsets: the run of digit d starts at gbase[d * nb])
+__device__ __forceinline__ int tile_lower_bound(const int32_t *__restrict__ keys, const int32_t *__restrict__ gbase,
+                                                int shift, int nbins, int nb, int P, int t) {
+    if (gbase == nullptr) return lower_bound_in(keys, 0, P, t);
+    const int d = t >> shift;
+    if (d >= nbins) return P;
+    const int lo = __ldg(gbase + static_cast<int64_t>(d) * nb);
+    const int hi = d + 1 < nbins ? __ldg(gbase + static_cast<int64_t>(d + 1) * nb) : P;
+    return lower_bound_in(keys, lo, hi, t);
+}
 
 // one thread per tile: its range in the tile-ordered pair list and its pieces (see "Work units" below)
 __global__ void __launch_bounds__(256)
-k_view_tiles(const int32_t *__restrict__ keys, int ntiles, int piece, int64_t cap, unsigned int *__restrict__ hdr,
-             int32_t *__restrict__ tcount, int32_t *__restrict__ tstart, int32_t *__restrict__ pextra,
-             int32_t *__restrict__ ptile_x, int32_t *__restrict__ mlist) {
+k_view_tiles(const int32_t *__restrict__ keys, const int32_t *__restrict__ gbase, int shift, int nbins, int nb,
+             int ntiles, int piece, int64_t cap, unsigned int *__restrict__ hdr, int32_t *__restrict__ tcount,
+             int32_t *__restrict__ tstart, int32_t *__restrict__ pextra, int32_t *__restrict__ ptile_x,
+             int32_t *__restrict__ mlist) {
     if (overflowed(hdr, cap)) return;
     const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int tt = t < ntiles ? t : ntiles;
-    const int lo = lower_bound_tile(keys, P, tt);
+    const int lo = tile_lower_bound(keys, gbase, shift, nbins, nb, P, tt);
     int hi = __shfl_down_sync(0xffffffffu, lo, 1);          // the next tile's lower bound ...
-    if (lane == 31) hi = lower_bound_tile(keys, P, tt + 1);  // ... which the last lane has to find itself
+    if (lane == 31) hi = tile_lower_bound(keys, gbase, shift, nbins, nb, P, tt + 1);   // ... the last lane finds itself
     if (t > ntiles) return;
     tstart[t] = lo;
     if (t == ntiles) return;
@@ -678,88 +618,6 @@ k_view_tiles(const int32_t *__restrict__ keys, int ntiles, int piece, int64_t ca
     pextra[t] = x;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// render: order inside the tiles.  A tile's segment holds distinct Gaussian ids in arbitrary order; sorted
-// ascending it is exactly what a stable sort of the Gaussian-major pair list by tile produces.
-//  * lists of up to SORT_REGS = 512 ids: one warp, the ids in registers (E = 1..16 per lane, index e*32 + lane,
-//    padded with INT_MAX), the classic bitonic network — partners in another lane through SHFL.BFLY, partners in
-//    the same lane as register compare-exchanges; ~3 instructions per id and step, no shared memory;
-//  * longer lists (bundled scene: thousands of Gaussians over one tile): one block each, the flip form of the
-//    network in place in global memory (ascending compare-exchanges only, so a length that is not a power of two
-//    needs no padding: a partner index beyond the end counts as +infinity and never moves).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int SORT_REGS = 512;
-
-template <int E>
-__device__ __forceinline__ void warp_bitonic_sort(int32_t (&v)[E], int lane) {
-    constexpr int N = 32 * E;
-#pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {   // partner in the same lane: registers e and e ^ (j / 32)
-                const int je = j >> 5;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if ((e & je) == 0) {
-                        const bool asc = ((e * 32) & k) == 0;   // k >= 64 here: the direction depends on e only
-                        const int32_t a = v[e], b = v[e | je];
-                        const int32_t lo = min(a, b), hi = max(a, b);
-                        v[e] = asc ? lo : hi;
-                        v[e | je] = asc ? hi : lo;
-                    }
-                }
-            } else {
-                const bool upper = (lane & j) != 0;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const bool asc = (((e * 32) | lane) & k) == 0;
-                    const int32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
-                    v[e] = (asc != upper) ? min(v[e], o) : max(v[e], o);
-                }
-            }
-        }
-    }
-}
-template <int E>
-__device__ __forceinline__ void sort_segment(int32_t *seg, int len, int lane) {
-    int32_t v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = (e * 32 + lane < len) ? seg[e * 32 + lane] : 0x7fffffff;
-    warp_bitonic_sort<E>(v, lane);
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-        if (e * 32 + lane < len) seg[e * 32 + lane] = v[e];
-}
-
-template <typename Sync>
-__device__ __forceinline__ void bitonic_ascending(int32_t *s, int len, int tid, int nthreads, Sync sync) {
-    int N = 2;
-    while (N < len) N <<= 1;
-    for (int k = 2; k <= N; k <<= 1) {
-        const int hs = 31 - __clz(k >> 1);   // log2(k / 2)
-        for (int i = tid; i < N / 2; i += nthreads) {
-            const int blk = i >> hs, off = i & ((k >> 1) - 1);
-            const int a = blk * k + off, b = blk * k + k - 1 - off;
-            if (b < len) {
-                const int32_t x = s[a], y = s[b];
-                if (x > y) { s[a] = y; s[b] = x; }
-            }
-        }
-        sync();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = tid; i < N / 2; i += nthreads) {
-                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1)), b = a + j;
-                if (b < len) {
-                    const int32_t x = s[a], y = s[b];
-                    if (x > y) { s[a] = y; s[b] = x; }
-                }
-            }
-            sync();
-        }
-    }
-}
-
 // Work units of the walk kernels are PIECES: at most `piece` consecutive pairs of one tile's list (a multiple of
 // 32).  Most tiles are one piece: work item t.  A tile with a longer list (bundled scene: thousands of Gaussians
 // over one tile, ten times the mean) is cut into np pieces walked by different warps at the same time, each
@@ -772,161 +630,6 @@ __device__ __forceinline__ void bitonic_ascending(int32_t *s, int len, int tid, 
 //             its aggregate and its colour, so the backward needs no pass of its own for them  (k_view_combine_bwd)
 // piece state per slot (f32[192]): {Tagg[32], C0[32], C1[32], C2[32], carry[32], U_in[32]}.
 constexpr int PIECE_STATE = 192;
-
-__global__ void __launch_bounds__(256)
-k_view_sort(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int ntiles, int piece, int64_t cap,
-            unsigned int *__restrict__ hdr, int32_t *__restrict__ pgid, int32_t *__restrict__ pextra,
-            int32_t *__restrict__ ptile_x, int32_t *__restrict__ mlist, int32_t *__restrict__ longlist) {
-    if (overflowed(hdr, cap)) return;
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (t >= ntiles) return;
-    const int len = __ldg(tcount + t), base = __ldg(tstart + t);
-    if (lane == 0) {
-        int x = -1;
-        if (len > piece) {
-            const int np = (len + piece - 1) / piece;
-            x = static_cast<int>(atomicAdd(hdr + H_XPIECES, static_cast<unsigned>(np)));
-            ptile_x[x] = -1;
-            for (int k = 1; k < np; ++k) ptile_x[x + k] = t;
-            mlist[atomicAdd(hdr + H_NMULTI, 1u)] = t;
-        }
-        pextra[t] = x;
-        if (len > SORT_REGS) longlist[atomicAdd(hdr + H_NLONG, 1u)] = t;
-    }
-    int32_t *seg = pgid + base;
-    if (len < 2 || len > SORT_REGS) return;   // warp-uniform
-    if (len <= 32) sort_segment<1>(seg, len, lane);
-    else if (len <= 64) sort_segment<2>(seg, len, lane);
-    else if (len <= 128) sort_segment<4>(seg, len, lane);
-    else if (len <= 256) sort_segment<8>(seg, len, lane);
-    else sort_segment<16>(seg, len, lane);
-}
-
-// lists longer than SORT_REGS.  Up to SORT_BLOCK = 8 warps x 512 ids: one block, the ids in registers.  Every
-// warp sorts its 512-id chunk with the register network, alternating directions, then the chunks are merged: in a
-// merge stage the partners at distance >= 512 sit in another warp (same lane, same register) and are exchanged
-// through shared memory, the distances below 512 are the register / shuffle steps again.  Only as many warps as
-// the list needs take part (a power of two).  Longer lists (the bundled scene's longest has 7 656 ids) go through
-// shared memory as a whole (up to SORT_SMEM ids), and what does not fit is sorted in place in global memory.
-constexpr int SORT_WARPS = 8;
-constexpr int SORT_BLOCK = SORT_WARPS * SORT_REGS;   // 4096
-constexpr int SORT_SMEM = 24576;                     // ids = 96 KB of dynamic shared memory (k_view_sort_huge)
-
-// the steps j = 256 .. 1 of a merge stage whose direction is the same for the whole warp
-template <int E>
-__device__ __forceinline__ void warp_bitonic_merge(int32_t (&v)[E], int lane, bool asc) {
-#pragma unroll
-    for (int j = (32 * E) >> 1; j > 0; j >>= 1) {
-        if (j >= 32) {
-            const int je = j >> 5;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if ((e & je) == 0) {
-                    const int32_t a = v[e], b = v[e | je];
-                    const int32_t lo = min(a, b), hi = max(a, b);
-                    v[e] = asc ? lo : hi;
-                    v[e | je] = asc ? hi : lo;
-                }
-            }
-        } else {
-            const bool upper = (lane & j) != 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
-                v[e] = (asc != upper) ? min(v[e], o) : max(v[e], o);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SORT_WARPS * 32)
-k_view_sort_long(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
-                 const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
-    constexpr int E = SORT_REGS / 32;
-    __shared__ int32_t s_x[SORT_BLOCK];
-    if (overflowed(hdr, cap)) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int nl = hdr[H_NLONG];
-    for (unsigned int i = blockIdx.x; i < nl; i += gridDim.x) {
-        const int t = longlist[i];
-        const int len = tcount[t];
-        if (len > SORT_BLOCK) continue;   // k_view_sort_huge
-        int32_t *seg = pgid + tstart[t];
-        int nw = 2;
-        while (nw * SORT_REGS < len) nw <<= 1;
-        const bool active = warp < nw;   // warp-uniform
-        int32_t v[E];
-        if (active) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int k = warp * SORT_REGS + e * 32 + lane;
-                v[e] = k < len ? seg[k] : 0x7fffffff;
-            }
-            warp_bitonic_sort<E>(v, lane);                 // ascending ...
-            if (warp & 1) {                                // ... odd chunks descending: reverse them
-#pragma unroll
-                for (int e = 0; e < E / 2; ++e) {
-                    const int32_t a = __shfl_sync(0xffffffffu, v[e], 31 - lane);
-                    const int32_t b = __shfl_sync(0xffffffffu, v[E - 1 - e], 31 - lane);
-                    v[e] = b; v[E - 1 - e] = a;
-                }
-            }
-        }
-        for (int k = 2 * SORT_REGS; k <= nw * SORT_REGS; k <<= 1) {
-            const bool asc = ((warp * SORT_REGS) & k) == 0;
-            for (int j = k >> 1; j >= SORT_REGS; j >>= 1) {
-                if (active) {
-#pragma unroll
-                    for (int e = 0; e < E; ++e) s_x[warp * SORT_REGS + e * 32 + lane] = v[e];
-                }
-                __syncthreads();
-                if (active) {
-                    const int pw = warp ^ (j / SORT_REGS);
-                    const bool upper = (warp * SORT_REGS) & j;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int32_t o = s_x[pw * SORT_REGS + e * 32 + lane];
-                        v[e] = (asc != upper) ? min(v[e], o) : max(v[e], o);
-                    }
-                }
-                __syncthreads();
-            }
-            if (active) warp_bitonic_merge<E>(v, lane, asc);
-        }
-        if (active) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int k = warp * SORT_REGS + e * 32 + lane;
-                if (k < len) seg[k] = v[e];
-            }
-        }
-    }
-}
-
-constexpr int SORT_HUGE_THREADS = 1024;
-__global__ void __launch_bounds__(SORT_HUGE_THREADS)
-k_view_sort_huge(const int32_t *__restrict__ tcount, const int32_t *__restrict__ tstart, int64_t cap,
-                 const unsigned int *__restrict__ hdr, const int32_t *__restrict__ longlist, int32_t *pgid) {
-    extern __shared__ int32_t s_ids[];
-    if (overflowed(hdr, cap)) return;
-    const unsigned int nl = hdr[H_NLONG];
-    for (unsigned int i = blockIdx.x; i < nl; i += gridDim.x) {
-        const int t = longlist[i];
-        const int len = tcount[t];
-        if (len <= SORT_BLOCK) continue;   // k_view_sort_long
-        int32_t *seg = pgid + tstart[t];
-        if (len <= SORT_SMEM) {
-            for (int k = threadIdx.x; k < len; k += blockDim.x) s_ids[k] = seg[k];
-            __syncthreads();
-            bitonic_ascending(s_ids, len, threadIdx.x, blockDim.x, [] { __syncthreads(); });
-            for (int k = threadIdx.x; k < len; k += blockDim.x) seg[k] = s_ids[k];
-            __syncthreads();
-        } else {
-            bitonic_ascending(seg, len, threadIdx.x, blockDim.x, [] { __syncthreads(); });
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // the walks
@@ -1537,7 +1240,6 @@ k_view_reduce_big(const float *__restrict__ partial, const int32_t *__restrict__
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 int g_piece = 128;  // pairs per piece (gcp_tile_set_piece_pairs)
-int g_binning = 1;  // 1: stable radix sort by tile (default); 0: atomic slots + per-tile sort (gcp_tile_set_binning)
 
 inline bool bad_image(int W, int H) { return W < 0 || H < 0 || W >= 32768 || H >= 32768; }
 inline int tiles_x(int W) { return (W + TW) >> TSX; }  // ceil((W+1)/TW): pixels 0..W inclusive (gs_model.py:505)
@@ -1545,18 +1247,16 @@ inline int tiles_y(int H) { return (H + TH) >> TSY; }
 
 // plan arena: everything whose size is known from (n, W, H) alone.  [0, zero_bytes) is cleared by gcp_view_plan.
 struct PlanLayout {
-    size_t hdr, desc1, desc2, tcount, zero_bytes, cnt, tbox, toff, tstart, pextra, mlist, longlist, big, rec, total;
-    unsigned nb1, nb2;
+    size_t hdr, desc1, tcount, zero_bytes, cnt, tbox, toff, tstart, pextra, mlist, big, rec, total;
+    unsigned nb1;
 };
 PlanLayout plan_layout(int64_t n, int ntiles) {
     PlanLayout L;
     L.nb1 = blocks_for(n, SCAN_TILE);
-    L.nb2 = blocks_for(ntiles, SCAN_TILE);
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
     L.hdr = take(HDR_WORDS * 4);
     L.desc1 = take(static_cast<size_t>(L.nb1) * 8);
-    L.desc2 = take(static_cast<size_t>(L.nb2) * 8);
     L.tcount = take(static_cast<size_t>(ntiles) * 4);
     L.zero_bytes = o;
     L.cnt = take(static_cast<size_t>(n > 0 ? n : 1) * 4);
@@ -1565,7 +1265,6 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
     L.tstart = take(static_cast<size_t>(ntiles + 1) * 4);
     L.pextra = take(static_cast<size_t>(ntiles) * 4);
     L.mlist = take(static_cast<size_t>(ntiles) * 4);
-    L.longlist = take(static_cast<size_t>(ntiles) * 4);
     L.big = take(static_cast<size_t>(n > 0 ? n : 1) * 4);
     L.rec = take(static_cast<size_t>(n > 0 ? n : 1) * 64);
     L.total = o;
@@ -1589,7 +1288,7 @@ BinPlan bin_plan(int64_t cap, int ntiles) {
     return b;
 }
 struct PairLayout {
-    size_t pgid, tck, ptile_x, pstate, partial, bin_pg, bin_pt, bin_ps, total;
+    size_t pgid, tck, ptile_x, pstate, partial, total;
     size_t rb[2], rb_hist, rb_base, rb_desc, rb_bstart;   // radix route
     int64_t xcap;
 };
@@ -1604,12 +1303,6 @@ PairLayout pair_layout(int64_t cap, int ntiles) {
     L.ptile_x = take(static_cast<size_t>(L.xcap) * 4);
     L.pstate = take(static_cast<size_t>(L.xcap) * PIECE_STATE * 4);
     L.partial = take(static_cast<size_t>(cap) * 32);
-    const size_t end_partial = o;
-    const size_t third = align256(static_cast<size_t>(cap + QPT) * 4);   // 3 * third <= 32 * cap for cap >= 16
-    L.bin_pg = L.partial;
-    L.bin_pt = L.partial + third;
-    L.bin_ps = L.partial + 2 * third;
-    if (L.partial + 3 * third > o) o = L.partial + 3 * third;
     {
         const BinPlan b = bin_plan(cap, ntiles);
         const size_t cells = (static_cast<size_t>(1) << b.bits) * b.nb;
@@ -1622,7 +1315,6 @@ PairLayout pair_layout(int64_t cap, int ntiles) {
         L.rb_bstart = rtake(static_cast<size_t>(b.nb + 1) * 4);
         if (r > o) o = r;
     }
-    (void)end_partial;
     L.total = o;
     return L;
 }
@@ -1703,12 +1395,6 @@ int gcp_tile_set_piece_pairs(int pairs) {
     return GCP_OK;
 }
 int gcp_tile_piece_pairs(void) { return g_piece; }
-int gcp_tile_set_binning(int mode) {
-    if (mode != 0 && mode != 1) return GCP_ERR_INVALID_ARG;
-    g_binning = mode;
-    return GCP_OK;
-}
-int gcp_tile_binning(void) { return g_binning; }
 int gcp_view_last_launch_count(void) { return t_view_launches; }
 
 size_t gcp_view_plan_bytes(int64_t n, int W, int H) {
@@ -1773,7 +1459,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     int32_t *pextra = at<int32_t>(plan, A.pextra), *ptile_x = at<int32_t>(pairs, B.ptile_x);
     int32_t *pgid = at<int32_t>(pairs, B.pgid);
     int4 *rec = at<int4>(plan, A.rec);
-    int32_t *bstart = g_binning == 1 ? at<int32_t>(pairs, B.rb_bstart) : nullptr;
+    int32_t *bstart = at<int32_t>(pairs, B.rb_bstart);
     const int bcount = bin_plan(pair_cap < 16 ? 16 : pair_cap, ntiles).nb + 1;
     if (n > 0) {
         if (((reinterpret_cast<uintptr_t>(mean) & 7) | (reinterpret_cast<uintptr_t>(lam) & 15)) == 0)
@@ -1784,7 +1470,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
                                                                    at<int32_t>(plan, A.toff), rec, bstart, bcount);
         ++t_view_launches;
     }
-    if (n > 0 && g_binning == 1) {
+    if (n > 0) {
         // stable radix sort of the pair list by tile: no atomics on tile counters, no sort afterwards
         const BinPlan bp = bin_plan(pair_cap < 16 ? 16 : pair_cap, ntiles);
         const int nbins = 1 << bp.bits;
@@ -1816,36 +1502,17 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
             launch_bin_scatter(k + 1 == bp.passes, bp, smem, st, in, gbase, k * bp.bits, pair_cap, hdr, out, pgid);
             t_view_launches += 2;
         }
-        k_view_tiles<<<blocks_for(ntiles + 1, 256), 256, 0, st>>>(at<int32_t>(pairs, B.rb[bp.passes & 1]), ntiles,
-                                                                  g_piece, pair_cap, hdr, tcount, tstart, pextra, ptile_x,
+        k_view_tiles<<<blocks_for(ntiles + 1, 256), 256, 0, st>>>(at<int32_t>(pairs, B.rb[bp.passes & 1]), gbase,
+                                                                  (bp.passes - 1) * bp.bits, nbins, bp.nb, ntiles, g_piece,
+                                                                  pair_cap, hdr, tcount, tstart, pextra, ptile_x,
                                                                   at<int32_t>(plan, A.mlist));
         ++t_view_launches;
     } else {
-        if (n > 0) {
-            int32_t *pg = at<int32_t>(pairs, B.bin_pg), *pt = at<int32_t>(pairs, B.bin_pt), *ps = at<int32_t>(pairs, B.bin_ps);
-            k_view_slots<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(rec, at<int32_t>(plan, A.toff), n, ntx, pair_cap,
-                                                                          hdr, tcount, pg, pt, ps);
-            k_view_scan<<<A.nb2, SCAN_THREADS, 0, st>>>(tcount, ntiles, tstart, hdr + H_TICKET_S2,
-                                                        at<unsigned long long>(plan, A.desc2),
-                                                        reinterpret_cast<unsigned long long *>(hdr) + H_T64, nullptr);
-            k_view_scatter<<<blocks_for(pair_cap, 256 * QPT), 256, 0, st>>>(pg, pt, ps, tstart, pair_cap, hdr, pgid);
-            t_view_launches += 3;
-        } else {
-            cudaError_t e = cudaMemsetAsync(tstart, 0, static_cast<size_t>(ntiles + 1) * 4, st);
-            if (e != cudaSuccess) return static_cast<int>(e);
-        }
-        k_view_sort<<<blocks_for(ntiles, 8), 256, 0, st>>>(tcount, tstart, ntiles, g_piece, pair_cap, hdr, pgid, pextra,
-                                                           ptile_x, at<int32_t>(plan, A.mlist),
-                                                           at<int32_t>(plan, A.longlist));
-        static bool attr_set = false;   // (per process; setting the attribute again costs nothing)
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_view_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM * 4);
-            attr_set = true;
-        }
-        const int32_t *ll = at<int32_t>(plan, A.longlist);
-        k_view_sort_long<<<148 * 4, SORT_WARPS * 32, 0, st>>>(tcount, tstart, pair_cap, hdr, ll, pgid);
-        k_view_sort_huge<<<148, SORT_HUGE_THREADS, SORT_SMEM * 4, st>>>(tcount, tstart, pair_cap, hdr, ll, pgid);
-        t_view_launches += 3;
+        // no Gaussians: every tile's list is empty (P = 0: nothing is read)
+        k_view_tiles<<<blocks_for(ntiles + 1, 256), 256, 0, st>>>(nullptr, nullptr, 0, 1, 1, ntiles, g_piece, pair_cap, hdr,
+                                                                  tcount, tstart, pextra, ptile_x,
+                                                                  at<int32_t>(plan, A.mlist));
+        ++t_view_launches;
     }
     float *tck = at<float>(pairs, B.tck), *pstate = at<float>(pairs, B.pstate);
     if (keep) {

@@ -310,18 +310,6 @@ def test_planned_view_equals_unplanned_gpu(route):
             assert torch.equal(a, b)
 
 
-@pytest.fixture(params=[1, 0], ids=["radix", "slots"])
-def binning(request):
-    """gcp_tile_set_binning: 1 = stable radix sort of the pair list by tile (the default), 0 = atomic slots + a sort
-    of every tile's list."""
-    from simplegaussiansplat_tk71_b200 import _lib
-
-    L = _lib.lib()
-    assert L.gcp_tile_set_binning(request.param) == 0
-    yield request.param
-    L.gcp_tile_set_binning(1)
-
-
 def _arena_arrays(L, view, W, H):
     """The integer arrays of a rendered tile-route view, read out of its two arenas (gcp_view_layout)."""
     import ctypes
@@ -339,13 +327,12 @@ def _arena_arrays(L, view, W, H):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["wide", "dense", "opaque"])
-def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch, binning):
+def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch):
     """Integer side of the tile route: pair offsets per Gaussian, pairs per tile, every tile's list in the order
     of a stable sort by tile, the tile offsets and the pieces of long lists, against the numpy restatement
     (oracle/tile_oracle.py, itself pinned on CPU to the reference's sorted element list by
     tests/test_compositor_oracle.py).  The native binning is a stable radix sort of the Gaussian-major pair list by
-    tile (or, binning 0, atomic slots followed by a sort of every tile's segment by Gaussian id): the RESULT must be
-    the stable sort, bit for bit."""
+    tile id: the RESULT must be the stable sort, bit for bit."""
     from oracle import tile_oracle as to
     from simplegaussiansplat_tk71_b200 import _lib, compositor
 
@@ -395,9 +382,8 @@ def test_tile_pair_list_is_bit_exact_gpu(name, monkeypatch, binning):
 
 
 @pytest.mark.gpu
-def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch, binning):
-    """Tile lists of thousands of pairs (bundled scene; with binning 0 they go through the block-per-tile sorts):
-    still the stable order."""
+def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch):
+    """Tile lists of thousands of pairs (bundled scene): still the stable order."""
     from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
@@ -410,8 +396,7 @@ def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch, binning):
         a = _arena_arrays(L, view, v.width, v.height)
         assert a["tcount"].max() > 2048, "this scene is expected to have long tile lists"
         assert int(a["tcount"].sum()) == view.P
-        # every segment of every tile strictly increasing (distinct Gaussian ids in depth order): lists of up to 512
-        # ids are sorted by one warp, up to 4096 by one block in registers, longer ones through shared memory
+        # every segment of every tile strictly increasing (distinct Gaussian ids in depth order)
         d = np.diff(a["pgid"][:view.P].astype(np.int64))
         ends = (a["tstart"][:-1] + a["tcount"])[a["tcount"] > 0] - 1          # last pair of every non-empty tile
         inner = np.ones(max(view.P - 1, 0), bool)
@@ -441,12 +426,14 @@ def test_tile_binning_of_long_lists_is_bit_exact_gpu(monkeypatch, binning):
                                             (16383, 4095, 20_000, 40), (5, 3, 40, 3), (2047, 2047, 3_000, 600),
                                             (1279, 719, 30_000, 12)],
                          ids=["1080p-2x8bit", "4k-2x9bit", "2M-tiles-3x7bit", "one-tile-1bit", "big-boxes", "holes"])
-def test_radix_binning_equals_slot_binning_bitwise_gpu(W, H, n, max_half, monkeypatch):
-    """The two binnings of the tile route build the same tile-ordered pair list, bit for bit, whatever the number of
-    digit passes the tile count asks for (1080p: 2 x 8 bits, 4K: 2 x 9, 2 Mi tiles: 3 x 7, one tile: 1 x 1), and so
-    the same image and gradients."""
+def test_radix_binning_is_the_stable_sort_by_tile_gpu(W, H, n, max_half, monkeypatch):
+    """The binning of the tile route — a stable radix sort of the Gaussian-major pair list on the tile id — against
+    the numpy restatement (oracle/tile_oracle.py: numpy.argsort(kind="stable")), bit for bit: pair offsets, pairs
+    per tile, tile offsets and every tile's list, whatever the number of digit passes the tile count asks for
+    (1080p: 2 x 8 bits, 4K: 2 x 9, 2 Mi tiles: 3 x 7, one tile: 1 x 1), for boxes of thousands of tiles, and for
+    long runs of Gaussians without any pair (the global-memory path of k_view_pairs)."""
+    from oracle import tile_oracle as to
     from simplegaussiansplat_tk71_b200 import _lib, compositor, workloads as wl
-    from simplegaussiansplat_tk71_b200.compositor import custom_autograd_grouped_cumprod as F
 
     monkeypatch.setattr(compositor, "ROUTE", "tiles")
     L = _lib.lib()
@@ -470,28 +457,19 @@ def test_radix_binning_equals_slot_binning_bitwise_gpu(W, H, n, max_half, monkey
                          endpoint=t(ep), mean=t(c.astype(np.float32)), lam=t(lam),
                          opacity=t(rng.uniform(0.01, 0.3, (n, 1)).astype(np.float32)),
                          l_d=t(rng.uniform(0.2, 1.0, (n, 3)).astype(np.float32)), width=W, height=H)
-    gI = torch.rand(v.height + 1, v.width + 1, 3, device="cuda") + 0.1
-    res = []
-    try:
-        for mode in (0, 1):
-            assert L.gcp_tile_set_binning(mode) == 0 and L.gcp_tile_binning() == mode
-            m, lam_, o, l = (v.mean.float().clone().requires_grad_(True), v.lam.clone().requires_grad_(True),
-                             v.opacity.clone().requires_grad_(True), v.l_d.clone().requires_grad_(True))
-            img = F.apply(v.boxsize, torch.tensor([v.n]), v.startpoint, v.endpoint, m, lam_, o, l, v.width, v.height)
-            view = img.grad_fn.view
-            torch.cuda.synchronize()
-            a = _arena_arrays(L, view, v.width, v.height)
-            ints = [a["tcount"].copy(), a["tstart"].copy(), a["pgid"][:view.P].copy()]
-            img.backward(gI)
-            res.append((ints, [img.detach().clone()] + [t_.grad.clone() for t_ in (m, lam_, o, l)]))
-            del img, view
-    finally:
-        L.gcp_tile_set_binning(1)
-    assert int(res[0][0][0].sum()) > 0
-    for x, y in zip(res[0][0], res[1][0]):
-        assert np.array_equal(x, y)
-    for x, y in zip(res[0][1], res[1][1]):
-        assert torch.equal(x, y)
+    img, view = compositor._render_forward(v.boxsize, v.startpoint, v.endpoint, v.mean.float(), v.lam, v.opacity, v.l_d,
+                                           v.width, v.height)
+    torch.cuda.synchronize()
+    assert torch.isfinite(img).all()
+    a = _arena_arrays(L, view, v.width, v.height)
+    ntx, nty = to.num_tiles(W, H)
+    tiles, gids, toff = to.tile_pairs_np(v.startpoint.cpu().numpy(), v.endpoint.cpu().numpy(), W, H)
+    gid_s, start, _ = to.sort_by_tile(tiles, gids, ntx * nty)
+    assert view.P == len(tiles) > 0
+    assert np.array_equal(a["toff"], toff.astype(np.int32))
+    assert np.array_equal(a["tstart"], start)
+    assert np.array_equal(a["tcount"], np.diff(start))
+    assert np.array_equal(a["pgid"][:view.P], gid_s)
 
 
 def _both_routes(v, gI, monkeypatch, repeats=1):

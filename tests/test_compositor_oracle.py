@@ -114,3 +114,9 @@ def test_tile_binning_random_boxes_and_image_sizes():
         ntx, nty = to.num_tiles(W, H)
         assert tiles.size == 0 or (tiles.min() >= 0 and tiles.max() < ntx * nty)
         assert np.array_equal(np.diff(toff), np.bincount(gids, minlength=n))
+        # the loop-free restatement used for large views (with some empty boxes thrown in): the same arrays
+        ep2 = ep.copy()
+        ep2[::5, 0] = sp[::5, 0] - 1
+        for e in (ep, ep2):
+            for a, b in zip(to.tile_pairs(sp, e, W, H), to.tile_pairs_np(sp, e, W, H)):
+                assert a.dtype == b.dtype and np.array_equal(a, b)

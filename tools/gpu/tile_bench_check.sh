@@ -1,6 +1,7 @@
 #!/bin/bash
+# compositor + batch + full-size tests, per-kernel breakdown of both scenes, a short bench (no CPU / reference legs)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_compositor.py tests/test_views_native.py -x -q -m gpu > gpurun_out/comp.log 2>&1; echo "compositor tests rc=$?"; tail -3 gpurun_out/comp.log
+timeout 1200 python -m pytest tests/test_compositor.py tests/test_views_native.py tests/test_gpu_fullsize.py tests/test_abi.py -x -q -m gpu > gpurun_out/comp.log 2>&1; echo "compositor tests rc=$?"; tail -3 gpurun_out/comp.log
 SPLAT_PROFILE=1 python tools/splat_time.py --route tiles --steps 6 2>&1 | grep "k_view\|splat step" | cut -c1-70,150-215 > gpurun_out/tile_breakdown.log
 SPLAT_PROFILE=1 python tools/splat_time.py --route tiles --c2 0 --steps 6 2>&1 | grep "k_view\|splat step" | cut -c1-70,150-215 >> gpurun_out/tile_breakdown.log
 cat gpurun_out/tile_breakdown.log

@@ -17,11 +17,7 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--c2", type=int, default=-1, help="use view K of the bundled-scene workload (C2) instead")
 ap.add_argument("--route", default=None, help="compositor route: tiles | lists (default: compositor.ROUTE)")
-ap.add_argument("--binning", type=int, default=-1, help="tile route: 1 = radix sort by tile, 0 = atomic slots + sort")
 a = ap.parse_args()
-if a.binning >= 0:
-    from simplegaussiansplat_tk71_b200 import _lib  # noqa: E402
-    _lib.check(_lib.lib().gcp_tile_set_binning(a.binning), "gcp_tile_set_binning")
 if a.route:
     from simplegaussiansplat_tk71_b200 import compositor  # noqa: E402
     compositor.ROUTE = a.route
