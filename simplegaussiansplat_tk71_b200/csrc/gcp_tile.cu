@@ -13,7 +13,7 @@
 //             k_view_scan     : their exclusive offsets (chained scan); the pair total goes to the host (.item() :348)
 //   render    k_view_pack     : packed per-Gaussian records
 //             k_view_pairs    : pair q of the Gaussian-major numbering -> {tile, Gaussian}
-//             k_view_scan + k_view_bin_scatter (+ k_view_bin_hist) per digit: a STABLE radix sort of the pairs by
+//             k_view_bin_rowscan + k_view_bin_scatter (+ k_view_bin_hist) per digit: a STABLE radix sort of the pairs by
 //                               tile id — inside a tile the pairs keep the Gaussian (= depth) order, which is the
 //                               stable torch.sort of the reference, bit for bit                (gs_model.py:538-548)
 //             k_view_tiles    : every tile's range in the sorted list; long lists are cut into pieces (the walk
@@ -60,9 +60,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255);
 // ---- arena headers (u32 words; zeroed by gcp_view_plan) ----
 constexpr int H_TICKET_S1 = 0, H_TICKET_FWD = 2, H_XPIECES = 3, H_NMULTI = 4;
 constexpr int H_TICKET_BWD = 6, H_NBIG = 7, H_TICKET_RED = 8;   // adjacent u32 words: reset together by every backward
-constexpr int H_TICKET_BIN = 10;                // .. 12: scan tickets of the (up to three) radix passes of the binning
 constexpr int H_P64 = 8;                        // u64 index (byte 64): the pair count of the view
-constexpr int H_B64 = 12;                       // u64 index (byte 96): sink for the totals of the radix passes' scans
 constexpr int HDR_WORDS = 64;
 
 // box of Gaussian g clipped to the image [0,W] x [0,H] (the caller clamps already, gs_model.py:419-425)
@@ -90,6 +88,8 @@ __device__ __forceinline__ Box clip_box(const int32_t *__restrict__ sp, const in
 constexpr float EXP2_SCALE = -0.72134752044448170368f;    // -log2(e) / 2
 constexpr float EXP2_UNSCALE = -1.38629436111989061883f;  // 1 / EXP2_SCALE
 
+// pairs per Gaussian = tiles its (clipped) box touches (uitility.py:336-366), and {first tile, tiles per row} of the
+// box: what the binning reads instead of the 64-byte records
 __global__ void __launch_bounds__(256)
 k_view_cnt(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64_t n, int W, int H,
            int32_t *__restrict__ cnt, int2 *__restrict__ tbox) {
@@ -100,13 +100,9 @@ k_view_cnt(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, int64
     int c = 0;
     if (b.ex >= b.sx && b.ey >= b.sy) c = nx * ((b.ey >> TSY) - ty0 + 1);
     cnt[g] = c;
-    tbox[g] = make_int2(tx0 | (ty0 << 16), nx);   // first tile and tiles per row of the box: what the binning needs
+    tbox[g] = make_int2(tx0 | (ty0 << 16), nx);
 }
 
-// VEC: mean / lam are 8- / 16-byte aligned (whole tensors; a sliced view may not be) and are read as float2 /
-// float4.  The records of a block's 256 Gaussians are one contiguous 16 KB range: they are staged in shared memory
-// (quarter planes, one 16-byte word per lane and store) and written out as consecutive 16-byte words — a store of
-// a record's quarter straight from its thread touches 32 different 64-byte records per instruction.
 constexpr int BIN_CHUNK_SHIFT = 12;   // the binning's blocks of 4096 pairs (BIN_CHUNK below)
 
 template <bool VEC>
@@ -152,12 +148,15 @@ k_view_pack(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// exclusive offsets (pairs per Gaussian -> toff in the plan, pairs per tile -> tstart in the render): the classic
-// single-pass chained scan — a block publishes its aggregate, then walks back over its predecessors' descriptors
-// (32 per step) to the nearest inclusive prefix.  Tile order comes from an atomic ticket, so a block only ever waits for blocks that
-// are already running.  descriptor = status (2 bits: 1 aggregate, 2 inclusive) << 62 | value.
+// exclusive pair offsets of the Gaussians (toff): the classic single-pass chained scan — a block publishes its
+// aggregate, then walks back over its predecessors' descriptors (32 per step) to the nearest inclusive prefix.  Tile
+// order comes from an atomic ticket, so a block only ever waits for blocks that are already running.
+// descriptor = status (2 bits: 1 aggregate, 2 inclusive) << 62 | value.
+// 8192 Gaussians per block: 1 M Gaussians = 111 blocks, four look-back steps at most (2048 per block: 443 blocks,
+// 14 steps: 16.7 us against 13.6; counting the pairs inside this kernel instead of a kernel of its own, 5.6 us,
+// was slower: 27.7 us — sixteen consecutive boxes per thread are sixteen uncoalesced loads).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+constexpr int SCAN_ITEMS = 16, SCAN_THREADS = 512, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -168,9 +167,9 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ void chained_scan_block(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out,
-                                                   unsigned int *ticket, unsigned long long *desc,
-                                                   unsigned long long *total_dev, int64_t *total_host) {
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_view_scan(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out, unsigned int *ticket,
+            unsigned long long *desc, unsigned long long *total_dev, int64_t *total_host) {
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_tile;
@@ -245,11 +244,6 @@ __device__ __forceinline__ void chained_scan_block(const int32_t *__restrict__ i
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_view_scan(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out, unsigned int *ticket,
-            unsigned long long *desc, unsigned long long *total_dev, int64_t *total_host) {
-    chained_scan_block(in, n, out, ticket, desc, total_dev, total_host);
-}
 // empty views (n == 0): the offsets of nothing
 __global__ void k_view_scan_empty(int32_t *toff, unsigned int *hdr, int64_t *totals_host) {
     if (threadIdx.x == 0) {
@@ -274,8 +268,8 @@ __device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap)
 // thousands of ids needed block-wide sorts — 126 / 228 us against 102 / 104 us now.)
 //   k_view_pairs        : pair q -> (tile, Gaussian), 16 consecutive pairs per thread (one binary search for the
 //                         owner of the first, then a walk); per-block histogram of the first digit
-//   per digit           : k_view_scan over the [digit][block] counts -> where every block's run of every digit
-//                         value starts; k_view_bin_scatter moves the block's 4096 pairs there, ranked inside the
+//   per digit           : k_view_bin_rowscan over the [digit][block] counts -> where every block's run of every
+//                         digit value starts; k_view_bin_scatter moves the block's 4096 pairs there, ranked inside the
 //                         block in list order (a warp takes 512 consecutive pairs, 32 per round: MATCH.ANY gives the
 //                         lanes holding the same digit, the lowest of them bumps the warp's running counter of that
 //                         digit — no atomics; the warps' counters are then offset in warp order); k_view_bin_hist
@@ -366,14 +360,11 @@ __device__ __forceinline__ void emit_pairs(const Source &src, int ng, int g_lo, 
 __global__ void __launch_bounds__(PAIR_THREADS, 3)
 k_view_pairs(const int2 *__restrict__ tbox, const int32_t *__restrict__ toff, const int32_t *__restrict__ bstart,
              int64_t n, int ntx, int64_t cap, const unsigned int *__restrict__ hdr, int bits, int nb,
-             int2 *__restrict__ out, int32_t *__restrict__ hist, unsigned long long *__restrict__ desc,
-             int desc_words) {
+             int2 *__restrict__ out, int32_t *__restrict__ hist) {
     extern __shared__ __align__(16) int s_dyn[];
     int *s_toff = s_dyn;                                               // [PW_GAUSS + 1]
     int2 *s_box = reinterpret_cast<int2 *>(s_dyn + PW_GAUSS + 2);      // [PW_GAUSS] {tx0 | ty0 << 16, nx}
     int *s_cnt = s_dyn + PW_GAUSS + 2 + 2 * PW_GAUSS;                  // [nbins]
-    // the descriptors of the digit scans (used by later kernels of this view only)
-    for (int i = blockIdx.x * PAIR_THREADS + threadIdx.x; i < desc_words; i += gridDim.x * PAIR_THREADS) desc[i] = 0ull;
     if (overflowed(hdr, cap)) return;
     const int nbins = 1 << bits;
     for (int d = threadIdx.x; d < nbins; d += PAIR_THREADS) s_cnt[d] = 0;
@@ -414,6 +405,88 @@ k_view_pairs(const int2 *__restrict__ tbox, const int32_t *__restrict__ toff, co
     for (int d = threadIdx.x; d < nbins; d += PAIR_THREADS) hist[static_cast<int64_t>(d) * nb + blockIdx.x] = s_cnt[d];
 }
 
+// Exclusive scan of nbins (<= 512) ints by a block of 256 threads: s_out[d] = src[0] + .. + src[d-1], s_out[nbins] =
+// the total.  src may be global or shared, and may be s_out itself.  Thread t owns the values [t K, t K + K).
+__device__ __forceinline__ void scan_bins_256(const int *src, int nbins, int *s_out, int *s_wsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = (nbins + BIN_THREADS - 1) / BIN_THREADS;
+    int v[(1 << BIN_MAX_BITS) / BIN_THREADS];
+    int mysum = 0;
+#pragma unroll
+    for (int k = 0; k < (1 << BIN_MAX_BITS) / BIN_THREADS; ++k) {
+        const int d = threadIdx.x * K + k;
+        v[k] = (k < K && d < nbins) ? src[d] : 0;
+        mysum += v[k];
+    }
+    int inc = mysum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    __syncthreads();   // s_wsum free again, every src value read
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int pre = inc - mysum;
+#pragma unroll
+    for (int w = 0; w < BIN_WARPS; ++w)
+        if (w < warp) pre += s_wsum[w];
+#pragma unroll
+    for (int k = 0; k < (1 << BIN_MAX_BITS) / BIN_THREADS; ++k) {
+        const int d = threadIdx.x * K + k;
+        if (k < K && d < nbins) s_out[d] = pre;
+        pre += v[k];
+    }
+    if (threadIdx.x == BIN_THREADS - 1) s_out[nbins] = pre;
+    __syncthreads();
+}
+
+// The [digit value][block] counts of a pass, scanned along the blocks: rowpre[d][b] = pairs with digit value d in the
+// blocks before b, tot[d] = all of them.  One block per digit value, no dependency between blocks (the chained scan
+// over the whole matrix spent 10 us per pass, most of it in its look-back; where a digit value's run starts in the
+// output — the exclusive scan of tot — is 256..512 numbers that every consumer block scans for itself).
+__global__ void __launch_bounds__(BIN_THREADS)
+k_view_bin_rowscan(const int32_t *__restrict__ hist, int nb, int64_t cap, const unsigned int *__restrict__ hdr,
+                   int32_t *__restrict__ rowpre, int32_t *__restrict__ tot) {
+    __shared__ int s_w[BIN_WARPS];
+    if (overflowed(hdr, cap)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t *row = hist + static_cast<int64_t>(blockIdx.x) * nb;
+    int32_t *out = rowpre + static_cast<int64_t>(blockIdx.x) * nb;
+    int carry = 0;
+    for (int c0 = 0; c0 < nb; c0 += BIN_THREADS * 8) {
+        const int b0 = c0 + threadIdx.x * 8;
+        int v[8], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = b0 + i < nb ? __ldg(row + b0 + i) : 0;
+            sum += v[i];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        int pre = carry + inc - sum, all = 0;
+#pragma unroll
+        for (int w = 0; w < BIN_WARPS; ++w) {
+            if (w < warp) pre += s_w[w];
+            all += s_w[w];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (b0 + i < nb) out[b0 + i] = pre;
+            pre += v[i];
+        }
+        carry += all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tot[blockIdx.x] = carry;
+}
+
 __global__ void __launch_bounds__(BIN_THREADS)
 k_view_bin_hist(const int2 *__restrict__ in, int shift, int bits, int nb, int64_t cap,
                 const unsigned int *__restrict__ hdr, int32_t *__restrict__ hist) {
@@ -441,15 +514,17 @@ k_view_bin_hist(const int2 *__restrict__ in, int shift, int bits, int nb, int64_
 // LAST: the final pass writes the Gaussian ids (the tile-ordered pair list) and the tile ids as two int arrays.
 template <bool LAST, int BITS>   // BITS: ballots per rank (>= the digit's bits; 7, 8 or 9)
 __global__ void __launch_bounds__(BIN_THREADS, 3)
-k_view_bin_scatter(const int2 *__restrict__ in, const int32_t *__restrict__ gbase, int shift, int bits, int nb,
-                   int64_t cap, const unsigned int *__restrict__ hdr, int2 *__restrict__ out,
-                   int32_t *__restrict__ out_keys, int32_t *__restrict__ out_gid) {
-    // [BIN_WARPS][nbins] running count per warp and digit value, then its offset | [nbins] start of the digit's run
-    // inside the block | [nbins] start of the block's run of the digit in the output | the sorted pairs
+k_view_bin_scatter(const int2 *__restrict__ in, const int32_t *__restrict__ rowpre, const int32_t *__restrict__ tot,
+                   int shift, int bits, int nb, int64_t cap, const unsigned int *__restrict__ hdr,
+                   int2 *__restrict__ out, int32_t *__restrict__ out_keys, int32_t *__restrict__ out_gid) {
+    // [BIN_WARPS][nbins] running count per warp and digit value, then its offset | [nbins + 1] start of the digit's run
+    // inside the block | [nbins + 1] start of the digit's run in the output | [nbins] start of the block's run of the
+    // digit in the output, relative to its place inside the block | the sorted pairs
     extern __shared__ __align__(16) int s_dyn[];
     if (overflowed(hdr, cap)) return;
     const int nbins = 1 << bits;
-    int *s_wcnt = s_dyn, *s_lstart = s_dyn + BIN_WARPS * nbins, *s_gbase = s_lstart + nbins;
+    int *s_wcnt = s_dyn, *s_lstart = s_dyn + BIN_WARPS * nbins, *s_dstart = s_lstart + nbins + 1;
+    int *s_gbase = s_dstart + nbins + 1;
     int2 *s_stage = reinterpret_cast<int2 *>(s_gbase + nbins);
     __shared__ int s_wsum[BIN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -458,7 +533,7 @@ k_view_bin_scatter(const int2 *__restrict__ in, const int32_t *__restrict__ gbas
     if (base >= P) return;
     const int count = static_cast<int>(min(static_cast<int64_t>(BIN_CHUNK), P - base));
     for (int d = threadIdx.x; d < BIN_WARPS * nbins; d += BIN_THREADS) s_wcnt[d] = 0;
-    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_gbase[d] = __ldg(gbase + static_cast<int64_t>(d) * nb + blockIdx.x);
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_gbase[d] = __ldg(rowpre + static_cast<int64_t>(d) * nb + blockIdx.x);
     __syncthreads();
     int *mine = s_wcnt + warp * nbins;
     const unsigned lt = (1u << lane) - 1u;
@@ -496,52 +571,22 @@ k_view_bin_scatter(const int2 *__restrict__ in, const int32_t *__restrict__ gbas
         __syncwarp();
     }
     __syncthreads();
-    // per digit value: the warps' offsets inside its run; then the runs' starts inside the block (exclusive scan
-    // over the digit values: thread t owns values [t K, t K + K), K = nbins / 256 rounded up)
-    {
-        const int K = (nbins + BIN_THREADS - 1) / BIN_THREADS;
-        int tot[(1 << BIN_MAX_BITS) / BIN_THREADS > 0 ? (1 << BIN_MAX_BITS) / BIN_THREADS : 1];
-        int mysum = 0;
+    // per digit value: the warps' offsets inside its run and the block's total
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) {
+        int run = 0;
 #pragma unroll
-        for (int k = 0; k < (1 << BIN_MAX_BITS) / BIN_THREADS; ++k) {
-            const int d = threadIdx.x * K + k;
-            tot[k] = 0;
-            if (k < K && d < nbins) {
-                int run = 0;
-#pragma unroll
-                for (int w = 0; w < BIN_WARPS; ++w) {
-                    const int c = s_wcnt[w * nbins + d];
-                    s_wcnt[w * nbins + d] = run;
-                    run += c;
-                }
-                tot[k] = run;
-                mysum += run;
-            }
+        for (int w = 0; w < BIN_WARPS; ++w) {
+            const int c = s_wcnt[w * nbins + d];
+            s_wcnt[w * nbins + d] = run;
+            run += c;
         }
-        int inc = mysum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_wsum[warp] = inc;
-        __syncthreads();
-        int pre = inc - mysum;
-#pragma unroll
-        for (int w = 0; w < BIN_WARPS; ++w)
-            if (w < warp) pre += s_wsum[w];
-#pragma unroll
-        for (int k = 0; k < (1 << BIN_MAX_BITS) / BIN_THREADS; ++k) {
-            const int d = threadIdx.x * K + k;
-            if (k < K && d < nbins) {
-                s_lstart[d] = pre;
-                pre += tot[k];
-            }
-        }
+        s_lstart[d] = run;
     }
     __syncthreads();
+    scan_bins_256(s_lstart, nbins, s_lstart, s_wsum);   // -> where the digit value's run starts inside the block
+    scan_bins_256(tot, nbins, s_dstart, s_wsum);        // -> where it starts in the output
     // s_gbase[d] becomes (start of the block's run of d in the output) - (start of d's run inside the block)
-    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_gbase[d] -= s_lstart[d];
+    for (int d = threadIdx.x; d < nbins; d += BIN_THREADS) s_gbase[d] += s_dstart[d] - s_lstart[d];
 #pragma unroll
     for (int r = 0; r < BIN_ROUNDS; ++r) {
         if (it[r].x >= 0) {
@@ -576,32 +621,29 @@ __device__ __forceinline__ int lower_bound_in(const int32_t *__restrict__ keys, 
     }
     return lo;
 }
-// where the pairs of tile t start in the sorted list: searched only inside the run of t's last digit, whose bounds
-// the last pass's scan left in gbase ([digit][block] offsets: the run of digit d starts at gbase[d * nb])
-__device__ __forceinline__ int tile_lower_bound(const int32_t *__restrict__ keys, const int32_t *__restrict__ gbase,
-                                                int shift, int nbins, int nb, int P, int t) {
-    if (gbase == nullptr) return lower_bound_in(keys, 0, P, t);
-    const int d = t >> shift;
-    if (d >= nbins) return P;
-    const int lo = __ldg(gbase + static_cast<int64_t>(d) * nb);
-    const int hi = d + 1 < nbins ? __ldg(gbase + static_cast<int64_t>(d + 1) * nb) : P;
-    return lower_bound_in(keys, lo, hi, t);
-}
-
-// one thread per tile: its range in the tile-ordered pair list and its pieces (see "Work units" below)
-__global__ void __launch_bounds__(256)
-k_view_tiles(const int32_t *__restrict__ keys, const int32_t *__restrict__ gbase, int shift, int nbins, int nb,
-             int ntiles, int piece, int64_t cap, unsigned int *__restrict__ hdr, int32_t *__restrict__ tcount,
+// one thread per tile: its range in the tile-ordered pair list (a lower bound of its id, searched only inside the run
+// of its last digit, whose bounds are the exclusive scan of the last pass's totals) and its pieces ("Work units")
+__global__ void __launch_bounds__(BIN_THREADS)
+k_view_tiles(const int32_t *__restrict__ keys, const int32_t *__restrict__ tot, int shift, int nbins, int ntiles,
+             int piece, int64_t cap, unsigned int *__restrict__ hdr, int32_t *__restrict__ tcount,
              int32_t *__restrict__ tstart, int32_t *__restrict__ pextra, int32_t *__restrict__ ptile_x,
              int32_t *__restrict__ mlist) {
+    __shared__ int s_dstart[(1 << BIN_MAX_BITS) + 1];
+    __shared__ int s_wsum[BIN_WARPS];
     if (overflowed(hdr, cap)) return;
     const int P = static_cast<int>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]);
+    if (tot != nullptr) scan_bins_256(tot, nbins, s_dstart, s_wsum);
+    auto lower = [&](int t) {
+        if (tot == nullptr) return 0;   // no pairs at all
+        const int d = t >> shift;
+        return d >= nbins ? P : lower_bound_in(keys, s_dstart[d], s_dstart[d + 1], t);
+    };
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int tt = t < ntiles ? t : ntiles;
-    const int lo = tile_lower_bound(keys, gbase, shift, nbins, nb, P, tt);
-    int hi = __shfl_down_sync(0xffffffffu, lo, 1);          // the next tile's lower bound ...
-    if (lane == 31) hi = tile_lower_bound(keys, gbase, shift, nbins, nb, P, tt + 1);   // ... the last lane finds itself
+    const int lo = lower(tt);
+    int hi = __shfl_down_sync(0xffffffffu, lo, 1);   // the next tile's lower bound ...
+    if (lane == 31) hi = lower(tt + 1);              // ... which the last lane has to find itself
     if (t > ntiles) return;
     tstart[t] = lo;
     if (t == ntiles) return;
@@ -1275,7 +1317,6 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
 // their scanned offsets and the scans' descriptors; the slot route's Gaussian, tile and slot of every pair.
 struct BinPlan {
     int passes, bits, nb;        // digit passes, bits per digit, blocks of BIN_CHUNK pairs
-    unsigned nscan;              // blocks of one digit scan
 };
 BinPlan bin_plan(int64_t cap, int ntiles) {
     int total = 1;
@@ -1284,12 +1325,11 @@ BinPlan bin_plan(int64_t cap, int ntiles) {
     b.passes = (total + BIN_MAX_BITS - 1) / BIN_MAX_BITS;   // <= BIN_MAX_PASSES: tiles < 2^30 (bad_image)
     b.bits = (total + b.passes - 1) / b.passes;
     b.nb = static_cast<int>(blocks_for(cap, BIN_CHUNK));
-    b.nscan = blocks_for((int64_t(1) << b.bits) * b.nb, SCAN_TILE);
     return b;
 }
 struct PairLayout {
     size_t pgid, tck, ptile_x, pstate, partial, total;
-    size_t rb[2], rb_hist, rb_base, rb_desc, rb_bstart;   // radix route
+    size_t rb[2], rb_hist, rb_base, rb_tot, rb_bstart;   // the binning's buffers
     int64_t xcap;
 };
 PairLayout pair_layout(int64_t cap, int ntiles) {
@@ -1310,8 +1350,8 @@ PairLayout pair_layout(int64_t cap, int ntiles) {
         auto rtake = [&](size_t bytes) { const size_t at = r; r += align256(bytes); return at; };
         for (int k = 0; k < 2; ++k) L.rb[k] = rtake(static_cast<size_t>(cap + PAIR_PAD) * 8);
         L.rb_hist = rtake(cells * 4);
-        L.rb_base = rtake((cells + 1) * 4);
-        L.rb_desc = rtake(static_cast<size_t>(b.passes) * b.nscan * 8);
+        L.rb_base = rtake(cells * 4);
+        L.rb_tot = rtake(static_cast<size_t>(4) << BIN_MAX_BITS);
         L.rb_bstart = rtake(static_cast<size_t>(b.nb + 1) * 4);
         if (r > o) o = r;
     }
@@ -1354,30 +1394,31 @@ inline const T *at(const void *base, size_t off) {
 
 // one digit pass: the instantiation with just enough ballots for the digit
 template <bool LAST, int BITS>
-void launch_bin_scatter_as(const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *gbase, int shift,
-                           int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
+void launch_bin_scatter_as(const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *rowpre,
+                           const int32_t *tot, int shift, int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_view_bin_scatter<LAST, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             ((BIN_WARPS + 2) << BIN_MAX_BITS) * 4 + BIN_CHUNK * 8);
+                             ((BIN_WARPS + 3) << BIN_MAX_BITS) * 4 + 8 + BIN_CHUNK * 8);
         attr_set = true;
     }
-    k_view_bin_scatter<LAST, BITS><<<bp.nb, BIN_THREADS, smem, st>>>(in, gbase, shift, bp.bits, bp.nb, cap, hdr,
+    k_view_bin_scatter<LAST, BITS><<<bp.nb, BIN_THREADS, smem, st>>>(in, rowpre, tot, shift, bp.bits, bp.nb, cap, hdr,
                                                                      LAST ? nullptr : out,
                                                                      LAST ? reinterpret_cast<int32_t *>(out) : nullptr,
                                                                      LAST ? pgid : nullptr);
 }
 template <bool LAST>
-void launch_bin_scatter_last(const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *gbase,
-                             int shift, int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
-    if (bp.bits <= 7) launch_bin_scatter_as<LAST, 7>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
-    else if (bp.bits == 8) launch_bin_scatter_as<LAST, 8>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
-    else launch_bin_scatter_as<LAST, 9>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+void launch_bin_scatter_last(const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *rowpre,
+                             const int32_t *tot, int shift, int64_t cap, const unsigned int *hdr, int2 *out,
+                             int32_t *pgid) {
+    if (bp.bits <= 7) launch_bin_scatter_as<LAST, 7>(bp, smem, st, in, rowpre, tot, shift, cap, hdr, out, pgid);
+    else if (bp.bits == 8) launch_bin_scatter_as<LAST, 8>(bp, smem, st, in, rowpre, tot, shift, cap, hdr, out, pgid);
+    else launch_bin_scatter_as<LAST, 9>(bp, smem, st, in, rowpre, tot, shift, cap, hdr, out, pgid);
 }
-void launch_bin_scatter(bool last, const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *gbase,
-                        int shift, int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
-    if (last) launch_bin_scatter_last<true>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
-    else launch_bin_scatter_last<false>(bp, smem, st, in, gbase, shift, cap, hdr, out, pgid);
+void launch_bin_scatter(bool last, const BinPlan &bp, size_t smem, cudaStream_t st, const int2 *in, const int32_t *rowpre,
+                        const int32_t *tot, int shift, int64_t cap, const unsigned int *hdr, int2 *out, int32_t *pgid) {
+    if (last) launch_bin_scatter_last<true>(bp, smem, st, in, rowpre, tot, shift, cap, hdr, out, pgid);
+    else launch_bin_scatter_last<false>(bp, smem, st, in, rowpre, tot, shift, cap, hdr, out, pgid);
 }
 
 thread_local int t_view_launches = 0;
@@ -1474,11 +1515,9 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
         // stable radix sort of the pair list by tile: no atomics on tile counters, no sort afterwards
         const BinPlan bp = bin_plan(pair_cap < 16 ? 16 : pair_cap, ntiles);
         const int nbins = 1 << bp.bits;
-        const int64_t cells = static_cast<int64_t>(nbins) * bp.nb;
-        int32_t *hist = at<int32_t>(pairs, B.rb_hist), *gbase = at<int32_t>(pairs, B.rb_base);
-        unsigned long long *desc = at<unsigned long long>(pairs, B.rb_desc);
-        unsigned long long *sink = reinterpret_cast<unsigned long long *>(hdr) + H_B64;
-        const size_t smem = (static_cast<size_t>(BIN_WARPS + 2) * nbins) * 4 + static_cast<size_t>(BIN_CHUNK) * 8;
+        int32_t *hist = at<int32_t>(pairs, B.rb_hist), *rowpre = at<int32_t>(pairs, B.rb_base);
+        int32_t *tot = at<int32_t>(pairs, B.rb_tot);
+        const size_t smem = (static_cast<size_t>(BIN_WARPS + 3) * nbins + 2) * 4 + static_cast<size_t>(BIN_CHUNK) * 8;
         {
             static bool attr_set = false;   // (per process; setting the attribute again costs nothing)
             if (!attr_set) {
@@ -1487,8 +1526,7 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
             }
         }
         k_view_pairs<<<bp.nb, PAIR_THREADS, PW_SMEM, st>>>(at<int2>(plan, A.tbox), at<int32_t>(plan, A.toff), bstart, n, ntx, pair_cap, hdr, bp.bits, bp.nb,
-                                                    at<int2>(pairs, B.rb[0]), hist, desc,
-                                                    static_cast<int>(bp.passes * bp.nscan));
+                                                    at<int2>(pairs, B.rb[0]), hist);
         ++t_view_launches;
         for (int k = 0; k < bp.passes; ++k) {
             const int2 *in = at<int2>(pairs, B.rb[k & 1]);
@@ -1497,21 +1535,19 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
                 k_view_bin_hist<<<bp.nb, BIN_THREADS, 0, st>>>(in, k * bp.bits, bp.bits, bp.nb, pair_cap, hdr, hist);
                 ++t_view_launches;
             }
-            k_view_scan<<<bp.nscan, SCAN_THREADS, 0, st>>>(hist, cells, gbase, hdr + H_TICKET_BIN + k,
-                                                           desc + static_cast<size_t>(k) * bp.nscan, sink, nullptr);
-            launch_bin_scatter(k + 1 == bp.passes, bp, smem, st, in, gbase, k * bp.bits, pair_cap, hdr, out, pgid);
+            k_view_bin_rowscan<<<nbins, BIN_THREADS, 0, st>>>(hist, bp.nb, pair_cap, hdr, rowpre, tot);
+            launch_bin_scatter(k + 1 == bp.passes, bp, smem, st, in, rowpre, tot, k * bp.bits, pair_cap, hdr, out, pgid);
             t_view_launches += 2;
         }
-        k_view_tiles<<<blocks_for(ntiles + 1, 256), 256, 0, st>>>(at<int32_t>(pairs, B.rb[bp.passes & 1]), gbase,
-                                                                  (bp.passes - 1) * bp.bits, nbins, bp.nb, ntiles, g_piece,
-                                                                  pair_cap, hdr, tcount, tstart, pextra, ptile_x,
-                                                                  at<int32_t>(plan, A.mlist));
+        k_view_tiles<<<blocks_for(ntiles + 1, BIN_THREADS), BIN_THREADS, 0, st>>>(
+            at<int32_t>(pairs, B.rb[bp.passes & 1]), tot, (bp.passes - 1) * bp.bits, nbins, ntiles, g_piece, pair_cap, hdr,
+            tcount, tstart, pextra, ptile_x, at<int32_t>(plan, A.mlist));
         ++t_view_launches;
     } else {
         // no Gaussians: every tile's list is empty (P = 0: nothing is read)
-        k_view_tiles<<<blocks_for(ntiles + 1, 256), 256, 0, st>>>(nullptr, nullptr, 0, 1, 1, ntiles, g_piece, pair_cap, hdr,
-                                                                  tcount, tstart, pextra, ptile_x,
-                                                                  at<int32_t>(plan, A.mlist));
+        k_view_tiles<<<blocks_for(ntiles + 1, BIN_THREADS), BIN_THREADS, 0, st>>>(nullptr, nullptr, 0, 1, ntiles, g_piece,
+                                                                                  pair_cap, hdr, tcount, tstart, pextra,
+                                                                                  ptile_x, at<int32_t>(plan, A.mlist));
         ++t_view_launches;
     }
     float *tck = at<float>(pairs, B.tck), *pstate = at<float>(pairs, B.pstate);
