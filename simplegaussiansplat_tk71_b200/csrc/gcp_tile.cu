@@ -36,6 +36,7 @@
 // No library kernels (CUB / thrust) on this route.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <new>
 #include <utility>
@@ -1472,6 +1473,12 @@ void launch_bin_scatter(bool last, const BinPlan &bp, size_t smem, cudaStream_t 
 
 thread_local int t_view_launches = 0;
 
+// experiments only: an integer from the environment
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1819,7 +1826,7 @@ int gcp_views_step_split(gcp_views_ctx *ctx, const gcp_view_desc *views, int n_v
     struct WalkCap {   // restored on every return path
         WalkCap(int v, bool dep) { t_walk_per_sm = v; t_dep_launch = dep; }
         ~WalkCap() { t_walk_per_sm = 0; t_dep_launch = true; }
-    } walk_cap(lanes >= 3 ? 2 : 0, lanes == 1);
+    } walk_cap(env_int("GCP_WALK_PER_SM", lanes >= 3 ? 2 : 0), env_int("GCP_BATCH_PDL", lanes <= 2) != 0);
     for (int v = 0; v < n_views; ++v) {
         const gcp_view_desc &d = views[v];
         const int lane = v % lanes;
