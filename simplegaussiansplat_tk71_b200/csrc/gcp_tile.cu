@@ -87,7 +87,8 @@ struct DepLaunch {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = t_dep_launch ? 1 : 0;
+        static const bool off = getenv("GCP_NO_DEP_LAUNCH") != nullptr;   // per-kernel timings: a kernel's time then
+        cfg.numAttrs = (t_dep_launch && !off) ? 1 : 0;                    // excludes its wait for the one in front
         cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);   // errors: cudaGetLastError
     }
 };
