@@ -305,17 +305,19 @@ __device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap)
 // bit for bit, with no atomic on a tile counter and no sort afterwards.  (Round 2's first binning took a slot per
 // pair from an atomic counter per tile and then sorted every tile's list by Gaussian id: 3.6 M returning atomics cost
 // ~45 us per 1080p view, twice that on the bundled scene whose 8 600 tiles are hit ~500 times each, and the lists of
-// thousands of ids needed block-wide sorts — 126 / 228 us against 102 / 104 us now.)
-//   k_view_pairs        : pair q -> (tile, Gaussian), 16 consecutive pairs per thread (one binary search for the
-//                         owner of the first, then a walk); per-block histogram of the first digit
-//   per digit           : k_view_bin_rowscan over the [digit][block] counts -> where every block's run of every
-//                         digit value starts; k_view_bin_scatter moves the block's 4096 pairs there, ranked inside the
-//                         block in list order (a warp takes 512 consecutive pairs, 32 per round: MATCH.ANY gives the
-//                         lanes holding the same digit, the lowest of them bumps the warp's running counter of that
-//                         digit — no atomics; the warps' counters are then offset in warp order); k_view_bin_hist
-//                         counts the next digit
+// thousands of ids needed block-wide sorts — 126 / 228 us against 90 / 90 us now.)
+//   k_view_pairs        : pair q -> {tile, Gaussian}: a block stages the pair offsets and tile boxes of its Gaussians
+//                         in shared memory, every thread emits 8 consecutive pairs (one binary search for the owner of
+//                         the first, then a walk); per-block counts of the first digit
+//   per digit           : k_view_bin_rowscan scans the [digit value][block] counts along the blocks; k_view_bin_scatter
+//                         sorts the block's 4096 pairs by the digit in shared memory — ranked in list order: a warp takes
+//                         512 consecutive pairs, 32 per round; one ballot per digit bit gives the lanes holding the same
+//                         digit value, the lowest of them bumps the warp's running counter of that value (no atomics);
+//                         the warps' counters are then offset in warp order — and copies them out, every digit value's
+//                         run to its place (block's row-scan value + start of the value's run = scan of the totals);
+//                         k_view_bin_hist counts the next digit
 //   k_view_tiles        : every tile's range in the sorted list (lower bound of its id) and its pieces
-// Digits: ceil(log2(tiles) / passes) bits each, at most 10 (1080p: 2 x 8, 4K: 2 x 9, the largest image: 3 x 9).
+// Digits: ceil(log2(tiles) / passes) bits each, at most 9 (1080p: 2 x 8, 4K: 2 x 9, the largest image: 3 x 9).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BIN_THREADS = 256, BIN_WARPS = BIN_THREADS / 32, BIN_ROUNDS = 16;
 constexpr int BIN_PER_WARP = 32 * BIN_ROUNDS;             // 512 consecutive pairs per warp
@@ -1364,8 +1366,8 @@ PlanLayout plan_layout(int64_t n, int ntiles) {
     return L;
 }
 // pair arena: everything sized by the pair capacity.  What the binning needs (dead once the pair list is built) shares
-// the space of the backward's partials (32 B per pair): the radix route's two (tile, Gaussian) buffers, digit counts,
-// their scanned offsets and the scans' descriptors; the slot route's Gaussian, tile and slot of every pair.
+// the space of the backward's partials (32 B per pair): the two {tile, Gaussian} buffers of the radix passes (8 B per
+// pair each), the [digit value][block] counts and their row scans, the digit totals and the block starts.
 struct BinPlan {
     int passes, bits, nb;        // digit passes, bits per digit, blocks of BIN_CHUNK pairs
 };
