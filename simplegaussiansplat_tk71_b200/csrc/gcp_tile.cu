@@ -99,6 +99,12 @@ constexpr int H_TICKET_BWD = 6, H_NBIG = 7, H_TICKET_RED = 8;   // adjacent u32 
 constexpr int H_P64 = 8;                        // u64 index (byte 64): the pair count of the view
 constexpr int HDR_WORDS = 64;
 
+// A view rendered on a caller-provided pair capacity (gcp_view_forward) may turn out to have more pairs than that:
+// every kernel behind the plan then does nothing, the host sees the count and redoes the view on a larger arena.
+__device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap) {
+    return static_cast<int64_t>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]) > cap;
+}
+
 // box of Gaussian g clipped to the image [0,W] x [0,H] (the caller clamps already, gs_model.py:419-425)
 struct Box {
     int sx, sy, ex, ey;
@@ -147,18 +153,17 @@ __global__ void __launch_bounds__(256)
 k_view_pack(const int32_t *__restrict__ sp, const int32_t *__restrict__ ep, const float *__restrict__ mean,
             const float *__restrict__ lam, const float *__restrict__ opac, const float *__restrict__ l_d, int64_t n,
             int W, int H, const int32_t *__restrict__ toff, int4 *__restrict__ rec, int32_t *__restrict__ bstart,
-            int bcount) {
+            int bcount, const unsigned int *__restrict__ hdr, int64_t cap) {
     grid_dep_sync();
     __shared__ int4 stage[4][257];
     const int64_t g0 = static_cast<int64_t>(blockIdx.x) * 256;
     const int64_t g = g0 + threadIdx.x;
     if (g < n) {
         const Box b = clip_box(sp, ep, g, W, H);
-        if (bstart != nullptr) {
+        if (bstart != nullptr && !overflowed(hdr, cap)) {   // (beyond 2^31 pairs the 32-bit offsets are meaningless)
             // bstart[m] = the Gaussian that owns pair m * 4096: k_view_pairs' block m starts there (saves it a search)
             const int q0 = __ldg(toff + g), q1 = __ldg(toff + g + 1);
-            // (m < bcount: a view with more pairs than the arena holds is not rendered, but must not write outside)
-            for (int m = (q0 + (1 << BIN_CHUNK_SHIFT) - 1) >> BIN_CHUNK_SHIFT; m < bcount && (m << BIN_CHUNK_SHIFT) < q1; ++m)
+            for (int m = (q0 + (1 << BIN_CHUNK_SHIFT) - 1) >> BIN_CHUNK_SHIFT; m < bcount && (static_cast<int64_t>(m) << BIN_CHUNK_SHIFT) < q1; ++m)
                 bstart[m] = static_cast<int32_t>(g);
         }
         auto f = [](float v) { return __float_as_int(v); };
@@ -295,9 +300,6 @@ __global__ void k_view_scan_empty(int32_t *toff, unsigned int *hdr, int64_t *tot
 // ---------------------------------------------------------------------------------------------------------------
 // render: binning
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool overflowed(const unsigned int *hdr, int64_t cap) {
-    return static_cast<int64_t>(reinterpret_cast<const unsigned long long *>(hdr)[H_P64]) > cap;
-}
 // ---------------------------------------------------------------------------------------------------------------
 // The Gaussian-major pair list (pair q of a Gaussian = tile q of its box, row-major) is put in tile order by a STABLE
 // least-significant-digit radix sort on the tile id — stable, so inside a tile the pairs keep the Gaussian (= depth)
@@ -1564,10 +1566,10 @@ int gcp_view_render(const int32_t *sp, const int32_t *ep, const float *mean, con
     if (n > 0) {
         if (((reinterpret_cast<uintptr_t>(mean) & 7) | (reinterpret_cast<uintptr_t>(lam) & 15)) == 0)
             DepLaunch{blocks_for(n, 256), 256, 0, st}(k_view_pack<true>, sp, ep, mean, lam, opac, l_d, n, W, H,
-                                                                  at<int32_t>(plan, A.toff), rec, bstart, bcount);
+                                                                  at<int32_t>(plan, A.toff), rec, bstart, bcount, hdr, pair_cap);
         else
             DepLaunch{blocks_for(n, 256), 256, 0, st}(k_view_pack<false>, sp, ep, mean, lam, opac, l_d, n, W, H,
-                                                                   at<int32_t>(plan, A.toff), rec, bstart, bcount);
+                                                                   at<int32_t>(plan, A.toff), rec, bstart, bcount, hdr, pair_cap);
         ++t_view_launches;
     }
     if (n > 0) {
