@@ -57,7 +57,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed on {src}")
     if relink or any(_mtime(o) > _mtime(LIB_PATH) for o in objs):
-        subprocess.check_call([nvcc, "-shared", "-Xcompiler", "-fopenmp", "-o", LIB_PATH, *objs])
+        subprocess.check_call([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fopenmp", "-o", LIB_PATH,
+                               *objs])
     return LIB_PATH
 
 
