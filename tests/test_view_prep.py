@@ -1,6 +1,5 @@
 """Row a10 (gs_model.py:402-449): per-view culling/clamping and the chunker, on CPU."""
 import os
-import sys
 
 import numpy as np
 import pytest

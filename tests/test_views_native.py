@@ -2,7 +2,6 @@
 scatter-added into the parameters' gradient arrays — in one native call, against the same batch driven view by view
 through the drop-in Function `custom_autograd_grouped_cumprod` (the per-view loop of gs_model.py:402-449 followed by
 what autograd does with the reference's `param[mask]` selections)."""
-import numpy as np
 import pytest
 import torch
 

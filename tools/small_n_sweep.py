@@ -4,7 +4,6 @@ n = 16 Ki ... 64 Mi (C1's segment-length law), with the L2 flushed before every 
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
