@@ -60,3 +60,26 @@ def test_multi_gpu_lines_are_whole_job_aggregates(name, n):
     # (every rank scans its own view: the ranks' element counts differ by a few 1e-4 from rank 0's)
     assert d["value"] == pytest.approx(n * d["config"]["elements_per_gpu"] / (d["ms_per_step"] * 1e-3) / 1e9, rel=2e-3)
     assert 0.9 * n * one["value"] < d["value"] < 1.1 * n * one["value"]       # weak scaling, no data-path collective
+
+
+def test_reference_arm_runs_without_a_gpu_and_prints_one_contract_line():
+    """`bench.py --impl reference` is CPU code (the pure-PyTorch path BASELINE.json names, oracle/torch_cpu_path.py):
+    on the 1 Mi-element workload it finishes in seconds here; non-zero ranks print nothing and exit 0."""
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+           "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    assert r["impl"] == "reference" and r["unit"] == "Gelem/s" and r["value"] > 0 and r["gpu_launches"] == 0
+    assert r["config"]["elements_per_gpu"] == 1 << 20 and r["config"]["segments_per_gpu"] == 1 << 16
+    assert r["e2e"] == {"value": r["value"], "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT,
+                           env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
