@@ -113,3 +113,25 @@ def test_render_views_shapes_and_skip_empty_gpu():
     l = torch.rand(2, n, 3, generator=g)
     imgs = views.render_views(mean.to(dev), half.to(dev), z.to(dev), lam.to(dev), o.to(dev), l.to(dev), W, H)
     assert imgs.shape == (1, 3, H, W) and float(imgs.sum()) > 0
+
+
+def test_compositor_passes_ready_tensors_through_and_converts_the_rest():
+    """Host logic of the compositor's input preparation: tensors that are already fp32 / int32 and contiguous go to the
+    kernels as they are (no copy, no autograd node), everything else is converted; box corners end up 8-byte aligned."""
+    import torch
+
+    from simplegaussiansplat_tk71_b200 import compositor as c
+
+    a = torch.arange(12, dtype=torch.float32).reshape(6, 2).requires_grad_(True)
+    assert c._f32(a, (6, 2)) is a
+    b = c._f32(a.double(), (12,))
+    assert b.dtype == torch.float32 and b.shape == (12,) and not b.requires_grad and b.is_contiguous()
+    t = c._f32(a.detach().t(), (2, 6))                       # not contiguous: copied
+    assert t.is_contiguous() and torch.equal(t, a.detach().t())
+    p = torch.arange(16, dtype=torch.int32).reshape(8, 2)
+    assert c._i32_pairs(p) is p
+    q = c._i32_pairs(p.long())
+    assert q.dtype == torch.int32 and torch.equal(q, p) and q.data_ptr() % 8 == 0
+    odd = torch.arange(17, dtype=torch.int32)[1:].reshape(8, 2)   # 4-byte offset into its storage
+    r = c._i32_pairs(odd)
+    assert r.data_ptr() % 8 == 0 and torch.equal(r, odd)
