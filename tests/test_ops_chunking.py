@@ -143,3 +143,31 @@ def test_max_elements_in_one_call_and_more_than_2_31_chunked_gpu():
         torch.cuda.synchronize()
         assert ops.workspace_status() == 0
     assert len(ops.segment_cuts(key_big)) == 3
+
+
+def test_segment_cuts_property_random_layouts():
+    """Property test (hypothesis): for any segment layout and any limit that the longest segment fits, the cuts start
+    at 0, end at n, increase strictly, fall on segment boundaries, respect the limit, and are greedy (the next segment
+    would not have fitted) — so the number of calls is minimal for cuts at boundaries."""
+    from hypothesis import given, settings, strategies as st
+
+    from simplegaussiansplat_tk71_b200 import ops
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=300), min_size=1, max_size=120), st.integers(0, 1000), st.booleans())
+    def check(lengths, slack, sparse_ids):
+        L = np.asarray(lengths, np.int64)
+        ids = np.repeat(np.arange(len(L), dtype=np.int32) * (3 if sparse_ids else 1), L)   # ids need not be dense
+        limit = int(L.max()) + slack
+        cuts = ops.segment_cuts(torch.from_numpy(ids), limit)
+        n = int(L.sum())
+        ends = np.cumsum(L)
+        assert cuts[0] == 0 and cuts[-1] == n
+        assert all(b > a for a, b in zip(cuts, cuts[1:])) or n == 0
+        starts = np.r_[0, ends[:-1]]
+        for a, b in zip(cuts, cuts[1:]):
+            assert b - a <= limit and b in set(ends.tolist())
+            if b < n:
+                assert b - a + int(L[np.searchsorted(starts, b)]) > limit
+
+    check()
